@@ -1,0 +1,238 @@
+/*
+ * mrt.h — C ABI of libmrt.so, the B200-native volume ray-marcher.
+ *
+ * This is the drop-in boundary for the reference's compute-dispatch seam
+ * (klukaszek/MRI-RayTracer).  Each entry point names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   kernel.dispatch(thread_count=[W,H,1], vars={gOutput, gIntensity0..3, gLabels,
+ *                   gPreds, gParams})            inr/viewer/brats_viewer.py:431-442
+ *     -> mrt_render_forward()                    (shader: inr/viewer/brats_rt.slang:85-168)
+ *   kernel.dispatch(vars={gOutput, gParams, gVolumeU8})
+ *                                                scripts/volumeRendering/app.py:350-358
+ *     -> mrt_render_slab_u8()                    (shader: volume_render.slang:104-148)
+ *   device.create_buffer + Buffer.copy_from_numpy per modality
+ *                                                inr/viewer/brats_viewer.py:182-186,219-230
+ *     -> mrt_pack_volume_f32()  (+ mrt_build_occupancy, which the reference lacks)
+ *   docs/DifferentiableRendering.md:88-127  (maths only, no reference code)
+ *     -> mrt_render_backward()
+ *
+ * Rules of the boundary:
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - the CALLER owns every buffer (inputs, outputs, scratch); the library never
+ *     allocates persistent device memory and never frees caller memory;
+ *   - device entry points are stream-ordered on the `stream` argument
+ *     (a cudaStream_t passed as void*) and never synchronise it;
+ *     only the *_host entry points (host buffers in, host buffers out) synchronise;
+ *   - return 0 on success, a negative MrtStatus on failure; the message is in
+ *     mrt_last_error() (thread-local);
+ *   - re-entrant, no global mutable state apart from the thread-local error string.
+ */
+#ifndef MRT_H_
+#define MRT_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRT_VERSION 100  /* 0.1.0 */
+
+typedef enum MrtStatus {
+  MRT_OK = 0,
+  MRT_ERR_BAD_ARG = -1,
+  MRT_ERR_LAUNCH = -2,
+  MRT_ERR_UNSUPPORTED = -3,
+  MRT_ERR_CUDA = -4
+} MrtStatus;
+
+/* Brick edge (voxels) of the min/max occupancy grid. */
+#define MRT_BRICK 8
+/* Screen-space tile edge (pixels): [numthreads(8,8,1)], brats_rt.slang:86. */
+#define MRT_TILE 8
+/* Largest transfer-function LUT held in shared memory. */
+#define MRT_MAX_TF 1024
+
+/*
+ * MrtParams — the operator's config block.
+ *
+ * The first 368 bytes are byte-for-byte the reference's `struct Params` constant
+ * buffer (inr/viewer/brats_rt.slang:12-31; filled at brats_viewer.py:405-426), so a
+ * host that already builds that block can copy it in unchanged.  The tail holds the
+ * extensions SURVEY.md §8 adds; all-zero tail == reference behaviour.
+ */
+typedef struct MrtParams {
+  uint32_t imageSize[2]; float fovY; float pad0;
+  float eye[3]; float pad1;
+  float U[3]; float pad2;
+  float V[3]; float pad3;
+  float W[3]; float pad4;
+  float volMin[3]; float pad5;
+  float voxelSize[3]; float pad6;
+  uint32_t dims[3]; uint32_t pad7;          /* (X, Y, Z) */
+  float stepSize; float nearT; float farT; float pad8;
+  float bgColor[3]; float pad9;
+  uint32_t volEnabled[4];
+  float volWeight[4];
+  float ww; float wl; float intensityAlpha; float padInt;
+  float gamma; float gradBoost; float gradScale; float padTone;   /* gradBoost/gradScale: declared, never read */
+  uint32_t showSeg; uint32_t showPred; uint32_t padFlags[2];
+  float lutColorAlpha[8][4];
+  /* ---- extensions (offset 368) ---- */
+  uint32_t ortho;           /* 0 pinhole (makePrimary), 1 orthographic */
+  float orthoHalfHeight;    /* world half-height of the ortho window */
+  float ertThreshold;       /* 0 -> 0.01 (brats_rt.slang:117) */
+  uint32_t maxSteps;        /* 0 -> unlimited ([MaxIters(1024)] is a hint) */
+  uint32_t tMode;           /* 0 indexed t_k = t0 + k*dt ; 1 accumulate t += dt (reference, Q4) */
+  uint32_t alphaMode;       /* 0 alpha = 1 (reference :167) ; 1 alpha = 1 - T */
+  uint32_t skipEmpty;       /* 1 use the occupancy brick grid (needs `occupancy` != NULL) */
+  uint32_t tfMode;          /* 0 reference window/level intensity TF (:132-140) ; 1 1D LUT tf[N][4] */
+} MrtParams;
+
+/* Slab renderer params: `struct Params` of scripts/volumeRendering/volume_render.slang:9-21
+ * (std140-like packing of that cbuffer is backend-defined; this is our own plain layout). */
+typedef struct MrtSlabParams {
+  uint32_t imageSize[2]; float fovY; float stepCount;
+  float nearPlane; float farPlane; float pad0[2];
+  float eye[3]; float padEye;
+  float U[3]; float padU;
+  float V[3]; float padV;
+  float W[3]; float padW;
+  uint32_t volDim[3]; uint32_t padDim;
+} MrtSlabParams;
+
+/* -------------------------------------------------------------------- misc */
+int mrt_version(void);
+const char* mrt_last_error(void);
+/* sizeof(MrtParams) as compiled into the library (ABI self-check for bindings). */
+size_t mrt_sizeof_params(void);
+size_t mrt_sizeof_slab_params(void);
+
+/* ------------------------------------------------ integer tile map (host)
+ * The bit-exact integer contract of the dispatch geometry
+ * (`numthreads(8,8,1)`, `thread_count=[W,H,1]`, brats_rt.slang:86-89;
+ * brats_viewer.py:431-432): pixel (x,y) -> tile (x>>3, y>>3), tile id
+ * ty*ceil(W/8)+tx, lane (y&7)*8+(x&7), linear pixel y*W+x. */
+int32_t mrt_tiles_x(int32_t W);
+int32_t mrt_tiles_y(int32_t H);
+int32_t mrt_tile_count(int32_t W, int32_t H);
+int32_t mrt_tile_of_pixel(int32_t x, int32_t y, int32_t W);
+int32_t mrt_lane_of_pixel(int32_t x, int32_t y);
+/* Contiguous tile range of `rank` out of `nranks`: [floor(r*T/R), floor((r+1)*T/R)). */
+void mrt_rank_tile_range(int32_t ntiles, int32_t rank, int32_t nranks, int32_t* begin, int32_t* end);
+/* Same map evaluated on the device for every pixel (bit-exactness check of the kernels'
+ * own indexing): out_tile[y*W+x], out_lane[y*W+x]. Device pointers. */
+int mrt_tile_index_map(int32_t W, int32_t H, int32_t* out_tile, int32_t* out_lane, void* stream);
+
+/* ------------------------------------------------ volume layout
+ * Planar [C][Z][Y][X] fp32 (the reference's one-buffer-per-modality flatten,
+ * brats_viewer.py:64) -> the packed layout the sampler reads:
+ *   C == 1 : [Z][Y][X] float        (packed may alias planar; the call is then a no-op)
+ *   C == 2 : [Z][Y][X] float2
+ *   C == 3,4 : [Z][Y][X] float4     (missing channel = 0)
+ * One LDG.128 per trilinear corner fetches all modalities. */
+size_t mrt_packed_volume_bytes(int32_t C, int32_t X, int32_t Y, int32_t Z);
+int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, int32_t Z,
+                        void* packed, void* stream);
+/* Inverse (used for dL/dvolume): packed -> planar [C][Z][Y][X]. */
+int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z,
+                          float* planar, void* stream);
+
+/* ------------------------------------------------ occupancy brick grid
+ * (new relative to the reference; must never change the image.)
+ * Grid of ceil(dim/8)^3 bricks; brick b holds per-channel (min,max) over voxels
+ * [8b, 8b+8] (inclusive: the whole trilinear/nearest footprint of any sample whose
+ * base index lies in the brick).  minmax: float2[nbricks][Cp] with Cp = packed channel
+ * count (1,2,4).  label_any: optional uint8[nbricks], 1 if any label in 1..7. */
+int32_t mrt_brick_count(int32_t X, int32_t Y, int32_t Z);
+int mrt_build_occupancy(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z,
+                        float* minmax, void* stream);
+int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32_t Z,
+                              uint8_t* label_any, void* stream);
+/* Per-frame classification: bit b of `active_bits` (uint32 words, ceil(nbricks/32)) is 0
+ * only if every sample in brick b is provably a no-op under (params, tf, labels). */
+int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C,
+                        const float* tf, int32_t tfN,
+                        const uint8_t* seg_any, const uint8_t* pred_any,
+                        uint32_t* active_bits, void* stream);
+
+/* ------------------------------------------------ forward
+ * Renders tiles [tile_begin, tile_end) of the [H][W] image (tile ids as above).
+ *   packed      : packed volume (see mrt_pack_volume_f32), C = logical channel count (1..4)
+ *   tf, tfN     : LUT [tfN][4] (r,g,b,sigma) fp32, used when params->tfMode == 1
+ *   active_bits : from mrt_classify_bricks, or NULL (then skipEmpty is ignored)
+ *   labels/preds: optional int32 [Z][Y][X] (gLabels / gPreds), used when showSeg / showPred
+ *   out_rgba    : float4 [H][W]  (row 0 = top)
+ *   out_T       : optional float [H][W], final transmittance
+ *   out_counts  : optional int32 [H][W][4] = (n_clip, n_taken, n_evaluated, n_segments)
+ */
+int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C,
+                       const float* tf, int32_t tfN, const uint32_t* active_bits,
+                       const int32_t* labels, const int32_t* preds,
+                       float* out_rgba, float* out_T, int32_t* out_counts,
+                       int32_t tile_begin, int32_t tile_end, void* stream);
+
+/* ------------------------------------------------ backward
+ * Adjoint of mrt_render_forward w.r.t. the volume and the transfer function
+ * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray.
+ *   out_rgba   : the forward's output (needed for the suffix sums)
+ *   dL_dout    : float4 [H][W]
+ *   dL_dvol    : packed layout, same shape as `packed`, ACCUMULATED into (caller zeroes)
+ *   dL_dtf     : float [tfN][4] (tfMode 1) or float[2][4] (tfMode 0: entry [1][3] is
+ *                dL/d intensityAlpha), ACCUMULATED into (caller zeroes)
+ */
+int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C,
+                        const float* tf, int32_t tfN,
+                        const int32_t* labels, const int32_t* preds,
+                        const float* out_rgba, const float* dL_dout,
+                        void* dL_dvol, float* dL_dtf,
+                        int32_t tile_begin, int32_t tile_end, void* stream);
+
+/* ------------------------------------------------ slab renderer (u8 volume)
+ * volume_cs, scripts/volumeRendering/volume_render.slang:104-148.
+ * vol_u8: uint8 [Z][Y][X], one byte per voxel (the reference stores one voxel per u32
+ * lane, app.py:150-158; values are identical). */
+int mrt_render_slab_u8(const MrtSlabParams* params, const uint8_t* vol_u8,
+                       float* out_rgba, int32_t tile_begin, int32_t tile_end, void* stream);
+
+/* ------------------------------------------------ ingest formats
+ * BC4 (single-channel block compression) decode, scripts/volumeRendering/app.py:200-250:
+ * blocks: uint8 [D][ceil(H/4)*ceil(W/4)][8]  ->  out: uint8 [D][H][W]. */
+int mrt_decode_bc4(const uint8_t* blocks, int32_t W, int32_t H, int32_t D, uint8_t* out, void* stream);
+/* u8 -> fp32 /255 (volume_render.slang:38). */
+int mrt_u8_to_f32(const uint8_t* in, size_t n, float* out, void* stream);
+/* Affine normalise + clip to [0,1]: out = clip((in - vmin)/rng, 0, 1)
+ * (inr/viewer/brats_viewer.py:50-56; percentiles are computed by the host). */
+int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* out, void* stream);
+
+/* ------------------------------------------------ sort-last compositing
+ * Ordered front-to-back `over` of K partial images (premultiplied colour + transmittance):
+ *   (C,T) <- (C_a + T_a*C_b, T_a*T_b), front first; bg added once at the end, like the
+ *   reference's `C = bgColor` start (brats_rt.slang:111): out = (bg + C, alpha).
+ * partials: float4 [K][npix] = (r,g,b,T); order: int32[K] front-to-back indices. */
+int mrt_composite_over(const float* partials, int32_t K, const int32_t* order, size_t npix,
+                       const float* bg3, int32_t alphaMode, float* out_rgba, void* stream);
+
+/* ------------------------------------------------ roofline probe
+ * Random 32-byte-sector gather over a buffer of `bytes` (power of two), `n_gathers`
+ * sectors per launch; writes a checksum so the loads cannot be elided.  Used by bench.py
+ * to measure the L2-resident and HBM-resident gather ceilings. */
+int mrt_gather_probe(const void* buf, size_t bytes, size_t n_gathers, uint32_t seed,
+                     float* out_checksum, void* stream);
+
+/* ------------------------------------------------ host-buffer entry point
+ * The call a non-CUDA host makes: host volume in, host image out.  Allocates and frees
+ * its own temporary device memory, copies H2D, packs, builds + classifies occupancy,
+ * renders, copies D2H, and synchronises.  planar_host: [C][Z][Y][X] fp32; out_rgba_host:
+ * float4 [H][W].  labels/preds may be NULL. */
+int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C,
+                    const float* tf_host, int32_t tfN,
+                    const int32_t* labels_host, const int32_t* preds_host,
+                    float* out_rgba_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRT_H_ */

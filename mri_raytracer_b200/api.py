@@ -1,0 +1,329 @@
+"""Public Python API: volume tensor + camera + transfer function in, RGBA image out.
+
+This is the host-side mirror of the reference's dispatch seam
+(``kernel.dispatch(thread_count=[W,H,1], vars={gOutput, gIntensity0..3, gLabels, gPreds,
+gParams})``, inr/viewer/brats_viewer.py:431-442) and of the functional form its authors
+planned (``module.render(pixel=..., volume=..., params=..., _result=out)``,
+docs/Methodology-ROI-Neural-Volumetric-Rendering.md:88-96).  PyTorch only supplies device
+memory, streams and autograd plumbing; every kernel is in libmrt.so (include/mrt.h).
+There is no CPU fallback: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import replace
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .camera import Camera
+from .params import RenderParams, SlabParams
+from . import tiles as _tiles
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the render path has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def packed_channels(Cn: int) -> int:
+    return 1 if Cn <= 1 else (2 if Cn == 2 else 4)
+
+
+# ----------------------------------------------------------------------------- low level
+def pack_volume(planar: torch.Tensor) -> torch.Tensor:
+    """[C,Z,Y,X] fp32 -> packed [Z,Y,X,Cp] (Cp = 1,2,4).  C == 1 aliases the input."""
+    _need_cuda(planar, "volume", torch.float32)
+    Cn, Z, Y, X = planar.shape
+    pc = packed_channels(Cn)
+    if pc == 1:
+        return planar.reshape(Z, Y, X, 1)
+    packed = torch.empty((Z, Y, X, pc), dtype=torch.float32, device=planar.device)
+    check(lib().mrt_pack_volume_f32(planar.data_ptr(), Cn, X, Y, Z, packed.data_ptr(), _stream()), "pack_volume")
+    return packed
+
+
+def unpack_volume(packed: torch.Tensor, Cn: int) -> torch.Tensor:
+    Z, Y, X, pc = packed.shape
+    if pc == 1:
+        return packed.reshape(1, Z, Y, X)
+    planar = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=packed.device)
+    check(lib().mrt_unpack_volume_f32(packed.data_ptr(), Cn, X, Y, Z, planar.data_ptr(), _stream()), "unpack_volume")
+    return planar
+
+
+def build_occupancy(packed: torch.Tensor, Cn: int) -> torch.Tensor:
+    """Per-brick (min,max) per packed channel: float32 [nbricks, Cp, 2]."""
+    Z, Y, X, pc = packed.shape
+    nb = lib().mrt_brick_count(X, Y, Z)
+    mm = torch.empty((nb, pc, 2), dtype=torch.float32, device=packed.device)
+    check(lib().mrt_build_occupancy(packed.data_ptr(), Cn, X, Y, Z, mm.data_ptr(), _stream()), "build_occupancy")
+    return mm
+
+
+def build_label_occupancy(labels: torch.Tensor) -> torch.Tensor:
+    _need_cuda(labels, "labels", torch.int32)
+    Z, Y, X = labels.shape
+    nb = lib().mrt_brick_count(X, Y, Z)
+    out = torch.empty((nb,), dtype=torch.uint8, device=labels.device)
+    check(lib().mrt_build_label_occupancy(labels.data_ptr(), X, Y, Z, out.data_ptr(), _stream()),
+          "build_label_occupancy")
+    return out
+
+
+def classify_bricks(P: RenderParams, minmax: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
+                    seg_any: Optional[torch.Tensor] = None, pred_any: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nb = minmax.shape[0]
+    if out is None:
+        out = torch.empty(((nb + 31) // 32,), dtype=torch.int32, device=minmax.device)
+    s = P.to_struct()
+    check(lib().mrt_classify_bricks(C.byref(s), minmax.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                    _ptr(seg_any), _ptr(pred_any), out.data_ptr(), _stream()), "classify_bricks")
+    return out
+
+
+def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor] = None,
+                   active_bits: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                   preds: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   out_T: Optional[torch.Tensor] = None, out_counts: Optional[torch.Tensor] = None,
+                   tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Thin wrapper over ``mrt_render_forward`` (no allocation beyond the output image)."""
+    W, H = P.imageSize
+    if out is None:
+        out = torch.empty((H, W, 4), dtype=torch.float32, device=packed.device)
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    s = P.to_struct()
+    check(lib().mrt_render_forward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                   _ptr(active_bits), _ptr(labels), _ptr(preds), out.data_ptr(), _ptr(out_T),
+                                   _ptr(out_counts), t0, t1, _stream()), "render_forward")
+    return out
+
+
+def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
+                    labels: Optional[torch.Tensor], preds: Optional[torch.Tensor], out_rgba: torch.Tensor,
+                    dL_dout: torch.Tensor, want_dvol: bool = True, want_dtf: bool = True,
+                    tile_range: Optional[Tuple[int, int]] = None):
+    """-> (dL/dvolume packed or None, dL/dtf [N,4] or None)."""
+    W, H = P.imageSize
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    dvol = torch.zeros_like(packed) if want_dvol else None
+    ntf = tf.shape[0] if (tf is not None and P.tfMode) else 2
+    dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_dtf else None
+    s = P.to_struct()
+    check(lib().mrt_render_backward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                    _ptr(labels), _ptr(preds), out_rgba.data_ptr(), dL_dout.data_ptr(),
+                                    _ptr(dvol), _ptr(dtf), t0, t1, _stream()), "render_backward")
+    return dvol, dtf
+
+
+# ----------------------------------------------------------------------------- Volume
+class Volume:
+    """A device-resident volume prepared for rendering: packed layout, occupancy brick grid,
+    optional label volumes, and the reference's world scaling
+    (inr/viewer/brats_viewer.py:204-210: voxelSize = zooms*1.8/max_dim, volMin = -extent/2)."""
+
+    def __init__(self, planar: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                 preds: Optional[torch.Tensor] = None, zooms=(1.0, 1.0, 1.0), occupancy: bool = True):
+        _need_cuda(planar, "volume", torch.float32)
+        if planar.dim() != 4 or not (1 <= planar.shape[0] <= 4):
+            raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(planar.shape)}")
+        self.C = int(planar.shape[0])
+        Z, Y, X = (int(v) for v in planar.shape[1:])
+        self.dims = (X, Y, Z)
+        self.packed = pack_volume(planar)
+        self.minmax = build_occupancy(self.packed, self.C) if occupancy else None
+        self.labels = self.preds = self.seg_any = self.pred_any = None
+        self.set_labels(labels)
+        self.set_preds(preds)
+        from .synth import world_box
+        self.voxel_size, self.vol_min = world_box(self.dims, zooms)
+        self._bits = None
+
+    def set_labels(self, labels: Optional[torch.Tensor]):
+        """gLabels (inr/viewer/brats_viewer.py:233-237)."""
+        self.labels = self._check_labels(labels)
+        self.seg_any = build_label_occupancy(self.labels) if (self.labels is not None and self.minmax is not None) else None
+
+    def set_preds(self, preds: Optional[torch.Tensor]):
+        """gPreds (inr/viewer/brats_viewer.py:293-299)."""
+        self.preds = self._check_labels(preds)
+        self.pred_any = build_label_occupancy(self.preds) if (self.preds is not None and self.minmax is not None) else None
+
+    def _check_labels(self, lab):
+        if lab is None:
+            return None
+        _need_cuda(lab, "labels", torch.int32)
+        X, Y, Z = self.dims
+        if tuple(lab.shape) != (Z, Y, X):
+            raise ValueError(f"labels must be [Z,Y,X]={Z, Y, X}, got {tuple(lab.shape)}")
+        return lab
+
+    def frame_params(self, P: RenderParams) -> RenderParams:
+        """Fill dims / voxelSize / volMin from the volume."""
+        return replace(P, dims=self.dims, voxelSize=tuple(float(v) for v in self.voxel_size),
+                       volMin=tuple(float(v) for v in self.vol_min))
+
+    def frame_camera(self, cam):
+        """``frame_volume`` (inr/viewer/brats_viewer.py:320-324): target = centre, radius = 0.8*|extent|."""
+        ext = self.voxel_size * np.asarray(self.dims, dtype=np.float32)
+        cam.target = (self.vol_min + 0.5 * ext).astype(np.float32)
+        cam.radius = float(np.linalg.norm(ext) * 0.8)
+        return cam
+
+    def active_bits(self, P: RenderParams, tf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
+            return None
+        nb = self.minmax.shape[0]
+        if self._bits is None:
+            self._bits = torch.empty(((nb + 31) // 32,), dtype=torch.int32, device=self.packed.device)
+        return classify_bricks(P, self.minmax, self.C, tf, self.seg_any, self.pred_any, out=self._bits)
+
+
+# ----------------------------------------------------------------------------- autograd
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planar, tf, P: RenderParams, labels, preds):
+        Cn = planar.shape[0]
+        packed = pack_volume(planar.detach())
+        bits = None
+        if P.skipEmpty and P.tMode == "indexed":
+            mm = build_occupancy(packed, Cn)
+            seg_any = build_label_occupancy(labels) if (labels is not None and P.showSeg) else None
+            pred_any = build_label_occupancy(preds) if (preds is not None and P.showPred) else None
+            bits = classify_bricks(P, mm, Cn, tf, seg_any, pred_any)
+        out = render_forward(P, packed, Cn, tf, bits, labels, preds)
+        ctx.P, ctx.Cn = P, Cn
+        ctx.labels, ctx.preds = labels, preds
+        ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=planar.device), out)
+        ctx.has_tf = tf is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        packed, tf, out = ctx.saved_tensors
+        tf = tf if ctx.has_tf else None
+        want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
+        dvol, dtf = render_backward(ctx.P, packed, ctx.Cn, tf, ctx.labels, ctx.preds, out,
+                                    g.contiguous(), want_dvol=want_vol, want_dtf=want_tf)
+        gvol = unpack_volume(dvol, ctx.Cn) if want_vol else None
+        return gvol, (dtf if want_tf else None), None, None, None
+
+
+def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Optional[torch.Tensor],
+           params: RenderParams, labels: Optional[torch.Tensor] = None,
+           preds: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Render one frame: -> float32 ``[H, W, 4]`` (row 0 = top of the image).
+
+    volume : ``[C,Z,Y,X]`` CUDA fp32 tensor (differentiable) or a prepared :class:`Volume`.
+    camera : :class:`camera.Camera` (eye/U/V/W/fov/ortho); ``None`` keeps the ones in ``params``.
+    tf     : ``[N,4]`` fp32 (r,g,b,sigma) 1D LUT, or ``None`` for the reference's window/level
+             intensity transfer function (brats_rt.slang:132-140).
+    params : :class:`RenderParams` (the reference's ``struct Params`` + extensions).
+    labels, preds : optional int32 ``[Z,Y,X]`` overlays (gLabels / gPreds).
+    Differentiable w.r.t. ``volume`` and ``tf`` when ``volume`` is a tensor.
+    """
+    P = params if camera is None else params.with_camera(camera)
+    if tf is not None:
+        _need_cuda(tf, "tf", torch.float32)
+        if tf.dim() != 2 or tf.shape[1] != 4 or not (2 <= tf.shape[0] <= _lib.MRT_MAX_TF):
+            raise ValueError(f"tf must be [N,4] with 2 <= N <= {_lib.MRT_MAX_TF}, got {tuple(tf.shape)}")
+    P = replace(P, tfMode=1 if tf is not None else 0)
+    if isinstance(volume, Volume):
+        V = volume
+        if tuple(P.dims) != tuple(V.dims):
+            raise ValueError(f"params.dims {P.dims} != volume dims {V.dims}")
+        lab = labels if labels is not None else V.labels
+        prd = preds if preds is not None else V.preds
+        bits = V.active_bits(P, tf)
+        return render_forward(P, V.packed, V.C, tf, bits, lab, prd)
+    _need_cuda(volume, "volume", torch.float32)
+    if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
+        raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(volume.shape)}")
+    Z, Y, X = (int(v) for v in volume.shape[1:])
+    if tuple(P.dims) != (X, Y, Z):
+        raise ValueError(f"params.dims {P.dims} != volume dims {(X, Y, Z)}")
+    for name, lab in (("labels", labels), ("preds", preds)):
+        if lab is not None:
+            _need_cuda(lab, name, torch.int32)
+            if tuple(lab.shape) != (Z, Y, X):
+                raise ValueError(f"{name} must be [Z,Y,X]")
+    return _RenderFn.apply(volume, tf, P, labels, preds)
+
+
+def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams):
+    """Like :func:`render` on a prepared Volume, additionally returning the final transmittance
+    ``T [H,W]`` and per-ray counters ``[H,W,4]`` = (n_clip, n_taken, n_evaluated, n_segments)."""
+    P = params if camera is None else params.with_camera(camera)
+    P = replace(P, tfMode=1 if tf is not None else 0)
+    W, H = P.imageSize
+    dev = volume.packed.device
+    out_T = torch.empty((H, W), dtype=torch.float32, device=dev)
+    counts = torch.zeros((H, W, 4), dtype=torch.int32, device=dev)
+    bits = volume.active_bits(P, tf)
+    img = render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds,
+                         out_T=out_T, out_counts=counts)
+    return img, out_T, counts
+
+
+def render_slab(vol_u8: torch.Tensor, camera: Optional[Camera], params: SlabParams,
+                tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """The single-volume slab renderer (``volume_cs``, volume_render.slang:104-148) over a
+    uint8 ``[Z,Y,X]`` CUDA volume -> float32 ``[H,W,4]``."""
+    _need_cuda(vol_u8, "vol_u8", torch.uint8)
+    P = params if camera is None else params.with_camera(camera)
+    Z, Y, X = (int(v) for v in vol_u8.shape)
+    if tuple(P.volDim) != (X, Y, Z):
+        raise ValueError(f"params.volDim {P.volDim} != volume dims {(X, Y, Z)}")
+    W, H = P.imageSize
+    out = torch.empty((H, W, 4), dtype=torch.float32, device=vol_u8.device)
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    s = P.to_struct()
+    check(lib().mrt_render_slab_u8(C.byref(s), vol_u8.data_ptr(), out.data_ptr(), t0, t1, _stream()), "render_slab")
+    return out
+
+
+def render_host(volume: np.ndarray, params: RenderParams, tf: Optional[np.ndarray] = None,
+                labels: Optional[np.ndarray] = None, preds: Optional[np.ndarray] = None,
+                out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Host buffers in, host image out (``mrt_render_host``): the call a non-CUDA host makes.
+    Copies H2D, packs, builds the occupancy grid, renders, copies D2H, synchronises."""
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    Cn, Z, Y, X = vol.shape
+    P = replace(params, tfMode=1 if tf is not None else 0, dims=(X, Y, Z))
+    W, H = P.imageSize
+    if out is None:
+        out = np.empty((H, W, 4), dtype=np.float32)
+    tfa = None if tf is None else np.ascontiguousarray(tf, dtype=np.float32)
+    la = None if labels is None else np.ascontiguousarray(labels, dtype=np.int32)
+    pa = None if preds is None else np.ascontiguousarray(preds, dtype=np.int32)
+    hp = lambda a: None if a is None else a.ctypes.data
+    s = P.to_struct()
+    check(lib().mrt_render_host(C.byref(s), hp(vol), Cn, hp(tfa), 0 if tfa is None else tfa.shape[0],
+                                hp(la), hp(pa), hp(out)), "render_host")
+    return out
+
+
+def tile_index_map(W: int, H: int, device="cuda"):
+    """Device evaluation of the integer tile map (bit-exactness check): (tile[H,W], lane[H,W])."""
+    t = torch.full((H, W), -1, dtype=torch.int32, device=device)
+    l = torch.full((H, W), -1, dtype=torch.int32, device=device)
+    check(lib().mrt_tile_index_map(W, H, t.data_ptr(), l.data_ptr(), _stream()), "tile_index_map")
+    return t, l

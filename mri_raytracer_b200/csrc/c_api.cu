@@ -1,0 +1,317 @@
+// c_api.cu — the extern "C" boundary declared in include/mrt.h.
+//
+// Validates arguments, derives the kernel constant block (KParams) from the reference's
+// `struct Params` layout (MrtParams), launches on the caller's stream, and reports errors
+// through a thread-local string.  No allocation, no synchronisation (except *_host).
+#include "march.cuh"
+#include "kernels.h"
+#include "../../include/mrt.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MRT_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+}
+#define MRT_REQUIRE(cond, ...) do { if (!(cond)) return fail(MRT_ERR_BAD_ARG, __VA_ARGS__); } while (0)
+
+extern "C" {
+
+int mrt_version(void) { return MRT_VERSION; }
+const char* mrt_last_error(void) { return g_err; }
+size_t mrt_sizeof_params(void) { return sizeof(MrtParams); }
+size_t mrt_sizeof_slab_params(void) { return sizeof(MrtSlabParams); }
+
+// ---------------------------------------------------------------- tiles (host)
+int32_t mrt_tiles_x(int32_t W) { return mrt_tiles_x_(W); }
+int32_t mrt_tiles_y(int32_t H) { return mrt_tiles_y_(H); }
+int32_t mrt_tile_count(int32_t W, int32_t H) { return mrt_tiles_x_(W) * mrt_tiles_y_(H); }
+int32_t mrt_tile_of_pixel(int32_t x, int32_t y, int32_t W) { return mrt_tile_of_pixel_(x, y, W); }
+int32_t mrt_lane_of_pixel(int32_t x, int32_t y) { return mrt_lane_of_pixel_(x, y); }
+void mrt_rank_tile_range(int32_t ntiles, int32_t rank, int32_t nranks, int32_t* begin, int32_t* end) {
+  *begin = mrt_rank_tile_begin_(ntiles, rank, nranks);
+  *end = mrt_rank_tile_begin_(ntiles, rank + 1, nranks);
+}
+int mrt_tile_index_map(int32_t W, int32_t H, int32_t* out_tile, int32_t* out_lane, void* stream) {
+  MRT_REQUIRE(W > 0 && H > 0 && out_tile && out_lane, "tile_index_map: bad arguments");
+  cudaError_t e = mrt_launch_tile_map(W, H, out_tile, out_lane, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "tile_index_map");
+}
+
+// ---------------------------------------------------------------- layout
+size_t mrt_packed_volume_bytes(int32_t C, int32_t X, int32_t Y, int32_t Z) {
+  if (C < 1 || C > 4 || X < 1 || Y < 1 || Z < 1) return 0;
+  return (size_t)X * Y * Z * sizeof(float) * mrt_packed_channels(C);
+}
+static int check_dims(const char* who, int C, int X, int Y, int Z) {
+  MRT_REQUIRE(C >= 1 && C <= 4, "%s: C=%d outside 1..4", who, C);
+  // dims-1.001 clamp (brats_rt.slang:62) needs >= 2 voxels per axis
+  MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
+  MRT_REQUIRE((uint64_t)X * Y * Z < (1ull << 32), "%s: more than 2^32 voxels per shard (SURVEY Q14)", who);
+  return MRT_OK;
+}
+int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream) {
+  MRT_REQUIRE(planar && packed, "pack_volume: null pointer");
+  if (int r = check_dims("pack_volume", C, X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_pack(planar, C, X, Y, Z, packed, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume");
+}
+int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z, float* planar, void* stream) {
+  MRT_REQUIRE(planar && packed, "unpack_volume: null pointer");
+  if (int r = check_dims("unpack_volume", C, X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_unpack(packed, C, X, Y, Z, planar, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "unpack_volume");
+}
+
+// ---------------------------------------------------------------- params
+static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_begin, int tile_end, KParams* K) {
+  MRT_REQUIRE(M != nullptr, "params is null");
+  memset(K, 0, sizeof(*K));
+  K->W = (int)M->imageSize[0]; K->H = (int)M->imageSize[1];
+  MRT_REQUIRE(K->W > 0 && K->H > 0 && K->W <= 65536 && K->H <= 65536, "imageSize (%d,%d) invalid", K->W, K->H);
+  for (int i = 0; i < 3; ++i) {
+    K->eye[i] = M->eye[i]; K->U[i] = M->U[i]; K->V[i] = M->V[i]; K->Wv[i] = M->W[i];
+    K->bmin[i] = M->volMin[i]; K->vs[i] = M->voxelSize[i]; K->dims[i] = (int)M->dims[i];
+    K->bg[i] = M->bgColor[i];
+    MRT_REQUIRE(M->voxelSize[i] > 0.0f, "voxelSize[%d] must be > 0", i);
+  }
+  if (int r = check_dims("render", C, K->dims[0], K->dims[1], K->dims[2])) return r;
+  // tan evaluated once in double, rounded to float (documented deviation from the per-thread fp32 tan)
+  K->ortho = M->ortho ? 1 : 0;
+  K->halfH = M->orthoHalfHeight;
+  if (!K->ortho) {
+    MRT_REQUIRE(M->fovY > 0.0f && M->fovY < 3.14159f, "fovY %g outside (0, pi)", (double)M->fovY);
+    K->focal = (float)(1.0 / tan(0.5 * (double)M->fovY));
+  } else {
+    MRT_REQUIRE(M->orthoHalfHeight > 0.0f, "orthoHalfHeight must be > 0");
+    K->focal = 1.0f;
+  }
+  MRT_REQUIRE(M->stepSize > 0.0f, "stepSize must be > 0");
+  K->dt = M->stepSize; K->nearT = M->nearT; K->farT = M->farT;
+  MRT_REQUIRE(M->ww > 0.0f, "ww must be > 0 (SURVEY Q10)");
+  float wsum = 0.0f;
+  for (int c = 0; c < 4; ++c) {
+    const bool en = (c < C) && (M->volEnabled[c] != 0);
+    K->wgt[c] = en ? M->volWeight[c] : 0.0f;
+    if (en) wsum += M->volWeight[c];                       // brats_rt.slang:125-128
+  }
+  K->inv_wsum = (wsum > 0.0f) ? 1.0f / wsum : 1.0f;        // :130
+  K->lo = M->wl - M->ww * 0.5f;                            // :132
+  K->inv_ww = 1.0f / M->ww;
+  K->ia = M->intensityAlpha;
+  K->gamma = M->gamma;
+  K->showSeg = M->showSeg ? 1 : 0; K->showPred = M->showPred ? 1 : 0;
+  memcpy(K->lut, M->lutColorAlpha, sizeof(K->lut));
+  K->thr = (M->ertThreshold != 0.0f) ? M->ertThreshold : 0.01f;   // :117
+  K->maxSteps = (int)M->maxSteps;
+  MRT_REQUIRE(M->tMode <= 1, "tMode %u unknown", M->tMode);
+  K->tMode = (int)M->tMode; K->alphaMode = M->alphaMode ? 1 : 0;
+  K->tfMode = M->tfMode ? 1 : 0;
+  K->tfN = K->tfMode ? tfN : 0;
+  if (K->tfMode) MRT_REQUIRE(tfN >= 2 && tfN <= MRT_MAX_TF, "tfN=%d outside 2..%d", tfN, MRT_MAX_TF);
+  K->skip = (M->skipEmpty && have_bits && K->tMode == 0) ? 1 : 0;
+  K->nbx = (K->dims[0] + 7) >> 3; K->nby = (K->dims[1] + 7) >> 3; K->nbz = (K->dims[2] + 7) >> 3;
+  const int nt = mrt_tiles_x_(K->W) * mrt_tiles_y_(K->H);
+  MRT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt,
+              "tile range [%d,%d) outside [0,%d]", tile_begin, tile_end, nt);
+  K->tile_begin = tile_begin; K->tile_end = tile_end;
+  return MRT_OK;
+}
+
+// ---------------------------------------------------------------- occupancy
+int32_t mrt_brick_count(int32_t X, int32_t Y, int32_t Z) {
+  if (X < 1 || Y < 1 || Z < 1) return 0;
+  return ((X + 7) >> 3) * ((Y + 7) >> 3) * ((Z + 7) >> 3);
+}
+int mrt_build_occupancy(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream) {
+  MRT_REQUIRE(packed && minmax, "build_occupancy: null pointer");
+  if (int r = check_dims("build_occupancy", C, X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_build_occupancy(packed, mrt_packed_channels(C), X, Y, Z, minmax, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_occupancy");
+}
+int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32_t Z, uint8_t* any, void* stream) {
+  MRT_REQUIRE(labels && any, "build_label_occupancy: null pointer");
+  if (int r = check_dims("build_label_occupancy", 1, X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_label_occupancy(labels, X, Y, Z, any, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_label_occupancy");
+}
+int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C, const float* tf, int32_t tfN,
+                        const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* active_bits, void* stream) {
+  MRT_REQUIRE(minmax && active_bits, "classify_bricks: null pointer");
+  KParams K;
+  if (int r = derive(params, C, tfN, true, 0, 0, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "classify_bricks: tfMode=1 needs tf");
+  cudaError_t e = mrt_launch_classify(K, minmax, mrt_packed_channels(C), tf, seg_any, pred_any, active_bits,
+                                      (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "classify_bricks");
+}
+
+// ---------------------------------------------------------------- forward / backward
+int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                       const uint32_t* active_bits, const int32_t* labels, const int32_t* preds,
+                       float* out_rgba, float* out_T, int32_t* out_counts,
+                       int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba, "render_forward: null volume or output");
+  KParams K;
+  if (int r = derive(params, C, tfN, active_bits != nullptr, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward: tfMode=1 needs tf");
+  if (K.showSeg && !labels) K.showSeg = 0;                  // brats_viewer.py:423 (showSeg only with a buffer)
+  if (K.showPred && !preds) K.showPred = 0;                 // brats_viewer.py:424
+  cudaError_t e = mrt_launch_forward(K, mrt_packed_channels(C), packed, tf, active_bits, labels, preds,
+                                     out_rgba, out_T, out_counts, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
+}
+
+int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                        const int32_t* labels, const int32_t* preds, const float* out_rgba, const float* dL_dout,
+                        void* dL_dvol, float* dL_dtf, int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && dL_dout, "render_backward: null pointer");
+  MRT_REQUIRE(dL_dvol || dL_dtf, "render_backward: nothing to differentiate");
+  KParams K;
+  if (int r = derive(params, C, tfN, false, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
+  if (K.showSeg && !labels) K.showSeg = 0;
+  if (K.showPred && !preds) K.showPred = 0;
+  cudaError_t e = mrt_launch_backward(K, mrt_packed_channels(C), packed, tf, labels, preds, out_rgba, dL_dout,
+                                      dL_dvol, dL_dtf, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
+}
+
+// ---------------------------------------------------------------- slab
+int mrt_render_slab_u8(const MrtSlabParams* P, const uint8_t* vol_u8, float* out_rgba,
+                       int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(P && vol_u8 && out_rgba, "render_slab: null pointer");
+  const int W = (int)P->imageSize[0], H = (int)P->imageSize[1];
+  MRT_REQUIRE(W > 0 && H > 0, "render_slab: imageSize invalid");
+  MRT_REQUIRE(P->volDim[0] >= 1 && P->volDim[1] >= 1 && P->volDim[2] >= 1, "render_slab: volDim invalid");
+  MRT_REQUIRE((uint64_t)P->volDim[0] * P->volDim[1] * P->volDim[2] < (1ull << 32), "render_slab: volume too large");
+  const int nt = mrt_tiles_x_(W) * mrt_tiles_y_(H);
+  MRT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt, "render_slab: tile range invalid");
+  const float tan_half = (float)tan(0.5 * (double)P->fovY);
+  cudaError_t e = mrt_launch_slab(*P, tan_half, vol_u8, out_rgba, tile_begin, tile_end, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_slab");
+}
+
+// ---------------------------------------------------------------- ingest
+int mrt_decode_bc4(const uint8_t* blocks, int32_t W, int32_t H, int32_t D, uint8_t* out, void* stream) {
+  MRT_REQUIRE(blocks && out && W > 0 && H > 0 && D > 0, "decode_bc4: bad arguments");
+  MRT_REQUIRE(((uintptr_t)blocks & 7) == 0, "decode_bc4: blocks must be 8-byte aligned");
+  cudaError_t e = mrt_launch_bc4(blocks, W, H, D, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "decode_bc4");
+}
+int mrt_u8_to_f32(const uint8_t* in, size_t n, float* out, void* stream) {
+  MRT_REQUIRE(in && out, "u8_to_f32: null pointer");
+  cudaError_t e = mrt_launch_u8_to_f32(in, n, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "u8_to_f32");
+}
+int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* out, void* stream) {
+  MRT_REQUIRE(in && out, "normalize_f32: null pointer");
+  MRT_REQUIRE(rng > 0.0f, "normalize_f32: rng must be > 0");
+  cudaError_t e = mrt_launch_normalize(in, n, vmin, rng, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "normalize_f32");
+}
+
+// ---------------------------------------------------------------- compositing / probe
+int mrt_composite_over(const float* partials, int32_t K, const int32_t* order, size_t npix, const float* bg3,
+                       int32_t alphaMode, float* out_rgba, void* stream) {
+  MRT_REQUIRE(partials && order && out_rgba && bg3 && K >= 1, "composite_over: bad arguments");
+  cudaError_t e = mrt_launch_composite(partials, K, order, npix, bg3[0], bg3[1], bg3[2], alphaMode, out_rgba,
+                                       (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "composite_over");
+}
+int mrt_gather_probe(const void* buf, size_t bytes, size_t n_gathers, uint32_t seed, float* out, void* stream) {
+  MRT_REQUIRE(buf && out, "gather_probe: null pointer");
+  cudaError_t e = mrt_launch_gather_probe(buf, bytes, n_gathers, seed, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "gather_probe");
+}
+
+// ---------------------------------------------------------------- host-buffer entry
+#define MRT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(MRT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto done; } } while (0)
+#define MRT_CALL(call) do { rc = (call); if (rc != MRT_OK) goto done; } while (0)
+
+int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C, const float* tf_host, int32_t tfN,
+                    const int32_t* labels_host, const int32_t* preds_host, float* out_rgba_host) {
+  MRT_REQUIRE(params && planar_host && out_rgba_host, "render_host: null pointer");
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("render_host", C, X, Y, Z)) return r;
+  const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
+  MRT_REQUIRE(W > 0 && H > 0, "render_host: imageSize invalid");
+  MRT_REQUIRE(!params->tfMode || (tf_host && tfN >= 2 && tfN <= MRT_MAX_TF), "render_host: tf invalid");
+  const size_t nvox = (size_t)X * Y * Z, npix = (size_t)W * H;
+  const int pc = mrt_packed_channels(C);
+  const int nb = mrt_brick_count(X, Y, Z);
+  int rc = MRT_OK;
+  cudaStream_t st = nullptr;
+  float *d_planar = nullptr, *d_tf = nullptr, *d_minmax = nullptr, *d_out = nullptr;
+  void* d_packed = nullptr;
+  int32_t *d_lab = nullptr, *d_pred = nullptr;
+  uint8_t *d_seg_any = nullptr, *d_pred_any = nullptr;
+  uint32_t* d_bits = nullptr;
+  MrtParams P = *params;
+  const bool useSeg = P.showSeg && labels_host, usePred = P.showPred && preds_host;
+  P.showSeg = useSeg; P.showPred = usePred;
+  MRT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  MRT_CUDA(cudaMallocAsync(&d_planar, nvox * C * sizeof(float), st));
+  MRT_CUDA(cudaMemcpyAsync(d_planar, planar_host, nvox * C * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (pc == 1) d_packed = d_planar;
+  else MRT_CUDA(cudaMallocAsync(&d_packed, nvox * pc * sizeof(float), st));
+  MRT_CALL(mrt_pack_volume_f32(d_planar, C, X, Y, Z, d_packed, st));
+  if (P.tfMode) {
+    MRT_CUDA(cudaMallocAsync(&d_tf, (size_t)tfN * 4 * sizeof(float), st));
+    MRT_CUDA(cudaMemcpyAsync(d_tf, tf_host, (size_t)tfN * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (useSeg) {
+    MRT_CUDA(cudaMallocAsync(&d_lab, nvox * sizeof(int32_t), st));
+    MRT_CUDA(cudaMemcpyAsync(d_lab, labels_host, nvox * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  if (usePred) {
+    MRT_CUDA(cudaMallocAsync(&d_pred, nvox * sizeof(int32_t), st));
+    MRT_CUDA(cudaMemcpyAsync(d_pred, preds_host, nvox * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  MRT_CUDA(cudaMallocAsync(&d_out, npix * 4 * sizeof(float), st));
+  if (P.skipEmpty && P.tMode == 0) {
+    MRT_CUDA(cudaMallocAsync(&d_minmax, (size_t)nb * pc * 2 * sizeof(float), st));
+    MRT_CUDA(cudaMallocAsync(&d_bits, (size_t)((nb + 31) / 32) * sizeof(uint32_t), st));
+    MRT_CALL(mrt_build_occupancy(d_packed, C, X, Y, Z, d_minmax, st));
+    if (useSeg) {
+      MRT_CUDA(cudaMallocAsync(&d_seg_any, nb, st));
+      MRT_CALL(mrt_build_label_occupancy(d_lab, X, Y, Z, d_seg_any, st));
+    }
+    if (usePred) {
+      MRT_CUDA(cudaMallocAsync(&d_pred_any, nb, st));
+      MRT_CALL(mrt_build_label_occupancy(d_pred, X, Y, Z, d_pred_any, st));
+    }
+    MRT_CALL(mrt_classify_bricks(&P, d_minmax, C, d_tf, tfN, d_seg_any, d_pred_any, d_bits, st));
+  }
+  MRT_CALL(mrt_render_forward(&P, d_packed, C, d_tf, tfN, d_bits, d_lab, d_pred, d_out, nullptr, nullptr,
+                              0, mrt_tile_count(W, H), st));
+  MRT_CUDA(cudaMemcpyAsync(out_rgba_host, d_out, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MRT_CUDA(cudaStreamSynchronize(st));
+done:
+  if (st) {
+    if (d_packed && d_packed != d_planar) cudaFreeAsync(d_packed, st);
+    if (d_planar) cudaFreeAsync(d_planar, st);
+    if (d_tf) cudaFreeAsync(d_tf, st);
+    if (d_lab) cudaFreeAsync(d_lab, st);
+    if (d_pred) cudaFreeAsync(d_pred, st);
+    if (d_out) cudaFreeAsync(d_out, st);
+    if (d_minmax) cudaFreeAsync(d_minmax, st);
+    if (d_bits) cudaFreeAsync(d_bits, st);
+    if (d_seg_any) cudaFreeAsync(d_seg_any, st);
+    if (d_pred_any) cudaFreeAsync(d_pred_any, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// forward.cu — the ray-march forward kernel (brats_main, inr/viewer/brats_rt.slang:85-168).
+//
+// One warp = one 8x4 half of an 8x8 screen tile (rays of a warp stay in one brick
+// neighbourhood); MRT_FWD_TPB tiles per CTA.  Per ray: exact set-up (march.cuh), then a
+// segment loop: locate the 8^3 brick of the current sample slot, look up its bit in the
+// per-frame active mask, and either jump over the whole brick (exact: those slots are
+// provably no-ops) or march the slots inside it: fp32 trilinear from the packed
+// multi-channel layout (8 vector loads per sample), modality blend, window/level, TF
+// (shared-memory LUT), front-to-back compositing with early ray termination.
+#include "march.cuh"
+#include "kernels.h"
+
+#ifndef MRT_FWD_TPB
+#define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
+#endif
+
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB)
+mrt_fwd_kernel(const __grid_constant__ KParams P,
+               const typename Vox<NCH>::T* __restrict__ vol,
+               const float4* __restrict__ tf,
+               const uint32_t* __restrict__ active_bits,
+               const int32_t* __restrict__ labels,
+               const int32_t* __restrict__ preds,
+               float4* __restrict__ out_rgba,
+               float* __restrict__ out_T,
+               int4* __restrict__ out_counts) {
+  extern __shared__ float4 s_tf[];          // [tfN] LUT, then 16 label entries
+  float4* s_lab = s_tf + (P.tfMode ? P.tfN : 0);   // [0..7] seg (rgb, alpha), [8..15] pred
+
+  if (P.tfMode) {
+    for (int i = threadIdx.x; i < P.tfN; i += blockDim.x) s_tf[i] = __ldg(tf + i);
+  }
+  if (LABELS) {
+    if (threadIdx.x < 16) {
+      const int l = threadIdx.x & 7;
+      const float boost = threadIdx.x < 8 ? 1.0f : 1.5f;                   // :158
+      const float a = 1.0f - expf(-P.lut[l][3] * P.dt * boost);            // :147
+      s_lab[threadIdx.x] = make_float4(P.lut[l][0], P.lut[l][1], P.lut[l][2], (l > 0) ? a : 0.0f);
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = P.tile_begin + blockIdx.x * MRT_FWD_TPB + (warp >> 1);
+  if (tile >= P.tile_end) return;
+  int px, py;
+  mrt_pixel_of_tile_lane_(tile, ((warp & 1) << 5) + lane, P.W, &px, &py);
+  if (px >= P.W || py >= P.H) return;                                      // :89
+
+  const Ray ray = mrt_setup_ray(P, px, py);
+  float Cr = P.bg[0], Cg = P.bg[1], Cb = P.bg[2];                          // :111
+  float T = 1.0f;                                                          // :112
+  int k = 0, n_eval = 0, n_seg = 0;
+
+  if (ray.n > 0) {
+    const IdxRay q = mrt_index_ray(P, ray);
+    const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
+    const float dt = P.dt, thr = P.thr;
+
+    // one sample slot at ray parameter t  (:119-162)
+    auto shade = [&](float t) {
+      const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+      const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
+      const float v = mrt_sample_blend<NCH>(P, vol, c);
+      const float val = mrt_window<GENERIC>(P, v);
+      if (P.tfMode) {
+        const float4 rgba = mrt_tf_lookup(s_tf, P.tfN, val);
+        const float alpha = 1.0f - expf(-rgba.w * dt);
+        const float aT = alpha * T;
+        Cr = fmaf(aT, rgba.x, Cr); Cg = fmaf(aT, rgba.y, Cg); Cb = fmaf(aT, rgba.z, Cb);
+        T *= (1.0f - alpha);
+      } else if (val > 0.0f) {                                             // :135
+        const float a = val * P.ia;
+        const float alpha = 1.0f - expf(-a * dt);                          // :137
+        const float c1 = alpha * T * val;                                  // :138
+        Cr += c1; Cg += c1; Cb += c1;
+        T *= (1.0f - alpha);                                               // :139
+      }
+      if (LABELS) {
+        if (P.showSeg) {                                                   // :143-151
+          const int l = mrt_sample_label(P, labels, ppx, ppy, ppz);
+          if (l > 0 && l < 8) {
+            const float4 col = s_lab[l];
+            const float aT = col.w * T;
+            Cr = fmaf(aT, col.x, Cr); Cg = fmaf(aT, col.y, Cg); Cb = fmaf(aT, col.z, Cb);
+            T *= (1.0f - col.w);
+          }
+        }
+        if (P.showPred) {                                                  // :154-162
+          const int l = mrt_sample_label(P, preds, ppx, ppy, ppz);
+          if (l > 0 && l < 8) {
+            const float4 col = s_lab[8 + l];
+            const float aT = col.w * T;
+            Cr = fmaf(aT, col.x, Cr); Cg = fmaf(aT, col.y, Cg); Cb = fmaf(aT, col.z, Cb);
+            T *= (1.0f - col.w);
+          }
+        }
+      }
+    };
+
+    if (GENERIC && P.tMode == 1) {
+      // reference-faithful running sum t += stepSize (:113,:164); no skipping possible
+      float t = ray.t0;
+      while (t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) {
+        shade(t);
+        t += dt; ++k; ++n_eval;
+      }
+    } else if (SKIP) {
+      const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
+      const float inv_dt = 1.0f / dt;
+      const int n = ray.n;
+      while (k < n && T > thr) {
+        const float t = fmaf((float)k, dt, ray.t0);
+        const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+        const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
+        const int bx = c.ix >> MRT_BRICK_SHIFT, by = c.iy >> MRT_BRICK_SHIFT, bz = c.iz >> MRT_BRICK_SHIFT;
+        const int bid = (bz * P.nby + by) * P.nbx + bx;
+        const bool act = (__ldg(active_bits + (bid >> 5)) >> (bid & 31)) & 1u;
+        const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, bx, by, bz, t, inv_dt));
+        if (GENERIC) ++n_seg;
+        if (!act) { k = kend; continue; }
+        do {
+          shade(fmaf((float)k, dt, ray.t0));
+          ++k; if (GENERIC) ++n_eval;
+        } while (k < kend && T > thr);
+      }
+    } else {
+      const int n = ray.n;
+      while (k < n && T > thr) {                                           // :117
+        shade(fmaf((float)k, dt, ray.t0));
+        ++k; if (GENERIC) ++n_eval;
+      }
+    }
+  }
+  const size_t pix = (size_t)py * P.W + px;
+  out_rgba[pix] = make_float4(Cr, Cg, Cb, P.alphaMode ? 1.0f - T : 1.0f);  // :167
+  if (out_T) out_T[pix] = T;
+  if (GENERIC) { if (out_counts) out_counts[pix] = make_int4(ray.n, k, n_eval, n_seg); }
+}
+
+// ------------------------------------------------------------------------- dispatch
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint32_t* bits,
+                              const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
+                              int32_t* out_counts, cudaStream_t st) {
+  const int ntiles = P.tile_end - P.tile_begin;
+  if (ntiles <= 0) return cudaSuccess;
+  const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
+  const size_t smem = ((P.tfMode ? P.tfN : 0) + 16) * sizeof(float4);
+  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC><<<grid, 64 * MRT_FWD_TPB, smem, st>>>(
+      P, (const typename Vox<NCH>::T*)vol, (const float4*)tf, bits, labels, preds,
+      (float4*)out_rgba, out_T, (int4*)out_counts);
+  return cudaGetLastError();
+}
+
+template <int NCH>
+static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen, const void* vol, const float* tf,
+                                const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                                float* o, float* oT, int32_t* oc, cudaStream_t st) {
+#define MRT_CASE(L, S, G) if (lab == L && skip == S && gen == G) \
+    return launch_fwd<NCH, L, S, G>(P, vol, tf, bits, labels, preds, o, oT, oc, st);
+  MRT_CASE(false, false, false) MRT_CASE(false, true, false)
+  MRT_CASE(true, false, false)  MRT_CASE(true, true, false)
+  MRT_CASE(false, false, true)  MRT_CASE(false, true, true)
+  MRT_CASE(true, false, true)   MRT_CASE(true, true, true)
+#undef MRT_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                               const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                               float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st) {
+  const bool lab = (P.showSeg || P.showPred);
+  const bool skip = P.skip && bits != nullptr && P.tMode == 0;
+  const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
+  switch (packed_ch) {
+    case 1: return dispatch_fwd<1>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
+    case 2: return dispatch_fwd<2>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
+    case 4: return dispatch_fwd<4>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
+  }
+  return cudaErrorInvalidValue;
+}

@@ -1,0 +1,41 @@
+// kernels.h — internal launcher prototypes (one per .cu translation unit).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+struct KParams;
+
+cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                               const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                               float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st);
+
+cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                                const int32_t* labels, const int32_t* preds,
+                                const float* out_rgba, const float* dL_dout,
+                                void* dvol, float* dtf, cudaStream_t st);
+
+cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
+cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
+
+cudaError_t mrt_launch_build_occupancy(const void* packed, int packed_ch, int X, int Y, int Z,
+                                       float* minmax, cudaStream_t st);
+cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int Z, uint8_t* any, cudaStream_t st);
+cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int packed_ch, const float* tf,
+                                const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* bits,
+                                cudaStream_t st);
+
+cudaError_t mrt_launch_tile_map(int W, int H, int32_t* out_tile, int32_t* out_lane, cudaStream_t st);
+cudaError_t mrt_launch_gather_probe(const void* buf, size_t bytes, size_t n, uint32_t seed, float* out,
+                                    cudaStream_t st);
+cudaError_t mrt_launch_composite(const float* partials, int K, const int32_t* order, size_t npix,
+                                 float bgr, float bgg, float bgb, int alphaMode, float* out, cudaStream_t st);
+cudaError_t mrt_launch_bc4(const uint8_t* blocks, int W, int H, int D, uint8_t* out, cudaStream_t st);
+cudaError_t mrt_launch_u8_to_f32(const uint8_t* in, size_t n, float* out, cudaStream_t st);
+cudaError_t mrt_launch_normalize(const float* in, size_t n, float vmin, float rng, float* out, cudaStream_t st);
+
+struct MrtSlabParams;
+cudaError_t mrt_launch_slab(const MrtSlabParams& P, float tan_half, const uint8_t* vol, float* out,
+                            int tile_begin, int tile_end, cudaStream_t st);
+
+static inline int mrt_packed_channels(int C) { return C <= 1 ? 1 : (C == 2 ? 2 : 4); }

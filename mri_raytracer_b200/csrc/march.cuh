@@ -1,0 +1,224 @@
+// march.cuh — device-side building blocks shared by the forward and backward kernels.
+//
+// Follows inr/viewer/brats_rt.slang (reference) row by row; see DESIGN.md §kernels for
+// the arithmetic contract.  Ray set-up uses explicit round-to-nearest intrinsics
+// (no FMA contraction) so that o, d, t0, t1 and the per-ray sample count n are
+// bit-identical to a one-IEEE-op-at-a-time CPU evaluation; the per-sample math is
+// allowed to contract (tolerance 1e-4, see tests/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tiles.h"
+
+#define MRT_BRICK_SHIFT 3
+
+// Kernel-side constant block, derived on the host from MrtParams (c_api.cu).
+struct KParams {
+  int W, H;
+  float eye[3], U[3], V[3], Wv[3];
+  float focal;            // 1/tan(fovY/2), evaluated in double on the host
+  int ortho; float halfH;
+  float bmin[3], vs[3];
+  int dims[3];            // X, Y, Z
+  float dt, nearT, farT;
+  float bg[3];
+  float wgt[4];           // volWeight if enabled else 0
+  float inv_wsum;         // 1/wSum if wSum > 0 else 1
+  float lo, inv_ww;       // window: val = saturate((v - lo) * inv_ww)
+  float ia, gamma;
+  int showSeg, showPred;
+  float lut[8][4];
+  float thr;
+  int maxSteps, tMode, alphaMode, tfMode, tfN;
+  int skip;               // occupancy skipping enabled
+  int nbx, nby, nbz;      // brick grid
+  int tile_begin, tile_end;
+};
+
+struct Ray {
+  float ox, oy, oz, dx, dy, dz;
+  float t0, t1;
+  int n;        // # of sample slots k with t0 + k*dt < t1 (0 if miss)
+};
+
+__device__ __forceinline__ float mrt_norm3(float x, float y, float z) {
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// makePrimary (brats_rt.slang:36-46) / orthographic, then de-zero + aabbHit +
+// near/far clamp (:95-99, :48-57, :107-109) and the indexed sample count.
+__device__ __forceinline__ Ray mrt_setup_ray(const KParams& P, int px, int py) {
+  Ray r;
+  const float dimx = (float)P.W, dimy = (float)P.H;
+  const float ndcx = __fdiv_rn(__fadd_rn((float)px, 0.5f), dimx);
+  const float ndcy = __fdiv_rn(__fadd_rn((float)py, 0.5f), dimy);
+  const float uvx = __fsub_rn(__fmul_rn(ndcx, 2.0f), 1.0f);
+  const float uvy = __fsub_rn(__fmul_rn(ndcy, 2.0f), 1.0f);
+  const float aspect = __fdiv_rn(dimx, fmaxf(1.0f, dimy));
+  if (P.ortho) {
+    const float halfW = __fmul_rn(aspect, P.halfH);
+    const float ax = __fmul_rn(uvx, halfW);
+    const float ay = -__fmul_rn(uvy, P.halfH);
+    r.ox = __fadd_rn(__fadd_rn(P.eye[0], __fmul_rn(ax, P.U[0])), __fmul_rn(ay, P.V[0]));
+    r.oy = __fadd_rn(__fadd_rn(P.eye[1], __fmul_rn(ax, P.U[1])), __fmul_rn(ay, P.V[1]));
+    r.oz = __fadd_rn(__fadd_rn(P.eye[2], __fmul_rn(ax, P.U[2])), __fmul_rn(ay, P.V[2]));
+    r.dx = P.Wv[0]; r.dy = P.Wv[1]; r.dz = P.Wv[2];
+  } else {
+    float cx = __fdiv_rn(__fmul_rn(uvx, aspect), P.focal);
+    float cy = __fdiv_rn(-uvy, P.focal);
+    float cz = 1.0f;
+    const float inv = mrt_norm3(cx, cy, cz);
+    cx = __fdiv_rn(cx, inv); cy = __fdiv_rn(cy, inv); cz = __fdiv_rn(cz, inv);
+    const float rx = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[0]), __fmul_rn(cy, P.V[0])), __fmul_rn(cz, P.Wv[0]));
+    const float ry = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[1]), __fmul_rn(cy, P.V[1])), __fmul_rn(cz, P.Wv[1]));
+    const float rz = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[2]), __fmul_rn(cy, P.V[2])), __fmul_rn(cz, P.Wv[2]));
+    const float n = mrt_norm3(rx, ry, rz);
+    r.dx = __fdiv_rn(rx, n); r.dy = __fdiv_rn(ry, n); r.dz = __fdiv_rn(rz, n);
+    r.ox = P.eye[0]; r.oy = P.eye[1]; r.oz = P.eye[2];
+  }
+  // de-zero: sign dropped on purpose (:96-98); rcpDir uses the patched copy only
+  const float ex = fabsf(r.dx) < 1e-6f ? 1e-6f : r.dx;
+  const float ey = fabsf(r.dy) < 1e-6f ? 1e-6f : r.dy;
+  const float ez = fabsf(r.dz) < 1e-6f ? 1e-6f : r.dz;
+  const float rx_ = __fdiv_rn(1.0f, ex), ry_ = __fdiv_rn(1.0f, ey), rz_ = __fdiv_rn(1.0f, ez);
+  const float bxm = __fadd_rn(P.bmin[0], __fmul_rn(P.vs[0], (float)P.dims[0]));
+  const float bym = __fadd_rn(P.bmin[1], __fmul_rn(P.vs[1], (float)P.dims[1]));
+  const float bzm = __fadd_rn(P.bmin[2], __fmul_rn(P.vs[2], (float)P.dims[2]));
+  const float ax0 = __fmul_rn(__fsub_rn(P.bmin[0], r.ox), rx_), ax1 = __fmul_rn(__fsub_rn(bxm, r.ox), rx_);
+  const float ay0 = __fmul_rn(__fsub_rn(P.bmin[1], r.oy), ry_), ay1 = __fmul_rn(__fsub_rn(bym, r.oy), ry_);
+  const float az0 = __fmul_rn(__fsub_rn(P.bmin[2], r.oz), rz_), az1 = __fmul_rn(__fsub_rn(bzm, r.oz), rz_);
+  const float tmin = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
+  const float tmax = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
+  bool hit = tmax >= fmaxf(tmin, 0.0f);
+  r.t0 = fmaxf(tmin, fmaxf(0.0f, P.nearT));
+  r.t1 = (P.farT > 0.0f) ? fminf(tmax, P.farT) : tmax;
+  hit = hit && !(r.t1 <= r.t0);
+  int n = 0;
+  if (hit) {
+    n = (int)ceilf(__fdiv_rn(__fsub_rn(r.t1, r.t0), P.dt));
+    n = max(n, 0);
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {   // exact fix-up: n = #{k : t0 + k*dt < t1}
+      if (__fadd_rn(r.t0, __fmul_rn((float)n, P.dt)) < r.t1) ++n;
+      if (n > 0 && !(__fadd_rn(r.t0, __fmul_rn((float)(n - 1), P.dt)) < r.t1)) --n;
+    }
+    if (P.maxSteps > 0) n = min(n, P.maxSteps);
+  }
+  r.n = n;
+  return r;
+}
+
+// ---- voxel vector types -------------------------------------------------------------
+template <int NCH> struct Vox;
+template <> struct Vox<1> { typedef float T; };
+template <> struct Vox<2> { typedef float2 T; };
+template <> struct Vox<4> { typedef float4 T; };
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
+__device__ __forceinline__ float  vlerp(float a, float b, float t) { return lerpf(a, b, t); }
+__device__ __forceinline__ float2 vlerp(float2 a, float2 b, float t) {
+  return make_float2(lerpf(a.x, b.x, t), lerpf(a.y, b.y, t));
+}
+__device__ __forceinline__ float4 vlerp(float4 a, float4 b, float t) {
+  return make_float4(lerpf(a.x, b.x, t), lerpf(a.y, b.y, t), lerpf(a.z, b.z, t), lerpf(a.w, b.w, t));
+}
+__device__ __forceinline__ float blendv(float s, const KParams& P) { return s * P.wgt[0]; }
+__device__ __forceinline__ float blendv(float2 s, const KParams& P) {
+  return fmaf(s.y, P.wgt[1], s.x * P.wgt[0]);
+}
+__device__ __forceinline__ float blendv(float4 s, const KParams& P) {
+  return fmaf(s.w, P.wgt[3], fmaf(s.z, P.wgt[2], fmaf(s.y, P.wgt[1], s.x * P.wgt[0])));
+}
+
+// Index-space ray: pIdx(t) = oi + t*di  (== (o + t*d - bmin)/voxelSize up to rounding).
+struct IdxRay { float ox, oy, oz, dx, dy, dz; };
+__device__ __forceinline__ IdxRay mrt_index_ray(const KParams& P, const Ray& r) {
+  IdxRay q;
+  q.ox = (r.ox - P.bmin[0]) / P.vs[0]; q.oy = (r.oy - P.bmin[1]) / P.vs[1]; q.oz = (r.oz - P.bmin[2]) / P.vs[2];
+  q.dx = r.dx / P.vs[0]; q.dy = r.dy / P.vs[1]; q.dz = r.dz / P.vs[2];
+  return q;
+}
+
+// sampleLinear (brats_rt.slang:60-76) on the packed multi-channel layout, then the
+// modality blend (:123-130).  Returns v; also the integer base + fractions if wanted.
+struct Cell { int ix, iy, iz; float fx, fy, fz; };
+
+__device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, float pz,
+                                         float hix, float hiy, float hiz) {
+  Cell c;
+  const float qx = fminf(fmaxf(px, 0.0f), hix);
+  const float qy = fminf(fmaxf(py, 0.0f), hiy);
+  const float qz = fminf(fmaxf(pz, 0.0f), hiz);
+  const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
+  c.ix = (int)flx; c.iy = (int)fly; c.iz = (int)flz;
+  c.fx = qx - flx; c.fy = qy - fly; c.fz = qz - flz;
+  return c;
+}
+
+template <int NCH>
+__device__ __forceinline__ float mrt_sample_blend(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
+                                                  const Cell& c) {
+  typedef typename Vox<NCH>::T VT;
+  const uint32_t sY = (uint32_t)P.dims[0];
+  const uint32_t sZ = sY * (uint32_t)P.dims[1];
+  const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ;
+  const VT* p0 = vol + b;
+  const VT* p1 = p0 + sY;
+  const VT* p2 = p0 + sZ;
+  const VT* p3 = p2 + sY;
+  const VT c000 = __ldg(p0), c100 = __ldg(p0 + 1);
+  const VT c010 = __ldg(p1), c110 = __ldg(p1 + 1);
+  const VT c001 = __ldg(p2), c101 = __ldg(p2 + 1);
+  const VT c011 = __ldg(p3), c111 = __ldg(p3 + 1);
+  const VT s = vlerp(vlerp(vlerp(c000, c100, c.fx), vlerp(c010, c110, c.fx), c.fy),
+                     vlerp(vlerp(c001, c101, c.fx), vlerp(c011, c111, c.fx), c.fy), c.fz);
+  return blendv(s, P) * P.inv_wsum;
+}
+
+// sampleLabel (brats_rt.slang:78-83): round half away from zero.
+__device__ __forceinline__ int mrt_sample_label(const KParams& P, const int32_t* __restrict__ lab,
+                                                float px, float py, float pz) {
+  const float qx = fminf(fmaxf(px, 0.0f), (float)P.dims[0] - 1.0f);
+  const float qy = fminf(fmaxf(py, 0.0f), (float)P.dims[1] - 1.0f);
+  const float qz = fminf(fmaxf(pz, 0.0f), (float)P.dims[2] - 1.0f);
+  const uint32_t ix = (uint32_t)roundf(qx), iy = (uint32_t)roundf(qy), iz = (uint32_t)roundf(qz);
+  const uint32_t idx = ix + iy * (uint32_t)P.dims[0] + iz * (uint32_t)P.dims[0] * (uint32_t)P.dims[1];
+  return __ldg(lab + idx);
+}
+
+// window/level (+gamma) (brats_rt.slang:132-133)
+template <bool GENERIC>
+__device__ __forceinline__ float mrt_window(const KParams& P, float v) {
+  float val = __saturatef((v - P.lo) * P.inv_ww);
+  if (GENERIC) { if (P.gamma != 1.0f) val = powf(val, P.gamma); }
+  return val;
+}
+
+// 1D LUT lookup: u = val*(N-1), lerp(tf[floor u], tf[min(floor u + 1, N-1)], frac)
+__device__ __forceinline__ float4 mrt_tf_lookup(const float4* __restrict__ s_tf, int N, float val,
+                                                int* j0o = nullptr, int* j1o = nullptr, float* fro = nullptr) {
+  const float u = val * (float)(N - 1);
+  const float j0f = floorf(u);
+  const float fr = u - j0f;
+  const int j0 = min(max((int)j0f, 0), N - 1);
+  const int j1 = min(j0 + 1, N - 1);
+  const float4 a = s_tf[j0], b = s_tf[j1];
+  if (j0o) { *j0o = j0; *j1o = j1; *fro = fr; }
+  return make_float4(lerpf(a.x, b.x, fr), lerpf(a.y, b.y, fr), lerpf(a.z, b.z, fr), lerpf(a.w, b.w, fr));
+}
+
+// Exit of the ray from brick cell (bx,by,bz) in index space; returns # of further sample
+// slots (>= 1) guaranteed to lie strictly inside the cell, starting from slot time t.
+__device__ __forceinline__ int mrt_cell_slots(const IdxRay& q, float ivx, float ivy, float ivz,
+                                              int bx, int by, int bz, float t, float inv_dt) {
+  const float plx = (float)((bx + (q.dx > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
+  const float ply = (float)((by + (q.dy > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
+  const float plz = (float)((bz + (q.dz > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
+  // an axis the ray does not move along never bounds the exit
+  const float tx = (q.dx != 0.0f) ? (plx - q.ox) * ivx : 3.0e38f;
+  const float ty = (q.dy != 0.0f) ? (ply - q.oy) * ivy : 3.0e38f;
+  const float tz = (q.dz != 0.0f) ? (plz - q.oz) * ivz : 3.0e38f;
+  const float te = fminf(fminf(tx, ty), tz);
+  const float ns = floorf((te - t) * inv_dt);
+  return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
+}

@@ -1,0 +1,209 @@
+// misc.cu — layout, ingest, tile-map, compositing and roofline-probe kernels.
+#include "march.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------ pack / unpack
+// planar [C][Z][Y][X] (reference flatten, inr/viewer/brats_viewer.py:64) <-> interleaved.
+template <int PC>
+__global__ void mrt_pack_kernel(const float* __restrict__ planar, int C, size_t nvox,
+                                typename Vox<PC>::T* __restrict__ packed) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += stride) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < PC; ++c) if (c < C) v[c] = __ldg(planar + (size_t)c * nvox + i);
+    typename Vox<PC>::T o;
+    float* f = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int c = 0; c < PC; ++c) f[c] = v[c];
+    packed[i] = o;
+  }
+}
+template <int PC>
+__global__ void mrt_unpack_kernel(const typename Vox<PC>::T* __restrict__ packed, int C, size_t nvox,
+                                  float* __restrict__ planar) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += stride) {
+    const typename Vox<PC>::T o = packed[i];
+    const float* f = reinterpret_cast<const float*>(&o);
+#pragma unroll
+    for (int c = 0; c < PC; ++c) if (c < C) planar[(size_t)c * nvox + i] = f[c];
+  }
+}
+
+static inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = 148 * 16;          // a few CTAs per SM, grid-stride beyond that
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int pc = mrt_packed_channels(C);
+  if (pc == 1) {
+    if ((const void*)planar != packed)
+      return cudaMemcpyAsync(packed, planar, nvox * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return cudaSuccess;
+  }
+  const int g = grid_for(nvox, 256);
+  if (pc == 2) mrt_pack_kernel<2><<<g, 256, 0, st>>>(planar, C, nvox, (float2*)packed);
+  else mrt_pack_kernel<4><<<g, 256, 0, st>>>(planar, C, nvox, (float4*)packed);
+  return cudaGetLastError();
+}
+
+cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int pc = mrt_packed_channels(C);
+  if (pc == 1) {
+    if (packed != (const void*)planar)
+      return cudaMemcpyAsync(planar, packed, nvox * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return cudaSuccess;
+  }
+  const int g = grid_for(nvox, 256);
+  if (pc == 2) mrt_unpack_kernel<2><<<g, 256, 0, st>>>((const float2*)packed, C, nvox, planar);
+  else mrt_unpack_kernel<4><<<g, 256, 0, st>>>((const float4*)packed, C, nvox, planar);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ tile map on device
+__global__ void mrt_tile_map_kernel(int W, int H, int32_t* __restrict__ out_tile, int32_t* __restrict__ out_lane) {
+  // same launch geometry as the renderer: 64 threads (one 8x8 tile) per CTA
+  const int tile = blockIdx.x;
+  int x, y;
+  mrt_pixel_of_tile_lane_(tile, threadIdx.x, W, &x, &y);
+  if (x >= W || y >= H) return;
+  out_tile[(size_t)y * W + x] = mrt_tile_of_pixel_(x, y, W);
+  out_lane[(size_t)y * W + x] = mrt_lane_of_pixel_(x, y);
+}
+cudaError_t mrt_launch_tile_map(int W, int H, int32_t* out_tile, int32_t* out_lane, cudaStream_t st) {
+  const int nt = mrt_tiles_x_(W) * mrt_tiles_y_(H);
+  if (nt <= 0) return cudaSuccess;
+  mrt_tile_map_kernel<<<nt, 64, 0, st>>>(W, H, out_tile, out_lane);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ gather probe
+// Each thread issues independent random 32-byte-sector loads (one float4 x2 = 32 B) and
+// folds them into a checksum; 8 loads in flight per thread like one trilinear sample.
+__device__ __forceinline__ uint32_t mrt_hash(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
+}
+__global__ void __launch_bounds__(256)
+mrt_gather_probe_kernel(const float4* __restrict__ buf, uint32_t sector_mask, size_t n_per_thread,
+                        uint32_t seed, float* __restrict__ out) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t s = mrt_hash(tid * 0x9E3779B9U + seed);
+  float acc = 0.0f;
+  for (size_t i = 0; i < n_per_thread; i += 8) {
+    float4 a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s = s * 1664525U + 1013904223U;
+      const uint32_t sec = mrt_hash(s) & sector_mask;
+      a[j] = __ldg(buf + (size_t)sec * 2);
+      b[j] = __ldg(buf + (size_t)sec * 2 + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a[j].x + a[j].w + b[j].y + b[j].z;
+  }
+  if (acc == 123.456f) out[0] = acc;      // practically never; keeps the loads alive
+  if (tid == 0) out[1] = 1.0f;
+}
+cudaError_t mrt_launch_gather_probe(const void* buf, size_t bytes, size_t n, uint32_t seed, float* out,
+                                    cudaStream_t st) {
+  const size_t sectors = bytes / 32;
+  if (sectors == 0 || (sectors & (sectors - 1)) != 0 || sectors > 0xffffffffull) return cudaErrorInvalidValue;
+  const int block = 256, grid = 148 * 8;
+  size_t per_thread = n / ((size_t)grid * block);
+  per_thread = (per_thread + 7) / 8 * 8;
+  if (per_thread == 0) per_thread = 8;
+  mrt_gather_probe_kernel<<<grid, block, 0, st>>>((const float4*)buf, (uint32_t)(sectors - 1), per_thread, seed, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ sort-last compositing
+// (C,T) <- (C_a + T_a*C_b, T_a*T_b), front first; bg added once at the end.
+__global__ void __launch_bounds__(256)
+mrt_composite_kernel(const float4* __restrict__ partials, int K, const int32_t* __restrict__ order,
+                     size_t npix, float bgr, float bgg, float bgb, int alphaMode, float4* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+    float r = 0.f, g = 0.f, b = 0.f, T = 1.f;
+    for (int k = 0; k < K; ++k) {
+      const float4 p = __ldg(partials + (size_t)__ldg(order + k) * npix + i);
+      r = fmaf(T, p.x, r); g = fmaf(T, p.y, g); b = fmaf(T, p.z, b);
+      T *= p.w;
+    }
+    out[i] = make_float4(bgr + r, bgg + g, bgb + b, alphaMode ? 1.0f - T : 1.0f);
+  }
+}
+cudaError_t mrt_launch_composite(const float* partials, int K, const int32_t* order, size_t npix,
+                                 float bgr, float bgg, float bgb, int alphaMode, float* out, cudaStream_t st) {
+  if (npix == 0) return cudaSuccess;
+  mrt_composite_kernel<<<grid_for(npix, 256), 256, 0, st>>>((const float4*)partials, K, order, npix,
+                                                           bgr, bgg, bgb, alphaMode, (float4*)out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ BC4 decode
+// scripts/volumeRendering/app.py:200-250: 8-byte blocks (r0, r1, 48 bits of 3-bit codes),
+// 4x4 texels, slices of ceil(H/4) x ceil(W/4) blocks, cropped to H x W.
+__global__ void __launch_bounds__(256)
+mrt_bc4_kernel(const uint2* __restrict__ blocks, int W, int H, int D, int bw, int bh, uint8_t* __restrict__ out) {
+  const size_t nblocks = (size_t)D * bw * bh;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t bi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; bi < nblocks; bi += stride) {
+    const uint2 raw = __ldg(blocks + bi);
+    const int r0 = raw.x & 0xff, r1 = (raw.x >> 8) & 0xff;
+    const uint64_t idx = ((uint64_t)raw.y << 16) | (raw.x >> 16);
+    int pal[8];
+    pal[0] = r0; pal[1] = r1;
+    if (r0 > r1) {
+#pragma unroll
+      for (int i = 1; i < 7; ++i) pal[i + 1] = ((7 - i) * r0 + i * r1 + 3) / 7;     // :227-229
+    } else {
+#pragma unroll
+      for (int i = 1; i < 5; ++i) pal[i + 1] = ((5 - i) * r0 + i * r1 + 2) / 5;     // :231-233
+      pal[6] = 0; pal[7] = 255;                                                      // :234-235
+    }
+    const int d = (int)(bi / ((size_t)bw * bh));
+    const int rem = (int)(bi % ((size_t)bw * bh));
+    const int byy = rem / bw, bxx = rem % bw;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int code = (int)((idx >> (3 * t)) & 7);
+      const int x = bxx * 4 + (t & 3), y = byy * 4 + (t >> 2);
+      if (x < W && y < H) out[((size_t)d * H + y) * W + x] = (uint8_t)pal[code];
+    }
+  }
+}
+cudaError_t mrt_launch_bc4(const uint8_t* blocks, int W, int H, int D, uint8_t* out, cudaStream_t st) {
+  const int bw = (W + 3) / 4, bh = (H + 3) / 4;
+  const size_t nblocks = (size_t)D * bw * bh;
+  if (nblocks == 0) return cudaSuccess;
+  mrt_bc4_kernel<<<grid_for(nblocks, 256), 256, 0, st>>>((const uint2*)blocks, W, H, D, bw, bh, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ u8 -> f32, normalise
+__global__ void mrt_u8_to_f32_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float)__ldg(in + i) / 255.0f;                   // volume_render.slang:38
+}
+cudaError_t mrt_launch_u8_to_f32(const uint8_t* in, size_t n, float* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  mrt_u8_to_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, out);
+  return cudaGetLastError();
+}
+__global__ void mrt_normalize_kernel(const float* __restrict__ in, size_t n, float vmin, float rng,
+                                     float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __saturatef(__fdiv_rn(__fsub_rn(__ldg(in + i), vmin), rng));   // brats_viewer.py:56
+}
+cudaError_t mrt_launch_normalize(const float* in, size_t n, float vmin, float rng, float* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  mrt_normalize_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, vmin, rng, out);
+  return cudaGetLastError();
+}

@@ -1,0 +1,162 @@
+// occupancy.cu — min/max occupancy brick grid and the per-frame active-brick mask.
+//
+// No reference code (empty-space skipping is only mentioned in the reference's docs:
+// docs/Methodology-ROI-Neural-Volumetric-Rendering.md:34, docs/showcase-plan.md:20).
+// Contract: skipping must never change the image.  A brick is marked inactive only when
+// every sample slot whose trilinear base index lies in it is provably a no-op
+// (sigma == 0 for the whole reachable TF range, and no overlay label present).
+#include "march.cuh"
+#include "kernels.h"
+#include <float.h>
+
+// ---------------------------------------------------------------- build (once per volume)
+// brick b covers voxel indices [8b, 8b+8] per axis (clipped): the union of the 2x2x2
+// footprints of all samples with base index in [8b, 8b+7], and of the nearest-label
+// footprint round(p) of the same samples.
+template <int NCH>
+__global__ void __launch_bounds__(128)
+mrt_build_minmax_kernel(const typename Vox<NCH>::T* __restrict__ vol, int X, int Y, int Z,
+                        int nbx, int nby, float2* __restrict__ minmax) {
+  const int b = blockIdx.x;
+  const int bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+  const int x0 = bx << 3, y0 = by << 3, z0 = bz << 3;
+  const int ex = min(9, X - x0), ey = min(9, Y - y0), ez = min(9, Z - z0);
+  const int nvox = ex * ey * ez;
+  float mn[NCH], mx[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { mn[c] = FLT_MAX; mx[c] = -FLT_MAX; }
+  for (int i = threadIdx.x; i < nvox; i += blockDim.x) {
+    const int lx = i % ex, ly = (i / ex) % ey, lz = i / (ex * ey);
+    const size_t idx = (size_t)(x0 + lx) + (size_t)X * ((size_t)(y0 + ly) + (size_t)Y * (size_t)(z0 + lz));
+    const typename Vox<NCH>::T v = __ldg(vol + idx);
+    const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { mn[c] = fminf(mn[c], f[c]); mx[c] = fmaxf(mx[c], f[c]); }
+  }
+  __shared__ float s_mn[4][NCH], s_mx[4][NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { s_mn[warp][c] = mn[c]; s_mx[warp][c] = mx[c]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < NCH) {
+    const int c = threadIdx.x;
+    float a = s_mn[0][c], z = s_mx[0][c];
+    for (int w = 1; w < 4; ++w) { a = fminf(a, s_mn[w][c]); z = fmaxf(z, s_mx[w][c]); }
+    minmax[(size_t)b * NCH + c] = make_float2(a, z);
+  }
+}
+
+cudaError_t mrt_launch_build_occupancy(const void* packed, int pc, int X, int Y, int Z, float* minmax,
+                                       cudaStream_t st) {
+  const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
+  const int nb = nbx * nby * nbz;
+  switch (pc) {
+    case 1: mrt_build_minmax_kernel<1><<<nb, 128, 0, st>>>((const float*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
+    case 2: mrt_build_minmax_kernel<2><<<nb, 128, 0, st>>>((const float2*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
+    case 4: mrt_build_minmax_kernel<4><<<nb, 128, 0, st>>>((const float4*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128)
+mrt_label_any_kernel(const int32_t* __restrict__ lab, int X, int Y, int Z, int nbx, int nby,
+                     uint8_t* __restrict__ any) {
+  const int b = blockIdx.x;
+  const int bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+  const int x0 = bx << 3, y0 = by << 3, z0 = bz << 3;
+  const int ex = min(9, X - x0), ey = min(9, Y - y0), ez = min(9, Z - z0);
+  const int nvox = ex * ey * ez;
+  int found = 0;
+  for (int i = threadIdx.x; i < nvox; i += blockDim.x) {
+    const int lx = i % ex, ly = (i / ex) % ey, lz = i / (ex * ey);
+    const size_t idx = (size_t)(x0 + lx) + (size_t)X * ((size_t)(y0 + ly) + (size_t)Y * (size_t)(z0 + lz));
+    const int l = __ldg(lab + idx);
+    found |= (l > 0 && l < 8);                                  // brats_rt.slang:145
+  }
+  const int r = __syncthreads_or(found);
+  if (threadIdx.x == 0) any[b] = (uint8_t)(r != 0);
+}
+
+cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int Z, uint8_t* any, cudaStream_t st) {
+  const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
+  mrt_label_any_kernel<<<nbx * nby * nbz, 128, 0, st>>>(labels, X, Y, Z, nbx, nby, any);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- classify (per frame)
+// Conservative interval arithmetic: blended value range -> window/level range -> the TF
+// entries a sample in this brick can touch.  Margins (1e-5 on v, 1e-3 of a LUT bin) are far
+// wider than any fp32 rounding in the sampler and far narrower than a LUT bin.
+template <int NCH>
+__global__ void __launch_bounds__(128)
+mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict__ minmax,
+                    const float4* __restrict__ tf, const uint8_t* __restrict__ seg_any,
+                    const uint8_t* __restrict__ pred_any, uint32_t* __restrict__ bits, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = false;
+  if (b < nb) {
+    float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float2 mm = __ldg(minmax + (size_t)b * NCH + c);
+      const float w = P.wgt[c];
+      lo += (w >= 0.0f) ? w * mm.x : w * mm.y;
+      hi += (w >= 0.0f) ? w * mm.y : w * mm.x;
+    }
+    float a = lo * P.inv_wsum, z = hi * P.inv_wsum;
+    if (a > z) { const float t = a; a = z; z = t; }
+    const float mv = 1e-5f * (1.0f + fmaxf(fabsf(a), fabsf(z)));
+    a -= mv; z += mv;
+    float r0 = (a - P.lo) * P.inv_ww, r1 = (z - P.lo) * P.inv_ww;
+    if (r0 > r1) { const float t = r0; r0 = r1; r1 = t; }
+    const float mr = 1e-5f * (1.0f + fmaxf(fabsf(r0), fabsf(r1)));
+    r0 -= mr; r1 += mr;
+    float v0 = __saturatef(r0), v1 = __saturatef(r1);
+    if (P.gamma != 1.0f) {                       // pow is monotone on [0,1] for gamma > 0
+      const float p0 = powf(v0, P.gamma), p1 = powf(v1, P.gamma);
+      v0 = fmaxf(fminf(p0, p1) - 1e-5f, 0.0f); v1 = fminf(fmaxf(p0, p1) + 1e-5f, 1.0f);
+      if (!(P.gamma > 0.0f)) { v0 = 0.0f; v1 = 1.0f; }
+    }
+    if (P.tfMode == 0) {
+      act = (v1 > 0.0f) && (P.ia != 0.0f);        // sigma = val*intensityAlpha, gated on val > 0 (:135)
+    } else {
+      const float s = (float)(P.tfN - 1);
+      int j0 = (int)floorf(v0 * s - 1e-3f), j1 = (int)floorf(v1 * s + 1e-3f) + 1;
+      j0 = max(j0, 0); j1 = min(j1, P.tfN - 1);
+      for (int j = j0; j <= j1; ++j) {
+        if (__ldg(&tf[j].w) != 0.0f) { act = true; break; }
+      }
+    }
+    if (P.showSeg && seg_any != nullptr && seg_any[b]) act = true;
+    if (P.showPred && pred_any != nullptr && pred_any[b]) act = true;
+    if (P.showSeg && seg_any == nullptr) act = true;     // no label grid supplied: stay exact
+    if (P.showPred && pred_any == nullptr) act = true;
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, act);
+  if ((threadIdx.x & 31) == 0 && b < nb) bits[b >> 5] = word;
+}
+
+cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int pc, const float* tf,
+                                const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* bits,
+                                cudaStream_t st) {
+  const int nb = P.nbx * P.nby * P.nbz;
+  const int grid = (nb + 127) / 128;
+  switch (pc) {
+    case 1: mrt_classify_kernel<1><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
+    case 2: mrt_classify_kernel<2><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
+    case 4: mrt_classify_kernel<4><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}

@@ -1,0 +1,156 @@
+"""RenderParams — the operator's config block.
+
+Field names, meaning and defaults are the reference's: ``struct Params``
+(inr/viewer/brats_rt.slang:12-31) as filled every frame by the viewer
+(inr/viewer/brats_viewer.py:405-426; defaults :112,126-135,138-144).  The tail fields are
+the extensions SURVEY.md §8 defines (ortho camera, indexed stepping, LUT transfer function,
+empty-space skipping); their defaults keep reference behaviour except ``tMode`` (indexed,
+SURVEY Q4) and ``skipEmpty`` (exact, never changes the image).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field, replace
+from typing import Sequence, Tuple
+
+import numpy as np
+
+from ._lib import MrtParams, MrtSlabParams
+
+T_INDEXED, T_ACCUMULATE = "indexed", "accumulate"
+
+
+def default_label_lut() -> np.ndarray:
+    """The viewer's fixed 8-entry label LUT (inr/viewer/brats_viewer.py:138-144)."""
+    lut = np.zeros((8, 4), dtype=np.float32)
+    lut[1] = (0.0, 0.4, 1.0, 0.9)     # NCR/NET
+    lut[2] = (0.0, 0.8, 0.0, 0.7)     # edema
+    lut[3] = (1.0, 0.1, 0.1, 0.9)     # enhancing
+    lut[4] = (1.0, 0.1, 0.1, 0.9)     # BraTS label 4 = enhancing (older numbering)
+    return lut
+
+
+def _v3(x) -> Tuple[float, float, float]:
+    a = np.asarray(x, dtype=np.float32).reshape(3)
+    return (float(a[0]), float(a[1]), float(a[2]))
+
+
+@dataclass
+class RenderParams:
+    imageSize: Tuple[int, int] = (512, 512)          # (W, H)
+    fovY: float = math.radians(70.0)
+    eye: Sequence[float] = (0.0, 0.0, -3.0)
+    U: Sequence[float] = (1.0, 0.0, 0.0)
+    V: Sequence[float] = (0.0, 1.0, 0.0)
+    W: Sequence[float] = (0.0, 0.0, 1.0)
+    volMin: Sequence[float] = (-0.9, -0.9, -0.9)
+    voxelSize: Sequence[float] = (0.0075, 0.0075, 0.0075)
+    dims: Tuple[int, int, int] = (240, 240, 155)     # (X, Y, Z)
+    stepSize: float = 0.05
+    nearT: float = 0.0
+    farT: float = 0.0
+    bgColor: Sequence[float] = (0.0, 0.0, 0.0)
+    volEnabled: Sequence[int] = (1, 1, 1, 1)
+    volWeight: Sequence[float] = (1.0, 1.0, 1.0, 1.0)
+    ww: float = 1.0
+    wl: float = 0.5
+    intensityAlpha: float = 0.4
+    gamma: float = 1.0
+    gradBoost: float = 1.5      # declared by the shader, never read
+    gradScale: float = 1.0      # declared by the shader, never read
+    showSeg: int = 0
+    showPred: int = 0
+    lutColorAlpha: np.ndarray = field(default_factory=default_label_lut)
+    # ---- extensions ----
+    ortho: int = 0
+    orthoHalfHeight: float = 1.0
+    ertThreshold: float = 0.01
+    maxSteps: int = 0
+    tMode: str = T_INDEXED
+    alphaMode: int = 0
+    skipEmpty: int = 1
+    tfMode: int = 0             # set by render(): 1 when a LUT tensor is passed
+
+    def validate(self):
+        W, H = self.imageSize
+        if W <= 0 or H <= 0:
+            raise ValueError(f"imageSize {self.imageSize} must be positive")
+        if not (self.ww > 0):
+            raise ValueError("ww must be > 0 (the reference's slider minimum is 0.01)")
+        if not (self.stepSize > 0):
+            raise ValueError("stepSize must be > 0")
+        if any(int(d) < 2 for d in self.dims):
+            raise ValueError(f"dims {self.dims} must be >= 2 per axis")
+        if self.tMode not in (T_INDEXED, T_ACCUMULATE):
+            raise ValueError(f"tMode {self.tMode!r} unknown")
+        if np.asarray(self.lutColorAlpha).shape != (8, 4):
+            raise ValueError("lutColorAlpha must be [8,4]")
+
+    def with_camera(self, cam) -> "RenderParams":
+        """Copy with eye/U/V/W/fov/ortho taken from a :class:`camera.Camera`."""
+        return replace(self, eye=_v3(cam.eye), U=_v3(cam.U), V=_v3(cam.V), W=_v3(cam.W), fovY=float(cam.fovY),
+                       ortho=int(cam.ortho), orthoHalfHeight=float(cam.ortho_half_height))
+
+    def to_struct(self) -> MrtParams:
+        self.validate()
+        s = MrtParams()
+        s.imageSize[0], s.imageSize[1] = int(self.imageSize[0]), int(self.imageSize[1])
+        s.fovY = float(self.fovY)
+        for name in ("eye", "U", "V", "W", "volMin", "voxelSize", "bgColor"):
+            arr = getattr(s, name)
+            for i, v in enumerate(_v3(getattr(self, name))):
+                arr[i] = v
+        for i in range(3):
+            s.dims[i] = int(self.dims[i])
+        s.stepSize, s.nearT, s.farT = float(self.stepSize), float(self.nearT), float(self.farT)
+        for i in range(4):
+            s.volEnabled[i] = 1 if int(self.volEnabled[i]) else 0
+            s.volWeight[i] = float(self.volWeight[i])
+        s.ww, s.wl, s.intensityAlpha = float(self.ww), float(self.wl), float(self.intensityAlpha)
+        s.gamma, s.gradBoost, s.gradScale = float(self.gamma), float(self.gradBoost), float(self.gradScale)
+        s.showSeg, s.showPred = int(bool(self.showSeg)), int(bool(self.showPred))
+        lut = np.asarray(self.lutColorAlpha, dtype=np.float32)
+        for i in range(8):
+            for j in range(4):
+                s.lutColorAlpha[i][j] = float(lut[i, j])
+        s.ortho = int(bool(self.ortho))
+        s.orthoHalfHeight = float(self.orthoHalfHeight)
+        s.ertThreshold = float(self.ertThreshold)
+        s.maxSteps = int(self.maxSteps)
+        s.tMode = 0 if self.tMode == T_INDEXED else 1
+        s.alphaMode = int(bool(self.alphaMode))
+        s.skipEmpty = int(bool(self.skipEmpty))
+        s.tfMode = int(bool(self.tfMode))
+        return s
+
+
+@dataclass
+class SlabParams:
+    """``struct Params`` of scripts/volumeRendering/volume_render.slang:9-21
+    (filled at scripts/volumeRendering/app.py:336-347: fov 72 deg, 64 steps, near 4.3, far 4.4)."""
+    imageSize: Tuple[int, int] = (512, 512)
+    fovY: float = math.radians(72.0)
+    stepCount: float = 64.0
+    nearPlane: float = 4.3
+    farPlane: float = 4.4
+    eye: Sequence[float] = (0.0, 0.0, -4.2)
+    U: Sequence[float] = (1.0, 0.0, 0.0)
+    V: Sequence[float] = (0.0, 1.0, 0.0)
+    W: Sequence[float] = (0.0, 0.0, 1.0)
+    volDim: Tuple[int, int, int] = (180, 216, 180)
+
+    def with_camera(self, cam) -> "SlabParams":
+        return replace(self, eye=_v3(cam.eye), U=_v3(cam.U), V=_v3(cam.V), W=_v3(cam.W))
+
+    def to_struct(self) -> MrtSlabParams:
+        s = MrtSlabParams()
+        s.imageSize[0], s.imageSize[1] = int(self.imageSize[0]), int(self.imageSize[1])
+        s.fovY, s.stepCount = float(self.fovY), float(self.stepCount)
+        s.nearPlane, s.farPlane = float(self.nearPlane), float(self.farPlane)
+        for name in ("eye", "U", "V", "W"):
+            arr = getattr(s, name)
+            for i, v in enumerate(_v3(getattr(self, name))):
+                arr[i] = v
+        for i in range(3):
+            s.volDim[i] = int(self.volDim[i])
+        return s

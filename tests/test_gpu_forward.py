@@ -1,0 +1,129 @@
+"""Forward parity: CUDA kernels (through the C ABI) vs the CPU-torch oracle — max-abs 1e-4."""
+import math
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+from mri_raytracer_b200 import api
+from mri_raytracer_b200.synth import ramp_tf
+from scenes import small_scene
+from parity import check_forward, O
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_both(vol, P, tf, lab=None, prd=None, dev="cuda"):
+    V = api.Volume(vol.to(dev), labels=None if lab is None else lab.to(dev), preds=None if prd is None else prd.to(dev))
+    tfd = None if tf is None else tf.to(dev)
+    img = api.render(V, None, tfd, P)
+    img2, T, counts = api.render_aux(V, None, tfd, P)
+    torch.cuda.synchronize()
+    return img, img2, T, counts
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 4])
+@pytest.mark.parametrize("use_tf", [False, True])
+def test_forward_matches_oracle(cuda, C, use_tf):
+    vol, _, P = small_scene(C=C, dims=(40, 36, 28), W=72, H=56, seed=C)
+    tf = ramp_tf(64) if use_tf else None
+    P = replace(P, intensityAlpha=25.0)
+    img, img2, T, counts = _render_both(vol, P, tf)
+    assert torch.equal(img, img2), "fast and counting kernel variants must agree bit-for-bit"
+    stats, ref, aux = check_forward(img, counts, vol, replace(P, tfMode=int(use_tf)), tf)
+    assert stats["max_abs"] <= 1e-4
+    assert stats["samples_taken"] == int(aux["n_taken"].sum()) or stats["n_flip"] > 0
+    assert (T.cpu() - aux["T"]).abs().max() <= 1e-4 or stats["n_flip"] > 0
+
+
+@pytest.mark.parametrize("ortho", [False, True])
+def test_skipping_is_exact(cuda, ortho):
+    vol, _, P = small_scene(C=4, dims=(64, 48, 40), W=96, H=80, seed=3, ortho=ortho)
+    tf = ramp_tf(256)
+    a, _, _, ca = _render_both(vol, replace(P, skipEmpty=1), tf)
+    b, _, _, cb = _render_both(vol, replace(P, skipEmpty=0), tf)
+    assert torch.equal(a, b), "empty-space skipping changed the image"
+    ca, cb = ca.cpu(), cb.cpu()
+    assert torch.equal(ca[..., :2], cb[..., :2])
+    assert int(ca[..., 2].sum()) < int(cb[..., 2].sum()), "skipping skipped nothing"
+    check_forward(a, ca, vol, replace(P, tfMode=1), tf)
+
+
+def test_labels_overlay(cuda):
+    vol, lab, P = small_scene(C=4, dims=(48, 40, 32), W=64, H=64, seed=5, labels=True)
+    assert int((lab > 0).sum()) > 0
+    prd = torch.roll(lab, shifts=2, dims=2).contiguous()
+    # sample label positions avoid exact .5 ties with overwhelming probability
+    P = replace(P, showSeg=1, showPred=1, intensityAlpha=5.0)
+    img, img2, T, counts = _render_both(vol, P, None, lab, prd)
+    assert torch.equal(img, img2)
+    stats, _, _ = check_forward(img, counts, vol, P, None, lab.long(), prd.long())
+    assert stats["max_abs"] <= 1e-4
+
+
+def test_accumulate_mode_and_gamma(cuda):
+    vol, _, P = small_scene(C=1, dims=(32, 32, 32), W=40, H=40, seed=2)
+    P = replace(P, tMode="accumulate", gamma=1.7, intensityAlpha=10.0)
+    V = api.Volume(vol.cuda())
+    img = api.render(V, None, None, P).cpu()
+    ref = O.render(vol, P)
+    # powf differs between libm and CUDA by a few ulp; still far inside the tolerance
+    assert (img - ref).abs().max() <= 1e-4
+
+
+def test_miss_inside_and_degenerate_rays(cuda):
+    vol, _, P = small_scene(C=1, dims=(24, 24, 24), W=33, H=17, seed=1)
+    tf = ramp_tf(32)
+    cases = [
+        replace(P, eye=(5.0, 5.0, 5.0), W=(1.0, 0.0, 0.0)),                       # every ray misses
+        replace(P, eye=(0.0, 0.0, 0.0)),                                           # eye inside the box
+        replace(P, eye=(0.0, 0.0, -3.0), U=(1, 0, 0), V=(0, 1, 0), W=(0, 0, 1), ortho=1, orthoHalfHeight=0.8),  # d.x=d.y=0
+        replace(P, nearT=1.9, farT=2.3),                                           # near/far clamp
+        replace(P, bgColor=(0.2, 0.3, 0.4), alphaMode=1),
+        replace(P, maxSteps=7),
+    ]
+    for Pc in cases:
+        img, img2, T, counts = _render_both(vol, Pc, tf)
+        stats, _, _ = check_forward(img, counts, vol, replace(Pc, tfMode=1), tf)
+        assert stats["max_abs"] <= 1e-4
+
+
+def test_ragged_image_sizes_and_tile_ranges(cuda):
+    vol, _, P0 = small_scene(C=2, dims=(24, 20, 16), W=8, H=8, seed=4)
+    V = api.Volume(vol.cuda())
+    for (W, H) in [(1, 1), (7, 3), (9, 17), (70, 33)]:
+        P = replace(P0, imageSize=(W, H))
+        full = api.render(V, None, None, P)
+        ref = O.render(vol, P)
+        assert (full.cpu() - ref).abs().max() <= 1e-4
+        # render in two disjoint tile ranges: union must equal the full frame bit-for-bit
+        from mri_raytracer_b200 import tiles
+        nt = tiles.tile_count(W, H)
+        out = torch.full((H, W, 4), -7.0, device="cuda")
+        for r in range(2):
+            api.render_forward(replace(P, tfMode=0), V.packed, V.C, None, V.active_bits(P, None), out=out,
+                               tile_range=tiles.rank_tile_range(nt, r, 2))
+        assert torch.equal(out, full)
+
+
+def test_render_host_entry_point(cuda):
+    vol, _, P = small_scene(C=4, dims=(32, 28, 24), W=40, H=32, seed=6)
+    tf = ramp_tf(128)
+    V = api.Volume(vol.cuda())
+    dev_img = api.render(V, None, tf.cuda(), P).cpu()
+    host_img = api.render_host(vol.numpy(), P, tf.numpy())
+    assert np.array_equal(host_img, dev_img.numpy())
+
+
+def test_bad_arguments_raise(cuda):
+    vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
+    V = api.Volume(vol.cuda())
+    with pytest.raises(RuntimeError):
+        api.render(vol, None, None, P)                      # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        api.render(V, None, None, replace(P, ww=0.0))
+    with pytest.raises(ValueError):
+        api.render(V, None, None, replace(P, dims=(8, 8, 8)))
+    with pytest.raises(api._lib.MrtError):
+        api.render_forward(replace(P, fovY=4.0), V.packed, V.C)
