@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the volume ray-march hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the one the metric is quoted on): synthetic BraTS-shaped
+4-modality 240x240x155 fp32 volume, 1024x1024 perspective (fov 70 deg), step 0.5 voxel,
+256-entry LUT transfer function, early ray termination at T <= 0.01 and occupancy-brick
+empty-space skipping.  One STEP = one orbit batch of `--views` frames (default 8,
+theta_k = 25 deg + k*360/V, phi = 80 deg).
+
+Metric: ray samples/s — the number of sample slots the ORACLE's definition of the frame
+evaluates (sum over rays of ceil((t1-t0)/dt) truncated by early termination; counted once by an
+untimed counting pass, so skipping cannot inflate it) divided by device time.  frames/s rides
+along.  `roofline` is computed from the samples the march kernel ACTUALLY evaluates (trilinear
+fetches really issued), see DESIGN.md §measurement.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks, L2 flushed between timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from dataclasses import replace
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+DIMS = (240, 240, 155)
+NCH = 4
+IMG = 1024
+TF_N = 256
+METRIC = "ray_samples_per_sec"
+UNIT = "samples/s"
+WORKLOAD = ("cfg2: synthetic BraTS 4-modality 240x240x155 fp32, 1024x1024 perspective fov70, step 0.5 voxel, "
+            "256-entry LUT TF, ERT 0.01, occupancy-brick skipping")
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _scene(views: int):
+    import numpy as np
+    from mri_raytracer_b200 import Camera, OrbitalCamera, RenderParams
+    from mri_raytracer_b200.synth import world_box
+    vs, vmin = world_box(DIMS)
+    ext = vs * np.asarray(DIMS, dtype=np.float32)
+    cam = OrbitalCamera(initial_radius=3.0, initial_theta=math.radians(25.0), initial_phi=math.radians(80.0))
+    cam.set_fov_degrees(70.0)
+    cam.target = (vmin + 0.5 * ext).astype(np.float32)
+    cam.radius = float(np.linalg.norm(ext) * 0.8)            # frame_volume, brats_viewer.py:320-324
+    cams = []
+    th0 = cam.theta
+    for k in range(views):
+        cam.theta = th0 + 2.0 * math.pi * k / views
+        cams.append(Camera.from_orbital(cam))
+    P = RenderParams(imageSize=(IMG, IMG), dims=DIMS, voxelSize=tuple(float(v) for v in vs),
+                     volMin=tuple(float(v) for v in vmin), stepSize=float(np.float32(0.5) * vs[0]),
+                     skipEmpty=1, tfMode=1)
+    return P, cams
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_sample(stride: int, threads: int):
+    """The reference CPU path = the CPU-torch oracle, on a bounded sample:
+    every `stride`-th pixel in x and y of view 0.  Returns (samples_taken, callable)."""
+    import torch
+    from oracle import oracle_torch as O
+    from mri_raytracer_b200.synth import make_brats_like, ramp_tf
+    torch.set_num_threads(threads)
+    vol = make_brats_like(NCH, DIMS, seed=0)
+    tf = ramp_tf(TF_N)
+    P, cams = _scene(8)
+    P0 = P.with_camera(cams[0])
+    ys, xs = torch.meshgrid(torch.arange(0, IMG, stride), torch.arange(0, IMG, stride), indexing="ij")
+    px, py = xs.reshape(-1), ys.reshape(-1)
+
+    def run():
+        _, aux = O.render(vol, P0, tf=tf, pixels=(px, py), return_aux=True)
+        return int(aux["n_taken"].sum())
+    return run, f"view 0, every {stride}th pixel in x and y ({px.numel()} of {IMG * IMG} rays), CPU-torch oracle fp32"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    run, sample = cpu_reference_sample(stride=4, threads=threads)
+    for _ in range(max(args.warmup, 1)):
+        n = run()
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        tot += run()
+    dt = time.perf_counter() - t0
+    val = tot / dt
+    frames = args.steps / 16.0 / dt           # one step = 1/16 of a frame's rays
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": sample},
+        "frames_per_sec_equiv": frames,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mri_raytracer_b200 import api, build, tiles
+    from mri_raytracer_b200 import dist as mdist
+    from mri_raytracer_b200.synth import make_brats_like, ramp_tf
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    V = args.views
+    P, cams = _scene(V)
+    vol_host = make_brats_like(NCH, DIMS, seed=0).pin_memory()
+    tf_host = ramp_tf(TF_N)
+    vol = vol_host.to(dev, non_blocking=True)
+    tf = tf_host.to(dev)
+    volume = api.Volume(vol)
+    W = H = IMG
+    nt = tiles.tile_count(W, H)
+    mode = args.mode if world > 1 else "views"
+    if mode == "views" and V % world != 0:
+        raise SystemExit(f"--views {V} must be divisible by the number of GPUs {world}")
+
+    # ---- untimed counting pass: the oracle-defined sample count of every view (rank 0 counts all)
+    taken = evaluated = clip = 0
+    per_view_eval = []
+    for c in cams:
+        _, _, counts = api.render_aux(volume, c, tf, P)
+        s = counts.sum(dim=(0, 1)).tolist()
+        clip += s[0]; taken += s[1]; evaluated += s[2]
+        per_view_eval.append(s[2])
+    torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    frames = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+    kern_ev = []
+
+    def step(record_kernels: bool):
+        """One orbit batch through the public API; returns nothing (frames land in `frames`)."""
+        if world == 1:
+            for v, c in enumerate(cams):
+                Pv = P.with_camera(c)
+                bits = volume.active_bits(Pv, tf)
+                if record_kernels:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                api.render_forward(Pv, volume.packed, volume.C, tf, bits, out=frames[v])
+                if record_kernels:
+                    b.record(); kern_ev.append((a, b, v))
+        else:
+            mdist.render_views(volume, cams, tf, P, mode=mode)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                                # L2 flush, outside the timed events
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(True)
+        b.record()
+        barrier()
+        step_ms.append(a.elapsed_time(b))
+    clocks = sampler.stop() if rank == 0 else None
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_s = float(tot_ms) / 1e3
+    value = taken * args.steps / tot_s
+
+    # ---- roofline of the dominant kernel (march), from live CUDA-event launch durations
+    roof = None
+    if kern_ev:
+        durs = [a.elapsed_time(b) for a, b, _ in kern_ev]
+        avg_ms = sum(durs) / len(durs)
+        avg_eval = sum(per_view_eval[v] for _, _, v in kern_ev) / len(kern_ev)
+        bytes_per_sample = 32 * NCH                                   # 8 corners x 4 B x C
+        achieved = avg_eval * bytes_per_sample / (avg_ms * 1e-3) / 1e9
+        peak, which = _peaks()
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("mrt_fwd_kernel_dram_bytes_per_launch")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": which, "kernel": "mrt_fwd_kernel<4,false,true,false>",
+                "avg_launch_ms": avg_ms, "bytes_per_sample": bytes_per_sample,
+                "evaluated_samples_per_launch": avg_eval,
+                "nominal_samples_per_launch": taken / V,
+                "note": "achieved counts only samples whose 8 corner fetches were really issued; "
+                        "the nominal (oracle-defined) count includes slots skipped as provably empty"}
+
+    # ---- e2e: host buffers in, host frames out, through the public API (N = 1 path)
+    e2e = None
+    if world == 1:
+        out_host = torch.empty((V, H, W, 4), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+
+        def e2e_step():
+            d_vol = vol_host.to(dev, non_blocking=True)               # H2D: the step's input volume
+            d_tf = tf_host.to(dev, non_blocking=True)
+            Vd = api.Volume(d_vol)                                    # pack + occupancy build
+            for v, c in enumerate(cams):
+                img = api.render(Vd, c, d_tf, P)
+                frames[v].copy_(img)
+                ev = torch.cuda.Event(); ev.record()
+                with torch.cuda.stream(copy_stream):                  # D2H overlaps the next view
+                    copy_stream.wait_event(ev)
+                    out_host[v].copy_(frames[v], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        ks = max(3, min(args.steps, 10))
+        t_e2e = 0.0
+        for _ in range(ks):
+            flush.fill_(1); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            t_e2e += time.perf_counter() - t0
+        e2e = {"value": taken * ks / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(vol_host.numel() * 4 + tf_host.numel() * 4 + V * 400),
+               "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": 1e3 * t_e2e / ks,
+               "frames_per_sec": V * ks / t_e2e,
+               "what": "per step: pinned-host volume H2D + pack + occupancy build + V x (classify, march) + "
+                       "V frames D2H to pinned host, wall clock with synchronize on both sides"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        run, sample = cpu_reference_sample(stride=2, threads=threads)
+        t0 = time.perf_counter()
+        n = run()
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step": V, "partition": mode if world > 1 else "single GPU",
+                       "l2": "flushed (256 MiB write) between timed steps; volume 142.8 MB > 126 MB L2"},
+            "frames_per_sec": V * args.steps / tot_s,
+            "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": 2 * V * args.steps if world == 1 else 2 * V * args.steps // world,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views", type=int, default=8, help="frames per step (orbit batch)")
+    ap.add_argument("--mode", default="views", choices=["views", "tiles"], help="multi-GPU partition")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

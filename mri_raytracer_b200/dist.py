@@ -1,0 +1,180 @@
+"""Multi-GPU rendering: one process per GPU (torch.distributed), SURVEY.md §8(e).
+
+The reference is single-GPU; these two modes are what BASELINE.json's north_star adds:
+
+* image space (``render_views``): the volume, TF and occupancy grid are replicated; a batch of
+  views is split over ranks either by whole views (``mode="views"``) or by contiguous
+  screen-space tile rows of every view (``mode="tiles"``, the integer map of tiles.py); the
+  framebuffer is gathered with ONE ``all_gather_into_tensor`` per batch (NCCL over NVLink).
+  Rays are independent, so there is no other exchange.
+* sort-last (``render_sort_last``): the volume is split into axis-aligned sub-boxes (+1 voxel
+  halo so trilinear sampling at the cut faces is exact); each rank marches every ray through
+  its own sub-box only, producing premultiplied colour + transmittance; image strips are
+  exchanged with ``all_to_all_single`` and composited front-to-back in visibility order
+  (``mrt_composite_over``), then the finished strips are all-gathered.
+
+Both take an optional ``render_fn`` so the host logic can be exercised on CPU with the gloo
+backend (tests/test_dist_gloo.py injects the oracle there); the default is the CUDA path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import replace
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import tiles
+from .params import RenderParams
+
+
+def _world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _default_render_fn(volume, tf):
+    from . import api
+
+    def fn(P: RenderParams, tile_range: Tuple[int, int], out: torch.Tensor):
+        P = replace(P, tfMode=1 if tf is not None else 0)
+        bits = volume.active_bits(P, tf)
+        api.render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds, out=out,
+                           tile_range=tile_range)
+    return fn
+
+
+# ----------------------------------------------------------------------------- image space
+def view_partition(n_views: int, rank: int, nranks: int) -> Tuple[int, int]:
+    """Whole-view split (needs n_views % nranks == 0 for the single fused gather)."""
+    return (rank * n_views) // nranks, ((rank + 1) * n_views) // nranks
+
+
+def padded_rows(H: int, nranks: int) -> int:
+    """Rows per rank in the gather buffer: whole tile rows, padded so every rank is equal."""
+    ty = tiles.tiles_y(H)
+    return ((ty + nranks - 1) // nranks) * tiles.TILE
+
+
+def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views", group=None,
+                 render_fn: Optional[Callable] = None, device=None, gather: bool = True) -> torch.Tensor:
+    """Render ``len(cams)`` views of one volume across all ranks -> ``[V,H,W,4]`` on every rank
+    (``gather=False``: only this rank's part is valid; used to time compute alone)."""
+    rank, R = _world(group)
+    W, H = P.imageSize
+    V = len(cams)
+    fn = render_fn or _default_render_fn(volume, tf)
+    device = device if device is not None else (volume.packed.device if hasattr(volume, "packed") else "cpu")
+    nt = tiles.tile_count(W, H)
+    if mode == "views":
+        if V % R != 0:
+            raise ValueError(f"mode='views' needs len(cams) ({V}) divisible by world size ({R})")
+        out = torch.empty((V, H, W, 4), dtype=torch.float32, device=device)
+        v0, v1 = view_partition(V, rank, R)
+        for v in range(v0, v1):
+            fn(P.with_camera(cams[v]), (0, nt), out[v])
+        if R > 1 and gather:
+            dist.all_gather_into_tensor(out.view(-1), out[v0:v1].reshape(-1), group=group)
+        return out
+    if mode == "tiles":
+        rows = padded_rows(H, R)
+        tx = tiles.tiles_x(W)
+        # rank r owns tile rows [r*rows/8, (r+1)*rows/8) of every view (clipped to the image)
+        buf = torch.zeros((R, V, rows, W, 4), dtype=torch.float32, device=device)
+        tr0 = min(rank * (rows // tiles.TILE), tiles.tiles_y(H))
+        tr1 = min((rank + 1) * (rows // tiles.TILE), tiles.tiles_y(H))
+        y0, y1 = tr0 * tiles.TILE, min(tr1 * tiles.TILE, H)
+        if tr1 > tr0:
+            full = torch.empty((H, W, 4), dtype=torch.float32, device=device)
+            for v in range(V):
+                fn(P.with_camera(cams[v]), (tr0 * tx, tr1 * tx), full)
+                buf[rank, v, : y1 - y0] = full[y0:y1]
+        if R > 1 and gather:
+            dist.all_gather_into_tensor(buf.view(-1), buf[rank].reshape(-1), group=group)
+        # [R,V,rows,W,4] -> [V, R*rows, W, 4] -> crop
+        img = buf.permute(1, 0, 2, 3, 4).reshape(V, R * rows, W, 4)[:, :H]
+        return img.contiguous()
+    raise ValueError(f"unknown mode {mode!r}")
+
+
+# ----------------------------------------------------------------------------- sort-last
+def shard_grid(nranks: int) -> Tuple[int, int, int]:
+    """Sub-box grid (gx,gy,gz) with gx*gy*gz == nranks, as cubic as possible (8 -> 2x2x2)."""
+    g = [1, 1, 1]
+    n = nranks
+    ax = 2
+    while n > 1:
+        p = next(q for q in (2, 3, 5, 7, 11, 13) if n % q == 0) if any(n % q == 0 for q in (2, 3, 5, 7, 11, 13)) else n
+        g[ax] *= p
+        n //= p
+        ax = (ax - 1) % 3
+    return g[0], g[1], g[2]
+
+
+def shard_box(dims: Tuple[int, int, int], grid: Tuple[int, int, int], rank: int):
+    """Voxel range of ``rank``'s sub-box: cells [lo, hi) per axis, i.e. voxels [lo, hi] inclusive
+    (the +1 halo voxel makes trilinear sampling inside the cell range exact).  Returns
+    (lo[3], hi[3]) in (x,y,z) order and the shard's grid coordinate."""
+    gx, gy, gz = grid
+    cx, cy, cz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
+    lo, hi = [], []
+    for c, g, d in ((cx, gx, dims[0]), (cy, gy, dims[1]), (cz, gz, dims[2])):
+        cells = d - 1                                   # trilinear cells along this axis
+        a, b = (c * cells) // g, ((c + 1) * cells) // g
+        lo.append(a)
+        hi.append(b)
+    return tuple(lo), tuple(hi), (cx, cy, cz)
+
+
+def visibility_order(eye: np.ndarray, P: RenderParams, grid: Tuple[int, int, int]) -> List[int]:
+    """Front-to-back order of the sub-boxes for a pinhole eye (or an ortho direction): along
+    each axis the slab containing the eye comes first, then slabs by increasing distance; the
+    lexicographic combination is a valid visibility order for an axis-aligned grid."""
+    dims = P.dims
+    vs = np.asarray(P.voxelSize, dtype=np.float64)
+    vmin = np.asarray(P.volMin, dtype=np.float64)
+    keys = []
+    for r in range(grid[0] * grid[1] * grid[2]):
+        lo, hi, _ = shard_box(dims, grid, r)
+        d = 0.0
+        k = []
+        for a in range(3):
+            if P.ortho:
+                # parallel rays along W: order by the slab centre projected on the view direction
+                c = vmin[a] + 0.5 * (lo[a] + hi[a]) * vs[a]
+                k.append(c * float(np.asarray(P.W, dtype=np.float64)[a]))
+            else:
+                a0, a1 = vmin[a] + lo[a] * vs[a], vmin[a] + hi[a] * vs[a]
+                e = float(eye[a])
+                k.append(0.0 if a0 <= e <= a1 else min(abs(e - a0), abs(e - a1)))
+        keys.append((sum(k) if P.ortho else 0.0, tuple(k) if not P.ortho else (), r))
+    if P.ortho:
+        return [r for _, _, r in sorted(keys)]
+    # per-axis rank of each slab, then sort boxes by the tuple of per-axis ranks
+    return [r for _, _, r in sorted(keys, key=lambda t: (t[1], t[2]))]
+
+
+def shard_params(P: RenderParams, lo, hi) -> RenderParams:
+    """RenderParams of a sub-box: dims = hi-lo+1 voxels, volMin shifted by lo voxels.  The
+    sub-box spans cells [lo,hi) exactly: its world extent is (hi-lo)*voxelSize, which is what
+    `dims*voxelSize` would overstate by one voxel, so the far faces are clamped via the
+    shard's own clip box (see render_sort_last)."""
+    vs = np.asarray(P.voxelSize, dtype=np.float32)
+    vmin = np.asarray(P.volMin, dtype=np.float32) + vs * np.asarray(lo, dtype=np.float32)
+    dims = tuple(int(h - l + 1) for l, h in zip(lo, hi))
+    return replace(P, dims=dims, volMin=tuple(float(v) for v in vmin))
+
+
+def composite_over_torch(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:
+    """Reference composite in torch (CPU tests): partials [K,npix,4] = (premult rgb, T)."""
+    C = torch.zeros_like(partials[0, :, :3])
+    T = torch.ones_like(partials[0, :, 3])
+    for k in order:
+        C = C + T[:, None] * partials[k, :, :3]
+        T = T * partials[k, :, 3]
+    bgv = torch.as_tensor(bg, dtype=C.dtype, device=C.device)
+    a = (1.0 - T) if alpha_mode else torch.ones_like(T)
+    return torch.cat([bgv[None, :] + C, a[:, None]], dim=1)
