@@ -221,7 +221,7 @@ def run_ours(args):
         if world == 1:
             for v, c in enumerate(cams):
                 Pv = P.with_camera(c)
-                bits = volume.active_bits(Pv, tf)
+                bits = volume.skip_levels(Pv, tf)
                 if record_kernels:
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()

@@ -128,11 +128,14 @@ int mrt_tile_index_map(int32_t W, int32_t H, int32_t* out_tile, int32_t* out_lan
 
 /* ------------------------------------------------ volume layout
  * Planar [C][Z][Y][X] fp32 (the reference's one-buffer-per-modality flatten,
- * brats_viewer.py:64) -> the packed layout the sampler reads:
- *   C == 1 : [Z][Y][X] float        (packed may alias planar; the call is then a no-op)
- *   C == 2 : [Z][Y][X] float2
- *   C == 3,4 : [Z][Y][X] float4     (missing channel = 0)
- * One LDG.128 per trilinear corner fetches all modalities. */
+ * brats_viewer.py:64) -> the packed layout the sampler reads: channel-interleaved voxels
+ *   C == 1 : float,  C == 2 : float2,  C == 3,4 : float4 (missing channel = 0)
+ * so ONE vector load per trilinear corner fetches all modalities, at element index
+ *   x + pitchY*y + pitchZ*z      (pitchY >= X, pitchZ >= pitchY*Y, in voxels).
+ * The pitches are skewed (pitchY = S/4, pitchZ = S/2 modulo S, S = voxels per 128-byte line)
+ * so that the 2x2x2 neighbourhoods a warp gathers fall into distinct L1 data banks; the
+ * padding voxels are never read.  mrt_packed_layout is the single source of the pitches. */
+void mrt_packed_layout(int32_t C, int32_t X, int32_t Y, int32_t Z, int64_t* pitchY, int64_t* pitchZ);
 size_t mrt_packed_volume_bytes(int32_t C, int32_t X, int32_t Y, int32_t Z);
 int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, int32_t Z,
                         void* packed, void* stream);
@@ -151,25 +154,29 @@ int mrt_build_occupancy(const void* packed, int32_t C, int32_t X, int32_t Y, int
                         float* minmax, void* stream);
 int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32_t Z,
                               uint8_t* label_any, void* stream);
-/* Per-frame classification: bit b of `active_bits` (uint32 words, ceil(nbricks/32)) is 0
- * only if every sample in brick b is provably a no-op under (params, tf, labels). */
+/* Per-frame classification into a skip-level byte per brick:
+ *   0 : active (some sample in the brick may contribute);
+ *   l in 1..4 : the aligned cell of 2^(l-1) bricks per axis (8,16,32,64 voxels) that contains
+ *               this brick is provably empty under (params, tf, labels): every sample slot
+ *               whose trilinear base index lies in it is a no-op, so the march may leap to
+ *               the cell's exit. */
 int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C,
                         const float* tf, int32_t tfN,
                         const uint8_t* seg_any, const uint8_t* pred_any,
-                        uint32_t* active_bits, void* stream);
+                        uint8_t* skip_levels, void* stream);
 
 /* ------------------------------------------------ forward
  * Renders tiles [tile_begin, tile_end) of the [H][W] image (tile ids as above).
  *   packed      : packed volume (see mrt_pack_volume_f32), C = logical channel count (1..4)
  *   tf, tfN     : LUT [tfN][4] (r,g,b,sigma) fp32, used when params->tfMode == 1
- *   active_bits : from mrt_classify_bricks, or NULL (then skipEmpty is ignored)
+ *   skip_levels : uint8[nbricks] from mrt_classify_bricks, or NULL (then skipEmpty is ignored)
  *   labels/preds: optional int32 [Z][Y][X] (gLabels / gPreds), used when showSeg / showPred
  *   out_rgba    : float4 [H][W]  (row 0 = top)
  *   out_T       : optional float [H][W], final transmittance
  *   out_counts  : optional int32 [H][W][4] = (n_clip, n_taken, n_evaluated, n_segments)
  */
 int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C,
-                       const float* tf, int32_t tfN, const uint32_t* active_bits,
+                       const float* tf, int32_t tfN, const uint8_t* skip_levels,
                        const int32_t* labels, const int32_t* preds,
                        float* out_rgba, float* out_T, int32_t* out_counts,
                        int32_t tile_begin, int32_t tile_end, void* stream);

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "mrt_lane_of_pixel": (_i32, [_i32, _i32]),
     "mrt_rank_tile_range": (None, [_i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "mrt_tile_index_map": (C.c_int, [_i32, _i32, _vp, _vp, _vp]),
+    "mrt_packed_layout": (None, [_i32, _i32, _i32, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mrt_packed_volume_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mrt_pack_volume_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mrt_unpack_volume_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),

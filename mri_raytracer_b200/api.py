@@ -48,32 +48,39 @@ def packed_channels(Cn: int) -> int:
 
 
 # ----------------------------------------------------------------------------- low level
+def packed_layout(Cn: int, dims) -> Tuple[int, int]:
+    """(pitchY, pitchZ) in voxels of the packed layout (``mrt_packed_layout``)."""
+    X, Y, Z = dims
+    py, pz = C.c_int64(), C.c_int64()
+    lib().mrt_packed_layout(Cn, X, Y, Z, C.byref(py), C.byref(pz))
+    return int(py.value), int(pz.value)
+
+
 def pack_volume(planar: torch.Tensor) -> torch.Tensor:
-    """[C,Z,Y,X] fp32 -> packed [Z,Y,X,Cp] (Cp = 1,2,4).  C == 1 aliases the input."""
+    """[C,Z,Y,X] fp32 -> packed, channel-interleaved, bank-skewed layout (flat fp32 buffer;
+    voxel (x,y,z) at element ``(x + pitchY*y + pitchZ*z) * Cp``, Cp = 1,2,4)."""
     _need_cuda(planar, "volume", torch.float32)
     Cn, Z, Y, X = planar.shape
-    pc = packed_channels(Cn)
-    if pc == 1:
-        return planar.reshape(Z, Y, X, 1)
-    packed = torch.empty((Z, Y, X, pc), dtype=torch.float32, device=planar.device)
+    nbytes = lib().mrt_packed_volume_bytes(Cn, X, Y, Z)
+    if nbytes == 0:
+        raise ValueError(f"volume shape {tuple(planar.shape)} unsupported")
+    packed = torch.zeros((nbytes // 4,), dtype=torch.float32, device=planar.device)
     check(lib().mrt_pack_volume_f32(planar.data_ptr(), Cn, X, Y, Z, packed.data_ptr(), _stream()), "pack_volume")
     return packed
 
 
-def unpack_volume(packed: torch.Tensor, Cn: int) -> torch.Tensor:
-    Z, Y, X, pc = packed.shape
-    if pc == 1:
-        return packed.reshape(1, Z, Y, X)
+def unpack_volume(packed: torch.Tensor, Cn: int, dims) -> torch.Tensor:
+    X, Y, Z = dims
     planar = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=packed.device)
     check(lib().mrt_unpack_volume_f32(packed.data_ptr(), Cn, X, Y, Z, planar.data_ptr(), _stream()), "unpack_volume")
     return planar
 
 
-def build_occupancy(packed: torch.Tensor, Cn: int) -> torch.Tensor:
+def build_occupancy(packed: torch.Tensor, Cn: int, dims) -> torch.Tensor:
     """Per-brick (min,max) per packed channel: float32 [nbricks, Cp, 2]."""
-    Z, Y, X, pc = packed.shape
+    X, Y, Z = dims
     nb = lib().mrt_brick_count(X, Y, Z)
-    mm = torch.empty((nb, pc, 2), dtype=torch.float32, device=packed.device)
+    mm = torch.empty((nb, packed_channels(Cn), 2), dtype=torch.float32, device=packed.device)
     check(lib().mrt_build_occupancy(packed.data_ptr(), Cn, X, Y, Z, mm.data_ptr(), _stream()), "build_occupancy")
     return mm
 
@@ -93,7 +100,7 @@ def classify_bricks(P: RenderParams, minmax: torch.Tensor, Cn: int, tf: Optional
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb = minmax.shape[0]
     if out is None:
-        out = torch.empty(((nb + 31) // 32,), dtype=torch.int32, device=minmax.device)
+        out = torch.empty((nb,), dtype=torch.uint8, device=minmax.device)
     s = P.to_struct()
     check(lib().mrt_classify_bricks(C.byref(s), minmax.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
                                     _ptr(seg_any), _ptr(pred_any), out.data_ptr(), _stream()), "classify_bricks")
@@ -101,7 +108,7 @@ def classify_bricks(P: RenderParams, minmax: torch.Tensor, Cn: int, tf: Optional
 
 
 def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor] = None,
-                   active_bits: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                   skip_levels: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
                    preds: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                    out_T: Optional[torch.Tensor] = None, out_counts: Optional[torch.Tensor] = None,
                    tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
@@ -112,7 +119,7 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     s = P.to_struct()
     check(lib().mrt_render_forward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
-                                   _ptr(active_bits), _ptr(labels), _ptr(preds), out.data_ptr(), _ptr(out_T),
+                                   _ptr(skip_levels), _ptr(labels), _ptr(preds), out.data_ptr(), _ptr(out_T),
                                    _ptr(out_counts), t0, t1, _stream()), "render_forward")
     return out
 
@@ -149,7 +156,7 @@ class Volume:
         Z, Y, X = (int(v) for v in planar.shape[1:])
         self.dims = (X, Y, Z)
         self.packed = pack_volume(planar)
-        self.minmax = build_occupancy(self.packed, self.C) if occupancy else None
+        self.minmax = build_occupancy(self.packed, self.C, self.dims) if occupancy else None
         self.labels = self.preds = self.seg_any = self.pred_any = None
         self.set_labels(labels)
         self.set_preds(preds)
@@ -188,12 +195,13 @@ class Volume:
         cam.radius = float(np.linalg.norm(ext) * 0.8)
         return cam
 
-    def active_bits(self, P: RenderParams, tf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    def skip_levels(self, P: RenderParams, tf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Per-frame skip-level byte per brick (``mrt_classify_bricks``), or None if skipping is off."""
         if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
             return None
         nb = self.minmax.shape[0]
         if self._bits is None:
-            self._bits = torch.empty(((nb + 31) // 32,), dtype=torch.int32, device=self.packed.device)
+            self._bits = torch.empty((nb,), dtype=torch.uint8, device=self.packed.device)
         return classify_bricks(P, self.minmax, self.C, tf, self.seg_any, self.pred_any, out=self._bits)
 
 
@@ -205,7 +213,7 @@ class _RenderFn(torch.autograd.Function):
         packed = pack_volume(planar.detach())
         bits = None
         if P.skipEmpty and P.tMode == "indexed":
-            mm = build_occupancy(packed, Cn)
+            mm = build_occupancy(packed, Cn, P.dims)
             seg_any = build_label_occupancy(labels) if (labels is not None and P.showSeg) else None
             pred_any = build_label_occupancy(preds) if (preds is not None and P.showPred) else None
             bits = classify_bricks(P, mm, Cn, tf, seg_any, pred_any)
@@ -223,7 +231,7 @@ class _RenderFn(torch.autograd.Function):
         want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
         dvol, dtf = render_backward(ctx.P, packed, ctx.Cn, tf, ctx.labels, ctx.preds, out,
                                     g.contiguous(), want_dvol=want_vol, want_dtf=want_tf)
-        gvol = unpack_volume(dvol, ctx.Cn) if want_vol else None
+        gvol = unpack_volume(dvol, ctx.Cn, ctx.P.dims) if want_vol else None
         return gvol, (dtf if want_tf else None), None, None, None
 
 
@@ -252,7 +260,7 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
             raise ValueError(f"params.dims {P.dims} != volume dims {V.dims}")
         lab = labels if labels is not None else V.labels
         prd = preds if preds is not None else V.preds
-        bits = V.active_bits(P, tf)
+        bits = V.skip_levels(P, tf)
         return render_forward(P, V.packed, V.C, tf, bits, lab, prd)
     _need_cuda(volume, "volume", torch.float32)
     if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
@@ -277,7 +285,7 @@ def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tens
     dev = volume.packed.device
     out_T = torch.empty((H, W), dtype=torch.float32, device=dev)
     counts = torch.zeros((H, W, 4), dtype=torch.int32, device=dev)
-    bits = volume.active_bits(P, tf)
+    bits = volume.skip_levels(P, tf)
     img = render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds,
                          out_T=out_T, out_counts=counts)
     return img, out_T, counts

@@ -64,7 +64,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
   int px = -1, py = -1;
   bool live = tile < P.tile_end;
   if (live) {
-    mrt_pixel_of_tile_lane_(tile, ((warp & 1) << 5) + lane, P.W, &px, &py);
+    mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
     live = (px < P.W && py < P.H);
   }
 
@@ -80,7 +80,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
       const IdxRay q = mrt_index_ray(P, ray);
       const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
       const float dt = P.dt, thr = P.thr;
-      const uint32_t sY = (uint32_t)P.dims[0], sZ = sY * (uint32_t)P.dims[1];
+      const uint32_t sY = P.pitchY, sZ = P.pitchZ;
       float T = 1.0f, prefix = 0.0f;
       int k = 0;
       float t_run = ray.t0;

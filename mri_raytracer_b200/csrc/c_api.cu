@@ -48,15 +48,22 @@ int mrt_tile_index_map(int32_t W, int32_t H, int32_t* out_tile, int32_t* out_lan
 }
 
 // ---------------------------------------------------------------- layout
+void mrt_packed_layout(int32_t C, int32_t X, int32_t Y, int32_t Z, int64_t* pitchY, int64_t* pitchZ) {
+  mrt_layout(mrt_packed_channels(C), X, Y, Z, pitchY, pitchZ);
+}
 size_t mrt_packed_volume_bytes(int32_t C, int32_t X, int32_t Y, int32_t Z) {
   if (C < 1 || C > 4 || X < 1 || Y < 1 || Z < 1) return 0;
-  return (size_t)X * Y * Z * sizeof(float) * mrt_packed_channels(C);
+  int64_t pY, pZ;
+  mrt_layout(mrt_packed_channels(C), X, Y, Z, &pY, &pZ);
+  return (size_t)pZ * Z * sizeof(float) * mrt_packed_channels(C);
 }
 static int check_dims(const char* who, int C, int X, int Y, int Z) {
   MRT_REQUIRE(C >= 1 && C <= 4, "%s: C=%d outside 1..4", who, C);
   // dims-1.001 clamp (brats_rt.slang:62) needs >= 2 voxels per axis
   MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
-  MRT_REQUIRE((uint64_t)X * Y * Z < (1ull << 32), "%s: more than 2^32 voxels per shard (SURVEY Q14)", who);
+  int64_t pY, pZ;
+  mrt_layout(mrt_packed_channels(C), X, Y, Z, &pY, &pZ);
+  MRT_REQUIRE((uint64_t)pZ * Z < (1ull << 32), "%s: more than 2^32 voxels per shard (SURVEY Q14)", who);
   return MRT_OK;
 }
 int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream) {
@@ -85,6 +92,11 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(M->voxelSize[i] > 0.0f, "voxelSize[%d] must be > 0", i);
   }
   if (int r = check_dims("render", C, K->dims[0], K->dims[1], K->dims[2])) return r;
+  {
+    int64_t pY, pZ;
+    mrt_layout(mrt_packed_channels(C), K->dims[0], K->dims[1], K->dims[2], &pY, &pZ);
+    K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
+  }
   // tan evaluated once in double, rounded to float (documented deviation from the per-thread fp32 tan)
   K->ortho = M->ortho ? 1 : 0;
   K->halfH = M->orthoHalfHeight;
@@ -145,28 +157,28 @@ int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_label_occupancy");
 }
 int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C, const float* tf, int32_t tfN,
-                        const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* active_bits, void* stream) {
-  MRT_REQUIRE(minmax && active_bits, "classify_bricks: null pointer");
+                        const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* skip_levels, void* stream) {
+  MRT_REQUIRE(minmax && skip_levels, "classify_bricks: null pointer");
   KParams K;
   if (int r = derive(params, C, tfN, true, 0, 0, &K)) return r;
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "classify_bricks: tfMode=1 needs tf");
-  cudaError_t e = mrt_launch_classify(K, minmax, mrt_packed_channels(C), tf, seg_any, pred_any, active_bits,
+  cudaError_t e = mrt_launch_classify(K, minmax, mrt_packed_channels(C), tf, seg_any, pred_any, skip_levels,
                                       (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "classify_bricks");
 }
 
 // ---------------------------------------------------------------- forward / backward
 int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
-                       const uint32_t* active_bits, const int32_t* labels, const int32_t* preds,
+                       const uint8_t* skip_levels, const int32_t* labels, const int32_t* preds,
                        float* out_rgba, float* out_T, int32_t* out_counts,
                        int32_t tile_begin, int32_t tile_end, void* stream) {
   MRT_REQUIRE(packed && out_rgba, "render_forward: null volume or output");
   KParams K;
-  if (int r = derive(params, C, tfN, active_bits != nullptr, tile_begin, tile_end, &K)) return r;
+  if (int r = derive(params, C, tfN, skip_levels != nullptr, tile_begin, tile_end, &K)) return r;
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward: tfMode=1 needs tf");
   if (K.showSeg && !labels) K.showSeg = 0;                  // brats_viewer.py:423 (showSeg only with a buffer)
   if (K.showPred && !preds) K.showPred = 0;                 // brats_viewer.py:424
-  cudaError_t e = mrt_launch_forward(K, mrt_packed_channels(C), packed, tf, active_bits, labels, preds,
+  cudaError_t e = mrt_launch_forward(K, mrt_packed_channels(C), packed, tf, skip_levels, labels, preds,
                                      out_rgba, out_T, out_counts, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
 }
@@ -255,15 +267,16 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
   void* d_packed = nullptr;
   int32_t *d_lab = nullptr, *d_pred = nullptr;
   uint8_t *d_seg_any = nullptr, *d_pred_any = nullptr;
-  uint32_t* d_bits = nullptr;
+  uint8_t* d_bits = nullptr;
+  const size_t packed_bytes = mrt_packed_volume_bytes(C, X, Y, Z);
   MrtParams P = *params;
   const bool useSeg = P.showSeg && labels_host, usePred = P.showPred && preds_host;
   P.showSeg = useSeg; P.showPred = usePred;
   MRT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   MRT_CUDA(cudaMallocAsync(&d_planar, nvox * C * sizeof(float), st));
   MRT_CUDA(cudaMemcpyAsync(d_planar, planar_host, nvox * C * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (pc == 1) d_packed = d_planar;
-  else MRT_CUDA(cudaMallocAsync(&d_packed, nvox * pc * sizeof(float), st));
+  MRT_CUDA(cudaMallocAsync(&d_packed, packed_bytes, st));
+  MRT_CUDA(cudaMemsetAsync(d_packed, 0, packed_bytes, st));
   MRT_CALL(mrt_pack_volume_f32(d_planar, C, X, Y, Z, d_packed, st));
   if (P.tfMode) {
     MRT_CUDA(cudaMallocAsync(&d_tf, (size_t)tfN * 4 * sizeof(float), st));
@@ -280,7 +293,7 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
   MRT_CUDA(cudaMallocAsync(&d_out, npix * 4 * sizeof(float), st));
   if (P.skipEmpty && P.tMode == 0) {
     MRT_CUDA(cudaMallocAsync(&d_minmax, (size_t)nb * pc * 2 * sizeof(float), st));
-    MRT_CUDA(cudaMallocAsync(&d_bits, (size_t)((nb + 31) / 32) * sizeof(uint32_t), st));
+    MRT_CUDA(cudaMallocAsync(&d_bits, (size_t)nb, st));
     MRT_CALL(mrt_build_occupancy(d_packed, C, X, Y, Z, d_minmax, st));
     if (useSeg) {
       MRT_CUDA(cudaMallocAsync(&d_seg_any, nb, st));
@@ -298,7 +311,7 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
   MRT_CUDA(cudaStreamSynchronize(st));
 done:
   if (st) {
-    if (d_packed && d_packed != d_planar) cudaFreeAsync(d_packed, st);
+    if (d_packed) cudaFreeAsync(d_packed, st);
     if (d_planar) cudaFreeAsync(d_planar, st);
     if (d_tf) cudaFreeAsync(d_tf, st);
     if (d_lab) cudaFreeAsync(d_lab, st);

@@ -2,9 +2,9 @@
 //
 // One warp = one 8x4 half of an 8x8 screen tile (rays of a warp stay in one brick
 // neighbourhood); MRT_FWD_TPB tiles per CTA.  Per ray: exact set-up (march.cuh), then a
-// segment loop: locate the 8^3 brick of the current sample slot, look up its bit in the
-// per-frame active mask, and either jump over the whole brick (exact: those slots are
-// provably no-ops) or march the slots inside it: fp32 trilinear from the packed
+// segment loop: locate the 8^3 brick of the current sample slot, look up its per-frame skip
+// level, and either leap over the largest empty aligned cell around it (8..64 voxels; exact:
+// those slots are provably no-ops) or march the slots inside the brick: fp32 trilinear from the packed
 // multi-channel layout (8 vector loads per sample), modality blend, window/level, TF
 // (shared-memory LUT), front-to-back compositing with early ray termination.
 #include "march.cuh"
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(64 * MRT_FWD_TPB)
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const typename Vox<NCH>::T* __restrict__ vol,
                const float4* __restrict__ tf,
-               const uint32_t* __restrict__ active_bits,
+               const uint8_t* __restrict__ levels,
                const int32_t* __restrict__ labels,
                const int32_t* __restrict__ preds,
                float4* __restrict__ out_rgba,
@@ -45,7 +45,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   const int tile = P.tile_begin + blockIdx.x * MRT_FWD_TPB + (warp >> 1);
   if (tile >= P.tile_end) return;
   int px, py;
-  mrt_pixel_of_tile_lane_(tile, ((warp & 1) << 5) + lane, P.W, &px, &py);
+  mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
   if (px >= P.W || py >= P.H) return;                                      // :89
 
   const Ray ray = mrt_setup_ray(P, px, py);
@@ -115,9 +115,11 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
         const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
         const int bx = c.ix >> MRT_BRICK_SHIFT, by = c.iy >> MRT_BRICK_SHIFT, bz = c.iz >> MRT_BRICK_SHIFT;
-        const int bid = (bz * P.nby + by) * P.nbx + bx;
-        const bool act = (__ldg(active_bits + (bid >> 5)) >> (bid & 31)) & 1u;
-        const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, bx, by, bz, t, inv_dt));
+        const int lvl = __ldg(levels + ((bz * P.nby + by) * P.nbx + bx));
+        // active brick: march to the brick's exit; empty: leap over the largest empty aligned cell
+        const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+        const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, c.ix >> sh, c.iy >> sh, c.iz >> sh, sh, t, inv_dt));
+        const bool act = (lvl == 0);
         if (GENERIC) ++n_seg;
         if (!act) { k = kend; continue; }
         do {
@@ -141,7 +143,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
 
 // ------------------------------------------------------------------------- dispatch
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint32_t* bits,
+static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint8_t* bits,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
@@ -156,7 +158,7 @@ static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf
 
 template <int NCH>
 static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen, const void* vol, const float* tf,
-                                const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                                const uint8_t* bits, const int32_t* labels, const int32_t* preds,
                                 float* o, float* oT, int32_t* oc, cudaStream_t st) {
 #define MRT_CASE(L, S, G) if (lab == L && skip == S && gen == G) \
     return launch_fwd<NCH, L, S, G>(P, vol, tf, bits, labels, preds, o, oT, oc, st);
@@ -169,7 +171,7 @@ static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen,
 }
 
 cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                               const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                               const uint8_t* bits, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st) {
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && bits != nullptr && P.tMode == 0;

@@ -7,7 +7,7 @@
 struct KParams;
 
 cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                               const uint32_t* bits, const int32_t* labels, const int32_t* preds,
+                               const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st);
 
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
@@ -22,7 +22,7 @@ cudaError_t mrt_launch_build_occupancy(const void* packed, int packed_ch, int X,
                                        float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int Z, uint8_t* any, cudaStream_t st);
 cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int packed_ch, const float* tf,
-                                const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* bits,
+                                const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* levels,
                                 cudaStream_t st);
 
 cudaError_t mrt_launch_tile_map(int W, int H, int32_t* out_tile, int32_t* out_lane, cudaStream_t st);
@@ -39,3 +39,17 @@ cudaError_t mrt_launch_slab(const MrtSlabParams& P, float tan_half, const uint8_
                             int tile_begin, int tile_end, cudaStream_t st);
 
 static inline int mrt_packed_channels(int C) { return C <= 1 ? 1 : (C == 2 ? 2 : 4); }
+
+// Skewed pitches of the packed layout (see include/mrt.h "volume layout"): with S voxels per
+// 128-byte line, pitchY = S/4 and pitchZ = S/2 (mod S) put the cells of a small 3-D
+// neighbourhood into distinct L1 data banks, so a warp's gather is not serialised by bank
+// conflicts between rows/slices (row pitches that are multiples of 128 B alias every row).
+static inline void mrt_layout(int packed_ch, int X, int Y, int Z, int64_t* pitchY, int64_t* pitchZ) {
+  const int64_t S = 32 / packed_ch;
+  int64_t py = X;
+  while (py % S != S / 4) ++py;
+  int64_t pz = py * Y;
+  while (pz % S != S / 2) ++pz;
+  (void)Z;
+  *pitchY = py; *pitchZ = pz;
+}

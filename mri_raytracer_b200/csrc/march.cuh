@@ -20,6 +20,7 @@ struct KParams {
   int ortho; float halfH;
   float bmin[3], vs[3];
   int dims[3];            // X, Y, Z
+  unsigned pitchY, pitchZ; // packed-layout pitches in voxels (kernels.h mrt_layout)
   float dt, nearT, farT;
   float bg[3];
   float wgt[4];           // volWeight if enabled else 0
@@ -159,8 +160,8 @@ template <int NCH>
 __device__ __forceinline__ float mrt_sample_blend(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
                                                   const Cell& c) {
   typedef typename Vox<NCH>::T VT;
-  const uint32_t sY = (uint32_t)P.dims[0];
-  const uint32_t sZ = sY * (uint32_t)P.dims[1];
+  const uint32_t sY = P.pitchY;
+  const uint32_t sZ = P.pitchZ;
   const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ;
   const VT* p0 = vol + b;
   const VT* p1 = p0 + sY;
@@ -207,18 +208,32 @@ __device__ __forceinline__ float4 mrt_tf_lookup(const float4* __restrict__ s_tf,
   return make_float4(lerpf(a.x, b.x, fr), lerpf(a.y, b.y, fr), lerpf(a.z, b.z, fr), lerpf(a.w, b.w, fr));
 }
 
-// Exit of the ray from brick cell (bx,by,bz) in index space; returns # of further sample
-// slots (>= 1) guaranteed to lie strictly inside the cell, starting from slot time t.
+// Physical lane (0..31) of a warp -> logical lane (0..63) inside the 8x8 tile.  A warp owns an
+// 8-wide x 4-tall half tile; each group of 8 consecutive lanes (the unit a 128-bit load is
+// processed in) is a compact 4x2 pixel block, so its eight 2x2x2 footprints overlap as much
+// as possible.  The LOGICAL lane is the reference's (y&7)*8+(x&7) (tiles.h).
+__device__ __forceinline__ int mrt_logical_lane(int half, int lane) {
+  const int qd = lane >> 3, j = lane & 7;
+  const int x = ((qd & 1) << 2) + (j & 3);
+  const int y = (half << 2) + ((qd >> 1) << 1) + (j >> 2);
+  return (y << 3) + x;
+}
+
+// Exit of the ray from the aligned cell (cx,cy,cz) of edge 2^sh voxels, in index space, with
+// the exit planes pulled inward by 1/64 voxel (>> any fp32 rounding of the positions):
+// returns the number of consecutive sample slots, starting at slot time t, that are
+// guaranteed to lie inside the cell; always >= 1 so the march progresses.
+#define MRT_PLANE_EPS 0.015625f
 __device__ __forceinline__ int mrt_cell_slots(const IdxRay& q, float ivx, float ivy, float ivz,
-                                              int bx, int by, int bz, float t, float inv_dt) {
-  const float plx = (float)((bx + (q.dx > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
-  const float ply = (float)((by + (q.dy > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
-  const float plz = (float)((bz + (q.dz > 0.0f ? 1 : 0)) << MRT_BRICK_SHIFT);
+                                              int cx, int cy, int cz, int sh, float t, float inv_dt) {
+  const float plx = (q.dx > 0.0f) ? (float)((cx + 1) << sh) - MRT_PLANE_EPS : (float)(cx << sh) + MRT_PLANE_EPS;
+  const float ply = (q.dy > 0.0f) ? (float)((cy + 1) << sh) - MRT_PLANE_EPS : (float)(cy << sh) + MRT_PLANE_EPS;
+  const float plz = (q.dz > 0.0f) ? (float)((cz + 1) << sh) - MRT_PLANE_EPS : (float)(cz << sh) + MRT_PLANE_EPS;
   // an axis the ray does not move along never bounds the exit
   const float tx = (q.dx != 0.0f) ? (plx - q.ox) * ivx : 3.0e38f;
   const float ty = (q.dy != 0.0f) ? (ply - q.oy) * ivy : 3.0e38f;
   const float tz = (q.dz != 0.0f) ? (plz - q.oz) * ivz : 3.0e38f;
   const float te = fminf(fminf(tx, ty), tz);
-  const float ns = floorf((te - t) * inv_dt);
+  const float ns = floorf((te - t) * inv_dt) + 1.0f;     // slots j with t + j*dt <= te
   return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
 }

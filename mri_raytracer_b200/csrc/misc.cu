@@ -4,30 +4,42 @@
 
 // ------------------------------------------------------------------ pack / unpack
 // planar [C][Z][Y][X] (reference flatten, inr/viewer/brats_viewer.py:64) <-> interleaved.
+// One CTA row = one (y,z) scanline: consecutive threads read consecutive x of each planar
+// channel (coalesced) and write consecutive packed voxels (coalesced); the pitches only move
+// the scanline's start.
 template <int PC>
-__global__ void mrt_pack_kernel(const float* __restrict__ planar, int C, size_t nvox,
-                                typename Vox<PC>::T* __restrict__ packed) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += stride) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+__global__ void __launch_bounds__(256)
+mrt_pack_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                typename Vox<PC>::T* __restrict__ packed) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const size_t src = (size_t)row * X, dst = (size_t)y * pitchY + (size_t)z * pitchZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      typename Vox<PC>::T o;
+      float* f = reinterpret_cast<float*>(&o);
 #pragma unroll
-    for (int c = 0; c < PC; ++c) if (c < C) v[c] = __ldg(planar + (size_t)c * nvox + i);
-    typename Vox<PC>::T o;
-    float* f = reinterpret_cast<float*>(&o);
-#pragma unroll
-    for (int c = 0; c < PC; ++c) f[c] = v[c];
-    packed[i] = o;
+      for (int c = 0; c < PC; ++c) f[c] = (c < C) ? __ldg(planar + (size_t)c * nvox + src + x) : 0.0f;
+      packed[dst + x] = o;
+    }
   }
 }
 template <int PC>
-__global__ void mrt_unpack_kernel(const typename Vox<PC>::T* __restrict__ packed, int C, size_t nvox,
-                                  float* __restrict__ planar) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += stride) {
-    const typename Vox<PC>::T o = packed[i];
-    const float* f = reinterpret_cast<const float*>(&o);
+__global__ void __launch_bounds__(256)
+mrt_unpack_kernel(const typename Vox<PC>::T* __restrict__ packed, int C, int X, int Y, int Z, size_t pitchY,
+                  size_t pitchZ, float* __restrict__ planar) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const size_t dst = (size_t)row * X, src = (size_t)y * pitchY + (size_t)z * pitchZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      const typename Vox<PC>::T o = packed[src + x];
+      const float* f = reinterpret_cast<const float*>(&o);
 #pragma unroll
-    for (int c = 0; c < PC; ++c) if (c < C) planar[(size_t)c * nvox + i] = f[c];
+      for (int c = 0; c < PC; ++c) if (c < C) planar[(size_t)c * nvox + dst + x] = f[c];
+    }
   }
 }
 
@@ -38,30 +50,26 @@ static inline int grid_for(size_t n, int block) {
 }
 
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st) {
-  const size_t nvox = (size_t)X * Y * Z;
   const int pc = mrt_packed_channels(C);
-  if (pc == 1) {
-    if ((const void*)planar != packed)
-      return cudaMemcpyAsync(packed, planar, nvox * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    return cudaSuccess;
-  }
-  const int g = grid_for(nvox, 256);
-  if (pc == 2) mrt_pack_kernel<2><<<g, 256, 0, st>>>(planar, C, nvox, (float2*)packed);
-  else mrt_pack_kernel<4><<<g, 256, 0, st>>>(planar, C, nvox, (float4*)packed);
+  int64_t pY, pZ;
+  mrt_layout(pc, X, Y, Z, &pY, &pZ);
+  const int g = grid_for((size_t)Y * Z * 256, 256);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  if (pc == 1) mrt_pack_kernel<1><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float*)packed);
+  else if (pc == 2) mrt_pack_kernel<2><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float2*)packed);
+  else mrt_pack_kernel<4><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float4*)packed);
   return cudaGetLastError();
 }
 
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st) {
-  const size_t nvox = (size_t)X * Y * Z;
   const int pc = mrt_packed_channels(C);
-  if (pc == 1) {
-    if (packed != (const void*)planar)
-      return cudaMemcpyAsync(planar, packed, nvox * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    return cudaSuccess;
-  }
-  const int g = grid_for(nvox, 256);
-  if (pc == 2) mrt_unpack_kernel<2><<<g, 256, 0, st>>>((const float2*)packed, C, nvox, planar);
-  else mrt_unpack_kernel<4><<<g, 256, 0, st>>>((const float4*)packed, C, nvox, planar);
+  int64_t pY, pZ;
+  mrt_layout(pc, X, Y, Z, &pY, &pZ);
+  const int g = grid_for((size_t)Y * Z * 256, 256);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  if (pc == 1) mrt_unpack_kernel<1><<<g, blk, 0, st>>>((const float*)packed, C, X, Y, Z, pY, pZ, planar);
+  else if (pc == 2) mrt_unpack_kernel<2><<<g, blk, 0, st>>>((const float2*)packed, C, X, Y, Z, pY, pZ, planar);
+  else mrt_unpack_kernel<4><<<g, blk, 0, st>>>((const float4*)packed, C, X, Y, Z, pY, pZ, planar);
   return cudaGetLastError();
 }
 

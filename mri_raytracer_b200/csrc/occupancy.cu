@@ -1,10 +1,10 @@
-// occupancy.cu — min/max occupancy brick grid and the per-frame active-brick mask.
+// occupancy.cu — min/max occupancy brick grid and the per-frame skip-level map.
 //
 // No reference code (empty-space skipping is only mentioned in the reference's docs:
 // docs/Methodology-ROI-Neural-Volumetric-Rendering.md:34, docs/showcase-plan.md:20).
-// Contract: skipping must never change the image.  A brick is marked inactive only when
-// every sample slot whose trilinear base index lies in it is provably a no-op
-// (sigma == 0 for the whole reachable TF range, and no overlay label present).
+// Contract: skipping must never change the image.  A brick is marked empty only when every
+// sample slot whose trilinear base index lies in it is provably a no-op (sigma == 0 for the
+// whole reachable TF range, and no overlay label present).
 #include "march.cuh"
 #include "kernels.h"
 #include <float.h>
@@ -16,7 +16,7 @@
 template <int NCH>
 __global__ void __launch_bounds__(128)
 mrt_build_minmax_kernel(const typename Vox<NCH>::T* __restrict__ vol, int X, int Y, int Z,
-                        int nbx, int nby, float2* __restrict__ minmax) {
+                        size_t pitchY, size_t pitchZ, int nbx, int nby, float2* __restrict__ minmax) {
   const int b = blockIdx.x;
   const int bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
   const int x0 = bx << 3, y0 = by << 3, z0 = bz << 3;
@@ -27,7 +27,7 @@ mrt_build_minmax_kernel(const typename Vox<NCH>::T* __restrict__ vol, int X, int
   for (int c = 0; c < NCH; ++c) { mn[c] = FLT_MAX; mx[c] = -FLT_MAX; }
   for (int i = threadIdx.x; i < nvox; i += blockDim.x) {
     const int lx = i % ex, ly = (i / ex) % ey, lz = i / (ex * ey);
-    const size_t idx = (size_t)(x0 + lx) + (size_t)X * ((size_t)(y0 + ly) + (size_t)Y * (size_t)(z0 + lz));
+    const size_t idx = (size_t)(x0 + lx) + pitchY * (size_t)(y0 + ly) + pitchZ * (size_t)(z0 + lz);
     const typename Vox<NCH>::T v = __ldg(vol + idx);
     const float* f = reinterpret_cast<const float*>(&v);
 #pragma unroll
@@ -60,10 +60,12 @@ cudaError_t mrt_launch_build_occupancy(const void* packed, int pc, int X, int Y,
                                        cudaStream_t st) {
   const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
   const int nb = nbx * nby * nbz;
+  int64_t pY, pZ;
+  mrt_layout(pc, X, Y, Z, &pY, &pZ);
   switch (pc) {
-    case 1: mrt_build_minmax_kernel<1><<<nb, 128, 0, st>>>((const float*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
-    case 2: mrt_build_minmax_kernel<2><<<nb, 128, 0, st>>>((const float2*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
-    case 4: mrt_build_minmax_kernel<4><<<nb, 128, 0, st>>>((const float4*)packed, X, Y, Z, nbx, nby, (float2*)minmax); break;
+    case 1: mrt_build_minmax_kernel<1><<<nb, 128, 0, st>>>((const float*)packed, X, Y, Z, pY, pZ, nbx, nby, (float2*)minmax); break;
+    case 2: mrt_build_minmax_kernel<2><<<nb, 128, 0, st>>>((const float2*)packed, X, Y, Z, pY, pZ, nbx, nby, (float2*)minmax); break;
+    case 4: mrt_build_minmax_kernel<4><<<nb, 128, 0, st>>>((const float4*)packed, X, Y, Z, pY, pZ, nbx, nby, (float2*)minmax); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -99,63 +101,119 @@ cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int 
 // entries a sample in this brick can touch.  Margins (1e-5 on v, 1e-3 of a LUT bin) are far
 // wider than any fp32 rounding in the sampler and far narrower than a LUT bin.
 template <int NCH>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ bool mrt_brick_active(const KParams& P, const float2* __restrict__ minmax,
+                                                 const float4* __restrict__ tf, const uint8_t* __restrict__ seg_any,
+                                                 const uint8_t* __restrict__ pred_any, int b) {
+  bool act = false;
+  float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float2 mm = __ldg(minmax + (size_t)b * NCH + c);
+    const float w = P.wgt[c];
+    lo += (w >= 0.0f) ? w * mm.x : w * mm.y;
+    hi += (w >= 0.0f) ? w * mm.y : w * mm.x;
+  }
+  float a = lo * P.inv_wsum, z = hi * P.inv_wsum;
+  if (a > z) { const float t = a; a = z; z = t; }
+  const float mv = 1e-5f * (1.0f + fmaxf(fabsf(a), fabsf(z)));
+  a -= mv; z += mv;
+  float r0 = (a - P.lo) * P.inv_ww, r1 = (z - P.lo) * P.inv_ww;
+  if (r0 > r1) { const float t = r0; r0 = r1; r1 = t; }
+  const float mr = 1e-5f * (1.0f + fmaxf(fabsf(r0), fabsf(r1)));
+  r0 -= mr; r1 += mr;
+  float v0 = __saturatef(r0), v1 = __saturatef(r1);
+  if (P.gamma != 1.0f) {                       // pow is monotone on [0,1] for gamma > 0
+    const float p0 = powf(v0, P.gamma), p1 = powf(v1, P.gamma);
+    v0 = fmaxf(fminf(p0, p1) - 1e-5f, 0.0f); v1 = fminf(fmaxf(p0, p1) + 1e-5f, 1.0f);
+    if (!(P.gamma > 0.0f)) { v0 = 0.0f; v1 = 1.0f; }
+  }
+  if (P.tfMode == 0) {
+    act = (v1 > 0.0f) && (P.ia != 0.0f);        // sigma = val*intensityAlpha, gated on val > 0 (:135)
+  } else {
+    const float s = (float)(P.tfN - 1);
+    int j0 = (int)floorf(v0 * s - 1e-3f), j1 = (int)floorf(v1 * s + 1e-3f) + 1;
+    j0 = max(j0, 0); j1 = min(j1, P.tfN - 1);
+    for (int j = j0; j <= j1; ++j) {
+      if (__ldg(&tf[j].w) != 0.0f) { act = true; break; }
+    }
+  }
+  if (P.showSeg && (seg_any == nullptr || seg_any[b])) act = true;     // no label grid supplied: stay exact
+  if (P.showPred && (pred_any == nullptr || pred_any[b])) act = true;
+  return act;
+}
+
+// One CTA per 8x8x8-brick super-cell (64^3 voxels): classify each brick, then OR-reduce the
+// flags over the aligned 2^3, 4^3 and 8^3 brick cells and store, per brick, the largest
+// aligned empty cell that contains it (skip level 1..4; 0 = active).  Bricks outside the
+// grid count as empty (no sample slot ever lands there).
+template <int NCH>
+__global__ void __launch_bounds__(512)
 mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict__ minmax,
                     const float4* __restrict__ tf, const uint8_t* __restrict__ seg_any,
-                    const uint8_t* __restrict__ pred_any, uint32_t* __restrict__ bits, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  bool act = false;
-  if (b < nb) {
-    float lo = 0.0f, hi = 0.0f;
+                    const uint8_t* __restrict__ pred_any, uint8_t* __restrict__ levels, int sbx, int sby) {
+  __shared__ uint8_t s_act[512];
+  __shared__ uint8_t s_or2[64];
+  __shared__ uint8_t s_or4[8];
+  __shared__ uint8_t s_or8;
+  const int t = threadIdx.x;
+  const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+  const int sx = blockIdx.x % sbx, sy = (blockIdx.x / sbx) % sby, sz = blockIdx.x / (sbx * sby);
+  const int bx = (sx << 3) + lx, by = (sy << 3) + ly, bz = (sz << 3) + lz;
+  const bool inside = bx < P.nbx && by < P.nby && bz < P.nbz;
+  const int b = (bz * P.nby + by) * P.nbx + bx;
+  const bool act = inside && mrt_brick_active<NCH>(P, minmax, tf, seg_any, pred_any, b);
+  s_act[t] = act;
+  __syncthreads();
+  if (t < 64) {            // 2x2x2 groups: group (gx,gy,gz) in 4x4x4
+    const int gx = t & 3, gy = (t >> 2) & 3, gz = t >> 4;
+    int o = 0;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const float2 mm = __ldg(minmax + (size_t)b * NCH + c);
-      const float w = P.wgt[c];
-      lo += (w >= 0.0f) ? w * mm.x : w * mm.y;
-      hi += (w >= 0.0f) ? w * mm.y : w * mm.x;
-    }
-    float a = lo * P.inv_wsum, z = hi * P.inv_wsum;
-    if (a > z) { const float t = a; a = z; z = t; }
-    const float mv = 1e-5f * (1.0f + fmaxf(fabsf(a), fabsf(z)));
-    a -= mv; z += mv;
-    float r0 = (a - P.lo) * P.inv_ww, r1 = (z - P.lo) * P.inv_ww;
-    if (r0 > r1) { const float t = r0; r0 = r1; r1 = t; }
-    const float mr = 1e-5f * (1.0f + fmaxf(fabsf(r0), fabsf(r1)));
-    r0 -= mr; r1 += mr;
-    float v0 = __saturatef(r0), v1 = __saturatef(r1);
-    if (P.gamma != 1.0f) {                       // pow is monotone on [0,1] for gamma > 0
-      const float p0 = powf(v0, P.gamma), p1 = powf(v1, P.gamma);
-      v0 = fmaxf(fminf(p0, p1) - 1e-5f, 0.0f); v1 = fminf(fmaxf(p0, p1) + 1e-5f, 1.0f);
-      if (!(P.gamma > 0.0f)) { v0 = 0.0f; v1 = 1.0f; }
-    }
-    if (P.tfMode == 0) {
-      act = (v1 > 0.0f) && (P.ia != 0.0f);        // sigma = val*intensityAlpha, gated on val > 0 (:135)
-    } else {
-      const float s = (float)(P.tfN - 1);
-      int j0 = (int)floorf(v0 * s - 1e-3f), j1 = (int)floorf(v1 * s + 1e-3f) + 1;
-      j0 = max(j0, 0); j1 = min(j1, P.tfN - 1);
-      for (int j = j0; j <= j1; ++j) {
-        if (__ldg(&tf[j].w) != 0.0f) { act = true; break; }
+    for (int i = 0; i < 8; ++i)
+      o |= s_act[((gz * 2 + (i >> 2)) << 6) + ((gy * 2 + ((i >> 1) & 1)) << 3) + gx * 2 + (i & 1)];
+    s_or2[t] = (uint8_t)o;
+  }
+  __syncthreads();
+  if (t < 8) {             // 4x4x4 groups: (hx,hy,hz) in 2x2x2, each = 2x2x2 of the or2 groups
+    const int hx = t & 1, hy = (t >> 1) & 1, hz = t >> 2;
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o |= s_or2[((hz * 2 + (i >> 2)) << 4) + ((hy * 2 + ((i >> 1) & 1)) << 2) + hx * 2 + (i & 1)];
+    s_or4[t] = (uint8_t)o;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= s_or4[i];
+    s_or8 = (uint8_t)o;
+  }
+  __syncthreads();
+  if (inside) {
+    int lvl = 0;
+    if (!act) {
+      lvl = 1;
+      if (!s_or2[((lz >> 1) << 4) + ((ly >> 1) << 2) + (lx >> 1)]) {
+        lvl = 2;
+        if (!s_or4[((lz >> 2) << 2) + ((ly >> 2) << 1) + (lx >> 2)]) {
+          lvl = 3;
+          if (!s_or8) lvl = 4;
+        }
       }
     }
-    if (P.showSeg && seg_any != nullptr && seg_any[b]) act = true;
-    if (P.showPred && pred_any != nullptr && pred_any[b]) act = true;
-    if (P.showSeg && seg_any == nullptr) act = true;     // no label grid supplied: stay exact
-    if (P.showPred && pred_any == nullptr) act = true;
+    levels[b] = (uint8_t)lvl;
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, act);
-  if ((threadIdx.x & 31) == 0 && b < nb) bits[b >> 5] = word;
 }
 
 cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int pc, const float* tf,
-                                const uint8_t* seg_any, const uint8_t* pred_any, uint32_t* bits,
+                                const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* levels,
                                 cudaStream_t st) {
-  const int nb = P.nbx * P.nby * P.nbz;
-  const int grid = (nb + 127) / 128;
+  const int sbx = (P.nbx + 7) >> 3, sby = (P.nby + 7) >> 3, sbz = (P.nbz + 7) >> 3;
+  const int grid = sbx * sby * sbz;
   switch (pc) {
-    case 1: mrt_classify_kernel<1><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
-    case 2: mrt_classify_kernel<2><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
-    case 4: mrt_classify_kernel<4><<<grid, 128, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, bits, nb); break;
+    case 1: mrt_classify_kernel<1><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
+    case 2: mrt_classify_kernel<2><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
+    case 4: mrt_classify_kernel<4><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -46,7 +46,7 @@ mrt_slab_kernel(const __grid_constant__ SlabK P, const uint8_t* __restrict__ vol
   const int tile = P.tile_begin + blockIdx.x * 2 + (warp >> 1);
   if (tile >= P.tile_end) return;
   int px, py;
-  mrt_pixel_of_tile_lane_(tile, ((warp & 1) << 5) + lane, P.W, &px, &py);
+  mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
   if (px >= P.W || py >= P.H) return;                                                  // :109
   const float invx = __fdiv_rn(1.0f, (float)P.W), invy = __fdiv_rn(1.0f, (float)P.H);   // :111
   const float uvx = __fmul_rn(__fadd_rn((float)px, 0.5f), invx);                       // :115

@@ -41,7 +41,7 @@ def _default_render_fn(volume, tf):
 
     def fn(P: RenderParams, tile_range: Tuple[int, int], out: torch.Tensor):
         P = replace(P, tfMode=1 if tf is not None else 0)
-        bits = volume.active_bits(P, tf)
+        bits = volume.skip_levels(P, tf)
         api.render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds, out=out,
                            tile_range=tile_range)
     return fn

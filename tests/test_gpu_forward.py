@@ -102,7 +102,7 @@ def test_ragged_image_sizes_and_tile_ranges(cuda):
         nt = tiles.tile_count(W, H)
         out = torch.full((H, W, 4), -7.0, device="cuda")
         for r in range(2):
-            api.render_forward(replace(P, tfMode=0), V.packed, V.C, None, V.active_bits(P, None), out=out,
+            api.render_forward(replace(P, tfMode=0), V.packed, V.C, None, V.skip_levels(P, None), out=out,
                                tile_range=tiles.rank_tile_range(nt, r, 2))
         assert torch.equal(out, full)
 
