@@ -221,11 +221,12 @@ def run_ours(args):
         if world == 1:
             for v, c in enumerate(cams):
                 Pv = P.with_camera(c)
+                packed, Ce, Pe = volume.prepared(Pv)
                 bits = volume.skip_levels(Pv, tf)
                 if record_kernels:
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()
-                api.render_forward(Pv, volume.packed, volume.C, tf, bits, out=frames[v])
+                api.render_forward(Pe, packed, Ce, tf, bits, out=frames[v])
                 if record_kernels:
                     b.record(); kern_ev.append((a, b, v))
         else:

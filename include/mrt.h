@@ -143,6 +143,17 @@ int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, in
 int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z,
                           float* planar, void* stream);
 
+/* ------------------------------------------------ modality fold
+ * The modality blend v = sum_c w_c s_c / wSum (brats_rt.slang:123-130) is linear and commutes
+ * with trilinear interpolation.  mrt_fold_volume_f32 evaluates it ONCE per voxel for the
+ * (volEnabled, volWeight) in `params`, from planar [C][Z][Y][X] fp32 into a single-channel
+ * volume in the packed C=1 layout (size mrt_packed_volume_bytes(1,X,Y,Z)); rendering that
+ * volume with C=1, volEnabled=(1,0,0,0), volWeight=(1,..) gives the same image (to fp32
+ * rounding) with 8 scalar loads per sample instead of 8 float4 loads.  Re-fold when the
+ * weights change.  mrt_unfold_grad_f32 is the adjoint: dL/dplanar[c] = w_c/wSum * dL/dfolded. */
+int mrt_fold_volume_f32(const MrtParams* params, const float* planar, int32_t C, float* folded, void* stream);
+int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C, float* dplanar, void* stream);
+
 /* ------------------------------------------------ occupancy brick grid
  * (new relative to the reference; must never change the image.)
  * Grid of ceil(dim/8)^3 bricks; brick b holds per-channel (min,max) over voxels

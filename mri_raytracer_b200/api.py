@@ -141,22 +141,65 @@ def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional
     return dvol, dtf
 
 
+# ----------------------------------------------------------------------------- fold
+def fold_volume(planar: torch.Tensor, P: RenderParams) -> torch.Tensor:
+    """Blend the modalities once per voxel (``mrt_fold_volume_f32``): [C,Z,Y,X] -> packed C=1."""
+    _need_cuda(planar, "volume", torch.float32)
+    Cn, Z, Y, X = planar.shape
+    nbytes = lib().mrt_packed_volume_bytes(1, X, Y, Z)
+    folded = torch.zeros((nbytes // 4,), dtype=torch.float32, device=planar.device)
+    s = replace(P, dims=(X, Y, Z)).to_struct()
+    check(lib().mrt_fold_volume_f32(C.byref(s), planar.data_ptr(), Cn, folded.data_ptr(), _stream()), "fold_volume")
+    return folded
+
+
+def unfold_grad(dfolded: torch.Tensor, P: RenderParams, Cn: int) -> torch.Tensor:
+    X, Y, Z = P.dims
+    out = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=dfolded.device)
+    s = P.to_struct()
+    check(lib().mrt_unfold_grad_f32(C.byref(s), dfolded.data_ptr(), Cn, out.data_ptr(), _stream()), "unfold_grad")
+    return out
+
+
+def folded_params(P: RenderParams) -> RenderParams:
+    """Params for rendering a folded (pre-blended) volume as a single modality."""
+    return replace(P, volEnabled=(1, 0, 0, 0), volWeight=(1.0, 1.0, 1.0, 1.0))
+
+
+def _fold_key(P: RenderParams, Cn: int):
+    return (tuple(int(bool(e)) for e in P.volEnabled[:Cn]), tuple(float(np.float32(w)) for w in P.volWeight[:Cn]))
+
+
 # ----------------------------------------------------------------------------- Volume
 class Volume:
-    """A device-resident volume prepared for rendering: packed layout, occupancy brick grid,
+    """A device-resident volume prepared for rendering: sampler layout, occupancy brick grid,
     optional label volumes, and the reference's world scaling
-    (inr/viewer/brats_viewer.py:204-210: voxelSize = zooms*1.8/max_dim, volMin = -extent/2)."""
+    (inr/viewer/brats_viewer.py:204-210: voxelSize = zooms*1.8/max_dim, volMin = -extent/2).
+
+    ``fold=True`` (default for C > 1): the modality blend is evaluated once per voxel for the
+    current (volEnabled, volWeight) and cached, so the march gathers 8 scalars per sample; the
+    cache is rebuilt when the weights change.  ``fold=False`` keeps the channel-interleaved
+    layout (one float4 gather per corner) and blends per sample like the reference shader."""
 
     def __init__(self, planar: torch.Tensor, labels: Optional[torch.Tensor] = None,
-                 preds: Optional[torch.Tensor] = None, zooms=(1.0, 1.0, 1.0), occupancy: bool = True):
+                 preds: Optional[torch.Tensor] = None, zooms=(1.0, 1.0, 1.0), occupancy: bool = True,
+                 fold: bool = True):
         _need_cuda(planar, "volume", torch.float32)
         if planar.dim() != 4 or not (1 <= planar.shape[0] <= 4):
             raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(planar.shape)}")
         self.C = int(planar.shape[0])
         Z, Y, X = (int(v) for v in planar.shape[1:])
         self.dims = (X, Y, Z)
-        self.packed = pack_volume(planar)
-        self.minmax = build_occupancy(self.packed, self.C, self.dims) if occupancy else None
+        self.device = planar.device
+        self.occupancy = occupancy
+        self.fold = bool(fold) and self.C > 1
+        self.planar = planar if self.fold else None
+        self._key = None
+        if self.fold:
+            self.packed = self.minmax = None
+        else:
+            self.packed = pack_volume(planar)
+            self.minmax = build_occupancy(self.packed, self.C, self.dims) if occupancy else None
         self.labels = self.preds = self.seg_any = self.pred_any = None
         self.set_labels(labels)
         self.set_preds(preds)
@@ -164,15 +207,26 @@ class Volume:
         self.voxel_size, self.vol_min = world_box(self.dims, zooms)
         self._bits = None
 
+    def prepared(self, P: RenderParams):
+        """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
+        if not self.fold:
+            return self.packed, self.C, P
+        key = _fold_key(P, self.C)
+        if key != self._key:
+            self.packed = fold_volume(self.planar, P)
+            self.minmax = build_occupancy(self.packed, 1, self.dims) if self.occupancy else None
+            self._key = key
+        return self.packed, 1, folded_params(P)
+
     def set_labels(self, labels: Optional[torch.Tensor]):
         """gLabels (inr/viewer/brats_viewer.py:233-237)."""
         self.labels = self._check_labels(labels)
-        self.seg_any = build_label_occupancy(self.labels) if (self.labels is not None and self.minmax is not None) else None
+        self.seg_any = build_label_occupancy(self.labels) if (self.labels is not None and self.occupancy) else None
 
     def set_preds(self, preds: Optional[torch.Tensor]):
         """gPreds (inr/viewer/brats_viewer.py:293-299)."""
         self.preds = self._check_labels(preds)
-        self.pred_any = build_label_occupancy(self.preds) if (self.preds is not None and self.minmax is not None) else None
+        self.pred_any = build_label_occupancy(self.preds) if (self.preds is not None and self.occupancy) else None
 
     def _check_labels(self, lab):
         if lab is None:
@@ -197,28 +251,43 @@ class Volume:
 
     def skip_levels(self, P: RenderParams, tf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """Per-frame skip-level byte per brick (``mrt_classify_bricks``), or None if skipping is off."""
+        packed, Cn, Pe = self.prepared(P)
         if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
             return None
         nb = self.minmax.shape[0]
         if self._bits is None:
-            self._bits = torch.empty((nb,), dtype=torch.uint8, device=self.packed.device)
-        return classify_bricks(P, self.minmax, self.C, tf, self.seg_any, self.pred_any, out=self._bits)
+            self._bits = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+        return classify_bricks(Pe, self.minmax, Cn, tf, self.seg_any, self.pred_any, out=self._bits)
+
+    def forward(self, P: RenderParams, tf: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                out_T: Optional[torch.Tensor] = None, out_counts: Optional[torch.Tensor] = None,
+                tile_range: Optional[Tuple[int, int]] = None, labels=None, preds=None) -> torch.Tensor:
+        """classify + march for one frame (two launches); ``P.tfMode`` must already be set."""
+        packed, Cn, Pe = self.prepared(P)
+        bits = self.skip_levels(P, tf)
+        return render_forward(Pe, packed, Cn, tf, bits, labels if labels is not None else self.labels,
+                              preds if preds is not None else self.preds, out=out, out_T=out_T,
+                              out_counts=out_counts, tile_range=tile_range)
 
 
 # ----------------------------------------------------------------------------- autograd
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, planar, tf, P: RenderParams, labels, preds):
+    def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold):
         Cn = planar.shape[0]
-        packed = pack_volume(planar.detach())
+        fold = bool(fold) and Cn > 1
+        if fold:
+            packed, Ce, Pe = fold_volume(planar.detach(), P), 1, folded_params(P)
+        else:
+            packed, Ce, Pe = pack_volume(planar.detach()), Cn, P
         bits = None
         if P.skipEmpty and P.tMode == "indexed":
-            mm = build_occupancy(packed, Cn, P.dims)
+            mm = build_occupancy(packed, Ce, P.dims)
             seg_any = build_label_occupancy(labels) if (labels is not None and P.showSeg) else None
             pred_any = build_label_occupancy(preds) if (preds is not None and P.showPred) else None
-            bits = classify_bricks(P, mm, Cn, tf, seg_any, pred_any)
-        out = render_forward(P, packed, Cn, tf, bits, labels, preds)
-        ctx.P, ctx.Cn = P, Cn
+            bits = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any)
+        out = render_forward(Pe, packed, Ce, tf, bits, labels, preds)
+        ctx.P, ctx.Pe, ctx.Cn, ctx.Ce, ctx.fold = P, Pe, Cn, Ce, fold
         ctx.labels, ctx.preds = labels, preds
         ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=planar.device), out)
         ctx.has_tf = tf is not None
@@ -229,15 +298,17 @@ class _RenderFn(torch.autograd.Function):
         packed, tf, out = ctx.saved_tensors
         tf = tf if ctx.has_tf else None
         want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
-        dvol, dtf = render_backward(ctx.P, packed, ctx.Cn, tf, ctx.labels, ctx.preds, out,
+        dvol, dtf = render_backward(ctx.Pe, packed, ctx.Ce, tf, ctx.labels, ctx.preds, out,
                                     g.contiguous(), want_dvol=want_vol, want_dtf=want_tf)
-        gvol = unpack_volume(dvol, ctx.Cn, ctx.P.dims) if want_vol else None
-        return gvol, (dtf if want_tf else None), None, None, None
+        gvol = None
+        if want_vol:
+            gvol = unfold_grad(dvol, ctx.P, ctx.Cn) if ctx.fold else unpack_volume(dvol, ctx.Cn, ctx.P.dims)
+        return gvol, (dtf if want_tf else None), None, None, None, None
 
 
 def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Optional[torch.Tensor],
            params: RenderParams, labels: Optional[torch.Tensor] = None,
-           preds: Optional[torch.Tensor] = None) -> torch.Tensor:
+           preds: Optional[torch.Tensor] = None, fold: bool = True) -> torch.Tensor:
     """Render one frame: -> float32 ``[H, W, 4]`` (row 0 = top of the image).
 
     volume : ``[C,Z,Y,X]`` CUDA fp32 tensor (differentiable) or a prepared :class:`Volume`.
@@ -246,6 +317,8 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
              intensity transfer function (brats_rt.slang:132-140).
     params : :class:`RenderParams` (the reference's ``struct Params`` + extensions).
     labels, preds : optional int32 ``[Z,Y,X]`` overlays (gLabels / gPreds).
+    fold   : tensor input only — blend the modalities once per voxel before marching
+             (see :class:`Volume`); ``False`` blends per sample like the reference shader.
     Differentiable w.r.t. ``volume`` and ``tf`` when ``volume`` is a tensor.
     """
     P = params if camera is None else params.with_camera(camera)
@@ -258,10 +331,8 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
         V = volume
         if tuple(P.dims) != tuple(V.dims):
             raise ValueError(f"params.dims {P.dims} != volume dims {V.dims}")
-        lab = labels if labels is not None else V.labels
-        prd = preds if preds is not None else V.preds
-        bits = V.skip_levels(P, tf)
-        return render_forward(P, V.packed, V.C, tf, bits, lab, prd)
+        P.validate()
+        return V.forward(P, tf, labels=labels, preds=preds)
     _need_cuda(volume, "volume", torch.float32)
     if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
         raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(volume.shape)}")
@@ -273,7 +344,7 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
             _need_cuda(lab, name, torch.int32)
             if tuple(lab.shape) != (Z, Y, X):
                 raise ValueError(f"{name} must be [Z,Y,X]")
-    return _RenderFn.apply(volume, tf, P, labels, preds)
+    return _RenderFn.apply(volume, tf, P, labels, preds, fold)
 
 
 def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams):
@@ -282,12 +353,9 @@ def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tens
     P = params if camera is None else params.with_camera(camera)
     P = replace(P, tfMode=1 if tf is not None else 0)
     W, H = P.imageSize
-    dev = volume.packed.device
-    out_T = torch.empty((H, W), dtype=torch.float32, device=dev)
-    counts = torch.zeros((H, W, 4), dtype=torch.int32, device=dev)
-    bits = volume.skip_levels(P, tf)
-    img = render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds,
-                         out_T=out_T, out_counts=counts)
+    out_T = torch.empty((H, W), dtype=torch.float32, device=volume.device)
+    counts = torch.zeros((H, W, 4), dtype=torch.int32, device=volume.device)
+    img = volume.forward(P, tf, out_T=out_T, out_counts=counts)
     return img, out_T, counts
 
 

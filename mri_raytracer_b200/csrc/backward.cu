@@ -20,13 +20,13 @@
 #endif
 
 __device__ __forceinline__ void vox_atomic_add(float* p, float w, const KParams& P) {
-  atomicAdd(p, w * P.wgt[0]);
+  atomicAdd(p, w * P.wq[0]);
 }
 __device__ __forceinline__ void vox_atomic_add(float2* p, float w, const KParams& P) {
-  atomicAdd(p, make_float2(w * P.wgt[0], w * P.wgt[1]));
+  atomicAdd(p, make_float2(w * P.wq[0], w * P.wq[1]));
 }
 __device__ __forceinline__ void vox_atomic_add(float4* p, float w, const KParams& P) {
-  atomicAdd(p, make_float4(w * P.wgt[0], w * P.wgt[1], w * P.wgt[2], w * P.wgt[3]));
+  atomicAdd(p, make_float4(w * P.wq[0], w * P.wq[1], w * P.wq[2], w * P.wq[3]));
 }
 
 template <int NCH, bool LABELS, bool GENERIC>
@@ -41,19 +41,25 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
                typename Vox<NCH>::T* __restrict__ dvol,
                float* __restrict__ dtf) {
   typedef typename Vox<NCH>::T VT;
-  extern __shared__ float4 s_tf[];                     // [ntf] LUT | [16] labels | [ntf*4] dtf accum
+  extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels | [ntf*4] dtf accum
   const int ntf = P.tfMode ? P.tfN : 2;
-  float4* s_lab = s_tf + ntf;
+  TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);
+  float4* s_lab = reinterpret_cast<float4*>(s_tf + ntf);
   float* s_dtf = reinterpret_cast<float*>(s_lab + 16);
 
-  for (int i = threadIdx.x; i < ntf; i += blockDim.x)
-    s_tf[i] = P.tfMode ? __ldg(tf + i) : (i == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(1.f, 1.f, 1.f, P.ia));
+  if (P.tfMode) {
+    mrt_tf_stage(s_tf, tf, ntf);
+  } else if (threadIdx.x == 0) {
+    // the reference intensity TF (:135-138) is the 2-entry LUT [(0,0,0,0), (1,1,1,intensityAlpha)]
+    s_tf[0].base = make_float4(0.f, 0.f, 0.f, 0.f); s_tf[0].delta = make_float4(1.f, 1.f, 1.f, P.ia);
+    s_tf[1].base = make_float4(1.f, 1.f, 1.f, P.ia); s_tf[1].delta = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int i = threadIdx.x; i < ntf * 4; i += blockDim.x) s_dtf[i] = 0.0f;
   if (LABELS) {
     if (threadIdx.x < 16) {
       const int l = threadIdx.x & 7;
       const float boost = threadIdx.x < 8 ? 1.0f : 1.5f;
-      const float a = 1.0f - expf(-P.lut[l][3] * P.dt * boost);
+      const float a = mrt_alpha(P, P.lut[l][3] * boost);
       s_lab[threadIdx.x] = make_float4(P.lut[l][0], P.lut[l][1], P.lut[l][2], (l > 0) ? a : 0.0f);
     }
   }
@@ -80,6 +86,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
       const IdxRay q = mrt_index_ray(P, ray);
       const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
       const float dt = P.dt, thr = P.thr;
+      const float nm1 = (float)(ntf - 1);
       const uint32_t sY = P.pitchY, sZ = P.pitchZ;
       float T = 1.0f, prefix = 0.0f;
       int k = 0;
@@ -95,13 +102,12 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
         }
         const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
         const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-        const float v = mrt_sample_blend<NCH>(P, vol, c);
-        const float raw = (v - P.lo) * P.inv_ww;
-        const float val = mrt_window<GENERIC>(P, v);
+        const float raw = mrt_sample_raw<NCH>(P, vol, c);
+        const float val = mrt_window<GENERIC>(P, raw);
         if (P.tfMode || val > 0.0f) {
-          int j0, j1; float fr;
-          const float4 rgba = mrt_tf_lookup(s_tf, ntf, val, &j0, &j1, &fr);
-          const float alpha = 1.0f - expf(-rgba.w * dt);
+          int j0; float fr;
+          const float4 rgba = mrt_tf_lookup(s_tf, nm1, val, &j0, &fr);
+          const float alpha = mrt_alpha(P, rgba.w);
           const float aT = alpha * T;
           const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
           prefix = fmaf(aT, gc, prefix);
@@ -113,22 +119,19 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
             atomicAdd(s_dtf + j0 * 4 + 0, w0 * dr); atomicAdd(s_dtf + j0 * 4 + 1, w0 * dg);
             atomicAdd(s_dtf + j0 * 4 + 2, w0 * db); atomicAdd(s_dtf + j0 * 4 + 3, w0 * dsig);
             if (fr != 0.0f) {
+              const int j1 = min(j0 + 1, ntf - 1);
               atomicAdd(s_dtf + j1 * 4 + 0, fr * dr); atomicAdd(s_dtf + j1 * 4 + 1, fr * dg);
               atomicAdd(s_dtf + j1 * 4 + 2, fr * db); atomicAdd(s_dtf + j1 * 4 + 3, fr * dsig);
             }
           }
           if (dvol != nullptr) {
-            const float4 a4 = s_tf[j0], b4 = s_tf[j1];
-            float dval = (float)(ntf - 1) * (dr * (b4.x - a4.x) + dg * (b4.y - a4.y) + db * (b4.z - a4.z) +
-                                             dsig * (b4.w - a4.w));
+            const float4 d4 = s_tf[j0].delta;
+            float dval = nm1 * (dr * d4.x + dg * d4.y + db * d4.z + dsig * d4.w);
             if (GENERIC) {
-              if (P.gamma != 1.0f) {
-                const float rs = __saturatef(raw);
-                dval *= P.gamma * powf(rs, P.gamma - 1.0f);
-              }
+              if (P.gamma != 1.0f) dval *= P.gamma * powf(__saturatef(raw), P.gamma - 1.0f);
             }
             // saturate: torch.clamp passes the gradient on the closed interval [0,1]
-            const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval * P.inv_ww * P.inv_wsum : 0.0f;
+            const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval : 0.0f;
             if (dv != 0.0f) {
               const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ;
               VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
@@ -183,7 +186,7 @@ static cudaError_t launch_bwd(const KParams& P, const void* vol, const float* tf
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_BWD_TPB - 1) / MRT_BWD_TPB;
   const int ntf = P.tfMode ? P.tfN : 2;
-  const size_t smem = (size_t)(ntf + 16) * sizeof(float4) + (size_t)ntf * 4 * sizeof(float);
+  const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4) + (size_t)ntf * 4 * sizeof(float);
   mrt_bwd_kernel<NCH, LABELS, GENERIC><<<grid, 64 * MRT_BWD_TPB, smem, st>>>(
       P, (const VT*)vol, (const float4*)tf, labels, preds, (const float4*)out_rgba, (const float4*)dL_dout,
       (VT*)dvol, dtf);

@@ -119,6 +119,9 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   K->inv_wsum = (wsum > 0.0f) ? 1.0f / wsum : 1.0f;        // :130
   K->lo = M->wl - M->ww * 0.5f;                            // :132
   K->inv_ww = 1.0f / M->ww;
+  for (int c = 0; c < 4; ++c) K->wq[c] = K->wgt[c] * K->inv_wsum * K->inv_ww;
+  K->wbias = -K->lo * K->inv_ww;
+  K->neg_dt_log2e = -(float)((double)M->stepSize * 1.4426950408889634);
   K->ia = M->intensityAlpha;
   K->gamma = M->gamma;
   K->showSeg = M->showSeg ? 1 : 0; K->showPred = M->showPred ? 1 : 0;
@@ -137,6 +140,35 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
               "tile range [%d,%d) outside [0,%d]", tile_begin, tile_end, nt);
   K->tile_begin = tile_begin; K->tile_end = tile_end;
   return MRT_OK;
+}
+
+// ---------------------------------------------------------------- modality fold
+static void blend_weights(const MrtParams* M, int C, float wgt[4], float* inv_wsum) {
+  float wsum = 0.0f;
+  for (int c = 0; c < 4; ++c) {
+    const bool en = (c < C) && (M->volEnabled[c] != 0);
+    wgt[c] = en ? M->volWeight[c] : 0.0f;
+    if (en) wsum += M->volWeight[c];                       // brats_rt.slang:125-128
+  }
+  *inv_wsum = (wsum > 0.0f) ? 1.0f / wsum : 1.0f;          // :130
+}
+int mrt_fold_volume_f32(const MrtParams* params, const float* planar, int32_t C, float* folded, void* stream) {
+  MRT_REQUIRE(params && planar && folded, "fold_volume: null pointer");
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("fold_volume", C, X, Y, Z)) return r;
+  float wgt[4], inv_wsum;
+  blend_weights(params, C, wgt, &inv_wsum);
+  cudaError_t e = mrt_launch_fold(planar, C, X, Y, Z, wgt, inv_wsum, folded, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fold_volume");
+}
+int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C, float* dplanar, void* stream) {
+  MRT_REQUIRE(params && dfolded && dplanar, "unfold_grad: null pointer");
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("unfold_grad", C, X, Y, Z)) return r;
+  float wgt[4], inv_wsum;
+  blend_weights(params, C, wgt, &inv_wsum);
+  cudaError_t e = mrt_launch_unfold_grad(dfolded, C, X, Y, Z, wgt, inv_wsum, dplanar, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "unfold_grad");
 }
 
 // ---------------------------------------------------------------- occupancy

@@ -1,12 +1,15 @@
 // forward.cu — the ray-march forward kernel (brats_main, inr/viewer/brats_rt.slang:85-168).
 //
 // One warp = one 8x4 half of an 8x8 screen tile (rays of a warp stay in one brick
-// neighbourhood); MRT_FWD_TPB tiles per CTA.  Per ray: exact set-up (march.cuh), then a
-// segment loop: locate the 8^3 brick of the current sample slot, look up its per-frame skip
-// level, and either leap over the largest empty aligned cell around it (8..64 voxels; exact:
-// those slots are provably no-ops) or march the slots inside the brick: fp32 trilinear from the packed
-// multi-channel layout (8 vector loads per sample), modality blend, window/level, TF
-// (shared-memory LUT), front-to-back compositing with early ray termination.
+// neighbourhood); MRT_FWD_TPB tiles per CTA.  Per ray: exact set-up (march.cuh), then the
+// march as a two-phase loop that keeps the warp converged on the expensive part:
+//   phase 1 (cheap, per-lane loop): locate the 8^3 brick of the current sample slot, read its
+//           per-frame skip level, and leap over the largest empty aligned cell around it
+//           (8..64 voxels; exact: those slots are provably no-ops) until the slot lies in an
+//           active brick;
+//   phase 2 (all live lanes together): shade ONE slot — fp32 trilinear of the folded scalar
+//           field from the packed multi-channel layout (8 vector loads), saturate, TF
+//           (shared-memory LUT), front-to-back compositing, early ray termination.
 #include "march.cuh"
 #include "kernels.h"
 
@@ -25,17 +28,16 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
                float4* __restrict__ out_rgba,
                float* __restrict__ out_T,
                int4* __restrict__ out_counts) {
-  extern __shared__ float4 s_tf[];          // [tfN] LUT, then 16 label entries
-  float4* s_lab = s_tf + (P.tfMode ? P.tfN : 0);   // [0..7] seg (rgb, alpha), [8..15] pred
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);                        // [tfN]
+  float4* s_lab = reinterpret_cast<float4*>(s_tf + (P.tfMode ? P.tfN : 0));  // [0..7] seg, [8..15] pred
 
-  if (P.tfMode) {
-    for (int i = threadIdx.x; i < P.tfN; i += blockDim.x) s_tf[i] = __ldg(tf + i);
-  }
+  if (P.tfMode) mrt_tf_stage(s_tf, tf, P.tfN);
   if (LABELS) {
     if (threadIdx.x < 16) {
       const int l = threadIdx.x & 7;
       const float boost = threadIdx.x < 8 ? 1.0f : 1.5f;                   // :158
-      const float a = 1.0f - expf(-P.lut[l][3] * P.dt * boost);            // :147
+      const float a = mrt_alpha(P, P.lut[l][3] * boost);                   // :147
       s_lab[threadIdx.x] = make_float4(P.lut[l][0], P.lut[l][1], P.lut[l][2], (l > 0) ? a : 0.0f);
     }
   }
@@ -57,22 +59,21 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     const IdxRay q = mrt_index_ray(P, ray);
     const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
     const float dt = P.dt, thr = P.thr;
+    const float nm1 = (float)(P.tfN - 1);
 
     // one sample slot at ray parameter t  (:119-162)
     auto shade = [&](float t) {
       const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
       const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-      const float v = mrt_sample_blend<NCH>(P, vol, c);
-      const float val = mrt_window<GENERIC>(P, v);
+      const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH>(P, vol, c));
       if (P.tfMode) {
-        const float4 rgba = mrt_tf_lookup(s_tf, P.tfN, val);
-        const float alpha = 1.0f - expf(-rgba.w * dt);
+        const float4 rgba = mrt_tf_lookup(s_tf, nm1, val);
+        const float alpha = mrt_alpha(P, rgba.w);
         const float aT = alpha * T;
         Cr = fmaf(aT, rgba.x, Cr); Cg = fmaf(aT, rgba.y, Cg); Cb = fmaf(aT, rgba.z, Cb);
         T *= (1.0f - alpha);
       } else if (val > 0.0f) {                                             // :135
-        const float a = val * P.ia;
-        const float alpha = 1.0f - expf(-a * dt);                          // :137
+        const float alpha = mrt_alpha(P, val * P.ia);                      // :136-137
         const float c1 = alpha * T * val;                                  // :138
         Cr += c1; Cg += c1; Cb += c1;
         T *= (1.0f - alpha);                                               // :139
@@ -110,22 +111,26 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
       const float inv_dt = 1.0f / dt;
       const int n = ray.n;
-      while (k < n && T > thr) {
-        const float t = fmaf((float)k, dt, ray.t0);
-        const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-        const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-        const int bx = c.ix >> MRT_BRICK_SHIFT, by = c.iy >> MRT_BRICK_SHIFT, bz = c.iz >> MRT_BRICK_SHIFT;
-        const int lvl = __ldg(levels + ((bz * P.nby + by) * P.nbx + bx));
-        // active brick: march to the brick's exit; empty: leap over the largest empty aligned cell
-        const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-        const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, c.ix >> sh, c.iy >> sh, c.iz >> sh, sh, t, inv_dt));
-        const bool act = (lvl == 0);
-        if (GENERIC) ++n_seg;
-        if (!act) { k = kend; continue; }
-        do {
-          shade(fmaf((float)k, dt, ray.t0));
-          ++k; if (GENERIC) ++n_eval;
-        } while (k < kend && T > thr);
+      int kact = 0;                      // slots [k, kact) are known to lie in an active brick
+      for (;;) {
+        // phase 1: advance to the next slot inside an active brick
+        while (k >= kact && k < n && T > thr) {
+          const float t = fmaf((float)k, dt, ray.t0);
+          const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+          const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);               // == floor of the clamped coord
+          const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
+          const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+          const int lvl = __ldg(levels + (((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx +
+                                          (ix >> MRT_BRICK_SHIFT)));
+          const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+          const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
+          if (GENERIC) ++n_seg;
+          if (lvl) k = kend; else kact = kend;
+        }
+        if (!(k < n && T > thr)) break;                                    // :117
+        // phase 2: every live lane of the warp shades one slot
+        shade(fmaf((float)k, dt, ray.t0));
+        ++k; if (GENERIC) ++n_eval;
       }
     } else {
       const int n = ray.n;
@@ -143,25 +148,25 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
 
 // ------------------------------------------------------------------------- dispatch
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint8_t* bits,
+static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
-  const size_t smem = ((P.tfMode ? P.tfN : 0) + 16) * sizeof(float4);
+  const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
   mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC><<<grid, 64 * MRT_FWD_TPB, smem, st>>>(
-      P, (const typename Vox<NCH>::T*)vol, (const float4*)tf, bits, labels, preds,
+      P, (const typename Vox<NCH>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
 }
 
 template <int NCH>
 static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen, const void* vol, const float* tf,
-                                const uint8_t* bits, const int32_t* labels, const int32_t* preds,
+                                const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                 float* o, float* oT, int32_t* oc, cudaStream_t st) {
 #define MRT_CASE(L, S, G) if (lab == L && skip == S && gen == G) \
-    return launch_fwd<NCH, L, S, G>(P, vol, tf, bits, labels, preds, o, oT, oc, st);
+    return launch_fwd<NCH, L, S, G>(P, vol, tf, levels, labels, preds, o, oT, oc, st);
   MRT_CASE(false, false, false) MRT_CASE(false, true, false)
   MRT_CASE(true, false, false)  MRT_CASE(true, true, false)
   MRT_CASE(false, false, true)  MRT_CASE(false, true, true)
@@ -171,15 +176,15 @@ static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen,
 }
 
 cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                               const uint8_t* bits, const int32_t* labels, const int32_t* preds,
+                               const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st) {
   const bool lab = (P.showSeg || P.showPred);
-  const bool skip = P.skip && bits != nullptr && P.tMode == 0;
+  const bool skip = P.skip && levels != nullptr && P.tMode == 0;
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
   switch (packed_ch) {
-    case 1: return dispatch_fwd<1>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
-    case 2: return dispatch_fwd<2>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
-    case 4: return dispatch_fwd<4>(P, lab, skip, gen, vol, tf, bits, labels, preds, out_rgba, out_T, out_counts, st);
+    case 1: return dispatch_fwd<1>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 2: return dispatch_fwd<2>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 4: return dispatch_fwd<4>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
   }
   return cudaErrorInvalidValue;
 }

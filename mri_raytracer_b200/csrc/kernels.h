@@ -18,6 +18,11 @@ cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
 
+cudaError_t mrt_launch_fold(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                            float* folded, cudaStream_t st);
+cudaError_t mrt_launch_unfold_grad(const float* dfolded, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                                   float* dplanar, cudaStream_t st);
+
 cudaError_t mrt_launch_build_occupancy(const void* packed, int packed_ch, int X, int Y, int Z,
                                        float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int Z, uint8_t* any, cudaStream_t st);

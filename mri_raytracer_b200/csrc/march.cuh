@@ -26,6 +26,9 @@ struct KParams {
   float wgt[4];           // volWeight if enabled else 0
   float inv_wsum;         // 1/wSum if wSum > 0 else 1
   float lo, inv_ww;       // window: val = saturate((v - lo) * inv_ww)
+  float wq[4];            // folded per-channel weight wgt[c]*inv_wsum*inv_ww
+  float wbias;            // -lo*inv_ww
+  float neg_dt_log2e;     // -dt*log2(e)
   float ia, gamma;
   int showSeg, showPred;
   float lut[8][4];
@@ -116,19 +119,15 @@ template <> struct Vox<2> { typedef float2 T; };
 template <> struct Vox<4> { typedef float4 T; };
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
-__device__ __forceinline__ float  vlerp(float a, float b, float t) { return lerpf(a, b, t); }
-__device__ __forceinline__ float2 vlerp(float2 a, float2 b, float t) {
-  return make_float2(lerpf(a.x, b.x, t), lerpf(a.y, b.y, t));
-}
-__device__ __forceinline__ float4 vlerp(float4 a, float4 b, float t) {
-  return make_float4(lerpf(a.x, b.x, t), lerpf(a.y, b.y, t), lerpf(a.z, b.z, t), lerpf(a.w, b.w, t));
-}
-__device__ __forceinline__ float blendv(float s, const KParams& P) { return s * P.wgt[0]; }
-__device__ __forceinline__ float blendv(float2 s, const KParams& P) {
-  return fmaf(s.y, P.wgt[1], s.x * P.wgt[0]);
-}
-__device__ __forceinline__ float blendv(float4 s, const KParams& P) {
-  return fmaf(s.w, P.wgt[3], fmaf(s.z, P.wgt[2], fmaf(s.y, P.wgt[1], s.x * P.wgt[0])));
+
+// Folded modality blend + window/level of ONE voxel (all four are linear maps, so they commute
+// with the trilinear interpolation; doing them per corner turns 7 vector lerps into 7 scalar
+// ones):  sum_c wq[c]*s_c  with  wq[c] = volWeight[c]/wSum/ww  (0 for disabled channels).
+// The constant -(wl - ww/2)/ww is added once after interpolation (weights sum to 1).
+__device__ __forceinline__ float foldv(float s, const KParams& P) { return s * P.wq[0]; }
+__device__ __forceinline__ float foldv(float2 s, const KParams& P) { return fmaf(s.y, P.wq[1], s.x * P.wq[0]); }
+__device__ __forceinline__ float foldv(float4 s, const KParams& P) {
+  return fmaf(s.w, P.wq[3], fmaf(s.z, P.wq[2], fmaf(s.y, P.wq[1], s.x * P.wq[0])));
 }
 
 // Index-space ray: pIdx(t) = oi + t*di  (== (o + t*d - bmin)/voxelSize up to rounding).
@@ -156,9 +155,11 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
   return c;
 }
 
+// sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
+// raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
 template <int NCH>
-__device__ __forceinline__ float mrt_sample_blend(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
-                                                  const Cell& c) {
+__device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
+                                                const Cell& c) {
   typedef typename Vox<NCH>::T VT;
   const uint32_t sY = P.pitchY;
   const uint32_t sZ = P.pitchZ;
@@ -167,13 +168,15 @@ __device__ __forceinline__ float mrt_sample_blend(const KParams& P, const typena
   const VT* p1 = p0 + sY;
   const VT* p2 = p0 + sZ;
   const VT* p3 = p2 + sY;
-  const VT c000 = __ldg(p0), c100 = __ldg(p0 + 1);
-  const VT c010 = __ldg(p1), c110 = __ldg(p1 + 1);
-  const VT c001 = __ldg(p2), c101 = __ldg(p2 + 1);
-  const VT c011 = __ldg(p3), c111 = __ldg(p3 + 1);
-  const VT s = vlerp(vlerp(vlerp(c000, c100, c.fx), vlerp(c010, c110, c.fx), c.fy),
-                     vlerp(vlerp(c001, c101, c.fx), vlerp(c011, c111, c.fx), c.fy), c.fz);
-  return blendv(s, P) * P.inv_wsum;
+  const VT v000 = __ldg(p0), v100 = __ldg(p0 + 1);
+  const VT v010 = __ldg(p1), v110 = __ldg(p1 + 1);
+  const VT v001 = __ldg(p2), v101 = __ldg(p2 + 1);
+  const VT v011 = __ldg(p3), v111 = __ldg(p3 + 1);
+  const float c000 = foldv(v000, P), c100 = foldv(v100, P), c010 = foldv(v010, P), c110 = foldv(v110, P);
+  const float c001 = foldv(v001, P), c101 = foldv(v101, P), c011 = foldv(v011, P), c111 = foldv(v111, P);
+  const float s = lerpf(lerpf(lerpf(c000, c100, c.fx), lerpf(c010, c110, c.fx), c.fy),
+                        lerpf(lerpf(c001, c101, c.fx), lerpf(c011, c111, c.fx), c.fy), c.fz);
+  return s + P.wbias;
 }
 
 // sampleLabel (brats_rt.slang:78-83): round half away from zero.
@@ -187,25 +190,41 @@ __device__ __forceinline__ int mrt_sample_label(const KParams& P, const int32_t*
   return __ldg(lab + idx);
 }
 
-// window/level (+gamma) (brats_rt.slang:132-133)
+// saturate (+gamma) (brats_rt.slang:132-133)
 template <bool GENERIC>
-__device__ __forceinline__ float mrt_window(const KParams& P, float v) {
-  float val = __saturatef((v - P.lo) * P.inv_ww);
+__device__ __forceinline__ float mrt_window(const KParams& P, float raw) {
+  float val = __saturatef(raw);
   if (GENERIC) { if (P.gamma != 1.0f) val = powf(val, P.gamma); }
   return val;
 }
 
-// 1D LUT lookup: u = val*(N-1), lerp(tf[floor u], tf[min(floor u + 1, N-1)], frac)
-__device__ __forceinline__ float4 mrt_tf_lookup(const float4* __restrict__ s_tf, int N, float val,
-                                                int* j0o = nullptr, int* j1o = nullptr, float* fro = nullptr) {
-  const float u = val * (float)(N - 1);
-  const float j0f = floorf(u);
-  const float fr = u - j0f;
-  const int j0 = min(max((int)j0f, 0), N - 1);
-  const int j1 = min(j0 + 1, N - 1);
-  const float4 a = s_tf[j0], b = s_tf[j1];
-  if (j0o) { *j0o = j0; *j1o = j1; *fro = fr; }
-  return make_float4(lerpf(a.x, b.x, fr), lerpf(a.y, b.y, fr), lerpf(a.z, b.z, fr), lerpf(a.w, b.w, fr));
+// alpha = 1 - exp(-sigma*dt)  (:137) as 1 - 2^(sigma * (-dt*log2 e)): one FMUL + MUFU.EX2.
+// ex2.approx is accurate to 2 ulp of a result in (0,1], i.e. ~1.2e-7 absolute on alpha.
+__device__ __forceinline__ float mrt_alpha(const KParams& P, float sigma) {
+  return 1.0f - exp2f(sigma * P.neg_dt_log2e);
+}
+
+// Shared-memory LUT: entry j holds tf[j] and the forward difference tf[min(j+1,N-1)] - tf[j],
+// so the lerp of SURVEY §8 A7  (u = val*(N-1); lerp(tf[floor u], tf[min(floor u+1,N-1)], frac))
+// is one fma per component with the SAME rounding as a + t*(b-a).
+struct TfEntry { float4 base, delta; };
+
+__device__ __forceinline__ void mrt_tf_stage(TfEntry* __restrict__ s_tf, const float4* __restrict__ tf, int N) {
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 a = __ldg(tf + i), b = __ldg(tf + min(i + 1, N - 1));
+    s_tf[i].base = a;
+    s_tf[i].delta = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
+  }
+}
+
+__device__ __forceinline__ float4 mrt_tf_lookup(const TfEntry* __restrict__ s_tf, float nm1, float val,
+                                                int* j0o = nullptr, float* fro = nullptr) {
+  const float u = val * nm1;                 // val in [0,1] => 0 <= floor(u) <= N-1
+  const int j0 = (int)u;
+  const float fr = u - (float)j0;
+  const float4 a = s_tf[j0].base, d = s_tf[j0].delta;
+  if (j0o) { *j0o = j0; *fro = fr; }
+  return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
 }
 
 // Physical lane (0..31) of a warp -> logical lane (0..63) inside the 8x8 tile.  A warp owns an

@@ -73,6 +73,64 @@ cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, fl
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ modality fold
+// The modality blend (brats_rt.slang:123-130), v = sum_c w_c s_c / wSum, is linear, so it
+// commutes with trilinear interpolation: blending the <=4 planar channels ONCE per
+// (weights, enabled) setting into a single-channel volume lets the march gather 8 scalars
+// per sample instead of 8 float4.  Output is the packed C=1 layout (bank-skewed pitches).
+__global__ void __launch_bounds__(256)
+mrt_fold_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                float w0, float w1, float w2, float w3, float inv_wsum, float* __restrict__ folded) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const size_t src = (size_t)row * X, dst = (size_t)y * pitchY + (size_t)z * pitchZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      float v = __ldg(planar + src + x) * w0;
+      if (C > 1) v = fmaf(__ldg(planar + nvox + src + x), w1, v);
+      if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src + x), w2, v);
+      if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src + x), w3, v);
+      folded[dst + x] = v * inv_wsum;
+    }
+  }
+}
+// adjoint of the fold: dL/dplanar[c] = (w_c / wSum) * dL/dfolded
+__global__ void __launch_bounds__(256)
+mrt_unfold_grad_kernel(const float* __restrict__ dfolded, int C, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                       float w0, float w1, float w2, float w3, float inv_wsum, float* __restrict__ dplanar) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const int rows = Y * Z;
+  const float w[4] = {w0 * inv_wsum, w1 * inv_wsum, w2 * inv_wsum, w3 * inv_wsum};
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const size_t dst = (size_t)row * X, src = (size_t)y * pitchY + (size_t)z * pitchZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      const float g = __ldg(dfolded + src + x);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < C) dplanar[(size_t)c * nvox + dst + x] = g * w[c];
+    }
+  }
+}
+cudaError_t mrt_launch_fold(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                            float* folded, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout(1, X, Y, Z, &pY, &pZ);
+  const int g = grid_for((size_t)Y * Z * 256, 256);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  mrt_fold_kernel<<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, folded);
+  return cudaGetLastError();
+}
+cudaError_t mrt_launch_unfold_grad(const float* dfolded, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                                   float* dplanar, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout(1, X, Y, Z, &pY, &pZ);
+  const int g = grid_for((size_t)Y * Z * 256, 256);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  mrt_unfold_grad_kernel<<<g, blk, 0, st>>>(dfolded, C, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, dplanar);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ tile map on device
 __global__ void mrt_tile_map_kernel(int W, int H, int32_t* __restrict__ out_tile, int32_t* __restrict__ out_lane) {
   // same launch geometry as the renderer: 64 threads (one 8x8 tile) per CTA

@@ -40,10 +40,7 @@ def _default_render_fn(volume, tf):
     from . import api
 
     def fn(P: RenderParams, tile_range: Tuple[int, int], out: torch.Tensor):
-        P = replace(P, tfMode=1 if tf is not None else 0)
-        bits = volume.skip_levels(P, tf)
-        api.render_forward(P, volume.packed, volume.C, tf, bits, volume.labels, volume.preds, out=out,
-                           tile_range=tile_range)
+        volume.forward(replace(P, tfMode=1 if tf is not None else 0), tf, out=out, tile_range=tile_range)
     return fn
 
 
@@ -67,7 +64,7 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
     W, H = P.imageSize
     V = len(cams)
     fn = render_fn or _default_render_fn(volume, tf)
-    device = device if device is not None else (volume.packed.device if hasattr(volume, "packed") else "cpu")
+    device = device if device is not None else getattr(volume, "device", "cpu")
     nt = tiles.tile_count(W, H)
     if mode == "views":
         if V % R != 0:

@@ -27,10 +27,10 @@ def _oracle_grads(vol, P, tf, G, labels=None, preds=None, dtype=torch.float32):
     return img.detach(), v.grad, (None if t is None else t.grad), aux
 
 
-@pytest.mark.parametrize("C", [1, 2, 4])
-def test_backward_lut_matches_autograd(cuda, C):
+@pytest.mark.parametrize("C,fold", [(1, False), (2, False), (4, False), (3, True), (4, True)])
+def test_backward_lut_matches_autograd(cuda, C, fold):
     vol, _, P = small_scene(C=C, dims=(28, 24, 20), W=40, H=32, seed=10 + C)
-    P = replace(P, tfMode=1, alphaMode=1, bgColor=(0.1, 0.0, 0.2))
+    P = replace(P, tfMode=1, alphaMode=1, bgColor=(0.1, 0.0, 0.2), volWeight=(1.0, 0.5, 2.0, 0.75))
     tf = ramp_tf(32, sigma_scale=15.0, cutoff=0.2)
     tf[:, 1] = tf[:, 1] ** 2          # colour channels differ so dL/dtf rgb is exercised
     tf[:, 2] = 1.0 - tf[:, 2]
@@ -40,7 +40,7 @@ def test_backward_lut_matches_autograd(cuda, C):
     assert float(aux["ert_margin"].min()) > 1e-4, "pick another seed: an ERT tie would make the comparison ambiguous"
     v = vol.cuda().requires_grad_(True)
     t = tf.cuda().requires_grad_(True)
-    img = api.render(v, None, t, P)
+    img = api.render(v, None, t, P, fold=fold)
     (img * G.cuda()).sum().backward()
     assert (img.detach().cpu() - img_o).abs().max() <= 1e-4
     assert _rel(v.grad.cpu(), gv_o) <= RTOL

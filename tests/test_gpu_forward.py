@@ -14,8 +14,9 @@ from parity import check_forward, O
 pytestmark = pytest.mark.gpu
 
 
-def _render_both(vol, P, tf, lab=None, prd=None, dev="cuda"):
-    V = api.Volume(vol.to(dev), labels=None if lab is None else lab.to(dev), preds=None if prd is None else prd.to(dev))
+def _render_both(vol, P, tf, lab=None, prd=None, dev="cuda", fold=True):
+    V = api.Volume(vol.to(dev), labels=None if lab is None else lab.to(dev), preds=None if prd is None else prd.to(dev),
+                   fold=fold)
     tfd = None if tf is None else tf.to(dev)
     img = api.render(V, None, tfd, P)
     img2, T, counts = api.render_aux(V, None, tfd, P)
@@ -25,11 +26,14 @@ def _render_both(vol, P, tf, lab=None, prd=None, dev="cuda"):
 
 @pytest.mark.parametrize("C", [1, 2, 3, 4])
 @pytest.mark.parametrize("use_tf", [False, True])
-def test_forward_matches_oracle(cuda, C, use_tf):
+@pytest.mark.parametrize("fold", [False, True])
+def test_forward_matches_oracle(cuda, C, use_tf, fold):
+    if fold and C == 1:
+        pytest.skip("folding is the identity for one modality")
     vol, _, P = small_scene(C=C, dims=(40, 36, 28), W=72, H=56, seed=C)
     tf = ramp_tf(64) if use_tf else None
-    P = replace(P, intensityAlpha=25.0)
-    img, img2, T, counts = _render_both(vol, P, tf)
+    P = replace(P, intensityAlpha=25.0, volWeight=(1.0, 0.5, 2.0, 0.75), volEnabled=(1, 1, 0 if C == 4 else 1, 1))
+    img, img2, T, counts = _render_both(vol, P, tf, fold=fold)
     assert torch.equal(img, img2), "fast and counting kernel variants must agree bit-for-bit"
     stats, ref, aux = check_forward(img, counts, vol, replace(P, tfMode=int(use_tf)), tf)
     assert stats["max_abs"] <= 1e-4
@@ -102,15 +106,25 @@ def test_ragged_image_sizes_and_tile_ranges(cuda):
         nt = tiles.tile_count(W, H)
         out = torch.full((H, W, 4), -7.0, device="cuda")
         for r in range(2):
-            api.render_forward(replace(P, tfMode=0), V.packed, V.C, None, V.skip_levels(P, None), out=out,
-                               tile_range=tiles.rank_tile_range(nt, r, 2))
+            V.forward(replace(P, tfMode=0), None, out=out, tile_range=tiles.rank_tile_range(nt, r, 2))
         assert torch.equal(out, full)
+
+
+def test_refold_when_weights_change(cuda):
+    vol, _, P = small_scene(C=4, dims=(32, 28, 24), W=40, H=32, seed=9)
+    V = api.Volume(vol.cuda())
+    a = api.render(V, None, None, replace(P, intensityAlpha=8.0)).cpu()
+    P2 = replace(P, intensityAlpha=8.0, volWeight=(0.2, 3.0, 1.0, 0.0), volEnabled=(1, 1, 0, 1))
+    b = api.render(V, None, None, P2).cpu()
+    assert (a - b).abs().max() > 1e-3
+    assert (b - O.render(vol, P2)).abs().max() <= 1e-4
+    assert (api.render(V, None, None, replace(P, intensityAlpha=8.0)).cpu() - a).abs().max() == 0.0
 
 
 def test_render_host_entry_point(cuda):
     vol, _, P = small_scene(C=4, dims=(32, 28, 24), W=40, H=32, seed=6)
     tf = ramp_tf(128)
-    V = api.Volume(vol.cuda())
+    V = api.Volume(vol.cuda(), fold=False)
     dev_img = api.render(V, None, tf.cuda(), P).cpu()
     host_img = api.render_host(vol.numpy(), P, tf.numpy())
     assert np.array_equal(host_img, dev_img.numpy())
