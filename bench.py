@@ -74,6 +74,59 @@ def _scene(views: int):
     return P, cams
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons DURING the timed region, polled through NVML every ~2 ms (the
+    timed region of a default run is tens of ms: too short for `nvidia-smi -lms`)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop_flag, self.thread, self.ok = index, [], False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        if not self.ok:
+            return None
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, r in self.rows:
+            bits |= r
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(k for k, m in names.items() if bits & m)
+        try:
+            smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            smax = None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": reasons,
+                "samples": len(sm), "source": "NVML polled every 2 ms during the timed region"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -118,48 +171,59 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_sample(stride: int, threads: int):
-    """The reference CPU path = the CPU-torch oracle, on a bounded sample:
-    every `stride`-th pixel in x and y of view 0.  Returns (samples_taken, callable)."""
+def cpu_reference_sample(stride: int, threads: int, kind: str = "c"):
+    """The reference CPU path.  The reference ships no CPU renderer (its arithmetic exists only as
+    Slang shaders), so this is the oracle port: `kind="c"` = oracle/oracle_c.c (scalar C, POSIX
+    threads over all host cores — the faster of the two, hence the baseline we quote);
+    `kind="torch"` = oracle/oracle_torch.py (BASELINE.md section 4's CPU-torch path).  Bounded
+    sample: every `stride`-th pixel in x and y of view 0.  Returns (callable -> samples taken, text)."""
     import torch
-    from oracle import oracle_torch as O
     from mri_raytracer_b200.synth import make_brats_like, ramp_tf
-    torch.set_num_threads(threads)
     vol = make_brats_like(NCH, DIMS, seed=0)
     tf = ramp_tf(TF_N)
     P, cams = _scene(8)
     P0 = P.with_camera(cams[0])
     ys, xs = torch.meshgrid(torch.arange(0, IMG, stride), torch.arange(0, IMG, stride), indexing="ij")
     px, py = xs.reshape(-1), ys.reshape(-1)
+    what = f"view 0, every {stride}th pixel in x and y ({px.numel()} of {IMG * IMG} rays)"
+    if kind == "c":
+        from oracle import oracle_c
+        voln, tfn, pxn, pyn = vol.numpy(), tf.numpy(), px.numpy(), py.numpy()
+
+        def run():
+            _, aux = oracle_c.render(voln, P0, tf=tfn, pixels=(pxn, pyn), return_aux=True, threads=threads)
+            return int(aux["n_taken"].sum())
+        return run, what + f", scalar C oracle, {threads} POSIX threads, fp32"
+    from oracle import oracle_torch as O
+    torch.set_num_threads(threads)
 
     def run():
         _, aux = O.render(vol, P0, tf=tf, pixels=(px, py), return_aux=True)
         return int(aux["n_taken"].sum())
-    return run, f"view 0, every {stride}th pixel in x and y ({px.numel()} of {IMG * IMG} rays), CPU-torch oracle fp32"
+    return run, what + f", CPU-torch oracle, {threads} threads, fp32"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     threads = os.cpu_count() or 1
-    run, sample = cpu_reference_sample(stride=4, threads=threads)
+    stride = 2                                  # 1/4 of a frame's rays per step
+    run, sample = cpu_reference_sample(stride=stride, threads=threads, kind="c")
     for _ in range(max(args.warmup, 1)):
-        n = run()
+        run()
     t0 = time.perf_counter()
     tot = 0
     for _ in range(args.steps):
         tot += run()
     dt = time.perf_counter() - t0
     val = tot / dt
-    frames = args.steps / 16.0 / dt           # one step = 1/16 of a frame's rays
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": sample},
-        "frames_per_sec_equiv": frames,
+        "frames_per_sec": args.steps / float(stride * stride) / dt,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -195,7 +259,7 @@ def run_ours(args):
     tf_host = ramp_tf(TF_N)
     vol = vol_host.to(dev, non_blocking=True)
     tf = tf_host.to(dev)
-    volume = api.Volume(vol)
+    volume = api.Volume(vol, fold=not args.no_fold)
     W = H = IMG
     nt = tiles.tile_count(W, H)
     mode = args.mode if world > 1 else "views"
@@ -218,6 +282,7 @@ def run_ours(args):
 
     def step(record_kernels: bool):
         """One orbit batch through the public API; returns nothing (frames land in `frames`)."""
+        volume.invalidate()      # every step re-folds the modalities + rebuilds the occupancy grid
         if world == 1:
             for v, c in enumerate(cams):
                 Pv = P.with_camera(c)
@@ -241,7 +306,9 @@ def run_ours(args):
         step(False)
     barrier()
 
-    sampler = ClockSampler(local)
+    sampler = NvmlSampler(local)
+    if not sampler.ok:
+        sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     step_ms = []
@@ -267,7 +334,8 @@ def run_ours(args):
         durs = [a.elapsed_time(b) for a, b, _ in kern_ev]
         avg_ms = sum(durs) / len(durs)
         avg_eval = sum(per_view_eval[v] for _, _, v in kern_ev) / len(kern_ev)
-        bytes_per_sample = 32 * NCH                                   # 8 corners x 4 B x C
+        kch = 1 if volume.fold else NCH                               # channels the march kernel gathers
+        bytes_per_sample = 32 * kch                                   # 8 corners x 4 B x C
         achieved = avg_eval * bytes_per_sample / (avg_ms * 1e-3) / 1e9
         peak, which = _peaks()
         traffic = None
@@ -275,12 +343,18 @@ def run_ours(args):
         if tp.exists():
             traffic = json.loads(tp.read_text()).get("mrt_fwd_kernel_dram_bytes_per_launch")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": which, "kernel": "mrt_fwd_kernel<4,false,true,false>",
+                "traffic": traffic, "peak_source": which,
+                "kernel": f"mrt_fwd_kernel<{kch},false,true,false>",
                 "avg_launch_ms": avg_ms, "bytes_per_sample": bytes_per_sample,
+                "achieved_at_survey_128B_per_sample": avg_eval * 32 * NCH / (avg_ms * 1e-3) / 1e9,
                 "evaluated_samples_per_launch": avg_eval,
                 "nominal_samples_per_launch": taken / V,
-                "note": "achieved counts only samples whose 8 corner fetches were really issued; "
-                        "the nominal (oracle-defined) count includes slots skipped as provably empty"}
+                "note": "achieved = bytes the march kernel's own gathers request (8 corners x 4 B x channels "
+                        "it reads; 1 channel after the modality fold) x samples whose fetches were really "
+                        "issued / CUDA-event launch time. The nominal (oracle-defined) sample count also "
+                        "includes slots skipped as provably empty. The volume is L1/L2 resident (DRAM traffic "
+                        "per launch is ~1e-2 of this), so the HBM peak is a reference line, not the bound: "
+                        "see DESIGN.md"}
 
     # ---- e2e: host buffers in, host frames out, through the public API (N = 1 path)
     e2e = None
@@ -316,18 +390,23 @@ def run_ours(args):
                "h2d_bytes_per_step": int(vol_host.numel() * 4 + tf_host.numel() * 4 + V * 400),
                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": 1e3 * t_e2e / ks,
                "frames_per_sec": V * ks / t_e2e,
-               "what": "per step: pinned-host volume H2D + pack + occupancy build + V x (classify, march) + "
+               "what": "per step: pinned-host volume H2D + modality fold + occupancy build + V x (classify, march) + "
                        "V frames D2H to pinned host, wall clock with synchronize on both sides"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        run, sample = cpu_reference_sample(stride=2, threads=threads)
+        run, sample = cpu_reference_sample(stride=1, threads=threads, kind="c")
+        run_t, sample_t = cpu_reference_sample(stride=4, threads=threads, kind="torch")
         t0 = time.perf_counter()
         n = run()
         dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": dt}
+        t0 = time.perf_counter()
+        nt_ = run_t()
+        dtt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": dt,
+               "torch_oracle": {"value": nt_ / dtt, "sample": sample_t, "seconds": dtt}}
 
     if rank == 0:
         line = {
@@ -339,7 +418,8 @@ def run_ours(args):
             "frames_per_sec": V * args.steps / tot_s,
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * V * args.steps if world == 1 else 2 * V * args.steps // world,
+            "gpu_launches": (2 * V + (2 if volume.fold else 1)) * args.steps if world == 1
+            else (2 * V // world + (2 if volume.fold else 1)) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -355,6 +435,7 @@ def main():
     ap.add_argument("--views", type=int, default=8, help="frames per step (orbit batch)")
     ap.add_argument("--mode", default="views", choices=["views", "tiles"], help="multi-GPU partition")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    ap.add_argument("--no-fold", action="store_true", help="blend modalities per sample (float4 gathers) instead of folding")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

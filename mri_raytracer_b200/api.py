@@ -218,6 +218,11 @@ class Volume:
             self._key = key
         return self.packed, 1, folded_params(P)
 
+    def invalidate(self):
+        """Drop the folded-volume cache (the next frame re-folds and rebuilds the occupancy grid)."""
+        if self.fold:
+            self._key = None
+
     def set_labels(self, labels: Optional[torch.Tensor]):
         """gLabels (inr/viewer/brats_viewer.py:233-237)."""
         self.labels = self._check_labels(labels)
@@ -360,7 +365,7 @@ def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tens
 
 
 def render_slab(vol_u8: torch.Tensor, camera: Optional[Camera], params: SlabParams,
-                tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                tile_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The single-volume slab renderer (``volume_cs``, volume_render.slang:104-148) over a
     uint8 ``[Z,Y,X]`` CUDA volume -> float32 ``[H,W,4]``."""
     _need_cuda(vol_u8, "vol_u8", torch.uint8)
@@ -369,7 +374,8 @@ def render_slab(vol_u8: torch.Tensor, camera: Optional[Camera], params: SlabPara
     if tuple(P.volDim) != (X, Y, Z):
         raise ValueError(f"params.volDim {P.volDim} != volume dims {(X, Y, Z)}")
     W, H = P.imageSize
-    out = torch.empty((H, W, 4), dtype=torch.float32, device=vol_u8.device)
+    if out is None:
+        out = torch.empty((H, W, 4), dtype=torch.float32, device=vol_u8.device)
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     s = P.to_struct()
     check(lib().mrt_render_slab_u8(C.byref(s), vol_u8.data_ptr(), out.data_ptr(), t0, t1, _stream()), "render_slab")

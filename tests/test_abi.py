@@ -1,0 +1,59 @@
+"""The C ABI: the library loads, exports every symbol include/mrt.h declares, and the
+MrtParams layout begins with the reference's 368-byte `struct Params` cbuffer
+(inr/viewer/brats_rt.slang:12-31).  No GPU needed (no compute calls)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+from mri_raytracer_b200 import RenderParams, _lib
+from mri_raytracer_b200._lib import MrtParams, MrtSlabParams, PROTOTYPES
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_functions():
+    src = (ROOT / "include" / "mrt.h").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(built_lib):
+    names = _declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(built_lib, n), f"libmrt.so lacks {n}"
+        assert n in PROTOTYPES, f"_lib.py does not bind {n}"
+    assert sorted(PROTOTYPES) == names
+    assert built_lib.mrt_version() == 100
+    assert built_lib.mrt_last_error() is not None
+
+
+def test_params_layout_matches_reference_cbuffer(built_lib):
+    assert built_lib.mrt_sizeof_params() == C.sizeof(MrtParams) == 400
+    assert built_lib.mrt_sizeof_slab_params() == C.sizeof(MrtSlabParams)
+    off = {f[0]: getattr(MrtParams, f[0]).offset for f in MrtParams._fields_}
+    # 16-byte rows of the cbuffer, in order
+    want = dict(imageSize=0, fovY=8, eye=16, U=32, V=48, W=64, volMin=80, voxelSize=96, dims=112, stepSize=128,
+                nearT=132, farT=136, bgColor=144, volEnabled=160, volWeight=176, ww=192, wl=196, intensityAlpha=200,
+                gamma=208, gradBoost=212, gradScale=216, showSeg=224, showPred=228, lutColorAlpha=240, ortho=368)
+    for k, v in want.items():
+        assert off[k] == v, (k, off[k], v)
+
+
+def test_render_params_round_trip():
+    P = RenderParams(imageSize=(33, 17), dims=(5, 6, 7), volEnabled=(1, 0, 1, 0), volWeight=(1, 2, 3, 4), tMode="accumulate")
+    s = P.to_struct()
+    assert tuple(s.imageSize) == (33, 17) and tuple(s.dims) == (5, 6, 7)
+    assert tuple(s.volEnabled) == (1, 0, 1, 0) and s.tMode == 1
+    assert abs(s.lutColorAlpha[2][1] - 0.8) < 1e-7 and s.lutColorAlpha[3][0] == 1.0
+
+
+def test_host_side_helpers_need_no_gpu(built_lib):
+    py, pz = C.c_int64(), C.c_int64()
+    for Cn, S in ((1, 32), (2, 16), (4, 8)):
+        built_lib.mrt_packed_layout(Cn, 240, 240, 155, C.byref(py), C.byref(pz))
+        assert py.value >= 240 and pz.value >= py.value * 240
+        assert py.value % S == S // 4 and pz.value % S == S // 2
+        assert built_lib.mrt_packed_volume_bytes(Cn, 240, 240, 155) == pz.value * 155 * 4 * Cn
+    assert built_lib.mrt_brick_count(240, 240, 155) == 30 * 30 * 20
+    assert built_lib.mrt_packed_volume_bytes(5, 8, 8, 8) == 0
