@@ -66,7 +66,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + blockIdx.x * MRT_BWD_TPB + (warp >> 1);
+  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_BWD_TPB + (warp >> 1);
   int px = -1, py = -1;
   bool live = tile < P.tile_end;
   if (live) {

@@ -44,7 +44,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + blockIdx.x * MRT_FWD_TPB + (warp >> 1);
+  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
   if (tile >= P.tile_end) return;
   int px, py;
   mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);

@@ -227,6 +227,17 @@ __device__ __forceinline__ float4 mrt_tf_lookup(const TfEntry* __restrict__ s_tf
   return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
 }
 
+// CTA index -> position in the launch's tile range, "middle-out": CTA 0 takes the middle of the
+// range and successive CTAs alternate outward.  The tile ids of a frame are row-major, so the
+// rows through the image centre — where the camera frames the volume and rays are longest —
+// are scheduled first and the cheap border rows last: the tail of the grid is filled with
+// short CTAs instead of leaving SMs idle behind a few long ones (ncu: SM-active 61 % -> see
+// profiles/).  Pure integer map, a bijection of [0, n).
+__device__ __forceinline__ int mrt_middle_out(int b, int n) {
+  const int mid = n >> 1;
+  return (b & 1) ? mid - 1 - (b >> 1) : mid + (b >> 1);
+}
+
 // Physical lane (0..31) of a warp -> logical lane (0..63) inside the 8x8 tile.  A warp owns an
 // 8-wide x 4-tall half tile; each group of 8 consecutive lanes (the unit a 128-bit load is
 // processed in) is a compact 4x2 pixel block, so its eight 2x2x2 footprints overlap as much

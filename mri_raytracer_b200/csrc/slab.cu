@@ -43,7 +43,7 @@ struct SlabK {
 __global__ void __launch_bounds__(128)
 mrt_slab_kernel(const __grid_constant__ SlabK P, const uint8_t* __restrict__ vol, float4* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + blockIdx.x * 2 + (warp >> 1);
+  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * 2 + (warp >> 1);
   if (tile >= P.tile_end) return;
   int px, py;
   mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);

@@ -1,0 +1,142 @@
+"""Secondary measurements: the other BASELINE.json configs on one GPU (not the bench.py headline).
+
+    python tools/bench_configs.py cfg1 cfg3 cfg4
+
+cfg1: 1x240x240x155, 512^2 orthographic, step 0.5 voxel, 256-entry LUT (the reference's CPU-runnable case)
+cfg3: differentiable rendering, forward+backward over a 256^3 volume and TF at 512^2
+cfg4: orbit views at 2048^2 over a 512^3 volume (8 of the 64 views per timing batch on one GPU)
+Each line: device time (CUDA events, pipelined launches), sample counts, and an oracle parity
+spot check on a strided subset of pixels (forward) / a small-scene gradient check (cfg3).
+"""
+import json
+import math
+import sys
+import time
+from dataclasses import replace
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+
+from mri_raytracer_b200 import api  # noqa: E402
+from mri_raytracer_b200.synth import make_brats_like, ramp_tf  # noqa: E402
+from scenes import framed_params  # noqa: E402
+
+
+def timeit(fn, n=5, warm=2, reps=4):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def parity_subset(vol_cpu, P, tf_cpu, img, stride):
+    from oracle import oracle_c
+    W, H = P.imageSize
+    ys, xs = torch.meshgrid(torch.arange(0, H, stride), torch.arange(0, W, stride), indexing="ij")
+    px, py = xs.reshape(-1).numpy(), ys.reshape(-1).numpy()
+    ref = oracle_c.render(vol_cpu.numpy(), P, tf=None if tf_cpu is None else tf_cpu.numpy(), pixels=(px, py), threads=16)
+    got = img.cpu().numpy()[py, px]
+    d = abs(got - ref).max(axis=-1)
+    return float(d.max()), int((d > 1e-4).sum()), int(px.size)
+
+
+def cfg1():
+    dims = (240, 240, 155)
+    vol = make_brats_like(1, dims, seed=0)
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 512, 512, ortho=True), tfMode=1)
+    V = api.Volume(vol.cuda())
+    tfd = tf.cuda()
+    img, T, counts = api.render_aux(V, None, tfd, P)
+    c = counts.sum(dim=(0, 1)).tolist()
+    ms = timeit(lambda: api.render(V, None, tfd, P), reps=10)
+    mx, nbad, npx = parity_subset(vol, P, tf, img, 4)
+    return dict(cfg="cfg1", ms_per_frame=ms, fps=1e3 / ms, samples_taken=c[1], samples_evaluated=c[2],
+                gsamples_per_s=c[1] / ms / 1e6, parity_max_abs=mx, parity_pixels_over_1e4=nbad, parity_pixels=npx)
+
+
+def cfg3():
+    dims = (256, 256, 256)
+    vol = make_brats_like(1, dims, seed=4)
+    tf = ramp_tf(256, sigma_scale=20.0, cutoff=0.05)
+    P = replace(framed_params(dims, 512, 512), tfMode=1)
+    with torch.no_grad():
+        target = api.render(api.Volume(vol.cuda()), None, (tf * torch.tensor([0.8, 1.0, 1.1, 1.3])).cuda(), P)
+    v = vol.cuda().requires_grad_(True)
+    t = tf.cuda().requires_grad_(True)
+
+    def step():
+        v.grad = None; t.grad = None
+        loss = ((api.render(v, None, t, P) - target) ** 2).mean()
+        loss.backward()
+        return loss
+
+    ms = timeit(step, reps=2)
+    Vv = api.Volume(vol.cuda())
+    _, _, counts = api.render_aux(Vv, None, tf.cuda(), P)
+    c = counts.sum(dim=(0, 1)).tolist()
+    ms_fwd = timeit(lambda: api.render(Vv, None, t.detach(), P), reps=4)
+    # gradient parity on a small scene (the oracle's autograd cannot hold 256^3 x 512^2)
+    from scenes import small_scene
+    from oracle import oracle_torch as O
+    sv, _, sP = small_scene(C=1, dims=(32, 32, 32), W=48, H=48, seed=4)
+    sP = replace(sP, tfMode=1)
+    stf = ramp_tf(64, sigma_scale=20.0, cutoff=0.05)
+    a = sv.clone().requires_grad_(True); b = stf.clone().requires_grad_(True)
+    O.render(a, sP, tf=b).square().mean().backward()
+    ga = sv.cuda().requires_grad_(True); gb = stf.cuda().requires_grad_(True)
+    api.render(ga, None, gb, sP).square().mean().backward()
+    rel_v = float((ga.grad.cpu() - a.grad).abs().max() / a.grad.abs().max())
+    rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
+    return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_fwd_only=ms_fwd, steps_per_s=1e3 / ms, samples_taken=c[1],
+                gsamples_per_s_fwd_bwd=c[1] / ms / 1e6, grad_rel_volume=rel_v, grad_rel_tf=rel_t,
+                note="fwd+bwd through the autograd API incl. pack, occupancy build, classify, march, adjoint, unpack")
+
+
+def cfg4():
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    import numpy as np
+    dims = (512, 512, 512)
+    vol = make_brats_like(1, dims, seed=5, device="cuda")
+    tf = ramp_tf(256).cuda()
+    P = replace(framed_params(dims, 2048, 2048, theta_deg=0.0), tfMode=1)
+    V = api.Volume(vol)
+    cam = V.frame_camera(OrbitalCamera(initial_phi=math.radians(80.0)))
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 64)[::8]
+    taken = 0
+    for c in cams:
+        _, _, counts = api.render_aux(V, c, tf, P)
+        taken += int(counts[..., 1].sum())
+    out = torch.empty((len(cams), 2048, 2048, 4), device="cuda")
+
+    def batch():
+        for i, c in enumerate(cams):
+            V.forward(replace(P.with_camera(c), tfMode=1), tf, out=out[i])
+    ms = timeit(batch, reps=1)
+    return dict(cfg="cfg4", views_timed=len(cams), ms_per_view=ms / len(cams), fps=len(cams) * 1e3 / ms,
+                samples_taken_per_view=taken / len(cams), gsamples_per_s=taken / ms / 1e6,
+                note="8 of the 64 orbit views (every 8th) on one GPU; volume generated on device")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4"]
+    for w in which:
+        t0 = time.time()
+        r = dict(cfg1=cfg1, cfg3=cfg3, cfg4=cfg4)[w]()
+        r["wall_s"] = time.time() - t0
+        print(json.dumps(r), flush=True)
