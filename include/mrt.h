@@ -170,11 +170,14 @@ int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32
  *   l in 1..4 : the aligned cell of 2^(l-1) bricks per axis (8,16,32,64 voxels) that contains
  *               this brick is provably empty under (params, tf, labels): every sample slot
  *               whose trilinear base index lies in it is a no-op, so the march may leap to
- *               the cell's exit. */
+ *               the cell's exit.
+ *   flat != 0 (levels for the BACKWARD): a cell additionally has to be flat — every voxel in it
+ *               holds one and the same value — so that all slots inside share one TF bin and
+ *               one dL/dsigma, which mrt_render_backward adds in closed form. */
 int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C,
                         const float* tf, int32_t tfN,
                         const uint8_t* seg_any, const uint8_t* pred_any,
-                        uint8_t* skip_levels, void* stream);
+                        uint8_t* skip_levels, int32_t flat, void* stream);
 
 /* ------------------------------------------------ forward
  * Renders tiles [tile_begin, tile_end) of the [H][W] image (tile ids as above).
@@ -195,17 +198,24 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C,
 /* ------------------------------------------------ backward
  * Adjoint of mrt_render_forward w.r.t. the volume and the transfer function
  * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray.
+ *   flat_levels: optional uint8[nbricks] from mrt_classify_bricks(..., flat=1) together with
+ *                `minmax` (from mrt_build_occupancy): flat-empty cells are leapt with their exact
+ *                closed-form contribution to dL/dtf (single-channel layouts only; else ignored)
  *   out_rgba   : the forward's output (needed for the suffix sums)
  *   dL_dout    : float4 [H][W]
  *   dL_dvol    : packed layout, same shape as `packed`, ACCUMULATED into (caller zeroes)
  *   dL_dtf     : float [tfN][4] (tfMode 1) or float[2][4] (tfMode 0: entry [1][3] is
  *                dL/d intensityAlpha), ACCUMULATED into (caller zeroes)
+ *   scratch    : device scratch of mrt_backward_scratch_bytes(tfN) bytes (privatised dL/dtf
+ *                accumulators; zeroed by the call); required when dL_dtf != NULL
  */
+size_t mrt_backward_scratch_bytes(int32_t tfN);
 int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C,
                         const float* tf, int32_t tfN,
+                        const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds,
                         const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf,
+                        void* dL_dvol, float* dL_dtf, void* scratch,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
 /* ------------------------------------------------ slab renderer (u8 volume)

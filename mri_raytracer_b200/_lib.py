@@ -81,9 +81,11 @@ PROTOTYPES = {
     "mrt_brick_count": (_i32, [_i32, _i32, _i32]),
     "mrt_build_occupancy": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mrt_build_label_occupancy": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
-    "mrt_classify_bricks": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mrt_classify_bricks": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_render_forward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
-    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mrt_backward_scratch_bytes": (_sz, [_i32]),
+    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _i32, _i32, _vp]),
     "mrt_render_slab_u8": (C.c_int, [_SP, _vp, _vp, _i32, _i32, _vp]),
     "mrt_decode_bc4": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_u8_to_f32": (C.c_int, [_vp, _sz, _vp, _vp]),

@@ -97,13 +97,14 @@ def build_label_occupancy(labels: torch.Tensor) -> torch.Tensor:
 
 def classify_bricks(P: RenderParams, minmax: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                     seg_any: Optional[torch.Tensor] = None, pred_any: Optional[torch.Tensor] = None,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, flat: bool = False) -> torch.Tensor:
     nb = minmax.shape[0]
     if out is None:
         out = torch.empty((nb,), dtype=torch.uint8, device=minmax.device)
     s = P.to_struct()
     check(lib().mrt_classify_bricks(C.byref(s), minmax.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
-                                    _ptr(seg_any), _ptr(pred_any), out.data_ptr(), _stream()), "classify_bricks")
+                                    _ptr(seg_any), _ptr(pred_any), out.data_ptr(), int(flat), _stream()),
+          "classify_bricks")
     return out
 
 
@@ -127,17 +128,21 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
 def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                     labels: Optional[torch.Tensor], preds: Optional[torch.Tensor], out_rgba: torch.Tensor,
                     dL_dout: torch.Tensor, want_dvol: bool = True, want_dtf: bool = True,
-                    tile_range: Optional[Tuple[int, int]] = None):
+                    tile_range: Optional[Tuple[int, int]] = None, flat_levels: Optional[torch.Tensor] = None,
+                    minmax: Optional[torch.Tensor] = None):
     """-> (dL/dvolume packed or None, dL/dtf [N,4] or None)."""
     W, H = P.imageSize
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     dvol = torch.zeros_like(packed) if want_dvol else None
     ntf = tf.shape[0] if (tf is not None and P.tfMode) else 2
     dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_dtf else None
+    scratch = torch.empty((lib().mrt_backward_scratch_bytes(ntf) // 4,), dtype=torch.float32,
+                          device=packed.device) if want_dtf else None
     s = P.to_struct()
     check(lib().mrt_render_backward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
-                                    _ptr(labels), _ptr(preds), out_rgba.data_ptr(), dL_dout.data_ptr(),
-                                    _ptr(dvol), _ptr(dtf), t0, t1, _stream()), "render_backward")
+                                    _ptr(flat_levels), _ptr(minmax), _ptr(labels), _ptr(preds),
+                                    out_rgba.data_ptr(), dL_dout.data_ptr(), _ptr(dvol), _ptr(dtf), _ptr(scratch),
+                                    t0, t1, _stream()), "render_backward")
     return dvol, dtf
 
 
@@ -285,14 +290,17 @@ class _RenderFn(torch.autograd.Function):
             packed, Ce, Pe = fold_volume(planar.detach(), P), 1, folded_params(P)
         else:
             packed, Ce, Pe = pack_volume(planar.detach()), Cn, P
-        bits = None
+        bits = mm = flat = None
         if P.skipEmpty and P.tMode == "indexed":
             mm = build_occupancy(packed, Ce, P.dims)
             seg_any = build_label_occupancy(labels) if (labels is not None and P.showSeg) else None
             pred_any = build_label_occupancy(preds) if (preds is not None and P.showPred) else None
             bits = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any)
+            if Ce == 1:
+                flat = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any, flat=True)
         out = render_forward(Pe, packed, Ce, tf, bits, labels, preds)
         ctx.P, ctx.Pe, ctx.Cn, ctx.Ce, ctx.fold = P, Pe, Cn, Ce, fold
+        ctx.mm, ctx.flat = mm, flat
         ctx.labels, ctx.preds = labels, preds
         ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=planar.device), out)
         ctx.has_tf = tf is not None
@@ -304,7 +312,8 @@ class _RenderFn(torch.autograd.Function):
         tf = tf if ctx.has_tf else None
         want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
         dvol, dtf = render_backward(ctx.Pe, packed, ctx.Ce, tf, ctx.labels, ctx.preds, out,
-                                    g.contiguous(), want_dvol=want_vol, want_dtf=want_tf)
+                                    g.contiguous(), want_dvol=want_vol, want_dtf=want_tf,
+                                    flat_levels=ctx.flat, minmax=ctx.mm)
         gvol = None
         if want_vol:
             gvol = unfold_grad(dvol, ctx.P, ctx.Cn) if ctx.fold else unpack_volume(dvol, ctx.Cn, ctx.P.dims)

@@ -189,13 +189,14 @@ int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_label_occupancy");
 }
 int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C, const float* tf, int32_t tfN,
-                        const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* skip_levels, void* stream) {
+                        const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* skip_levels, int32_t flat,
+                        void* stream) {
   MRT_REQUIRE(minmax && skip_levels, "classify_bricks: null pointer");
   KParams K;
   if (int r = derive(params, C, tfN, true, 0, 0, &K)) return r;
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "classify_bricks: tfMode=1 needs tf");
   cudaError_t e = mrt_launch_classify(K, minmax, mrt_packed_channels(C), tf, seg_any, pred_any, skip_levels,
-                                      (cudaStream_t)stream);
+                                      flat != 0, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "classify_bricks");
 }
 
@@ -215,18 +216,23 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, c
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
 }
 
+size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }
+
 int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                        const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds, const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf, int32_t tile_begin, int32_t tile_end, void* stream) {
+                        void* dL_dvol, float* dL_dtf, void* scratch,
+                        int32_t tile_begin, int32_t tile_end, void* stream) {
   MRT_REQUIRE(packed && out_rgba && dL_dout, "render_backward: null pointer");
   MRT_REQUIRE(dL_dvol || dL_dtf, "render_backward: nothing to differentiate");
+  MRT_REQUIRE(!dL_dtf || scratch, "render_backward: dL_dtf needs the scratch buffer");
   KParams K;
-  if (int r = derive(params, C, tfN, false, tile_begin, tile_end, &K)) return r;
+  if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
   if (K.showSeg && !labels) K.showSeg = 0;
   if (K.showPred && !preds) K.showPred = 0;
-  cudaError_t e = mrt_launch_backward(K, mrt_packed_channels(C), packed, tf, labels, preds, out_rgba, dL_dout,
-                                      dL_dvol, dL_dtf, (cudaStream_t)stream);
+  cudaError_t e = mrt_launch_backward(K, mrt_packed_channels(C), packed, tf, flat_levels, minmax, labels, preds,
+                                      out_rgba, dL_dout, dL_dvol, dL_dtf, scratch, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
 }
 
@@ -335,7 +341,7 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
       MRT_CUDA(cudaMallocAsync(&d_pred_any, nb, st));
       MRT_CALL(mrt_build_label_occupancy(d_pred, X, Y, Z, d_pred_any, st));
     }
-    MRT_CALL(mrt_classify_bricks(&P, d_minmax, C, d_tf, tfN, d_seg_any, d_pred_any, d_bits, st));
+    MRT_CALL(mrt_classify_bricks(&P, d_minmax, C, d_tf, tfN, d_seg_any, d_pred_any, d_bits, 0, st));
   }
   MRT_CALL(mrt_render_forward(&P, d_packed, C, d_tf, tfN, d_bits, d_lab, d_pred, d_out, nullptr, nullptr,
                               0, mrt_tile_count(W, H), st));

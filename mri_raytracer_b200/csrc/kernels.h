@@ -11,9 +11,11 @@ cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st);
 
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                                const uint8_t* flat_levels, const float* minmax,
                                 const int32_t* labels, const int32_t* preds,
                                 const float* out_rgba, const float* dL_dout,
-                                void* dvol, float* dtf, cudaStream_t st);
+                                void* dvol, float* dtf, void* scratch, cudaStream_t st);
+size_t mrt_bwd_scratch_bytes(int ntf);
 
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
@@ -28,7 +30,7 @@ cudaError_t mrt_launch_build_occupancy(const void* packed, int packed_ch, int X,
 cudaError_t mrt_launch_label_occupancy(const int32_t* labels, int X, int Y, int Z, uint8_t* any, cudaStream_t st);
 cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int packed_ch, const float* tf,
                                 const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* levels,
-                                cudaStream_t st);
+                                bool require_flat, cudaStream_t st);
 
 cudaError_t mrt_launch_tile_map(int W, int H, int32_t* out_tile, int32_t* out_lane, cudaStream_t st);
 cudaError_t mrt_launch_gather_probe(const void* buf, size_t bytes, size_t n, uint32_t seed, float* out,

@@ -142,11 +142,15 @@ __device__ __forceinline__ bool mrt_brick_active(const KParams& P, const float2*
   return act;
 }
 
-// One CTA per 8x8x8-brick super-cell (64^3 voxels): classify each brick, then OR-reduce the
+// One CTA per 8x8x8-brick super-cell (64^3 voxels): classify each brick, then reduce the
 // flags over the aligned 2^3, 4^3 and 8^3 brick cells and store, per brick, the largest
 // aligned empty cell that contains it (skip level 1..4; 0 = active).  Bricks outside the
 // grid count as empty (no sample slot ever lands there).
-template <int NCH>
+// FLAT variant (for the backward): a brick only counts as skippable if it is empty AND flat
+// (min == max: every voxel holds the same value), and a coarse cell only if all its bricks are
+// flat-empty with the SAME value — then every slot inside has identical TF bin, colour and
+// dL/dsigma, which the backward adds in closed form.
+template <int NCH, bool FLAT>
 __global__ void __launch_bounds__(512)
 mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict__ minmax,
                     const float4* __restrict__ tf, const uint8_t* __restrict__ seg_any,
@@ -155,37 +159,62 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
   __shared__ uint8_t s_or2[64];
   __shared__ uint8_t s_or4[8];
   __shared__ uint8_t s_or8;
+  __shared__ float s_lo[512], s_hi[512], s_lo2[64], s_hi2[64], s_lo4[8], s_hi4[8];
   const int t = threadIdx.x;
   const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
   const int sx = blockIdx.x % sbx, sy = (blockIdx.x / sbx) % sby, sz = blockIdx.x / (sbx * sby);
   const int bx = (sx << 3) + lx, by = (sy << 3) + ly, bz = (sz << 3) + lz;
   const bool inside = bx < P.nbx && by < P.nby && bz < P.nbz;
   const int b = (bz * P.nby + by) * P.nbx + bx;
-  const bool act = inside && mrt_brick_active<NCH>(P, minmax, tf, seg_any, pred_any, b);
+  bool act = inside && mrt_brick_active<NCH>(P, minmax, tf, seg_any, pred_any, b);
+  if (FLAT) {
+    float lo = 3.0e38f, hi = -3.0e38f;          // out-of-grid bricks are compatible with any value
+    if (inside) {
+      bool flat = true;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { const float2 mm = __ldg(minmax + (size_t)b * NCH + c); flat = flat && (mm.x == mm.y); }
+      const float2 m0 = __ldg(minmax + (size_t)b * NCH);
+      lo = m0.x; hi = m0.y;
+      if (!flat || NCH != 1) act = true;
+    }
+    s_lo[t] = lo; s_hi[t] = hi;
+  }
   s_act[t] = act;
   __syncthreads();
   if (t < 64) {            // 2x2x2 groups: group (gx,gy,gz) in 4x4x4
     const int gx = t & 3, gy = (t >> 2) & 3, gz = t >> 4;
     int o = 0;
+    float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o |= s_act[((gz * 2 + (i >> 2)) << 6) + ((gy * 2 + ((i >> 1) & 1)) << 3) + gx * 2 + (i & 1)];
+    for (int i = 0; i < 8; ++i) {
+      const int j = ((gz * 2 + (i >> 2)) << 6) + ((gy * 2 + ((i >> 1) & 1)) << 3) + gx * 2 + (i & 1);
+      o |= s_act[j];
+      if (FLAT) { lo = fminf(lo, s_lo[j]); hi = fmaxf(hi, s_hi[j]); }
+    }
+    if (FLAT) { s_lo2[t] = lo; s_hi2[t] = hi; if (lo < hi) o = 1; }
     s_or2[t] = (uint8_t)o;
   }
   __syncthreads();
   if (t < 8) {             // 4x4x4 groups: (hx,hy,hz) in 2x2x2, each = 2x2x2 of the or2 groups
     const int hx = t & 1, hy = (t >> 1) & 1, hz = t >> 2;
     int o = 0;
+    float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o |= s_or2[((hz * 2 + (i >> 2)) << 4) + ((hy * 2 + ((i >> 1) & 1)) << 2) + hx * 2 + (i & 1)];
+    for (int i = 0; i < 8; ++i) {
+      const int j = ((hz * 2 + (i >> 2)) << 4) + ((hy * 2 + ((i >> 1) & 1)) << 2) + hx * 2 + (i & 1);
+      o |= s_or2[j];
+      if (FLAT) { lo = fminf(lo, s_lo2[j]); hi = fmaxf(hi, s_hi2[j]); }
+    }
+    if (FLAT) { s_lo4[t] = lo; s_hi4[t] = hi; if (lo < hi) o = 1; }
     s_or4[t] = (uint8_t)o;
   }
   __syncthreads();
   if (t == 0) {
     int o = 0;
+    float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o |= s_or4[i];
+    for (int i = 0; i < 8; ++i) { o |= s_or4[i]; if (FLAT) { lo = fminf(lo, s_lo4[i]); hi = fmaxf(hi, s_hi4[i]); } }
+    if (FLAT && lo < hi) o = 1;
     s_or8 = (uint8_t)o;
   }
   __syncthreads();
@@ -207,14 +236,16 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
 
 cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int pc, const float* tf,
                                 const uint8_t* seg_any, const uint8_t* pred_any, uint8_t* levels,
-                                cudaStream_t st) {
+                                bool require_flat, cudaStream_t st) {
   const int sbx = (P.nbx + 7) >> 3, sby = (P.nby + 7) >> 3, sbz = (P.nbz + 7) >> 3;
   const int grid = sbx * sby * sbz;
+#define MRT_CL(N, F) mrt_classify_kernel<N, F><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby)
   switch (pc) {
-    case 1: mrt_classify_kernel<1><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
-    case 2: mrt_classify_kernel<2><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
-    case 4: mrt_classify_kernel<4><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby); break;
+    case 1: if (require_flat) MRT_CL(1, true); else MRT_CL(1, false); break;
+    case 2: if (require_flat) MRT_CL(2, true); else MRT_CL(2, false); break;
+    case 4: if (require_flat) MRT_CL(4, true); else MRT_CL(4, false); break;
     default: return cudaErrorInvalidValue;
   }
+#undef MRT_CL
   return cudaGetLastError();
 }
