@@ -220,7 +220,7 @@ def run_reference(args):
     val = tot / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": sample},
         "frames_per_sec": args.steps / float(stride * stride) / dt,
@@ -253,8 +253,9 @@ def run_ours(args):
         build.build()
     if world > 1:
         dist.barrier()
-    V = args.views
-    P, cams = _scene(V)
+    V = args.views                      # views per GPU per step (weak scaling: per-GPU work is fixed)
+    P, cams_all = _scene(V * world)
+    cams = cams_all[rank * V:(rank + 1) * V] if args.mode == "views" else cams_all[:V]
     vol_host = make_brats_like(NCH, DIMS, seed=0).pin_memory()
     tf_host = ramp_tf(TF_N)
     vol = vol_host.to(dev, non_blocking=True)
@@ -263,10 +264,9 @@ def run_ours(args):
     W = H = IMG
     nt = tiles.tile_count(W, H)
     mode = args.mode if world > 1 else "views"
-    if mode == "views" and V % world != 0:
-        raise SystemExit(f"--views {V} must be divisible by the number of GPUs {world}")
+    fb = mdist.PeerFramebuffer(V, H, W, dev) if (world > 1 and mode == "views") else None
 
-    # ---- untimed counting pass: the oracle-defined sample count of every view (rank 0 counts all)
+    # ---- untimed counting pass: the oracle-defined sample count of this rank's views
     taken = evaluated = clip = 0
     per_view_eval = []
     for c in cams:
@@ -275,6 +275,10 @@ def run_ours(args):
         clip += s[0]; taken += s[1]; evaluated += s[2]
         per_view_eval.append(s[2])
     torch.cuda.synchronize()
+    if world > 1 and mode == "views":          # whole-job totals (each rank renders different views)
+        tot = torch.tensor([taken, evaluated, clip], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        taken, evaluated, clip = (int(x) for x in tot.tolist())
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     frames = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
@@ -294,6 +298,9 @@ def run_ours(args):
                 api.render_forward(Pe, packed, Ce, tf, bits, out=frames[v])
                 if record_kernels:
                     b.record(); kern_ev.append((a, b, v))
+        elif mode == "views":
+            mdist.render_views_to(fb, volume, cams, tf, P)           # pixels go straight to rank 0 over NVLink
+            fb.finish()
         else:
             mdist.render_views(volume, cams, tf, P, mode=mode)
 
@@ -412,14 +419,19 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_step": V, "partition": mode if world > 1 else "single GPU",
+            "scaling": "weak" if mode == "views" else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V,
+                       "views_per_step_total": V * world if mode == "views" else V,
+                       "partition": ("whole views per rank; framebuffer gathered on rank 0 by "
+                                     + ("peer (NVLink) stores from inside the march kernel" if (fb and fb.p2p)
+                                        else "NCCL all_gather")) if (world > 1 and mode == "views")
+                       else ("tile rows + NCCL all_gather" if world > 1 else "single GPU"),
                        "l2": "flushed (256 MiB write) between timed steps; volume 142.8 MB > 126 MB L2"},
-            "frames_per_sec": V * args.steps / tot_s,
+            "frames_per_sec": (V * world if mode == "views" else V) * args.steps / tot_s,
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": (2 * V + (2 if volume.fold else 1)) * args.steps if world == 1
-            else (2 * V // world + (2 if volume.fold else 1)) * args.steps,
+            "gpu_launches": (2 * V + (2 if volume.fold else 1)) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
