@@ -89,6 +89,14 @@ typedef struct MrtParams {
   uint32_t alphaMode;       /* 0 alpha = 1 (reference :167) ; 1 alpha = 1 - T */
   uint32_t skipEmpty;       /* 1 use the occupancy brick grid (needs `occupancy` != NULL) */
   uint32_t tfMode;          /* 0 reference window/level intensity TF (:132-140) ; 1 1D LUT tf[N][4] */
+  /* ---- brick-sharded (sort-last) rendering, offset 400; all zero = off ----
+   * `dims`, `volMin`, `voxelSize` keep describing the WHOLE volume (rays, slots and the global
+   * dims-1.001 clamp are unchanged); the `packed` buffer holds only voxels
+   * [shardLo, shardHi] inclusive (dims shardHi-shardLo+1, +1-voxel halo), and this call shades
+   * exactly the slots whose trilinear base index lies in the cell range [shardLo, shardHi).
+   * Output is the partial (r,g,b premultiplied WITHOUT background, a = T_local) for
+   * mrt_composite_over.  Early termination acts on the shard-local transmittance. */
+  uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3]; uint32_t padShard;
 } MrtParams;
 
 /* Slab renderer params: `struct Params` of scripts/volumeRendering/volume_render.slang:9-21

@@ -39,6 +39,7 @@ class MrtParams(C.Structure):
         ("ortho", C.c_uint32), ("orthoHalfHeight", C.c_float), ("ertThreshold", C.c_float),
         ("maxSteps", C.c_uint32),
         ("tMode", C.c_uint32), ("alphaMode", C.c_uint32), ("skipEmpty", C.c_uint32), ("tfMode", C.c_uint32),
+        ("shardEnabled", C.c_uint32), ("shardLo", C.c_uint32 * 3), ("shardHi", C.c_uint32 * 3), ("padShard", C.c_uint32),
     ]
 
 

@@ -188,13 +188,24 @@ class Volume:
 
     def __init__(self, planar: torch.Tensor, labels: Optional[torch.Tensor] = None,
                  preds: Optional[torch.Tensor] = None, zooms=(1.0, 1.0, 1.0), occupancy: bool = True,
-                 fold: bool = True):
+                 fold: bool = True, shard=None, global_dims=None):
+        """``shard=((lox,loy,loz),(hix,hiy,hiz))`` + ``global_dims``: ``planar`` holds only voxels
+        [lo, hi] (inclusive) of a larger volume — a sort-last sub-box (dist.render_sort_last)."""
         _need_cuda(planar, "volume", torch.float32)
         if planar.dim() != 4 or not (1 <= planar.shape[0] <= 4):
             raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(planar.shape)}")
         self.C = int(planar.shape[0])
         Z, Y, X = (int(v) for v in planar.shape[1:])
         self.dims = (X, Y, Z)
+        self.shard = None
+        self.global_dims = self.dims
+        if shard is not None:
+            lo, hi = tuple(int(v) for v in shard[0]), tuple(int(v) for v in shard[1])
+            if tuple(h - l + 1 for l, h in zip(lo, hi)) != self.dims:
+                raise ValueError(f"shard {shard} does not match the sub-volume dims {self.dims}")
+            if labels is not None or preds is not None:
+                raise ValueError("label overlays are not supported on sharded volumes")
+            self.shard, self.global_dims = (lo, hi), tuple(int(v) for v in global_dims)
         self.device = planar.device
         self.occupancy = occupancy
         self.fold = bool(fold) and self.C > 1
@@ -209,11 +220,13 @@ class Volume:
         self.set_labels(labels)
         self.set_preds(preds)
         from .synth import world_box
-        self.voxel_size, self.vol_min = world_box(self.dims, zooms)
+        self.voxel_size, self.vol_min = world_box(self.global_dims, zooms)
         self._bits = None
 
     def prepared(self, P: RenderParams):
         """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
+        if self.shard is not None:
+            P = replace(P, shard=self.shard)
         if not self.fold:
             return self.packed, self.C, P
         key = _fold_key(P, self.C)
@@ -249,12 +262,12 @@ class Volume:
 
     def frame_params(self, P: RenderParams) -> RenderParams:
         """Fill dims / voxelSize / volMin from the volume."""
-        return replace(P, dims=self.dims, voxelSize=tuple(float(v) for v in self.voxel_size),
+        return replace(P, dims=self.global_dims, voxelSize=tuple(float(v) for v in self.voxel_size),
                        volMin=tuple(float(v) for v in self.vol_min))
 
     def frame_camera(self, cam):
         """``frame_volume`` (inr/viewer/brats_viewer.py:320-324): target = centre, radius = 0.8*|extent|."""
-        ext = self.voxel_size * np.asarray(self.dims, dtype=np.float32)
+        ext = self.voxel_size * np.asarray(self.global_dims, dtype=np.float32)
         cam.target = (self.vol_min + 0.5 * ext).astype(np.float32)
         cam.radius = float(np.linalg.norm(ext) * 0.8)
         return cam
@@ -343,8 +356,8 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
     P = replace(P, tfMode=1 if tf is not None else 0)
     if isinstance(volume, Volume):
         V = volume
-        if tuple(P.dims) != tuple(V.dims):
-            raise ValueError(f"params.dims {P.dims} != volume dims {V.dims}")
+        if tuple(P.dims) != tuple(V.global_dims):
+            raise ValueError(f"params.dims {P.dims} != volume dims {V.global_dims}")
         P.validate()
         return V.forward(P, tf, labels=labels, preds=preds)
     _need_cuda(volume, "volume", torch.float32)

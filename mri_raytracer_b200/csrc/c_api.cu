@@ -92,10 +92,24 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(M->voxelSize[i] > 0.0f, "voxelSize[%d] must be > 0", i);
   }
   if (int r = check_dims("render", C, K->dims[0], K->dims[1], K->dims[2])) return r;
+  int ldim[3] = {K->dims[0], K->dims[1], K->dims[2]};       // dims of the buffer actually sampled
+  if (M->shardEnabled) {
+    K->shard = 1;
+    for (int i = 0; i < 3; ++i) {
+      MRT_REQUIRE(M->shardLo[i] < M->shardHi[i] && (int)M->shardHi[i] <= K->dims[i] - 1,
+                  "shard range [%u,%u) on axis %d outside the cell range [0,%d)", M->shardLo[i], M->shardHi[i], i,
+                  K->dims[i] - 1);
+      K->slo[i] = (int)M->shardLo[i]; K->shi[i] = (int)M->shardHi[i];
+      ldim[i] = K->shi[i] - K->slo[i] + 1;
+    }
+    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on sharded volumes");
+    MRT_REQUIRE(M->tMode == 0, "sharded volumes need indexed stepping (tMode 0)");
+  }
   {
     int64_t pY, pZ;
-    mrt_layout(mrt_packed_channels(C), K->dims[0], K->dims[1], K->dims[2], &pY, &pZ);
+    mrt_layout(mrt_packed_channels(C), ldim[0], ldim[1], ldim[2], &pY, &pZ);
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
+    K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;
   }
   // tan evaluated once in double, rounded to float (documented deviation from the per-thread fp32 tan)
   K->ortho = M->ortho ? 1 : 0;
@@ -134,7 +148,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   K->tfN = K->tfMode ? tfN : 0;
   if (K->tfMode) MRT_REQUIRE(tfN >= 2 && tfN <= MRT_MAX_TF, "tfN=%d outside 2..%d", tfN, MRT_MAX_TF);
   K->skip = (M->skipEmpty && have_bits && K->tMode == 0) ? 1 : 0;
-  K->nbx = (K->dims[0] + 7) >> 3; K->nby = (K->dims[1] + 7) >> 3; K->nbz = (K->dims[2] + 7) >> 3;
+  K->nbx = (ldim[0] + 7) >> 3; K->nby = (ldim[1] + 7) >> 3; K->nbz = (ldim[2] + 7) >> 3;
   const int nt = mrt_tiles_x_(K->W) * mrt_tiles_y_(K->H);
   MRT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt,
               "tile range [%d,%d) outside [0,%d]", tile_begin, tile_end, nt);

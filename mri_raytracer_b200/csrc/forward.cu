@@ -51,7 +51,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   if (px >= P.W || py >= P.H) return;                                      // :89
 
   const Ray ray = mrt_setup_ray(P, px, py);
-  float Cr = P.bg[0], Cg = P.bg[1], Cb = P.bg[2];                          // :111
+  // a sort-last shard renders a partial: premultiplied colour WITHOUT background, alpha = T_local
+  float Cr = P.shard ? 0.0f : P.bg[0], Cg = P.shard ? 0.0f : P.bg[1], Cb = P.shard ? 0.0f : P.bg[2];   // :111
   float T = 1.0f;                                                          // :112
   int k = 0, n_eval = 0, n_seg = 0;
 
@@ -110,7 +111,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     } else if (SKIP) {
       const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
       const float inv_dt = 1.0f / dt;
-      const int n = ray.n;
+      int n = ray.n;
+      if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, inv_dt, ray.n, &ks, &n); k = ks; }
       int kact = 0;                      // slots [k, kact) are known to lie in an active brick
       for (;;) {
         // phase 1: advance to the next slot inside an active brick
@@ -120,11 +122,16 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
           const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);               // == floor of the clamped coord
           const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
           const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
-          const int lvl = __ldg(levels + (((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx +
-                                          (ix >> MRT_BRICK_SHIFT)));
+          if (P.shard && !mrt_shard_owns(P, ix, iy, iz)) { ++k; continue; }   // another rank's slot
+          const int jx = ix - P.slo[0], jy = iy - P.slo[1], jz = iz - P.slo[2];   // brick grid is shard-local
+          const int lvl = __ldg(levels + (((jz >> MRT_BRICK_SHIFT) * P.nby + (jy >> MRT_BRICK_SHIFT)) * P.nbx +
+                                          (jx >> MRT_BRICK_SHIFT)));
           const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-          const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
+          int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, jx >> sh, jy >> sh, jz >> sh, sh, t, inv_dt,
+                                               P.slo[0], P.slo[1], P.slo[2]));
           if (GENERIC) ++n_seg;
+          // an ACTIVE brick may straddle the shard's far faces: stop at the owned box's exit
+          if (P.shard && !lvl) kend = min(kend, k + mrt_shard_slots(P, q, ivx, ivy, ivz, t, inv_dt));
           if (lvl) k = kend; else kact = kend;
         }
         if (!(k < n && T > thr)) break;                                    // :117
@@ -133,15 +140,23 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         ++k; if (GENERIC) ++n_eval;
       }
     } else {
-      const int n = ray.n;
+      int n = ray.n;
+      if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, 1.0f / dt, ray.n, &ks, &n); k = ks; }
       while (k < n && T > thr) {                                           // :117
-        shade(fmaf((float)k, dt, ray.t0));
+        const float t = fmaf((float)k, dt, ray.t0);
+        if (P.shard) {
+          const int ix = (int)fminf(fmaxf(fmaf(t, q.dx, q.ox), 0.0f), hix);
+          const int iy = (int)fminf(fmaxf(fmaf(t, q.dy, q.oy), 0.0f), hiy);
+          const int iz = (int)fminf(fmaxf(fmaf(t, q.dz, q.oz), 0.0f), hiz);
+          if (!mrt_shard_owns(P, ix, iy, iz)) { ++k; continue; }
+        }
+        shade(t);
         ++k; if (GENERIC) ++n_eval;
       }
     }
   }
   const size_t pix = (size_t)py * P.W + px;
-  out_rgba[pix] = make_float4(Cr, Cg, Cb, P.alphaMode ? 1.0f - T : 1.0f);  // :167
+  out_rgba[pix] = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
   if (out_T) out_T[pix] = T;
   if (GENERIC) { if (out_counts) out_counts[pix] = make_int4(ray.n, k, n_eval, n_seg); }
 }

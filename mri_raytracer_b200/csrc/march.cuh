@@ -37,6 +37,11 @@ struct KParams {
   int skip;               // occupancy skipping enabled
   int nbx, nby, nbz;      // brick grid
   int tile_begin, tile_end;
+  // sort-last shard (all zero when off): owned cell range [slo, shi) in GLOBAL voxel indices;
+  // the packed buffer / brick grid / pitches are those of the sub-volume starting at slo.
+  int shard;
+  int slo[3], shi[3];
+  unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
 };
 
 struct Ray {
@@ -163,7 +168,7 @@ __device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename
   typedef typename Vox<NCH>::T VT;
   const uint32_t sY = P.pitchY;
   const uint32_t sZ = P.pitchZ;
-  const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ;
+  const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ - P.base_off;
   const VT* p0 = vol + b;
   const VT* p1 = p0 + sY;
   const VT* p2 = p0 + sZ;
@@ -255,10 +260,12 @@ __device__ __forceinline__ int mrt_logical_lane(int half, int lane) {
 // guaranteed to lie inside the cell; always >= 1 so the march progresses.
 #define MRT_PLANE_EPS 0.015625f
 __device__ __forceinline__ int mrt_cell_slots(const IdxRay& q, float ivx, float ivy, float ivz,
-                                              int cx, int cy, int cz, int sh, float t, float inv_dt) {
-  const float plx = (q.dx > 0.0f) ? (float)((cx + 1) << sh) - MRT_PLANE_EPS : (float)(cx << sh) + MRT_PLANE_EPS;
-  const float ply = (q.dy > 0.0f) ? (float)((cy + 1) << sh) - MRT_PLANE_EPS : (float)(cy << sh) + MRT_PLANE_EPS;
-  const float plz = (q.dz > 0.0f) ? (float)((cz + 1) << sh) - MRT_PLANE_EPS : (float)(cz << sh) + MRT_PLANE_EPS;
+                                              int cx, int cy, int cz, int sh, float t, float inv_dt,
+                                              int ox = 0, int oy = 0, int oz = 0) {
+  // (cx,cy,cz) index cells of the (sub-)volume whose origin sits at global voxel (ox,oy,oz)
+  const float plx = (q.dx > 0.0f) ? (float)(ox + ((cx + 1) << sh)) - MRT_PLANE_EPS : (float)(ox + (cx << sh)) + MRT_PLANE_EPS;
+  const float ply = (q.dy > 0.0f) ? (float)(oy + ((cy + 1) << sh)) - MRT_PLANE_EPS : (float)(oy + (cy << sh)) + MRT_PLANE_EPS;
+  const float plz = (q.dz > 0.0f) ? (float)(oz + ((cz + 1) << sh)) - MRT_PLANE_EPS : (float)(oz + (cz << sh)) + MRT_PLANE_EPS;
   // an axis the ray does not move along never bounds the exit
   const float tx = (q.dx != 0.0f) ? (plx - q.ox) * ivx : 3.0e38f;
   const float ty = (q.dy != 0.0f) ? (ply - q.oy) * ivy : 3.0e38f;
@@ -266,4 +273,41 @@ __device__ __forceinline__ int mrt_cell_slots(const IdxRay& q, float ivx, float 
   const float te = fminf(fminf(tx, ty), tz);
   const float ns = floorf((te - t) * inv_dt) + 1.0f;     // slots j with t + j*dt <= te
   return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
+}
+
+// Sort-last: candidate slot range [ks, ke) of a ray inside a shard's sub-box (expanded by one
+// voxel so that the global dims-1.001 clamp and fp32 rounding can never hide an owned slot);
+// ownership itself is decided per slot, exactly, from the integer base index.
+__device__ __forceinline__ void mrt_shard_range(const KParams& P, const IdxRay& q, float t0, float inv_dt, int n,
+                                                int* ks, int* ke) {
+  float tin = -3.0e38f, tout = 3.0e38f;
+  const float o[3] = {q.ox, q.oy, q.oz}, d[3] = {q.dx, q.dy, q.dz};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = (float)P.slo[a] - 1.0f, hi = (float)P.shi[a] + 1.0f;
+    if (d[a] != 0.0f) {
+      const float inv = 1.0f / d[a];
+      const float ta = (lo - o[a]) * inv, tb = (hi - o[a]) * inv;
+      tin = fmaxf(tin, fminf(ta, tb)); tout = fminf(tout, fmaxf(ta, tb));
+    } else if (o[a] < lo || o[a] > hi) { tin = 3.0e38f; tout = -3.0e38f; }
+  }
+  if (!(tout >= tin)) { *ks = 0; *ke = 0; return; }
+  const float a = floorf((tin - t0) * inv_dt) - 1.0f, b = ceilf((tout - t0) * inv_dt) + 2.0f;
+  *ks = (int)fminf(fmaxf(a, 0.0f), (float)n);
+  *ke = (int)fminf(fmaxf(b, 0.0f), (float)n);
+}
+// slots, starting at slot time t, guaranteed to stay inside the shard's owned box [slo, shi)
+__device__ __forceinline__ int mrt_shard_slots(const KParams& P, const IdxRay& q, float ivx, float ivy, float ivz,
+                                               float t, float inv_dt) {
+  const float plx = (q.dx > 0.0f) ? (float)P.shi[0] - MRT_PLANE_EPS : (float)P.slo[0] + MRT_PLANE_EPS;
+  const float ply = (q.dy > 0.0f) ? (float)P.shi[1] - MRT_PLANE_EPS : (float)P.slo[1] + MRT_PLANE_EPS;
+  const float plz = (q.dz > 0.0f) ? (float)P.shi[2] - MRT_PLANE_EPS : (float)P.slo[2] + MRT_PLANE_EPS;
+  const float tx = (q.dx != 0.0f) ? (plx - q.ox) * ivx : 3.0e38f;
+  const float ty = (q.dy != 0.0f) ? (ply - q.oy) * ivy : 3.0e38f;
+  const float tz = (q.dz != 0.0f) ? (plz - q.oz) * ivz : 3.0e38f;
+  const float ns = floorf((fminf(fminf(tx, ty), tz) - t) * inv_dt) + 1.0f;
+  return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
+}
+__device__ __forceinline__ bool mrt_shard_owns(const KParams& P, int ix, int iy, int iz) {
+  return ix >= P.slo[0] && ix < P.shi[0] && iy >= P.slo[1] && iy < P.shi[1] && iz >= P.slo[2] && iz < P.shi[2];
 }

@@ -214,15 +214,79 @@ def visibility_order(eye: np.ndarray, P: RenderParams, grid: Tuple[int, int, int
     return [r for _, _, r in sorted(keys, key=lambda t: (t[1], t[2]))]
 
 
-def shard_params(P: RenderParams, lo, hi) -> RenderParams:
-    """RenderParams of a sub-box: dims = hi-lo+1 voxels, volMin shifted by lo voxels.  The
-    sub-box spans cells [lo,hi) exactly: its world extent is (hi-lo)*voxelSize, which is what
-    `dims*voxelSize` would overstate by one voxel, so the far faces are clamped via the
-    shard's own clip box (see render_sort_last)."""
-    vs = np.asarray(P.voxelSize, dtype=np.float32)
-    vmin = np.asarray(P.volMin, dtype=np.float32) + vs * np.asarray(lo, dtype=np.float32)
-    dims = tuple(int(h - l + 1) for l, h in zip(lo, hi))
-    return replace(P, dims=dims, volMin=tuple(float(v) for v in vmin))
+def slice_shard(planar: torch.Tensor, lo, hi) -> torch.Tensor:
+    """Voxels [lo, hi] inclusive of a ``[C,Z,Y,X]`` volume (cells [lo,hi) + the 1-voxel halo)."""
+    return planar[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1].contiguous()
+
+
+def composite_over(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:
+    """Ordered front-to-back `over` of ``[K,npix,4]`` partials -> ``[npix,4]``: the CUDA kernel
+    (``mrt_composite_over``) on CUDA tensors, the torch restatement on CPU tensors (gloo tests)."""
+    if not partials.is_cuda:
+        return composite_over_torch(partials, order, bg, alpha_mode)
+    import ctypes as C
+    from ._lib import check, lib
+    K, npix = partials.shape[0], partials.shape[1]
+    o = torch.tensor(list(order), dtype=torch.int32, device=partials.device)
+    bga = np.asarray(bg, dtype=np.float32)
+    out = torch.empty((npix, 4), dtype=torch.float32, device=partials.device)
+    check(lib().mrt_composite_over(partials.contiguous().data_ptr(), K, o.data_ptr(), npix, bga.ctypes.data,
+                                   int(alpha_mode), out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+          "composite_over")
+    return out
+
+
+def render_sort_last(shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, int, int], group=None,
+                     partial_fn: Optional[Callable] = None, device=None) -> torch.Tensor:
+    """One frame of a brick-sharded volume (BASELINE config 5): this rank marches every ray through
+    its own sub-box only (``shard_volume`` = Volume(..., shard=shard_box(dims, grid, rank))) ->
+    partial (premultiplied rgb, T); image strips are exchanged with ONE ``all_to_all_single``;
+    each rank composites its strip front-to-back in visibility order and the finished strips are
+    all-gathered.  Early termination acts per shard (use a small ``ertThreshold``: the result
+    equals the unsharded render to within it).  ``partial_fn(P) -> [H,W,4]`` overrides the CUDA
+    march (CPU/gloo tests)."""
+    rank, R = _world(group)
+    if grid[0] * grid[1] * grid[2] != R:
+        raise ValueError(f"grid {grid} does not match world size {R}")
+    W, H = P.imageSize
+    Pc = P.with_camera(cam) if cam is not None else P
+    if partial_fn is not None:
+        partial = partial_fn(Pc)
+    else:
+        partial = shard_volume.forward(replace(Pc, tfMode=1 if tf is not None else 0), tf)
+    device = partial.device
+    order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
+    if R == 1:
+        return composite_over(partial.reshape(1, H * W, 4), order, Pc.bgColor, Pc.alphaMode).reshape(H, W, 4)
+    rows = padded_rows(H, R)
+    send = torch.zeros((R, rows, W, 4), dtype=torch.float32, device=device)
+    send[..., 3] = 1.0                                  # padding rows: empty partial (T = 1)
+    send.view(R * rows, W, 4)[:H] = partial
+    recv = torch.empty_like(send)                       # recv[j] = rank j's partial of MY strip
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    mine = composite_over(recv.reshape(R, rows * W, 4), order, Pc.bgColor, Pc.alphaMode)
+    full = torch.empty((R, rows * W, 4), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1).contiguous(), group=group)
+    return full.reshape(R * rows, W, 4)[:H].contiguous()
+
+
+def render_sort_last_emulated(planar: torch.Tensor, cam, tf, P: RenderParams, grid: Tuple[int, int, int],
+                              fold: bool = True) -> torch.Tensor:
+    """All shards of ``grid`` rendered one after the other on ONE GPU, then composited: the
+    single-process equivalent of :func:`render_sort_last` (tests, and hosts with fewer GPUs
+    than shards)."""
+    from . import api
+    R = grid[0] * grid[1] * grid[2]
+    Z, Y, X = (int(v) for v in planar.shape[1:])
+    W, H = P.imageSize
+    Pc = P.with_camera(cam) if cam is not None else P
+    parts = []
+    for r in range(R):
+        lo, hi, _ = shard_box((X, Y, Z), grid, r)
+        V = api.Volume(slice_shard(planar, lo, hi), shard=(lo, hi), global_dims=(X, Y, Z), fold=fold)
+        parts.append(V.forward(replace(Pc, tfMode=1 if tf is not None else 0), tf).reshape(H * W, 4))
+    order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
+    return composite_over(torch.stack(parts), order, Pc.bgColor, Pc.alphaMode).reshape(H, W, 4)
 
 
 def composite_over_torch(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:

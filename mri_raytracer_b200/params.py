@@ -70,6 +70,7 @@ class RenderParams:
     alphaMode: int = 0
     skipEmpty: int = 1
     tfMode: int = 0             # set by render(): 1 when a LUT tensor is passed
+    shard: object = None        # ((lox,loy,loz), (hix,hiy,hiz)) voxel range of a sort-last sub-box, or None
 
     def validate(self):
         W, H = self.imageSize
@@ -121,6 +122,13 @@ class RenderParams:
         s.alphaMode = int(bool(self.alphaMode))
         s.skipEmpty = int(bool(self.skipEmpty))
         s.tfMode = int(bool(self.tfMode))
+        if self.shard is not None:
+            lo, hi = self.shard
+            s.shardEnabled = 1
+            for i in range(3):
+                if not (0 <= int(lo[i]) < int(hi[i]) <= int(self.dims[i]) - 1):
+                    raise ValueError(f"shard {self.shard} outside the volume's cell range")
+                s.shardLo[i], s.shardHi[i] = int(lo[i]), int(hi[i])
         return s
 
 

@@ -29,13 +29,14 @@ def test_every_declared_symbol_is_exported_and_bound(built_lib):
 
 
 def test_params_layout_matches_reference_cbuffer(built_lib):
-    assert built_lib.mrt_sizeof_params() == C.sizeof(MrtParams) == 400
+    assert built_lib.mrt_sizeof_params() == C.sizeof(MrtParams) == 432
     assert built_lib.mrt_sizeof_slab_params() == C.sizeof(MrtSlabParams)
     off = {f[0]: getattr(MrtParams, f[0]).offset for f in MrtParams._fields_}
     # 16-byte rows of the cbuffer, in order
     want = dict(imageSize=0, fovY=8, eye=16, U=32, V=48, W=64, volMin=80, voxelSize=96, dims=112, stepSize=128,
                 nearT=132, farT=136, bgColor=144, volEnabled=160, volWeight=176, ww=192, wl=196, intensityAlpha=200,
-                gamma=208, gradBoost=212, gradScale=216, showSeg=224, showPred=228, lutColorAlpha=240, ortho=368)
+                gamma=208, gradBoost=212, gradScale=216, showSeg=224, showPred=228, lutColorAlpha=240, ortho=368,
+                shardEnabled=400)
     for k, v in want.items():
         assert off[k] == v, (k, off[k], v)
 
