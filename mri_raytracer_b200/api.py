@@ -153,7 +153,7 @@ def fold_volume(planar: torch.Tensor, P: RenderParams) -> torch.Tensor:
     Cn, Z, Y, X = planar.shape
     nbytes = lib().mrt_packed_volume_bytes(1, X, Y, Z)
     folded = torch.zeros((nbytes // 4,), dtype=torch.float32, device=planar.device)
-    s = replace(P, dims=(X, Y, Z)).to_struct()
+    s = replace(P, dims=(X, Y, Z), shard=None).to_struct()
     check(lib().mrt_fold_volume_f32(C.byref(s), planar.data_ptr(), Cn, folded.data_ptr(), _stream()), "fold_volume")
     return folded
 

@@ -92,6 +92,46 @@ def test_image_space_partition_world2(mode, W, H, V):
         assert np.array_equal(got[v], want), (mode, v)
 
 
+def _sl_worker(rank, world, port, W, H, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mri_raytracer_b200 import dist as mdist, RenderParams
+        P = RenderParams(imageSize=(W, H), dims=(32, 32, 32), voxelSize=(0.05, 0.05, 0.05), volMin=(-0.8, -0.8, -0.8),
+                         eye=(3.0, 2.0, 1.0), bgColor=(0.1, 0.2, 0.3), alphaMode=1)
+        g = torch.Generator().manual_seed(100 + rank)
+        partial = torch.rand(H, W, 4, generator=g)
+        img = mdist.render_sort_last(None, None, None, P, (2, 1, 1), partial_fn=lambda Pc: partial)
+        if rank == 0:
+            ret.put(img.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("W,H", [(16, 16), (21, 27)])
+def test_sort_last_exchange_world2(W, H):
+    """all_to_all of image strips + ordered composite + all_gather == compositing whole partials."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sl_worker, args=(r, 2, port, W, H, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    from mri_raytracer_b200 import dist as mdist, RenderParams
+    P = RenderParams(imageSize=(W, H), dims=(32, 32, 32), voxelSize=(0.05, 0.05, 0.05), volMin=(-0.8, -0.8, -0.8),
+                     eye=(3.0, 2.0, 1.0), bgColor=(0.1, 0.2, 0.3), alphaMode=1)
+    parts = torch.stack([torch.rand(H, W, 4, generator=torch.Generator().manual_seed(100 + r)).reshape(-1, 4)
+                         for r in range(2)])
+    order = mdist.visibility_order(np.array(P.eye, dtype=np.float64), P, (2, 1, 1))
+    assert order == [1, 0]                                     # eye on the +x side: the +x half is in front
+    want = mdist.composite_over_torch(parts, order, P.bgColor, 1).reshape(H, W, 4).numpy()
+    assert np.array_equal(got, want)
+
+
 def test_sort_last_helpers():
     from mri_raytracer_b200 import dist as mdist, RenderParams
     for R in (1, 2, 4, 8):
