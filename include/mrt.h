@@ -99,6 +99,16 @@ typedef struct MrtParams {
   uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3]; uint32_t padShard;
 } MrtParams;
 
+/* One camera of a batch of views: the four camera rows of `struct Params`
+ * (brats_rt.slang:15-18; filled per frame from OrbitalCamera.get_basis(), brats_viewer.py:400-410),
+ * with the same 16-byte row padding. */
+typedef struct MrtCamera {
+  float eye[3]; float pad0;
+  float U[3]; float pad1;
+  float V[3]; float pad2;
+  float W[3]; float pad3;
+} MrtCamera;
+
 /* Slab renderer params: `struct Params` of scripts/volumeRendering/volume_render.slang:9-21
  * (std140-like packing of that cbuffer is backend-defined; this is our own plain layout). */
 typedef struct MrtSlabParams {
@@ -117,6 +127,9 @@ const char* mrt_last_error(void);
 /* sizeof(MrtParams) as compiled into the library (ABI self-check for bindings). */
 size_t mrt_sizeof_params(void);
 size_t mrt_sizeof_slab_params(void);
+size_t mrt_sizeof_camera(void);
+/* Views rendered by one kernel launch of mrt_render_forward_batch (larger batches are chunked). */
+int32_t mrt_max_views_per_launch(void);
 
 /* ------------------------------------------------ integer tile map (host)
  * The bit-exact integer contract of the dispatch geometry
@@ -202,6 +215,20 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C,
                        const int32_t* labels, const int32_t* preds,
                        float* out_rgba, float* out_T, int32_t* out_counts,
                        int32_t tile_begin, int32_t tile_end, void* stream);
+
+/* A batch of views of ONE volume under ONE parameter block: what the reference's frame loop
+ * does with `nviews` successive dispatches whose params differ only in (eye, U, V, W)
+ * (brats_viewer.py:400-442).  Here it is one launch per <= mrt_max_views_per_launch() views
+ * (grid.y = view), so the long central rays of one view overlap the short border rays of the
+ * next.  `cams` is a HOST array; params->eye/U/V/W are ignored.  Outputs are contiguous
+ * [nviews][H][W](...) device buffers; view v of the batch is bit-identical to
+ * mrt_render_forward with cams[v] copied into params. */
+int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                             const void* packed, int32_t C,
+                             const float* tf, int32_t tfN, const uint8_t* skip_levels,
+                             const int32_t* labels, const int32_t* preds,
+                             float* out_rgba, float* out_T, int32_t* out_counts,
+                             int32_t tile_begin, int32_t tile_end, void* stream);
 
 /* ------------------------------------------------ backward
  * Adjoint of mrt_render_forward w.r.t. the volume and the transfer function

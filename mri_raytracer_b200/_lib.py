@@ -43,6 +43,13 @@ class MrtParams(C.Structure):
     ]
 
 
+class MrtCamera(C.Structure):
+    """Mirror of ``struct MrtCamera``: the four camera rows of the reference's ``struct Params``
+    (inr/viewer/brats_rt.slang:15-18)."""
+    _fields_ = [("eye", C.c_float * 3), ("pad0", C.c_float), ("U", C.c_float * 3), ("pad1", C.c_float),
+                ("V", C.c_float * 3), ("pad2", C.c_float), ("W", C.c_float * 3), ("pad3", C.c_float)]
+
+
 class MrtSlabParams(C.Structure):
     """Mirror of ``struct MrtSlabParams`` (scripts/volumeRendering/volume_render.slang:9-21)."""
     _fields_ = [
@@ -66,6 +73,8 @@ PROTOTYPES = {
     "mrt_last_error": (C.c_char_p, []),
     "mrt_sizeof_params": (_sz, []),
     "mrt_sizeof_slab_params": (_sz, []),
+    "mrt_sizeof_camera": (_sz, []),
+    "mrt_max_views_per_launch": (_i32, []),
     "mrt_tiles_x": (_i32, [_i32]),
     "mrt_tiles_y": (_i32, [_i32]),
     "mrt_tile_count": (_i32, [_i32, _i32]),
@@ -84,6 +93,8 @@ PROTOTYPES = {
     "mrt_build_label_occupancy": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_classify_bricks": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_render_forward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mrt_render_forward_batch": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _i32, _i32, _vp]),
     "mrt_backward_scratch_bytes": (_sz, [_i32]),
     "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _i32, _i32, _vp]),
@@ -119,6 +130,8 @@ def lib():
         raise MrtError(f"MrtParams ABI mismatch: lib {L.mrt_sizeof_params()} vs ctypes {C.sizeof(MrtParams)}")
     if L.mrt_sizeof_slab_params() != C.sizeof(MrtSlabParams):
         raise MrtError("MrtSlabParams ABI mismatch")
+    if L.mrt_sizeof_camera() != C.sizeof(MrtCamera):
+        raise MrtError("MrtCamera ABI mismatch")
     _lib = L
     return L
 

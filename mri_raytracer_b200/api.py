@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import replace
-from typing import Optional, Tuple, Union
+from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -122,6 +122,43 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
     check(lib().mrt_render_forward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
                                    _ptr(skip_levels), _ptr(labels), _ptr(preds), out.data_ptr(), _ptr(out_T),
                                    _ptr(out_counts), t0, t1, _stream()), "render_forward")
+    return out
+
+
+def _camera_array(cams: Sequence) -> "C.Array":
+    arr = (_lib.MrtCamera * len(cams))()
+    for a, c in zip(arr, cams):
+        for name in ("eye", "U", "V", "W"):
+            v = np.asarray(getattr(c, name), dtype=np.float32)
+            getattr(a, name)[:] = [float(v[0]), float(v[1]), float(v[2])]
+    return arr
+
+
+def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
+                         tf: Optional[torch.Tensor] = None, skip_levels: Optional[torch.Tensor] = None,
+                         labels: Optional[torch.Tensor] = None, preds: Optional[torch.Tensor] = None,
+                         out: Optional[torch.Tensor] = None, out_T: Optional[torch.Tensor] = None,
+                         out_counts: Optional[torch.Tensor] = None,
+                         tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Thin wrapper over ``mrt_render_forward_batch``: ``len(cams)`` views of one volume under one
+    parameter block in one launch (per 64 views) -> ``[V,H,W,4]``.  ``cams`` are
+    :class:`camera.Camera` objects; they must share fov / projection with ``P`` (only
+    eye/U/V/W vary inside a batch, like successive frames of the reference's loop)."""
+    W, H = P.imageSize
+    V = len(cams)
+    if V < 1:
+        raise ValueError("render_forward_batch needs at least one camera")
+    if out is None:
+        out = torch.empty((V, H, W, 4), dtype=torch.float32, device=packed.device)
+    elif tuple(out.shape) != (V, H, W, 4) or not out.is_contiguous():
+        raise ValueError(f"out must be contiguous [V,H,W,4]={(V, H, W, 4)}, got {tuple(out.shape)}")
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    s = P.to_struct()
+    arr = _camera_array(cams)
+    check(lib().mrt_render_forward_batch(C.byref(s), C.cast(arr, C.c_void_p), V, packed.data_ptr(), Cn, _ptr(tf),
+                                         0 if tf is None else tf.shape[0], _ptr(skip_levels), _ptr(labels),
+                                         _ptr(preds), out.data_ptr(), _ptr(out_T), _ptr(out_counts), t0, t1,
+                                         _stream()), "render_forward_batch")
     return out
 
 
@@ -293,6 +330,18 @@ class Volume:
                               out_counts=out_counts, tile_range=tile_range)
 
 
+    def forward_batch(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor],
+                      out: Optional[torch.Tensor] = None, out_T: Optional[torch.Tensor] = None,
+                      out_counts: Optional[torch.Tensor] = None,
+                      tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """classify ONCE (the skip levels do not depend on the camera) + one batched march."""
+        P = P.with_camera(cams[0])
+        packed, Cn, Pe = self.prepared(P)
+        bits = self.skip_levels(P, tf)
+        return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
+                                    out_T=out_T, out_counts=out_counts, tile_range=tile_range)
+
+
 # ----------------------------------------------------------------------------- autograd
 class _RenderFn(torch.autograd.Function):
     @staticmethod
@@ -372,6 +421,35 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
             if tuple(lab.shape) != (Z, Y, X):
                 raise ValueError(f"{name} must be [Z,Y,X]")
     return _RenderFn.apply(volume, tf, P, labels, preds, fold)
+
+
+def render_views(volume: Volume, cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,
+                 out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Render a batch of views of a prepared :class:`Volume` -> float32 ``[V,H,W,4]``: the
+    reference's frame loop over successive camera poses (inr/viewer/brats_viewer.py:400-442) as
+    one classify + one march launch per 64 views.  View ``v`` is bit-identical to
+    ``render(volume, cams[v], tf, params)``.  The cameras must share the projection
+    (fov / ortho window) — only eye/U/V/W vary within a batch.  Not differentiable (use
+    :func:`render` per view for gradients)."""
+    if not isinstance(volume, Volume):
+        raise TypeError("render_views needs a prepared Volume")
+    cams = list(cams)
+    if not cams:
+        raise ValueError("render_views needs at least one camera")
+    c0 = cams[0]
+    for c in cams[1:]:
+        if (bool(c.ortho), float(c.fovY)) != (bool(c0.ortho), float(c0.fovY)) or (
+                c.ortho and float(c.ortho_half_height) != float(c0.ortho_half_height)):
+            raise ValueError("all cameras of a batch must share fovY / ortho / orthoHalfHeight")
+    if tf is not None:
+        _need_cuda(tf, "tf", torch.float32)
+        if tf.dim() != 2 or tf.shape[1] != 4 or not (2 <= tf.shape[0] <= _lib.MRT_MAX_TF):
+            raise ValueError(f"tf must be [N,4] with 2 <= N <= {_lib.MRT_MAX_TF}, got {tuple(tf.shape)}")
+    P = replace(params.with_camera(c0), tfMode=1 if tf is not None else 0)
+    if tuple(P.dims) != tuple(volume.global_dims):
+        raise ValueError(f"params.dims {P.dims} != volume dims {volume.global_dims}")
+    P.validate()
+    return volume.forward_batch(P, cams, tf, out=out, tile_range=tile_range)
 
 
 def render_aux(volume: Volume, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams):

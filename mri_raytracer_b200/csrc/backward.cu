@@ -87,7 +87,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
 
   const size_t pix = (size_t)py * P.W + px;
   const float4 G = __ldg(dL_dout + pix);
-  const Ray ray = mrt_setup_ray(P, px, py);
+  const Ray ray = mrt_setup_ray(P, P.eye, px, py);
   if (!(ray.n > 0 && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || (P.alphaMode && G.w != 0.0f)))) return;
 
   const float4 Cout = __ldg(out_rgba + pix);

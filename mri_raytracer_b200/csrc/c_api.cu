@@ -30,6 +30,8 @@ int mrt_version(void) { return MRT_VERSION; }
 const char* mrt_last_error(void) { return g_err; }
 size_t mrt_sizeof_params(void) { return sizeof(MrtParams); }
 size_t mrt_sizeof_slab_params(void) { return sizeof(MrtSlabParams); }
+size_t mrt_sizeof_camera(void) { return sizeof(MrtCamera); }
+int32_t mrt_max_views_per_launch(void) { return MRT_MAX_VIEWS; }
 
 // ---------------------------------------------------------------- tiles (host)
 int32_t mrt_tiles_x(int32_t W) { return mrt_tiles_x_(W); }
@@ -225,9 +227,40 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, c
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward: tfMode=1 needs tf");
   if (K.showSeg && !labels) K.showSeg = 0;                  // brats_viewer.py:423 (showSeg only with a buffer)
   if (K.showPred && !preds) K.showPred = 0;                 // brats_viewer.py:424
-  cudaError_t e = mrt_launch_forward(K, mrt_packed_channels(C), packed, tf, skip_levels, labels, preds,
+  cudaError_t e = mrt_launch_forward(K, nullptr, 1, mrt_packed_channels(C), packed, tf, skip_levels, labels, preds,
                                      out_rgba, out_T, out_counts, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
+}
+
+int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                             const void* packed, int32_t C, const float* tf, int32_t tfN,
+                             const uint8_t* skip_levels, const int32_t* labels, const int32_t* preds,
+                             float* out_rgba, float* out_T, int32_t* out_counts,
+                             int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba, "render_forward_batch: null volume or output");
+  MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch: needs >= 1 camera");
+  KParams K;
+  if (int r = derive(params, C, tfN, skip_levels != nullptr, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_batch: tfMode=1 needs tf");
+  if (K.showSeg && !labels) K.showSeg = 0;
+  if (K.showPred && !preds) K.showPred = 0;
+  static_assert(sizeof(MrtCamera) == 16 * sizeof(float), "MrtCamera layout");
+  cudaError_t e = cudaSuccess;
+  float chunk[MRT_MAX_VIEWS * 12];
+  const size_t npix = (size_t)K.W * K.H;
+  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
+    const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+    for (int v = 0; v < nv; ++v)
+      for (int i = 0; i < 3; ++i) {
+        const MrtCamera& c = cams[v0 + v];
+        chunk[v * 12 + i] = c.eye[i]; chunk[v * 12 + 3 + i] = c.U[i];
+        chunk[v * 12 + 6 + i] = c.V[i]; chunk[v * 12 + 9 + i] = c.W[i];
+      }
+    e = mrt_launch_forward(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels, labels, preds,
+                           out_rgba + (size_t)v0 * npix * 4, out_T ? out_T + (size_t)v0 * npix : nullptr,
+                           out_counts ? out_counts + (size_t)v0 * npix * 4 : nullptr, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch");
 }
 
 size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }

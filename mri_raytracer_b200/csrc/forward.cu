@@ -18,8 +18,9 @@
 #endif
 
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-__global__ void __launch_bounds__(64 * MRT_FWD_TPB)
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB, 1024 / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
+               const __grid_constant__ CamBatch B,
                const typename Vox<NCH>::T* __restrict__ vol,
                const float4* __restrict__ tf,
                const uint8_t* __restrict__ levels,
@@ -50,7 +51,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
   if (px >= P.W || py >= P.H) return;                                      // :89
 
-  const Ray ray = mrt_setup_ray(P, px, py);
+  const int view = blockIdx.y;                                             // batch of views: one camera each
+  const Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
   // a sort-last shard renders a partial: premultiplied colour WITHOUT background, alpha = T_local
   float Cr = P.shard ? 0.0f : P.bg[0], Cg = P.shard ? 0.0f : P.bg[1], Cb = P.shard ? 0.0f : P.bg[2];   // :111
   float T = 1.0f;                                                          // :112
@@ -155,7 +157,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       }
     }
   }
-  const size_t pix = (size_t)py * P.W + px;
+  const size_t pix = ((size_t)view * P.H + py) * P.W + px;
   out_rgba[pix] = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
   if (out_T) out_T[pix] = T;
   if (GENERIC) { if (out_counts) out_counts[pix] = make_int4(ray.n, k, n_eval, n_seg); }
@@ -163,25 +165,25 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
 
 // ------------------------------------------------------------------------- dispatch
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-static cudaError_t launch_fwd(const KParams& P, const void* vol, const float* tf, const uint8_t* levels,
+static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
   const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
-  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC><<<grid, 64 * MRT_FWD_TPB, smem, st>>>(
-      P, (const typename Vox<NCH>::T*)vol, (const float4*)tf, levels, labels, preds,
+  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
+      P, B, (const typename Vox<NCH>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
 }
 
 template <int NCH>
-static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen, const void* vol, const float* tf,
+static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews, bool lab, bool skip, bool gen, const void* vol, const float* tf,
                                 const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                 float* o, float* oT, int32_t* oc, cudaStream_t st) {
 #define MRT_CASE(L, S, G) if (lab == L && skip == S && gen == G) \
-    return launch_fwd<NCH, L, S, G>(P, vol, tf, levels, labels, preds, o, oT, oc, st);
+    return launch_fwd<NCH, L, S, G>(P, B, nviews, vol, tf, levels, labels, preds, o, oT, oc, st);
   MRT_CASE(false, false, false) MRT_CASE(false, true, false)
   MRT_CASE(true, false, false)  MRT_CASE(true, true, false)
   MRT_CASE(false, false, true)  MRT_CASE(false, true, true)
@@ -190,16 +192,39 @@ static cudaError_t dispatch_fwd(const KParams& P, bool lab, bool skip, bool gen,
   return cudaErrorInvalidValue;
 }
 
-cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                               const uint8_t* levels, const int32_t* labels, const int32_t* preds,
+// `cams` = nviews x 12 floats (eye, U, V, W per view), nullptr = the single camera in P.  The
+// outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
+// MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
+// central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
+cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                               const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st) {
+  if (cams != nullptr && nviews > MRT_MAX_VIEWS) {
+    const size_t npix = (size_t)P.W * P.H;
+    for (int v0 = 0; v0 < nviews; v0 += MRT_MAX_VIEWS) {
+      const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+      cudaError_t e = mrt_launch_forward(P, cams + (size_t)v0 * 12, nv, packed_ch, vol, tf, levels, labels, preds,
+                                         out_rgba + (size_t)v0 * npix * 4, out_T ? out_T + (size_t)v0 * npix : nullptr,
+                                         out_counts ? out_counts + (size_t)v0 * npix * 4 : nullptr, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  CamBatch B;
+  if (cams == nullptr) {
+    nviews = 1;
+    for (int i = 0; i < 3; ++i) { B.cam[0][i] = P.eye[i]; B.cam[0][3 + i] = P.U[i]; B.cam[0][6 + i] = P.V[i]; B.cam[0][9 + i] = P.Wv[i]; }
+  } else {
+    if (nviews < 1) return cudaSuccess;
+    for (int v = 0; v < nviews; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)v * 12 + i];
+  }
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && levels != nullptr && P.tMode == 0;
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
   switch (packed_ch) {
-    case 1: return dispatch_fwd<1>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    case 2: return dispatch_fwd<2>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    case 4: return dispatch_fwd<4>(P, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 1: return dispatch_fwd<1>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 2: return dispatch_fwd<2>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 4: return dispatch_fwd<4>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
   }
   return cudaErrorInvalidValue;
 }

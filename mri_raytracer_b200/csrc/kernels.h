@@ -6,8 +6,8 @@
 
 struct KParams;
 
-cudaError_t mrt_launch_forward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                               const uint8_t* levels, const int32_t* labels, const int32_t* preds,
+cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                               const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st);
 
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,

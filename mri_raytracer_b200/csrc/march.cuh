@@ -44,6 +44,11 @@ struct KParams {
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
 };
 
+// Cameras of a batch of views rendered by ONE launch (blockIdx.y = view): everything else in
+// KParams is shared.  12 floats per view: eye, U, V, W.
+#define MRT_MAX_VIEWS 64
+struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
+
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
   float t0, t1;
@@ -56,8 +61,11 @@ __device__ __forceinline__ float mrt_norm3(float x, float y, float z) {
 
 // makePrimary (brats_rt.slang:36-46) / orthographic, then de-zero + aabbHit +
 // near/far clamp (:95-99, :48-57, :107-109) and the indexed sample count.
-__device__ __forceinline__ Ray mrt_setup_ray(const KParams& P, int px, int py) {
+// `cam` = 12 floats (eye, U, V, W): KParams::eye for a single frame, one row of CamBatch for a
+// batch of views.
+__device__ __forceinline__ Ray mrt_setup_ray(const KParams& P, const float* __restrict__ cam, int px, int py) {
   Ray r;
+  const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
   const float dimx = (float)P.W, dimy = (float)P.H;
   const float ndcx = __fdiv_rn(__fadd_rn((float)px, 0.5f), dimx);
   const float ndcy = __fdiv_rn(__fadd_rn((float)py, 0.5f), dimy);
@@ -68,22 +76,22 @@ __device__ __forceinline__ Ray mrt_setup_ray(const KParams& P, int px, int py) {
     const float halfW = __fmul_rn(aspect, P.halfH);
     const float ax = __fmul_rn(uvx, halfW);
     const float ay = -__fmul_rn(uvy, P.halfH);
-    r.ox = __fadd_rn(__fadd_rn(P.eye[0], __fmul_rn(ax, P.U[0])), __fmul_rn(ay, P.V[0]));
-    r.oy = __fadd_rn(__fadd_rn(P.eye[1], __fmul_rn(ax, P.U[1])), __fmul_rn(ay, P.V[1]));
-    r.oz = __fadd_rn(__fadd_rn(P.eye[2], __fmul_rn(ax, P.U[2])), __fmul_rn(ay, P.V[2]));
-    r.dx = P.Wv[0]; r.dy = P.Wv[1]; r.dz = P.Wv[2];
+    r.ox = __fadd_rn(__fadd_rn(eye[0], __fmul_rn(ax, U[0])), __fmul_rn(ay, V[0]));
+    r.oy = __fadd_rn(__fadd_rn(eye[1], __fmul_rn(ax, U[1])), __fmul_rn(ay, V[1]));
+    r.oz = __fadd_rn(__fadd_rn(eye[2], __fmul_rn(ax, U[2])), __fmul_rn(ay, V[2]));
+    r.dx = Wv[0]; r.dy = Wv[1]; r.dz = Wv[2];
   } else {
     float cx = __fdiv_rn(__fmul_rn(uvx, aspect), P.focal);
     float cy = __fdiv_rn(-uvy, P.focal);
     float cz = 1.0f;
     const float inv = mrt_norm3(cx, cy, cz);
     cx = __fdiv_rn(cx, inv); cy = __fdiv_rn(cy, inv); cz = __fdiv_rn(cz, inv);
-    const float rx = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[0]), __fmul_rn(cy, P.V[0])), __fmul_rn(cz, P.Wv[0]));
-    const float ry = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[1]), __fmul_rn(cy, P.V[1])), __fmul_rn(cz, P.Wv[1]));
-    const float rz = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.U[2]), __fmul_rn(cy, P.V[2])), __fmul_rn(cz, P.Wv[2]));
+    const float rx = __fadd_rn(__fadd_rn(__fmul_rn(cx, U[0]), __fmul_rn(cy, V[0])), __fmul_rn(cz, Wv[0]));
+    const float ry = __fadd_rn(__fadd_rn(__fmul_rn(cx, U[1]), __fmul_rn(cy, V[1])), __fmul_rn(cz, Wv[1]));
+    const float rz = __fadd_rn(__fadd_rn(__fmul_rn(cx, U[2]), __fmul_rn(cy, V[2])), __fmul_rn(cz, Wv[2]));
     const float n = mrt_norm3(rx, ry, rz);
     r.dx = __fdiv_rn(rx, n); r.dy = __fdiv_rn(ry, n); r.dz = __fdiv_rn(rz, n);
-    r.ox = P.eye[0]; r.oy = P.eye[1]; r.oz = P.eye[2];
+    r.ox = eye[0]; r.oy = eye[1]; r.oz = eye[2];
   }
   // de-zero: sign dropped on purpose (:96-98); rcpDir uses the patched copy only
   const float ex = fabsf(r.dx) < 1e-6f ? 1e-6f : r.dx;

@@ -37,11 +37,23 @@ def _world(group=None) -> Tuple[int, int]:
 
 
 def _default_render_fn(volume, tf):
-    from . import api
-
     def fn(P: RenderParams, tile_range: Tuple[int, int], out: torch.Tensor):
         volume.forward(replace(P, tfMode=1 if tf is not None else 0), tf, out=out, tile_range=tile_range)
     return fn
+
+
+def _render_batch(volume, tf, P: RenderParams, cams: Sequence, tile_range: Tuple[int, int], out: torch.Tensor,
+                  render_fn: Optional[Callable]):
+    """``len(cams)`` views into the contiguous ``out [V,H,W,4]``: ONE batched launch on the CUDA
+    path (api.Volume.forward_batch), a per-view loop when a ``render_fn`` is injected (CPU tests)."""
+    if not len(cams):
+        return
+    if render_fn is None:
+        volume.forward_batch(replace(P, tfMode=1 if tf is not None else 0), list(cams), tf, out=out,
+                             tile_range=tile_range)
+    else:
+        for v, cam in enumerate(cams):
+            render_fn(P.with_camera(cam), tile_range, out[v])
 
 
 # ----------------------------------------------------------------------------- image space
@@ -63,7 +75,6 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
     rank, R = _world(group)
     W, H = P.imageSize
     V = len(cams)
-    fn = render_fn or _default_render_fn(volume, tf)
     device = device if device is not None else getattr(volume, "device", "cpu")
     nt = tiles.tile_count(W, H)
     if mode == "views":
@@ -71,8 +82,7 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
             raise ValueError(f"mode='views' needs len(cams) ({V}) divisible by world size ({R})")
         out = torch.empty((V, H, W, 4), dtype=torch.float32, device=device)
         v0, v1 = view_partition(V, rank, R)
-        for v in range(v0, v1):
-            fn(P.with_camera(cams[v]), (0, nt), out[v])
+        _render_batch(volume, tf, P, cams[v0:v1], (0, nt), out[v0:v1], render_fn)
         if R > 1 and gather:
             dist.all_gather_into_tensor(out.view(-1), out[v0:v1].reshape(-1), group=group)
         return out
@@ -85,10 +95,9 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
         tr1 = min((rank + 1) * (rows // tiles.TILE), tiles.tiles_y(H))
         y0, y1 = tr0 * tiles.TILE, min(tr1 * tiles.TILE, H)
         if tr1 > tr0:
-            full = torch.empty((H, W, 4), dtype=torch.float32, device=device)
-            for v in range(V):
-                fn(P.with_camera(cams[v]), (tr0 * tx, tr1 * tx), full)
-                buf[rank, v, : y1 - y0] = full[y0:y1]
+            full = torch.empty((V, H, W, 4), dtype=torch.float32, device=device)
+            _render_batch(volume, tf, P, cams, (tr0 * tx, tr1 * tx), full, render_fn)
+            buf[rank, :, : y1 - y0] = full[:, y0:y1]
         if R > 1 and gather:
             dist.all_gather_into_tensor(buf.view(-1), buf[rank].reshape(-1), group=group)
         # [R,V,rows,W,4] -> [V, R*rows, W, 4] -> crop
@@ -131,6 +140,11 @@ class PeerFramebuffer:
         buf = self.remote if self.p2p else self.local
         return buf[self.rank * self.Vloc + v_local]
 
+    def targets(self) -> torch.Tensor:
+        """This rank's contiguous ``[Vloc,H,W,4]`` slice of the (root's, when p2p) framebuffer."""
+        buf = self.remote if self.p2p else self.local
+        return buf[self.rank * self.Vloc:(self.rank + 1) * self.Vloc]
+
     def finish(self):
         """Make the batch visible on the root: a barrier (p2p) or the NCCL gather (fallback)."""
         if self.R == 1:
@@ -152,9 +166,9 @@ def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: Re
     """Render this rank's views into the (peer) framebuffer; call ``fb.finish()`` afterwards."""
     W, H = P.imageSize
     nt = tiles.tile_count(W, H)
-    fn = render_fn or _default_render_fn(volume, tf)
-    for v, cam in enumerate(cams_local):
-        fn(P.with_camera(cam), (0, nt), fb.target(v))
+    if len(cams_local) != fb.Vloc:
+        raise ValueError(f"framebuffer holds {fb.Vloc} views per rank, got {len(cams_local)} cameras")
+    _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
 
 
 # ----------------------------------------------------------------------------- sort-last

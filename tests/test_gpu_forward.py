@@ -110,6 +110,35 @@ def test_ragged_image_sizes_and_tile_ranges(cuda):
         assert torch.equal(out, full)
 
 
+@pytest.mark.parametrize("ortho", [False, True])
+def test_batched_views_equal_single_frames(cuda, ortho):
+    """mrt_render_forward_batch: view v of one batched launch == the single-frame call, bit for bit
+    (incl. a batch larger than one launch's 64 views, tile ranges and the per-ray counters)."""
+    from mri_raytracer_b200 import Camera, OrbitalCamera, orbit_views, tiles
+    vol, lab, P = small_scene(C=4, dims=(40, 36, 28), W=41, H=27, seed=8, labels=True, ortho=ortho)
+    tf = ramp_tf(64).cuda()
+    V = api.Volume(vol.cuda(), labels=lab.cuda())
+    P = replace(P, showSeg=1)
+    cam = V.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.3, initial_phi=1.2))
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 67, ortho=ortho)
+    batch = api.render_views(V, cams, tf, P)
+    assert batch.shape == (67, 27, 41, 4)
+    for v in (0, 1, 31, 63, 64, 66):
+        single = api.render(V, cams[v], tf, P)
+        assert torch.equal(batch[v], single), f"view {v} differs from the single-frame render"
+    ref = O.render(vol, replace(P.with_camera(cams[5]), tfMode=1), tf=tf.cpu(), labels=lab.long())
+    assert (batch[5].cpu() - ref).abs().max() <= 1e-4
+    # two disjoint tile ranges of the batch == the whole batch
+    nt = tiles.tile_count(41, 27)
+    out = torch.full((3, 27, 41, 4), -7.0, device="cuda")
+    for r in range(2):
+        api.render_views(V, cams[:3], tf, P, out=out, tile_range=tiles.rank_tile_range(nt, r, 2))
+    assert torch.equal(out, batch[:3])
+    with pytest.raises(ValueError):
+        api.render_views(V, [cams[0], replace(cams[1], fovY=0.5)], tf, P)
+
+
 def test_refold_when_weights_change(cuda):
     vol, _, P = small_scene(C=4, dims=(32, 28, 24), W=40, H=32, seed=9)
     V = api.Volume(vol.cuda())
