@@ -98,6 +98,8 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
   const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
   const float dt = P.dt, thr = P.thr;
   const float nm1 = (float)(ntf - 1);
+  uint32_t s_tf_addr = (uint32_t)__cvta_generic_to_shared(s_tf);
+    asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
   const uint32_t sY = P.pitchY, sZ = P.pitchZ;
   float T = 1.0f, prefix = 0.0f;
   int k = 0;
@@ -110,7 +112,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
     const float val = mrt_window<GENERIC>(P, raw);
     if (P.tfMode || val > 0.0f) {
       int j0; float fr;
-      const float4 rgba = mrt_tf_lookup(s_tf, nm1, val, &j0, &fr);
+      const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
       const float alpha = mrt_alpha(P, rgba.w);
       const float aT = alpha * T;
       const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
@@ -131,7 +133,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
         // saturate: torch.clamp passes the gradient on the closed interval [0,1]
         const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval : 0.0f;
         if (dv != 0.0f) {
-          const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ;
+          const uint32_t b = (uint32_t)c.ix() + (uint32_t)c.iy() * sY + (uint32_t)c.iz() * sZ;
           VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
           const float gx0 = 1.0f - c.fx, gy0 = 1.0f - c.fy, gz0 = 1.0f - c.fz;
           const float w00 = dv * gy0 * gz0, w10 = dv * c.fy * gz0, w01 = dv * gy0 * c.fz, w11 = dv * c.fy * c.fz;
@@ -193,7 +195,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
             const float val = mrt_window<GENERIC>(P, cval * P.wq[0] + P.wbias);
             if (P.tfMode || val > 0.0f) {
               int j0; float fr;
-              const float4 rgba = mrt_tf_lookup(s_tf, nm1, val, &j0, &fr);
+              const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
               const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
               const float dsig = (float)(kend - k) * dt * (T * gc - (S_tot - prefix) - tn_term);
               dtf_add(dtfp, j0, 1.0f - fr, 0.f, 0.f, 0.f, dsig);

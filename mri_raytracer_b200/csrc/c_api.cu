@@ -112,6 +112,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     mrt_layout(mrt_packed_channels(C), ldim[0], ldim[1], ldim[2], &pY, &pZ);
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
     K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;
+    K->idx_bias = K->base_off + 0x4b000000u * (1u + K->pitchY + K->pitchZ);
   }
   // tan evaluated once in double, rounded to float (documented deviation from the per-thread fp32 tan)
   K->ortho = M->ortho ? 1 : 0;

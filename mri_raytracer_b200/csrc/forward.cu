@@ -18,7 +18,7 @@
 #endif
 
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-__global__ void __launch_bounds__(64 * MRT_FWD_TPB, 1024 / (64 * MRT_FWD_TPB))
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 1024) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
                const typename Vox<NCH>::T* __restrict__ vol,
@@ -49,20 +49,25 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   if (tile >= P.tile_end) return;
   int px, py;
   mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
-  if (px >= P.W || py >= P.H) return;                                      // :89
+  // :89 — pixels outside the image keep their lane alive (the skip loop uses warp votes) with an
+  // empty ray, and never store
+  const bool inside = (px < P.W) && (py < P.H);
 
   const int view = blockIdx.y;                                             // batch of views: one camera each
-  const Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
+  Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
+  if (!inside) ray.n = 0;
   // a sort-last shard renders a partial: premultiplied colour WITHOUT background, alpha = T_local
   float Cr = P.shard ? 0.0f : P.bg[0], Cg = P.shard ? 0.0f : P.bg[1], Cb = P.shard ? 0.0f : P.bg[2];   // :111
   float T = 1.0f;                                                          // :112
   int k = 0, n_eval = 0, n_seg = 0;
 
-  if (ray.n > 0) {
+  {                                           // rays with n == 0 (miss / outside) run zero iterations below
     const IdxRay q = mrt_index_ray(P, ray);
     const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
     const float dt = P.dt, thr = P.thr;
     const float nm1 = (float)(P.tfN - 1);
+    uint32_t s_tf_addr = (uint32_t)__cvta_generic_to_shared(s_tf);
+    asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
 
     // one sample slot at ray parameter t  (:119-162)
     auto shade = [&](float t) {
@@ -70,7 +75,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
       const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH>(P, vol, c));
       if (P.tfMode) {
-        const float4 rgba = mrt_tf_lookup(s_tf, nm1, val);
+        const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val);
         const float alpha = mrt_alpha(P, rgba.w);
         const float aT = alpha * T;
         Cr = fmaf(aT, rgba.x, Cr); Cg = fmaf(aT, rgba.y, Cg); Cb = fmaf(aT, rgba.z, Cb);
@@ -106,7 +111,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     if (GENERIC && P.tMode == 1) {
       // reference-faithful running sum t += stepSize (:113,:164); no skipping possible
       float t = ray.t0;
-      while (t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) {
+      while (ray.n > 0 && t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) {
         shade(t);
         t += dt; ++k; ++n_eval;
       }
@@ -115,31 +120,55 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       const float inv_dt = 1.0f / dt;
       int n = ray.n;
       if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, inv_dt, ray.n, &ks, &n); k = ks; }
-      int kact = 0;                      // slots [k, kact) are known to lie in an active brick
+      // Per-lane knowledge of the ray, in slot indices (k <= kact <= kf <= kl):
+      //   [k, kact)   current run, inside active bricks: to be shaded
+      //   [kact, kf)  known empty (leapt cells / another shard's slots)
+      //   [kf, kl)    look-ahead run, known active (empty when kl == kf)
+      //   [kl, n)     unknown
+      int kact = k, kf = k, kl = k;
       for (;;) {
-        // phase 1: advance to the next slot inside an active brick
-        while (k >= kact && k < n && T > thr) {
-          const float t = fmaf((float)k, dt, ray.t0);
-          const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-          const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);               // == floor of the clamped coord
-          const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
-          const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
-          if (P.shard && !mrt_shard_owns(P, ix, iy, iz)) { ++k; continue; }   // another rank's slot
-          const int jx = ix - P.slo[0], jy = iy - P.slo[1], jz = iz - P.slo[2];   // brick grid is shard-local
-          const int lvl = __ldg(levels + (((jz >> MRT_BRICK_SHIFT) * P.nby + (jy >> MRT_BRICK_SHIFT)) * P.nbx +
-                                          (jx >> MRT_BRICK_SHIFT)));
-          const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-          int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, jx >> sh, jy >> sh, jz >> sh, sh, t, inv_dt,
-                                               P.slo[0], P.slo[1], P.slo[2]));
-          if (GENERIC) ++n_seg;
-          // an ACTIVE brick may straddle the shard's far faces: stop at the owned box's exit
-          if (P.shard && !lvl) kend = min(kend, k + mrt_shard_slots(P, q, ivx, ivy, ivz, t, inv_dt));
-          if (lvl) k = kend; else kact = kend;
+        if (k >= kact && T > thr) {                       // current run exhausted: take the look-ahead
+          k = kf; kact = kl; kf = kl;                     // (not after ERT: k stays the oracle's n_taken)
         }
-        if (!(k < n && T > thr)) break;                                    // :117
+        const bool live = (k < n) && (T > thr);            // :117
+        // phase 1 (warp-wide): as soon as ONE lane has nothing to shade, EVERY lane extends its
+        // knowledge by one brick look-up at its own frontier kl — an instruction costs the same
+        // for 1 lane or 32, so the other lanes' look-ups ride along for free and the (divergent)
+        // look-up code runs once per ~brick length instead of once per shaded slot.
+        // one warp reduction answers both questions: bit 0 = some lane is live, bit 1 = some live
+        // lane has nothing to shade
+        const unsigned wst = __reduce_or_sync(0xffffffffu, (live ? 1u : 0u) | ((live && k >= kact) ? 2u : 0u));
+        if (wst & 2u) {
+          if (live && kl < n) {
+            const float t = fmaf((float)kl, dt, ray.t0);
+            const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+            const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);             // == floor of the clamped coord
+            const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
+            const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+            int lvl = 1, kend = kl + 1;                                   // another rank's slot: a 1-slot gap
+            if (!P.shard || mrt_shard_owns(P, ix, iy, iz)) {
+              const int jx = ix - P.slo[0], jy = iy - P.slo[1], jz = iz - P.slo[2];   // brick grid is shard-local
+              lvl = __ldg(levels + (((jz >> MRT_BRICK_SHIFT) * P.nby + (jy >> MRT_BRICK_SHIFT)) * P.nbx +
+                                    (jx >> MRT_BRICK_SHIFT)));
+              const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+              kend = min(n, kl + mrt_cell_slots(q, ivx, ivy, ivz, jx >> sh, jy >> sh, jz >> sh, sh, t, inv_dt,
+                                                P.slo[0], P.slo[1], P.slo[2]));
+              // an ACTIVE brick may straddle the shard's far faces: stop at the owned box's exit
+              if (P.shard && !lvl) kend = min(kend, kl + mrt_shard_slots(P, q, ivx, ivy, ivz, t, inv_dt));
+              if (GENERIC) ++n_seg;
+            }
+            if (!lvl) kl = kend;                           // active: start / extend the look-ahead run
+            else if (kl == kf) kf = kl = kend;             // empty, directly behind the gap: widen the gap
+            // (an empty cell behind a look-ahead run cannot be recorded yet: looked up again later)
+          }
+          continue;
+        }
+        if (!wst) break;
         // phase 2: every live lane of the warp shades one slot
-        shade(fmaf((float)k, dt, ray.t0));
-        ++k; if (GENERIC) ++n_eval;
+        if (live) {
+          shade(fmaf((float)k, dt, ray.t0));
+          ++k; if (GENERIC) ++n_eval;
+        }
       }
     } else {
       int n = ray.n;
@@ -157,6 +186,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       }
     }
   }
+  if (!inside) return;
   const size_t pix = ((size_t)view * P.H + py) * P.W + px;
   out_rgba[pix] = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
   if (out_T) out_T[pix] = T;

@@ -42,6 +42,7 @@ struct KParams {
   int shard;
   int slo[3], shi[3];
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
+  unsigned idx_bias;      // base_off + 0x4b000000*(1 + pitchY + pitchZ) mod 2^32 (see mrt_sample_raw)
 };
 
 // Cameras of a batch of views rendered by ONE launch (blockIdx.y = view): everything else in
@@ -154,7 +155,14 @@ __device__ __forceinline__ IdxRay mrt_index_ray(const KParams& P, const Ray& r) 
 
 // sampleLinear (brats_rt.slang:60-76) on the packed multi-channel layout, then the
 // modality blend (:123-130).  Returns v; also the integer base + fractions if wanted.
-struct Cell { int ix, iy, iz; float fx, fy, fz; };
+// mx/my/mz hold the raw bits of (q + 2^23) rounded toward -inf, i.e. 0x4b000000 + floor(q).
+#define MRT_MAGIC_BITS 0x4b000000u
+struct Cell {
+  uint32_t mx, my, mz; float fx, fy, fz;
+  __device__ __forceinline__ int ix() const { return (int)(mx - MRT_MAGIC_BITS); }
+  __device__ __forceinline__ int iy() const { return (int)(my - MRT_MAGIC_BITS); }
+  __device__ __forceinline__ int iz() const { return (int)(mz - MRT_MAGIC_BITS); }
+};
 
 __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, float pz,
                                          float hix, float hiy, float hiz) {
@@ -162,9 +170,12 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
   const float qx = fminf(fmaxf(px, 0.0f), hix);
   const float qy = fminf(fmaxf(py, 0.0f), hiy);
   const float qz = fminf(fmaxf(pz, 0.0f), hiz);
-  const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
-  c.ix = (int)flx; c.iy = (int)fly; c.iz = (int)flz;
-  c.fx = qx - flx; c.fy = qy - fly; c.fz = qz - flz;
+  // floor of a value in [0, 2^22) without the conversion (XU) pipe: q + 2^23 rounded toward
+  // -inf is exactly 2^23 + floor(q); its low mantissa bits are the integer.  Same result as
+  // floorf / (int), three FADD/IADD instead of F2I + FRND per axis.
+  const float mx = __fadd_rd(qx, 8388608.0f), my = __fadd_rd(qy, 8388608.0f), mz = __fadd_rd(qz, 8388608.0f);
+  c.mx = __float_as_uint(mx); c.my = __float_as_uint(my); c.mz = __float_as_uint(mz);
+  c.fx = qx - (mx - 8388608.0f); c.fy = qy - (my - 8388608.0f); c.fz = qz - (mz - 8388608.0f);
   return c;
 }
 
@@ -174,17 +185,28 @@ template <int NCH>
 __device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
                                                 const Cell& c) {
   typedef typename Vox<NCH>::T VT;
-  const uint32_t sY = P.pitchY;
-  const uint32_t sZ = P.pitchZ;
-  const uint32_t b = (uint32_t)c.ix + (uint32_t)c.iy * sY + (uint32_t)c.iz * sZ - P.base_off;
-  const VT* p0 = vol + b;
-  const VT* p1 = p0 + sY;
-  const VT* p2 = p0 + sZ;
-  const VT* p3 = p2 + sY;
+  // element index straight from the magic-number bits: the three -0x4b000000 corrections and the
+  // shard offset are one precomputed constant (uint32 wrap-around is exact)
+  const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
+  const char* q0 = reinterpret_cast<const char*>(vol) + (size_t)b * sizeof(VT);
+  const VT* p0 = reinterpret_cast<const VT*>(q0);
+  const VT* p1 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchY * sizeof(VT));
+  const VT* p2 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchZ * sizeof(VT));
+  const VT* p3 = reinterpret_cast<const VT*>(q0 + ((size_t)P.pitchY + (size_t)P.pitchZ) * sizeof(VT));
   const VT v000 = __ldg(p0), v100 = __ldg(p0 + 1);
   const VT v010 = __ldg(p1), v110 = __ldg(p1 + 1);
   const VT v001 = __ldg(p2), v101 = __ldg(p2 + 1);
   const VT v011 = __ldg(p3), v111 = __ldg(p3 + 1);
+  if (NCH == 1) {
+    // one modality: the (linear) window scale is applied once, after the interpolation
+    const float* f0 = reinterpret_cast<const float*>(&v000); const float* f1 = reinterpret_cast<const float*>(&v100);
+    const float* f2 = reinterpret_cast<const float*>(&v010); const float* f3 = reinterpret_cast<const float*>(&v110);
+    const float* f4 = reinterpret_cast<const float*>(&v001); const float* f5 = reinterpret_cast<const float*>(&v101);
+    const float* f6 = reinterpret_cast<const float*>(&v011); const float* f7 = reinterpret_cast<const float*>(&v111);
+    const float s = lerpf(lerpf(lerpf(*f0, *f1, c.fx), lerpf(*f2, *f3, c.fx), c.fy),
+                          lerpf(lerpf(*f4, *f5, c.fx), lerpf(*f6, *f7, c.fx), c.fy), c.fz);
+    return fmaf(s, P.wq[0], P.wbias);
+  }
   const float c000 = foldv(v000, P), c100 = foldv(v100, P), c010 = foldv(v010, P), c110 = foldv(v110, P);
   const float c001 = foldv(v001, P), c101 = foldv(v101, P), c011 = foldv(v011, P), c111 = foldv(v111, P);
   const float s = lerpf(lerpf(lerpf(c000, c100, c.fx), lerpf(c010, c110, c.fx), c.fy),
@@ -213,8 +235,13 @@ __device__ __forceinline__ float mrt_window(const KParams& P, float raw) {
 
 // alpha = 1 - exp(-sigma*dt)  (:137) as 1 - 2^(sigma * (-dt*log2 e)): one FMUL + MUFU.EX2.
 // ex2.approx is accurate to 2 ulp of a result in (0,1], i.e. ~1.2e-7 absolute on alpha.
+__device__ __forceinline__ float mrt_ex2(float x) {
+  float y;                                  // x <= 0 here; a denormal result flushes to 0: alpha = 1 either way
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float mrt_alpha(const KParams& P, float sigma) {
-  return 1.0f - exp2f(sigma * P.neg_dt_log2e);
+  return 1.0f - mrt_ex2(sigma * P.neg_dt_log2e);
 }
 
 // Shared-memory LUT: entry j holds tf[j] and the forward difference tf[min(j+1,N-1)] - tf[j],
@@ -230,12 +257,21 @@ __device__ __forceinline__ void mrt_tf_stage(TfEntry* __restrict__ s_tf, const f
   }
 }
 
-__device__ __forceinline__ float4 mrt_tf_lookup(const TfEntry* __restrict__ s_tf, float nm1, float val,
+__device__ __forceinline__ float4 mrt_lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// `s_tf` as a shared-window address (__cvta_generic_to_shared, once per thread): keeps the
+// generic->shared conversion out of the sample loop.
+__device__ __forceinline__ float4 mrt_tf_lookup(uint32_t s_tf, float nm1, float val,
                                                 int* j0o = nullptr, float* fro = nullptr) {
   const float u = val * nm1;                 // val in [0,1] => 0 <= floor(u) <= N-1
-  const int j0 = (int)u;
-  const float fr = u - (float)j0;
-  const float4 a = s_tf[j0].base, d = s_tf[j0].delta;
+  const float mu = __fadd_rd(u, 8388608.0f);  // floor without the conversion pipe (see mrt_cell)
+  const int j0 = __float_as_int(mu) - 0x4b000000;
+  const float fr = u - (mu - 8388608.0f);
+  const uint32_t ea = s_tf + (uint32_t)j0 * (uint32_t)sizeof(TfEntry);
+  const float4 a = mrt_lds128(ea), d = mrt_lds128(ea + 16);
   if (j0o) { *j0o = j0; *fro = fr; }
   return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
 }
