@@ -194,7 +194,13 @@ int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32
  *               the cell's exit.
  *   flat != 0 (levels for the BACKWARD): a cell additionally has to be flat — every voxel in it
  *               holds one and the same value — so that all slots inside share one TF bin and
- *               one dL/dsigma, which mrt_render_backward adds in closed form. */
+ *               one dL/dsigma, which mrt_render_backward adds in closed form.
+ *
+ * `skip_levels` is a buffer of mrt_skip_levels_bytes(X,Y,Z) bytes: uint8[nbricks] followed, 16-byte
+ * aligned, by int32[8] holding the bounding box of the active bricks, which the march uses to cull
+ * rays / CTAs that cannot touch an active brick before any exact ray set-up and to clip every
+ * ray's slot range. */
+size_t mrt_skip_levels_bytes(int32_t X, int32_t Y, int32_t Z);
 int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C,
                         const float* tf, int32_t tfN,
                         const uint8_t* seg_any, const uint8_t* pred_any,
@@ -204,7 +210,8 @@ int mrt_classify_bricks(const MrtParams* params, const float* minmax, int32_t C,
  * Renders tiles [tile_begin, tile_end) of the [H][W] image (tile ids as above).
  *   packed      : packed volume (see mrt_pack_volume_f32), C = logical channel count (1..4)
  *   tf, tfN     : LUT [tfN][4] (r,g,b,sigma) fp32, used when params->tfMode == 1
- *   skip_levels : uint8[nbricks] from mrt_classify_bricks, or NULL (then skipEmpty is ignored)
+ *   skip_levels : the mrt_skip_levels_bytes() buffer filled by mrt_classify_bricks, or NULL (then
+ *                 skipEmpty is ignored)
  *   labels/preds: optional int32 [Z][Y][X] (gLabels / gPreds), used when showSeg / showPred
  *   out_rgba    : float4 [H][W]  (row 0 = top)
  *   out_T       : optional float [H][W], final transmittance

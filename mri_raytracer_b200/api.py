@@ -95,12 +95,21 @@ def build_label_occupancy(labels: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def skip_levels_buffer(P: RenderParams, device) -> torch.Tensor:
+    """uint8 buffer for ``mrt_classify_bricks``: one level byte per brick + the active-brick box tail
+    (``mrt_skip_levels_bytes``); sized for the (sub-)volume the params describe."""
+    if P.shard is not None:
+        X, Y, Z = (int(h) - int(l) + 1 for l, h in zip(P.shard[0], P.shard[1]))
+    else:
+        X, Y, Z = P.dims
+    return torch.empty((lib().mrt_skip_levels_bytes(X, Y, Z),), dtype=torch.uint8, device=device)
+
+
 def classify_bricks(P: RenderParams, minmax: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                     seg_any: Optional[torch.Tensor] = None, pred_any: Optional[torch.Tensor] = None,
                     out: Optional[torch.Tensor] = None, flat: bool = False) -> torch.Tensor:
-    nb = minmax.shape[0]
     if out is None:
-        out = torch.empty((nb,), dtype=torch.uint8, device=minmax.device)
+        out = skip_levels_buffer(P, minmax.device)
     s = P.to_struct()
     check(lib().mrt_classify_bricks(C.byref(s), minmax.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
                                     _ptr(seg_any), _ptr(pred_any), out.data_ptr(), int(flat), _stream()),
@@ -314,9 +323,8 @@ class Volume:
         packed, Cn, Pe = self.prepared(P)
         if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
             return None
-        nb = self.minmax.shape[0]
         if self._bits is None:
-            self._bits = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+            self._bits = skip_levels_buffer(Pe, self.device)
         return classify_bricks(Pe, self.minmax, Cn, tf, self.seg_any, self.pred_any, out=self._bits)
 
     def forward(self, P: RenderParams, tf: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,

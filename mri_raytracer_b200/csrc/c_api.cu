@@ -156,6 +156,10 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   MRT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt,
               "tile range [%d,%d) outside [0,%d]", tile_begin, tile_end, nt);
   K->tile_begin = tile_begin; K->tile_end = tile_end;
+  {  // n*m >> 32 == n/d for m = floor(2^32/d)+1 whenever n*d < 2^32 (d = tiles_x, n = any tile id)
+    const uint64_t d = (uint64_t)mrt_tiles_x_(K->W);
+    K->tdiv_mul = (d > 1 && (uint64_t)nt * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
+  }
   return MRT_OK;
 }
 
@@ -192,6 +196,10 @@ int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C
 int32_t mrt_brick_count(int32_t X, int32_t Y, int32_t Z) {
   if (X < 1 || Y < 1 || Z < 1) return 0;
   return ((X + 7) >> 3) * ((Y + 7) >> 3) * ((Z + 7) >> 3);
+}
+size_t mrt_skip_levels_bytes(int32_t X, int32_t Y, int32_t Z) {
+  const int32_t nb = mrt_brick_count(X, Y, Z);
+  return nb > 0 ? mrt_levels_box_offset((size_t)nb) + 8 * sizeof(int32_t) : 0;
 }
 int mrt_build_occupancy(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream) {
   MRT_REQUIRE(packed && minmax, "build_occupancy: null pointer");
@@ -379,7 +387,7 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
   MRT_CUDA(cudaMallocAsync(&d_out, npix * 4 * sizeof(float), st));
   if (P.skipEmpty && P.tMode == 0) {
     MRT_CUDA(cudaMallocAsync(&d_minmax, (size_t)nb * pc * 2 * sizeof(float), st));
-    MRT_CUDA(cudaMallocAsync(&d_bits, (size_t)nb, st));
+    MRT_CUDA(cudaMallocAsync(&d_bits, mrt_skip_levels_bytes(X, Y, Z), st));
     MRT_CALL(mrt_build_occupancy(d_packed, C, X, Y, Z, d_minmax, st));
     if (useSeg) {
       MRT_CUDA(cudaMallocAsync(&d_seg_any, nb, st));

@@ -33,6 +33,38 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);                        // [tfN]
   float4* s_lab = reinterpret_cast<float4*>(s_tf + (P.tfMode ? P.tfN : 0));  // [0..7] seg, [8..15] pred
 
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
+  const int view = blockIdx.y;                                             // batch of views: one camera each
+  int px = 0, py = 0;
+  if (tile < P.tile_end) mrt_pixel_of_tile_lane_fast(P, tile, mrt_logical_lane(warp & 1, lane), &px, &py);
+  // :89 — pixels outside the image keep their lane alive (the skip loop uses warp votes) with an
+  // empty ray, and never store
+  const bool inside = (tile < P.tile_end) && (px < P.W) && (py < P.H);
+  const size_t pix = ((size_t)view * P.H + py) * P.W + px;
+
+  // Cull against the active-brick box BEFORE any expensive work: a ray that cannot enter it is
+  // pure background.  Whole CTAs of such rays (most of the frame outside the head) skip the LUT
+  // staging and the exact ray set-up; whole warps skip the set-up.
+  bool maybe = inside;
+  ActiveBox abox;
+  if (SKIP) {
+    abox = mrt_active_box(P, levels);
+    if (!GENERIC) {                                                        // the counting variant needs every exact n
+      maybe = inside && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
+      const bool cta_any = __syncthreads_or(maybe);
+      if (!cta_any || !__any_sync(0xffffffffu, maybe)) {
+        if (inside) {
+          out_rgba[pix] = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
+                                  : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
+          if (out_T) out_T[pix] = 1.0f;
+        }
+        if (!cta_any) return;                                              // nobody needs the LUT
+        maybe = false;                                                     // this warp only keeps the barrier company
+      }
+    }
+  }
+
   if (P.tfMode) mrt_tf_stage(s_tf, tf, P.tfN);
   if (LABELS) {
     if (threadIdx.x < 16) {
@@ -43,19 +75,11 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     }
   }
   __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
   if (tile >= P.tile_end) return;
-  int px, py;
-  mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
-  // :89 — pixels outside the image keep their lane alive (the skip loop uses warp votes) with an
-  // empty ray, and never store
-  const bool inside = (px < P.W) && (py < P.H);
+  if (SKIP && !GENERIC) { if (!__any_sync(0xffffffffu, maybe)) return; }   // culled warp (already stored)
 
-  const int view = blockIdx.y;                                             // batch of views: one camera each
   Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
-  if (!inside) ray.n = 0;
+  if (!maybe) ray.n = 0;
   // a sort-last shard renders a partial: premultiplied colour WITHOUT background, alpha = T_local
   float Cr = P.shard ? 0.0f : P.bg[0], Cg = P.shard ? 0.0f : P.bg[1], Cb = P.shard ? 0.0f : P.bg[2];   // :111
   float T = 1.0f;                                                          // :112
@@ -120,6 +144,18 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       const float inv_dt = 1.0f / dt;
       int n = ray.n;
       if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, inv_dt, ray.n, &ks, &n); k = ks; }
+      const int n_full = n;
+      {   // slots outside the ray's interval in the active-brick box are no-ops: clip [k, n) to it
+        float tin, tout;
+        mrt_box_interval(abox, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, &tin, &tout);
+        if (tout >= fmaxf(tin, 0.0f)) {
+          const float a = floorf((tin - ray.t0) * inv_dt) - 1.0f, b = ceilf((tout - ray.t0) * inv_dt) + 1.0f;
+          k = max(k, (int)fminf(fmaxf(a, 0.0f), (float)n));
+          n = min(n, (int)fminf(fmaxf(b, 0.0f), (float)n));
+        } else {
+          n = k;
+        }
+      }
       // Per-lane knowledge of the ray, in slot indices (k <= kact <= kf <= kl):
       //   [k, kact)   current run, inside active bricks: to be shaded
       //   [kact, kf)  known empty (leapt cells / another shard's slots)
@@ -164,12 +200,20 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
           continue;
         }
         if (!wst) break;
-        // phase 2: every live lane of the warp shades one slot
-        if (live) {
-          shade(fmaf((float)k, dt, ray.t0));
-          ++k; if (GENERIC) ++n_eval;
+        // phase 2: every live lane owns a run; the warp shades m = the shortest remaining run
+        // slots back to back (no lane can run dry before that, so nothing has to be re-checked
+        // but the lane's own early termination)
+        const int m = __reduce_min_sync(0xffffffffu, live ? kact - k : 0x7fffffff);
+        bool on = live;
+        for (int i = 0; i < m; ++i) {
+          if (on) {
+            shade(fmaf((float)k, dt, ray.t0));
+            ++k; if (GENERIC) ++n_eval;
+            on = T > thr;
+          }
         }
       }
+      if (T > thr) k = n_full;             // ran to the end: the oracle's n_taken counts the clipped no-op slots too
     } else {
       int n = ray.n;
       if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, 1.0f / dt, ray.n, &ks, &n); k = ks; }
@@ -187,7 +231,6 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     }
   }
   if (!inside) return;
-  const size_t pix = ((size_t)view * P.H + py) * P.W + px;
   out_rgba[pix] = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
   if (out_T) out_T[pix] = T;
   if (GENERIC) { if (out_counts) out_counts[pix] = make_int4(ray.n, k, n_eval, n_seg); }

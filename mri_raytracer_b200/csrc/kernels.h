@@ -45,6 +45,10 @@ struct MrtSlabParams;
 cudaError_t mrt_launch_slab(const MrtSlabParams& P, float tan_half, const uint8_t* vol, float* out,
                             int tile_begin, int tile_end, cudaStream_t st);
 
+// The skip-level buffer is uint8[nbricks] followed (16-byte aligned) by int32[8]: the bounding
+// box of the active bricks in brick units, stored as maxima (-lox, -loy, -loz, hix, hiy, hiz, -, -).
+static inline size_t mrt_levels_box_offset(size_t nbricks) { return (nbricks + 15) & ~(size_t)15; }
+
 static inline int mrt_packed_channels(int C) { return C <= 1 ? 1 : (C == 2 ? 2 : 4); }
 
 // Skewed pitches of the packed layout (see include/mrt.h "volume layout"): with S voxels per

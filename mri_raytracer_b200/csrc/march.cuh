@@ -42,6 +42,7 @@ struct KParams {
   int shard;
   int slo[3], shi[3];
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
+  unsigned tdiv_mul;      // floor(2^32/tiles_x)+1 when tile/tiles_x == umulhi(tile, tdiv_mul) for every tile id, else 0
   unsigned idx_bias;      // base_off + 0x4b000000*(1 + pitchY + pitchZ) mod 2^32 (see mrt_sample_raw)
 };
 
@@ -124,6 +125,66 @@ __device__ __forceinline__ Ray mrt_setup_ray(const KParams& P, const float* __re
   }
   r.n = n;
   return r;
+}
+
+// ---- active-brick box ------------------------------------------------------------------
+// Bounding box of the active bricks (tail of the skip-level buffer, written by the classify
+// kernel) in GLOBAL index space, widened by MRT_BOX_MARGIN voxels.  Every sample slot that can
+// contribute has its position inside it, so (i) a ray whose line never enters the box is
+// background, whatever its exact set-up says, and (ii) slots outside the ray's box interval are
+// no-ops.  The margin (1/4 voxel) is ~300x the worst error of the approximate ray below.
+#define MRT_BOX_MARGIN 0.25f
+struct ActiveBox { float lo[3], hi[3]; };
+__device__ __forceinline__ float mrt_rcp(float x) {        // MUFU.RCP, 1 ulp; rcp(0) = +inf
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ ActiveBox mrt_active_box(const KParams& P, const uint8_t* __restrict__ levels) {
+  const size_t nb = (size_t)P.nbx * P.nby * P.nbz;
+  const int* b = reinterpret_cast<const int*>(levels + ((nb + 15) & ~(size_t)15));
+  ActiveBox A;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int mlo = __ldg(b + a), mhi = __ldg(b + 3 + a);       // (max(-lo), max(hi)) in bricks; INT_MIN-ish = none
+    const bool none = mhi < 0;
+    A.lo[a] = none ? 3.0e38f : (float)(((-mlo) << MRT_BRICK_SHIFT) + P.slo[a]) - MRT_BOX_MARGIN;
+    A.hi[a] = none ? -3.0e38f : (float)(((mhi + 1) << MRT_BRICK_SHIFT) + P.slo[a]) + MRT_BOX_MARGIN;
+  }
+  return A;
+}
+// [tin, tout] of the line o + t*d (index space) inside the box; empty when tout < max(tin, 0)
+__device__ __forceinline__ void mrt_box_interval(const ActiveBox& A, float ox, float oy, float oz,
+                                                 float dx, float dy, float dz, float* tin, float* tout) {
+  const float ix = mrt_rcp(dx), iy = mrt_rcp(dy), iz = mrt_rcp(dz);   // +-inf for a zero component: standard slab rule
+  const float ax = (A.lo[0] - ox) * ix, bx = (A.hi[0] - ox) * ix;
+  const float ay = (A.lo[1] - oy) * iy, by = (A.hi[1] - oy) * iy;
+  const float az = (A.lo[2] - oz) * iz, bz = (A.hi[2] - oz) * iz;
+  *tin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));        // NaN (0*inf) drops out of fmin/fmax: conservative
+  *tout = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+}
+// Cheap conservative test with an APPROXIMATE, un-normalised ray (no IEEE divisions, no sqrt):
+// false only if the pixel's ray certainly misses the active box.
+__device__ __forceinline__ bool mrt_ray_may_hit(const KParams& P, const float* __restrict__ cam, int px, int py,
+                                                const ActiveBox& A) {
+  const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
+  const float uvx = ((float)px + 0.5f) * (2.0f * mrt_rcp((float)P.W)) - 1.0f;
+  const float uvy = ((float)py + 0.5f) * (2.0f * mrt_rcp((float)P.H)) - 1.0f;
+  const float aspect = (float)P.W * mrt_rcp(fmaxf(1.0f, (float)P.H));
+  float ox, oy, oz, dx, dy, dz;
+  if (P.ortho) {
+    const float ax = uvx * aspect * P.halfH, ay = -uvy * P.halfH;
+    ox = eye[0] + ax * U[0] + ay * V[0]; oy = eye[1] + ax * U[1] + ay * V[1]; oz = eye[2] + ax * U[2] + ay * V[2];
+    dx = Wv[0]; dy = Wv[1]; dz = Wv[2];
+  } else {
+    const float inv_f = mrt_rcp(P.focal);
+    const float cx = uvx * aspect * inv_f, cy = -uvy * inv_f;
+    dx = cx * U[0] + cy * V[0] + Wv[0]; dy = cx * U[1] + cy * V[1] + Wv[1]; dz = cx * U[2] + cy * V[2] + Wv[2];
+    ox = eye[0]; oy = eye[1]; oz = eye[2];
+  }
+  const float sx = mrt_rcp(P.vs[0]), sy = mrt_rcp(P.vs[1]), sz = mrt_rcp(P.vs[2]);
+  float tin, tout;
+  mrt_box_interval(A, (ox - P.bmin[0]) * sx, (oy - P.bmin[1]) * sy, (oz - P.bmin[2]) * sz, dx * sx, dy * sy, dz * sz,
+                   &tin, &tout);
+  return tout >= fmaxf(tin, 0.0f);
 }
 
 // ---- voxel vector types -------------------------------------------------------------
@@ -285,6 +346,16 @@ __device__ __forceinline__ float4 mrt_tf_lookup(uint32_t s_tf, float nm1, float 
 __device__ __forceinline__ int mrt_middle_out(int b, int n) {
   const int mid = n >> 1;
   return (b & 1) ? mid - 1 - (b >> 1) : mid + (b >> 1);
+}
+
+// tiles.h mrt_pixel_of_tile_lane_ with the division by tiles_x done as a multiply-high when the
+// host has proven it exact for this image size (KParams::tdiv_mul != 0).
+__device__ __forceinline__ void mrt_pixel_of_tile_lane_fast(const KParams& P, int tile, int lane, int* x, int* y) {
+  const int txn = mrt_tiles_x_(P.W);
+  const int ty = P.tdiv_mul ? (int)__umulhi((unsigned)tile, P.tdiv_mul) : tile / txn;
+  const int tx = tile - ty * txn;
+  *x = (tx << MRT_TILE_SHIFT) + (lane & MRT_TILE_MASK);
+  *y = (ty << MRT_TILE_SHIFT) + (lane >> MRT_TILE_SHIFT);
 }
 
 // Physical lane (0..31) of a warp -> logical lane (0..63) inside the 8x8 tile.  A warp owns an

@@ -8,6 +8,7 @@
 #include "march.cuh"
 #include "kernels.h"
 #include <float.h>
+#include <limits.h>
 
 // ---------------------------------------------------------------- build (once per volume)
 // brick b covers voxel indices [8b, 8b+8] per axis (clipped): the union of the 2x2x2
@@ -154,11 +155,13 @@ template <int NCH, bool FLAT>
 __global__ void __launch_bounds__(512)
 mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict__ minmax,
                     const float4* __restrict__ tf, const uint8_t* __restrict__ seg_any,
-                    const uint8_t* __restrict__ pred_any, uint8_t* __restrict__ levels, int sbx, int sby) {
+                    const uint8_t* __restrict__ pred_any, uint8_t* __restrict__ levels, int* __restrict__ box,
+                    int sbx, int sby) {
   __shared__ uint8_t s_act[512];
   __shared__ uint8_t s_or2[64];
   __shared__ uint8_t s_or4[8];
   __shared__ uint8_t s_or8;
+  __shared__ int s_box[6];
   __shared__ float s_lo[512], s_hi[512], s_lo2[64], s_hi2[64], s_lo4[8], s_hi4[8];
   const int t = threadIdx.x;
   const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
@@ -166,6 +169,7 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
   const int bx = (sx << 3) + lx, by = (sy << 3) + ly, bz = (sz << 3) + lz;
   const bool inside = bx < P.nbx && by < P.nby && bz < P.nbz;
   const int b = (bz * P.nby + by) * P.nbx + bx;
+  if (t < 6) s_box[t] = INT_MIN;
   bool act = inside && mrt_brick_active<NCH>(P, minmax, tf, seg_any, pred_any, b);
   if (FLAT) {
     float lo = 3.0e38f, hi = -3.0e38f;          // out-of-grid bricks are compatible with any value
@@ -181,6 +185,13 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
   }
   s_act[t] = act;
   __syncthreads();
+  // bounding box of the active bricks (brick units), all six as maxima: (-lo, hi).  The march
+  // culls rays / whole CTAs against it before the exact ray set-up and clips every ray's slot
+  // range to it (mrt_active_box).
+  if (act) {
+    atomicMax(&s_box[0], -bx); atomicMax(&s_box[1], -by); atomicMax(&s_box[2], -bz);
+    atomicMax(&s_box[3], bx);  atomicMax(&s_box[4], by);  atomicMax(&s_box[5], bz);
+  }
   if (t < 64) {            // 2x2x2 groups: group (gx,gy,gz) in 4x4x4
     const int gx = t & 3, gy = (t >> 2) & 3, gz = t >> 4;
     int o = 0;
@@ -218,6 +229,7 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
     s_or8 = (uint8_t)o;
   }
   __syncthreads();
+  if (t < 6 && s_box[t] != INT_MIN) atomicMax(box + t, s_box[t]);     // s_box complete: 3 barriers ago
   if (inside) {
     int lvl = 0;
     if (!act) {
@@ -239,7 +251,11 @@ cudaError_t mrt_launch_classify(const KParams& P, const float* minmax, int pc, c
                                 bool require_flat, cudaStream_t st) {
   const int sbx = (P.nbx + 7) >> 3, sby = (P.nby + 7) >> 3, sbz = (P.nbz + 7) >> 3;
   const int grid = sbx * sby * sbz;
-#define MRT_CL(N, F) mrt_classify_kernel<N, F><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, sbx, sby)
+  // tail of the levels buffer (mrt_skip_levels_bytes): the active-brick box, reset to "nothing"
+  int* box = reinterpret_cast<int*>(levels + mrt_levels_box_offset(P.nbx * P.nby * P.nbz));
+  cudaError_t e0 = cudaMemsetAsync(box, 0x80, 8 * sizeof(int), st);
+  if (e0 != cudaSuccess) return e0;
+#define MRT_CL(N, F) mrt_classify_kernel<N, F><<<grid, 512, 0, st>>>(P, (const float2*)minmax, (const float4*)tf, seg_any, pred_any, levels, box, sbx, sby)
   switch (pc) {
     case 1: if (require_flat) MRT_CL(1, true); else MRT_CL(1, false); break;
     case 2: if (require_flat) MRT_CL(2, true); else MRT_CL(2, false); break;
