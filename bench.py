@@ -434,7 +434,7 @@ def run_ours(args):
             "frames_per_sec": (V * world if mode == "views" else V) * args.steps / tot_s,
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": ((V if args.per_view else 1) + 1 + (2 if volume.fold else 0)) * args.steps,
+            "gpu_launches": ((V if args.per_view else 1) + 1 + (1 if volume.fold else 0)) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -174,6 +174,10 @@ int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, i
  * weights change.  mrt_unfold_grad_f32 is the adjoint: dL/dplanar[c] = w_c/wSum * dL/dfolded. */
 int mrt_fold_volume_f32(const MrtParams* params, const float* planar, int32_t C, float* folded, void* stream);
 int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C, float* dplanar, void* stream);
+/* mrt_fold_volume_f32 + mrt_build_occupancy(folded, C=1) fused into one pass over the planar
+ * volume: `minmax` is float2[mrt_brick_count] of the FOLDED field.  Same outputs, bit for bit. */
+int mrt_fold_volume_occupancy_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
+                                  float* minmax, void* stream);
 
 /* ------------------------------------------------ occupancy brick grid
  * (new relative to the reference; must never change the image.)

@@ -204,6 +204,20 @@ def fold_volume(planar: torch.Tensor, P: RenderParams) -> torch.Tensor:
     return folded
 
 
+def fold_volume_occupancy(planar: torch.Tensor, P: RenderParams) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fold + occupancy grid of the folded field in one pass (``mrt_fold_volume_occupancy_f32``):
+    -> (packed C=1 volume, minmax float32 [nbricks,1,2])."""
+    _need_cuda(planar, "volume", torch.float32)
+    Cn, Z, Y, X = planar.shape
+    nbytes = lib().mrt_packed_volume_bytes(1, X, Y, Z)
+    folded = torch.empty((nbytes // 4,), dtype=torch.float32, device=planar.device)   # padding is never read
+    mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=planar.device)
+    s = replace(P, dims=(X, Y, Z), shard=None).to_struct()
+    check(lib().mrt_fold_volume_occupancy_f32(C.byref(s), planar.data_ptr(), Cn, folded.data_ptr(), mm.data_ptr(),
+                                              _stream()), "fold_volume_occupancy")
+    return folded, mm
+
+
 def unfold_grad(dfolded: torch.Tensor, P: RenderParams, Cn: int) -> torch.Tensor:
     X, Y, Z = P.dims
     out = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=dfolded.device)
@@ -277,8 +291,10 @@ class Volume:
             return self.packed, self.C, P
         key = _fold_key(P, self.C)
         if key != self._key:
-            self.packed = fold_volume(self.planar, P)
-            self.minmax = build_occupancy(self.packed, 1, self.dims) if self.occupancy else None
+            if self.occupancy:
+                self.packed, self.minmax = fold_volume_occupancy(self.planar, P)
+            else:
+                self.packed, self.minmax = fold_volume(self.planar, P), None
             self._key = key
         return self.packed, 1, folded_params(P)
 
@@ -356,13 +372,18 @@ class _RenderFn(torch.autograd.Function):
     def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold):
         Cn = planar.shape[0]
         fold = bool(fold) and Cn > 1
-        if fold:
+        want_occ = bool(P.skipEmpty) and P.tMode == "indexed"
+        mm = None
+        if fold and want_occ:
+            (packed, mm), Ce, Pe = fold_volume_occupancy(planar.detach(), P), 1, folded_params(P)
+        elif fold:
             packed, Ce, Pe = fold_volume(planar.detach(), P), 1, folded_params(P)
         else:
             packed, Ce, Pe = pack_volume(planar.detach()), Cn, P
-        bits = mm = flat = None
-        if P.skipEmpty and P.tMode == "indexed":
-            mm = build_occupancy(packed, Ce, P.dims)
+        bits = flat = None
+        if want_occ:
+            if mm is None:
+                mm = build_occupancy(packed, Ce, P.dims)
             seg_any = build_label_occupancy(labels) if (labels is not None and P.showSeg) else None
             pred_any = build_label_occupancy(preds) if (preds is not None and P.showPred) else None
             bits = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any)

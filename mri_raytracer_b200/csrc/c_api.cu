@@ -182,6 +182,16 @@ int mrt_fold_volume_f32(const MrtParams* params, const float* planar, int32_t C,
   cudaError_t e = mrt_launch_fold(planar, C, X, Y, Z, wgt, inv_wsum, folded, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fold_volume");
 }
+int mrt_fold_volume_occupancy_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
+                                  float* minmax, void* stream) {
+  MRT_REQUIRE(params && planar && folded && minmax, "fold_volume_occupancy: null pointer");
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("fold_volume_occupancy", C, X, Y, Z)) return r;
+  float wgt[4], inv_wsum;
+  blend_weights(params, C, wgt, &inv_wsum);
+  cudaError_t e = mrt_launch_fold_occ(planar, C, X, Y, Z, wgt, inv_wsum, folded, minmax, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fold_volume_occupancy");
+}
 int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C, float* dplanar, void* stream) {
   MRT_REQUIRE(params && dfolded && dplanar, "unfold_grad: null pointer");
   const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];

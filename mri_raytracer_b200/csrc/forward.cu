@@ -13,6 +13,9 @@
 #include "march.cuh"
 #include "kernels.h"
 
+#ifndef MRT_RUN_MIN
+#define MRT_RUN_MIN 1           // slots of known-active run a lane likes to keep ahead of itself
+#endif
 #ifndef MRT_FWD_TPB
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
 #endif
@@ -173,7 +176,10 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         // look-up code runs once per ~brick length instead of once per shaded slot.
         // one warp reduction answers both questions: bit 0 = some lane is live, bit 1 = some live
         // lane has nothing to shade
-        const unsigned wst = __reduce_or_sync(0xffffffffu, (live ? 1u : 0u) | ((live && k >= kact) ? 2u : 0u));
+        // (a lane also asks for a look-up when its run is short and directly extensible, so that
+        // the warp-uniform runs of phase 2 stay long)
+        const bool want = live && kl < n && (k >= kact || (kl == kact && kact - k < MRT_RUN_MIN));
+        const unsigned wst = __reduce_or_sync(0xffffffffu, (live ? 1u : 0u) | (want ? 2u : 0u));
         if (wst & 2u) {
           if (live && kl < n) {
             const float t = fmaf((float)kl, dt, ray.t0);
@@ -193,8 +199,10 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
               if (P.shard && !lvl) kend = min(kend, kl + mrt_shard_slots(P, q, ivx, ivy, ivz, t, inv_dt));
               if (GENERIC) ++n_seg;
             }
-            if (!lvl) kl = kend;                           // active: start / extend the look-ahead run
-            else if (kl == kf) kf = kl = kend;             // empty, directly behind the gap: widen the gap
+            if (!lvl) {
+              if (kl == kact) kact = kf = kl = kend;       // active, directly behind the current run: extend it
+              else kl = kend;                              // active behind a gap: start / extend the look-ahead run
+            } else if (kl == kf) kf = kl = kend;           // empty, directly behind the gap: widen the gap
             // (an empty cell behind a look-ahead run cannot be recorded yet: looked up again later)
           }
           continue;

@@ -1,6 +1,7 @@
 // misc.cu — layout, ingest, tile-map, compositing and roofline-probe kernels.
 #include "march.cuh"
 #include "kernels.h"
+#include <float.h>
 
 // ------------------------------------------------------------------ pack / unpack
 // planar [C][Z][Y][X] (reference flatten, inr/viewer/brats_viewer.py:64) <-> interleaved.
@@ -94,6 +95,77 @@ mrt_fold_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, si
       folded[dst + x] = v * inv_wsum;
     }
   }
+}
+// Fold + occupancy in ONE pass over the planar volume.  A CTA owns the bricks (bx = chunk.., by, bz):
+// it streams the 9 x 9 scanlines y in [8by, 8by+8], z in [8bz, 8bz+8] (the bricks' footprint incl.
+// the +1 halo), thread = x column, blends the modalities, stores the 8 x 8 scanlines it owns in
+// the packed C=1 layout, keeps a running (min, max) per column and finally reduces 9 columns per
+// brick.  The halo rows are read twice (81/64), mostly from L2; the separate min/max pass over
+// the folded volume (and its 1.42x re-read) disappears.
+#define MRT_FOLD_COLS 248          // 31 bricks of 8 columns (+1 halo column) per 256-thread CTA
+template <int C>
+__global__ void __launch_bounds__(256)
+mrt_fold_occ_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                    float w0, float w1, float w2, float w3, float inv_wsum, int nbx, int nby,
+                    float* __restrict__ folded, float2* __restrict__ minmax) {
+  __shared__ float s_mn[256], s_mx[256];
+  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const int chunk = blockIdx.x % chunks, by = (blockIdx.x / chunks) % nby, bz = blockIdx.x / (chunks * nby);
+  const int x0 = chunk * MRT_FOLD_COLS;
+  const int x = x0 + threadIdx.x;
+  // columns [x0, x0+248] are read (the last one only as the halo of brick 30); [x0, x0+247] are stored
+  const bool rd = (threadIdx.x <= MRT_FOLD_COLS) && (x < X);
+  const bool wr = rd && (threadIdx.x < MRT_FOLD_COLS);
+  const size_t nvox = (size_t)X * Y * Z;
+  const int y0 = by << 3, z0 = bz << 3;
+  const int ny = min(9, Y - y0), nz = min(9, Z - z0);
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  if (rd) {
+    for (int lz = 0; lz < nz; ++lz) {
+      const int z = z0 + lz;
+#pragma unroll 3
+      for (int ly = 0; ly < ny; ++ly) {
+        const int y = y0 + ly;
+        const size_t src = ((size_t)z * Y + y) * X + x;
+        float v = __ldg(planar + src) * w0;
+        if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
+        if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
+        if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
+        v *= inv_wsum;
+        if (wr && ly < 8 && lz < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+      }
+    }
+  }
+  s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
+  __syncthreads();
+  const int bxl = threadIdx.x;                       // local brick
+  const int bx = chunk * (MRT_FOLD_COLS >> 3) + bxl;
+  if (bxl < (MRT_FOLD_COLS >> 3) && bx < nbx) {
+    float a = FLT_MAX, b = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i <= 8; ++i) { a = fminf(a, s_mn[(bxl << 3) + i]); b = fmaxf(b, s_mx[(bxl << 3) + i]); }
+    minmax[((size_t)bz * nby + by) * nbx + bx] = make_float2(a, b);
+  }
+}
+cudaError_t mrt_launch_fold_occ(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                                float* folded, float* minmax, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout(1, X, Y, Z, &pY, &pZ);
+  const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
+  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const long long grid = (long long)chunks * nby * nbz;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+#define MRT_FO(CC) mrt_fold_occ_kernel<CC><<<(int)grid, 256, 0, st>>>(planar, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, nbx, nby, folded, (float2*)minmax)
+  switch (C) {
+    case 1: MRT_FO(1); break;
+    case 2: MRT_FO(2); break;
+    case 3: MRT_FO(3); break;
+    case 4: MRT_FO(4); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef MRT_FO
+  return cudaGetLastError();
 }
 // adjoint of the fold: dL/dplanar[c] = (w_c / wSum) * dL/dfolded
 __global__ void __launch_bounds__(256)

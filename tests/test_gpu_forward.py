@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from mri_raytracer_b200 import api
+from mri_raytracer_b200 import api, RenderParams
 from mri_raytracer_b200.synth import ramp_tf
 from scenes import small_scene
 from parity import check_forward, O
@@ -137,6 +137,28 @@ def test_batched_views_equal_single_frames(cuda, ortho):
     assert torch.equal(out, batch[:3])
     with pytest.raises(ValueError):
         api.render_views(V, [cams[0], replace(cams[1], fovY=0.5)], tf, P)
+
+
+@pytest.mark.parametrize("C,dims", [(4, (250, 37, 21)), (3, (40, 33, 17)), (2, (8, 8, 8)), (1, (505, 10, 9))])
+def test_fused_fold_occupancy_equals_two_pass(cuda, C, dims):
+    """mrt_fold_volume_occupancy_f32 == mrt_fold_volume_f32 + mrt_build_occupancy, bit for bit
+    (ragged dims, more than one 248-column chunk, every channel count)."""
+    X, Y, Z = dims
+    g = torch.Generator().manual_seed(C)
+    vol = (torch.rand((C, Z, Y, X), generator=g) - 0.3).cuda()
+    P = RenderParams(imageSize=(8, 8), dims=dims, volWeight=(1.0, -0.5, 2.0, 0.75), volEnabled=(1, 1, 0 if C == 4 else 1, 1))
+    folded_a = api.fold_volume(vol, P)
+    mm_a = api.build_occupancy(folded_a, 1, dims)
+    folded_b, mm_b = api.fold_volume_occupancy(vol, P)
+    assert torch.equal(api.unpack_volume(folded_a, 1, dims), api.unpack_volume(folded_b, 1, dims))
+    assert torch.equal(mm_a, mm_b)
+    # independent check of the brick ranges: brick b covers voxels [8b, 8b+8] per axis
+    f = api.unpack_volume(folded_b, 1, dims)[0].cpu()
+    nbx, nby = (X + 7) // 8, (Y + 7) // 8
+    for b in (0, mm_b.shape[0] // 2, mm_b.shape[0] - 1):
+        bx, by, bz = b % nbx, (b // nbx) % nby, b // (nbx * nby)
+        blk = f[8 * bz:8 * bz + 9, 8 * by:8 * by + 9, 8 * bx:8 * bx + 9]
+        assert float(mm_b[b, 0, 0]) == float(blk.min()) and float(mm_b[b, 0, 1]) == float(blk.max())
 
 
 def test_refold_when_weights_change(cuda):
