@@ -96,7 +96,8 @@ typedef struct MrtParams {
    * exactly the slots whose trilinear base index lies in the cell range [shardLo, shardHi).
    * Output is the partial (r,g,b premultiplied WITHOUT background, a = T_local) for
    * mrt_composite_over.  Early termination acts on the shard-local transmittance. */
-  uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3]; uint32_t padShard;
+  uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3];
+  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16 single-channel (mrt_pack_volume_f16), forward only */
 } MrtParams;
 
 /* One camera of a batch of views: the four camera rows of `struct Params`
@@ -163,6 +164,16 @@ int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, in
 /* Inverse (used for dL/dvolume): packed -> planar [C][Z][Y][X]. */
 int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z,
                           float* planar, void* stream);
+
+/* fp16 storage (BASELINE config 5: 2048^3 fp16, brick-sharded): single-channel planar
+ * [Z][Y][X] half <-> packed half, same skew rule with 64 voxels per 128-byte line.  Render it
+ * with C = 1 and params->volDtype = 1; the sampler widens each corner to fp32 and interpolates
+ * in fp32 (results equal the fp32 path on the fp16-rounded values).  Forward only. */
+size_t mrt_packed_volume_bytes_f16(int32_t X, int32_t Y, int32_t Z);
+void mrt_packed_layout_f16(int32_t X, int32_t Y, int32_t Z, int64_t* pitchY, int64_t* pitchZ);
+int mrt_pack_volume_f16(const void* planar_f16, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream);
+int mrt_unpack_volume_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, void* planar_f16, void* stream);
+int mrt_build_occupancy_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream);
 
 /* ------------------------------------------------ modality fold
  * The modality blend v = sum_c w_c s_c / wSum (brats_rt.slang:123-130) is linear and commutes

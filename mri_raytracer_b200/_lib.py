@@ -39,7 +39,7 @@ class MrtParams(C.Structure):
         ("ortho", C.c_uint32), ("orthoHalfHeight", C.c_float), ("ertThreshold", C.c_float),
         ("maxSteps", C.c_uint32),
         ("tMode", C.c_uint32), ("alphaMode", C.c_uint32), ("skipEmpty", C.c_uint32), ("tfMode", C.c_uint32),
-        ("shardEnabled", C.c_uint32), ("shardLo", C.c_uint32 * 3), ("shardHi", C.c_uint32 * 3), ("padShard", C.c_uint32),
+        ("shardEnabled", C.c_uint32), ("shardLo", C.c_uint32 * 3), ("shardHi", C.c_uint32 * 3), ("volDtype", C.c_uint32),
     ]
 
 
@@ -86,6 +86,11 @@ PROTOTYPES = {
     "mrt_packed_volume_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mrt_pack_volume_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mrt_unpack_volume_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mrt_packed_volume_bytes_f16": (_sz, [_i32, _i32, _i32]),
+    "mrt_packed_layout_f16": (None, [_i32, _i32, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mrt_pack_volume_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "mrt_unpack_volume_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "mrt_build_occupancy_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_fold_volume_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
     "mrt_fold_volume_occupancy_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp, _vp]),
     "mrt_unfold_grad_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),

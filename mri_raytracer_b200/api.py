@@ -69,6 +69,30 @@ def pack_volume(planar: torch.Tensor) -> torch.Tensor:
     return packed
 
 
+def pack_volume_f16(planar: torch.Tensor) -> torch.Tensor:
+    """[1,Z,Y,X] (or [Z,Y,X]) fp16 -> packed fp16 buffer (``mrt_pack_volume_f16``)."""
+    _need_cuda(planar, "volume", torch.float16)
+    Z, Y, X = planar.shape[-3:]
+    nbytes = lib().mrt_packed_volume_bytes_f16(X, Y, Z)
+    packed = torch.empty((nbytes // 2,), dtype=torch.float16, device=planar.device)
+    check(lib().mrt_pack_volume_f16(planar.data_ptr(), X, Y, Z, packed.data_ptr(), _stream()), "pack_volume_f16")
+    return packed
+
+
+def unpack_volume_f16(packed: torch.Tensor, dims) -> torch.Tensor:
+    X, Y, Z = dims
+    planar = torch.empty((1, Z, Y, X), dtype=torch.float16, device=packed.device)
+    check(lib().mrt_unpack_volume_f16(packed.data_ptr(), X, Y, Z, planar.data_ptr(), _stream()), "unpack_volume_f16")
+    return planar
+
+
+def build_occupancy_f16(packed: torch.Tensor, dims) -> torch.Tensor:
+    X, Y, Z = dims
+    mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=packed.device)
+    check(lib().mrt_build_occupancy_f16(packed.data_ptr(), X, Y, Z, mm.data_ptr(), _stream()), "build_occupancy_f16")
+    return mm
+
+
 def unpack_volume(packed: torch.Tensor, Cn: int, dims) -> torch.Tensor:
     X, Y, Z = dims
     planar = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=packed.device)
@@ -251,10 +275,13 @@ class Volume:
                  fold: bool = True, shard=None, global_dims=None):
         """``shard=((lox,loy,loz),(hix,hiy,hiz))`` + ``global_dims``: ``planar`` holds only voxels
         [lo, hi] (inclusive) of a larger volume — a sort-last sub-box (dist.render_sort_last)."""
-        _need_cuda(planar, "volume", torch.float32)
+        self.half = isinstance(planar, torch.Tensor) and planar.dtype == torch.float16
+        _need_cuda(planar, "volume", torch.float16 if self.half else torch.float32)
         if planar.dim() != 4 or not (1 <= planar.shape[0] <= 4):
             raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(planar.shape)}")
         self.C = int(planar.shape[0])
+        if self.half and (self.C != 1 or labels is not None or preds is not None):
+            raise ValueError("fp16 volumes are single-channel and take no label overlays")
         Z, Y, X = (int(v) for v in planar.shape[1:])
         self.dims = (X, Y, Z)
         self.shard = None
@@ -273,6 +300,9 @@ class Volume:
         self._key = None
         if self.fold:
             self.packed = self.minmax = None
+        elif self.half:
+            self.packed = pack_volume_f16(planar)
+            self.minmax = build_occupancy_f16(self.packed, self.dims) if occupancy else None
         else:
             self.packed = pack_volume(planar)
             self.minmax = build_occupancy(self.packed, self.C, self.dims) if occupancy else None
@@ -287,6 +317,8 @@ class Volume:
         """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
         if self.shard is not None:
             P = replace(P, shard=self.shard)
+        if self.half:
+            P = replace(P, volDtype=1)
         if not self.fold:
             return self.packed, self.C, P
         key = _fold_key(P, self.C)

@@ -74,6 +74,40 @@ int mrt_pack_volume_f32(const float* planar, int32_t C, int32_t X, int32_t Y, in
   cudaError_t e = mrt_launch_pack(planar, C, X, Y, Z, packed, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume");
 }
+size_t mrt_packed_volume_bytes_f16(int32_t X, int32_t Y, int32_t Z) {
+  if (X < 1 || Y < 1 || Z < 1) return 0;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
+  return ((size_t)pZ * Z * 2 + 15) & ~(size_t)15;
+}
+void mrt_packed_layout_f16(int32_t X, int32_t Y, int32_t Z, int64_t* pitchY, int64_t* pitchZ) {
+  mrt_layout_e(1, 2, X, Y, Z, pitchY, pitchZ);
+}
+static int check_dims_f16(const char* who, int X, int Y, int Z) {
+  MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
+  int64_t pY, pZ;
+  mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
+  MRT_REQUIRE((uint64_t)pZ * Z < (1ull << 32), "%s: more than 2^32 voxels per shard (SURVEY Q14)", who);
+  return MRT_OK;
+}
+int mrt_pack_volume_f16(const void* planar_f16, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream) {
+  MRT_REQUIRE(planar_f16 && packed, "pack_volume_f16: null pointer");
+  if (int r = check_dims_f16("pack_volume_f16", X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_pack_f16(planar_f16, X, Y, Z, packed, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume_f16");
+}
+int mrt_unpack_volume_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, void* planar_f16, void* stream) {
+  MRT_REQUIRE(planar_f16 && packed, "unpack_volume_f16: null pointer");
+  if (int r = check_dims_f16("unpack_volume_f16", X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_unpack_f16(packed, X, Y, Z, planar_f16, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "unpack_volume_f16");
+}
+int mrt_build_occupancy_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream) {
+  MRT_REQUIRE(packed && minmax, "build_occupancy_f16: null pointer");
+  if (int r = check_dims_f16("build_occupancy_f16", X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_build_occupancy_f16(packed, X, Y, Z, minmax, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_occupancy_f16");
+}
 int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z, float* planar, void* stream) {
   MRT_REQUIRE(planar && packed, "unpack_volume: null pointer");
   if (int r = check_dims("unpack_volume", C, X, Y, Z)) return r;
@@ -93,7 +127,9 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     K->bg[i] = M->bgColor[i];
     MRT_REQUIRE(M->voxelSize[i] > 0.0f, "voxelSize[%d] must be > 0", i);
   }
-  if (int r = check_dims("render", C, K->dims[0], K->dims[1], K->dims[2])) return r;
+  MRT_REQUIRE(C >= 1 && C <= 4, "render: C=%d outside 1..4", C);
+  MRT_REQUIRE(K->dims[0] >= 2 && K->dims[1] >= 2 && K->dims[2] >= 2, "render: dims (%d,%d,%d) must be >= 2 per axis",
+              K->dims[0], K->dims[1], K->dims[2]);
   int ldim[3] = {K->dims[0], K->dims[1], K->dims[2]};       // dims of the buffer actually sampled
   if (M->shardEnabled) {
     K->shard = 1;
@@ -107,9 +143,16 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on sharded volumes");
     MRT_REQUIRE(M->tMode == 0, "sharded volumes need indexed stepping (tMode 0)");
   }
+  MRT_REQUIRE(M->volDtype <= 1, "volDtype %u unknown (0 fp32, 1 fp16)", M->volDtype);
+  K->half = M->volDtype == 1;
+  if (K->half) {
+    MRT_REQUIRE(C == 1, "fp16 volumes are single-channel (C=%d)", C);
+    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on fp16 volumes");
+  }
   {
     int64_t pY, pZ;
-    mrt_layout(mrt_packed_channels(C), ldim[0], ldim[1], ldim[2], &pY, &pZ);
+    mrt_layout_e(mrt_packed_channels(C), K->half ? 2 : 4, ldim[0], ldim[1], ldim[2], &pY, &pZ);
+    MRT_REQUIRE((uint64_t)pZ * ldim[2] < (1ull << 32), "more than 2^32 voxels per shard (SURVEY Q14)");
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
     K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;
     K->idx_bias = K->base_off + 0x4b000000u * (1u + K->pitchY + K->pitchZ);
@@ -294,6 +337,7 @@ int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, 
   MRT_REQUIRE(!dL_dtf || scratch, "render_backward: dL_dtf needs the scratch buffer");
   KParams K;
   if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
+  if (K.half) return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 volumes are forward-only");
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
   if (K.showSeg && !labels) K.showSeg = 0;
   if (K.showPred && !preds) K.showPred = 0;

@@ -20,11 +20,11 @@
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
 #endif
 
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF>
 __global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 1024) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
-               const typename Vox<NCH>::T* __restrict__ vol,
+               const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                const float4* __restrict__ tf,
                const uint8_t* __restrict__ levels,
                const int32_t* __restrict__ labels,
@@ -100,7 +100,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     auto shade = [&](float t) {
       const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
       const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-      const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH>(P, vol, c));
+      const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH, HALF>(P, vol, c));
       if (P.tfMode) {
         const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val);
         const float alpha = mrt_alpha(P, rgba.w);
@@ -245,7 +245,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
 }
 
 // ------------------------------------------------------------------------- dispatch
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false>
 static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st) {
@@ -253,8 +253,8 @@ static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, c
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
   const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
-  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
-      P, B, (const typename Vox<NCH>::T*)vol, (const float4*)tf, levels, labels, preds,
+  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
+      P, B, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
 }
@@ -302,6 +302,13 @@ cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, 
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && levels != nullptr && P.tMode == 0;
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
+  if (P.half) {            // fp16 voxels: single channel, no label overlays (c_api.cu checks)
+    if (packed_ch != 1 || lab) return cudaErrorInvalidValue;
+    if (skip) return gen ? launch_fwd<1, false, true, true, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
+                         : launch_fwd<1, false, true, false, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    return gen ? launch_fwd<1, false, false, true, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
+               : launch_fwd<1, false, false, false, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+  }
   switch (packed_ch) {
     case 1: return dispatch_fwd<1>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
     case 2: return dispatch_fwd<2>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);

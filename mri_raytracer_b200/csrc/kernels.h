@@ -17,6 +17,9 @@ cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol
                                 void* dvol, float* dtf, void* scratch, cudaStream_t st);
 size_t mrt_bwd_scratch_bytes(int ntf);
 
+cudaError_t mrt_launch_pack_f16(const void* planar_f16, int X, int Y, int Z, void* packed, cudaStream_t st);
+cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar_f16, cudaStream_t st);
+cudaError_t mrt_launch_build_occupancy_f16(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
 
@@ -57,12 +60,16 @@ static inline int mrt_packed_channels(int C) { return C <= 1 ? 1 : (C == 2 ? 2 :
 // 128-byte line, pitchY = S/4 and pitchZ = S/2 (mod S) put the cells of a small 3-D
 // neighbourhood into distinct L1 data banks, so a warp's gather is not serialised by bank
 // conflicts between rows/slices (row pitches that are multiples of 128 B alias every row).
-static inline void mrt_layout(int packed_ch, int X, int Y, int Z, int64_t* pitchY, int64_t* pitchZ) {
-  const int64_t S = 32 / packed_ch;
+// `elem_bytes` = 4 (fp32 voxels) or 2 (fp16, single channel).
+static inline void mrt_layout_e(int packed_ch, int elem_bytes, int X, int Y, int Z, int64_t* pitchY, int64_t* pitchZ) {
+  const int64_t S = 128 / (packed_ch * elem_bytes);
   int64_t py = X;
   while (py % S != S / 4) ++py;
   int64_t pz = py * Y;
   while (pz % S != S / 2) ++pz;
   (void)Z;
   *pitchY = py; *pitchZ = pz;
+}
+static inline void mrt_layout(int packed_ch, int X, int Y, int Z, int64_t* pitchY, int64_t* pitchZ) {
+  mrt_layout_e(packed_ch, 4, X, Y, Z, pitchY, pitchZ);
 }

@@ -7,6 +7,7 @@
 // allowed to contract (tolerance 1e-4, see tests/).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "tiles.h"
 
@@ -39,6 +40,7 @@ struct KParams {
   int tile_begin, tile_end;
   // sort-last shard (all zero when off): owned cell range [slo, shi) in GLOBAL voxel indices;
   // the packed buffer / brick grid / pitches are those of the sub-volume starting at slo.
+  int half;               // voxels are fp16 (single channel): the sampler widens them to fp32 on load
   int shard;
   int slo[3], shi[3];
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
@@ -192,6 +194,9 @@ template <int NCH> struct Vox;
 template <> struct Vox<1> { typedef float T; };
 template <> struct Vox<2> { typedef float2 T; };
 template <> struct Vox<4> { typedef float4 T; };
+// element type the sampler loads: Vox<NCH> in fp32, __half for the single-channel fp16 layout
+template <int NCH, bool HALF> struct VoxT { typedef typename Vox<NCH>::T T; };
+template <> struct VoxT<1, true> { typedef __half T; };
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
@@ -200,6 +205,14 @@ __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(
 // ones):  sum_c wq[c]*s_c  with  wq[c] = volWeight[c]/wSum/ww  (0 for disabled channels).
 // The constant -(wl - ww/2)/ww is added once after interpolation (weights sum to 1).
 __device__ __forceinline__ float foldv(float s, const KParams& P) { return s * P.wq[0]; }
+__device__ __forceinline__ float mrt_f32(float v) { return v; }
+__device__ __forceinline__ float2 mrt_f32(float2 v) { return v; }
+__device__ __forceinline__ float4 mrt_f32(float4 v) { return v; }
+__device__ __forceinline__ float mrt_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float mrt_scalar(float v) { return v; }
+__device__ __forceinline__ float mrt_scalar(__half v) { return __half2float(v); }
+__device__ __forceinline__ float mrt_scalar(float2 v) { return v.x; }   // never used (NCH == 1 only)
+__device__ __forceinline__ float mrt_scalar(float4 v) { return v.x; }
 __device__ __forceinline__ float foldv(float2 s, const KParams& P) { return fmaf(s.y, P.wq[1], s.x * P.wq[0]); }
 __device__ __forceinline__ float foldv(float4 s, const KParams& P) {
   return fmaf(s.w, P.wq[3], fmaf(s.z, P.wq[2], fmaf(s.y, P.wq[1], s.x * P.wq[0])));
@@ -242,10 +255,10 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
 
 // sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
-template <int NCH>
-__device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename Vox<NCH>::T* __restrict__ vol,
+template <int NCH, bool HALF = false>
+__device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                                                 const Cell& c) {
-  typedef typename Vox<NCH>::T VT;
+  typedef typename VoxT<NCH, HALF>::T VT;
   // element index straight from the magic-number bits: the three -0x4b000000 corrections and the
   // shard offset are one precomputed constant (uint32 wrap-around is exact)
   const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
@@ -260,19 +273,18 @@ __device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename
   const VT v011 = __ldg(p3), v111 = __ldg(p3 + 1);
   if (NCH == 1) {
     // one modality: the (linear) window scale is applied once, after the interpolation
-    const float* f0 = reinterpret_cast<const float*>(&v000); const float* f1 = reinterpret_cast<const float*>(&v100);
-    const float* f2 = reinterpret_cast<const float*>(&v010); const float* f3 = reinterpret_cast<const float*>(&v110);
-    const float* f4 = reinterpret_cast<const float*>(&v001); const float* f5 = reinterpret_cast<const float*>(&v101);
-    const float* f6 = reinterpret_cast<const float*>(&v011); const float* f7 = reinterpret_cast<const float*>(&v111);
-    const float s = lerpf(lerpf(lerpf(*f0, *f1, c.fx), lerpf(*f2, *f3, c.fx), c.fy),
-                          lerpf(lerpf(*f4, *f5, c.fx), lerpf(*f6, *f7, c.fx), c.fy), c.fz);
+    const float f0 = mrt_scalar(v000), f1 = mrt_scalar(v100), f2 = mrt_scalar(v010), f3 = mrt_scalar(v110);
+    const float f4 = mrt_scalar(v001), f5 = mrt_scalar(v101), f6 = mrt_scalar(v011), f7 = mrt_scalar(v111);
+    const float s = lerpf(lerpf(lerpf(f0, f1, c.fx), lerpf(f2, f3, c.fx), c.fy),
+                          lerpf(lerpf(f4, f5, c.fx), lerpf(f6, f7, c.fx), c.fy), c.fz);
     return fmaf(s, P.wq[0], P.wbias);
+  } else {
+    const float c000 = foldv(mrt_f32(v000), P), c100 = foldv(mrt_f32(v100), P), c010 = foldv(mrt_f32(v010), P), c110 = foldv(mrt_f32(v110), P);
+    const float c001 = foldv(mrt_f32(v001), P), c101 = foldv(mrt_f32(v101), P), c011 = foldv(mrt_f32(v011), P), c111 = foldv(mrt_f32(v111), P);
+    const float s = lerpf(lerpf(lerpf(c000, c100, c.fx), lerpf(c010, c110, c.fx), c.fy),
+                          lerpf(lerpf(c001, c101, c.fx), lerpf(c011, c111, c.fx), c.fy), c.fz);
+    return s + P.wbias;
   }
-  const float c000 = foldv(v000, P), c100 = foldv(v100, P), c010 = foldv(v010, P), c110 = foldv(v110, P);
-  const float c001 = foldv(v001, P), c101 = foldv(v101, P), c011 = foldv(v011, P), c111 = foldv(v111, P);
-  const float s = lerpf(lerpf(lerpf(c000, c100, c.fx), lerpf(c010, c110, c.fx), c.fy),
-                        lerpf(lerpf(c001, c101, c.fx), lerpf(c011, c111, c.fx), c.fy), c.fz);
-  return s + P.wbias;
 }
 
 // sampleLabel (brats_rt.slang:78-83): round half away from zero.

@@ -44,6 +44,22 @@ mrt_unpack_kernel(const typename Vox<PC>::T* __restrict__ packed, int C, int X, 
   }
 }
 
+// fp16 single-channel volume: planar [Z][Y][X] half <-> packed half with the skewed pitches of
+// mrt_layout_e(1, 2, ...) (64 voxels per 128-byte line)
+__global__ void __launch_bounds__(256)
+mrt_pack_f16_kernel(const __half* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                    __half* __restrict__ packed, bool inverse) {
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const size_t a = (size_t)row * X, b = (size_t)y * pitchY + (size_t)z * pitchZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      if (inverse) const_cast<__half*>(planar)[a + x] = packed[b + x];
+      else packed[b + x] = planar[a + x];
+    }
+  }
+}
+
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   const size_t cap = 148 * 16;          // a few CTAs per SM, grid-stride beyond that
@@ -59,6 +75,21 @@ cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, voi
   if (pc == 1) mrt_pack_kernel<1><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float*)packed);
   else if (pc == 2) mrt_pack_kernel<2><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float2*)packed);
   else mrt_pack_kernel<4><<<g, blk, 0, st>>>(planar, C, X, Y, Z, pY, pZ, (float4*)packed);
+  return cudaGetLastError();
+}
+
+cudaError_t mrt_launch_pack_f16(const void* planar, int X, int Y, int Z, void* packed, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
+  mrt_pack_f16_kernel<<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
+                                                                         (__half*)packed, false);
+  return cudaGetLastError();
+}
+cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
+  mrt_pack_f16_kernel<<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
+                                                                         (__half*)const_cast<void*>(packed), true);
   return cudaGetLastError();
 }
 

@@ -71,6 +71,7 @@ class RenderParams:
     skipEmpty: int = 1
     tfMode: int = 0             # set by render(): 1 when a LUT tensor is passed
     shard: object = None        # ((lox,loy,loz), (hix,hiy,hiz)) voxel range of a sort-last sub-box, or None
+    volDtype: int = 0           # 0 fp32 voxels, 1 fp16 single-channel (set by api.Volume)
 
     def validate(self):
         W, H = self.imageSize
@@ -122,6 +123,7 @@ class RenderParams:
         s.alphaMode = int(bool(self.alphaMode))
         s.skipEmpty = int(bool(self.skipEmpty))
         s.tfMode = int(bool(self.tfMode))
+        s.volDtype = int(self.volDtype)
         if self.shard is not None:
             lo, hi = self.shard
             s.shardEnabled = 1

@@ -161,6 +161,33 @@ def test_fused_fold_occupancy_equals_two_pass(cuda, C, dims):
         assert float(mm_b[b, 0, 0]) == float(blk.min()) and float(mm_b[b, 0, 1]) == float(blk.max())
 
 
+@pytest.mark.parametrize("ortho,use_tf", [(False, True), (True, False)])
+def test_fp16_volume_matches_oracle_on_rounded_values(cuda, ortho, use_tf):
+    """fp16 storage (BASELINE config 5): corners are widened to fp32 on load, interpolation stays
+    fp32 — so the image equals the oracle's on the fp16-rounded volume to the usual 1e-4, the
+    per-ray sample counts stay bit-exact, and skipping stays exact."""
+    vol, _, P = small_scene(C=1, dims=(67, 36, 29), W=72, H=56, seed=11, ortho=ortho)
+    tf = ramp_tf(64) if use_tf else None
+    P = replace(P, intensityAlpha=25.0)
+    volh = vol.half()
+    V = api.Volume(volh.cuda())
+    assert V.half and V.packed.dtype == torch.float16
+    assert torch.equal(api.unpack_volume_f16(V.packed, V.dims).cpu(), volh)
+    tfd = None if tf is None else tf.cuda()
+    img, T, counts = api.render_aux(V, None, tfd, P)
+    stats, ref, aux = check_forward(img, counts, volh.float(), replace(P, tfMode=int(use_tf)), tf)
+    assert stats["max_abs"] <= 1e-4
+    fast = api.render(V, None, tfd, P)
+    assert torch.equal(fast, img)
+    dense = api.render(V, None, tfd, replace(P, skipEmpty=0))
+    assert torch.equal(dense, img), "empty-space skipping changed an fp16 render"
+    # fp32 render of the same (rounded) values: same arithmetic after the load
+    img32 = api.render(api.Volume(volh.float().cuda()), None, tfd, P)
+    assert torch.equal(img32, img)
+    with pytest.raises(ValueError):
+        api.Volume(torch.zeros((2, 8, 8, 8), dtype=torch.float16, device="cuda"))
+
+
 def test_refold_when_weights_change(cuda):
     vol, _, P = small_scene(C=4, dims=(32, 28, 24), W=40, H=32, seed=9)
     V = api.Volume(vol.cuda())

@@ -39,6 +39,19 @@ def test_sort_last_eye_inside_grid_and_skipping_exact(cuda):
     assert (a - full).abs().max() <= 2e-5
 
 
+def test_sort_last_fp16_shards(cuda):
+    """config 5's shape in miniature: fp16 voxels, 2x2x2 shards, premultiplied partials."""
+    vol, _, P = small_scene(C=1, dims=(45, 38, 33), W=64, H=48, seed=21, theta_deg=41.0, phi_deg=70.0)
+    P = replace(P, tfMode=1, ertThreshold=1e-6)
+    tf = ramp_tf(64, sigma_scale=10.0, cutoff=0.1)
+    volh = vol.half()
+    full = api.render(api.Volume(volh.cuda()), None, tf.cuda(), P)
+    sl = mdist.render_sort_last_emulated(volh.cuda(), None, tf.cuda(), P, (2, 2, 2))
+    assert (sl - full).abs().max() <= 2e-5
+    ref = O.render(volh.float(), P, tf=tf)
+    assert (sl.cpu() - ref).abs().max() <= 1e-4
+
+
 def test_shard_argument_checks(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     with pytest.raises(ValueError):
