@@ -300,6 +300,22 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
 int mrt_composite_over(const float* partials, int32_t K, const int32_t* order, size_t npix,
                        const float* bg3, int32_t alphaMode, float* out_rgba, void* stream);
 
+/* Same composite, stored to `nouts` (<= 16) images at once: the local one and/or peer-mapped copies
+ * on other GPUs, so that the final all-gather of sort-last rendering is done by the composite
+ * kernel's own stores over NVLink.  `outs` is a HOST array of device pointers. */
+int mrt_composite_over_multi(const float* partials, int32_t K, const int32_t* order, size_t npix,
+                             const float* bg3, int32_t alphaMode, float* const* outs, int32_t nouts, void* stream);
+
+/* Sort-last exchange fused into the march (one frame): image rows [s*strip_rows, (s+1)*strip_rows)
+ * are written to strip_out[s] (float4 [strip_rows][W], row 0 = the strip's first image row) instead
+ * of one [H][W] image — with strip_out[s] a peer-mapped buffer of strip s's owner GPU, the
+ * all-to-all of partial images happens through the kernel's stores.  `strip_out` is a HOST array of
+ * `nstrips` (<= 16) device pointers; nstrips*strip_rows >= H. */
+int mrt_render_forward_strips(const MrtParams* params, const void* packed, int32_t C,
+                              const float* tf, int32_t tfN, const uint8_t* skip_levels,
+                              float* const* strip_out, int32_t nstrips, int32_t strip_rows,
+                              int32_t tile_begin, int32_t tile_end, void* stream);
+
 /* ------------------------------------------------ roofline probe
  * Random 32-byte-sector gather over a buffer of `bytes` (power of two), `n_gathers`
  * sectors per launch; writes a checksum so the loads cannot be elided.  Used by bench.py

@@ -195,6 +195,32 @@ def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, 
     return out
 
 
+def render_forward_strips(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
+                          skip_levels: Optional[torch.Tensor], strip_ptrs: Sequence[int], strip_rows: int,
+                          tile_range: Optional[Tuple[int, int]] = None):
+    """``mrt_render_forward_strips``: one frame whose image rows are scattered to per-strip buffers
+    (``strip_ptrs`` = device addresses, e.g. peer-mapped memory of the strips' owner GPUs)."""
+    W, H = P.imageSize
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    arr = (C.c_void_p * len(strip_ptrs))(*[int(p) for p in strip_ptrs])
+    s = P.to_struct()
+    check(lib().mrt_render_forward_strips(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                          _ptr(skip_levels), C.cast(arr, C.c_void_p), len(strip_ptrs), int(strip_rows),
+                                          t0, t1, _stream()), "render_forward_strips")
+
+
+def composite_over_multi(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int, out_ptrs: Sequence[int]):
+    """``mrt_composite_over_multi``: ordered `over` of ``[K,npix,4]`` partials stored to every address
+    in ``out_ptrs`` (local and/or peer-mapped ``[npix,4]`` images)."""
+    _need_cuda(partials, "partials", torch.float32)
+    K, npix = int(partials.shape[0]), int(partials.shape[1])
+    o = torch.tensor(list(order), dtype=torch.int32, device=partials.device)
+    bga = np.asarray(bg, dtype=np.float32)
+    arr = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+    check(lib().mrt_composite_over_multi(partials.data_ptr(), K, o.data_ptr(), npix, bga.ctypes.data, int(alpha_mode),
+                                         C.cast(arr, C.c_void_p), len(out_ptrs), _stream()), "composite_over_multi")
+
+
 def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                     labels: Optional[torch.Tensor], preds: Optional[torch.Tensor], out_rgba: torch.Tensor,
                     dL_dout: torch.Tensor, want_dvol: bool = True, want_dtf: bool = True,

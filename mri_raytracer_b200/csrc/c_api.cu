@@ -384,9 +384,36 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
 int mrt_composite_over(const float* partials, int32_t K, const int32_t* order, size_t npix, const float* bg3,
                        int32_t alphaMode, float* out_rgba, void* stream) {
   MRT_REQUIRE(partials && order && out_rgba && bg3 && K >= 1, "composite_over: bad arguments");
-  cudaError_t e = mrt_launch_composite(partials, K, order, npix, bg3[0], bg3[1], bg3[2], alphaMode, out_rgba,
+  float* outs[1] = {out_rgba};
+  cudaError_t e = mrt_launch_composite(partials, K, order, npix, bg3[0], bg3[1], bg3[2], alphaMode, outs, 1,
                                        (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "composite_over");
+}
+int mrt_composite_over_multi(const float* partials, int32_t K, const int32_t* order, size_t npix, const float* bg3,
+                             int32_t alphaMode, float* const* outs, int32_t nouts, void* stream) {
+  MRT_REQUIRE(partials && order && outs && bg3 && K >= 1, "composite_over_multi: bad arguments");
+  MRT_REQUIRE(nouts >= 1 && nouts <= MRT_MAX_STRIPS, "composite_over_multi: nouts=%d outside 1..%d", nouts, MRT_MAX_STRIPS);
+  for (int j = 0; j < nouts; ++j) MRT_REQUIRE(outs[j] != nullptr, "composite_over_multi: outs[%d] is null", j);
+  cudaError_t e = mrt_launch_composite(partials, K, order, npix, bg3[0], bg3[1], bg3[2], alphaMode, outs, nouts,
+                                       (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "composite_over_multi");
+}
+int mrt_render_forward_strips(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                              const uint8_t* skip_levels, float* const* strip_out, int32_t nstrips, int32_t strip_rows,
+                              int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && strip_out, "render_forward_strips: null volume or strip table");
+  MRT_REQUIRE(nstrips >= 1 && nstrips <= MRT_MAX_STRIPS, "render_forward_strips: nstrips=%d outside 1..%d", nstrips,
+              MRT_MAX_STRIPS);
+  KParams K;
+  if (int r = derive(params, C, tfN, skip_levels != nullptr, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_strips: tfMode=1 needs tf");
+  MRT_REQUIRE(strip_rows >= 1 && (int64_t)nstrips * strip_rows >= K.H, "render_forward_strips: %d strips of %d rows do not cover H=%d",
+              nstrips, strip_rows, K.H);
+  for (int j = 0; j < nstrips; ++j) MRT_REQUIRE(strip_out[j] != nullptr, "render_forward_strips: strip_out[%d] is null", j);
+  K.showSeg = K.showPred = 0;
+  cudaError_t e = mrt_launch_forward_strips(K, mrt_packed_channels(C), packed, tf, skip_levels, strip_out, nstrips,
+                                            strip_rows, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_strips");
 }
 int mrt_gather_probe(const void* buf, size_t bytes, size_t n_gathers, uint32_t seed, float* out, void* stream) {
   MRT_REQUIRE(buf && out, "gather_probe: null pointer");

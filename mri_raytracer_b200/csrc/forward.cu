@@ -24,6 +24,7 @@ template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF>
 __global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 1024) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
+               const __grid_constant__ StripTargets S,
                const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                const float4* __restrict__ tf,
                const uint8_t* __restrict__ levels,
@@ -45,6 +46,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   // empty ray, and never store
   const bool inside = (tile < P.tile_end) && (px < P.W) && (py < P.H);
   const size_t pix = ((size_t)view * P.H + py) * P.W + px;
+  float4* dst = out_rgba + pix;
+  if (S.n) { const int strip = py / S.rows; dst = S.base[strip] + ((size_t)(py - strip * S.rows) * P.W + px); }
 
   // Cull against the active-brick box BEFORE any expensive work: a ray that cannot enter it is
   // pure background.  Whole CTAs of such rays (most of the frame outside the head) skip the LUT
@@ -58,8 +61,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       const bool cta_any = __syncthreads_or(maybe);
       if (!cta_any || !__any_sync(0xffffffffu, maybe)) {
         if (inside) {
-          out_rgba[pix] = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
-                                  : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
+          *dst = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
+                         : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
           if (out_T) out_T[pix] = 1.0f;
         }
         if (!cta_any) return;                                              // nobody needs the LUT
@@ -239,12 +242,14 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     }
   }
   if (!inside) return;
-  out_rgba[pix] = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
+  *dst = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
   if (out_T) out_T[pix] = T;
   if (GENERIC) { if (out_counts) out_counts[pix] = make_int4(ray.n, k, n_eval, n_seg); }
 }
 
 // ------------------------------------------------------------------------- dispatch
+static const StripTargets g_no_strips = {};
+static thread_local const StripTargets* g_strips = &g_no_strips;   // set only for the duration of one launch call
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false>
 static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
@@ -254,7 +259,7 @@ static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, c
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
   const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
   mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
-      P, B, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
+      P, B, *g_strips, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
 }
@@ -277,6 +282,21 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews,
 // outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
+cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                                      const uint8_t* levels, float* const* strip_out, int nstrips, int strip_rows,
+                                      cudaStream_t st) {
+  if (nstrips < 1 || nstrips > MRT_MAX_STRIPS || strip_rows < 1 || (long long)nstrips * strip_rows < P.H)
+    return cudaErrorInvalidValue;
+  StripTargets S = {};
+  for (int i = 0; i < nstrips; ++i) S.base[i] = reinterpret_cast<float4*>(strip_out[i]);
+  S.n = nstrips; S.rows = strip_rows;
+  g_strips = &S;
+  cudaError_t e = mrt_launch_forward(P, nullptr, 1, packed_ch, vol, tf, levels, nullptr, nullptr,
+                                     strip_out[0], nullptr, nullptr, st);
+  g_strips = &g_no_strips;
+  return e;
+}
+
 cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st) {

@@ -10,6 +10,10 @@ cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, 
                                const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                float* out_rgba, float* out_T, int32_t* out_counts, cudaStream_t st);
 
+cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const void* vol, const float* tf,
+                                      const uint8_t* levels, float* const* strip_out, int nstrips, int strip_rows,
+                                      cudaStream_t st);
+
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
                                 const uint8_t* flat_levels, const float* minmax,
                                 const int32_t* labels, const int32_t* preds,
@@ -41,7 +45,8 @@ cudaError_t mrt_launch_tile_map(int W, int H, int32_t* out_tile, int32_t* out_la
 cudaError_t mrt_launch_gather_probe(const void* buf, size_t bytes, size_t n, uint32_t seed, float* out,
                                     cudaStream_t st);
 cudaError_t mrt_launch_composite(const float* partials, int K, const int32_t* order, size_t npix,
-                                 float bgr, float bgg, float bgb, int alphaMode, float* out, cudaStream_t st);
+                                 float bgr, float bgg, float bgb, int alphaMode, float* const* outs, int nouts,
+                                 cudaStream_t st);
 cudaError_t mrt_launch_bc4(const uint8_t* blocks, int W, int H, int D, uint8_t* out, cudaStream_t st);
 cudaError_t mrt_launch_u8_to_f32(const uint8_t* in, size_t n, float* out, cudaStream_t st);
 cudaError_t mrt_launch_normalize(const float* in, size_t n, float vmin, float rng, float* out, cudaStream_t st);

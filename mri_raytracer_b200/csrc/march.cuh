@@ -53,6 +53,11 @@ struct KParams {
 #define MRT_MAX_VIEWS 64
 struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 
+// Sort-last exchange fused into the march: image row y belongs to strip y / rows, whose pixels go
+// to base[strip] (a peer-mapped buffer of the strip's owner rank) instead of the local image.
+#define MRT_MAX_STRIPS 16
+struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; };
+
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
   float t0, t1;

@@ -292,9 +292,10 @@ cudaError_t mrt_launch_gather_probe(const void* buf, size_t bytes, size_t n, uin
 
 // ------------------------------------------------------------------ sort-last compositing
 // (C,T) <- (C_a + T_a*C_b, T_a*T_b), front first; bg added once at the end.
+struct CompositeOuts { float4* out[MRT_MAX_STRIPS]; int n; };
 __global__ void __launch_bounds__(256)
 mrt_composite_kernel(const float4* __restrict__ partials, int K, const int32_t* __restrict__ order,
-                     size_t npix, float bgr, float bgg, float bgb, int alphaMode, float4* __restrict__ out) {
+                     size_t npix, float bgr, float bgg, float bgb, int alphaMode, const __grid_constant__ CompositeOuts O) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
     float r = 0.f, g = 0.f, b = 0.f, T = 1.f;
@@ -303,14 +304,20 @@ mrt_composite_kernel(const float4* __restrict__ partials, int K, const int32_t* 
       r = fmaf(T, p.x, r); g = fmaf(T, p.y, g); b = fmaf(T, p.z, b);
       T *= p.w;
     }
-    out[i] = make_float4(bgr + r, bgg + g, bgb + b, alphaMode ? 1.0f - T : 1.0f);
+    const float4 v = make_float4(bgr + r, bgg + g, bgb + b, alphaMode ? 1.0f - T : 1.0f);
+    for (int j = 0; j < O.n; ++j) O.out[j][i] = v;       // local image and/or peer-mapped copies (all-gather by stores)
   }
 }
 cudaError_t mrt_launch_composite(const float* partials, int K, const int32_t* order, size_t npix,
-                                 float bgr, float bgg, float bgb, int alphaMode, float* out, cudaStream_t st) {
+                                 float bgr, float bgg, float bgb, int alphaMode, float* const* outs, int nouts,
+                                 cudaStream_t st) {
   if (npix == 0) return cudaSuccess;
+  if (nouts < 1 || nouts > MRT_MAX_STRIPS) return cudaErrorInvalidValue;
+  CompositeOuts O = {};
+  for (int j = 0; j < nouts; ++j) O.out[j] = reinterpret_cast<float4*>(outs[j]);
+  O.n = nouts;
   mrt_composite_kernel<<<grid_for(npix, 256), 256, 0, st>>>((const float4*)partials, K, order, npix,
-                                                           bgr, bgg, bgb, alphaMode, (float4*)out);
+                                                           bgr, bgg, bgb, alphaMode, O);
   return cudaGetLastError();
 }
 

@@ -284,6 +284,98 @@ def render_sort_last(shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, in
     return full.reshape(R * rows, W, 4)[:H].contiguous()
 
 
+class PeerSortLast:
+    """Sort-last rendering with BOTH exchanges done by kernel stores over NVLink (symmetric memory):
+
+    1. the march of rank i scatters the image rows of its partial straight into slot i of the
+       strip owners' receive buffers (``mrt_render_forward_strips``) — the all-to-all;
+    2. one stream-ordered barrier;
+    3. rank j composites the R partials of its strip front to back and stores the finished strip
+       into EVERY rank's final image (``mrt_composite_over_multi``) — the all-gather;
+    4. one barrier (also protects the receive buffers from the next frame's stores).
+
+    No NCCL collective and no staging copy is on the data path.  Falls back to
+    :func:`render_sort_last` (NCCL all_to_all + all_gather) when symmetric memory is unavailable
+    (``self.p2p`` False).  ``emulate=R`` builds the single-process equivalent (all "ranks" on this
+    GPU, plain device buffers) used by the tests."""
+
+    def __init__(self, H: int, W: int, device, group=None, emulate: int = 0):
+        self.rank, self.R = (0, int(emulate)) if emulate else _world(group)
+        self.emulate = bool(emulate)
+        self.group = group if group is not None else (dist.group.WORLD if (self.R > 1 and not emulate) else None)
+        self.H, self.W = H, W
+        self.rows = padded_rows(H, self.R)
+        R, rows = self.R, self.rows
+        self.p2p = False
+        self.hdl_recv = self.hdl_final = None
+        rshape, fshape = (R, rows, W, 4), (R * rows, W, 4)
+        if self.emulate:
+            self.recv_all = torch.zeros((R,) + rshape, dtype=torch.float32, device=device)     # [owner][src]
+            self.final_all = torch.zeros((R,) + fshape, dtype=torch.float32, device=device)
+            self.p2p = True
+        elif R > 1 and torch.device(device).type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.recv = symm_mem.empty(rshape, dtype=torch.float32, device=device)
+                self.final = symm_mem.empty(fshape, dtype=torch.float32, device=device)
+                self.hdl_recv = symm_mem.rendezvous(self.recv, self.group)
+                self.hdl_final = symm_mem.rendezvous(self.final, self.group)
+                self.recv_peer = [self.hdl_recv.get_buffer(j, rshape, torch.float32) for j in range(R)]
+                self.final_peer = [self.hdl_final.get_buffer(j, fshape, torch.float32) for j in range(R)]
+                self.p2p = True
+            except Exception as e:                      # pragma: no cover - depends on the platform
+                self.why = f"{type(e).__name__}: {e}"
+        if not self.p2p and not self.emulate:
+            self.recv = torch.zeros(rshape, dtype=torch.float32, device=device)
+            self.final = torch.zeros(fshape, dtype=torch.float32, device=device)
+
+    # the two halves, rank-parametrised so that the emulation can run them for every "rank"
+    def _march(self, rank, shard_volume, tf, Pc):
+        from . import api
+        Pm = replace(Pc, tfMode=1 if tf is not None else 0)
+        packed, Cn, Pe = shard_volume.prepared(Pm)
+        bits = shard_volume.skip_levels(Pm, tf)
+        if self.emulate:
+            ptrs = [self.recv_all[j, rank].data_ptr() for j in range(self.R)]
+        else:
+            ptrs = [self.recv_peer[j][rank].data_ptr() for j in range(self.R)]
+        api.render_forward_strips(Pe, packed, Cn, tf, bits, ptrs, self.rows)
+
+    def _composite(self, rank, Pc, order):
+        from . import api
+        R, rows, W = self.R, self.rows, self.W
+        if self.emulate:
+            parts = self.recv_all[rank].view(R, rows * W, 4)
+            outs = [self.final_all[j, rank * rows:(rank + 1) * rows].data_ptr() for j in range(R)]
+        else:
+            parts = self.recv.view(R, rows * W, 4)
+            outs = [self.final_peer[j][rank * rows:(rank + 1) * rows].data_ptr() for j in range(R)]
+        api.composite_over_multi(parts, order, Pc.bgColor, Pc.alphaMode, outs)
+
+    def render(self, shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, int, int]) -> torch.Tensor:
+        """One frame -> ``[H,W,4]`` (complete on every rank).  ``shard_volume`` = this rank's
+        Volume(..., shard=shard_box(dims, grid, rank)); in emulation, a list of all ranks' volumes."""
+        if grid[0] * grid[1] * grid[2] != self.R:
+            raise ValueError(f"grid {grid} does not match world size {self.R}")
+        Pc = P.with_camera(cam) if cam is not None else P
+        if (Pc.imageSize[0], Pc.imageSize[1]) != (self.W, self.H):
+            raise ValueError("imageSize does not match the exchange buffers")
+        order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
+        if self.emulate:
+            for r in range(self.R):
+                self._march(r, shard_volume[r], tf, Pc)
+            for r in range(self.R):
+                self._composite(r, Pc, order)
+            return self.final_all[0, :self.H]
+        if not self.p2p:
+            return render_sort_last(shard_volume, None, tf, Pc, grid, group=self.group)
+        self._march(self.rank, shard_volume, tf, Pc)
+        self.hdl_recv.barrier()
+        self._composite(self.rank, Pc, order)
+        self.hdl_final.barrier()
+        return self.final[:self.H]
+
+
 def render_sort_last_emulated(planar: torch.Tensor, cam, tf, P: RenderParams, grid: Tuple[int, int, int],
                               fold: bool = True) -> torch.Tensor:
     """All shards of ``grid`` rendered one after the other on ONE GPU, then composited: the

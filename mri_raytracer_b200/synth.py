@@ -83,6 +83,59 @@ def make_brats_like(C: int = 1, dims: Tuple[int, int, int] = (240, 240, 155), se
     return vol, lab.contiguous()
 
 
+def _interp_axis(table: torch.Tensor, n_global: int, lo: int, hi: int, dim: int) -> torch.Tensor:
+    """Linear interpolation (align_corners) of ``table`` along ``dim`` from 8 knots to the global
+    positions lo..hi of an axis with n_global samples."""
+    pos = torch.arange(lo, hi + 1, dtype=torch.float64, device=table.device) * (7.0 / max(n_global - 1, 1))
+    i0 = pos.floor().clamp(0, 6).to(torch.int64)
+    f = (pos - i0.to(torch.float64)).to(torch.float32)
+    a = table.index_select(dim, i0)
+    b = table.index_select(dim, i0 + 1)
+    shape = [1] * table.dim()
+    shape[dim] = -1
+    return a + (b - a) * f.view(shape)
+
+
+def make_brats_like_box(dims: Tuple[int, int, int], lo, hi, seed: int = 0, device=None,
+                        dtype: torch.dtype = torch.float16, zchunk: int = 32) -> torch.Tensor:
+    """Voxels [lo, hi] (inclusive, (x,y,z) order) of a single-channel BraTS-like volume of GLOBAL
+    size ``dims`` -> ``[1, nz, ny, nx]``.  Same recipe as :func:`make_brats_like` (ellipsoid mask,
+    smooth 8^3 tissue table, hashed per-voxel noise, three blobs) but every voxel is a pure function
+    of (seed, dims, global index), so a brick-sharded volume (BASELINE config 5: 2048^3 over 8
+    GPUs) is generated shard by shard, slab by slab, never materialising the whole."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    X, Y, Z = dims
+    nx, ny, nz = (int(h) - int(l) + 1 for l, h in zip(lo, hi))
+    g = torch.Generator().manual_seed(seed * 131 + 7)
+    table = torch.rand(8, 8, 8, generator=g).to(device)                    # [z][y][x] knots
+    txy = _interp_axis(_interp_axis(table, X, lo[0], hi[0], 2), Y, lo[1], hi[1], 1)      # [8, ny, nx]
+    blobs = _blobs(dims, seed)
+    x = torch.arange(lo[0], hi[0] + 1, dtype=torch.float32, device=device)[None, None, :]
+    y = torch.arange(lo[1], hi[1] + 1, dtype=torch.float32, device=device)[None, :, None]
+    out = torch.empty((1, nz, ny, nx), dtype=dtype, device=device)
+    xi = torch.arange(lo[0], hi[0] + 1, dtype=torch.int64, device=device)[None, None, :]
+    yi = torch.arange(lo[1], hi[1] + 1, dtype=torch.int64, device=device)[None, :, None]
+    for z0 in range(lo[2], hi[2] + 1, zchunk):
+        z1 = min(z0 + zchunk - 1, hi[2])
+        z = torch.arange(z0, z1 + 1, dtype=torch.float32, device=device)[:, None, None]
+        zi = torch.arange(z0, z1 + 1, dtype=torch.int64, device=device)[:, None, None]
+        ex = ((x - 0.5 * (X - 1)) / (0.36 * X)) ** 2 + ((y - 0.5 * (Y - 1)) / (0.42 * Y)) ** 2 \
+            + ((z - 0.5 * (Z - 1)) / (0.40 * Z)) ** 2
+        smooth = _interp_axis(txy, Z, z0, z1, 0)
+        lin = (zi * Y + yi) * X + xi
+        h = (lin + 0x9E3779B9 * (seed + 1)) & 0xFFFFFFFF
+        h = ((h ^ (h >> 16)) * 0x7FEB352D) & 0xFFFFFFFF
+        h = ((h ^ (h >> 15)) * 0x846CA68B) & 0xFFFFFFFF
+        h = h ^ (h >> 16)
+        noise = (h & 0xFFFFFF).to(torch.float32) * (2.0 / 16777216.0) - 1.0
+        v = 0.35 + 0.25 * smooth + 0.05 * noise
+        for (cx, cy, cz, sig) in blobs:
+            v = v + 0.3 * torch.exp(-((x - cx) ** 2 + (y - cy) ** 2 + (z - cz) ** 2) / (2 * sig * sig))
+        v = torch.where(ex <= 1.0, v.clamp(0.0, 1.0), torch.zeros_like(v))
+        out[0, z0 - lo[2]:z1 - lo[2] + 1] = v.to(dtype)
+    return out
+
+
 def ramp_tf(n: int = 256, sigma_scale: float = 40.0, cutoff: float = 0.08) -> torch.Tensor:
     """The bench transfer function: rgb = val, sigma = 40*val above 0.08 else 0."""
     val = torch.linspace(0.0, 1.0, n)

@@ -52,6 +52,27 @@ def test_sort_last_fp16_shards(cuda):
     assert (sl.cpu() - ref).abs().max() <= 1e-4
 
 
+@pytest.mark.parametrize("grid,H", [((2, 2, 2), 56), ((1, 3, 1), 50), ((2, 1, 1), 8)])
+def test_fused_strip_exchange_equals_staged(cuda, grid, H):
+    """mrt_render_forward_strips + mrt_composite_over_multi (the peer-memory exchange, emulated in
+    one process) give bit-for-bit the image of the staged path (partials, reorder, composite)."""
+    vol, _, P = small_scene(C=1, dims=(41, 35, 29), W=72, H=H, seed=33, theta_deg=12.0, phi_deg=100.0)
+    P = replace(P, tfMode=1, ertThreshold=1e-6, bgColor=(0.2, 0.1, 0.3), alphaMode=1)
+    tf = ramp_tf(64, sigma_scale=12.0, cutoff=0.1).cuda()
+    dims = (41, 35, 29)
+    R = grid[0] * grid[1] * grid[2]
+    vols = []
+    for r in range(R):
+        lo, hi, _ = mdist.shard_box(dims, grid, r)
+        vols.append(api.Volume(mdist.slice_shard(vol.cuda(), lo, hi), shard=(lo, hi), global_dims=dims))
+    ex = mdist.PeerSortLast(H, 72, "cuda", emulate=R)
+    fused = ex.render(vols, None, tf, P, grid).clone()
+    staged = mdist.render_sort_last_emulated(vol.cuda(), None, tf, P, grid)
+    assert torch.equal(fused, staged)
+    for j in range(1, R):            # every "rank" holds the same finished image
+        assert torch.equal(ex.final_all[j, :H], fused)
+
+
 def test_shard_argument_checks(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     with pytest.raises(ValueError):

@@ -1,0 +1,64 @@
+"""Multi-GPU correctness check (torchrun, 2+ GPUs): image-space peer framebuffer, sort-last through
+NCCL and through peer memory, all against single-GPU renders.  Prints one line per check."""
+import os, sys
+from dataclasses import replace
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import torch, torch.distributed as dist
+from mri_raytracer_b200 import api, dist as mdist
+from mri_raytracer_b200.synth import make_brats_like, ramp_tf
+from scenes import framed_params
+import bench
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok_all = True
+
+def report(name, ok, extra=""):
+    global ok_all
+    t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ok_all &= bool(t.item())
+    if rank == 0:
+        print(f"{name}: {'OK' if t.item() else 'FAIL'} {extra}", flush=True)
+
+# 1. image space, views per rank, fused peer gather
+V = 2
+P, cams_all = bench._scene(V * world)
+P = replace(P, imageSize=(256, 256))
+vol = make_brats_like(4, bench.DIMS, seed=0, device=dev); tf = ramp_tf(256).to(dev)
+volume = api.Volume(vol)
+fb = mdist.PeerFramebuffer(V, 256, 256, dev)
+mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P); fb.finish()
+torch.cuda.synchronize(); dist.barrier()
+ok = True
+if rank == 0:
+    ref = api.render_views(volume, cams_all, tf, P)
+    ok = bool(torch.equal(ref, fb.frames()))
+report("image-space peer framebuffer == local renders", ok, f"(p2p={fb.p2p})")
+for mode in ("views", "tiles"):
+    got = mdist.render_views(volume, cams_all, tf, P, mode=mode)
+    ref = api.render_views(volume, cams_all, tf, P)
+    report(f"image-space NCCL all_gather mode={mode}", bool(torch.equal(got, ref)))
+
+# 2. sort-last: NCCL exchange and peer exchange vs the unsharded render
+dims = (72, 60, 52)
+volc = make_brats_like(1, dims, seed=3, device=dev)
+Ps = replace(framed_params(dims, 200, 136, theta_deg=33.0, phi_deg=64.0), tfMode=1, ertThreshold=1e-6, bgColor=(0.1, 0.2, 0.3))
+tfs = ramp_tf(64, sigma_scale=10.0, cutoff=0.1).to(dev)
+grid = mdist.shard_grid(world)
+lo, hi, _ = mdist.shard_box(dims, grid, rank)
+for half in (False, True):
+    src = volc.half() if half else volc
+    full = api.render(api.Volume(src), None, tfs, Ps)
+    sv = api.Volume(mdist.slice_shard(src, lo, hi), shard=(lo, hi), global_dims=dims)
+    a = mdist.render_sort_last(sv, None, tfs, Ps, grid)
+    report(f"sort-last NCCL (half={half}) vs unsharded", float((a - full).abs().max()) <= 2e-5, f"max {float((a - full).abs().max()):.2e}")
+    ex = mdist.PeerSortLast(136, 200, dev)
+    for it in range(3):
+        b = ex.render(sv, None, tfs, Ps, grid)
+    report(f"sort-last peer exchange (half={half}, p2p={ex.p2p}) == NCCL path", bool(torch.equal(a, b.clone())))
+if rank == 0:
+    print("ALL OK" if ok_all else "SOME FAILED", flush=True)
+dist.destroy_process_group()
