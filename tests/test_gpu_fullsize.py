@@ -1,0 +1,125 @@
+"""Parity at BASELINE.json's FULL sizes.  The oracle cannot render whole frames at these sizes in
+seconds, so each configuration is checked through (a) the C oracle on a strided pixel subset
+(max-abs 1e-4, per-ray counts bit-exact, ERT tie rule) and (b) size-independent properties that
+must hold bit for bit over the whole frame: skipping on == off, batched == single launch, union of
+tile ranges == whole frame, and exact linearity in the emission colours (scaling the LUT's rgb by a
+power of two scales the image's rgb by it)."""
+import math
+from dataclasses import replace
+
+import pytest
+import torch
+
+from mri_raytracer_b200 import OrbitalCamera, api, orbit_views, tiles
+from mri_raytracer_b200.synth import make_brats_like, ramp_tf
+from scenes import framed_params
+from parity import O, check_subset
+
+pytestmark = pytest.mark.gpu
+
+
+def _properties(V, P, tf, img, cams=None):
+    dense = api.render(V, None, tf, replace(P, skipEmpty=0))
+    assert torch.equal(dense, img), "empty-space skipping changed the full-size frame"
+    tf2 = tf.clone(); tf2[:, :3] *= 2.0
+    img2 = api.render(V, None, tf2, P)
+    assert torch.equal(img2[..., :3], 2.0 * img[..., :3]) and torch.equal(img2[..., 3], img[..., 3]), \
+        "emission linearity (x2) is not exact"
+    W, H = P.imageSize
+    nt = tiles.tile_count(W, H)
+    out = torch.full_like(img, -7.0)
+    for r in range(3):
+        V.forward(replace(P, tfMode=1), tf, out=out, tile_range=tiles.rank_tile_range(nt, r, 3))
+    assert torch.equal(out, img), "union of 3 tile ranges differs from the whole frame"
+
+
+def test_cfg1_single_modality_ortho_512(cuda):
+    dims = (240, 240, 155)
+    vol = make_brats_like(1, dims, seed=0)
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 512, 512, ortho=True), tfMode=1)
+    V = api.Volume(vol.cuda())
+    img, T, counts = api.render_aux(V, None, tf.cuda(), P)
+    assert torch.equal(api.render(V, None, tf.cuda(), P), img)
+    st = check_subset(img, counts, vol, P, tf, stride=4)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    _properties(V, P, tf.cuda(), img)
+
+
+def test_cfg2_four_modalities_perspective_1024(cuda):
+    dims = (240, 240, 155)
+    vol = make_brats_like(4, dims, seed=0)
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 1024, 1024), tfMode=1)
+    V = api.Volume(vol.cuda())
+    img, T, counts = api.render_aux(V, None, tf.cuda(), P)
+    st = check_subset(img, counts, vol, P, tf, stride=8)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    _properties(V, P, tf.cuda(), img)
+    # per-sample blending from the interleaved layout (fold=False) agrees with the folded volume
+    Vn = api.Volume(vol.cuda(), fold=False)
+    assert (api.render(Vn, None, tf.cuda(), P) - img).abs().max() <= 1e-4
+    # the bench's orbit batch: one launch == eight launches
+    cam = V.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=math.radians(25.0), initial_phi=math.radians(80.0)))
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 8)
+    batch = api.render_views(V, cams, tf.cuda(), P)
+    assert torch.equal(batch[0], img)
+    for v in (3, 7):
+        assert torch.equal(batch[v], api.render(V, cams[v], tf.cuda(), P))
+
+
+def test_cfg3_gradients_256_cubed_on_a_ray_subset(cuda):
+    """forward+backward over the 256^3 volume at 512^2; the loss sees a strided ray subset so the
+    oracle can follow.  (A) dL/dTF against the oracle's autograd, 1e-3 relative.  (B) dL/dvolume
+    through directional derivatives: <dL/dvolume, delta> against a float64 central difference of the
+    oracle's loss along smooth fields delta (the oracle's dense autograd over 256^3 takes minutes;
+    full dL/dvolume-vs-autograd parity is in test_gpu_backward.py on small volumes).  The finite
+    difference of a piecewise-linear function carries its own O(eps) error: tolerance 2e-3."""
+    import torch.nn.functional as F
+    dims = (256, 256, 256)
+    vol = make_brats_like(1, dims, seed=4)
+    tf = ramp_tf(64, sigma_scale=20.0, cutoff=0.05)
+    P = replace(framed_params(dims, 512, 512), tfMode=1)
+    ys, xs = torch.meshgrid(torch.arange(3, 512, 16), torch.arange(5, 512, 16), indexing="ij")
+    px, py = xs.reshape(-1), ys.reshape(-1)
+    g = torch.Generator().manual_seed(0)
+    wgt = torch.rand(px.numel(), 4, generator=g)
+    # (A)
+    b = tf.clone().requires_grad_(True)
+    (O.render(vol, P, tf=b, pixels=(px, py)) * wgt).sum().backward()
+    ga = vol.cuda().requires_grad_(True); gb = tf.cuda().requires_grad_(True)
+    img = api.render(ga, None, gb, P)
+    (img[py.cuda(), px.cuda()] * wgt.cuda()).sum().backward()
+    rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
+    assert rel_t <= 1e-3, rel_t
+    assert int((ga.grad != 0).sum()) > 1000
+    # (B) early termination off (a hard threshold is not differentiable across a flip)
+    P2 = replace(P, ertThreshold=1e-9)
+    gv = vol.cuda().requires_grad_(True)
+    img = api.render(gv, None, tf.cuda(), P2)
+    (img[py.cuda(), px.cuda()] * wgt.cuda()).sum().backward()
+    grad = gv.grad.cpu().double()
+    eps = 1e-3
+    for seed in (1, 2):
+        gd = torch.Generator().manual_seed(seed)
+        d = F.interpolate(torch.rand(1, 1, 6, 6, 6, generator=gd) - 0.5, size=(256, 256, 256), mode="trilinear",
+                          align_corners=True)[0] * (vol > 0)
+        lp = (O.render((vol + eps * d).double(), P2, tf=tf.double(), pixels=(px, py), dtype=torch.float64) * wgt.double()).sum()
+        lm = (O.render((vol - eps * d).double(), P2, tf=tf.double(), pixels=(px, py), dtype=torch.float64) * wgt.double()).sum()
+        fd = float((lp - lm) / (2 * eps))
+        an = float((grad * d.double()).sum())
+        assert abs(an - fd) <= 2e-3 * abs(fd), (seed, an, fd)
+
+
+def test_cfg4_orbit_view_2048_over_512_cubed(cuda):
+    dims = (512, 512, 512)
+    vol = make_brats_like(1, dims, seed=5, device="cuda")
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 2048, 2048, theta_deg=0.0), tfMode=1)
+    V = api.Volume(vol)
+    img, T, counts = api.render_aux(V, None, tf.cuda(), P)
+    st = check_subset(img, counts, vol.cpu(), P, tf, stride=32)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    assert int(counts[..., 0].max()) > 1024, "config 4 must exceed the reference's [MaxIters(1024)] hint"
+    _properties(V, P, tf.cuda(), img)

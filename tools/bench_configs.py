@@ -125,8 +125,7 @@ def cfg4():
     out = torch.empty((len(cams), 2048, 2048, 4), device="cuda")
 
     def batch():
-        for i, c in enumerate(cams):
-            V.forward(replace(P.with_camera(c), tfMode=1), tf, out=out[i])
+        api.render_views(V, cams, tf, P, out=out)                 # one classify + one batched march
     ms = timeit(batch, reps=1)
     return dict(cfg="cfg4", views_timed=len(cams), ms_per_view=ms / len(cams), fps=len(cams) * 1e3 / ms,
                 samples_taken_per_view=taken / len(cams), gsamples_per_s=taken / ms / 1e6,
