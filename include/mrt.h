@@ -333,6 +333,25 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
                     const int32_t* labels_host, const int32_t* preds_host,
                     float* out_rgba_host);
 
+/* ------------------------------------------------ host-buffer pipeline
+ * mrt_render_host for a host that renders step after step (each step: a [C][Z][Y][X] volume, a TF
+ * and `nviews` cameras in, `nviews` frames out — the reference's load_dir + frame loop,
+ * inr/viewer/brats_viewer.py:188-248,369-450, without a window): a double-buffered object that
+ * owns its device buffers and three streams (upload / prepare+march / download), so that the
+ * download of step i, the compute of step i+1 and the upload of step i+2 overlap.  Host buffers
+ * should be page-locked for the copies to be asynchronous.  submit() returns after queueing;
+ * wait(ticket) blocks until that step's frames are in out_rgba_host.  Fixed geometry per object
+ * (C, dims, image size); fp32 volumes without label overlays.  One thread at a time per object. */
+typedef struct MrtHostPipeline MrtHostPipeline;
+int mrt_host_pipeline_create(MrtHostPipeline** out, int32_t C, int32_t X, int32_t Y, int32_t Z,
+                             int32_t W, int32_t H, int32_t max_views, int32_t max_tfN, int32_t depth);
+int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                             const float* planar_host, const float* tf_host, int32_t tfN,
+                             float* out_rgba_host, int64_t* ticket);
+int mrt_host_pipeline_wait(MrtHostPipeline* p, int64_t ticket);
+const char* mrt_host_pipeline_error(const MrtHostPipeline* p);
+void mrt_host_pipeline_destroy(MrtHostPipeline* p);
+
 #ifdef __cplusplus
 }
 #endif

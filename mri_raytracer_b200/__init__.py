@@ -10,7 +10,7 @@ from .params import RenderParams, SlabParams, default_label_lut
 from . import tiles
 
 __all__ = ["Camera", "OrbitalCamera", "OrbitalCameraYUp", "orbit_views", "RenderParams", "SlabParams",
-           "default_label_lut", "tiles", "render", "render_views", "render_aux", "render_slab", "render_host", "Volume"]
+           "default_label_lut", "tiles", "render", "render_views", "render_aux", "render_slab", "render_host", "HostPipeline", "Volume"]
 
 
 def __getattr__(name):

@@ -113,6 +113,11 @@ PROTOTYPES = {
     "mrt_composite_over_multi": (C.c_int, [_vp, _i32, _vp, _sz, _vp, _i32, _vp, _i32, _vp]),
     "mrt_render_forward_strips": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mrt_gather_probe": (C.c_int, [_vp, _sz, _sz, _u32, _vp, _vp]),
+    "mrt_host_pipeline_create": (C.c_int, [C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mrt_host_pipeline_submit": (C.c_int, [_vp, _PP, _vp, _i32, _vp, _vp, _i32, _vp, C.POINTER(C.c_int64)]),
+    "mrt_host_pipeline_wait": (C.c_int, [_vp, C.c_int64]),
+    "mrt_host_pipeline_error": (C.c_char_p, [_vp]),
+    "mrt_host_pipeline_destroy": (None, [_vp]),
     "mrt_render_host": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
 }
 

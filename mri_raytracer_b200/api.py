@@ -590,6 +590,68 @@ def render_host(volume: np.ndarray, params: RenderParams, tf: Optional[np.ndarra
     return out
 
 
+class HostPipeline:
+    """Host buffers in, host frames out, double-buffered (``mrt_host_pipeline_*``): per step a
+    ``[C,Z,Y,X]`` float32 host volume, an optional ``[N,4]`` TF and a list of cameras go in, and
+    ``[V,H,W,4]`` frames land in a host array.  Upload, prepare+march and download of successive
+    steps overlap (three streams); pass page-locked arrays (e.g. ``torch.Tensor.pin_memory()``
+    ``.numpy()``) so the copies are asynchronous.  ``submit`` queues a step and returns a ticket;
+    ``wait`` blocks until that step's frames are on the host."""
+
+    def __init__(self, C_: int, dims, image_size, max_views: int, max_tf: int = 256, depth: int = 2):
+        X, Y, Z = (int(v) for v in dims)
+        W, H = (int(v) for v in image_size)
+        self._h = C.c_void_p()
+        self.C, self.dims, self.image_size, self.max_views = int(C_), (X, Y, Z), (W, H), int(max_views)
+        rc = lib().mrt_host_pipeline_create(C.byref(self._h), self.C, X, Y, Z, W, H, int(max_views), int(max_tf), int(depth))
+        if rc != 0:
+            raise _lib.MrtError(f"host_pipeline_create failed ({rc})")
+        self._keep = {}
+
+    def submit(self, volume: np.ndarray, cams: Sequence, params: RenderParams, tf: Optional[np.ndarray],
+               out: np.ndarray) -> int:
+        X, Y, Z = self.dims
+        W, H = self.image_size
+        if volume.dtype != np.float32 or not volume.flags.c_contiguous or volume.shape != (self.C, Z, Y, X):
+            raise ValueError(f"volume must be C-contiguous float32 {(self.C, Z, Y, X)}")
+        V = len(cams)
+        if out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (V, H, W, 4):
+            raise ValueError(f"out must be C-contiguous float32 {(V, H, W, 4)}")
+        if tf is not None and (tf.dtype != np.float32 or not tf.flags.c_contiguous or tf.ndim != 2 or tf.shape[1] != 4):
+            raise ValueError("tf must be C-contiguous float32 [N,4]")
+        P = replace(params.with_camera(cams[0]), tfMode=1 if tf is not None else 0, dims=self.dims, imageSize=self.image_size)
+        s = P.to_struct()
+        arr = _camera_array(cams)
+        ticket = C.c_int64(-1)
+        rc = lib().mrt_host_pipeline_submit(self._h, C.byref(s), C.cast(arr, C.c_void_p), V, volume.ctypes.data,
+                                            None if tf is None else tf.ctypes.data, 0 if tf is None else tf.shape[0],
+                                            out.ctypes.data, C.byref(ticket))
+        if rc != 0:
+            raise _lib.MrtError(f"host_pipeline_submit failed ({rc}): "
+                                f"{lib().mrt_host_pipeline_error(self._h).decode('utf-8', 'replace')}")
+        self._keep[ticket.value] = (volume, tf, out)      # the host buffers must outlive the queued copies
+        return int(ticket.value)
+
+    def wait(self, ticket: int):
+        rc = lib().mrt_host_pipeline_wait(self._h, int(ticket))
+        if rc != 0:
+            raise _lib.MrtError(f"host_pipeline_wait failed ({rc}): "
+                                f"{lib().mrt_host_pipeline_error(self._h).decode('utf-8', 'replace')}")
+        for t in [t for t in self._keep if t <= ticket]:
+            del self._keep[t]
+
+    def close(self):
+        if self._h:
+            lib().mrt_host_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def tile_index_map(W: int, H: int, device="cuda"):
     """Device evaluation of the integer tile map (bit-exactness check): (tile[H,W], lane[H,W])."""
     t = torch.full((H, W), -1, dtype=torch.int32, device=device)

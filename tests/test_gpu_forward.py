@@ -208,6 +208,36 @@ def test_render_host_entry_point(cuda):
     assert np.array_equal(host_img, dev_img.numpy())
 
 
+@pytest.mark.parametrize("C,use_tf", [(4, True), (1, False)])
+def test_host_pipeline_equals_device_renders(cuda, C, use_tf):
+    """mrt_host_pipeline_*: several queued steps (different volumes / cameras per step, more steps
+    than slots) give bit for bit the frames of the device-side API."""
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    dims, W, H, V = (40, 36, 28), 41, 27, 3
+    _, _, P = small_scene(C=C, dims=dims, W=W, H=H, seed=1)
+    P = replace(P, intensityAlpha=9.0, volWeight=(1.0, 0.5, 2.0, 0.75))
+    tf = ramp_tf(64) if use_tf else None
+    pipe = api.HostPipeline(C, dims, (W, H), max_views=V, max_tf=64, depth=2)
+    vols, outs, tickets, cams_per_step = [], [], [], []
+    for step in range(5):
+        vol, _, _ = small_scene(C=C, dims=dims, W=W, H=H, seed=20 + step)
+        vh = vol.pin_memory()
+        oh = torch.empty((V, H, W, 4)).pin_memory()
+        Vd = api.Volume(vol.cuda())
+        cam = Vd.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.4 * step, initial_phi=1.3))
+        cam.set_fov_degrees(70.0)
+        cams = orbit_views(cam, V)
+        tickets.append(pipe.submit(vh.numpy(), cams, P, None if tf is None else tf.numpy(), oh.numpy()))
+        vols.append(Vd); outs.append(oh); cams_per_step.append(cams)
+    for step in (4, 0, 2, 1, 3):
+        pipe.wait(tickets[step])
+        ref = api.render_views(vols[step], cams_per_step[step], None if tf is None else tf.cuda(), P)
+        assert torch.equal(outs[step], ref.cpu()), f"step {step} differs"
+    with pytest.raises(ValueError):
+        pipe.submit(np.zeros((C, 2, 2, 2), np.float32), cams, P, None, outs[0].numpy())
+    pipe.close()
+
+
 def test_bad_arguments_raise(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     V = api.Volume(vol.cuda())
