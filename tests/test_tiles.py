@@ -48,3 +48,19 @@ def test_row_ranges_cover_image():
             assert rows[0][0] == 0 and rows[-1][1] == H
             for a, b in zip(rows, rows[1:]):
                 assert a[1] == b[0]
+
+
+def test_fast_tile_division_constant_is_exact():
+    """The march kernel divides tile ids by tiles_x with a multiply-high when the host has proven it
+    exact (c_api.cu derive(): tdiv_mul); same rule restated here and checked exhaustively for small
+    images and on boundaries for large ones."""
+    for W in list(range(1, 200)) + [512, 1000, 1024, 2048, 4096, 4099, 8192, 65536]:
+        d = (W + 7) >> 3
+        for H in (1, 7, 64, 1024, 4096, 65536):
+            nt = d * ((H + 7) >> 3)
+            if d > 1 and nt * d < 2 ** 32:
+                m = 2 ** 32 // d + 1
+                assert m < 2 ** 32
+                probe = range(nt) if nt <= 4096 else [0, 1, d - 1, d, d + 1, nt // 2, nt - d, nt - 1]
+                for n in probe:
+                    assert (n * m) >> 32 == n // d, (W, H, n)
