@@ -460,7 +460,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V,
                        "views_per_step_total": V * world if mode == "views" else V,
                        "partition": ("whole views per rank; framebuffer gathered on rank 0 by "
-                                     + ("peer (NVLink) stores from inside the march kernel" if (fb and fb.p2p)
+                                     + (("peer (NVLink) stores from inside the march kernel" + (", background tiles not sent (sparse gather)" if fb.sparse else "")) if (fb and fb.p2p)
                                         else "NCCL all_gather")) if (world > 1 and mode == "views")
                        else ("tile rows + NCCL all_gather" if world > 1 else "single GPU"),
                        "l2": "flushed (256 MiB write) between timed steps; volume 142.8 MB > 126 MB L2"},

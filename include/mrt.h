@@ -252,6 +252,20 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
                              float* out_rgba, float* out_T, int32_t* out_counts,
                              int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* Sparse variant for a framebuffer that lives on ANOTHER GPU (image-space gather through peer
+ * memory): CTAs whose rays all miss the active-brick box do not store their (pure background)
+ * pixels into `out_rgba` but set one byte in `cta_mask` (mrt_sparse_mask_bytes(W,H,nviews) bytes,
+ * every byte is written: 1 = not stored, 0 = stored); the owner of the image then calls
+ * mrt_fill_masked_tiles on its local copy.  Result == mrt_render_forward_batch, bit for bit, with
+ * the background (typically > half of the frame) never crossing NVLink.  Whole image only
+ * (no tile range), skipping required. */
+size_t mrt_sparse_mask_bytes(int32_t W, int32_t H, int32_t nviews);
+int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                    const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                    const uint8_t* skip_levels, float* out_rgba, uint8_t* cta_mask, void* stream);
+int mrt_fill_masked_tiles(const MrtParams* params, const uint8_t* cta_mask, int32_t nviews,
+                          float* out_rgba, void* stream);
+
 /* ------------------------------------------------ backward
  * Adjoint of mrt_render_forward w.r.t. the volume and the transfer function
  * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray.

@@ -195,6 +195,28 @@ def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, 
     return out
 
 
+def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
+                                tf: Optional[torch.Tensor], skip_levels: torch.Tensor, out_ptr: int, mask_ptr: int):
+    """``mrt_render_forward_batch_sparse``: like :func:`render_forward_batch` into the (peer) image at
+    ``out_ptr``, but all-background CTAs only set their byte at ``mask_ptr`` instead of storing."""
+    s = P.to_struct()
+    arr = _camera_array(cams)
+    check(lib().mrt_render_forward_batch_sparse(C.byref(s), C.cast(arr, C.c_void_p), len(cams), packed.data_ptr(), Cn,
+                                                _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
+                                                int(out_ptr), int(mask_ptr), _stream()), "render_forward_batch_sparse")
+
+
+def fill_masked_tiles(P: RenderParams, mask: torch.Tensor, nviews: int, out: torch.Tensor):
+    """``mrt_fill_masked_tiles``: background into every tile pair flagged in ``mask``."""
+    s = P.to_struct()
+    check(lib().mrt_fill_masked_tiles(C.byref(s), mask.data_ptr(), int(nviews), out.data_ptr(), _stream()),
+          "fill_masked_tiles")
+
+
+def sparse_mask_bytes(W: int, H: int, nviews: int) -> int:
+    return int(lib().mrt_sparse_mask_bytes(int(W), int(H), int(nviews)))
+
+
 def render_forward_strips(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                           skip_levels: Optional[torch.Tensor], strip_ptrs: Sequence[int], strip_rows: int,
                           tile_range: Optional[Tuple[int, int]] = None):
@@ -422,6 +444,21 @@ class Volume:
         bits = self.skip_levels(P, tf)
         return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
                                     out_T=out_T, out_counts=out_counts, tile_range=tile_range)
+
+
+    def forward_batch_sparse(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor], out_ptr: int,
+                             mask_ptr: int) -> bool:
+        """Sparse batched march into a (peer) image; False if this configuration cannot use it
+        (no occupancy grid / skipping off / gamma != 1 / overlays) — the caller then renders densely."""
+        P = P.with_camera(cams[0])
+        if (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred) or P.gamma != 1.0:
+            return False
+        packed, Cn, Pe = self.prepared(P)
+        bits = self.skip_levels(P, tf)
+        if bits is None:
+            return False
+        render_forward_batch_sparse(Pe, cams, packed, Cn, tf, bits, out_ptr, mask_ptr)
+        return True
 
 
 # ----------------------------------------------------------------------------- autograd

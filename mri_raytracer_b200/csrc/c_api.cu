@@ -325,6 +325,61 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch");
 }
 
+size_t mrt_sparse_mask_bytes(int32_t W, int32_t H, int32_t nviews) {
+  if (W < 1 || H < 1 || nviews < 1) return 0;
+  return (size_t)mrt_forward_ctas_per_view(mrt_tiles_x_(W) * mrt_tiles_y_(H)) * (size_t)nviews;
+}
+int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                    const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                    const uint8_t* skip_levels, float* out_rgba, uint8_t* cta_mask, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && cta_mask && skip_levels, "render_forward_batch_sparse: null pointer");
+  MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch_sparse: needs >= 1 camera");
+  KParams K;
+  const int W = params ? (int)params->imageSize[0] : 0, H = params ? (int)params->imageSize[1] : 0;
+  if (int r = derive(params, C, tfN, true, 0, mrt_tile_count(W > 0 ? W : 1, H > 0 ? H : 1), &K)) return r;
+  MRT_REQUIRE(K.skip, "render_forward_batch_sparse: needs skipEmpty=1 with indexed stepping");
+  MRT_REQUIRE(K.gamma == 1.0f, "render_forward_batch_sparse: gamma != 1 takes the generic kernel, which does not cull");
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_batch_sparse: tfMode=1 needs tf");
+  K.showSeg = K.showPred = 0;
+  cudaError_t e = cudaSuccess;
+  float chunk[MRT_MAX_VIEWS * 12];
+  const size_t npix = (size_t)K.W * K.H;
+  const size_t per_view = (size_t)mrt_forward_ctas_per_view(K.tile_end - K.tile_begin);
+  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
+    const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+    for (int v = 0; v < nv; ++v)
+      for (int i = 0; i < 3; ++i) {
+        const MrtCamera& c = cams[v0 + v];
+        chunk[v * 12 + i] = c.eye[i]; chunk[v * 12 + 3 + i] = c.U[i];
+        chunk[v * 12 + 6 + i] = c.V[i]; chunk[v * 12 + 9 + i] = c.W[i];
+      }
+    e = mrt_launch_forward_masked(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels,
+                                  out_rgba + (size_t)v0 * npix * 4, cta_mask + (size_t)v0 * per_view, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_sparse");
+}
+int mrt_fill_masked_tiles(const MrtParams* params, const uint8_t* cta_mask, int32_t nviews, float* out_rgba, void* stream) {
+  MRT_REQUIRE(params && cta_mask && out_rgba && nviews >= 1, "fill_masked_tiles: bad arguments");
+  const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
+  MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_masked_tiles: imageSize invalid");
+  KParams K;
+  memset(&K, 0, sizeof(K));
+  K.W = W; K.H = H; K.tile_begin = 0; K.tile_end = mrt_tile_count(W, H);
+  for (int i = 0; i < 3; ++i) K.bg[i] = params->bgColor[i];
+  K.alphaMode = params->alphaMode ? 1 : 0; K.shard = params->shardEnabled ? 1 : 0;
+  {
+    const uint64_t d = (uint64_t)mrt_tiles_x_(W);
+    K.tdiv_mul = (d > 1 && (uint64_t)K.tile_end * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
+  }
+  cudaError_t e = cudaSuccess;
+  const size_t npix = (size_t)W * H, per_view = (size_t)mrt_forward_ctas_per_view(K.tile_end);
+  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += 65535) {
+    const int nv = nviews - v0 < 65535 ? nviews - v0 : 65535;
+    e = mrt_launch_fill_masked(K, nv, cta_mask + (size_t)v0 * per_view, out_rgba + (size_t)v0 * npix * 4, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_masked_tiles");
+}
+
 size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }
 
 int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,

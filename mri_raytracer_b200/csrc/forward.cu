@@ -59,6 +59,11 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     if (!GENERIC) {                                                        // the counting variant needs every exact n
       maybe = inside && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
       const bool cta_any = __syncthreads_or(maybe);
+      if (S.cta_mask) {
+        if (threadIdx.x == 0)
+          S.cta_mask[(size_t)view * gridDim.x + mrt_middle_out(blockIdx.x, gridDim.x)] = cta_any ? 0 : 1;
+        if (!cta_any) return;                                                // background tiles: filled by the image's owner
+      }
       if (!cta_any || !__any_sync(0xffffffffu, maybe)) {
         if (inside) {
           *dst = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
@@ -282,6 +287,42 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews,
 // outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
+// Sparse framebuffer gather, receiving side: write the background pixel into every tile pair whose
+// CTA reported "all background, not stored" (StripTargets::cta_mask).  Same tile geometry as the march.
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB)
+mrt_fill_masked_kernel(const __grid_constant__ KParams P, const unsigned char* __restrict__ mask, float4* __restrict__ out) {
+  const int view = blockIdx.y;
+  if (!mask[(size_t)view * gridDim.x + blockIdx.x]) return;
+  const int tile = P.tile_begin + blockIdx.x * MRT_FWD_TPB + (threadIdx.x >> 6);
+  if (tile >= P.tile_end) return;
+  int px, py;
+  mrt_pixel_of_tile_lane_fast(P, tile, threadIdx.x & 63, &px, &py);
+  if (px >= P.W || py >= P.H) return;
+  out[((size_t)view * P.H + py) * P.W + px] = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
+                                                      : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
+}
+cudaError_t mrt_launch_fill_masked(const KParams& P, int nviews, const unsigned char* mask, float* out_rgba, cudaStream_t st) {
+  const int ntiles = P.tile_end - P.tile_begin;
+  if (ntiles <= 0 || nviews <= 0) return cudaSuccess;
+  const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
+  mrt_fill_masked_kernel<<<dim3(grid, nviews), 64 * MRT_FWD_TPB, 0, st>>>(P, mask, (float4*)out_rgba);
+  return cudaGetLastError();
+}
+int mrt_forward_ctas_per_view(int ntiles) { return (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB; }
+
+cudaError_t mrt_launch_forward_masked(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                      const float* tf, const uint8_t* levels, float* out_rgba, unsigned char* cta_mask,
+                                      cudaStream_t st) {
+  if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (mask offsets depend on it)
+  StripTargets S = {};
+  S.cta_mask = cta_mask;
+  g_strips = &S;
+  cudaError_t e = mrt_launch_forward(P, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
+                                     nullptr, st);
+  g_strips = &g_no_strips;
+  return e;
+}
+
 cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const void* vol, const float* tf,
                                       const uint8_t* levels, float* const* strip_out, int nstrips, int strip_rows,
                                       cudaStream_t st) {

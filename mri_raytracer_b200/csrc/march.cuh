@@ -56,7 +56,10 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // Sort-last exchange fused into the march: image row y belongs to strip y / rows, whose pixels go
 // to base[strip] (a peer-mapped buffer of the strip's owner rank) instead of the local image.
 #define MRT_MAX_STRIPS 16
-struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; };
+// cta_mask (optional): one byte per CTA of the launch, index view*ctas_per_view + position of the
+// CTA's tile pair in the tile range; 1 = "every pixel of this CTA is background and was NOT stored"
+// (sparse framebuffer gather: the owner of the image fills those tiles itself, mrt_fill_masked_tiles).
+struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; unsigned char* cta_mask; };
 
 struct Ray {
   float ox, oy, oz, dx, dy, dz;

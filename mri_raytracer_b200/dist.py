@@ -112,16 +112,25 @@ class PeerFramebuffer:
     ``[R*Vloc,H,W,4]`` buffer; rank r's march kernel stores its pixels straight into the ROOT
     rank's buffer through the NVLink peer mapping (16-byte coalesced stores, fire-and-forget),
     so the transfer overlaps the march of the following rays and there is no separate collective
-    on the data path - only one barrier per batch.  Falls back to NCCL ``all_gather`` when
-    symmetric memory is unavailable (``self.p2p`` is then False)."""
+    on the data path - only one barrier per batch.
 
-    def __init__(self, views_per_rank: int, H: int, W: int, device, group=None, root: int = 0):
+    ``sparse=True`` (default): CTAs whose rays all miss the active-brick box do not send their
+    background pixels; they set one byte in a (peer-mapped) mask on the root, and after the barrier
+    the root fills those tiles itself (``mrt_fill_masked_tiles``).  More than half of a frame is
+    background, and the root's NVLink ingress (7 ranks x frames) is what bounds the gather at 8 GPUs.
+
+    Falls back to NCCL ``all_gather`` when symmetric memory is unavailable (``self.p2p`` False)."""
+
+    def __init__(self, views_per_rank: int, H: int, W: int, device, group=None, root: int = 0, sparse: bool = True):
         self.rank, self.R = _world(group)
         self.group = group if group is not None else (dist.group.WORLD if self.R > 1 else None)
         self.Vloc, self.H, self.W, self.root = int(views_per_rank), H, W, root
         self.shape = (self.R * self.Vloc, H, W, 4)
         self.p2p = False
         self.hdl = None
+        self.sparse = False
+        self._sparse_used = False
+        self._P = None
         if self.R > 1 and torch.device(device).type == "cuda":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -129,6 +138,14 @@ class PeerFramebuffer:
                 self.hdl = symm_mem.rendezvous(self.local, self.group)
                 self.remote = self.hdl.get_buffer(root, self.shape, torch.float32)
                 self.p2p = True
+                if sparse:
+                    from . import api
+                    self.mask_per_rank = api.sparse_mask_bytes(W, H, self.Vloc)
+                    mshape = (self.R * self.mask_per_rank,)
+                    self.mask_local = symm_mem.empty(mshape, dtype=torch.uint8, device=device)
+                    self.mask_hdl = symm_mem.rendezvous(self.mask_local, self.group)
+                    self.mask_remote = self.mask_hdl.get_buffer(root, mshape, torch.uint8)
+                    self.sparse = True
             except Exception as e:                      # pragma: no cover - depends on the platform
                 self.why = f"{type(e).__name__}: {e}"
         if not self.p2p:
@@ -145,12 +162,20 @@ class PeerFramebuffer:
         buf = self.remote if self.p2p else self.local
         return buf[self.rank * self.Vloc:(self.rank + 1) * self.Vloc]
 
+    def mask_target(self) -> torch.Tensor:
+        return self.mask_remote[self.rank * self.mask_per_rank:(self.rank + 1) * self.mask_per_rank]
+
     def finish(self):
-        """Make the batch visible on the root: a barrier (p2p) or the NCCL gather (fallback)."""
+        """Make the batch visible on the root: a barrier (p2p) — followed, on the root, by the fill of
+        the tiles the senders skipped as background — or the NCCL gather (fallback)."""
         if self.R == 1:
             return
         if self.p2p:
             self.hdl.barrier()          # stream-ordered: after this rank's march kernels
+            if self._sparse_used and self.rank == self.root:
+                from . import api
+                api.fill_masked_tiles(self._P, self.mask_local, self.R * self.Vloc, self.local)
+            self._sparse_used = False
         else:
             lo = self.rank * self.Vloc
             dist.all_gather_into_tensor(self.local.view(-1), self.local[lo:lo + self.Vloc].reshape(-1).clone(),
@@ -168,6 +193,14 @@ def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: Re
     nt = tiles.tile_count(W, H)
     if len(cams_local) != fb.Vloc:
         raise ValueError(f"framebuffer holds {fb.Vloc} views per rank, got {len(cams_local)} cameras")
+    if fb.sparse and render_fn is None:
+        Pm = replace(P, tfMode=1 if tf is not None else 0)
+        # every rank must take the same branch (the root fills by the masks of ALL ranks): the
+        # decision only depends on params and volume kind, which are replicated
+        if volume.forward_batch_sparse(Pm, list(cams_local), tf, fb.targets().data_ptr(), fb.mask_target().data_ptr()):
+            fb._sparse_used = True
+            fb._P = Pm.with_camera(cams_local[0])
+            return
     _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
 
 
