@@ -158,13 +158,13 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
     return out
 
 
-def _camera_array(cams: Sequence) -> "C.Array":
-    arr = (_lib.MrtCamera * len(cams))()
-    for a, c in zip(arr, cams):
-        for name in ("eye", "U", "V", "W"):
-            v = np.asarray(getattr(c, name), dtype=np.float32)
-            getattr(a, name)[:] = [float(v[0]), float(v[1]), float(v[2])]
-    return arr
+def _camera_array(cams: Sequence) -> np.ndarray:
+    """``MrtCamera[len(cams)]`` as a float32 ``[V,16]`` array (rows eye|pad, U|pad, V|pad, W|pad)."""
+    a = np.zeros((len(cams), 16), dtype=np.float32)
+    for i, c in enumerate(cams):
+        r = a[i]
+        r[0:3] = c.eye; r[4:7] = c.U; r[8:11] = c.V; r[12:15] = c.W
+    return a
 
 
 def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
@@ -188,7 +188,7 @@ def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, 
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     s = P.to_struct()
     arr = _camera_array(cams)
-    check(lib().mrt_render_forward_batch(C.byref(s), C.cast(arr, C.c_void_p), V, packed.data_ptr(), Cn, _ptr(tf),
+    check(lib().mrt_render_forward_batch(C.byref(s), arr.ctypes.data, V, packed.data_ptr(), Cn, _ptr(tf),
                                          0 if tf is None else tf.shape[0], _ptr(skip_levels), _ptr(labels),
                                          _ptr(preds), out.data_ptr(), _ptr(out_T), _ptr(out_counts), t0, t1,
                                          _stream()), "render_forward_batch")
@@ -201,7 +201,7 @@ def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.T
     ``out_ptr``, but all-background CTAs only set their byte at ``mask_ptr`` instead of storing."""
     s = P.to_struct()
     arr = _camera_array(cams)
-    check(lib().mrt_render_forward_batch_sparse(C.byref(s), C.cast(arr, C.c_void_p), len(cams), packed.data_ptr(), Cn,
+    check(lib().mrt_render_forward_batch_sparse(C.byref(s), arr.ctypes.data, len(cams), packed.data_ptr(), Cn,
                                                 _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
                                                 int(out_ptr), int(mask_ptr), _stream()), "render_forward_batch_sparse")
 
@@ -284,7 +284,7 @@ def fold_volume_occupancy(planar: torch.Tensor, P: RenderParams) -> Tuple[torch.
     nbytes = lib().mrt_packed_volume_bytes(1, X, Y, Z)
     folded = torch.empty((nbytes // 4,), dtype=torch.float32, device=planar.device)   # padding is never read
     mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=planar.device)
-    s = replace(P, dims=(X, Y, Z), shard=None).to_struct()
+    s = (P if (tuple(P.dims) == (X, Y, Z) and P.shard is None) else replace(P, dims=(X, Y, Z), shard=None)).to_struct()
     check(lib().mrt_fold_volume_occupancy_f32(C.byref(s), planar.data_ptr(), Cn, folded.data_ptr(), mm.data_ptr(),
                                               _stream()), "fold_volume_occupancy")
     return folded, mm
@@ -417,6 +417,9 @@ class Volume:
     def skip_levels(self, P: RenderParams, tf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """Per-frame skip-level byte per brick (``mrt_classify_bricks``), or None if skipping is off."""
         packed, Cn, Pe = self.prepared(P)
+        return self._classify(P, Pe, Cn, tf)
+
+    def _classify(self, P: RenderParams, Pe: RenderParams, Cn: int, tf: Optional[torch.Tensor]):
         if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
             return None
         if self._bits is None:
@@ -428,7 +431,7 @@ class Volume:
                 tile_range: Optional[Tuple[int, int]] = None, labels=None, preds=None) -> torch.Tensor:
         """classify + march for one frame (two launches); ``P.tfMode`` must already be set."""
         packed, Cn, Pe = self.prepared(P)
-        bits = self.skip_levels(P, tf)
+        bits = self._classify(P, Pe, Cn, tf)
         return render_forward(Pe, packed, Cn, tf, bits, labels if labels is not None else self.labels,
                               preds if preds is not None else self.preds, out=out, out_T=out_T,
                               out_counts=out_counts, tile_range=tile_range)
@@ -439,12 +442,11 @@ class Volume:
                       out_counts: Optional[torch.Tensor] = None,
                       tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """classify ONCE (the skip levels do not depend on the camera) + one batched march."""
-        P = P.with_camera(cams[0])
+        P = P.with_camera(cams[0])                     # projection (fov / ortho window) of the batch
         packed, Cn, Pe = self.prepared(P)
-        bits = self.skip_levels(P, tf)
+        bits = self._classify(P, Pe, Cn, tf)
         return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
                                     out_T=out_T, out_counts=out_counts, tile_range=tile_range)
-
 
     def forward_batch_sparse(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor], out_ptr: int,
                              mask_ptr: int) -> bool:
@@ -454,7 +456,7 @@ class Volume:
         if (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred) or P.gamma != 1.0:
             return False
         packed, Cn, Pe = self.prepared(P)
-        bits = self.skip_levels(P, tf)
+        bits = self._classify(P, Pe, Cn, tf)
         if bits is None:
             return False
         render_forward_batch_sparse(Pe, cams, packed, Cn, tf, bits, out_ptr, mask_ptr)
@@ -569,7 +571,7 @@ def render_views(volume: Volume, cams: Sequence, tf: Optional[torch.Tensor], par
         _need_cuda(tf, "tf", torch.float32)
         if tf.dim() != 2 or tf.shape[1] != 4 or not (2 <= tf.shape[0] <= _lib.MRT_MAX_TF):
             raise ValueError(f"tf must be [N,4] with 2 <= N <= {_lib.MRT_MAX_TF}, got {tuple(tf.shape)}")
-    P = replace(params.with_camera(c0), tfMode=1 if tf is not None else 0)
+    P = replace(params, tfMode=1 if tf is not None else 0)
     if tuple(P.dims) != tuple(volume.global_dims):
         raise ValueError(f"params.dims {P.dims} != volume dims {volume.global_dims}")
     P.validate()
@@ -660,7 +662,7 @@ class HostPipeline:
         s = P.to_struct()
         arr = _camera_array(cams)
         ticket = C.c_int64(-1)
-        rc = lib().mrt_host_pipeline_submit(self._h, C.byref(s), C.cast(arr, C.c_void_p), V, volume.ctypes.data,
+        rc = lib().mrt_host_pipeline_submit(self._h, C.byref(s), arr.ctypes.data, V, volume.ctypes.data,
                                             None if tf is None else tf.ctypes.data, 0 if tf is None else tf.shape[0],
                                             out.ctypes.data, C.byref(ticket))
         if rc != 0:

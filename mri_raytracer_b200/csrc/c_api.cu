@@ -371,12 +371,7 @@ int mrt_fill_masked_tiles(const MrtParams* params, const uint8_t* cta_mask, int3
     const uint64_t d = (uint64_t)mrt_tiles_x_(W);
     K.tdiv_mul = (d > 1 && (uint64_t)K.tile_end * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
   }
-  cudaError_t e = cudaSuccess;
-  const size_t npix = (size_t)W * H, per_view = (size_t)mrt_forward_ctas_per_view(K.tile_end);
-  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += 65535) {
-    const int nv = nviews - v0 < 65535 ? nviews - v0 : 65535;
-    e = mrt_launch_fill_masked(K, nv, cta_mask + (size_t)v0 * per_view, out_rgba + (size_t)v0 * npix * 4, (cudaStream_t)stream);
-  }
+  cudaError_t e = mrt_launch_fill_masked(K, nviews, cta_mask, out_rgba, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_masked_tiles");
 }
 

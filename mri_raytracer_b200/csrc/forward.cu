@@ -289,23 +289,35 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews,
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
 // Sparse framebuffer gather, receiving side: write the background pixel into every tile pair whose
 // CTA reported "all background, not stored" (StripTargets::cta_mask).  Same tile geometry as the march.
-__global__ void __launch_bounds__(64 * MRT_FWD_TPB)
-mrt_fill_masked_kernel(const __grid_constant__ KParams P, const unsigned char* __restrict__ mask, float4* __restrict__ out) {
-  const int view = blockIdx.y;
-  if (!mask[(size_t)view * gridDim.x + blockIdx.x]) return;
-  const int tile = P.tile_begin + blockIdx.x * MRT_FWD_TPB + (threadIdx.x >> 6);
-  if (tile >= P.tile_end) return;
-  int px, py;
-  mrt_pixel_of_tile_lane_fast(P, tile, threadIdx.x & 63, &px, &py);
-  if (px >= P.W || py >= P.H) return;
-  out[((size_t)view * P.H + py) * P.W + px] = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
-                                                      : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
+__global__ void __launch_bounds__(256)
+mrt_fill_masked_kernel(const __grid_constant__ KParams P, const unsigned char* __restrict__ mask, size_t nmask,
+                       int ctas_per_view, float4* __restrict__ out) {
+  // one WARP per flagged tile pair (2 x 64 pixels = four 512-byte warp stores), grid-stride over the mask
+  const float4 bgp = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
+                             : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t m = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < nmask; m += nwarps) {
+    if (!mask[m]) continue;
+    const int view = (int)(m / (size_t)ctas_per_view), c = (int)(m - (size_t)view * ctas_per_view);
+#pragma unroll
+    for (int j = 0; j < 2 * MRT_FWD_TPB; ++j) {
+      const int tile = P.tile_begin + c * MRT_FWD_TPB + (j >> 1);
+      if (tile >= P.tile_end) break;
+      int px, py;
+      mrt_pixel_of_tile_lane_fast(P, tile, ((j & 1) << 5) + lane, &px, &py);
+      if (px < P.W && py < P.H) out[((size_t)view * P.H + py) * P.W + px] = bgp;
+    }
+  }
 }
 cudaError_t mrt_launch_fill_masked(const KParams& P, int nviews, const unsigned char* mask, float* out_rgba, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0 || nviews <= 0) return cudaSuccess;
-  const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
-  mrt_fill_masked_kernel<<<dim3(grid, nviews), 64 * MRT_FWD_TPB, 0, st>>>(P, mask, (float4*)out_rgba);
+  const int per_view = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
+  const size_t nmask = (size_t)per_view * nviews;
+  size_t grid = (nmask + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  mrt_fill_masked_kernel<<<(int)grid, 256, 0, st>>>(P, mask, nmask, per_view, (float4*)out_rgba);
   return cudaGetLastError();
 }
 int mrt_forward_ctas_per_view(int ntiles) { return (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB; }
