@@ -264,7 +264,7 @@ def run_ours(args):
     W = H = IMG
     nt = tiles.tile_count(W, H)
     mode = args.mode if world > 1 else "views"
-    fb = mdist.PeerFramebuffer(V, H, W, dev) if (world > 1 and mode == "views") else None
+    fb = mdist.PeerFramebuffer(V, H, W, dev, sparse=not args.dense_gather) if (world > 1 and mode == "views") else None
 
     # ---- untimed counting pass: the oracle-defined sample count of this rank's views
     taken = evaluated = clip = 0
@@ -302,8 +302,11 @@ def run_ours(args):
             if record_kernels:
                 b.record(); kern_ev.append((a, b))
         elif mode == "views":
-            mdist.render_views_to(fb, volume, cams, tf, P)           # pixels go straight to rank 0 over NVLink
-            fb.finish()
+            if args.no_gather:                                        # diagnosis only: compute without the gather
+                api.render_views(volume, cams, tf, P, out=frames)
+            else:
+                mdist.render_views_to(fb, volume, cams, tf, P)       # pixels go straight to rank 0 over NVLink
+                fb.finish()
         else:
             mdist.render_views(volume, cams, tf, P, mode=mode)
 
@@ -467,6 +470,7 @@ def run_ours(args):
             "frames_per_sec": (V * world if mode == "views" else V) * args.steps / tot_s,
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            **({"INVALID": "--no-gather diagnosis run"} if args.no_gather else {}),
             "gpu_launches": ((V if args.per_view else 1) + 1 + (1 if volume.fold else 0)) * args.steps,
         }
         print(json.dumps(line), flush=True)
@@ -483,6 +487,8 @@ def main():
     ap.add_argument("--views", type=int, default=8, help="frames per step (orbit batch)")
     ap.add_argument("--mode", default="views", choices=["views", "tiles"], help="multi-GPU partition")
     ap.add_argument("--per-view", action="store_true", help="one march launch per view instead of one per batch")
+    ap.add_argument("--dense-gather", action="store_true", help="multi-GPU: send background tiles too")
+    ap.add_argument("--no-gather", action="store_true", help="multi-GPU diagnosis: render locally, gather nothing (INVALID as a result)")
     ap.add_argument("--no-probe", action="store_true", help="skip the gather-ceiling probe")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
     ap.add_argument("--no-fold", action="store_true", help="blend modalities per sample (float4 gathers) instead of folding")
