@@ -305,7 +305,7 @@ def run_ours(args):
             if args.no_gather:                                        # diagnosis only: compute without the gather
                 api.render_views(volume, cams, tf, P, out=frames)
             else:
-                mdist.render_views_to(fb, volume, cams, tf, P)       # pixels go straight to rank 0 over NVLink
+                mdist.render_views_to(fb, volume, cams, tf, P, cams_all=cams_all)   # pixels go straight to rank 0 over NVLink
                 fb.finish()
         else:
             mdist.render_views(volume, cams, tf, P, mode=mode)
@@ -463,7 +463,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V,
                        "views_per_step_total": V * world if mode == "views" else V,
                        "partition": ("whole views per rank; framebuffer gathered on rank 0 by "
-                                     + (("peer (NVLink) stores from inside the march kernel" + (", background tiles not sent (sparse gather)" if fb.sparse else "")) if (fb and fb.p2p)
+                                     + (("peer (NVLink) stores from inside the march kernel" + (", tiles outside the active bricks' screen rectangle not sent but filled by the root (sparse gather)" if fb.sparse else "")) if (fb and fb.p2p)
                                         else "NCCL all_gather")) if (world > 1 and mode == "views")
                        else ("tile rows + NCCL all_gather" if world > 1 else "single GPU"),
                        "l2": "flushed (256 MiB write) between timed steps; volume 142.8 MB > 126 MB L2"},

@@ -195,26 +195,36 @@ def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, 
     return out
 
 
+def view_rects(P: RenderParams, cams: Sequence, Cn: int, skip_levels: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mrt_view_rects``: per view the pixel rectangle (x0,y0,x1,y1) that contains every ray able to
+    reach an active brick -> int32 ``[V,4]`` on the device."""
+    if out is None:
+        out = torch.empty((len(cams), 4), dtype=torch.int32, device=skip_levels.device)
+    s = P.to_struct()
+    arr = _camera_array(cams)
+    check(lib().mrt_view_rects(C.byref(s), arr.ctypes.data, len(cams), Cn, skip_levels.data_ptr(), out.data_ptr(),
+                               _stream()), "view_rects")
+    return out
+
+
 def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
-                                tf: Optional[torch.Tensor], skip_levels: torch.Tensor, out_ptr: int, mask_ptr: int):
+                                tf: Optional[torch.Tensor], skip_levels: torch.Tensor, out_ptr: int,
+                                rects: torch.Tensor):
     """``mrt_render_forward_batch_sparse``: like :func:`render_forward_batch` into the (peer) image at
-    ``out_ptr``, but all-background CTAs only set their byte at ``mask_ptr`` instead of storing."""
+    ``out_ptr``, except that tiles outside the views' rectangles are not stored."""
     s = P.to_struct()
     arr = _camera_array(cams)
     check(lib().mrt_render_forward_batch_sparse(C.byref(s), arr.ctypes.data, len(cams), packed.data_ptr(), Cn,
                                                 _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
-                                                int(out_ptr), int(mask_ptr), _stream()), "render_forward_batch_sparse")
+                                                int(out_ptr), rects.data_ptr(), _stream()), "render_forward_batch_sparse")
 
 
-def fill_masked_tiles(P: RenderParams, mask: torch.Tensor, nviews: int, out: torch.Tensor):
-    """``mrt_fill_masked_tiles``: background into every tile pair flagged in ``mask``."""
+def fill_outside_rects(P: RenderParams, rects: torch.Tensor, out: torch.Tensor):
+    """``mrt_fill_outside_rects``: background into every tile outside its view's rectangle."""
     s = P.to_struct()
-    check(lib().mrt_fill_masked_tiles(C.byref(s), mask.data_ptr(), int(nviews), out.data_ptr(), _stream()),
-          "fill_masked_tiles")
-
-
-def sparse_mask_bytes(W: int, H: int, nviews: int) -> int:
-    return int(lib().mrt_sparse_mask_bytes(int(W), int(H), int(nviews)))
+    check(lib().mrt_fill_outside_rects(C.byref(s), rects.data_ptr(), int(rects.shape[0]), out.data_ptr(), _stream()),
+          "fill_outside_rects")
 
 
 def render_forward_strips(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
@@ -448,19 +458,17 @@ class Volume:
         return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
                                     out_T=out_T, out_counts=out_counts, tile_range=tile_range)
 
-    def forward_batch_sparse(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor], out_ptr: int,
-                             mask_ptr: int) -> bool:
-        """Sparse batched march into a (peer) image; False if this configuration cannot use it
-        (no occupancy grid / skipping off / gamma != 1 / overlays) — the caller then renders densely."""
+    def sparse_plan(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor]):
+        """Prepare a sparse batched march: -> (packed, Cn, Pe, skip_levels) or None if this
+        configuration cannot use it (no occupancy grid / skipping off / gamma != 1 / overlays)."""
         P = P.with_camera(cams[0])
         if (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred) or P.gamma != 1.0:
-            return False
+            return None
         packed, Cn, Pe = self.prepared(P)
         bits = self._classify(P, Pe, Cn, tf)
         if bits is None:
-            return False
-        render_forward_batch_sparse(Pe, cams, packed, Cn, tf, bits, out_ptr, mask_ptr)
-        return True
+            return None
+        return packed, Cn, Pe, bits
 
 
 # ----------------------------------------------------------------------------- autograd

@@ -325,14 +325,34 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch");
 }
 
-size_t mrt_sparse_mask_bytes(int32_t W, int32_t H, int32_t nviews) {
-  if (W < 1 || H < 1 || nviews < 1) return 0;
-  return (size_t)mrt_forward_ctas_per_view(mrt_tiles_x_(W) * mrt_tiles_y_(H)) * (size_t)nviews;
+static void pack_cams(const MrtCamera* cams, int n, float* out12) {
+  for (int v = 0; v < n; ++v)
+    for (int i = 0; i < 3; ++i) {
+      const MrtCamera& c = cams[v];
+      out12[v * 12 + i] = c.eye[i]; out12[v * 12 + 3 + i] = c.U[i];
+      out12[v * 12 + 6 + i] = c.V[i]; out12[v * 12 + 9 + i] = c.W[i];
+    }
+}
+int mrt_view_rects(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C, const uint8_t* skip_levels,
+                   int32_t* rects, void* stream) {
+  MRT_REQUIRE(params && cams && skip_levels && rects && nviews >= 1, "view_rects: bad arguments");
+  KParams K;
+  MrtParams Pg = *params;
+  Pg.tfMode = 0;                              // geometry only: the transfer function plays no role here
+  if (int r = derive(&Pg, C, 0, true, 0, 0, &K)) return r;
+  cudaError_t e = cudaSuccess;
+  float chunk[MRT_MAX_VIEWS * 12];
+  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
+    const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+    pack_cams(cams + v0, nv, chunk);
+    e = mrt_launch_view_rects(K, chunk, nv, skip_levels, rects + (size_t)v0 * 4, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "view_rects");
 }
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
-                                    const uint8_t* skip_levels, float* out_rgba, uint8_t* cta_mask, void* stream) {
-  MRT_REQUIRE(packed && out_rgba && cta_mask && skip_levels, "render_forward_batch_sparse: null pointer");
+                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* rects, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && rects && skip_levels, "render_forward_batch_sparse: null pointer");
   MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch_sparse: needs >= 1 camera");
   KParams K;
   const int W = params ? (int)params->imageSize[0] : 0, H = params ? (int)params->imageSize[1] : 0;
@@ -344,24 +364,18 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
   cudaError_t e = cudaSuccess;
   float chunk[MRT_MAX_VIEWS * 12];
   const size_t npix = (size_t)K.W * K.H;
-  const size_t per_view = (size_t)mrt_forward_ctas_per_view(K.tile_end - K.tile_begin);
   for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
-    for (int v = 0; v < nv; ++v)
-      for (int i = 0; i < 3; ++i) {
-        const MrtCamera& c = cams[v0 + v];
-        chunk[v * 12 + i] = c.eye[i]; chunk[v * 12 + 3 + i] = c.U[i];
-        chunk[v * 12 + 6 + i] = c.V[i]; chunk[v * 12 + 9 + i] = c.W[i];
-      }
-    e = mrt_launch_forward_masked(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels,
-                                  out_rgba + (size_t)v0 * npix * 4, cta_mask + (size_t)v0 * per_view, (cudaStream_t)stream);
+    pack_cams(cams + v0, nv, chunk);
+    e = mrt_launch_forward_sparse(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels,
+                                  out_rgba + (size_t)v0 * npix * 4, rects + (size_t)v0 * 4, (cudaStream_t)stream);
   }
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_sparse");
 }
-int mrt_fill_masked_tiles(const MrtParams* params, const uint8_t* cta_mask, int32_t nviews, float* out_rgba, void* stream) {
-  MRT_REQUIRE(params && cta_mask && out_rgba && nviews >= 1, "fill_masked_tiles: bad arguments");
+int mrt_fill_outside_rects(const MrtParams* params, const int32_t* rects, int32_t nviews, float* out_rgba, void* stream) {
+  MRT_REQUIRE(params && rects && out_rgba && nviews >= 1, "fill_outside_rects: bad arguments");
   const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
-  MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_masked_tiles: imageSize invalid");
+  MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_outside_rects: imageSize invalid");
   KParams K;
   memset(&K, 0, sizeof(K));
   K.W = W; K.H = H; K.tile_begin = 0; K.tile_end = mrt_tile_count(W, H);
@@ -371,8 +385,8 @@ int mrt_fill_masked_tiles(const MrtParams* params, const uint8_t* cta_mask, int3
     const uint64_t d = (uint64_t)mrt_tiles_x_(W);
     K.tdiv_mul = (d > 1 && (uint64_t)K.tile_end * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
   }
-  cudaError_t e = mrt_launch_fill_masked(K, nviews, cta_mask, out_rgba, (cudaStream_t)stream);
-  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_masked_tiles");
+  cudaError_t e = mrt_launch_fill_outside(K, nviews, rects, out_rgba, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_outside_rects");
 }
 
 size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }

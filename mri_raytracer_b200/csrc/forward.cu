@@ -54,18 +54,18 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   // staging and the exact ray set-up; whole warps skip the set-up.
   bool maybe = inside;
   ActiveBox abox;
+  bool stored = true;                 // sparse gather: tiles outside the view's rectangle are filled by the image's owner
   if (SKIP) {
     abox = mrt_active_box(P, levels);
     if (!GENERIC) {                                                        // the counting variant needs every exact n
-      maybe = inside && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
-      const bool cta_any = __syncthreads_or(maybe);
-      if (S.cta_mask) {
-        if (threadIdx.x == 0)
-          S.cta_mask[(size_t)view * gridDim.x + mrt_middle_out(blockIdx.x, gridDim.x)] = cta_any ? 0 : 1;
-        if (!cta_any) return;                                                // background tiles: filled by the image's owner
+      if (S.rects != nullptr && tile < P.tile_end) {
+        const int4 r = __ldg(S.rects + view);
+        stored = mrt_tile_in_rect(r, px & ~MRT_TILE_MASK, py & ~MRT_TILE_MASK);   // warp-uniform (one tile per warp pair)
       }
+      maybe = inside && stored && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
+      const bool cta_any = __syncthreads_or(maybe);
       if (!cta_any || !__any_sync(0xffffffffu, maybe)) {
-        if (inside) {
+        if (inside && stored) {
           *dst = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
                          : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
           if (out_T) out_T[pix] = 1.0f;
@@ -287,47 +287,65 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews,
 // outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
-// Sparse framebuffer gather, receiving side: write the background pixel into every tile pair whose
-// CTA reported "all background, not stored" (StripTargets::cta_mask).  Same tile geometry as the march.
+// Sparse framebuffer gather.  mrt_view_rects_kernel: one thread per view evaluates mrt_view_rect.
+// mrt_fill_outside_kernel (receiving side): background into every tile outside its view's rectangle —
+// exactly the tiles the senders skip.  Same tile geometry as the march.
+__global__ void mrt_view_rects_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B, int nviews,
+                                      const uint8_t* __restrict__ levels, int4* __restrict__ rects) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nviews) return;
+  const ActiveBox A = mrt_active_box(P, levels);
+  rects[v] = mrt_view_rect(P, B.cam[v], A);
+}
 __global__ void __launch_bounds__(256)
-mrt_fill_masked_kernel(const __grid_constant__ KParams P, const unsigned char* __restrict__ mask, size_t nmask,
-                       int ctas_per_view, float4* __restrict__ out) {
-  // one WARP per flagged tile pair (2 x 64 pixels = four 512-byte warp stores), grid-stride over the mask
+mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int4* __restrict__ rects, int nviews,
+                        float4* __restrict__ out) {
+  // one WARP per tile (two 512-byte warp stores), grid-stride over (view, tile)
   const float4 bgp = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
                              : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
   const int lane = threadIdx.x & 31;
+  const int ntiles = P.tile_end - P.tile_begin;
+  const size_t total = (size_t)ntiles * nviews;
   const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-  for (size_t m = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < nmask; m += nwarps) {
-    if (!mask[m]) continue;
-    const int view = (int)(m / (size_t)ctas_per_view), c = (int)(m - (size_t)view * ctas_per_view);
+  for (size_t m = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < total; m += nwarps) {
+    const int view = (int)(m / (size_t)ntiles), tile = P.tile_begin + (int)(m - (size_t)view * ntiles);
+    int px, py;
+    mrt_pixel_of_tile_lane_fast(P, tile, lane, &px, &py);                 // lanes 0..31 = the tile's upper half
+    if (mrt_tile_in_rect(__ldg(rects + view), px & ~MRT_TILE_MASK, py & ~MRT_TILE_MASK)) continue;
 #pragma unroll
-    for (int j = 0; j < 2 * MRT_FWD_TPB; ++j) {
-      const int tile = P.tile_begin + c * MRT_FWD_TPB + (j >> 1);
-      if (tile >= P.tile_end) break;
-      int px, py;
-      mrt_pixel_of_tile_lane_fast(P, tile, ((j & 1) << 5) + lane, &px, &py);
-      if (px < P.W && py < P.H) out[((size_t)view * P.H + py) * P.W + px] = bgp;
+    for (int h = 0; h < 2; ++h) {
+      const int y = py + 4 * h;
+      if (px < P.W && y < P.H) out[((size_t)view * P.H + y) * P.W + px] = bgp;
     }
   }
 }
-cudaError_t mrt_launch_fill_masked(const KParams& P, int nviews, const unsigned char* mask, float* out_rgba, cudaStream_t st) {
+cudaError_t mrt_launch_view_rects(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* rects,
+                                  cudaStream_t st) {
+  for (int v0 = 0; v0 < nviews; v0 += MRT_MAX_VIEWS) {
+    const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+    CamBatch B;
+    for (int v = 0; v < nv; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)(v0 + v) * 12 + i];
+    mrt_view_rects_kernel<<<1, MRT_MAX_VIEWS, 0, st>>>(P, B, nv, levels, reinterpret_cast<int4*>(rects) + v0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* rects, float* out_rgba, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0 || nviews <= 0) return cudaSuccess;
-  const int per_view = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
-  const size_t nmask = (size_t)per_view * nviews;
-  size_t grid = (nmask + 7) / 8;
+  size_t grid = ((size_t)ntiles * nviews + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
-  mrt_fill_masked_kernel<<<(int)grid, 256, 0, st>>>(P, mask, nmask, per_view, (float4*)out_rgba);
+  mrt_fill_outside_kernel<<<(int)grid, 256, 0, st>>>(P, reinterpret_cast<const int4*>(rects), nviews, (float4*)out_rgba);
   return cudaGetLastError();
 }
-int mrt_forward_ctas_per_view(int ntiles) { return (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB; }
 
-cudaError_t mrt_launch_forward_masked(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
-                                      const float* tf, const uint8_t* levels, float* out_rgba, unsigned char* cta_mask,
+cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                      const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* rects,
                                       cudaStream_t st) {
-  if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (mask offsets depend on it)
+  if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (rects offsets go with it)
   StripTargets S = {};
-  S.cta_mask = cta_mask;
+  S.rects = reinterpret_cast<const int4*>(rects);
   g_strips = &S;
   cudaError_t e = mrt_launch_forward(P, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
                                      nullptr, st);

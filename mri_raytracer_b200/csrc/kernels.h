@@ -14,11 +14,12 @@ cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const voi
                                       const uint8_t* levels, float* const* strip_out, int nstrips, int strip_rows,
                                       cudaStream_t st);
 
-cudaError_t mrt_launch_forward_masked(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
-                                      const float* tf, const uint8_t* levels, float* out_rgba, unsigned char* cta_mask,
+cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                      const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* rects,
                                       cudaStream_t st);
-cudaError_t mrt_launch_fill_masked(const KParams& P, int nviews, const unsigned char* mask, float* out_rgba, cudaStream_t st);
-int mrt_forward_ctas_per_view(int ntiles);
+cudaError_t mrt_launch_view_rects(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* rects,
+                                  cudaStream_t st);
+cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* rects, float* out_rgba, cudaStream_t st);
 
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
                                 const uint8_t* flat_levels, const float* minmax,

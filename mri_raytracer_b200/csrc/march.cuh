@@ -56,10 +56,11 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // Sort-last exchange fused into the march: image row y belongs to strip y / rows, whose pixels go
 // to base[strip] (a peer-mapped buffer of the strip's owner rank) instead of the local image.
 #define MRT_MAX_STRIPS 16
-// cta_mask (optional): one byte per CTA of the launch, index view*ctas_per_view + position of the
-// CTA's tile pair in the tile range; 1 = "every pixel of this CTA is background and was NOT stored"
-// (sparse framebuffer gather: the owner of the image fills those tiles itself, mrt_fill_masked_tiles).
-struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; unsigned char* cta_mask; };
+// rects (optional, sparse framebuffer gather): per view of the launch an int4 (x0, y0, x1, y1),
+// the inclusive pixel rectangle outside which every ray certainly misses the active-brick box
+// (mrt_view_rect).  Tiles outside it are NOT stored by the march: the owner of the image fills
+// them with the background itself (mrt_fill_outside_rects), from the same rectangles.
+struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int4* rects; };
 
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
@@ -195,6 +196,48 @@ __device__ __forceinline__ bool mrt_ray_may_hit(const KParams& P, const float* _
   mrt_box_interval(A, (ox - P.bmin[0]) * sx, (oy - P.bmin[1]) * sy, (oz - P.bmin[2]) * sz, dx * sx, dy * sy, dz * sz,
                    &tin, &tout);
   return tout >= fmaxf(tin, 0.0f);
+}
+
+// Screen rectangle of the active-brick box for one camera: project the 8 corners of the box widened by
+// MRT_RECT_MARGIN voxels (> MRT_BOX_MARGIN, so a ray the slab test lets through always lies inside)
+// and round outward by one pixel.  Deterministic in (P, cam, box): the sender of a sparse gather
+// and the owner of the image evaluate it independently and get the same integers.
+#define MRT_RECT_MARGIN 0.75f
+__device__ __forceinline__ int4 mrt_view_rect(const KParams& P, const float* __restrict__ cam, const ActiveBox& A) {
+  const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
+  if (A.hi[0] < A.lo[0]) return make_int4(1, 1, 0, 0);                     // no active brick: empty rectangle
+  const float m = MRT_RECT_MARGIN - MRT_BOX_MARGIN;
+  const float aspect = (float)P.W / fmaxf(1.0f, (float)P.H);
+  float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+  bool behind = false;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float ix = (c & 1) ? A.hi[0] + m : A.lo[0] - m;
+    const float iy = (c & 2) ? A.hi[1] + m : A.lo[1] - m;
+    const float iz = (c & 4) ? A.hi[2] + m : A.lo[2] - m;
+    const float wx = P.bmin[0] + ix * P.vs[0] - eye[0], wy = P.bmin[1] + iy * P.vs[1] - eye[1], wz = P.bmin[2] + iz * P.vs[2] - eye[2];
+    const float xc = wx * U[0] + wy * U[1] + wz * U[2];
+    const float yc = wx * V[0] + wy * V[1] + wz * V[2];
+    const float zc = wx * Wv[0] + wy * Wv[1] + wz * Wv[2];
+    float uvx, uvy;
+    if (P.ortho) {
+      uvx = xc / (aspect * P.halfH); uvy = -yc / P.halfH;
+    } else {
+      if (!(zc > 1e-4f)) { behind = true; continue; }
+      uvx = (xc / zc) * P.focal / aspect; uvy = -(yc / zc) * P.focal;
+    }
+    const float px = (uvx + 1.0f) * 0.5f * (float)P.W - 0.5f, py = (uvy + 1.0f) * 0.5f * (float)P.H - 0.5f;
+    xmin = fminf(xmin, px); xmax = fmaxf(xmax, px); ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
+  }
+  if (behind) return make_int4(0, 0, P.W - 1, P.H - 1);                    // the box reaches behind the eye: everything
+  const float lim = 1.0e8f;
+  const int x0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), y0 = max(0, (int)floorf(fmaxf(ymin, -lim)) - 1);
+  const int x1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1), y1 = min(P.H - 1, (int)ceilf(fminf(ymax, lim)) + 1);
+  return make_int4(x0, y0, x1, y1);
+}
+// does the 8x8 tile with top-left pixel (tx0, ty0) intersect the rectangle?
+__device__ __forceinline__ bool mrt_tile_in_rect(int4 r, int tx0, int ty0) {
+  return tx0 <= r.z && tx0 + (MRT_TILE_EDGE - 1) >= r.x && ty0 <= r.w && ty0 + (MRT_TILE_EDGE - 1) >= r.y;
 }
 
 // ---- voxel vector types -------------------------------------------------------------

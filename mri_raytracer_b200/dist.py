@@ -114,10 +114,13 @@ class PeerFramebuffer:
     so the transfer overlaps the march of the following rays and there is no separate collective
     on the data path - only one barrier per batch.
 
-    ``sparse=True`` (default): CTAs whose rays all miss the active-brick box do not send their
-    background pixels; they set one byte in a (peer-mapped) mask on the root, and after the barrier
-    the root fills those tiles itself (``mrt_fill_masked_tiles``).  More than half of a frame is
-    background, and the root's NVLink ingress (7 ranks x frames) is what bounds the gather at 8 GPUs.
+    ``sparse=True`` (default): tiles outside a view's *rectangle* — the screen bounding box of the
+    active bricks, a deterministic function of (camera, params, occupancy) that every rank computes
+    for itself (``mrt_view_rects``) — are not sent; the root fills them with the background on a
+    side stream while everybody marches (``mrt_fill_outside_rects``; disjoint pixels, so no ordering
+    is needed).  More than half of a frame is background, and the root's NVLink ingress (7 ranks x
+    frames) is what bounds the dense gather at 8 GPUs.  The root needs the cameras of ALL views
+    (``cams_all`` of :func:`render_views_to`).
 
     Falls back to NCCL ``all_gather`` when symmetric memory is unavailable (``self.p2p`` False)."""
 
@@ -129,8 +132,7 @@ class PeerFramebuffer:
         self.p2p = False
         self.hdl = None
         self.sparse = False
-        self._sparse_used = False
-        self._P = None
+        self._fill_done = None
         if self.R > 1 and torch.device(device).type == "cuda":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -138,14 +140,11 @@ class PeerFramebuffer:
                 self.hdl = symm_mem.rendezvous(self.local, self.group)
                 self.remote = self.hdl.get_buffer(root, self.shape, torch.float32)
                 self.p2p = True
-                if sparse:
-                    from . import api
-                    self.mask_per_rank = api.sparse_mask_bytes(W, H, self.Vloc)
-                    mshape = (self.R * self.mask_per_rank,)
-                    self.mask_local = symm_mem.empty(mshape, dtype=torch.uint8, device=device)
-                    self.mask_hdl = symm_mem.rendezvous(self.mask_local, self.group)
-                    self.mask_remote = self.mask_hdl.get_buffer(root, mshape, torch.uint8)
-                    self.sparse = True
+                self.sparse = bool(sparse)
+                if self.sparse:
+                    self.rects = torch.empty((self.Vloc, 4), dtype=torch.int32, device=device)
+                    self.rects_all = torch.empty((self.R * self.Vloc, 4), dtype=torch.int32, device=device)
+                    self.side = torch.cuda.Stream(device=device)
             except Exception as e:                      # pragma: no cover - depends on the platform
                 self.why = f"{type(e).__name__}: {e}"
         if not self.p2p:
@@ -162,20 +161,16 @@ class PeerFramebuffer:
         buf = self.remote if self.p2p else self.local
         return buf[self.rank * self.Vloc:(self.rank + 1) * self.Vloc]
 
-    def mask_target(self) -> torch.Tensor:
-        return self.mask_remote[self.rank * self.mask_per_rank:(self.rank + 1) * self.mask_per_rank]
-
     def finish(self):
-        """Make the batch visible on the root: a barrier (p2p) — followed, on the root, by the fill of
-        the tiles the senders skipped as background — or the NCCL gather (fallback)."""
+        """Make the batch visible on the root: a barrier (p2p; the root also joins its background
+        fill) or the NCCL gather (fallback)."""
         if self.R == 1:
             return
         if self.p2p:
             self.hdl.barrier()          # stream-ordered: after this rank's march kernels
-            if self._sparse_used and self.rank == self.root:
-                from . import api
-                api.fill_masked_tiles(self._P, self.mask_local, self.R * self.Vloc, self.local)
-            self._sparse_used = False
+            if self._fill_done is not None:
+                torch.cuda.current_stream().wait_event(self._fill_done)
+                self._fill_done = None
         else:
             lo = self.rank * self.Vloc
             dist.all_gather_into_tensor(self.local.view(-1), self.local[lo:lo + self.Vloc].reshape(-1).clone(),
@@ -187,19 +182,33 @@ class PeerFramebuffer:
 
 
 def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: RenderParams,
-                    render_fn: Optional[Callable] = None):
-    """Render this rank's views into the (peer) framebuffer; call ``fb.finish()`` afterwards."""
+                    render_fn: Optional[Callable] = None, cams_all: Optional[Sequence] = None):
+    """Render this rank's views into the (peer) framebuffer; call ``fb.finish()`` afterwards.
+    ``cams_all`` (the cameras of every rank's views, in framebuffer order) enables the sparse
+    gather; without it every pixel is sent."""
     W, H = P.imageSize
     nt = tiles.tile_count(W, H)
     if len(cams_local) != fb.Vloc:
         raise ValueError(f"framebuffer holds {fb.Vloc} views per rank, got {len(cams_local)} cameras")
-    if fb.sparse and render_fn is None:
+    if fb.sparse and render_fn is None and cams_all is not None:
+        from . import api
+        if len(cams_all) != fb.R * fb.Vloc:
+            raise ValueError(f"cams_all must hold {fb.R * fb.Vloc} cameras")
         Pm = replace(P, tfMode=1 if tf is not None else 0)
-        # every rank must take the same branch (the root fills by the masks of ALL ranks): the
-        # decision only depends on params and volume kind, which are replicated
-        if volume.forward_batch_sparse(Pm, list(cams_local), tf, fb.targets().data_ptr(), fb.mask_target().data_ptr()):
-            fb._sparse_used = True
-            fb._P = Pm.with_camera(cams_local[0])
+        # every rank takes the same branch: it only depends on params and volume kind, which are replicated
+        plan = volume.sparse_plan(Pm, list(cams_local), tf)
+        if plan is not None:
+            packed, Cn, Pe, bits = plan
+            if fb.rank == fb.root:
+                # background of ALL views outside their rectangles, on a side stream, while everybody marches
+                ev = torch.cuda.Event(); ev.record()
+                with torch.cuda.stream(fb.side):
+                    fb.side.wait_event(ev)                                   # the classify above
+                    api.view_rects(Pe, list(cams_all), Cn, bits, out=fb.rects_all)
+                    api.fill_outside_rects(Pe, fb.rects_all, fb.local)
+                    fb._fill_done = torch.cuda.Event(); fb._fill_done.record()
+            api.view_rects(Pe, list(cams_local), Cn, bits, out=fb.rects)
+            api.render_forward_batch_sparse(Pe, list(cams_local), packed, Cn, tf, bits, fb.targets().data_ptr(), fb.rects)
             return
     _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
 

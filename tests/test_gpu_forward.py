@@ -188,30 +188,35 @@ def test_fp16_volume_matches_oracle_on_rounded_values(cuda, ortho, use_tf):
         api.Volume(torch.zeros((2, 8, 8, 8), dtype=torch.float16, device="cuda"))
 
 
-@pytest.mark.parametrize("W,H,alpha", [(200, 136, 0), (41, 27, 1)])
-def test_sparse_batch_plus_fill_equals_dense_batch(cuda, W, H, alpha):
-    """mrt_render_forward_batch_sparse + mrt_fill_masked_tiles (the sparse framebuffer gather, here
-    into a local buffer full of garbage) == mrt_render_forward_batch, bit for bit; and some CTAs
-    really are skipped."""
-    from mri_raytracer_b200 import OrbitalCamera, orbit_views
-    vol, _, P = small_scene(C=4, dims=(40, 36, 28), W=W, H=H, seed=8, radius_scale=1.6)
+@pytest.mark.parametrize("W,H,alpha,ortho", [(200, 136, 0, False), (41, 27, 1, False), (96, 80, 0, True)])
+def test_sparse_batch_plus_fill_equals_dense_batch(cuda, W, H, alpha, ortho):
+    """mrt_view_rects + mrt_render_forward_batch_sparse + mrt_fill_outside_rects (the sparse
+    framebuffer gather, here into a local buffer full of NaNs) == mrt_render_forward_batch, bit for
+    bit; some tiles really are skipped; a camera inside the volume degrades to the full frame."""
+    from mri_raytracer_b200 import Camera, OrbitalCamera, orbit_views
+    vol, _, P = small_scene(C=4, dims=(40, 36, 28), W=W, H=H, seed=8, ortho=ortho)
     P = replace(P, bgColor=(0.1, 0.2, 0.3), alphaMode=alpha)
     tf = ramp_tf(64).cuda()
     V = api.Volume(vol.cuda())
     cam = V.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.3, initial_phi=1.2))
     cam.radius *= 2.0
     cam.set_fov_degrees(70.0)
-    cams = orbit_views(cam, 5)
+    cams = orbit_views(cam, 5, ortho=ortho)
+    if not ortho:
+        cams[4] = replace(cams[4], eye=np.asarray([0.02, 0.01, -0.03], dtype=np.float32))    # inside the box
     dense = api.render_views(V, cams, tf, P)
     out = torch.full((5, H, W, 4), float("nan"), device="cuda")
-    mask = torch.full((api.sparse_mask_bytes(W, H, 5),), 7, dtype=torch.uint8, device="cuda")
     Pm = replace(P, tfMode=1)
-    assert V.forward_batch_sparse(Pm, cams, tf, out.data_ptr(), mask.data_ptr())
-    assert int(mask.max()) <= 1 and int(mask.sum()) > 0, "no CTA was culled: the test scene must have empty borders"
-    assert bool(torch.isnan(out).any())
-    api.fill_masked_tiles(Pm.with_camera(cams[0]), mask, 5, out)
+    packed, Cn, Pe, bits = V.sparse_plan(Pm, cams, tf)
+    rects = api.view_rects(Pe, cams, Cn, bits)
+    api.render_forward_batch_sparse(Pe, cams, packed, Cn, tf, bits, out.data_ptr(), rects)
+    r = rects.cpu()
+    assert bool(torch.isnan(out[0]).any()), "nothing was skipped: the test scene must have empty borders"
+    if not ortho:
+        assert r[4].tolist() == [0, 0, W - 1, H - 1] and not bool(torch.isnan(out[4]).any())
+    api.fill_outside_rects(Pe, rects, out)
     assert torch.equal(out, dense)
-    assert not V.forward_batch_sparse(replace(Pm, gamma=1.5), cams, tf, out.data_ptr(), mask.data_ptr())
+    assert V.sparse_plan(replace(Pm, gamma=1.5), cams, tf) is None
 
 
 def test_refold_when_weights_change(cuda):

@@ -30,7 +30,7 @@ P = replace(P, imageSize=(256, 256))
 vol = make_brats_like(4, bench.DIMS, seed=0, device=dev); tf = ramp_tf(256).to(dev)
 volume = api.Volume(vol)
 fb = mdist.PeerFramebuffer(V, 256, 256, dev)
-mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P); fb.finish()
+mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P, cams_all=cams_all); fb.finish()
 torch.cuda.synchronize(); dist.barrier()
 ok = True
 if rank == 0:

@@ -17,7 +17,7 @@ vol = make_brats_like(4, bench.DIMS, seed=0, device=dev); tf = ramp_tf(256).to(d
 volume = api.Volume(vol)
 fb = mdist.PeerFramebuffer(V, 256, 256, dev)
 print(rank, "p2p", fb.p2p, getattr(fb, "why", ""), flush=True)
-mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P); fb.finish()
+mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P, cams_all=cams_all); fb.finish()
 torch.cuda.synchronize(); dist.barrier()
 if rank == 0:
     ok = True
