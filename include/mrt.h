@@ -253,21 +253,21 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
                              int32_t tile_begin, int32_t tile_end, void* stream);
 
 /* Sparse variant for a framebuffer that lives on ANOTHER GPU (image-space gather through peer
- * memory).  mrt_view_rects computes, per view, the inclusive pixel rectangle (x0,y0,x1,y1) outside
- * which every ray certainly misses the active-brick box (projection of the box recorded by
- * mrt_classify_bricks, rounded outward; deterministic in its inputs, so the sender and the owner of
- * the image compute identical rectangles independently).  mrt_render_forward_batch_sparse does NOT
- * store the tiles outside its views' rectangles; the owner of the image calls
- * mrt_fill_outside_rects on its local copy (any time: the two write disjoint pixels).  Together ==
- * mrt_render_forward_batch, bit for bit, with the background (typically > half of the frame) never
- * crossing NVLink and its fill off the critical path.  Whole image only, skipping required.
- * `rects`: device int32[nviews][4]. */
-int mrt_view_rects(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C,
-                   const uint8_t* skip_levels, int32_t* rects, void* stream);
+ * memory).  mrt_view_spans computes, per view and per tile row (8 pixel rows), the inclusive pixel
+ * span (x0,x1) outside which every ray certainly misses the active-brick box: the convex hull of
+ * the projected box recorded by mrt_classify_bricks, rounded outward (empty: x0 > x1).  It is
+ * deterministic in its inputs, so the sender and the owner of the image compute identical spans
+ * independently.  mrt_render_forward_batch_sparse does NOT store the tiles outside its views'
+ * spans; the owner of the image calls mrt_fill_outside_spans on its local copy (any time: the two
+ * write disjoint pixels).  Together == mrt_render_forward_batch, bit for bit, with the background
+ * (typically > half of the frame) never crossing NVLink and its fill off the critical path.
+ * Whole image only, skipping required.  `spans`: device int32[nviews][mrt_tiles_y(H)][2]. */
+int mrt_view_spans(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C,
+                   const uint8_t* skip_levels, int32_t* spans, void* stream);
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
-                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* rects, void* stream);
-int mrt_fill_outside_rects(const MrtParams* params, const int32_t* rects, int32_t nviews,
+                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* spans, void* stream);
+int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews,
                            float* out_rgba, void* stream);
 
 /* ------------------------------------------------ backward

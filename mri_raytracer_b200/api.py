@@ -160,11 +160,9 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
 
 def _camera_array(cams: Sequence) -> np.ndarray:
     """``MrtCamera[len(cams)]`` as a float32 ``[V,16]`` array (rows eye|pad, U|pad, V|pad, W|pad)."""
-    a = np.zeros((len(cams), 16), dtype=np.float32)
-    for i, c in enumerate(cams):
-        r = a[i]
-        r[0:3] = c.eye; r[4:7] = c.U; r[8:11] = c.V; r[12:15] = c.W
-    return a
+    a = np.zeros((len(cams), 4, 4), dtype=np.float32)
+    a[:, :, :3] = np.asarray([(c.eye, c.U, c.V, c.W) for c in cams], dtype=np.float32)
+    return a.reshape(len(cams), 16)
 
 
 def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
@@ -195,36 +193,36 @@ def render_forward_batch(P: RenderParams, cams: Sequence, packed: torch.Tensor, 
     return out
 
 
-def view_rects(P: RenderParams, cams: Sequence, Cn: int, skip_levels: torch.Tensor,
+def view_spans(P: RenderParams, cams: Sequence, Cn: int, skip_levels: torch.Tensor,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``mrt_view_rects``: per view the pixel rectangle (x0,y0,x1,y1) that contains every ray able to
-    reach an active brick -> int32 ``[V,4]`` on the device."""
+    """``mrt_view_spans``: per view and tile row the pixel span (x0,x1) that contains every ray able
+    to reach an active brick -> int32 ``[V, tiles_y, 2]`` on the device."""
     if out is None:
-        out = torch.empty((len(cams), 4), dtype=torch.int32, device=skip_levels.device)
+        out = torch.empty((len(cams), _tiles.tiles_y(P.imageSize[1]), 2), dtype=torch.int32, device=skip_levels.device)
     s = P.to_struct()
     arr = _camera_array(cams)
-    check(lib().mrt_view_rects(C.byref(s), arr.ctypes.data, len(cams), Cn, skip_levels.data_ptr(), out.data_ptr(),
-                               _stream()), "view_rects")
+    check(lib().mrt_view_spans(C.byref(s), arr.ctypes.data, len(cams), Cn, skip_levels.data_ptr(), out.data_ptr(),
+                               _stream()), "view_spans")
     return out
 
 
 def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
                                 tf: Optional[torch.Tensor], skip_levels: torch.Tensor, out_ptr: int,
-                                rects: torch.Tensor):
+                                spans: torch.Tensor):
     """``mrt_render_forward_batch_sparse``: like :func:`render_forward_batch` into the (peer) image at
-    ``out_ptr``, except that tiles outside the views' rectangles are not stored."""
+    ``out_ptr``, except that tiles outside the views' spans are not stored."""
     s = P.to_struct()
     arr = _camera_array(cams)
     check(lib().mrt_render_forward_batch_sparse(C.byref(s), arr.ctypes.data, len(cams), packed.data_ptr(), Cn,
                                                 _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
-                                                int(out_ptr), rects.data_ptr(), _stream()), "render_forward_batch_sparse")
+                                                int(out_ptr), spans.data_ptr(), _stream()), "render_forward_batch_sparse")
 
 
-def fill_outside_rects(P: RenderParams, rects: torch.Tensor, out: torch.Tensor):
-    """``mrt_fill_outside_rects``: background into every tile outside its view's rectangle."""
+def fill_outside_spans(P: RenderParams, spans: torch.Tensor, out: torch.Tensor):
+    """``mrt_fill_outside_spans``: background into every tile outside its row's span."""
     s = P.to_struct()
-    check(lib().mrt_fill_outside_rects(C.byref(s), rects.data_ptr(), int(rects.shape[0]), out.data_ptr(), _stream()),
-          "fill_outside_rects")
+    check(lib().mrt_fill_outside_spans(C.byref(s), spans.data_ptr(), int(spans.shape[0]), out.data_ptr(), _stream()),
+          "fill_outside_spans")
 
 
 def render_forward_strips(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],

@@ -333,9 +333,9 @@ static void pack_cams(const MrtCamera* cams, int n, float* out12) {
       out12[v * 12 + 6 + i] = c.V[i]; out12[v * 12 + 9 + i] = c.W[i];
     }
 }
-int mrt_view_rects(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C, const uint8_t* skip_levels,
-                   int32_t* rects, void* stream) {
-  MRT_REQUIRE(params && cams && skip_levels && rects && nviews >= 1, "view_rects: bad arguments");
+int mrt_view_spans(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C, const uint8_t* skip_levels,
+                   int32_t* spans, void* stream) {
+  MRT_REQUIRE(params && cams && skip_levels && spans && nviews >= 1, "view_spans: bad arguments");
   KParams K;
   MrtParams Pg = *params;
   Pg.tfMode = 0;                              // geometry only: the transfer function plays no role here
@@ -345,14 +345,14 @@ int mrt_view_rects(const MrtParams* params, const MrtCamera* cams, int32_t nview
   for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     pack_cams(cams + v0, nv, chunk);
-    e = mrt_launch_view_rects(K, chunk, nv, skip_levels, rects + (size_t)v0 * 4, (cudaStream_t)stream);
+    e = mrt_launch_view_spans(K, chunk, nv, skip_levels, spans + (size_t)v0 * 2 * mrt_tiles_y_(K.H), (cudaStream_t)stream);
   }
-  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "view_rects");
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "view_spans");
 }
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
-                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* rects, void* stream) {
-  MRT_REQUIRE(packed && out_rgba && rects && skip_levels, "render_forward_batch_sparse: null pointer");
+                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* spans, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && spans && skip_levels, "render_forward_batch_sparse: null pointer");
   MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch_sparse: needs >= 1 camera");
   KParams K;
   const int W = params ? (int)params->imageSize[0] : 0, H = params ? (int)params->imageSize[1] : 0;
@@ -368,14 +368,14 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     pack_cams(cams + v0, nv, chunk);
     e = mrt_launch_forward_sparse(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels,
-                                  out_rgba + (size_t)v0 * npix * 4, rects + (size_t)v0 * 4, (cudaStream_t)stream);
+                                  out_rgba + (size_t)v0 * npix * 4, spans + (size_t)v0 * 2 * mrt_tiles_y_(K.H), (cudaStream_t)stream);
   }
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_sparse");
 }
-int mrt_fill_outside_rects(const MrtParams* params, const int32_t* rects, int32_t nviews, float* out_rgba, void* stream) {
-  MRT_REQUIRE(params && rects && out_rgba && nviews >= 1, "fill_outside_rects: bad arguments");
+int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews, float* out_rgba, void* stream) {
+  MRT_REQUIRE(params && spans && out_rgba && nviews >= 1, "fill_outside_spans: bad arguments");
   const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
-  MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_outside_rects: imageSize invalid");
+  MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_outside_spans: imageSize invalid");
   KParams K;
   memset(&K, 0, sizeof(K));
   K.W = W; K.H = H; K.tile_begin = 0; K.tile_end = mrt_tile_count(W, H);
@@ -385,8 +385,8 @@ int mrt_fill_outside_rects(const MrtParams* params, const int32_t* rects, int32_
     const uint64_t d = (uint64_t)mrt_tiles_x_(W);
     K.tdiv_mul = (d > 1 && (uint64_t)K.tile_end * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
   }
-  cudaError_t e = mrt_launch_fill_outside(K, nviews, rects, out_rgba, (cudaStream_t)stream);
-  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_outside_rects");
+  cudaError_t e = mrt_launch_fill_outside(K, nviews, spans, out_rgba, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_outside_spans");
 }
 
 size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }

@@ -58,9 +58,9 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   if (SKIP) {
     abox = mrt_active_box(P, levels);
     if (!GENERIC) {                                                        // the counting variant needs every exact n
-      if (S.rects != nullptr && tile < P.tile_end) {
-        const int4 r = __ldg(S.rects + view);
-        stored = mrt_tile_in_rect(r, px & ~MRT_TILE_MASK, py & ~MRT_TILE_MASK);   // warp-uniform (one tile per warp pair)
+      if (S.spans != nullptr && tile < P.tile_end) {
+        const int2 sp = __ldg(S.spans + (size_t)view * mrt_tiles_y_(P.H) + (py >> MRT_TILE_SHIFT));
+        stored = mrt_tile_in_span(sp, px & ~MRT_TILE_MASK);                 // warp-uniform (one tile per warp pair)
       }
       maybe = inside && stored && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
       const bool cta_any = __syncthreads_or(maybe);
@@ -287,31 +287,33 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews,
 // outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
-// Sparse framebuffer gather.  mrt_view_rects_kernel: one thread per view evaluates mrt_view_rect.
-// mrt_fill_outside_kernel (receiving side): background into every tile outside its view's rectangle —
-// exactly the tiles the senders skip.  Same tile geometry as the march.
-__global__ void mrt_view_rects_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B, int nviews,
-                                      const uint8_t* __restrict__ levels, int4* __restrict__ rects) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nviews) return;
+// Sparse framebuffer gather.  mrt_view_spans_kernel: one thread per (view, tile row) evaluates
+// mrt_view_span.  mrt_fill_outside_kernel (receiving side): background into every tile outside its
+// row's span — exactly the tiles the senders skip.  Same tile geometry as the march.
+__global__ void __launch_bounds__(128)
+mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B, int nviews,
+                      const uint8_t* __restrict__ levels, int2* __restrict__ spans) {
+  const int band = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  const int ty = mrt_tiles_y_(P.H);
+  if (band >= ty || v >= nviews) return;
   const ActiveBox A = mrt_active_box(P, levels);
-  rects[v] = mrt_view_rect(P, B.cam[v], A);
+  spans[(size_t)v * ty + band] = mrt_view_span(P, B.cam[v], A, band);
 }
 __global__ void __launch_bounds__(256)
-mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int4* __restrict__ rects, int nviews,
+mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int2* __restrict__ spans, int nviews,
                         float4* __restrict__ out) {
   // one WARP per tile (two 512-byte warp stores), grid-stride over (view, tile)
   const float4 bgp = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
                              : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
   const int lane = threadIdx.x & 31;
-  const int ntiles = P.tile_end - P.tile_begin;
+  const int ntiles = P.tile_end - P.tile_begin, ty = mrt_tiles_y_(P.H);
   const size_t total = (size_t)ntiles * nviews;
   const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
   for (size_t m = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < total; m += nwarps) {
     const int view = (int)(m / (size_t)ntiles), tile = P.tile_begin + (int)(m - (size_t)view * ntiles);
     int px, py;
     mrt_pixel_of_tile_lane_fast(P, tile, lane, &px, &py);                 // lanes 0..31 = the tile's upper half
-    if (mrt_tile_in_rect(__ldg(rects + view), px & ~MRT_TILE_MASK, py & ~MRT_TILE_MASK)) continue;
+    if (mrt_tile_in_span(__ldg(spans + (size_t)view * ty + (py >> MRT_TILE_SHIFT)), px & ~MRT_TILE_MASK)) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int y = py + 4 * h;
@@ -319,33 +321,35 @@ mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int4* __restric
     }
   }
 }
-cudaError_t mrt_launch_view_rects(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* rects,
+cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* spans,
                                   cudaStream_t st) {
+  const int ty = mrt_tiles_y_(P.H);
   for (int v0 = 0; v0 < nviews; v0 += MRT_MAX_VIEWS) {
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     CamBatch B;
     for (int v = 0; v < nv; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)(v0 + v) * 12 + i];
-    mrt_view_rects_kernel<<<1, MRT_MAX_VIEWS, 0, st>>>(P, B, nv, levels, reinterpret_cast<int4*>(rects) + v0);
+    mrt_view_spans_kernel<<<dim3((ty + 127) / 128, nv), 128, 0, st>>>(P, B, nv, levels,
+                                                                     reinterpret_cast<int2*>(spans) + (size_t)v0 * ty);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
-cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* rects, float* out_rgba, cudaStream_t st) {
+cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0 || nviews <= 0) return cudaSuccess;
   size_t grid = ((size_t)ntiles * nviews + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
-  mrt_fill_outside_kernel<<<(int)grid, 256, 0, st>>>(P, reinterpret_cast<const int4*>(rects), nviews, (float4*)out_rgba);
+  mrt_fill_outside_kernel<<<(int)grid, 256, 0, st>>>(P, reinterpret_cast<const int2*>(spans), nviews, (float4*)out_rgba);
   return cudaGetLastError();
 }
 
 cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
-                                      const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* rects,
+                                      const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* spans,
                                       cudaStream_t st) {
-  if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (rects offsets go with it)
+  if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (span offsets go with it)
   StripTargets S = {};
-  S.rects = reinterpret_cast<const int4*>(rects);
+  S.spans = reinterpret_cast<const int2*>(spans);
   g_strips = &S;
   cudaError_t e = mrt_launch_forward(P, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
                                      nullptr, st);

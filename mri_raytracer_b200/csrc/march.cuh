@@ -56,11 +56,12 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // Sort-last exchange fused into the march: image row y belongs to strip y / rows, whose pixels go
 // to base[strip] (a peer-mapped buffer of the strip's owner rank) instead of the local image.
 #define MRT_MAX_STRIPS 16
-// rects (optional, sparse framebuffer gather): per view of the launch an int4 (x0, y0, x1, y1),
-// the inclusive pixel rectangle outside which every ray certainly misses the active-brick box
-// (mrt_view_rect).  Tiles outside it are NOT stored by the march: the owner of the image fills
-// them with the background itself (mrt_fill_outside_rects), from the same rectangles.
-struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int4* rects; };
+// spans (optional, sparse framebuffer gather): per view of the launch and per tile row an int2
+// (x0, x1), the inclusive pixel span outside which every ray of that row band certainly misses the
+// active-brick box (mrt_view_span); tiles_y entries per view.  Tiles outside are NOT stored by the
+// march: the owner of the image fills them with the background itself (mrt_fill_outside_spans),
+// from the same spans.
+struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; };
 
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
@@ -198,17 +199,21 @@ __device__ __forceinline__ bool mrt_ray_may_hit(const KParams& P, const float* _
   return tout >= fmaxf(tin, 0.0f);
 }
 
-// Screen rectangle of the active-brick box for one camera: project the 8 corners of the box widened by
-// MRT_RECT_MARGIN voxels (> MRT_BOX_MARGIN, so a ray the slab test lets through always lies inside)
-// and round outward by one pixel.  Deterministic in (P, cam, box): the sender of a sparse gather
-// and the owner of the image evaluate it independently and get the same integers.
-#define MRT_RECT_MARGIN 0.75f
-__device__ __forceinline__ int4 mrt_view_rect(const KParams& P, const float* __restrict__ cam, const ActiveBox& A) {
+// Screen footprint of the active-brick box for one camera, as one x-span per 8-pixel row band
+// (tile row): the 8 corners of the box widened by MRT_SPAN_MARGIN voxels (> MRT_BOX_MARGIN, so a ray
+// the slab test lets through always lies inside) are projected, and the convex hull's x-extent
+// inside the band is the extent of the 12 projected edges clipped to the band (the hull's boundary
+// is made of edges; the others lie inside), rounded outward by one pixel.  Deterministic in
+// (P, cam, box): the sender of a sparse gather and the owner of the image evaluate it
+// independently and get the same integers.  Empty span: x0 > x1.
+#define MRT_SPAN_MARGIN 0.75f
+__device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __restrict__ cam, const ActiveBox& A,
+                                              int band) {
   const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
-  if (A.hi[0] < A.lo[0]) return make_int4(1, 1, 0, 0);                     // no active brick: empty rectangle
-  const float m = MRT_RECT_MARGIN - MRT_BOX_MARGIN;
+  if (A.hi[0] < A.lo[0]) return make_int2(1, 0);                           // no active brick
+  const float m = MRT_SPAN_MARGIN - MRT_BOX_MARGIN;
   const float aspect = (float)P.W / fmaxf(1.0f, (float)P.H);
-  float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+  float cx[8], cy[8];
   bool behind = false;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -223,21 +228,40 @@ __device__ __forceinline__ int4 mrt_view_rect(const KParams& P, const float* __r
     if (P.ortho) {
       uvx = xc / (aspect * P.halfH); uvy = -yc / P.halfH;
     } else {
-      if (!(zc > 1e-4f)) { behind = true; continue; }
-      uvx = (xc / zc) * P.focal / aspect; uvy = -(yc / zc) * P.focal;
+      if (!(zc > 1e-4f)) { behind = true; uvx = uvy = 0.0f; }
+      else { uvx = (xc / zc) * P.focal / aspect; uvy = -(yc / zc) * P.focal; }
     }
-    const float px = (uvx + 1.0f) * 0.5f * (float)P.W - 0.5f, py = (uvy + 1.0f) * 0.5f * (float)P.H - 0.5f;
-    xmin = fminf(xmin, px); xmax = fmaxf(xmax, px); ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
+    cx[c] = (uvx + 1.0f) * 0.5f * (float)P.W - 0.5f; cy[c] = (uvy + 1.0f) * 0.5f * (float)P.H - 0.5f;
   }
-  if (behind) return make_int4(0, 0, P.W - 1, P.H - 1);                    // the box reaches behind the eye: everything
+  if (behind) return make_int2(0, P.W - 1);                                // the box reaches behind the eye: everything
+  const float ylo = (float)(band << MRT_TILE_SHIFT) - 1.0f, yhi = (float)((band << MRT_TILE_SHIFT) + MRT_TILE_EDGE);
+  float xmin = 3.0e38f, xmax = -3.0e38f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (c & (1 << a)) continue;                                          // each edge once: c -> c | (1 << a)
+      const int d = c | (1 << a);
+      const float y0 = cy[c], y1 = cy[d], x0 = cx[c], x1 = cx[d];
+      if ((y0 < ylo && y1 < ylo) || (y0 > yhi && y1 > yhi)) continue;
+      const float dy = y1 - y0;
+      float t0 = 0.0f, t1 = 1.0f;
+      if (fabsf(dy) > 1e-12f) {
+        const float ta = (ylo - y0) / dy, tb = (yhi - y0) / dy;
+        t0 = fmaxf(0.0f, fminf(ta, tb)); t1 = fminf(1.0f, fmaxf(ta, tb));
+      }
+      const float xa = x0 + t0 * (x1 - x0), xb = x0 + t1 * (x1 - x0);
+      xmin = fminf(xmin, fminf(xa, xb)); xmax = fmaxf(xmax, fmaxf(xa, xb));
+    }
+  }
+  if (!(xmin <= xmax)) return make_int2(1, 0);
   const float lim = 1.0e8f;
-  const int x0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), y0 = max(0, (int)floorf(fmaxf(ymin, -lim)) - 1);
-  const int x1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1), y1 = min(P.H - 1, (int)ceilf(fminf(ymax, lim)) + 1);
-  return make_int4(x0, y0, x1, y1);
+  const int x0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), x1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1);
+  return make_int2(x0, x1);
 }
-// does the 8x8 tile with top-left pixel (tx0, ty0) intersect the rectangle?
-__device__ __forceinline__ bool mrt_tile_in_rect(int4 r, int tx0, int ty0) {
-  return tx0 <= r.z && tx0 + (MRT_TILE_EDGE - 1) >= r.x && ty0 <= r.w && ty0 + (MRT_TILE_EDGE - 1) >= r.y;
+// does the 8x8 tile with left pixel column tx0 intersect its row band's span?
+__device__ __forceinline__ bool mrt_tile_in_span(int2 sp, int tx0) {
+  return tx0 <= sp.y && tx0 + (MRT_TILE_EDGE - 1) >= sp.x;
 }
 
 // ---- voxel vector types -------------------------------------------------------------

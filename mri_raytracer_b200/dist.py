@@ -114,10 +114,10 @@ class PeerFramebuffer:
     so the transfer overlaps the march of the following rays and there is no separate collective
     on the data path - only one barrier per batch.
 
-    ``sparse=True`` (default): tiles outside a view's *rectangle* — the screen bounding box of the
-    active bricks, a deterministic function of (camera, params, occupancy) that every rank computes
-    for itself (``mrt_view_rects``) — are not sent; the root fills them with the background on a
-    side stream while everybody marches (``mrt_fill_outside_rects``; disjoint pixels, so no ordering
+    ``sparse=True`` (default): tiles outside a view's *spans* — per tile row the x-extent of the
+    projected active-brick box, a deterministic function of (camera, params, occupancy) that every
+    rank computes for itself (``mrt_view_spans``) — are not sent; the root fills them with the
+    background on a side stream while everybody marches (``mrt_fill_outside_spans``; disjoint pixels, so no ordering
     is needed).  More than half of a frame is background, and the root's NVLink ingress (7 ranks x
     frames) is what bounds the dense gather at 8 GPUs.  The root needs the cameras of ALL views
     (``cams_all`` of :func:`render_views_to`).
@@ -142,8 +142,9 @@ class PeerFramebuffer:
                 self.p2p = True
                 self.sparse = bool(sparse)
                 if self.sparse:
-                    self.rects = torch.empty((self.Vloc, 4), dtype=torch.int32, device=device)
-                    self.rects_all = torch.empty((self.R * self.Vloc, 4), dtype=torch.int32, device=device)
+                    ty = tiles.tiles_y(H)
+                    self.spans = torch.empty((self.Vloc, ty, 2), dtype=torch.int32, device=device)
+                    self.spans_all = torch.empty((self.R * self.Vloc, ty, 2), dtype=torch.int32, device=device)
                     self.side = torch.cuda.Stream(device=device)
             except Exception as e:                      # pragma: no cover - depends on the platform
                 self.why = f"{type(e).__name__}: {e}"
@@ -199,16 +200,17 @@ def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: Re
         plan = volume.sparse_plan(Pm, list(cams_local), tf)
         if plan is not None:
             packed, Cn, Pe, bits = plan
+            api.view_spans(Pe, list(cams_local), Cn, bits, out=fb.spans)
+            api.render_forward_batch_sparse(Pe, list(cams_local), packed, Cn, tf, bits, fb.targets().data_ptr(), fb.spans)
             if fb.rank == fb.root:
-                # background of ALL views outside their rectangles, on a side stream, while everybody marches
+                # background of ALL views outside their rectangles, on a side stream, while everybody
+                # marches (queued after the root's own march so that its launch is not delayed)
                 ev = torch.cuda.Event(); ev.record()
                 with torch.cuda.stream(fb.side):
-                    fb.side.wait_event(ev)                                   # the classify above
-                    api.view_rects(Pe, list(cams_all), Cn, bits, out=fb.rects_all)
-                    api.fill_outside_rects(Pe, fb.rects_all, fb.local)
+                    fb.side.wait_event(ev)
+                    api.view_spans(Pe, list(cams_all), Cn, bits, out=fb.spans_all)
+                    api.fill_outside_spans(Pe, fb.spans_all, fb.local)
                     fb._fill_done = torch.cuda.Event(); fb._fill_done.record()
-            api.view_rects(Pe, list(cams_local), Cn, bits, out=fb.rects)
-            api.render_forward_batch_sparse(Pe, list(cams_local), packed, Cn, tf, bits, fb.targets().data_ptr(), fb.rects)
             return
     _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
 
