@@ -330,9 +330,13 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
 
 // sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
+// The 8 corners of a cell, fetched (mrt_fetch) separately from their interpolation (mrt_interp) so
+// that a kernel can issue the loads of the NEXT slot before the dependent arithmetic of this one.
+template <int NCH, bool HALF> struct Corners { typename VoxT<NCH, HALF>::T v[8]; };
+
 template <int NCH, bool HALF = false>
-__device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
-                                                const Cell& c) {
+__device__ __forceinline__ Corners<NCH, HALF> mrt_fetch(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
+                                                       const Cell& c) {
   typedef typename VoxT<NCH, HALF>::T VT;
   // element index straight from the magic-number bits: the three -0x4b000000 corrections and the
   // shard offset are one precomputed constant (uint32 wrap-around is exact)
@@ -342,24 +346,38 @@ __device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename
   const VT* p1 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchY * sizeof(VT));
   const VT* p2 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchZ * sizeof(VT));
   const VT* p3 = reinterpret_cast<const VT*>(q0 + ((size_t)P.pitchY + (size_t)P.pitchZ) * sizeof(VT));
-  const VT v000 = __ldg(p0), v100 = __ldg(p0 + 1);
-  const VT v010 = __ldg(p1), v110 = __ldg(p1 + 1);
-  const VT v001 = __ldg(p2), v101 = __ldg(p2 + 1);
-  const VT v011 = __ldg(p3), v111 = __ldg(p3 + 1);
+  Corners<NCH, HALF> k;
+  k.v[0] = __ldg(p0); k.v[1] = __ldg(p0 + 1);
+  k.v[2] = __ldg(p1); k.v[3] = __ldg(p1 + 1);
+  k.v[4] = __ldg(p2); k.v[5] = __ldg(p2 + 1);
+  k.v[6] = __ldg(p3); k.v[7] = __ldg(p3 + 1);
+  return k;
+}
+
+template <int NCH, bool HALF = false>
+__device__ __forceinline__ float mrt_interp(const KParams& P, const Corners<NCH, HALF>& k, const Cell& c) {
   if (NCH == 1) {
     // one modality: the (linear) window scale is applied once, after the interpolation
-    const float f0 = mrt_scalar(v000), f1 = mrt_scalar(v100), f2 = mrt_scalar(v010), f3 = mrt_scalar(v110);
-    const float f4 = mrt_scalar(v001), f5 = mrt_scalar(v101), f6 = mrt_scalar(v011), f7 = mrt_scalar(v111);
+    const float f0 = mrt_scalar(k.v[0]), f1 = mrt_scalar(k.v[1]), f2 = mrt_scalar(k.v[2]), f3 = mrt_scalar(k.v[3]);
+    const float f4 = mrt_scalar(k.v[4]), f5 = mrt_scalar(k.v[5]), f6 = mrt_scalar(k.v[6]), f7 = mrt_scalar(k.v[7]);
     const float s = lerpf(lerpf(lerpf(f0, f1, c.fx), lerpf(f2, f3, c.fx), c.fy),
                           lerpf(lerpf(f4, f5, c.fx), lerpf(f6, f7, c.fx), c.fy), c.fz);
     return fmaf(s, P.wq[0], P.wbias);
   } else {
-    const float c000 = foldv(mrt_f32(v000), P), c100 = foldv(mrt_f32(v100), P), c010 = foldv(mrt_f32(v010), P), c110 = foldv(mrt_f32(v110), P);
-    const float c001 = foldv(mrt_f32(v001), P), c101 = foldv(mrt_f32(v101), P), c011 = foldv(mrt_f32(v011), P), c111 = foldv(mrt_f32(v111), P);
+    const float c000 = foldv(mrt_f32(k.v[0]), P), c100 = foldv(mrt_f32(k.v[1]), P), c010 = foldv(mrt_f32(k.v[2]), P), c110 = foldv(mrt_f32(k.v[3]), P);
+    const float c001 = foldv(mrt_f32(k.v[4]), P), c101 = foldv(mrt_f32(k.v[5]), P), c011 = foldv(mrt_f32(k.v[6]), P), c111 = foldv(mrt_f32(k.v[7]), P);
     const float s = lerpf(lerpf(lerpf(c000, c100, c.fx), lerpf(c010, c110, c.fx), c.fy),
                           lerpf(lerpf(c001, c101, c.fx), lerpf(c011, c111, c.fx), c.fy), c.fz);
     return s + P.wbias;
   }
+}
+
+// sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
+// raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
+template <int NCH, bool HALF = false>
+__device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
+                                                const Cell& c) {
+  return mrt_interp<NCH, HALF>(P, mrt_fetch<NCH, HALF>(P, vol, c), c);
 }
 
 // sampleLabel (brats_rt.slang:78-83): round half away from zero.
