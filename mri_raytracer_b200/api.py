@@ -472,7 +472,7 @@ class Volume:
 # ----------------------------------------------------------------------------- autograd
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold):
+    def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold, tile_range=None):
         Cn = planar.shape[0]
         fold = bool(fold) and Cn > 1
         want_occ = bool(P.skipEmpty) and P.tMode == "indexed"
@@ -492,7 +492,12 @@ class _RenderFn(torch.autograd.Function):
             bits = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any)
             if Ce == 1:
                 flat = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any, flat=True)
-        out = render_forward(Pe, packed, Ce, tf, bits, labels, preds)
+        out = None
+        if tile_range is not None:      # a rank's share of the frame: the other pixels are exact zeros
+            W, H = P.imageSize
+            out = torch.zeros((H, W, 4), dtype=torch.float32, device=planar.device)
+        out = render_forward(Pe, packed, Ce, tf, bits, labels, preds, out=out, tile_range=tile_range)
+        ctx.tile_range = tile_range
         ctx.P, ctx.Pe, ctx.Cn, ctx.Ce, ctx.fold = P, Pe, Cn, Ce, fold
         ctx.mm, ctx.flat = mm, flat
         ctx.labels, ctx.preds = labels, preds
@@ -507,16 +512,17 @@ class _RenderFn(torch.autograd.Function):
         want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
         dvol, dtf = render_backward(ctx.Pe, packed, ctx.Ce, tf, ctx.labels, ctx.preds, out,
                                     g.contiguous(), want_dvol=want_vol, want_dtf=want_tf,
-                                    flat_levels=ctx.flat, minmax=ctx.mm)
+                                    flat_levels=ctx.flat, minmax=ctx.mm, tile_range=ctx.tile_range)
         gvol = None
         if want_vol:
             gvol = unfold_grad(dvol, ctx.P, ctx.Cn) if ctx.fold else unpack_volume(dvol, ctx.Cn, ctx.P.dims)
-        return gvol, (dtf if want_tf else None), None, None, None, None
+        return gvol, (dtf if want_tf else None), None, None, None, None, None
 
 
 def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Optional[torch.Tensor],
            params: RenderParams, labels: Optional[torch.Tensor] = None,
-           preds: Optional[torch.Tensor] = None, fold: bool = True) -> torch.Tensor:
+           preds: Optional[torch.Tensor] = None, fold: bool = True,
+           tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """Render one frame: -> float32 ``[H, W, 4]`` (row 0 = top of the image).
 
     volume : ``[C,Z,Y,X]`` CUDA fp32 tensor (differentiable) or a prepared :class:`Volume`.
@@ -527,6 +533,8 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
     labels, preds : optional int32 ``[Z,Y,X]`` overlays (gLabels / gPreds).
     fold   : tensor input only — blend the modalities once per voxel before marching
              (see :class:`Volume`); ``False`` blends per sample like the reference shader.
+    tile_range : render (and differentiate) only tiles ``[begin, end)``; the other pixels of the
+             returned image are zero (image-space data parallelism, ``dist.render_differentiable``).
     Differentiable w.r.t. ``volume`` and ``tf`` when ``volume`` is a tensor.
     """
     P = params if camera is None else params.with_camera(camera)
@@ -540,6 +548,10 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
         if tuple(P.dims) != tuple(V.global_dims):
             raise ValueError(f"params.dims {P.dims} != volume dims {V.global_dims}")
         P.validate()
+        if tile_range is not None:
+            W, H = P.imageSize
+            out = torch.zeros((H, W, 4), dtype=torch.float32, device=V.device)
+            return V.forward(P, tf, out=out, tile_range=tile_range, labels=labels, preds=preds)
         return V.forward(P, tf, labels=labels, preds=preds)
     _need_cuda(volume, "volume", torch.float32)
     if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
@@ -552,7 +564,7 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
             _need_cuda(lab, name, torch.int32)
             if tuple(lab.shape) != (Z, Y, X):
                 raise ValueError(f"{name} must be [Z,Y,X]")
-    return _RenderFn.apply(volume, tf, P, labels, preds, fold)
+    return _RenderFn.apply(volume, tf, P, labels, preds, fold, tile_range)
 
 
 def render_views(volume: Volume, cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,

@@ -215,6 +215,57 @@ def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: Re
     _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
 
 
+# ----------------------------------------------------------------------------- differentiable, image space
+def render_differentiable(volume: torch.Tensor, cam, tf: Optional[torch.Tensor], P: RenderParams, group=None,
+                          render_fn: Optional[Callable] = None, **kw) -> torch.Tensor:
+    """Differentiable rendering, data-parallel over screen tiles: the
+    volume and TF are replicated, rank r renders — and differentiates — tile range
+    ``tiles.rank_tile_range(ntiles, r, R)``, and the frame is assembled with ONE differentiable
+    ``all_reduce(SUM)`` (the ranks' images are disjoint and zero elsewhere).  Every rank gets the
+    whole ``[H,W,4]`` image and may compute any loss on it; after ``loss.backward()`` each rank holds
+    the gradient contribution of ITS tiles — finish with :func:`allreduce_gradients` (the volume-
+    sized ``all_reduce`` of dL/dvolume and the tiny one of dL/dtf), exactly like data-parallel
+    training.  ``render_fn(volume, tf, P, tile_range) -> [H,W,4]`` replaces the CUDA renderer
+    (CPU/gloo tests inject the oracle)."""
+    rank, R = _world(group)
+    Pc = P.with_camera(cam) if cam is not None else P
+    W, H = Pc.imageSize
+    tr = tiles.rank_tile_range(tiles.tile_count(W, H), rank, R)
+    if render_fn is not None:
+        part = render_fn(volume, tf, Pc, tr)
+    else:
+        from . import api
+        part = api.render(volume, None, tf, Pc, tile_range=tr, **kw)
+    if R == 1:
+        return part
+    import torch.distributed.nn.functional as dfn
+    # every rank evaluates the same loss on the whole image, so the upstream gradient of the summed
+    # frame arrives R times through the differentiable all_reduce: pre-divide the local part's path
+    return _ScaleGrad.apply(dfn.all_reduce(part, op=dist.ReduceOp.SUM, group=group if group is not None else dist.group.WORLD),
+                            1.0 / R)
+
+
+class _ScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.s, None
+
+
+def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None):
+    """``all_reduce(SUM)`` of the ``.grad`` of every tensor that has one (dL/dvolume, dL/dtf)."""
+    _, R = _world(group)
+    if R == 1:
+        return
+    for t in tensors:
+        if t is not None and t.grad is not None:
+            dist.all_reduce(t.grad, op=dist.ReduceOp.SUM, group=group)
+
+
 # ----------------------------------------------------------------------------- sort-last
 def shard_grid(nranks: int) -> Tuple[int, int, int]:
     """Sub-box grid (gx,gy,gz) with gx*gy*gz == nranks, as cubic as possible (8 -> 2x2x2)."""

@@ -174,3 +174,67 @@ def test_composite_kernel_matches_torch(cuda):
     check(lib().mrt_composite_over(p.data_ptr(), K, o.data_ptr(), n, bg.ctypes.data, 1, out.data_ptr(),
                                    torch.cuda.current_stream().cuda_stream))
     assert (out.cpu() - want).abs().max() <= 1e-6
+
+
+# ----------------------------------------------------------------------------- differentiable, data-parallel tiles
+def _oracle_part(volume, tf, P, tile_range):
+    """render_fn for dist.render_differentiable: the differentiable oracle on the pixels of a tile range."""
+    from oracle import oracle_torch as O
+    from mri_raytracer_b200 import tiles
+    W, H = P.imageSize
+    xs, ys = [], []
+    for t in range(*tile_range):
+        for lane in range(64):
+            x, y = tiles.pixel_of_tile_lane(t, lane, W)
+            if x < W and y < H:
+                xs.append(x); ys.append(y)
+    out = torch.zeros((H, W, 4), dtype=torch.float32)
+    if xs:
+        px, py = torch.tensor(xs), torch.tensor(ys)
+        out = out.index_put((py, px), O.render(volume, replace(P, tfMode=1), tf=tf, pixels=(px, py)))
+    return out
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mri_raytracer_b200 import dist as mdist
+        from mri_raytracer_b200.synth import ramp_tf
+        from scenes import small_scene
+        vol, _, P = small_scene(C=2, dims=(14, 12, 10), W=19, H=13, seed=5)
+        tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
+        v = vol.clone().requires_grad_(True); t = tf.clone().requires_grad_(True)
+        img = mdist.render_differentiable(v, None, t, P, render_fn=_oracle_part)
+        target = torch.linspace(0, 1, img.numel()).reshape(img.shape)
+        ((img - target) ** 2).mean().backward()
+        mdist.allreduce_gradients([v, t])
+        if rank == 0:
+            ret.put((img.detach().numpy(), v.grad.numpy(), t.grad.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_differentiable_tiles_world2_gradients_match_single_process():
+    from oracle import oracle_torch as O
+    from mri_raytracer_b200.synth import ramp_tf
+    from scenes import small_scene
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    img, gv, gt = ret.get()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    vol, _, P = small_scene(C=2, dims=(14, 12, 10), W=19, H=13, seed=5)
+    tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
+    v = vol.clone().requires_grad_(True); t = tf.clone().requires_grad_(True)
+    ref = O.render(v, replace(P, tfMode=1), tf=t)
+    target = torch.linspace(0, 1, ref.numel()).reshape(ref.shape)
+    ((ref - target) ** 2).mean().backward()
+    assert np.array_equal(img, ref.detach().numpy())
+    assert np.abs(gv - v.grad.numpy()).max() <= 1e-6 * max(1.0, float(v.grad.abs().max()))
+    assert np.abs(gt - t.grad.numpy()).max() <= 1e-5 * max(1.0, float(t.grad.abs().max()))

@@ -94,3 +94,27 @@ def test_backward_only_tf_or_only_volume(cuda):
     api.render(vol.cuda(), None, t2, P).sum().backward()
     # atomics make the summation order run-dependent: compare to 1e-5 relative, not bitwise
     assert _rel(v2.grad, gv) <= 1e-5 and _rel(t2.grad, gt) <= 1e-5
+
+
+def test_tile_range_gradients_sum_to_the_full_gradient(cuda):
+    """api.render(..., tile_range=...) — the per-rank share of dist.render_differentiable: images of
+    disjoint tile ranges add up to the frame bit for bit, and their gradients to the full gradient."""
+    from mri_raytracer_b200 import tiles
+    vol, _, P = small_scene(C=4, dims=(24, 20, 18), W=37, H=29, seed=3)
+    P = replace(P, tfMode=1)
+    tf = ramp_tf(32, sigma_scale=20.0, cutoff=0.1)
+    g = torch.rand((29, 37, 4), generator=torch.Generator().manual_seed(1)).cuda()
+    v = vol.cuda().requires_grad_(True); t = tf.cuda().requires_grad_(True)
+    full = api.render(v, None, t, P)
+    (full * g).sum().backward()
+    gv, gt = v.grad.clone(), t.grad.clone()
+    nt = tiles.tile_count(37, 29)
+    v.grad = None; t.grad = None
+    acc = torch.zeros_like(full)
+    for r in range(3):
+        part = api.render(v, None, t, P, tile_range=tiles.rank_tile_range(nt, r, 3))
+        (part * g).sum().backward()
+        acc = acc + part.detach()
+    assert torch.equal(acc, full.detach())
+    assert float((v.grad - gv).abs().max()) <= 1e-5 * float(gv.abs().max())
+    assert float((t.grad - gt).abs().max()) <= 1e-5 * float(gt.abs().max())
