@@ -11,6 +11,7 @@ There is no CPU fallback: tensors must live on a CUDA device.
 from __future__ import annotations
 
 import ctypes as C
+import struct
 from dataclasses import replace
 from typing import Optional, Sequence, Tuple, Union
 
@@ -312,7 +313,7 @@ def folded_params(P: RenderParams) -> RenderParams:
 
 
 def _fold_key(P: RenderParams, Cn: int):
-    return (tuple(int(bool(e)) for e in P.volEnabled[:Cn]), tuple(float(np.float32(w)) for w in P.volWeight[:Cn]))
+    return (tuple(int(bool(e)) for e in P.volEnabled[:Cn]), struct.pack(f"<{Cn}f", *P.volWeight[:Cn]))
 
 
 # ----------------------------------------------------------------------------- Volume

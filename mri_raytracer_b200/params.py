@@ -36,6 +36,9 @@ def default_label_lut() -> np.ndarray:
 
 
 def _v3(x) -> Tuple[float, float, float]:
+    """3 floats rounded to float32 (what the kernel will see)."""
+    if isinstance(x, np.ndarray) and x.dtype == np.float32 and x.shape == (3,):
+        return (float(x[0]), float(x[1]), float(x[2]))
     a = np.asarray(x, dtype=np.float32).reshape(3)
     return (float(a[0]), float(a[1]), float(a[2]))
 
