@@ -298,7 +298,7 @@ def run_ours(args):
                 for v, c in enumerate(cams):
                     api.render_forward(Pe.with_camera(c), packed, Ce, tf, bits, out=frames[v])
             else:
-                api.render_forward_batch(Pe, cams, packed, Ce, tf, bits, out=frames)   # ONE launch, grid.y = view
+                volume.march_batch(Pe, cams, packed, Ce, tf, bits, out=frames)   # spans (tiny) + ONE march launch, grid.y = view
             if record_kernels:
                 b.record(); kern_ev.append((a, b))
         elif mode == "views":
@@ -478,7 +478,7 @@ def run_ours(args):
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             **({"INVALID": "--no-gather diagnosis run"} if args.no_gather else {}),
-            "gpu_launches": ((V if args.per_view else 1) + 1 + (1 if volume.fold else 0)) * args.steps,
+            "gpu_launches": ((V if args.per_view else 2) + 1 + (1 if volume.fold else 0)) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -261,12 +261,17 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
  * spans; the owner of the image calls mrt_fill_outside_spans on its local copy (any time: the two
  * write disjoint pixels).  Together == mrt_render_forward_batch, bit for bit, with the background
  * (typically > half of the frame) never crossing NVLink and its fill off the critical path.
- * Whole image only, skipping required.  `spans`: device int32[nviews][mrt_tiles_y(H)][2]. */
+ * Whole image only, skipping required.  `spans`: device int32[nviews][mrt_tiles_y(H)][2].
+ * store_outside != 0: the march DOES store the background of the outside tiles itself — the
+ * single-GPU fast path: the spans then only replace the per-ray box test of mrt_render_forward_batch
+ * by one load and two compares per warp (same image, bit for bit); in this mode `spans` is pure
+ * scratch: the call computes it itself (mrt_view_spans) before the march. */
 int mrt_view_spans(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C,
                    const uint8_t* skip_levels, int32_t* spans, void* stream);
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
-                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* spans, void* stream);
+                                    const uint8_t* skip_levels, float* out_rgba, int32_t* spans,
+                                    int32_t store_outside, void* stream);
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews,
                            float* out_rgba, void* stream);
 

@@ -103,7 +103,7 @@ PROTOTYPES = {
     "mrt_render_forward_batch": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _i32, _i32, _vp]),
     "mrt_view_spans": (C.c_int, [_PP, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_fill_outside_spans": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
     "mrt_backward_scratch_bytes": (_sz, [_i32]),
     "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -209,14 +209,16 @@ def view_spans(P: RenderParams, cams: Sequence, Cn: int, skip_levels: torch.Tens
 
 def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
                                 tf: Optional[torch.Tensor], skip_levels: torch.Tensor, out_ptr: int,
-                                spans: torch.Tensor):
+                                spans: torch.Tensor, store_outside: bool = False):
     """``mrt_render_forward_batch_sparse``: like :func:`render_forward_batch` into the (peer) image at
-    ``out_ptr``, except that tiles outside the views' spans are not stored."""
+    ``out_ptr``, except that tiles outside the views' spans are not stored (unless ``store_outside``:
+    then the spans only replace the per-ray box test)."""
     s = P.to_struct()
     arr = _camera_array(cams)
     check(lib().mrt_render_forward_batch_sparse(C.byref(s), arr.ctypes.data, len(cams), packed.data_ptr(), Cn,
                                                 _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
-                                                int(out_ptr), spans.data_ptr(), _stream()), "render_forward_batch_sparse")
+                                                int(out_ptr), spans.data_ptr(), int(bool(store_outside)), _stream()),
+          "render_forward_batch_sparse")
 
 
 def fill_outside_spans(P: RenderParams, spans: torch.Tensor, out: torch.Tensor):
@@ -369,6 +371,7 @@ class Volume:
         from .synth import world_box
         self.voxel_size, self.vol_min = world_box(self.global_dims, zooms)
         self._bits = None
+        self._spans = None
 
     def prepared(self, P: RenderParams):
         """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
@@ -454,8 +457,32 @@ class Volume:
         P = P.with_camera(cams[0])                     # projection (fov / ortho window) of the batch
         packed, Cn, Pe = self.prepared(P)
         bits = self._classify(P, Pe, Cn, tf)
-        return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
-                                    out_T=out_T, out_counts=out_counts, tile_range=tile_range)
+        return self.march_batch(Pe, cams, packed, Cn, tf, bits, out=out, out_T=out_T, out_counts=out_counts,
+                                tile_range=tile_range)
+
+    def march_batch(self, Pe: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
+                    tf: Optional[torch.Tensor], bits: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                    out_T: Optional[torch.Tensor] = None, out_counts: Optional[torch.Tensor] = None,
+                    tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """The march of a prepared batch.  Whole frames without overlays / counters take the span path:
+        ``mrt_view_spans`` (a few microseconds) turns the per-ray box test into one load per warp."""
+        W, H = Pe.imageSize
+        V = len(cams)
+        plain = (bits is not None and tile_range is None and out_T is None and out_counts is None and Pe.gamma == 1.0
+                 and not (self.labels is not None and Pe.showSeg) and not (self.preds is not None and Pe.showPred))
+        if not plain:
+            return render_forward_batch(Pe, cams, packed, Cn, tf, bits, self.labels, self.preds, out=out,
+                                        out_T=out_T, out_counts=out_counts, tile_range=tile_range)
+        if out is None:
+            out = torch.empty((V, H, W, 4), dtype=torch.float32, device=packed.device)
+        elif tuple(out.shape) != (V, H, W, 4) or not out.is_contiguous():
+            raise ValueError(f"out must be contiguous [V,H,W,4]={(V, H, W, 4)}, got {tuple(out.shape)}")
+        ty = _tiles.tiles_y(H)
+        if self._spans is None or self._spans.shape[0] < V or self._spans.shape[1] != ty:
+            self._spans = torch.empty((V, ty, 2), dtype=torch.int32, device=packed.device)
+        # store_outside: the call computes the spans into the scratch itself, then marches
+        render_forward_batch_sparse(Pe, cams, packed, Cn, tf, bits, out.data_ptr(), self._spans[:V], store_outside=True)
+        return out
 
     def sparse_plan(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor]):
         """Prepare a sparse batched march: -> (packed, Cn, Pe, skip_levels) or None if this

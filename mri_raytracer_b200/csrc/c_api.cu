@@ -351,7 +351,8 @@ int mrt_view_spans(const MrtParams* params, const MrtCamera* cams, int32_t nview
 }
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
-                                    const uint8_t* skip_levels, float* out_rgba, const int32_t* spans, void* stream) {
+                                    const uint8_t* skip_levels, float* out_rgba, int32_t* spans,
+                                    int32_t store_outside, void* stream) {
   MRT_REQUIRE(packed && out_rgba && spans && skip_levels, "render_forward_batch_sparse: null pointer");
   MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch_sparse: needs >= 1 camera");
   KParams K;
@@ -367,8 +368,13 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
   for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     pack_cams(cams + v0, nv, chunk);
+    if (store_outside)      // single-GPU fast path: the spans are this call's own scratch, computed here
+      e = mrt_launch_view_spans(K, chunk, nv, skip_levels, const_cast<int32_t*>(spans) + (size_t)v0 * 2 * mrt_tiles_y_(K.H),
+                                (cudaStream_t)stream);
+    if (e != cudaSuccess) break;
     e = mrt_launch_forward_sparse(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels,
-                                  out_rgba + (size_t)v0 * npix * 4, spans + (size_t)v0 * 2 * mrt_tiles_y_(K.H), (cudaStream_t)stream);
+                                  out_rgba + (size_t)v0 * npix * 4, spans + (size_t)v0 * 2 * mrt_tiles_y_(K.H), store_outside ? 1 : 0,
+                                  (cudaStream_t)stream);
   }
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_sparse");
 }

@@ -54,15 +54,23 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   // staging and the exact ray set-up; whole warps skip the set-up.
   bool maybe = inside;
   ActiveBox abox;
-  bool stored = true;                 // sparse gather: tiles outside the view's rectangle are filled by the image's owner
+  bool stored = true;                 // sparse gather: tiles outside the view's spans are filled by the image's owner
   if (SKIP) {
-    abox = mrt_active_box(P, levels);
     if (!GENERIC) {                                                        // the counting variant needs every exact n
-      if (S.spans != nullptr && tile < P.tile_end) {
-        const int2 sp = __ldg(S.spans + (size_t)view * mrt_tiles_y_(P.H) + (py >> MRT_TILE_SHIFT));
-        stored = mrt_tile_in_span(sp, px & ~MRT_TILE_MASK);                 // warp-uniform (one tile per warp pair)
+      if (S.spans != nullptr) {
+        // the view's precomputed spans (projected hull of the active box, mrt_view_spans) answer the
+        // question for the whole tile: one load and two compares instead of a per-ray slab test
+        bool in_span = false;
+        if (tile < P.tile_end) {
+          const int2 sp = __ldg(S.spans + (size_t)view * mrt_tiles_y_(P.H) + (py >> MRT_TILE_SHIFT));
+          in_span = mrt_tile_in_span(sp, px & ~MRT_TILE_MASK);              // warp-uniform (one tile per warp pair)
+        }
+        maybe = inside && in_span;
+        stored = in_span || (S.store_outside != 0);
+      } else {
+        abox = mrt_active_box(P, levels);
+        maybe = inside && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
       }
-      maybe = inside && stored && mrt_ray_may_hit(P, B.cam[view], px, py, abox);
       const bool cta_any = __syncthreads_or(maybe);
       if (!cta_any || !__any_sync(0xffffffffu, maybe)) {
         if (inside && stored) {
@@ -74,6 +82,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         maybe = false;                                                     // this warp only keeps the barrier company
       }
     }
+    if (GENERIC || S.spans != nullptr) abox = mrt_active_box(P, levels);   // (still needed to clip the slot ranges)
   }
 
   if (P.tfMode) mrt_tf_stage(s_tf, tf, P.tfN);
@@ -346,10 +355,11 @@ cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t*
 
 cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                       const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* spans,
-                                      cudaStream_t st) {
+                                      int store_outside, cudaStream_t st) {
   if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (span offsets go with it)
   StripTargets S = {};
   S.spans = reinterpret_cast<const int2*>(spans);
+  S.store_outside = store_outside;
   g_strips = &S;
   cudaError_t e = mrt_launch_forward(P, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
                                      nullptr, st);

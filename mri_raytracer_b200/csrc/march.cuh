@@ -59,9 +59,10 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // spans (optional, sparse framebuffer gather): per view of the launch and per tile row an int2
 // (x0, x1), the inclusive pixel span outside which every ray of that row band certainly misses the
 // active-brick box (mrt_view_span); tiles_y entries per view.  Tiles outside are NOT stored by the
-// march: the owner of the image fills them with the background itself (mrt_fill_outside_spans),
-// from the same spans.
-struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; };
+// march unless store_outside is set: the owner of the image fills them with the background itself
+// (mrt_fill_outside_spans), from the same spans.  With store_outside the spans only serve as the
+// (much cheaper) replacement of the per-ray box test: one LDG + two compares per warp.
+struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; int store_outside; };
 
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
