@@ -1,0 +1,117 @@
+"""BASELINE config 4: a batch of 64 orbit views at 2048x2048 over a 512^3 fp32 volume, image-space
+partition across 1/2/4/8 B200 with the framebuffer gathered on rank 0.
+
+    python tools/bench_cfg4.py                                   # one GPU
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_cfg4.py
+
+STRONG scaling: the 64 views are fixed; rank r renders views [r*64/R, (r+1)*64/R) in ONE batched
+launch and stores them straight into rank 0's peer-mapped framebuffer (dist.PeerFramebuffer, sparse
+gather: tiles outside the projected active-brick box are not sent, the root fills them).  Prints one
+JSON line: ms per 64-view batch (CUDA events, max over ranks), views/s, nominal samples/s, and a
+check of a few gathered views against local renders on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+from dataclasses import replace
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from mri_raytracer_b200 import OrbitalCamera, api, orbit_views  # noqa: E402
+from mri_raytracer_b200 import dist as mdist  # noqa: E402
+from mri_raytracer_b200.synth import make_brats_like, ramp_tf  # noqa: E402
+from scenes import framed_params  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--img", type=int, default=2048)
+    ap.add_argument("--views", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--dense-gather", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.views % world:
+        raise SystemExit("--views must be divisible by the number of GPUs")
+    dims = (args.dim,) * 3
+    vol = make_brats_like(1, dims, seed=5, device=dev)
+    tf = ramp_tf(256).to(dev)
+    P = replace(framed_params(dims, args.img, args.img, theta_deg=0.0), tfMode=1)
+    V = api.Volume(vol)
+    cam = V.frame_camera(OrbitalCamera(initial_phi=math.radians(80.0)))
+    cam.set_fov_degrees(70.0)
+    cams_all = orbit_views(cam, args.views)
+    Vloc = args.views // world
+    mine = cams_all[rank * Vloc:(rank + 1) * Vloc]
+
+    # nominal sample count of the whole batch (each rank counts its own views)
+    taken = 0
+    for c in mine:
+        _, _, counts = api.render_aux(V, c, tf, P)
+        taken += int(counts[..., 1].sum())
+    tot = torch.tensor([taken], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    taken = int(tot)
+
+    fb = mdist.PeerFramebuffer(Vloc, args.img, args.img, dev, sparse=not args.dense_gather) if world > 1 else None
+    frames = torch.empty((Vloc, args.img, args.img, 4), device=dev) if world == 1 else None
+
+    def batch():
+        if world == 1:
+            api.render_views(V, mine, tf, P, out=frames)
+        else:
+            mdist.render_views_to(fb, V, mine, tf, P, cams_all=cams_all)
+            fb.finish()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        batch()
+    barrier()
+    ms = []
+    for _ in range(args.reps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); batch(); b.record()
+        barrier()
+        ms.append(a.elapsed_time(b))
+    t = torch.tensor([sorted(ms)[len(ms) // 2]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_batch = float(t)
+    ok = None
+    if rank == 0:
+        got = frames if world == 1 else fb.frames()
+        ok = True
+        for v in (0, args.views // 2 + 1, args.views - 1):
+            ok &= bool(torch.equal(got[v], api.render(V, cams_all[v], tf, P)))
+        print(json.dumps(dict(cfg="cfg4", dims=dims, image=args.img, views=args.views, n_gpus=world, scaling="strong",
+                              gather=("none (single GPU)" if world == 1 else
+                                      ("peer stores, sparse" if (fb.p2p and fb.sparse) else
+                                       ("peer stores, dense" if fb.p2p else "NCCL all_gather"))),
+                              ms_per_batch=ms_batch, views_per_s=args.views * 1e3 / ms_batch,
+                              ms_per_view=ms_batch / args.views, nominal_samples_per_batch=taken,
+                              gsamples_per_s=taken / ms_batch / 1e6, gathered_views_equal_local_renders=ok,
+                              reps=args.reps)), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
