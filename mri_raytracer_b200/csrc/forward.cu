@@ -16,12 +16,15 @@
 #ifndef MRT_RUN_MIN
 #define MRT_RUN_MIN 1           // slots of known-active run a lane likes to keep ahead of itself
 #endif
+#ifndef MRT_FWD_MINB
+#define MRT_FWD_MINB 8          // resident CTAs per SM the register allocation aims for (single-channel variants)
+#endif
 #ifndef MRT_FWD_TPB
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
 #endif
 
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF>
-__global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 1024) / (64 * MRT_FWD_TPB))
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 128 * MRT_FWD_MINB) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
                const __grid_constant__ StripTargets S,

@@ -133,6 +133,11 @@ mrt_fold_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, si
 // the packed C=1 layout, keeps a running (min, max) per column and finally reduces 9 columns per
 // brick.  The halo rows are read twice (81/64), mostly from L2; the separate min/max pass over
 // the folded volume (and its 1.42x re-read) disappears.
+#ifndef MRT_FOLD_UNROLL
+#define MRT_FOLD_UNROLL 3
+#endif
+#define MRT_STR2(x) #x
+#define MRT_STR(x) MRT_STR2(x)
 #define MRT_FOLD_COLS 248          // 31 bricks of 8 columns (+1 halo column) per 256-thread CTA
 template <int C>
 __global__ void __launch_bounds__(256)
@@ -154,7 +159,7 @@ mrt_fold_occ_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_
   if (rd) {
     for (int lz = 0; lz < nz; ++lz) {
       const int z = z0 + lz;
-#pragma unroll 3
+_Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
       for (int ly = 0; ly < ny; ++ly) {
         const int y = y0 + ly;
         const size_t src = ((size_t)z * Y + y) * X + x;

@@ -58,3 +58,41 @@ def test_host_side_helpers_need_no_gpu(built_lib):
         assert built_lib.mrt_packed_volume_bytes(Cn, 240, 240, 155) == pz.value * 155 * 4 * Cn
     assert built_lib.mrt_brick_count(240, 240, 155) == 30 * 30 * 20
     assert built_lib.mrt_packed_volume_bytes(5, 8, 8, 8) == 0
+
+
+def test_packed_params_equal_field_by_field_ctypes():
+    """RenderParams.to_struct packs the 432 bytes in one struct.pack call; this rebuilds the same
+    struct field by field through ctypes and compares the bytes (layout, order, rounding)."""
+    import numpy as np
+    from dataclasses import replace
+    rng = np.random.default_rng(0)
+    base = RenderParams(imageSize=(321, 123), dims=(31, 17, 9))
+    cases = [base,
+             replace(base, eye=tuple(rng.normal(size=3)), U=tuple(rng.normal(size=3)), V=tuple(rng.normal(size=3)),
+                     W=tuple(rng.normal(size=3)), volMin=(-0.3, -0.2, -0.1), voxelSize=(0.01, 0.02, 0.03),
+                     stepSize=0.0123, nearT=0.4, farT=7.5, bgColor=(0.1, 0.2, 0.3), volEnabled=(1, 0, 1, 0),
+                     volWeight=(0.5, 1.5, 2.5, 3.5), ww=0.7, wl=0.3, intensityAlpha=1.7, gamma=2.2, showSeg=1, showPred=1,
+                     ortho=1, orthoHalfHeight=0.77, ertThreshold=0.02, maxSteps=99, tMode="accumulate", alphaMode=1,
+                     skipEmpty=0, tfMode=1, volDtype=1),
+             replace(base, shard=((1, 2, 3), (20, 10, 7)))]
+    for P in cases:
+        s = MrtParams()
+        s.imageSize[:] = [int(v) for v in P.imageSize]; s.fovY = P.fovY
+        for k in ("eye", "U", "V", "W", "volMin", "voxelSize", "bgColor"):
+            getattr(s, k)[:] = [float(np.float32(v)) for v in getattr(P, k)]
+        s.dims[:] = [int(v) for v in P.dims]
+        s.stepSize, s.nearT, s.farT = P.stepSize, P.nearT, P.farT
+        s.volEnabled[:] = [int(bool(v)) for v in P.volEnabled]; s.volWeight[:] = list(P.volWeight)
+        s.ww, s.wl, s.intensityAlpha = P.ww, P.wl, P.intensityAlpha
+        s.gamma, s.gradBoost, s.gradScale = P.gamma, P.gradBoost, P.gradScale
+        s.showSeg, s.showPred = int(bool(P.showSeg)), int(bool(P.showPred))
+        lut = np.asarray(P.lutColorAlpha, dtype=np.float32)
+        for i in range(8):
+            s.lutColorAlpha[i][:] = [float(v) for v in lut[i]]
+        s.ortho, s.orthoHalfHeight, s.ertThreshold, s.maxSteps = int(bool(P.ortho)), P.orthoHalfHeight, P.ertThreshold, P.maxSteps
+        s.tMode, s.alphaMode = (0 if P.tMode == "indexed" else 1), int(bool(P.alphaMode))
+        s.skipEmpty, s.tfMode, s.volDtype = int(bool(P.skipEmpty)), int(bool(P.tfMode)), P.volDtype
+        if P.shard is not None:
+            s.shardEnabled = 1; s.shardLo[:] = list(P.shard[0]); s.shardHi[:] = list(P.shard[1])
+        assert bytes(P.to_struct()) == bytes(s)
+    assert C.sizeof(_lib.MrtCamera) == 64
