@@ -265,10 +265,13 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
 }
 
 // ------------------------------------------------------------------------- dispatch
-static const StripTargets g_no_strips = {};
-static thread_local const StripTargets* g_strips = &g_no_strips;   // set only for the duration of one launch call
+static const StripTargets g_no_targets = {};      // plain [views][H][W] image, every tile stored
+static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S, const float* cams, int nviews,
+                                         int packed_ch, const void* vol, const float* tf, const uint8_t* levels,
+                                         const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
+                                         int32_t* out_counts, cudaStream_t st);
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false>
-static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const float* tf, const uint8_t* levels,
+static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, const StripTargets& S, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
@@ -276,17 +279,17 @@ static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, int nviews, c
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
   const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
   mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
-      P, B, *g_strips, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
+      P, B, S, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
 }
 
 template <int NCH>
-static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, int nviews, bool lab, bool skip, bool gen, const void* vol, const float* tf,
+static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, const StripTargets& T, int nviews, bool lab, bool skip, bool gen, const void* vol, const float* tf,
                                 const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                 float* o, float* oT, int32_t* oc, cudaStream_t st) {
 #define MRT_CASE(L, S, G) if (lab == L && skip == S && gen == G) \
-    return launch_fwd<NCH, L, S, G>(P, B, nviews, vol, tf, levels, labels, preds, o, oT, oc, st);
+    return launch_fwd<NCH, L, S, G>(P, B, T, nviews, vol, tf, levels, labels, preds, o, oT, oc, st);
   MRT_CASE(false, false, false) MRT_CASE(false, true, false)
   MRT_CASE(true, false, false)  MRT_CASE(true, true, false)
   MRT_CASE(false, false, true)  MRT_CASE(false, true, true)
@@ -363,11 +366,8 @@ cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int n
   StripTargets S = {};
   S.spans = reinterpret_cast<const int2*>(spans);
   S.store_outside = store_outside;
-  g_strips = &S;
-  cudaError_t e = mrt_launch_forward(P, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
-                                     nullptr, st);
-  g_strips = &g_no_strips;
-  return e;
+  return mrt_launch_forward_to(P, S, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
+                               nullptr, st);
 }
 
 cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const void* vol, const float* tf,
@@ -378,11 +378,8 @@ cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const voi
   StripTargets S = {};
   for (int i = 0; i < nstrips; ++i) S.base[i] = reinterpret_cast<float4*>(strip_out[i]);
   S.n = nstrips; S.rows = strip_rows;
-  g_strips = &S;
-  cudaError_t e = mrt_launch_forward(P, nullptr, 1, packed_ch, vol, tf, levels, nullptr, nullptr,
-                                     strip_out[0], nullptr, nullptr, st);
-  g_strips = &g_no_strips;
-  return e;
+  return mrt_launch_forward_to(P, S, nullptr, 1, packed_ch, vol, tf, levels, nullptr, nullptr, strip_out[0], nullptr,
+                               nullptr, st);
 }
 
 cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
@@ -399,6 +396,15 @@ cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, 
     }
     return cudaSuccess;
   }
+  return mrt_launch_forward_to(P, g_no_targets, cams, nviews, packed_ch, vol, tf, levels, labels, preds, out_rgba, out_T,
+                               out_counts, st);
+}
+
+// one launch (<= MRT_MAX_VIEWS views) with explicit output targets (strips / sparse spans)
+static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S, const float* cams, int nviews,
+                                         int packed_ch, const void* vol, const float* tf, const uint8_t* levels,
+                                         const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
+                                         int32_t* out_counts, cudaStream_t st) {
   CamBatch B;
   if (cams == nullptr) {
     nviews = 1;
@@ -412,15 +418,15 @@ cudaError_t mrt_launch_forward(const KParams& P, const float* cams, int nviews, 
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
   if (P.half) {            // fp16 voxels: single channel, no label overlays (c_api.cu checks)
     if (packed_ch != 1 || lab) return cudaErrorInvalidValue;
-    if (skip) return gen ? launch_fwd<1, false, true, true, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
-                         : launch_fwd<1, false, true, false, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    return gen ? launch_fwd<1, false, false, true, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
-               : launch_fwd<1, false, false, false, true>(P, B, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    if (skip) return gen ? launch_fwd<1, false, true, true, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
+                         : launch_fwd<1, false, true, false, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    return gen ? launch_fwd<1, false, false, true, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
+               : launch_fwd<1, false, false, false, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
   }
   switch (packed_ch) {
-    case 1: return dispatch_fwd<1>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    case 2: return dispatch_fwd<2>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    case 4: return dispatch_fwd<4>(P, B, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 1: return dispatch_fwd<1>(P, B, S, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 2: return dispatch_fwd<2>(P, B, S, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    case 4: return dispatch_fwd<4>(P, B, S, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
   }
   return cudaErrorInvalidValue;
 }
