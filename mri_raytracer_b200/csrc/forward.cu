@@ -50,7 +50,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   const bool inside = (tile < P.tile_end) && (px < P.W) && (py < P.H);
   const size_t pix = ((size_t)view * P.H + py) * P.W + px;
   float4* dst = out_rgba + pix;
-  if (S.n) { const int strip = py / S.rows; dst = S.base[strip] + ((size_t)(py - strip * S.rows) * P.W + px); }
+  if (S.n && inside) { const int strip = py / S.rows; dst = S.base[strip] + ((size_t)(py - strip * S.rows) * P.W + px); }
 
   // Cull against the active-brick box BEFORE any expensive work: a ray that cannot enter it is
   // pure background.  Whole CTAs of such rays (most of the frame outside the head) skip the LUT
