@@ -134,7 +134,7 @@ mrt_fold_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, si
 // brick.  The halo rows are read twice (81/64), mostly from L2; the separate min/max pass over
 // the folded volume (and its 1.42x re-read) disappears.
 #ifndef MRT_FOLD_UNROLL
-#define MRT_FOLD_UNROLL 3
+#define MRT_FOLD_UNROLL 9
 #endif
 #define MRT_STR2(x) #x
 #define MRT_STR(x) MRT_STR2(x)
