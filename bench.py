@@ -28,7 +28,6 @@ import subprocess
 import sys
 import threading
 import time
-from dataclasses import replace
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -372,7 +371,6 @@ def run_ours(args):
     # ---- same-run gather ceilings: random 32-byte-sector gathers over an
     # L2-resident (32 MiB) and an HBM-resident (4 GiB) buffer, mrt_gather_probe
     if roof is not None and not args.no_probe:
-        import ctypes as C
         from mri_raytracer_b200._lib import lib, check
         chk = torch.zeros(2, dtype=torch.float32, device=dev)
 

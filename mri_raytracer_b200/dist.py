@@ -18,7 +18,6 @@ backend (tests/test_dist_gloo.py injects the oracle there); the default is the C
 """
 from __future__ import annotations
 
-import math
 from dataclasses import replace
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -34,12 +33,6 @@ def _world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
-
-
-def _default_render_fn(volume, tf):
-    def fn(P: RenderParams, tile_range: Tuple[int, int], out: torch.Tensor):
-        volume.forward(replace(P, tfMode=1 if tf is not None else 0), tf, out=out, tile_range=tile_range)
-    return fn
 
 
 def _render_batch(volume, tf, P: RenderParams, cams: Sequence, tile_range: Tuple[int, int], out: torch.Tensor,
@@ -151,11 +144,6 @@ class PeerFramebuffer:
         if not self.p2p:
             self.local = torch.empty(self.shape, dtype=torch.float32, device=device)
             self.remote = self.local
-
-    def target(self, v_local: int) -> torch.Tensor:
-        """Where this rank's local view ``v_local`` must be written (root's memory when p2p)."""
-        buf = self.remote if self.p2p else self.local
-        return buf[self.rank * self.Vloc + v_local]
 
     def targets(self) -> torch.Tensor:
         """This rank's contiguous ``[Vloc,H,W,4]`` slice of the (root's, when p2p) framebuffer."""
