@@ -288,6 +288,10 @@ int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_
  *                dL/d intensityAlpha), ACCUMULATED into (caller zeroes)
  *   scratch    : device scratch of mrt_backward_scratch_bytes(tfN) bytes (privatised dL/dtf
  *                accumulators; zeroed by the call); required when dL_dtf != NULL
+ *   dL_dray    : optional float [H][W][6] = (dL/do, dL/dd) per ray, world units, with the sample
+ *                times t_i held fixed (docs/DifferentiableRendering.md section 9, :172-188:
+ *                dL/do = sum_i dL/dx_i, dL/dd = sum_i t_i dL/dx_i; dL/dx_i through the trilinear
+ *                gradient of section 6).  Caller zeroes it (rays that miss are not written).
  */
 size_t mrt_backward_scratch_bytes(int32_t tfN);
 int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C,
@@ -295,7 +299,7 @@ int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C,
                         const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds,
                         const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf, void* scratch,
+                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
 /* ------------------------------------------------ slab renderer (u8 volume)

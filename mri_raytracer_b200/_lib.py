@@ -106,7 +106,7 @@ PROTOTYPES = {
     "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_fill_outside_spans": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
     "mrt_backward_scratch_bytes": (_sz, [_i32]),
-    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _i32, _i32, _vp]),
     "mrt_render_slab_u8": (C.c_int, [_SP, _vp, _vp, _i32, _i32, _vp]),
     "mrt_decode_bc4": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

@@ -258,8 +258,9 @@ def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional
                     labels: Optional[torch.Tensor], preds: Optional[torch.Tensor], out_rgba: torch.Tensor,
                     dL_dout: torch.Tensor, want_dvol: bool = True, want_dtf: bool = True,
                     tile_range: Optional[Tuple[int, int]] = None, flat_levels: Optional[torch.Tensor] = None,
-                    minmax: Optional[torch.Tensor] = None):
-    """-> (dL/dvolume packed or None, dL/dtf [N,4] or None)."""
+                    minmax: Optional[torch.Tensor] = None, want_dray: bool = False):
+    """-> (dL/dvolume packed or None, dL/dtf [N,4] or None), plus dL/d(o,d) ``[H,W,6]`` as a third
+    element when ``want_dray``."""
     W, H = P.imageSize
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     dvol = torch.zeros_like(packed) if want_dvol else None
@@ -267,12 +268,31 @@ def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional
     dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_dtf else None
     scratch = torch.empty((lib().mrt_backward_scratch_bytes(ntf) // 4,), dtype=torch.float32,
                           device=packed.device) if want_dtf else None
+    dray = torch.zeros((H, W, 6), dtype=torch.float32, device=packed.device) if want_dray else None
     s = P.to_struct()
     check(lib().mrt_render_backward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
                                     _ptr(flat_levels), _ptr(minmax), _ptr(labels), _ptr(preds),
                                     out_rgba.data_ptr(), dL_dout.data_ptr(), _ptr(dvol), _ptr(dtf), _ptr(scratch),
-                                    t0, t1, _stream()), "render_backward")
-    return dvol, dtf
+                                    _ptr(dray), t0, t1, _stream()), "render_backward")
+    return (dvol, dtf, dray) if want_dray else (dvol, dtf)
+
+
+def ray_gradients(volume: "Volume", camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams,
+                  dL_dout: torch.Tensor) -> torch.Tensor:
+    """dL/d(ray origin), dL/d(ray direction) per pixel, ``[H,W,6]`` in world units, for an upstream
+    image gradient ``dL_dout [H,W,4]``: docs/DifferentiableRendering.md section 9 (:172-188) with the
+    sample times held fixed — dL/do = sum_i dL/dx_i, dL/dd = sum_i t_i dL/dx_i — the entry point of
+    camera / pose optimisation (for the pinhole camera dL/d eye = the sum of dL/do over the rays)."""
+    if not isinstance(volume, Volume):
+        raise TypeError("ray_gradients needs a prepared Volume")
+    P = params if camera is None else params.with_camera(camera)
+    P = replace(P, tfMode=1 if tf is not None else 0)
+    _need_cuda(dL_dout, "dL_dout", torch.float32)
+    packed, Cn, Pe = volume.prepared(P)
+    out = render_forward(Pe, packed, Cn, tf, volume._classify(P, Pe, Cn, tf), volume.labels, volume.preds)
+    _, _, dray = render_backward(Pe, packed, Cn, tf, volume.labels, volume.preds, out, dL_dout.contiguous(),
+                                 want_dvol=False, want_dtf=False, want_dray=True)
+    return dray
 
 
 # ----------------------------------------------------------------------------- fold

@@ -53,7 +53,8 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
                const float4* __restrict__ out_rgba,
                const float4* __restrict__ dL_dout,
                typename Vox<NCH>::T* __restrict__ dvol,
-               float4* __restrict__ dtf_priv) {
+               float4* __restrict__ dtf_priv,
+               float* __restrict__ dray) {
   typedef typename Vox<NCH>::T VT;
   extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels
   const int ntf = P.tfMode ? P.tfN : 2;
@@ -103,12 +104,14 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
   const uint32_t sY = P.pitchY, sZ = P.pitchZ;
   float T = 1.0f, prefix = 0.0f;
   int k = 0;
+  float gox = 0.0f, goy = 0.0f, goz = 0.0f, gdx = 0.0f, gdy = 0.0f, gdz = 0.0f;   // dL/do, dL/dd of this ray
 
   // one sample slot with its adjoint
   auto shade = [&](float t) {
     const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
     const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-    const float raw = mrt_sample_raw<NCH>(P, vol, c);
+    const Corners<NCH, false> cor = mrt_fetch<NCH, false>(P, vol, c);
+    const float raw = mrt_interp<NCH, false>(P, cor, c);
     const float val = mrt_window<GENERIC>(P, raw);
     if (P.tfMode || val > 0.0f) {
       int j0; float fr;
@@ -124,7 +127,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
         dtf_add(dtfp, j0, 1.0f - fr, dr, dg, db, dsig);
         if (fr != 0.0f) dtf_add(dtfp, min(j0 + 1, ntf - 1), fr, dr, dg, db, dsig);
       }
-      if (dvol != nullptr) {
+      if (dvol != nullptr || dray != nullptr) {
         const float4 d4 = s_tf[j0].delta;
         float dval = nm1 * (dr * d4.x + dg * d4.y + db * d4.z + dsig * d4.w);
         if (GENERIC) {
@@ -132,7 +135,19 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
         }
         // saturate: torch.clamp passes the gradient on the closed interval [0,1]
         const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval : 0.0f;
-        if (dv != 0.0f) {
+        if (dray != nullptr && dv != 0.0f) {
+          // docs/DifferentiableRendering.md section 9 (:172-188): x_i = o + t_i d with fixed t_i, so
+          // dL/do += dL/dx_i and dL/dd += t_i dL/dx_i, with dL/dx_i = dL/ds * ds/dx (section 6); an
+          // axis on which the position was clamped (:62) carries no gradient
+          float sx, sy, sz;
+          mrt_interp_grad<NCH, false>(P, cor, c, &sx, &sy, &sz);
+          const float wx = (ppx >= 0.0f && ppx <= hix) ? dv * sx / P.vs[0] : 0.0f;
+          const float wy = (ppy >= 0.0f && ppy <= hiy) ? dv * sy / P.vs[1] : 0.0f;
+          const float wz = (ppz >= 0.0f && ppz <= hiz) ? dv * sz / P.vs[2] : 0.0f;
+          gox += wx; goy += wy; goz += wz;
+          gdx = fmaf(t, wx, gdx); gdy = fmaf(t, wy, gdy); gdz = fmaf(t, wz, gdz);
+        }
+        if (dvol != nullptr && dv != 0.0f) {
           const uint32_t b = (uint32_t)c.ix() + (uint32_t)c.iy() * sY + (uint32_t)c.iz() * sZ;
           VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
           const float gx0 = 1.0f - c.fx, gy0 = 1.0f - c.fy, gz0 = 1.0f - c.fz;
@@ -214,6 +229,10 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
   } else {
     while (k < ray.n && T > thr) { shade(fmaf((float)k, dt, ray.t0)); ++k; }
   }
+  if (dray != nullptr) {                      // [H][W][6] = (dL/do, dL/dd); rays that returned early keep the caller's zeros
+    float* r = dray + pix * 6;
+    r[0] = gox; r[1] = goy; r[2] = goz; r[3] = gdx; r[4] = gdy; r[5] = gdz;
+  }
 }
 
 // dtf[i] += sum over the privatised copies
@@ -229,7 +248,7 @@ template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
 static cudaError_t launch_bwd(const KParams& P, const void* vol, const float* tf, const uint8_t* flat_levels,
                               const float* minmax, const int32_t* labels, const int32_t* preds,
                               const float* out_rgba, const float* dL_dout, void* dvol, float* dtf, void* scratch,
-                              cudaStream_t st) {
+                              float* dray, cudaStream_t st) {
   typedef typename Vox<NCH>::T VT;
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
@@ -242,7 +261,7 @@ static cudaError_t launch_bwd(const KParams& P, const void* vol, const float* tf
   }
   mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC><<<grid, 64 * MRT_BWD_TPB, smem, st>>>(
       P, (const VT*)vol, (const float4*)tf, flat_levels, (const float2*)minmax, labels, preds,
-      (const float4*)out_rgba, (const float4*)dL_dout, (VT*)dvol, dtf ? (float4*)scratch : nullptr);
+      (const float4*)out_rgba, (const float4*)dL_dout, (VT*)dvol, dtf ? (float4*)scratch : nullptr, dray);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (dtf) {
@@ -257,25 +276,27 @@ size_t mrt_bwd_scratch_bytes(int ntf) { return (size_t)MRT_DTF_COPIES * ntf * si
 template <int NCH, bool SKIP>
 static cudaError_t dispatch_bwd(const KParams& P, bool lab, bool gen, const void* vol, const float* tf,
                                 const uint8_t* fl, const float* mm, const int32_t* labels, const int32_t* preds,
-                                const float* o, const float* g, void* dvol, float* dtf, void* scr, cudaStream_t st) {
-  if (lab) return gen ? launch_bwd<NCH, true, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, st)
-                      : launch_bwd<NCH, true, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, st);
-  return gen ? launch_bwd<NCH, false, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, st)
-             : launch_bwd<NCH, false, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, st);
+                                const float* o, const float* g, void* dvol, float* dtf, void* scr, float* dray,
+                                cudaStream_t st) {
+  if (lab) return gen ? launch_bwd<NCH, true, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st)
+                      : launch_bwd<NCH, true, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st);
+  return gen ? launch_bwd<NCH, false, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st)
+             : launch_bwd<NCH, false, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st);
 }
 
 cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
                                 const uint8_t* flat_levels, const float* minmax,
                                 const int32_t* labels, const int32_t* preds, const float* out_rgba,
-                                const float* dL_dout, void* dvol, float* dtf, void* scratch, cudaStream_t st) {
+                                const float* dL_dout, void* dvol, float* dtf, void* scratch, float* dray,
+                                cudaStream_t st) {
   const bool lab = (P.showSeg || P.showPred);
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f);
   const bool skip = P.skip && flat_levels != nullptr && minmax != nullptr && P.tMode == 0 && packed_ch == 1;
   switch (packed_ch) {
-    case 1: return skip ? dispatch_bwd<1, true>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, st)
-                        : dispatch_bwd<1, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, st);
-    case 2: return dispatch_bwd<2, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, st);
-    case 4: return dispatch_bwd<4, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, st);
+    case 1: return skip ? dispatch_bwd<1, true>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st)
+                        : dispatch_bwd<1, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
+    case 2: return dispatch_bwd<2, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
+    case 4: return dispatch_bwd<4, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -400,10 +400,10 @@ size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tf
 int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
                         const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds, const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf, void* scratch,
+                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray,
                         int32_t tile_begin, int32_t tile_end, void* stream) {
   MRT_REQUIRE(packed && out_rgba && dL_dout, "render_backward: null pointer");
-  MRT_REQUIRE(dL_dvol || dL_dtf, "render_backward: nothing to differentiate");
+  MRT_REQUIRE(dL_dvol || dL_dtf || dL_dray, "render_backward: nothing to differentiate");
   MRT_REQUIRE(!dL_dtf || scratch, "render_backward: dL_dtf needs the scratch buffer");
   KParams K;
   if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
@@ -412,7 +412,7 @@ int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, 
   if (K.showSeg && !labels) K.showSeg = 0;
   if (K.showPred && !preds) K.showPred = 0;
   cudaError_t e = mrt_launch_backward(K, mrt_packed_channels(C), packed, tf, flat_levels, minmax, labels, preds,
-                                      out_rgba, dL_dout, dL_dvol, dL_dtf, scratch, (cudaStream_t)stream);
+                                      out_rgba, dL_dout, dL_dvol, dL_dtf, scratch, dL_dray, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
 }
 

@@ -25,7 +25,7 @@ cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol
                                 const uint8_t* flat_levels, const float* minmax,
                                 const int32_t* labels, const int32_t* preds,
                                 const float* out_rgba, const float* dL_dout,
-                                void* dvol, float* dtf, void* scratch, cudaStream_t st);
+                                void* dvol, float* dtf, void* scratch, float* dray, cudaStream_t st);
 size_t mrt_bwd_scratch_bytes(int ntf);
 
 cudaError_t mrt_launch_pack_f16(const void* planar_f16, int X, int Y, int Z, void* packed, cudaStream_t st);

@@ -373,6 +373,20 @@ __device__ __forceinline__ float mrt_interp(const KParams& P, const Corners<NCH,
   }
 }
 
+// d(raw)/d(index-space position) of the same interpolant (docs/DifferentiableRendering.md section 6,
+// :116-127: ds/dx = sum_n v_n dw_n/dx), per axis the lerp of the four corner differences.
+template <int NCH, bool HALF = false>
+__device__ __forceinline__ void mrt_interp_grad(const KParams& P, const Corners<NCH, HALF>& k, const Cell& c,
+                                                float* gx, float* gy, float* gz) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (NCH == 1) ? mrt_scalar(k.v[i]) * P.wq[0] : foldv(mrt_f32(k.v[i]), P);
+  // corner order: v[0..7] = c000, c100, c010, c110, c001, c101, c011, c111
+  *gx = lerpf(lerpf(v[1] - v[0], v[3] - v[2], c.fy), lerpf(v[5] - v[4], v[7] - v[6], c.fy), c.fz);
+  *gy = lerpf(lerpf(v[2] - v[0], v[3] - v[1], c.fx), lerpf(v[6] - v[4], v[7] - v[5], c.fx), c.fz);
+  *gz = lerpf(lerpf(v[4] - v[0], v[5] - v[1], c.fx), lerpf(v[6] - v[2], v[7] - v[3], c.fx), c.fy);
+}
+
 // sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
 template <int NCH, bool HALF = false>

@@ -231,7 +231,7 @@ def sample_counts(P, t0, t1, dtype=torch.float32):
 def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
            labels: Optional[torch.Tensor] = None, preds: Optional[torch.Tensor] = None,
            pixels=None, dtype=torch.float32, force_steps: Optional[torch.Tensor] = None,
-           chunk: int = 1 << 16, return_aux: bool = False):
+           chunk: int = 1 << 16, return_aux: bool = False, ray_delta=None):
     """``brats_main`` (brats_rt.slang:85-168) restated on CPU.
 
     volume : [C,Z,Y,X] (C<=4) values; differentiable leaf allowed.
@@ -242,6 +242,10 @@ def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
     pixels : optional (px, py) int tensors to render a subset of rays; default all.
     force_steps : optional per-ray int tensor overriding the ERT decision (test aid:
              lets a test check that an ERT flip in the kernel was a justified tie).
+    ray_delta : optional (do, dd), two [nray,3] tensors ADDED to the ray origins / directions after
+             the clip and the sample times t_i are fixed — their autograd gradients are the
+             dL/do, dL/dd of docs/DifferentiableRendering.md section 9 (:172-188, "x_i = o + t_i d
+             with fixed t_i").
     Returns rgba [H,W,4] (or [N,4] with ``pixels``) and optionally aux dict with
     T, n_samples (clip count), n_taken (after ERT), ert_margin.
     """
@@ -294,6 +298,9 @@ def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
         hidx = torch.nonzero(hit).reshape(-1)
         if hidx.numel() > 0:
             ho, hd, ht0, ht1 = o[hidx], d[hidx], t0[hidx], t1[hidx]
+            if ray_delta is not None:
+                ho = ho + ray_delta[0][s:s + chunk][hidx].to(dtype)
+                hd = hd + ray_delta[1][s:s + chunk][hidx].to(dtype)
             hn = n_all[hidx]
             hC = Ccol[hidx]
             hT = T[hidx]

@@ -118,3 +118,23 @@ def test_tile_range_gradients_sum_to_the_full_gradient(cuda):
     assert torch.equal(acc, full.detach())
     assert float((v.grad - gv).abs().max()) <= 1e-5 * float(gv.abs().max())
     assert float((t.grad - gt).abs().max()) <= 1e-5 * float(gt.abs().max())
+
+
+@pytest.mark.parametrize("C,use_tf,ortho", [(1, True, False), (4, False, False), (2, True, True)])
+def test_ray_parameter_gradients_match_oracle_autograd(cuda, C, use_tf, ortho):
+    """dL/do, dL/dd per ray (docs/DifferentiableRendering.md section 9: fixed sample times) against the
+    oracle's autograd through per-ray perturbations of origin and direction; 1e-3 relative."""
+    vol, _, P = small_scene(C=C, dims=(26, 22, 18), W=24, H=20, seed=40 + C, ortho=ortho)
+    P = replace(P, tfMode=int(use_tf), intensityAlpha=6.0, volWeight=(1.0, 0.5, 2.0, 0.75))
+    tf = ramp_tf(32, sigma_scale=15.0, cutoff=0.1) if use_tf else None
+    g = torch.rand((20, 24, 4), generator=torch.Generator().manual_seed(3))
+    n = 20 * 24
+    do = torch.zeros((n, 3), requires_grad=True); dd = torch.zeros((n, 3), requires_grad=True)
+    ref = O.render(vol, P, tf=tf, ray_delta=(do, dd))
+    (ref * g).sum().backward()
+    want = torch.cat([do.grad, dd.grad], dim=1).reshape(20, 24, 6)
+    V = api.Volume(vol.cuda())
+    got = api.ray_gradients(V, None, None if tf is None else tf.cuda(), P, g.cuda()).cpu()
+    scale = float(want.abs().max())
+    assert scale > 0
+    assert float((got - want).abs().max()) <= 1e-3 * scale, (float((got - want).abs().max()), scale)
