@@ -468,7 +468,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V,
                        "views_per_step_total": V * world if mode == "views" else V,
                        "partition": ("whole views per rank; framebuffer gathered on rank 0 by "
-                                     + (("peer (NVLink) stores from inside the march kernel" + (", tiles outside the active bricks' screen rectangle not sent but filled by the root (sparse gather)" if fb.sparse else "")) if (fb and fb.p2p)
+                                     + (("peer (NVLink) stores from inside the march kernel" + (", tiles outside the projected active-brick box not sent but filled by the root (sparse gather)" if fb.sparse else "")) if (fb and fb.p2p)
                                         else "NCCL all_gather")) if (world > 1 and mode == "views")
                        else ("tile rows + NCCL all_gather" if world > 1 else "single GPU"),
                        "l2": "flushed (256 MiB write) between timed steps; volume 142.8 MB > 126 MB L2"},
@@ -476,7 +476,10 @@ def run_ours(args):
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             **({"INVALID": "--no-gather diagnosis run"} if args.no_gather else {}),
-            "gpu_launches": ((V if args.per_view else 2) + 1 + (1 if volume.fold else 0)) * args.steps,
+            # our kernels inside the timed region, whole job: per rank fold+occupancy, classify, spans, march
+            # (+ on the root of a sparse gather: spans of all views and the background fill)
+            "gpu_launches": (((V if args.per_view else 2) + 1 + (1 if volume.fold else 0)) * world
+                             + (2 if (fb is not None and fb.sparse and not args.no_gather) else 0)) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
