@@ -319,6 +319,22 @@ int mrt_u8_to_f32(const uint8_t* in, size_t n, float* out, void* stream);
  * (inr/viewer/brats_viewer.py:50-56; percentiles are computed by the host). */
 int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* out, void* stream);
 
+/* ------------------------------------------------ INR inference (the producer of gPreds)
+ * predict_volume of the reference's implicit-neural-representation segmenter (inr/inr/model.py:119-141,
+ * called at inr/viewer/brats_viewer.py:250-310): per voxel, normalised coordinates -> Fourier
+ * features (:11-18) -> [coords | features | M intensities] (:21-23) -> dense/ReLU chain (:43-50) ->
+ * argmax.  One fused kernel; fp32 accumulation.
+ *   mods_planar : device fp32 [M][Z][Y][X] (the renderer's planar layout), z-scored by the caller
+ *                 like brats_viewer.py:279-287
+ *   weights     : device fp32, per layer W[in][out] row-major followed by b[out]
+ *   layer_dims  : HOST int32[n_layers+1]; layer_dims[0] must equal 3 + 6*fourier_freqs + M;
+ *                 widths <= 64, classes <= 8, n_layers <= 8
+ *   out_labels  : device int32 [Z][Y][X] — directly usable as `preds` of mrt_render_forward
+ *   out_logits  : optional device fp32 [Z][Y][X][classes] */
+int mrt_inr_predict(const float* mods_planar, int32_t M, int32_t X, int32_t Y, int32_t Z,
+                    const float* weights, const int32_t* layer_dims, int32_t n_layers, int32_t fourier_freqs,
+                    int32_t* out_labels, float* out_logits, void* stream);
+
 /* ------------------------------------------------ sort-last compositing
  * Ordered front-to-back `over` of K partial images (premultiplied colour + transmittance):
  *   (C,T) <- (C_a + T_a*C_b, T_a*T_b), front first; bg added once at the end, like the

@@ -15,7 +15,7 @@ __all__ = ["Camera", "OrbitalCamera", "OrbitalCameraYUp", "orbit_views", "Render
 
 def __getattr__(name):
     # torch-dependent API is imported lazily so the pure-host pieces work without torch/CUDA
-    if name in ("render", "ray_gradients", "render_views", "render_aux", "render_slab", "render_host", "Volume", "pack_volume", "unpack_volume",
+    if name in ("render", "inr_predict", "ray_gradients", "render_views", "render_aux", "render_slab", "render_host", "Volume", "pack_volume", "unpack_volume",
                 "render_forward", "render_backward", "build_occupancy", "classify_bricks", "tile_index_map",
                 "build_label_occupancy"):
         from . import api

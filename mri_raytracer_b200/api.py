@@ -695,6 +695,31 @@ def render_host(volume: np.ndarray, params: RenderParams, tf: Optional[np.ndarra
     return out
 
 
+def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, return_logits: bool = False):
+    """INR segmentation of a whole volume on the GPU (``mrt_inr_predict``): the reference's
+    ``predict_volume`` (inr/inr/model.py:119-141) as one fused kernel.
+
+    mods   : ``[M,Z,Y,X]`` CUDA float32, z-scored per modality (:func:`volume.zscore_modalities`)
+    params : the reference's parameter list ``[{"W": [in,out], "b": [out]}, ...]`` (numpy or torch)
+    -> int32 labels ``[Z,Y,X]`` — directly usable as ``preds`` of :class:`Volume` / :func:`render` —
+    and, with ``return_logits``, float32 ``[Z,Y,X,classes]``."""
+    _need_cuda(mods, "mods", torch.float32)
+    M, Z, Y, X = (int(v) for v in mods.shape)
+    dims = [int(np.asarray(params[0]["W"]).shape[0])] + [int(np.asarray(p["W"]).shape[1]) for p in params]
+    flat = []
+    for p in params:
+        W = torch.as_tensor(np.asarray(p["W"], dtype=np.float32)) if not isinstance(p["W"], torch.Tensor) else p["W"].float().cpu()
+        b = torch.as_tensor(np.asarray(p["b"], dtype=np.float32)) if not isinstance(p["b"], torch.Tensor) else p["b"].float().cpu()
+        flat += [W.reshape(-1), b.reshape(-1)]
+    wts = torch.cat(flat).contiguous().to(mods.device)
+    labels = torch.empty((Z, Y, X), dtype=torch.int32, device=mods.device)
+    logits = torch.empty((Z, Y, X, dims[-1]), dtype=torch.float32, device=mods.device) if return_logits else None
+    ld = (C.c_int32 * len(dims))(*dims)
+    check(lib().mrt_inr_predict(mods.data_ptr(), M, X, Y, Z, wts.data_ptr(), C.cast(ld, C.c_void_p), len(params),
+                                int(fourier_freqs), labels.data_ptr(), _ptr(logits), _stream()), "inr_predict")
+    return (labels, logits) if return_logits else labels
+
+
 class HostPipeline:
     """Host buffers in, host frames out, double-buffered (``mrt_host_pipeline_*``): per step a
     ``[C,Z,Y,X]`` float32 host volume, an optional ``[N,4]`` TF and a list of cameras go in, and

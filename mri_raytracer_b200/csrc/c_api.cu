@@ -450,6 +450,26 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "normalize_f32");
 }
 
+// ---------------------------------------------------------------- INR inference (producer of gPreds)
+int mrt_inr_predict(const float* mods_planar, int32_t M, int32_t X, int32_t Y, int32_t Z, const float* weights,
+                    const int32_t* layer_dims, int32_t n_layers, int32_t fourier_freqs, int32_t* out_labels,
+                    float* out_logits, void* stream) {
+  MRT_REQUIRE(mods_planar && weights && layer_dims && out_labels, "inr_predict: null pointer");
+  MRT_REQUIRE(M >= 1 && M <= 8 && X >= 2 && Y >= 2 && Z >= 2, "inr_predict: bad volume shape");
+  MRT_REQUIRE(n_layers >= 1 && n_layers <= 8, "inr_predict: n_layers=%d outside 1..8", n_layers);
+  MRT_REQUIRE(fourier_freqs >= 0, "inr_predict: fourier_freqs must be >= 0");
+  MRT_REQUIRE(layer_dims[0] == 3 + 6 * fourier_freqs + M, "inr_predict: input width %d != 3 + 6*%d + %d (model.py:21-23)",
+              layer_dims[0], fourier_freqs, M);
+  MRT_REQUIRE(layer_dims[0] <= 64, "inr_predict: input width %d > 64 is not supported", layer_dims[0]);
+  for (int l = 1; l < n_layers; ++l)
+    MRT_REQUIRE(layer_dims[l] >= 1 && layer_dims[l] <= 64, "inr_predict: hidden width %d outside 1..64", layer_dims[l]);
+  MRT_REQUIRE(layer_dims[n_layers] >= 1 && layer_dims[n_layers] <= 8, "inr_predict: %d classes outside 1..8",
+              layer_dims[n_layers]);
+  cudaError_t e = mrt_launch_inr(mods_planar, M, X, Y, Z, weights, layer_dims, n_layers, fourier_freqs, out_labels,
+                                 out_logits, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "inr_predict");
+}
+
 // ---------------------------------------------------------------- compositing / probe
 int mrt_composite_over(const float* partials, int32_t K, const int32_t* order, size_t npix, const float* bg3,
                        int32_t alphaMode, float* out_rgba, void* stream) {

@@ -147,3 +147,23 @@ def normalize_on_device(data, vmin: float, rng: float):
     check(lib().mrt_normalize_f32(data.data_ptr(), data.numel(), float(vmin), float(rng), out.data_ptr(),
                                   _stream()), "normalize_f32")
     return out
+
+
+def zscore_modalities(planar):
+    """Per-modality z-score over the non-zero voxels, zeros included in the output as (0-mu)/sigma —
+    the viewer's preprocessing before INR inference (inr/viewer/brats_viewer.py:279-287:
+    ``mask = arr != 0; mu = arr[mask].mean(); sigma = arr[mask].std() + 1e-6``).  ``planar``: torch
+    ``[M,Z,Y,X]`` float32 on any device -> same shape."""
+    import torch
+    out = torch.empty_like(planar)
+    for m in range(planar.shape[0]):
+        arr = planar[m]
+        mask = arr != 0
+        if bool(mask.any()):
+            vals = arr[mask]
+            mu = vals.mean()
+            sigma = vals.std(unbiased=False) + 1e-6
+            out[m] = (arr - mu) / sigma
+        else:
+            out[m] = arr
+    return out

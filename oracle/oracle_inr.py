@@ -47,7 +47,8 @@ def apply_mlp(params: Sequence[dict], x: np.ndarray) -> np.ndarray:
     return h @ np.asarray(last["W"], dtype=F32) + np.asarray(last["b"], dtype=F32)
 
 
-def predict_volume(params: Sequence[dict], mods: np.ndarray, fourier_freqs: int, chunk: int = 200000) -> np.ndarray:
+def predict_volume(params: Sequence[dict], mods: np.ndarray, fourier_freqs: int, chunk: int = 200000,
+                   return_logits: bool = False):
     """inr/inr/model.py:119-141.  mods [M,H,W,D] (z-scored per modality by the caller,
     inr/viewer/brats_viewer.py:279-287) -> int16 labels [H,W,D]: coordinates on the ``ij`` meshgrid
     normalised to [-1,1] by (n-1), argmax over the logits."""
@@ -57,11 +58,17 @@ def predict_volume(params: Sequence[dict], mods: np.ndarray, fourier_freqs: int,
     grid = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), axis=-1).reshape(-1, 3)          # :125
     intens = mods.transpose(1, 2, 3, 0).reshape(-1, M)                                       # :126
     norm = (grid / np.array([H - 1, W - 1, D - 1])) * 2.0 - 1.0                              # :128 (float64, then cast)
-    preds = []
+    preds, logs = [], []
     for i in range(0, len(grid), chunk):                                                     # :131
         x_in = build_input(norm[i:i + chunk].astype(F32), intens[i:i + chunk], fourier_freqs)
-        preds.append(np.argmax(apply_mlp(params, x_in), axis=-1).astype(np.int16))           # :135-137
-    return np.concatenate(preds, axis=0).reshape(H, W, D)                                    # :139-140
+        logits = apply_mlp(params, x_in)
+        preds.append(np.argmax(logits, axis=-1).astype(np.int16))                            # :135-137
+        if return_logits:
+            logs.append(logits)
+    pred = np.concatenate(preds, axis=0).reshape(H, W, D)                                    # :139-140
+    if return_logits:
+        return pred, np.concatenate(logs, axis=0).reshape(H, W, D, -1)
+    return pred
 
 
 def to_renderer_labels(pred_hwd: np.ndarray) -> np.ndarray:

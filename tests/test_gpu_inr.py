@@ -1,0 +1,66 @@
+"""INR inference on the GPU (mrt_inr_predict) against the numpy
+restatement of the reference's predict_volume (oracle/oracle_inr.py): logits max-abs 1e-4, labels
+identical wherever the oracle's top-2 logits are more than 1e-4 apart; and the label volume feeds
+the renderer's prediction overlay."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+from mri_raytracer_b200 import api, volume as mvol
+from oracle import oracle_inr as I
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims,M,k,hidden", [((23, 19, 17), 4, 4, [64, 64, 64, 64]), ((9, 8, 7), 2, 2, [32, 16]),
+                                              ((12, 11, 10), 4, 0, [])])
+def test_inr_predict_matches_oracle(cuda, dims, M, k, hidden):
+    X, Y, Z = dims
+    rng = np.random.default_rng(7)
+    params = I.init_mlp(rng, I.input_dim(M, k), hidden, 4)
+    for p in params:                                     # non-zero biases exercise the bias path
+        p["b"] = rng.normal(scale=0.1, size=p["b"].shape).astype(np.float32)
+    raw = torch.from_numpy(rng.gamma(2.0, 50.0, size=(M, Z, Y, X)).astype(np.float32))
+    raw[:, :, :2] = 0.0                                  # background zeros, like skull-stripped MRI
+    mods = mvol.zscore_modalities(raw)
+    labels, logits = api.inr_predict(mods.cuda(), params, k, return_logits=True)
+    # oracle works in the reference's [M,H,W,D] = [M,X,Y,Z] order
+    pred, want = I.predict_volume(params, mods.numpy().transpose(0, 3, 2, 1), k, chunk=1000, return_logits=True)
+    got = logits.cpu().numpy().transpose(2, 1, 0, 3)     # [Z,Y,X,c] -> [X,Y,Z,c]
+    assert np.abs(got - want).max() <= 1e-4
+    lab = labels.cpu().numpy()
+    assert lab.shape == (Z, Y, X)
+    assert np.array_equal(I.to_renderer_labels(pred).shape, lab.shape)
+    top2 = np.sort(want, axis=-1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 1e-4
+    same = lab.transpose(2, 1, 0) == pred
+    assert bool(same[clear].all()) and float(same.mean()) > 0.999
+
+
+def test_zscore_matches_viewer_preprocessing(cuda):
+    rng = np.random.default_rng(1)
+    raw = rng.gamma(2.0, 50.0, size=(2, 6, 5, 4)).astype(np.float32)
+    raw[1] = 0.0                                         # an all-zero modality stays as it is
+    raw[0, :2] = 0.0
+    got = mvol.zscore_modalities(torch.from_numpy(raw).cuda()).cpu().numpy()
+    arr = raw[0]; mask = arr != 0
+    want0 = (arr - arr[mask].mean()) / (arr[mask].std() + 1e-6)      # inr/viewer/brats_viewer.py:279-287
+    assert np.abs(got[0] - want0).max() <= 1e-5 and np.array_equal(got[1], raw[1])
+
+
+def test_inr_labels_feed_the_prediction_overlay(cuda):
+    import sys
+    from scenes import small_scene
+    from parity import O
+    vol, _, P = small_scene(C=4, dims=(20, 18, 16), W=32, H=24, seed=2)
+    rng = np.random.default_rng(3)
+    params = I.init_mlp(rng, I.input_dim(4, 2), [32, 32], 4)
+    preds = api.inr_predict(mvol.zscore_modalities(vol).cuda(), params, 2)
+    assert int((preds > 0).sum()) > 0
+    P = replace(P, showPred=1, intensityAlpha=5.0)
+    V = api.Volume(vol.cuda(), preds=preds)
+    img = api.render(V, None, None, P).cpu()
+    ref = O.render(vol, P, preds=preds.cpu().long())
+    assert (img - ref).abs().max() <= 1e-4
