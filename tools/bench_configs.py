@@ -132,10 +132,33 @@ def cfg4():
                 note="8 of the 64 orbit views (every 8th) on one GPU; volume generated on device")
 
 
+def inr():
+    """INR predict_volume over a BraTS-sized case with the reference's network
+    (31 -> 64 x 4 -> 4, inr/interactive.ipynb cell 1); CPU leg = the numpy oracle on a 1/64 sample."""
+    import numpy as np
+    from mri_raytracer_b200 import volume as mvol
+    from oracle import oracle_inr as I
+    dims = (240, 240, 155)
+    X, Y, Z = dims
+    rng = np.random.default_rng(0)
+    params = I.init_mlp(rng, I.input_dim(4, 4), [64, 64, 64, 64], 4)
+    mods = mvol.zscore_modalities(make_brats_like(4, dims, seed=0, device="cuda"))
+    ms = timeit(lambda: api.inr_predict(mods, params, 4), reps=2)
+    nvox = X * Y * Z
+    flop = 2.0 * (31 * 64 + 3 * 64 * 64 + 64 * 4) * nvox
+    sub = mods[:, ::4, ::4, ::4].cpu().numpy().transpose(0, 3, 2, 1).copy()
+    t0 = time.perf_counter()
+    I.predict_volume(params, sub, 4)
+    cpu_s = time.perf_counter() - t0
+    return dict(cfg="inr_predict", dims=dims, ms=ms, gvoxels_per_s=nvox / ms / 1e6, tflops_fp32=flop / ms / 1e9,
+                cpu_numpy_oracle_voxels_per_s=sub[0].size / cpu_s, cpu_sample="every 4th voxel per axis (1/64 of the case)",
+                speedup_vs_numpy=(nvox / (ms * 1e-3)) / (sub[0].size / cpu_s))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4"]
     for w in which:
         t0 = time.time()
-        r = dict(cfg1=cfg1, cfg3=cfg3, cfg4=cfg4)[w]()
+        r = dict(cfg1=cfg1, cfg3=cfg3, cfg4=cfg4, inr=inr)[w]()
         r["wall_s"] = time.time() - t0
         print(json.dumps(r), flush=True)
