@@ -238,3 +238,55 @@ def test_differentiable_tiles_world2_gradients_match_single_process():
     assert np.array_equal(img, ref.detach().numpy())
     assert np.abs(gv - v.grad.numpy()).max() <= 1e-6 * max(1.0, float(v.grad.abs().max()))
     assert np.abs(gt - t.grad.numpy()).max() <= 1e-5 * max(1.0, float(t.grad.abs().max()))
+
+
+# ----------------------------------------------------------------------------- PeerFramebuffer fallback (no symmetric memory)
+def _fb_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mri_raytracer_b200 import dist as mdist, orbit_views, OrbitalCamera
+        from mri_raytracer_b200.synth import ramp_tf
+        from scenes import small_scene
+        W, H, Vloc = 19, 13, 2
+        vol, _, P = small_scene(C=1, dims=(16, 14, 12), W=W, H=H, seed=11)
+        tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
+        cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.2, initial_theta=0.1)
+        cam.set_fov_degrees(70.0)
+        cams = orbit_views(cam, Vloc * world)
+        fb = mdist.PeerFramebuffer(Vloc, H, W, "cpu")
+        assert not fb.p2p and not fb.sparse                  # CPU / gloo: the NCCL-style gather path
+        mdist.render_views_to(fb, None, cams[rank * Vloc:(rank + 1) * Vloc], tf, P, render_fn=_oracle_fn(vol, tf),
+                              cams_all=cams)
+        fb.finish()
+        if rank == 0:
+            ret.put(fb.frames().numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_framebuffer_falls_back_to_all_gather_world2():
+    from oracle import oracle_torch as O
+    from mri_raytracer_b200 import orbit_views, OrbitalCamera
+    from mri_raytracer_b200.synth import ramp_tf
+    from scenes import small_scene
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fb_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    W, H = 19, 13
+    vol, _, P = small_scene(C=1, dims=(16, 14, 12), W=W, H=H, seed=11)
+    tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
+    cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.2, initial_theta=0.1)
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 4)
+    assert got.shape == (4, H, W, 4)
+    for v, c in enumerate(cams):
+        ref = O.render(vol, replace(P.with_camera(c), tfMode=1), tf=tf).numpy()
+        assert np.array_equal(got[v], ref), f"view {v}"
