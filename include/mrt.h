@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MRT_VERSION 100  /* 0.1.0 */
+#define MRT_VERSION 200  /* 0.2.0 */
 
 typedef enum MrtStatus {
   MRT_OK = 0,
@@ -275,31 +275,62 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews,
                            float* out_rgba, void* stream);
 
+/* ------------------------------------------------ training forward (checkpoints)
+ * The forward of differentiable rendering.  docs/DifferentiableRendering.md:213 ("checkpointing")
+ * is the only hint the reference gives on storage; here the march records, per ray, its colour and
+ * transmittance (C, T) before every slot c*seg_slots and its end slot, so that the backward can
+ * differentiate a ray as independent segments (one warp task each) instead of one serial chain.
+ *   mrt_checkpoint_plan : slots per segment (hint 0 -> 32) and segment count for params' geometry
+ *                         (segment count is capped at 64 by growing the segment)
+ *   ckpt      : device float4 [nseg-1][nviews][H][W], mrt_checkpoint_bytes() bytes (NULL if nseg == 1)
+ *   k_end     : device int32 [nviews][H][W], every ray's end slot (the oracle's n_taken)
+ *   warp_kmax : device int32 [nviews][mrt_half_tile_count(W,H)], largest k_end per 8x4 half tile
+ * `cams` NULL: one view with the camera in params.  nviews <= mrt_max_views_per_launch().
+ * Image identical to mrt_render_forward(_batch), bit for bit.  fp32 unsharded volumes, tMode 0,
+ * gamma 1 (otherwise use mrt_render_forward and the unsegmented backward). */
+int mrt_checkpoint_plan(const MrtParams* params, int32_t seg_slots_hint, int32_t* seg_slots, int32_t* nseg);
+size_t mrt_checkpoint_bytes(int32_t W, int32_t H, int32_t nviews, int32_t nseg);
+int32_t mrt_half_tile_count(int32_t W, int32_t H);
+int mrt_render_forward_ckpt(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                            const void* packed, int32_t C, const float* tf, int32_t tfN,
+                            const uint8_t* skip_levels, const int32_t* labels, const int32_t* preds,
+                            float* out_rgba, float* ckpt, int32_t seg_slots, int32_t nseg,
+                            int32_t* k_end, int32_t* warp_kmax,
+                            int32_t tile_begin, int32_t tile_end, void* stream);
+
 /* ------------------------------------------------ backward
- * Adjoint of mrt_render_forward w.r.t. the volume and the transfer function
- * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray.
+ * Adjoint of the forward w.r.t. the volume and the transfer function
+ * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray (segment).
+ *   cams, nviews: like mrt_render_forward_ckpt; all per-view arrays are [nviews][H][W](...)
  *   flat_levels: optional uint8[nbricks] from mrt_classify_bricks(..., flat=1) together with
  *                `minmax` (from mrt_build_occupancy): flat-empty cells are leapt with their exact
  *                closed-form contribution to dL/dtf (single-channel layouts only; else ignored)
  *   out_rgba   : the forward's output (needed for the suffix sums)
- *   dL_dout    : float4 [H][W]
+ *   dL_dout    : float4 [nviews][H][W]
+ *   ckpt, seg_slots, nseg, k_end, warp_kmax : the outputs of mrt_render_forward_ckpt for the SAME
+ *                arguments -> segment-parallel backward; all NULL / 0 -> one task per half tile that
+ *                walks whole rays (any tMode / gamma)
  *   dL_dvol    : packed layout, same shape as `packed`, ACCUMULATED into (caller zeroes)
  *   dL_dtf     : float [tfN][4] (tfMode 1) or float[2][4] (tfMode 0: entry [1][3] is
  *                dL/d intensityAlpha), ACCUMULATED into (caller zeroes)
- *   scratch    : device scratch of mrt_backward_scratch_bytes(tfN) bytes (privatised dL/dtf
- *                accumulators; zeroed by the call); required when dL_dtf != NULL
- *   dL_dray    : optional float [H][W][6] = (dL/do, dL/dd) per ray, world units, with the sample
+ *   scratch    : device scratch of mrt_backward_scratch_bytes(W,H,nviews,tfN,nseg) bytes (task list,
+ *                counters, privatised dL/dtf accumulators; initialised by the call)
+ *   dL_dray    : optional float [nviews][H][W][6] = (dL/do, dL/dd) per ray, world units, with the sample
  *                times t_i held fixed (docs/DifferentiableRendering.md section 9, :172-188:
  *                dL/do = sum_i dL/dx_i, dL/dd = sum_i t_i dL/dx_i; dL/dx_i through the trilinear
- *                gradient of section 6).  Caller zeroes it (rays that miss are not written).
+ *                gradient of section 6).  ACCUMULATED into (caller zeroes).
+ *   stats      : optional device uint64[2], ACCUMULATED: sample slots shaded, warp tasks executed
  */
-size_t mrt_backward_scratch_bytes(int32_t tfN);
-int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C,
+size_t mrt_backward_scratch_bytes(int32_t W, int32_t H, int32_t nviews, int32_t tfN, int32_t nseg);
+int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                        const void* packed, int32_t C,
                         const float* tf, int32_t tfN,
                         const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds,
                         const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray,
+                        const float* ckpt, int32_t seg_slots, int32_t nseg,
+                        const int32_t* k_end, const int32_t* warp_kmax,
+                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray, uint64_t* stats,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
 /* ------------------------------------------------ slab renderer (u8 volume)

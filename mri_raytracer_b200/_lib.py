@@ -105,9 +105,14 @@ PROTOTYPES = {
     "mrt_view_spans": (C.c_int, [_PP, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_fill_outside_spans": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
-    "mrt_backward_scratch_bytes": (_sz, [_i32]),
-    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                      _i32, _i32, _vp]),
+    "mrt_checkpoint_plan": (C.c_int, [_PP, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "mrt_checkpoint_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "mrt_half_tile_count": (_i32, [_i32, _i32]),
+    "mrt_render_forward_ckpt": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                          _vp, _vp, _i32, _i32, _vp]),
+    "mrt_backward_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_slab_u8": (C.c_int, [_SP, _vp, _vp, _i32, _i32, _vp]),
     "mrt_decode_bc4": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_u8_to_f32": (C.c_int, [_vp, _sz, _vp, _vp]),

@@ -254,26 +254,86 @@ def composite_over_multi(partials: torch.Tensor, order: Sequence[int], bg, alpha
                                          C.cast(arr, C.c_void_p), len(out_ptrs), _stream()), "composite_over_multi")
 
 
+class Checkpoints:
+    """What the training forward (``mrt_render_forward_ckpt``) records for the segment-parallel
+    backward: ``ck [nseg-1,V,H,W,4]`` (colour, transmittance before every slot ``c*seg_slots``),
+    ``k_end [V,H,W]`` (every ray's end slot) and ``warp_kmax [V, half tiles]``."""
+    __slots__ = ("ck", "seg_slots", "nseg", "k_end", "warp_kmax")
+
+    def __init__(self, ck, seg_slots, nseg, k_end, warp_kmax):
+        self.ck, self.seg_slots, self.nseg, self.k_end, self.warp_kmax = ck, seg_slots, nseg, k_end, warp_kmax
+
+
+def checkpoint_plan(P: RenderParams, seg_slots: int = 0) -> Tuple[int, int]:
+    """(slots per segment, segments) for the geometry in ``P`` (``mrt_checkpoint_plan``)."""
+    s = P.to_struct()
+    S, n = C.c_int32(), C.c_int32()
+    check(lib().mrt_checkpoint_plan(C.byref(s), int(seg_slots), C.byref(S), C.byref(n)), "checkpoint_plan")
+    return int(S.value), int(n.value)
+
+
+def render_forward_ckpt(P: RenderParams, cams: Optional[Sequence], packed: torch.Tensor, Cn: int,
+                        tf: Optional[torch.Tensor] = None, skip_levels: Optional[torch.Tensor] = None,
+                        labels: Optional[torch.Tensor] = None, preds: Optional[torch.Tensor] = None,
+                        out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None,
+                        seg_slots: int = 0):
+    """``mrt_render_forward_ckpt``: the forward of differentiable rendering -> (image ``[V,H,W,4]``
+    — ``[H,W,4]`` when ``cams`` is None — and its :class:`Checkpoints`)."""
+    W, H = P.imageSize
+    V = 1 if cams is None else len(cams)
+    dev = packed.device
+    S, nseg = checkpoint_plan(P, seg_slots)
+    if out is None:
+        out = torch.empty((V, H, W, 4) if cams is not None else (H, W, 4), dtype=torch.float32, device=dev)
+    ck = torch.empty((max(nseg - 1, 0), V, H, W, 4), dtype=torch.float32, device=dev)
+    k_end = torch.empty((V, H, W), dtype=torch.int32, device=dev)
+    kmax = torch.empty((V, lib().mrt_half_tile_count(W, H)), dtype=torch.int32, device=dev)
+    t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
+    s = P.to_struct()
+    arr = None if cams is None else _camera_array(cams)
+    check(lib().mrt_render_forward_ckpt(C.byref(s), None if arr is None else arr.ctypes.data, V, packed.data_ptr(), Cn,
+                                        _ptr(tf), 0 if tf is None else tf.shape[0], _ptr(skip_levels), _ptr(labels),
+                                        _ptr(preds), out.data_ptr(), ck.data_ptr() if nseg > 1 else None, S, nseg,
+                                        k_end.data_ptr(), kmax.data_ptr(), t0, t1, _stream()), "render_forward_ckpt")
+    return out, Checkpoints(ck, S, nseg, k_end, kmax)
+
+
 def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
                     labels: Optional[torch.Tensor], preds: Optional[torch.Tensor], out_rgba: torch.Tensor,
                     dL_dout: torch.Tensor, want_dvol: bool = True, want_dtf: bool = True,
                     tile_range: Optional[Tuple[int, int]] = None, flat_levels: Optional[torch.Tensor] = None,
-                    minmax: Optional[torch.Tensor] = None, want_dray: bool = False):
-    """-> (dL/dvolume packed or None, dL/dtf [N,4] or None), plus dL/d(o,d) ``[H,W,6]`` as a third
-    element when ``want_dray``."""
+                    minmax: Optional[torch.Tensor] = None, want_dray: bool = False,
+                    cams: Optional[Sequence] = None, ckpt: Optional[Checkpoints] = None,
+                    stats: Optional[torch.Tensor] = None):
+    """``mrt_render_backward`` -> (dL/dvolume packed or None, dL/dtf [N,4] or None), plus dL/d(o,d)
+    ``[H,W,6]`` (``[V,H,W,6]`` with ``cams``) as a third element when ``want_dray``.  ``ckpt`` (from
+    :func:`render_forward_ckpt` with the same arguments) selects the segment-parallel path;
+    ``stats``: optional int64[2] device tensor accumulating (sample slots shaded, warp tasks)."""
     W, H = P.imageSize
+    V = 1 if cams is None else len(cams)
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
     dvol = torch.zeros_like(packed) if want_dvol else None
     ntf = tf.shape[0] if (tf is not None and P.tfMode) else 2
     dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_dtf else None
-    scratch = torch.empty((lib().mrt_backward_scratch_bytes(ntf) // 4,), dtype=torch.float32,
-                          device=packed.device) if want_dtf else None
-    dray = torch.zeros((H, W, 6), dtype=torch.float32, device=packed.device) if want_dray else None
+    nseg = ckpt.nseg if ckpt is not None else 1
+    scratch = torch.empty((lib().mrt_backward_scratch_bytes(W, H, V, ntf, nseg) // 4,), dtype=torch.float32,
+                          device=packed.device)
+    dray = None
+    if want_dray:
+        dray = torch.zeros((V, H, W, 6) if cams is not None else (H, W, 6), dtype=torch.float32, device=packed.device)
     s = P.to_struct()
-    check(lib().mrt_render_backward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+    arr = None if cams is None else _camera_array(cams)
+    ck = ckpt
+    check(lib().mrt_render_backward(C.byref(s), None if arr is None else arr.ctypes.data, V, packed.data_ptr(), Cn,
+                                    _ptr(tf), 0 if tf is None else tf.shape[0],
                                     _ptr(flat_levels), _ptr(minmax), _ptr(labels), _ptr(preds),
-                                    out_rgba.data_ptr(), dL_dout.data_ptr(), _ptr(dvol), _ptr(dtf), _ptr(scratch),
-                                    _ptr(dray), t0, t1, _stream()), "render_backward")
+                                    out_rgba.data_ptr(), dL_dout.data_ptr(),
+                                    None if (ck is None or ck.nseg <= 1) else ck.ck.data_ptr(),
+                                    0 if ck is None else ck.seg_slots, 0 if ck is None else ck.nseg,
+                                    None if ck is None else ck.k_end.data_ptr(),
+                                    None if ck is None else ck.warp_kmax.data_ptr(),
+                                    _ptr(dvol), _ptr(dtf), scratch.data_ptr(), _ptr(dray), _ptr(stats), t0, t1, _stream()),
+          "render_backward")
     return (dvol, dtf, dray) if want_dray else (dvol, dtf)
 
 
@@ -518,9 +578,16 @@ class Volume:
 
 
 # ----------------------------------------------------------------------------- autograd
+def _segmentable(P: RenderParams) -> bool:
+    """The checkpointing forward covers indexed stepping with gamma 1 (mrt_render_forward_ckpt)."""
+    return P.tMode == "indexed" and P.gamma == 1.0
+
+
 class _RenderFn(torch.autograd.Function):
+    """Differentiable rendering of one frame or (``cams`` given) a batch of views of one volume."""
+
     @staticmethod
-    def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold, tile_range=None):
+    def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold, tile_range=None, cams=None):
         Cn = planar.shape[0]
         fold = bool(fold) and Cn > 1
         want_occ = bool(P.skipEmpty) and P.tMode == "indexed"
@@ -540,12 +607,19 @@ class _RenderFn(torch.autograd.Function):
             bits = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any)
             if Ce == 1:
                 flat = classify_bricks(Pe, mm, Ce, tf, seg_any, pred_any, flat=True)
+        W, H = P.imageSize
+        V = None if cams is None else len(cams)
         out = None
         if tile_range is not None:      # a rank's share of the frame: the other pixels are exact zeros
-            W, H = P.imageSize
-            out = torch.zeros((H, W, 4), dtype=torch.float32, device=planar.device)
-        out = render_forward(Pe, packed, Ce, tf, bits, labels, preds, out=out, tile_range=tile_range)
-        ctx.tile_range = tile_range
+            out = torch.zeros((H, W, 4) if V is None else (V, H, W, 4), dtype=torch.float32, device=planar.device)
+        ck = None
+        if _segmentable(Pe):
+            out, ck = render_forward_ckpt(Pe, cams, packed, Ce, tf, bits, labels, preds, out=out, tile_range=tile_range)
+        elif cams is None:
+            out = render_forward(Pe, packed, Ce, tf, bits, labels, preds, out=out, tile_range=tile_range)
+        else:
+            out = render_forward_batch(Pe, cams, packed, Ce, tf, bits, labels, preds, out=out, tile_range=tile_range)
+        ctx.tile_range, ctx.cams, ctx.ck = tile_range, cams, ck
         ctx.P, ctx.Pe, ctx.Cn, ctx.Ce, ctx.fold = P, Pe, Cn, Ce, fold
         ctx.mm, ctx.flat = mm, flat
         ctx.labels, ctx.preds = labels, preds
@@ -560,11 +634,12 @@ class _RenderFn(torch.autograd.Function):
         want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
         dvol, dtf = render_backward(ctx.Pe, packed, ctx.Ce, tf, ctx.labels, ctx.preds, out,
                                     g.contiguous(), want_dvol=want_vol, want_dtf=want_tf,
-                                    flat_levels=ctx.flat, minmax=ctx.mm, tile_range=ctx.tile_range)
+                                    flat_levels=ctx.flat, minmax=ctx.mm, tile_range=ctx.tile_range,
+                                    cams=ctx.cams, ckpt=ctx.ck)
         gvol = None
         if want_vol:
             gvol = unfold_grad(dvol, ctx.P, ctx.Cn) if ctx.fold else unpack_volume(dvol, ctx.Cn, ctx.P.dims)
-        return gvol, (dtf if want_tf else None), None, None, None, None, None
+        return gvol, (dtf if want_tf else None), None, None, None, None, None, None
 
 
 def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Optional[torch.Tensor],
@@ -615,16 +690,15 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
     return _RenderFn.apply(volume, tf, P, labels, preds, fold, tile_range)
 
 
-def render_views(volume: Volume, cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,
-                 out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+def render_views(volume: Union[torch.Tensor, Volume], cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,
+                 out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None,
+                 fold: bool = True) -> torch.Tensor:
     """Render a batch of views of a prepared :class:`Volume` -> float32 ``[V,H,W,4]``: the
     reference's frame loop over successive camera poses (inr/viewer/brats_viewer.py:400-442) as
     one classify + one march launch per 64 views.  View ``v`` is bit-identical to
     ``render(volume, cams[v], tf, params)``.  The cameras must share the projection
-    (fov / ortho window) — only eye/U/V/W vary within a batch.  Not differentiable (use
-    :func:`render` per view for gradients)."""
-    if not isinstance(volume, Volume):
-        raise TypeError("render_views needs a prepared Volume")
+    (fov / ortho window) — only eye/U/V/W vary within a batch.  With a ``[C,Z,Y,X]`` tensor instead of
+    a Volume the batch is differentiable w.r.t. the tensor and ``tf`` (<= 64 views)."""
     cams = list(cams)
     if not cams:
         raise ValueError("render_views needs at least one camera")
@@ -638,6 +712,24 @@ def render_views(volume: Volume, cams: Sequence, tf: Optional[torch.Tensor], par
         if tf.dim() != 2 or tf.shape[1] != 4 or not (2 <= tf.shape[0] <= _lib.MRT_MAX_TF):
             raise ValueError(f"tf must be [N,4] with 2 <= N <= {_lib.MRT_MAX_TF}, got {tuple(tf.shape)}")
     P = replace(params, tfMode=1 if tf is not None else 0)
+    if isinstance(volume, torch.Tensor):
+        # differentiable w.r.t. the volume tensor and the TF: one checkpointing march + one
+        # segment-parallel backward launch for the whole batch (a multi-view training step)
+        _need_cuda(volume, "volume", torch.float32)
+        if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
+            raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(volume.shape)}")
+        Z, Y, X = (int(v) for v in volume.shape[1:])
+        if tuple(P.dims) != (X, Y, Z):
+            raise ValueError(f"params.dims {P.dims} != volume dims {(X, Y, Z)}")
+        if len(cams) > lib().mrt_max_views_per_launch():
+            raise ValueError(f"a differentiable batch holds at most {lib().mrt_max_views_per_launch()} views")
+        if out is not None:
+            raise ValueError("out= is not supported for a differentiable batch")
+        P = P.with_camera(c0)
+        P.validate()
+        return _RenderFn.apply(volume, tf, P, None, None, fold, tile_range, cams)
+    if not isinstance(volume, Volume):
+        raise TypeError("render_views needs a prepared Volume or a [C,Z,Y,X] tensor")
     if tuple(P.dims) != tuple(volume.global_dims):
         raise ValueError(f"params.dims {P.dims} != volume dims {volume.global_dims}")
     P.validate()

@@ -2,24 +2,38 @@
 //
 // Spec: docs/DifferentiableRendering.md §5-§6 (:88-127).  No reference code exists; the
 // ground truth is the oracle's autograd.  Per ray the forward is re-marched in the SAME
-// order with the SAME arithmetic (so every early-termination decision repeats), and the
-// doc's O(N) T-adjoint recurrence is evaluated front-to-back through the identity
+// order with the SAME arithmetic, and the doc's O(N) T-adjoint recurrence is evaluated
+// front-to-back through the identity
 //     sum_{j>i} G.c_j alpha_j T_{j-1}  =  G.(C_out - bg)  -  sum_{j<=i} G.c_j alpha_j T_{j-1}
-// so nothing but the forward image has to be stored:
+// so nothing but the forward image (and, optionally, its checkpoints) has to be stored:
 //     dL/dsigma_i = dt * ( (1-alpha_i) T_{i-1} (G.c_i)  -  suffix_i  -  T_N * dL/dT_N )
 //     dL/dc_i     = G * alpha_i T_{i-1}
 // then through the LUT lerp (-> dL/dtf[j0], dL/dtf[j1], dL/dval), window/level, the
 // modality blend and the trilinear weights (-> 8 scatter-adds per sample).
-// dL/dtf goes to one of 64 privatised L2-resident copies with one 16-byte vector reduction per
-// touched LUT entry (reduced by a tiny second kernel); dL/dvolume goes to L2 with native
-// reductions (scalar for the folded / single-modality layout, red.v2/.v4 for interleaved).
+//
+// Round-2 design (the round-1 kernel ran one warp per half tile over WHOLE rays: a 512^2 frame is
+// less than one wave and a few 500-slot rays were the whole tail — 14 % warps active):
+//   * segment-parallel: the checkpointing forward (forward.cu, CKPT) stores (C, T) every S slots
+//     (docs/DifferentiableRendering.md:213 suggests exactly this) plus every ray's end slot, so a
+//     ray is differentiated by ceil(k_end/S) independent warp tasks of <= S slots each;
+//   * persistent CTAs pull (view, half tile, segment) tasks from a compacted list through one atomic
+//     counter: no tail, any number of views per launch;
+//   * dL/dtf is accumulated in a per-WARP shared-memory histogram with plain read-modify-writes:
+//     lanes that hit the same LUT entry in the same slot are found with one MATCH.ANY and take
+//     turns (shared-memory fp32 atomics are CAS loops on sm_100a, and two 16-byte L2 reductions
+//     per sample were the round-1 kernel's dominant cost); bins shared by more than 4 lanes and
+//     LUTs too large for shared memory fall back to privatised L2 reductions;
+//   * dL/dvolume goes to L2 with native reductions (scalar for the folded / single-modality
+//     layout, red.v2/.v4 for interleaved).
 // Cells that are flat (one value) and empty are leapt with their closed-form dL/dtf term.
 #include "march.cuh"
 #include "kernels.h"
+#include <limits.h>
+#include <stdlib.h>
 
-#ifndef MRT_BWD_TPB
-#define MRT_BWD_TPB 2
-#endif
+#define MRT_BWD_WARPS 8
+#define MRT_DTF_COPIES 64     // privatised dL/dtf accumulators in L2 (CTA b uses copy b % 64)
+#define MRT_HIST_MAXMULT 4    // lanes sharing one LUT entry that still take turns in shared memory
 
 __device__ __forceinline__ void vox_atomic_add(float* p, float w, const KParams& P) {
   atomicAdd(p, w * P.wq[0]);
@@ -31,38 +45,62 @@ __device__ __forceinline__ void vox_atomic_add(float4* p, float w, const KParams
   atomicAdd(p, make_float4(w * P.wq[0], w * P.wq[1], w * P.wq[2], w * P.wq[3]));
 }
 
-#define MRT_DTF_COPIES 64     // privatised dL/dtf accumulators in L2 (CTA b uses copy b % 64)
+// Everything the kernel reads or writes besides the volume, in one constant block.
+struct BwdIO {
+  const float4* tf; const uint8_t* flat_levels; const float2* minmax;
+  const int32_t* labels; const int32_t* preds;
+  const float4* out_rgba; const float4* dL_dout;
+  const float4* ck;            // checkpoints [(c-1)][view][H][W] = (C, T) before slot c*S; nullptr = unsegmented
+  const int32_t* k_end;        // [view][H][W] end slot of every ray (forward's n_taken)
+  float4* dtf_priv;            // [MRT_DTF_COPIES][ntf][2]: (lo, hi) = contributions to entry j0 and j0+1
+  float* dray;                 // [view][H][W][6]
+  unsigned long long* stats;   // [0] lane-slots shaded, [1] warp tasks that did work
+  const uint2* tasks; const unsigned* ntasks; unsigned* next;
+  int S, nviews, hist;
+};
 
-// dL/dtf accumulation: one 16-byte vector reduction per touched LUT entry into this CTA's
-// privatised copy (global fp32 atomics are native REDG.F32x4; shared-memory fp32 atomicAdd
-// compiles to a CAS spin loop that serialises badly when a warp's lanes share a bin).
-__device__ __forceinline__ void dtf_add(float4* __restrict__ dtfp, int j, float w, float dr, float dg, float db,
-                                        float ds) {
-  atomicAdd(dtfp + j, make_float4(w * dr, w * dg, w * db, w * ds));
+// dL/dtf of one slot for the whole warp (converged call, all 32 lanes).  Entry j0 gets (1-fr)*g,
+// entry j0+1 gets fr*g; both live side by side in the histogram row of j0.  Lanes with the same
+// j0 are ranked (MATCH.ANY) and do their read-modify-write in turn; the trip count is warp-uniform.
+__device__ __forceinline__ void hist_add(float4* __restrict__ hw, float4* __restrict__ gpriv, int lane, bool valid,
+                                         int j0, float fr, float4 g) {
+  const unsigned full = 0xffffffffu;
+  const unsigned peers = __match_any_sync(full, valid ? j0 : (-1 - lane));
+  const int mult = __popc(peers);
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  const bool in_smem = valid && mult <= MRT_HIST_MAXMULT;
+  const int rounds = __reduce_max_sync(full, in_smem ? mult : 0);
+  const float f0 = 1.0f - fr;
+  for (int r = 0; r < rounds; ++r) {
+    if (in_smem && rank == r) {
+      float4 a = hw[2 * j0], b = hw[2 * j0 + 1];
+      a.x = fmaf(f0, g.x, a.x); a.y = fmaf(f0, g.y, a.y); a.z = fmaf(f0, g.z, a.z); a.w = fmaf(f0, g.w, a.w);
+      b.x = fmaf(fr, g.x, b.x); b.y = fmaf(fr, g.y, b.y); b.z = fmaf(fr, g.z, b.z); b.w = fmaf(fr, g.w, b.w);
+      hw[2 * j0] = a; hw[2 * j0 + 1] = b;
+    }
+    __syncwarp();
+  }
+  if (valid && !in_smem) {
+    atomicAdd(gpriv + 2 * j0, make_float4(f0 * g.x, f0 * g.y, f0 * g.z, f0 * g.w));
+    if (fr != 0.0f) atomicAdd(gpriv + 2 * j0 + 1, make_float4(fr * g.x, fr * g.y, fr * g.z, fr * g.w));
+  }
 }
 
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-__global__ void __launch_bounds__(64 * MRT_BWD_TPB)
-mrt_bwd_kernel(const __grid_constant__ KParams P,
-               const typename Vox<NCH>::T* __restrict__ vol,
-               const float4* __restrict__ tf,
-               const uint8_t* __restrict__ flat_levels,
-               const float2* __restrict__ minmax,
-               const int32_t* __restrict__ labels,
-               const int32_t* __restrict__ preds,
-               const float4* __restrict__ out_rgba,
-               const float4* __restrict__ dL_dout,
-               typename Vox<NCH>::T* __restrict__ dvol,
-               float4* __restrict__ dtf_priv,
-               float* __restrict__ dray) {
+__global__ void __launch_bounds__(32 * MRT_BWD_WARPS, 3)
+mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B,
+               const __grid_constant__ BwdIO IO,
+               const typename Vox<NCH>::T* __restrict__ vol, typename Vox<NCH>::T* __restrict__ dvol) {
   typedef typename Vox<NCH>::T VT;
-  extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels
+  extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels | [warps][ntf][2] histogram
   const int ntf = P.tfMode ? P.tfN : 2;
   TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);
   float4* s_lab = reinterpret_cast<float4*>(s_tf + ntf);
+  float4* s_hist = s_lab + 16;
+  const unsigned full = 0xffffffffu;
 
   if (P.tfMode) {
-    mrt_tf_stage(s_tf, tf, ntf);
+    mrt_tf_stage(s_tf, IO.tf, ntf);
   } else if (threadIdx.x == 0) {
     // the reference intensity TF (:135-138) is the 2-entry LUT [(0,0,0,0), (1,1,1,intensityAlpha)]
     s_tf[0].base = make_float4(0.f, 0.f, 0.f, 0.f); s_tf[0].delta = make_float4(1.f, 1.f, 1.f, P.ia);
@@ -76,227 +114,367 @@ mrt_bwd_kernel(const __grid_constant__ KParams P,
       s_lab[threadIdx.x] = make_float4(P.lut[l][0], P.lut[l][1], P.lut[l][2], (l > 0) ? a : 0.0f);
     }
   }
+  const bool want_tf = IO.dtf_priv != nullptr;
+  const bool use_hist = want_tf && IO.hist;
+  if (use_hist)
+    for (int i = threadIdx.x; i < MRT_BWD_WARPS * ntf * 2; i += blockDim.x) s_hist[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  float4* const dtfp = dtf_priv ? dtf_priv + (size_t)(blockIdx.x & (MRT_DTF_COPIES - 1)) * ntf : nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_BWD_TPB + (warp >> 1);
-  if (tile >= P.tile_end) return;
-  int px, py;
-  mrt_pixel_of_tile_lane_(tile, mrt_logical_lane(warp & 1, lane), P.W, &px, &py);
-  if (px >= P.W || py >= P.H) return;
-
-  const size_t pix = (size_t)py * P.W + px;
-  const float4 G = __ldg(dL_dout + pix);
-  const Ray ray = mrt_setup_ray(P, P.eye, px, py);
-  if (!(ray.n > 0 && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || (P.alphaMode && G.w != 0.0f)))) return;
-
-  const float4 Cout = __ldg(out_rgba + pix);
-  const float S_tot = G.x * (Cout.x - P.bg[0]) + G.y * (Cout.y - P.bg[1]) + G.z * (Cout.z - P.bg[2]);
-  // alphaMode 1: a = 1 - T_N  =>  dL/dT_N = -G.w ;  dsigma_i += -dt*T_N*dL/dT_N
-  const float tn_term = P.alphaMode ? -(1.0f - Cout.w) * G.w : 0.0f;   // = T_N * dL/dT_N
-  const IdxRay q = mrt_index_ray(P, ray);
+  float4* const hw = s_hist + (size_t)warp * ntf * 2;
+  float4* const gpriv = want_tf ? IO.dtf_priv + (size_t)(blockIdx.x & (MRT_DTF_COPIES - 1)) * ntf * 2 : nullptr;
+  const bool seg = IO.k_end != nullptr;
+  const int nht = 2 * mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
+  const size_t npix = (size_t)P.W * P.H;
+  const unsigned ntasks = __ldg(IO.ntasks);
   const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
   const float dt = P.dt, thr = P.thr;
   const float nm1 = (float)(ntf - 1);
   uint32_t s_tf_addr = (uint32_t)__cvta_generic_to_shared(s_tf);
-    asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
+  asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
   const uint32_t sY = P.pitchY, sZ = P.pitchZ;
-  float T = 1.0f, prefix = 0.0f;
-  int k = 0;
-  float gox = 0.0f, goy = 0.0f, goz = 0.0f, gdx = 0.0f, gdy = 0.0f, gdz = 0.0f;   // dL/do, dL/dd of this ray
+  const bool acc_mode = GENERIC && P.tMode == 1;           // reference-faithful running sum t += dt (unsegmented only)
+  unsigned n_shaded = 0, n_tasks = 0;
 
-  // one sample slot with its adjoint
-  auto shade = [&](float t) {
-    const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-    const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-    const Corners<NCH, false> cor = mrt_fetch<NCH, false>(P, vol, c);
-    const float raw = mrt_interp<NCH, false>(P, cor, c);
-    const float val = mrt_window<GENERIC>(P, raw);
-    if (P.tfMode || val > 0.0f) {
-      int j0; float fr;
-      const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
-      const float alpha = mrt_alpha(P, rgba.w);
-      const float aT = alpha * T;
-      const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
-      prefix = fmaf(aT, gc, prefix);
-      const float suffix = S_tot - prefix;
-      const float dsig = dt * ((1.0f - alpha) * T * gc - suffix - tn_term);
-      const float dr = aT * G.x, dg = aT * G.y, db = aT * G.z;
-      if (dtfp != nullptr) {
-        dtf_add(dtfp, j0, 1.0f - fr, dr, dg, db, dsig);
-        if (fr != 0.0f) dtf_add(dtfp, min(j0 + 1, ntf - 1), fr, dr, dg, db, dsig);
-      }
-      if (dvol != nullptr || dray != nullptr) {
-        const float4 d4 = s_tf[j0].delta;
-        float dval = nm1 * (dr * d4.x + dg * d4.y + db * d4.z + dsig * d4.w);
-        if (GENERIC) {
-          if (P.gamma != 1.0f) dval *= P.gamma * powf(__saturatef(raw), P.gamma - 1.0f);
-        }
-        // saturate: torch.clamp passes the gradient on the closed interval [0,1]
-        const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval : 0.0f;
-        if (dray != nullptr && dv != 0.0f) {
-          // docs/DifferentiableRendering.md section 9 (:172-188): x_i = o + t_i d with fixed t_i, so
-          // dL/do += dL/dx_i and dL/dd += t_i dL/dx_i, with dL/dx_i = dL/ds * ds/dx (section 6); an
-          // axis on which the position was clamped (:62) carries no gradient
-          float sx, sy, sz;
-          mrt_interp_grad<NCH, false>(P, cor, c, &sx, &sy, &sz);
-          const float wx = (ppx >= 0.0f && ppx <= hix) ? dv * sx / P.vs[0] : 0.0f;
-          const float wy = (ppy >= 0.0f && ppy <= hiy) ? dv * sy / P.vs[1] : 0.0f;
-          const float wz = (ppz >= 0.0f && ppz <= hiz) ? dv * sz / P.vs[2] : 0.0f;
-          gox += wx; goy += wy; goz += wz;
-          gdx = fmaf(t, wx, gdx); gdy = fmaf(t, wy, gdy); gdz = fmaf(t, wz, gdz);
-        }
-        if (dvol != nullptr && dv != 0.0f) {
-          const uint32_t b = (uint32_t)c.ix() + (uint32_t)c.iy() * sY + (uint32_t)c.iz() * sZ;
-          VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
-          const float gx0 = 1.0f - c.fx, gy0 = 1.0f - c.fy, gz0 = 1.0f - c.fz;
-          const float w00 = dv * gy0 * gz0, w10 = dv * c.fy * gz0, w01 = dv * gy0 * c.fz, w11 = dv * c.fy * c.fz;
-          vox_atomic_add(p0, w00 * gx0, P); vox_atomic_add(p0 + 1, w00 * c.fx, P);
-          vox_atomic_add(p1, w10 * gx0, P); vox_atomic_add(p1 + 1, w10 * c.fx, P);
-          vox_atomic_add(p2, w01 * gx0, P); vox_atomic_add(p2 + 1, w01 * c.fx, P);
-          vox_atomic_add(p3, w11 * gx0, P); vox_atomic_add(p3 + 1, w11 * c.fx, P);
-        }
-      }
-      T *= (1.0f - alpha);
+  for (;;) {
+    unsigned t_id = 0;
+    if (lane == 0) t_id = atomicAdd(IO.next, 1u);
+    t_id = __shfl_sync(full, t_id, 0);
+    if (t_id >= ntasks) break;
+    const uint2 task = __ldg(IO.tasks + t_id);
+    const int view = (int)(task.x / (unsigned)nht), ht = (int)(task.x - (unsigned)view * (unsigned)nht), sg = (int)task.y;
+    int px, py;
+    mrt_pixel_of_tile_lane_fast(P, ht >> 1, mrt_logical_lane(ht & 1, lane), &px, &py);
+    const bool inside = px < P.W && py < P.H;
+    const size_t pixl = inside ? (size_t)py * P.W + px : 0, pix = (size_t)view * npix + pixl;
+    const float4 G = inside ? __ldg(IO.dL_dout + pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool live = inside && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || (P.alphaMode && G.w != 0.0f));
+    int k0 = 0, k1 = INT_MAX;
+    if (seg) {
+      k0 = sg * IO.S;
+      k1 = inside ? min(__ldg(IO.k_end + pix), k0 + IO.S) : 0;
+      live = live && k1 > k0;
     }
-    if (LABELS) {          // overlays carry no gradient but attenuate what lies behind
-      if (P.showSeg) {
-        const int l = mrt_sample_label(P, labels, ppx, ppy, ppz);
-        if (l > 0 && l < 8) {
-          const float4 col = s_lab[l];
-          prefix = fmaf(col.w * T, G.x * col.x + G.y * col.y + G.z * col.z, prefix);
-          T *= (1.0f - col.w);
-        }
-      }
-      if (P.showPred) {
-        const int l = mrt_sample_label(P, preds, ppx, ppy, ppz);
-        if (l > 0 && l < 8) {
-          const float4 col = s_lab[8 + l];
-          prefix = fmaf(col.w * T, G.x * col.x + G.y * col.y + G.z * col.z, prefix);
-          T *= (1.0f - col.w);
-        }
-      }
-    }
-  };
+    if (!__any_sync(full, live)) continue;
+    const Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
+    k1 = min(k1, ray.n);
+    live = live && k1 > k0;
+    if (!__any_sync(full, live)) continue;
+    if (!live) k1 = k0;
+    ++n_tasks;
 
-  if (GENERIC && P.tMode == 1) {
-    float t = ray.t0;
-    while (t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) { shade(t); t += dt; ++k; }
-  } else if (SKIP) {
-    // Flat-empty cells (every voxel of the cell holds the same value c AND sigma == 0 over the TF
-    // bins c maps to AND no overlay label): all ns slots inside have the same (bin, frac, colour),
-    // alpha == 0, so T, prefix and hence dL/dsigma are identical for every slot; the volume
-    // gradient is exactly 0 (the LUT slope of sigma is 0 there and dL/dc = alpha*T*G = 0).
-    // Their whole contribution is ns * dL/dsigma onto two LUT entries: one reduction per cell.
+    const float4 Cout = live ? __ldg(IO.out_rgba + pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float S_tot = G.x * (Cout.x - P.bg[0]) + G.y * (Cout.y - P.bg[1]) + G.z * (Cout.z - P.bg[2]);
+    // alphaMode 1: a = 1 - T_N  =>  dL/dT_N = -G.w ;  dsigma_i += -dt*T_N*dL/dT_N
+    const float tn_term = P.alphaMode ? -(1.0f - Cout.w) * G.w : 0.0f;   // = T_N * dL/dT_N
+    float T = 1.0f, prefix = 0.0f;
+    if (seg && sg > 0 && live) {
+      const float4 c = __ldg(IO.ck + ((size_t)(sg - 1) * IO.nviews + view) * npix + pixl);
+      T = c.w;
+      prefix = G.x * (c.x - P.bg[0]) + G.y * (c.y - P.bg[1]) + G.z * (c.z - P.bg[2]);
+    }
+    const IdxRay q = mrt_index_ray(P, ray);
     const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
     const float inv_dt = 1.0f / dt;
-    const int n = ray.n;
-    int kact = 0;
+    int k = k0, kact = k0;
+    float tacc = ray.t0;
+    int lj = -1; float lfr = 0.0f, lacc = 0.0f;                  // dL/dsigma of the flat-empty cells leapt so far (one LUT entry)
+
     for (;;) {
-      while (k >= kact && k < n && T > thr) {
-        const float t = fmaf((float)k, dt, ray.t0);
-        const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-        const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);
-        const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
-        const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
-        const int bid = ((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx + (ix >> MRT_BRICK_SHIFT);
-        const int lvl = __ldg(flat_levels + bid);
-        const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-        const int kend = min(n, k + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
-        if (lvl) {
-          if (dtfp != nullptr) {
-            const float cval = __ldg(&minmax[(size_t)bid * NCH].x);
-            const float val = mrt_window<GENERIC>(P, cval * P.wq[0] + P.wbias);
-            if (P.tfMode || val > 0.0f) {
-              int j0; float fr;
-              const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
-              const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
-              const float dsig = (float)(kend - k) * dt * (T * gc - (S_tot - prefix) - tn_term);
-              dtf_add(dtfp, j0, 1.0f - fr, 0.f, 0.f, 0.f, dsig);
-              if (fr != 0.0f) dtf_add(dtfp, min(j0 + 1, ntf - 1), fr, 0.f, 0.f, 0.f, dsig);
+      if (SKIP) {
+        // Flat-empty cells (every voxel of the cell holds the same value c AND sigma == 0 over the TF
+        // bins c maps to AND no overlay label): all ns slots inside have the same (bin, frac, colour),
+        // alpha == 0, so T, prefix and hence dL/dsigma are identical for every slot; the volume
+        // gradient is exactly 0 (the LUT slope of sigma is 0 there and dL/dc = alpha*T*G = 0).
+        // Their whole contribution is ns * dL/dsigma onto two LUT entries.
+        while (k >= kact && k < k1 && (seg || T > thr)) {
+          const float t = fmaf((float)k, dt, ray.t0);
+          const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+          const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);
+          const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
+          const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+          const int bid = ((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx + (ix >> MRT_BRICK_SHIFT);
+          const int lvl = __ldg(IO.flat_levels + bid);
+          const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+          const int kend = min(k1, k + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
+          if (lvl) {
+            if (want_tf) {
+              const float cval = __ldg(&IO.minmax[(size_t)bid * NCH].x);
+              const float val = mrt_window<GENERIC>(P, cval * P.wq[0] + P.wbias);
+              if (P.tfMode || val > 0.0f) {
+                int j0; float fr;
+                const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
+                const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
+                const float dsig = (float)(kend - k) * dt * (T * gc - (S_tot - prefix) - tn_term);
+                if (j0 != lj || fr != lfr) {
+                  if (lj >= 0 && lacc != 0.0f) {
+                    atomicAdd(&gpriv[2 * lj].w, (1.0f - lfr) * lacc);
+                    if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
+                  }
+                  lj = j0; lfr = fr; lacc = 0.0f;
+                }
+                lacc += dsig;
+              }
             }
+            k = kend;
+          } else {
+            kact = kend;
           }
-          k = kend;
-        } else {
-          kact = kend;
         }
       }
-      if (!(k < n && T > thr)) break;
-      shade(fmaf((float)k, dt, ray.t0));
-      ++k;
+      const bool on = live && (acc_mode ? (tacc < ray.t1 && (P.maxSteps == 0 || k < P.maxSteps)) : (k < k1)) &&
+                      (seg || T > thr);
+      if (!__any_sync(full, on)) break;
+      bool addtf = false;
+      int j0 = 0; float fr = 0.0f;
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on) {
+        const float t = acc_mode ? tacc : fmaf((float)k, dt, ray.t0);
+        const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+        const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
+        const Corners<NCH, false> cor = mrt_fetch<NCH, false>(P, vol, c);
+        const float raw = mrt_interp<NCH, false>(P, cor, c);
+        const float val = mrt_window<GENERIC>(P, raw);
+        if (P.tfMode || val > 0.0f) {
+          const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
+          const float alpha = mrt_alpha(P, rgba.w);
+          const float aT = alpha * T;
+          const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
+          prefix = fmaf(aT, gc, prefix);
+          const float suffix = S_tot - prefix;
+          const float dsig = dt * ((1.0f - alpha) * T * gc - suffix - tn_term);
+          const float dr = aT * G.x, dg = aT * G.y, db = aT * G.z;
+          addtf = want_tf;
+          g4 = make_float4(dr, dg, db, dsig);
+          if (dvol != nullptr || IO.dray != nullptr) {
+            const float4 d4 = s_tf[j0].delta;
+            float dval = nm1 * (dr * d4.x + dg * d4.y + db * d4.z + dsig * d4.w);
+            if (GENERIC) {
+              if (P.gamma != 1.0f) dval *= P.gamma * powf(__saturatef(raw), P.gamma - 1.0f);
+            }
+            // saturate: torch.clamp passes the gradient on the closed interval [0,1]
+            const float dv = (raw >= 0.0f && raw <= 1.0f) ? dval : 0.0f;
+            if (IO.dray != nullptr && dv != 0.0f) {
+              // docs/DifferentiableRendering.md section 9 (:172-188): x_i = o + t_i d with fixed t_i, so
+              // dL/do += dL/dx_i and dL/dd += t_i dL/dx_i, with dL/dx_i = dL/ds * ds/dx (section 6); an
+              // axis on which the position was clamped (:62) carries no gradient
+              float sx, sy, sz;
+              mrt_interp_grad<NCH, false>(P, cor, c, &sx, &sy, &sz);
+              const float wx = (ppx >= 0.0f && ppx <= hix) ? dv * sx / P.vs[0] : 0.0f;
+              const float wy = (ppy >= 0.0f && ppy <= hiy) ? dv * sy / P.vs[1] : 0.0f;
+              const float wz = (ppz >= 0.0f && ppz <= hiz) ? dv * sz / P.vs[2] : 0.0f;
+              // (straight to memory: per-ray register accumulators would cost the common
+              // dL/dvolume + dL/dtf case six registers at the 80-register budget of 24 warps per SM)
+              float* r = IO.dray + pix * 6;
+              if (wx != 0.0f) { atomicAdd(r + 0, wx); atomicAdd(r + 3, t * wx); }
+              if (wy != 0.0f) { atomicAdd(r + 1, wy); atomicAdd(r + 4, t * wy); }
+              if (wz != 0.0f) { atomicAdd(r + 2, wz); atomicAdd(r + 5, t * wz); }
+            }
+            if (dvol != nullptr && dv != 0.0f) {
+              const uint32_t b = (uint32_t)c.ix() + (uint32_t)c.iy() * sY + (uint32_t)c.iz() * sZ;
+              VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
+              const float gx0 = 1.0f - c.fx, gy0 = 1.0f - c.fy, gz0 = 1.0f - c.fz;
+              const float w00 = dv * gy0 * gz0, w10 = dv * c.fy * gz0, w01 = dv * gy0 * c.fz, w11 = dv * c.fy * c.fz;
+              vox_atomic_add(p0, w00 * gx0, P); vox_atomic_add(p0 + 1, w00 * c.fx, P);
+              vox_atomic_add(p1, w10 * gx0, P); vox_atomic_add(p1 + 1, w10 * c.fx, P);
+              vox_atomic_add(p2, w01 * gx0, P); vox_atomic_add(p2 + 1, w01 * c.fx, P);
+              vox_atomic_add(p3, w11 * gx0, P); vox_atomic_add(p3 + 1, w11 * c.fx, P);
+            }
+          }
+          T *= (1.0f - alpha);
+        }
+        if (LABELS) {          // overlays carry no gradient but attenuate what lies behind
+          if (P.showSeg) {
+            const int l = mrt_sample_label(P, IO.labels, ppx, ppy, ppz);
+            if (l > 0 && l < 8) {
+              const float4 col = s_lab[l];
+              prefix = fmaf(col.w * T, G.x * col.x + G.y * col.y + G.z * col.z, prefix);
+              T *= (1.0f - col.w);
+            }
+          }
+          if (P.showPred) {
+            const int l = mrt_sample_label(P, IO.preds, ppx, ppy, ppz);
+            if (l > 0 && l < 8) {
+              const float4 col = s_lab[8 + l];
+              prefix = fmaf(col.w * T, G.x * col.x + G.y * col.y + G.z * col.z, prefix);
+              T *= (1.0f - col.w);
+            }
+          }
+        }
+        ++k; ++n_shaded;
+        if (GENERIC) tacc += dt;
+      }
+      if (use_hist) {
+        hist_add(hw, gpriv, lane, addtf, j0, fr, g4);
+      } else if (addtf) {
+        const float f0 = 1.0f - fr;
+        atomicAdd(gpriv + 2 * j0, make_float4(f0 * g4.x, f0 * g4.y, f0 * g4.z, f0 * g4.w));
+        if (fr != 0.0f) atomicAdd(gpriv + 2 * j0 + 1, make_float4(fr * g4.x, fr * g4.y, fr * g4.z, fr * g4.w));
+      }
     }
-  } else {
-    while (k < ray.n && T > thr) { shade(fmaf((float)k, dt, ray.t0)); ++k; }
+    if (lj >= 0 && lacc != 0.0f) {
+      atomicAdd(&gpriv[2 * lj].w, (1.0f - lfr) * lacc);
+      if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
+    }
   }
-  if (dray != nullptr) {                      // [H][W][6] = (dL/do, dL/dd); rays that returned early keep the caller's zeros
-    float* r = dray + pix * 6;
-    r[0] = gox; r[1] = goy; r[2] = goz; r[3] = gdx; r[4] = gdy; r[5] = gdz;
+
+  if (IO.stats != nullptr) {
+    const unsigned s = __reduce_add_sync(full, n_shaded);
+    if (lane == 0) { atomicAdd(IO.stats, (unsigned long long)s); atomicAdd(IO.stats + 1, (unsigned long long)n_tasks); }
+  }
+  if (use_hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntf * 2; i += blockDim.x) {
+      float4 s = s_hist[i];
+#pragma unroll
+      for (int w = 1; w < MRT_BWD_WARPS; ++w) {
+        const float4 v = s_hist[(size_t)w * ntf * 2 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      if (s.x != 0.0f || s.y != 0.0f || s.z != 0.0f || s.w != 0.0f) atomicAdd(gpriv + i, s);
+    }
   }
 }
 
-// dtf[i] += sum over the privatised copies
-__global__ void mrt_dtf_reduce_kernel(const float* __restrict__ priv, int ncopies, int nfloats, float* __restrict__ dtf) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nfloats) return;
-  float s = 0.0f;
-  for (int c = 0; c < ncopies; ++c) s += priv[(size_t)c * nfloats + i];
-  dtf[i] += s;
+// Task list of one backward launch: every (view, half tile) of the tile range contributes
+// ceil(kmax/S) segment tasks (kmax = the longest end slot among its 32 rays, recorded by the
+// checkpointing forward), or exactly one when the launch is unsegmented.
+__global__ void __launch_bounds__(256)
+mrt_bwd_tasks_kernel(int W, int H, int tile_begin, int tile_end, int nviews, int S, const int32_t* __restrict__ warp_kmax,
+                     uint2* __restrict__ tasks, unsigned* __restrict__ counters) {
+  const int nht = 2 * mrt_tiles_x_(W) * mrt_tiles_y_(H);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nviews * nht) return;
+  const int ht = (int)(i % nht), tile = ht >> 1;
+  if (tile < tile_begin || tile >= tile_end) return;
+  int nl = 1;
+  if (warp_kmax != nullptr) nl = (__ldg(warp_kmax + i) + S - 1) / S;
+  if (nl <= 0) return;
+  const unsigned base = atomicAdd(counters, (unsigned)nl);
+  for (int s = 0; s < nl; ++s) tasks[base + s] = make_uint2((unsigned)i, (unsigned)s);
+}
+
+// dtf[j] += sum over the privatised copies of lo[j] + hi[j-1]  (hi of the last entry belongs to itself)
+__global__ void mrt_dtf_reduce_kernel(const float4* __restrict__ priv, int ncopies, int ntf, float4* __restrict__ dtf) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ntf) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < ncopies; ++c) {
+    const float4* p = priv + (size_t)c * ntf * 2;
+    const float4 a = p[2 * j];
+    s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    if (j > 0) { const float4 b = p[2 * (j - 1) + 1]; s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w; }
+    if (j == ntf - 1) { const float4 b = p[2 * j + 1]; s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w; }
+  }
+  float4 d = dtf[j];
+  d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+  dtf[j] = d;
+}
+
+// scratch layout: [0,256) counters (ntasks, next) | privatised dL/dtf | task list
+static inline size_t bwd_priv_bytes(int ntf) { return (size_t)MRT_DTF_COPIES * ntf * 2 * sizeof(float4); }
+size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg) {
+  const size_t nht = 2 * (size_t)mrt_tiles_x_(W) * mrt_tiles_y_(H);
+  return 256 + bwd_priv_bytes(ntf) + nht * (size_t)nviews * (size_t)(nseg < 1 ? 1 : nseg) * sizeof(uint2);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      return 148;
+  }
+  return g_num_sms;
 }
 
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-static cudaError_t launch_bwd(const KParams& P, const void* vol, const float* tf, const uint8_t* flat_levels,
-                              const float* minmax, const int32_t* labels, const int32_t* preds,
-                              const float* out_rgba, const float* dL_dout, void* dvol, float* dtf, void* scratch,
-                              float* dray, cudaStream_t st) {
+static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const MrtBwdArgs& A,
+                              cudaStream_t st) {
   typedef typename Vox<NCH>::T VT;
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
-  const int grid = (ntiles + MRT_BWD_TPB - 1) / MRT_BWD_TPB;
   const int ntf = P.tfMode ? P.tfN : 2;
-  const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4);
-  if (dtf) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)MRT_DTF_COPIES * ntf * sizeof(float4), st);
-    if (e != cudaSuccess) return e;
-  }
-  mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC><<<grid, 64 * MRT_BWD_TPB, smem, st>>>(
-      P, (const VT*)vol, (const float4*)tf, flat_levels, (const float2*)minmax, labels, preds,
-      (const float4*)out_rgba, (const float4*)dL_dout, (VT*)dvol, dtf ? (float4*)scratch : nullptr, dray);
-  cudaError_t e = cudaGetLastError();
+  const int nht = 2 * mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
+  const bool seg = A.ck != nullptr && A.k_end != nullptr && A.warp_kmax != nullptr && A.seg_slots > 0;
+  unsigned char* scr = reinterpret_cast<unsigned char*>(A.scratch);
+  unsigned* counters = reinterpret_cast<unsigned*>(scr);
+  float4* priv = reinterpret_cast<float4*>(scr + 256);
+  uint2* tasks = reinterpret_cast<uint2*>(scr + 256 + bwd_priv_bytes(ntf));
+  cudaError_t e = cudaMemsetAsync(scr, 0, 256 + (A.dtf ? bwd_priv_bytes(ntf) : 0), st);
   if (e != cudaSuccess) return e;
-  if (dtf) {
-    mrt_dtf_reduce_kernel<<<(ntf * 4 + 255) / 256, 256, 0, st>>>((const float*)scratch, MRT_DTF_COPIES, ntf * 4, dtf);
+  const long long nthreads = (long long)nviews * nht;
+  mrt_bwd_tasks_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(P.W, P.H, P.tile_begin, P.tile_end, nviews,
+                                                                         seg ? A.seg_slots : 1, seg ? A.warp_kmax : nullptr,
+                                                                         tasks, counters);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+
+  // shared-memory histogram: LUTs of 16..256 entries (smaller ones collide in every slot, larger ones do not fit)
+  static const char* env_hist = getenv("MRT_BWD_HIST");
+  const bool hist = A.dtf != nullptr && P.tfMode && ntf >= 16 && ntf <= 256 && !(env_hist && env_hist[0] == '0');
+  const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4) +
+                      (hist ? (size_t)MRT_BWD_WARPS * ntf * 2 * sizeof(float4) : 0);
+  auto kern = mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * MRT_BWD_WARPS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const long long max_tasks = (long long)nviews * 2 * ntiles * (seg ? A.nseg : 1);
+  long long grid = (max_tasks + MRT_BWD_WARPS - 1) / MRT_BWD_WARPS;
+  if (grid > (long long)num_sms() * occ) grid = (long long)num_sms() * occ;
+  BwdIO IO = {};
+  IO.tf = (const float4*)A.tf; IO.flat_levels = A.flat_levels; IO.minmax = (const float2*)A.minmax;
+  IO.labels = A.labels; IO.preds = A.preds;
+  IO.out_rgba = (const float4*)A.out_rgba; IO.dL_dout = (const float4*)A.dL_dout;
+  IO.ck = seg ? (const float4*)A.ck : nullptr; IO.k_end = seg ? A.k_end : nullptr;
+  IO.dtf_priv = A.dtf ? priv : nullptr;
+  IO.dray = A.dray; IO.stats = (unsigned long long*)A.stats;
+  IO.tasks = tasks; IO.ntasks = counters; IO.next = counters + 1;
+  IO.S = seg ? A.seg_slots : 0; IO.nviews = nviews; IO.hist = hist ? 1 : 0;
+  kern<<<(unsigned)grid, 32 * MRT_BWD_WARPS, smem, st>>>(P, B, IO, (const VT*)vol, (VT*)A.dvol);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (A.dtf) {
+    mrt_dtf_reduce_kernel<<<(ntf + 127) / 128, 128, 0, st>>>(priv, MRT_DTF_COPIES, ntf, (float4*)A.dtf);
     e = cudaGetLastError();
   }
   return e;
 }
 
-size_t mrt_bwd_scratch_bytes(int ntf) { return (size_t)MRT_DTF_COPIES * ntf * sizeof(float4); }
-
 template <int NCH, bool SKIP>
-static cudaError_t dispatch_bwd(const KParams& P, bool lab, bool gen, const void* vol, const float* tf,
-                                const uint8_t* fl, const float* mm, const int32_t* labels, const int32_t* preds,
-                                const float* o, const float* g, void* dvol, float* dtf, void* scr, float* dray,
-                                cudaStream_t st) {
-  if (lab) return gen ? launch_bwd<NCH, true, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st)
-                      : launch_bwd<NCH, true, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st);
-  return gen ? launch_bwd<NCH, false, SKIP, true>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st)
-             : launch_bwd<NCH, false, SKIP, false>(P, vol, tf, fl, mm, labels, preds, o, g, dvol, dtf, scr, dray, st);
+static cudaError_t dispatch_bwd(const KParams& P, const CamBatch& B, int nviews, bool lab, bool gen, const void* vol,
+                                const MrtBwdArgs& A, cudaStream_t st) {
+  if (lab) return gen ? launch_bwd<NCH, true, SKIP, true>(P, B, nviews, vol, A, st)
+                      : launch_bwd<NCH, true, SKIP, false>(P, B, nviews, vol, A, st);
+  return gen ? launch_bwd<NCH, false, SKIP, true>(P, B, nviews, vol, A, st)
+             : launch_bwd<NCH, false, SKIP, false>(P, B, nviews, vol, A, st);
 }
 
-cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                                const uint8_t* flat_levels, const float* minmax,
-                                const int32_t* labels, const int32_t* preds, const float* out_rgba,
-                                const float* dL_dout, void* dvol, float* dtf, void* scratch, float* dray,
-                                cudaStream_t st) {
+// `cams` = nviews x 12 floats (eye, U, V, W per view), nullptr = the single camera in P; at most
+// MRT_MAX_VIEWS views per call (the C entry chunks).
+cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                const MrtBwdArgs& A, cudaStream_t st) {
+  CamBatch B;
+  if (cams == nullptr) {
+    nviews = 1;
+    for (int i = 0; i < 3; ++i) { B.cam[0][i] = P.eye[i]; B.cam[0][3 + i] = P.U[i]; B.cam[0][6 + i] = P.V[i]; B.cam[0][9 + i] = P.Wv[i]; }
+  } else {
+    if (nviews < 1 || nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;
+    for (int v = 0; v < nviews; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)v * 12 + i];
+  }
   const bool lab = (P.showSeg || P.showPred);
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f);
-  const bool skip = P.skip && flat_levels != nullptr && minmax != nullptr && P.tMode == 0 && packed_ch == 1;
+  const bool skip = P.skip && A.flat_levels != nullptr && A.minmax != nullptr && P.tMode == 0 && packed_ch == 1;
   switch (packed_ch) {
-    case 1: return skip ? dispatch_bwd<1, true>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st)
-                        : dispatch_bwd<1, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
-    case 2: return dispatch_bwd<2, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
-    case 4: return dispatch_bwd<4, false>(P, lab, gen, vol, tf, flat_levels, minmax, labels, preds, out_rgba, dL_dout, dvol, dtf, scratch, dray, st);
+    case 1: return skip ? dispatch_bwd<1, true>(P, B, nviews, lab, gen, vol, A, st)
+                        : dispatch_bwd<1, false>(P, B, nviews, lab, gen, vol, A, st);
+    case 2: return dispatch_bwd<2, false>(P, B, nviews, lab, gen, vol, A, st);
+    case 4: return dispatch_bwd<4, false>(P, B, nviews, lab, gen, vol, A, st);
   }
   return cudaErrorInvalidValue;
 }

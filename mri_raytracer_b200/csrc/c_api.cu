@@ -395,24 +395,102 @@ int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_outside_spans");
 }
 
-size_t mrt_backward_scratch_bytes(int32_t tfN) { return mrt_bwd_scratch_bytes(tfN < 2 ? 2 : tfN); }
+// ---------------------------------------------------------------- checkpointed forward + backward
+// Upper bound of any ray's slot count: the box diagonal (and the near/far window) over the step.
+static int max_ray_slots(const KParams& K) {
+  double d2 = 0.0;
+  for (int i = 0; i < 3; ++i) { const double e = (double)K.vs[i] * K.dims[i]; d2 += e * e; }
+  double len = sqrt(d2);
+  if (K.farT > 0.0f) { const double w = (double)K.farT - fmax(0.0, (double)K.nearT); if (w < len) len = w > 0.0 ? w : 0.0; }
+  double n = ceil(len / (double)K.dt) + 2.0;
+  if (K.maxSteps > 0 && n > K.maxSteps) n = K.maxSteps;
+  if (n > 2.0e9) n = 2.0e9;
+  return (int)n;
+}
+int mrt_checkpoint_plan(const MrtParams* params, int32_t seg_slots_hint, int32_t* seg_slots, int32_t* nseg) {
+  MRT_REQUIRE(params && seg_slots && nseg, "checkpoint_plan: null pointer");
+  KParams K;
+  MrtParams Pg = *params;
+  Pg.tfMode = 0;
+  if (int r = derive(&Pg, 1, 0, false, 0, 0, &K)) return r;
+  const int nmax = max_ray_slots(K);
+  int S = seg_slots_hint > 0 ? seg_slots_hint : 32;
+  const int max_seg = 64;
+  if ((nmax + S - 1) / S > max_seg) S = (((nmax + max_seg - 1) / max_seg) + 7) & ~7;
+  *seg_slots = S;
+  *nseg = (nmax + S - 1) / S < 1 ? 1 : (nmax + S - 1) / S;
+  return MRT_OK;
+}
+size_t mrt_checkpoint_bytes(int32_t W, int32_t H, int32_t nviews, int32_t nseg) {
+  if (W < 1 || H < 1 || nviews < 1 || nseg < 1) return 0;
+  return (size_t)(nseg - 1) * nviews * W * H * 4 * sizeof(float);
+}
+int32_t mrt_half_tile_count(int32_t W, int32_t H) { return 2 * mrt_tiles_x_(W) * mrt_tiles_y_(H); }
 
-int mrt_render_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+int mrt_render_forward_ckpt(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                            const void* packed, int32_t C, const float* tf, int32_t tfN,
+                            const uint8_t* skip_levels, const int32_t* labels, const int32_t* preds,
+                            float* out_rgba, float* ckpt, int32_t seg_slots, int32_t nseg,
+                            int32_t* k_end, int32_t* warp_kmax,
+                            int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && k_end && warp_kmax, "render_forward_ckpt: null pointer");
+  MRT_REQUIRE(seg_slots >= 1 && nseg >= 1 && (nseg == 1 || ckpt), "render_forward_ckpt: bad checkpoint plan");
+  MRT_REQUIRE(cams == nullptr || (nviews >= 1 && nviews <= MRT_MAX_VIEWS), "render_forward_ckpt: nviews outside 1..%d", MRT_MAX_VIEWS);
+  KParams K;
+  if (int r = derive(params, C, tfN, skip_levels != nullptr, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_ckpt: tfMode=1 needs tf");
+  if (K.half || K.shard || K.tMode != 0 || K.gamma != 1.0f)
+    return fail(MRT_ERR_UNSUPPORTED, "render_forward_ckpt: fp32 unsharded volumes, indexed stepping, gamma 1 only");
+  MRT_REQUIRE((long long)nseg * seg_slots >= max_ray_slots(K), "render_forward_ckpt: %d segments of %d slots cannot hold %d-slot rays",
+              nseg, seg_slots, max_ray_slots(K));
+  if (K.showSeg && !labels) K.showSeg = 0;
+  if (K.showPred && !preds) K.showPred = 0;
+  float chunk[MRT_MAX_VIEWS * 12];
+  if (cams) pack_cams(cams, nviews, chunk);
+  cudaError_t e = mrt_launch_forward_ckpt(K, cams ? chunk : nullptr, nviews, mrt_packed_channels(C), packed, tf, skip_levels,
+                                          labels, preds, out_rgba, ckpt, seg_slots, nseg, k_end, warp_kmax,
+                                          (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_ckpt");
+}
+
+size_t mrt_backward_scratch_bytes(int32_t W, int32_t H, int32_t nviews, int32_t tfN, int32_t nseg) {
+  if (W < 1 || H < 1 || nviews < 1) return 0;
+  return mrt_bwd_scratch_bytes(W, H, nviews, tfN < 2 ? 2 : tfN, nseg < 1 ? 1 : nseg);
+}
+
+int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                        const void* packed, int32_t C, const float* tf, int32_t tfN,
                         const uint8_t* flat_levels, const float* minmax,
                         const int32_t* labels, const int32_t* preds, const float* out_rgba, const float* dL_dout,
-                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray,
+                        const float* ckpt, int32_t seg_slots, int32_t nseg, const int32_t* k_end, const int32_t* warp_kmax,
+                        void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray, uint64_t* stats,
                         int32_t tile_begin, int32_t tile_end, void* stream) {
-  MRT_REQUIRE(packed && out_rgba && dL_dout, "render_backward: null pointer");
+  MRT_REQUIRE(packed && out_rgba && dL_dout && scratch, "render_backward: null pointer");
   MRT_REQUIRE(dL_dvol || dL_dtf || dL_dray, "render_backward: nothing to differentiate");
-  MRT_REQUIRE(!dL_dtf || scratch, "render_backward: dL_dtf needs the scratch buffer");
+  MRT_REQUIRE(cams == nullptr || (nviews >= 1 && nviews <= MRT_MAX_VIEWS), "render_backward: nviews outside 1..%d", MRT_MAX_VIEWS);
   KParams K;
   if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
   if (K.half) return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 volumes are forward-only");
+  if (K.shard) return fail(MRT_ERR_UNSUPPORTED, "render_backward: sharded volumes are forward-only");
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
+  const bool seg = k_end != nullptr || warp_kmax != nullptr || ckpt != nullptr;
+  if (seg) {
+    MRT_REQUIRE(k_end && warp_kmax && seg_slots >= 1 && nseg >= 1 && (nseg == 1 || ckpt),
+                "render_backward: the segmented path needs ckpt, k_end and warp_kmax of mrt_render_forward_ckpt");
+    MRT_REQUIRE(K.tMode == 0 && K.gamma == 1.0f, "render_backward: checkpoints need indexed stepping and gamma 1");
+  }
   if (K.showSeg && !labels) K.showSeg = 0;
   if (K.showPred && !preds) K.showPred = 0;
-  cudaError_t e = mrt_launch_backward(K, mrt_packed_channels(C), packed, tf, flat_levels, minmax, labels, preds,
-                                      out_rgba, dL_dout, dL_dvol, dL_dtf, scratch, dL_dray, (cudaStream_t)stream);
+  MrtBwdArgs A = {};
+  A.tf = tf; A.flat_levels = flat_levels; A.minmax = minmax; A.labels = labels; A.preds = preds;
+  A.out_rgba = out_rgba; A.dL_dout = dL_dout;
+  A.ck = seg ? (ckpt ? ckpt : out_rgba) : nullptr;   // nseg == 1: no checkpoint is ever read
+  A.seg_slots = seg_slots; A.nseg = nseg; A.k_end = k_end; A.warp_kmax = warp_kmax;
+  A.dvol = dL_dvol; A.dtf = dL_dtf; A.scratch = scratch; A.dray = dL_dray; A.stats = stats;
+  float chunk[MRT_MAX_VIEWS * 12];
+  if (cams) pack_cams(cams, nviews, chunk);
+  cudaError_t e = mrt_launch_backward(K, cams ? chunk : nullptr, cams ? nviews : 1, mrt_packed_channels(C), packed, A,
+                                      (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
 }
 

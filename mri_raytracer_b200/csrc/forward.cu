@@ -23,11 +23,14 @@
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
 #endif
 
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF>
+// CKPT (training forward): additionally stores (C, T) of every ray before each slot c*CK.S, the
+// ray's end slot and every warp's longest end slot, for the segment-parallel backward (backward.cu).
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF, bool CKPT = false>
 __global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 128 * MRT_FWD_MINB) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
                const __grid_constant__ StripTargets S,
+               const __grid_constant__ CkptOut CK,
                const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                const float4* __restrict__ tf,
                const uint8_t* __restrict__ levels,
@@ -59,7 +62,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   ActiveBox abox;
   bool stored = true;                 // sparse gather: tiles outside the view's spans are filled by the image's owner
   if (SKIP) {
-    if (!GENERIC) {                                                        // the counting variant needs every exact n
+    if (!GENERIC && !CKPT) {                                               // the counting / checkpointing variants need every exact n
       if (S.spans != nullptr) {
         // the view's precomputed spans (projected hull of the active box, mrt_view_spans) answer the
         // question for the whole tile: one load and two compares instead of a per-ray slab test
@@ -85,7 +88,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         maybe = false;                                                     // this warp only keeps the barrier company
       }
     }
-    if (GENERIC || S.spans != nullptr) abox = mrt_active_box(P, levels);   // (still needed to clip the slot ranges)
+    if (GENERIC || CKPT || S.spans != nullptr) abox = mrt_active_box(P, levels);   // (still needed to clip the slot ranges)
   }
 
   if (P.tfMode) mrt_tf_stage(s_tf, tf, P.tfN);
@@ -99,7 +102,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   }
   __syncthreads();
   if (tile >= P.tile_end) return;
-  if (SKIP && !GENERIC) { if (!__any_sync(0xffffffffu, maybe)) return; }   // culled warp (already stored)
+  if (SKIP && !GENERIC && !CKPT) { if (!__any_sync(0xffffffffu, maybe)) return; }   // culled warp (already stored)
 
   Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
   if (!maybe) ray.n = 0;
@@ -107,6 +110,17 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   float Cr = P.shard ? 0.0f : P.bg[0], Cg = P.shard ? 0.0f : P.bg[1], Cb = P.shard ? 0.0f : P.bg[2];   // :111
   float T = 1.0f;                                                          // :112
   int k = 0, n_eval = 0, n_seg = 0;
+  // checkpoint c (1 <= c < CK.nseg) = state before slot c*CK.S, layer c-1 of CK.ck ([layer][view][H][W])
+  int next_ck = CKPT ? CK.S : 0x7fffffff;
+  float4* ckp = CKPT ? CK.ck + pix : nullptr;
+  const size_t ck_layer = CKPT ? (size_t)gridDim.y * P.H * P.W : 0;
+  const int ck_end = CKPT ? CK.nseg * CK.S : 0;
+  auto ck_flush = [&](int kk) {          // the state is final for every slot boundary <= kk
+    while (next_ck <= kk && next_ck < ck_end) {
+      if (inside) *ckp = make_float4(Cr, Cg, Cb, T);
+      ckp += ck_layer; next_ck += CK.S;
+    }
+  };
 
   {                                           // rays with n == 0 (miss / outside) run zero iterations below
     const IdxRay q = mrt_index_ray(P, ray);
@@ -188,6 +202,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       for (;;) {
         if (k >= kact && T > thr) {                       // current run exhausted: take the look-ahead
           k = kf; kact = kl; kf = kl;                     // (not after ERT: k stays the oracle's n_taken)
+          if (CKPT) ck_flush(k);                          // the slots leapt over are no-ops
         }
         const bool live = (k < n) && (T > thr);            // :117
         // phase 1 (warp-wide): as soon as ONE lane has nothing to shade, EVERY lane extends its
@@ -237,11 +252,15 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
           if (on) {
             shade(fmaf((float)k, dt, ray.t0));
             ++k; if (GENERIC) ++n_eval;
+            if (CKPT) { if (k == next_ck) ck_flush(k); }
             on = T > thr;
           }
         }
       }
-      if (T > thr) k = n_full;             // ran to the end: the oracle's n_taken counts the clipped no-op slots too
+      if (T > thr) {                       // ran to the end: the oracle's n_taken counts the clipped no-op slots too
+        k = n_full;
+        if (CKPT) ck_flush(n_full - 1);
+      }
     } else {
       int n = ray.n;
       if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, 1.0f / dt, ray.n, &ks, &n); k = ks; }
@@ -255,8 +274,16 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         }
         shade(t);
         ++k; if (GENERIC) ++n_eval;
+        if (CKPT) { if (k == next_ck) ck_flush(k); }
       }
+      if (CKPT) { if (T > thr) ck_flush(n - 1); }
     }
+  }
+  if (CKPT) {                           // (culled warps / CTAs returned above: the launcher zero-fills both arrays)
+    const int km = __reduce_max_sync(0xffffffffu, inside ? k : 0);
+    const size_t nht = 2 * (size_t)mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
+    if (lane == 0) CK.warp_kmax[(size_t)view * nht + 2 * (size_t)tile + (warp & 1)] = km;
+    if (inside) CK.k_end[pix] = k;
   }
   if (!inside) return;
   *dst = make_float4(Cr, Cg, Cb, P.shard ? T : (P.alphaMode ? 1.0f - T : 1.0f));  // :167
@@ -270,18 +297,60 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
                                          int packed_ch, const void* vol, const float* tf, const uint8_t* levels,
                                          const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                                          int32_t* out_counts, cudaStream_t st);
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false>
+static const CkptOut g_no_ckpt = {};
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false, bool CKPT = false>
 static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, const StripTargets& S, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
-                              int32_t* out_counts, cudaStream_t st) {
+                              int32_t* out_counts, cudaStream_t st, const CkptOut& CK = g_no_ckpt) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
   const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
-  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
-      P, B, S, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
+  mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF, CKPT><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
+      P, B, S, CK, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);
   return cudaGetLastError();
+}
+
+// Training forward: one launch of <= MRT_MAX_VIEWS views that also records the checkpoints.
+template <int NCH>
+static cudaError_t dispatch_fwd_ckpt(const KParams& P, const CamBatch& B, int nviews, bool lab, bool skip, const void* vol,
+                                     const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
+                                     float* o, const CkptOut& CK, cudaStream_t st) {
+  if (lab) return skip ? launch_fwd<NCH, true, true, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
+                       : launch_fwd<NCH, true, false, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
+  return skip ? launch_fwd<NCH, false, true, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
+              : launch_fwd<NCH, false, false, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
+}
+cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                    const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
+                                    float* out_rgba, float* ck, int seg_slots, int nseg, int32_t* k_end, int32_t* warp_kmax,
+                                    cudaStream_t st) {
+  if (P.half || P.shard || P.tMode != 0 || P.gamma != 1.0f || seg_slots < 1 || nseg < 1 || !k_end || !warp_kmax ||
+      (nseg > 1 && !ck))
+    return cudaErrorInvalidValue;
+  CamBatch B;
+  if (cams == nullptr) {
+    nviews = 1;
+    for (int i = 0; i < 3; ++i) { B.cam[0][i] = P.eye[i]; B.cam[0][3 + i] = P.U[i]; B.cam[0][6 + i] = P.V[i]; B.cam[0][9 + i] = P.Wv[i]; }
+  } else {
+    if (nviews < 1 || nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;
+    for (int v = 0; v < nviews; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)v * 12 + i];
+  }
+  const size_t npix = (size_t)P.W * P.H, nht = 2 * (size_t)mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
+  cudaError_t e = cudaMemsetAsync(k_end, 0, npix * nviews * sizeof(int32_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(warp_kmax, 0, nht * nviews * sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  CkptOut CK;
+  CK.ck = reinterpret_cast<float4*>(ck); CK.S = seg_slots; CK.nseg = nseg; CK.k_end = k_end; CK.warp_kmax = warp_kmax;
+  const bool lab = (P.showSeg || P.showPred);
+  const bool skip = P.skip && levels != nullptr;
+  switch (packed_ch) {
+    case 1: return dispatch_fwd_ckpt<1>(P, B, nviews, lab, skip, vol, tf, levels, labels, preds, out_rgba, CK, st);
+    case 2: return dispatch_fwd_ckpt<2>(P, B, nviews, lab, skip, vol, tf, levels, labels, preds, out_rgba, CK, st);
+    case 4: return dispatch_fwd_ckpt<4>(P, B, nviews, lab, skip, vol, tf, levels, labels, preds, out_rgba, CK, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 template <int NCH>

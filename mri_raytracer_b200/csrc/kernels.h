@@ -21,12 +21,23 @@ cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nview
                                   cudaStream_t st);
 cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st);
 
-cudaError_t mrt_launch_backward(const KParams& P, int packed_ch, const void* vol, const float* tf,
-                                const uint8_t* flat_levels, const float* minmax,
-                                const int32_t* labels, const int32_t* preds,
-                                const float* out_rgba, const float* dL_dout,
-                                void* dvol, float* dtf, void* scratch, float* dray, cudaStream_t st);
-size_t mrt_bwd_scratch_bytes(int ntf);
+cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                    const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
+                                    float* out_rgba, float* ck, int seg_slots, int nseg, int32_t* k_end, int32_t* warp_kmax,
+                                    cudaStream_t st);
+
+// Everything mrt_launch_backward takes besides geometry and the volume.  ck / k_end / warp_kmax
+// (all three, from mrt_launch_forward_ckpt) switch on the segment-parallel path.
+struct MrtBwdArgs {
+  const float* tf; const uint8_t* flat_levels; const float* minmax;
+  const int32_t* labels; const int32_t* preds;
+  const float* out_rgba; const float* dL_dout;
+  const float* ck; int seg_slots, nseg; const int32_t* k_end; const int32_t* warp_kmax;
+  void* dvol; float* dtf; void* scratch; float* dray; void* stats;
+};
+cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
+                                const MrtBwdArgs& A, cudaStream_t st);
+size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg);
 
 cudaError_t mrt_launch_pack_f16(const void* planar_f16, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar_f16, cudaStream_t st);

@@ -64,6 +64,11 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // (much cheaper) replacement of the per-ray box test: one LDG + two compares per warp.
 struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; int store_outside; };
 
+// Outputs of the checkpointing (training) forward, consumed by the segment-parallel backward:
+// ck[(c-1)][view][H][W] = (C, T) of the ray before slot c*S (1 <= c < nseg), k_end[view][H][W] = the
+// ray's end slot (n_taken), warp_kmax[view][2*tiles] = the largest k_end of each half tile.
+struct CkptOut { float4* ck; int S, nseg; int32_t* k_end; int32_t* warp_kmax; };
+
 struct Ray {
   float ox, oy, oz, dx, dy, dz;
   float t0, t1;

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound(built_lib):
         assert hasattr(built_lib, n), f"libmrt.so lacks {n}"
         assert n in PROTOTYPES, f"_lib.py does not bind {n}"
     assert sorted(PROTOTYPES) == names
-    assert built_lib.mrt_version() == 100
+    assert built_lib.mrt_version() >= 200
     assert built_lib.mrt_last_error() is not None
 
 
@@ -96,3 +96,21 @@ def test_packed_params_equal_field_by_field_ctypes():
             s.shardEnabled = 1; s.shardLo[:] = list(P.shard[0]); s.shardHi[:] = list(P.shard[1])
         assert bytes(P.to_struct()) == bytes(s)
     assert C.sizeof(_lib.MrtCamera) == 64
+
+
+def test_checkpoint_plan_is_host_only(built_lib):
+    """mrt_checkpoint_plan: segments cover the longest possible ray (box diagonal / step), default 32
+    slots per segment, at most 64 segments (the segment grows instead)."""
+    from mri_raytracer_b200 import api
+    from scenes import framed_params
+    P = framed_params((256, 256, 256), 512, 512)
+    S, n = api.checkpoint_plan(P)
+    assert S == 32 and n * S >= 256 * 3 ** 0.5 / 0.5 and n <= 64
+    S4, n4 = api.checkpoint_plan(P, 4)
+    assert n4 <= 64 and S4 % 8 == 0 and n4 * S4 >= 887
+    P5 = framed_params((1024, 1024, 1024), 64, 64)
+    S5, n5 = api.checkpoint_plan(P5)
+    assert n5 <= 64 and n5 * S5 >= 1024 * 3 ** 0.5 / 0.5
+    assert built_lib.mrt_checkpoint_bytes(512, 512, 2, n) == (n - 1) * 2 * 512 * 512 * 16
+    assert built_lib.mrt_half_tile_count(37, 29) == 2 * 5 * 4
+    assert built_lib.mrt_backward_scratch_bytes(64, 64, 1, 256, 3) >= 64 * 256 * 32 + 128 * 3 * 8

@@ -138,3 +138,61 @@ def test_ray_parameter_gradients_match_oracle_autograd(cuda, C, use_tf, ortho):
     scale = float(want.abs().max())
     assert scale > 0
     assert float((got - want).abs().max()) <= 1e-3 * scale, (float((got - want).abs().max()), scale)
+
+
+def _prepared(vol, P, tf):
+    packed = api.pack_volume(vol)
+    Cn = vol.shape[0]
+    mm = api.build_occupancy(packed, Cn, P.dims)
+    bits = api.classify_bricks(P, mm, Cn, tf)
+    flat = api.classify_bricks(P, mm, Cn, tf, flat=True) if Cn == 1 else None
+    return packed, Cn, mm, bits, flat
+
+
+@pytest.mark.parametrize("C,seg_slots,tfN", [(1, 8, 64), (1, 40, 8), (4, 16, 32), (1, 8, 300)])
+def test_segmented_backward_equals_whole_ray_backward(cuda, C, seg_slots, tfN):
+    """The checkpointing forward reproduces the plain forward bit for bit and records every ray's end
+    slot; the segment-parallel backward (many short tasks per ray, shared-memory dL/dtf histogram for
+    16..256-entry LUTs, L2 reductions otherwise) equals the whole-ray backward to summation order."""
+    vol, _, P = small_scene(C=C, dims=(40, 36, 30), W=45, H=37, seed=31 + C)
+    P = replace(P, tfMode=1, alphaMode=1, bgColor=(0.2, 0.1, 0.0))
+    tf = ramp_tf(tfN, sigma_scale=12.0, cutoff=0.15).cuda()
+    packed, Cn, mm, bits, flat = _prepared(vol.cuda(), P, tf)
+    plain = api.render_forward(P, packed, Cn, tf, bits)
+    counts = torch.zeros((37, 45, 4), dtype=torch.int32, device="cuda")
+    api.render_forward(P, packed, Cn, tf, bits, out_counts=counts)
+    img, ck = api.render_forward_ckpt(P, None, packed, Cn, tf, bits, seg_slots=seg_slots)
+    assert torch.equal(img, plain)
+    assert torch.equal(ck.k_end[0], counts[..., 1])                      # integer work: bit-exact
+    assert ck.nseg >= 2 and int(ck.k_end.max()) > ck.seg_slots           # several segments really in play
+    G = torch.randn((37, 45, 4), generator=torch.Generator().manual_seed(5)).cuda()
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    dv0, dt0 = api.render_backward(P, packed, Cn, tf, None, None, plain, G, flat_levels=flat, minmax=mm)
+    dv1, dt1 = api.render_backward(P, packed, Cn, tf, None, None, plain, G, flat_levels=flat, minmax=mm, ckpt=ck, stats=stats)
+    assert _rel(dv1, dv0) <= 2e-5 and _rel(dt1, dt0) <= 2e-5
+    assert int(stats[0]) > 0 and int(stats[1]) > int(ck.warp_kmax.gt(0).sum())   # more tasks than half tiles
+
+
+def test_differentiable_batch_of_views(cuda):
+    """api.render_views on a tensor: ONE checkpointing march + ONE backward launch for all views;
+    gradients equal the sum of the per-view gradients and the oracle's autograd."""
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    import numpy as np
+    vol, _, P = small_scene(C=1, dims=(30, 28, 24), W=40, H=32, seed=17)
+    P = replace(P, tfMode=1)
+    tf = ramp_tf(32, sigma_scale=15.0, cutoff=0.1)
+    cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.3, initial_theta=0.4)
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 3)
+    G = torch.randn((3, 32, 40, 4), generator=torch.Generator().manual_seed(2))
+    v = vol.cuda().requires_grad_(True); t = tf.cuda().requires_grad_(True)
+    imgs = api.render_views(v, cams, t, P)
+    (imgs * G.cuda()).sum().backward()
+    vo = vol.clone().requires_grad_(True); to = tf.clone().requires_grad_(True)
+    tot = 0.0
+    for i, c in enumerate(cams):
+        ref = O.render(vo, P.with_camera(c), tf=to)
+        assert (imgs[i].detach().cpu() - ref.detach()).abs().max() <= 1e-4
+        tot = tot + (ref * G[i]).sum()
+    tot.backward()
+    assert _rel(v.grad.cpu(), vo.grad) <= RTOL and _rel(t.grad.cpu(), to.grad) <= RTOL
