@@ -589,8 +589,10 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planar, tf, P: RenderParams, labels, preds, fold, tile_range=None, cams=None):
         Cn = planar.shape[0]
-        fold = bool(fold) and Cn > 1
         want_occ = bool(P.skipEmpty) and P.tMode == "indexed"
+        # (a single modality takes the fold path too when the occupancy grid is wanted: its fused
+        # kernel lays the volume out and builds the brick min/max in one pass over the voxels)
+        fold = bool(fold) and (Cn > 1 or want_occ)
         mm = None
         if fold and want_occ:
             (packed, mm), Ce, Pe = fold_volume_occupancy(planar.detach(), P), 1, folded_params(P)

@@ -18,22 +18,29 @@
 //     ray is differentiated by ceil(k_end/S) independent warp tasks of <= S slots each;
 //   * persistent CTAs pull (view, half tile, segment) tasks from a compacted list through one atomic
 //     counter: no tail, any number of views per launch;
-//   * dL/dtf is accumulated in a per-WARP shared-memory histogram with plain read-modify-writes:
-//     lanes that hit the same LUT entry in the same slot are found with one MATCH.ANY and take
-//     turns (shared-memory fp32 atomics are CAS loops on sm_100a, and two 16-byte L2 reductions
-//     per sample were the round-1 kernel's dominant cost); bins shared by more than 4 lanes and
-//     LUTs too large for shared memory fall back to privatised L2 reductions;
-//   * dL/dvolume goes to L2 with native reductions (scalar for the folded / single-modality
-//     layout, red.v2/.v4 for interleaved).
+//   * dL/dtf goes to one of 64 privatised L2-resident copies with one 16-byte vector reduction per
+//     touched LUT entry (reduced by a tiny second kernel).  A per-warp shared-memory histogram
+//     (MATCH.ANY-ranked read-modify-writes, no atomics) was built and measured: it removes those
+//     reductions but its 8 KB per warp leave the SM with 12-28 KB of L1 for the gathers; at cfg3 it
+//     lost, 0.342 vs 0.295 ms (profiles/r02_time_bwd_cornercache_hist{0,1}.json), and was removed;
+//   * dL/dvolume: each lane keeps the eight weights of its current cell in registers (corner cache)
+//     and reduces into L2 only the corners it leaves behind when the ray moves to a neighbouring
+//     cell: ~3.5 instead of 8 native reductions per slot (scalar for the folded / single-modality
+//     layout, red.v2/.v4 for interleaved);
+//   * brick look-ups are warp-wide: when one lane runs out of known-active slots EVERY lane extends
+//     its knowledge by one cell at its own frontier (the forward's phase 1).
 // Cells that are flat (one value) and empty are leapt with their closed-form dL/dtf term.
 #include "march.cuh"
 #include "kernels.h"
 #include <limits.h>
-#include <stdlib.h>
 
-#define MRT_BWD_WARPS 8
+#ifndef MRT_BWD_WARPS
+#define MRT_BWD_WARPS 4
+#endif
+#ifndef MRT_BWD_MINB
+#define MRT_BWD_MINB 5           // resident CTAs per SM the register allocation aims for (102 registers)
+#endif
 #define MRT_DTF_COPIES 64     // privatised dL/dtf accumulators in L2 (CTA b uses copy b % 64)
-#define MRT_HIST_MAXMULT 4    // lanes sharing one LUT entry that still take turns in shared memory
 
 __device__ __forceinline__ void vox_atomic_add(float* p, float w, const KParams& P) {
   atomicAdd(p, w * P.wq[0]);
@@ -44,6 +51,13 @@ __device__ __forceinline__ void vox_atomic_add(float2* p, float w, const KParams
 __device__ __forceinline__ void vox_atomic_add(float4* p, float w, const KParams& P) {
   atomicAdd(p, make_float4(w * P.wq[0], w * P.wq[1], w * P.wq[2], w * P.wq[3]));
 }
+
+// Corner cache flushes (acc[i], i = x + 2y + 4z, belongs to voxel pb + x + y*sY + z*sZ).
+#define MRT_CORNER(pb, i) ((pb) + ((i) & 1) + (((i) >> 1) & 1) * sY + ((i) >> 2) * sZ)
+#define MRT_FLUSH1(pb, i) do { if (acc[i] != 0.0f) vox_atomic_add(MRT_CORNER(pb, i), acc[i], P); } while (0)
+#define MRT_FLUSH4(pb, a, b, c_, d) do { MRT_FLUSH1(pb, a); MRT_FLUSH1(pb, b); MRT_FLUSH1(pb, c_); MRT_FLUSH1(pb, d); } while (0)
+#define MRT_FLUSH_ALL(pb) do { MRT_FLUSH4(pb, 0, 1, 2, 3); MRT_FLUSH4(pb, 4, 5, 6, 7); \
+    acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = acc[5] = acc[6] = acc[7] = 0.0f; } while (0)
 
 // Everything the kernel reads or writes besides the volume, in one constant block.
 struct BwdIO {
@@ -56,47 +70,19 @@ struct BwdIO {
   float* dray;                 // [view][H][W][6]
   unsigned long long* stats;   // [0] lane-slots shaded, [1] warp tasks that did work
   const uint2* tasks; const unsigned* ntasks; unsigned* next;
-  int S, nviews, hist;
+  int S, nviews;
 };
 
-// dL/dtf of one slot for the whole warp (converged call, all 32 lanes).  Entry j0 gets (1-fr)*g,
-// entry j0+1 gets fr*g; both live side by side in the histogram row of j0.  Lanes with the same
-// j0 are ranked (MATCH.ANY) and do their read-modify-write in turn; the trip count is warp-uniform.
-__device__ __forceinline__ void hist_add(float4* __restrict__ hw, float4* __restrict__ gpriv, int lane, bool valid,
-                                         int j0, float fr, float4 g) {
-  const unsigned full = 0xffffffffu;
-  const unsigned peers = __match_any_sync(full, valid ? j0 : (-1 - lane));
-  const int mult = __popc(peers);
-  const int rank = __popc(peers & ((1u << lane) - 1u));
-  const bool in_smem = valid && mult <= MRT_HIST_MAXMULT;
-  const int rounds = __reduce_max_sync(full, in_smem ? mult : 0);
-  const float f0 = 1.0f - fr;
-  for (int r = 0; r < rounds; ++r) {
-    if (in_smem && rank == r) {
-      float4 a = hw[2 * j0], b = hw[2 * j0 + 1];
-      a.x = fmaf(f0, g.x, a.x); a.y = fmaf(f0, g.y, a.y); a.z = fmaf(f0, g.z, a.z); a.w = fmaf(f0, g.w, a.w);
-      b.x = fmaf(fr, g.x, b.x); b.y = fmaf(fr, g.y, b.y); b.z = fmaf(fr, g.z, b.z); b.w = fmaf(fr, g.w, b.w);
-      hw[2 * j0] = a; hw[2 * j0 + 1] = b;
-    }
-    __syncwarp();
-  }
-  if (valid && !in_smem) {
-    atomicAdd(gpriv + 2 * j0, make_float4(f0 * g.x, f0 * g.y, f0 * g.z, f0 * g.w));
-    if (fr != 0.0f) atomicAdd(gpriv + 2 * j0 + 1, make_float4(fr * g.x, fr * g.y, fr * g.z, fr * g.w));
-  }
-}
-
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
-__global__ void __launch_bounds__(32 * MRT_BWD_WARPS, 3)
+__global__ void __launch_bounds__(32 * MRT_BWD_WARPS, MRT_BWD_MINB)
 mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B,
                const __grid_constant__ BwdIO IO,
                const typename Vox<NCH>::T* __restrict__ vol, typename Vox<NCH>::T* __restrict__ dvol) {
   typedef typename Vox<NCH>::T VT;
-  extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels | [warps][ntf][2] histogram
+  extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels
   const int ntf = P.tfMode ? P.tfN : 2;
   TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);
   float4* s_lab = reinterpret_cast<float4*>(s_tf + ntf);
-  float4* s_hist = s_lab + 16;
   const unsigned full = 0xffffffffu;
 
   if (P.tfMode) {
@@ -115,13 +101,9 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
     }
   }
   const bool want_tf = IO.dtf_priv != nullptr;
-  const bool use_hist = want_tf && IO.hist;
-  if (use_hist)
-    for (int i = threadIdx.x; i < MRT_BWD_WARPS * ntf * 2; i += blockDim.x) s_hist[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* const hw = s_hist + (size_t)warp * ntf * 2;
+  const int lane = threadIdx.x & 31;
   float4* const gpriv = want_tf ? IO.dtf_priv + (size_t)(blockIdx.x & (MRT_DTF_COPIES - 1)) * ntf * 2 : nullptr;
   const bool seg = IO.k_end != nullptr;
   const int nht = 2 * mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
@@ -136,23 +118,31 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
   const bool acc_mode = GENERIC && P.tMode == 1;           // reference-faithful running sum t += dt (unsegmented only)
   unsigned n_shaded = 0, n_tasks = 0;
 
+  // the queue is read one task ahead: the atomic of the NEXT fetch is in flight while this task runs
+  unsigned t_raw = 0;
+  if (lane == 0) t_raw = atomicAdd(IO.next, 1u);
   for (;;) {
-    unsigned t_id = 0;
-    if (lane == 0) t_id = atomicAdd(IO.next, 1u);
-    t_id = __shfl_sync(full, t_id, 0);
+    const unsigned t_id = __shfl_sync(full, t_raw, 0);
     if (t_id >= ntasks) break;
     const uint2 task = __ldg(IO.tasks + t_id);
+    if (lane == 0) t_raw = atomicAdd(IO.next, 1u);
     const int view = (int)(task.x / (unsigned)nht), ht = (int)(task.x - (unsigned)view * (unsigned)nht), sg = (int)task.y;
     int px, py;
     mrt_pixel_of_tile_lane_fast(P, ht >> 1, mrt_logical_lane(ht & 1, lane), &px, &py);
     const bool inside = px < P.W && py < P.H;
     const size_t pixl = inside ? (size_t)py * P.W + px : 0, pix = (size_t)view * npix + pixl;
-    const float4 G = inside ? __ldg(IO.dL_dout + pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // everything the task needs from memory, requested together (one round trip, not four)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 G = inside ? __ldg(IO.dL_dout + pix) : zero4;
+    const float4 Cout = inside ? __ldg(IO.out_rgba + pix) : zero4;
+    const int ke = (seg && inside) ? __ldg(IO.k_end + pix) : 0;
+    float4 c0 = make_float4(P.bg[0], P.bg[1], P.bg[2], 1.0f);            // state before the segment's first slot
+    if (seg && sg > 0 && inside) c0 = __ldg(IO.ck + ((size_t)(sg - 1) * IO.nviews + view) * npix + pixl);
     bool live = inside && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || (P.alphaMode && G.w != 0.0f));
     int k0 = 0, k1 = INT_MAX;
     if (seg) {
       k0 = sg * IO.S;
-      k1 = inside ? min(__ldg(IO.k_end + pix), k0 + IO.S) : 0;
+      k1 = min(ke, k0 + IO.S);
       live = live && k1 > k0;
     }
     if (!__any_sync(full, live)) continue;
@@ -163,67 +153,74 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
     if (!live) k1 = k0;
     ++n_tasks;
 
-    const float4 Cout = live ? __ldg(IO.out_rgba + pix) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float S_tot = G.x * (Cout.x - P.bg[0]) + G.y * (Cout.y - P.bg[1]) + G.z * (Cout.z - P.bg[2]);
     // alphaMode 1: a = 1 - T_N  =>  dL/dT_N = -G.w ;  dsigma_i += -dt*T_N*dL/dT_N
     const float tn_term = P.alphaMode ? -(1.0f - Cout.w) * G.w : 0.0f;   // = T_N * dL/dT_N
-    float T = 1.0f, prefix = 0.0f;
-    if (seg && sg > 0 && live) {
-      const float4 c = __ldg(IO.ck + ((size_t)(sg - 1) * IO.nviews + view) * npix + pixl);
-      T = c.w;
-      prefix = G.x * (c.x - P.bg[0]) + G.y * (c.y - P.bg[1]) + G.z * (c.z - P.bg[2]);
-    }
+    float T = c0.w;
+    float prefix = G.x * (c0.x - P.bg[0]) + G.y * (c0.y - P.bg[1]) + G.z * (c0.z - P.bg[2]);
     const IdxRay q = mrt_index_ray(P, ray);
     const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
     const float inv_dt = 1.0f / dt;
     int k = k0, kact = k0;
     float tacc = ray.t0;
     int lj = -1; float lfr = 0.0f, lacc = 0.0f;                  // dL/dsigma of the flat-empty cells leapt so far (one LUT entry)
+    int ccx = -0x40000000, ccy = 0, ccz = 0;                     // corner cache: cell (none yet) and its eight weights
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
+    int kblk = -1;                                             // == kact: the cell at the frontier is known flat-empty (parked)
     for (;;) {
+      const bool alive = live && (seg || T > thr);
       if (SKIP) {
         // Flat-empty cells (every voxel of the cell holds the same value c AND sigma == 0 over the TF
         // bins c maps to AND no overlay label): all ns slots inside have the same (bin, frac, colour),
         // alpha == 0, so T, prefix and hence dL/dsigma are identical for every slot; the volume
         // gradient is exactly 0 (the LUT slope of sigma is 0 there and dL/dc = alpha*T*G = 0).
         // Their whole contribution is ns * dL/dsigma onto two LUT entries.
-        while (k >= kact && k < k1 && (seg || T > thr)) {
-          const float t = fmaf((float)k, dt, ray.t0);
-          const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-          const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);
-          const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
-          const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
-          const int bid = ((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx + (ix >> MRT_BRICK_SHIFT);
-          const int lvl = __ldg(IO.flat_levels + bid);
-          const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-          const int kend = min(k1, k + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
-          if (lvl) {
-            if (want_tf) {
-              const float cval = __ldg(&IO.minmax[(size_t)bid * NCH].x);
-              const float val = mrt_window<GENERIC>(P, cval * P.wq[0] + P.wbias);
-              if (P.tfMode || val > 0.0f) {
-                int j0; float fr;
-                const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
-                const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
-                const float dsig = (float)(kend - k) * dt * (T * gc - (S_tot - prefix) - tn_term);
-                if (j0 != lj || fr != lfr) {
-                  if (lj >= 0 && lacc != 0.0f) {
-                    atomicAdd(&gpriv[2 * lj].w, (1.0f - lfr) * lacc);
-                    if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
+        // Look-ups are warp-wide (an instruction costs the same for 1 lane or 32): as soon as ONE lane
+        // has no known-active slot left, EVERY lane extends its knowledge [k, kact) by one cell at
+        // its own frontier; a lane AT a flat-empty cell leaps it, a lane that finds one ahead parks.
+        const bool need = alive && k < k1 && k >= kact;
+        if (__any_sync(full, need)) {
+          if (alive && kact < k1 && (k >= kact || kblk != kact)) {
+            const float t = fmaf((float)kact, dt, ray.t0);
+            const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
+            const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);
+            const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
+            const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+            const int bid = ((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx + (ix >> MRT_BRICK_SHIFT);
+            const int lvl = __ldg(IO.flat_levels + bid);
+            const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+            const int kend = min(k1, kact + mrt_cell_slots(q, ivx, ivy, ivz, ix >> sh, iy >> sh, iz >> sh, sh, t, inv_dt));
+            if (!lvl) {
+              kact = kend;
+            } else if (k < kact) {
+              kblk = kact;
+            } else {
+              if (want_tf) {
+                const float cval = __ldg(&IO.minmax[(size_t)bid * NCH].x);
+                const float val = mrt_window<GENERIC>(P, cval * P.wq[0] + P.wbias);
+                if (P.tfMode || val > 0.0f) {
+                  int j0; float fr;
+                  const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
+                  const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
+                  const float dsig = (float)(kend - k) * dt * (T * gc - (S_tot - prefix) - tn_term);
+                  if (j0 != lj || fr != lfr) {
+                    if (lj >= 0 && lacc != 0.0f) {
+                      atomicAdd(&gpriv[2 * lj].w, (1.0f - lfr) * lacc);
+                      if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
+                    }
+                    lj = j0; lfr = fr; lacc = 0.0f;
                   }
-                  lj = j0; lfr = fr; lacc = 0.0f;
+                  lacc += dsig;
                 }
-                lacc += dsig;
               }
+              k = kact = kend;
             }
-            k = kend;
-          } else {
-            kact = kend;
           }
+          continue;
         }
       }
-      const bool on = live && (acc_mode ? (tacc < ray.t1 && (P.maxSteps == 0 || k < P.maxSteps)) : (k < k1)) &&
-                      (seg || T > thr);
+      const bool on = alive && (acc_mode ? (tacc < ray.t1 && (P.maxSteps == 0 || k < P.maxSteps)) : (k < k1));
       if (!__any_sync(full, on)) break;
       bool addtf = false;
       int j0 = 0; float fr = 0.0f;
@@ -271,14 +268,32 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
               if (wz != 0.0f) { atomicAdd(r + 2, wz); atomicAdd(r + 5, t * wz); }
             }
             if (dvol != nullptr && dv != 0.0f) {
-              const uint32_t b = (uint32_t)c.ix() + (uint32_t)c.iy() * sY + (uint32_t)c.iz() * sZ;
-              VT* p0 = dvol + b; VT* p1 = p0 + sY; VT* p2 = p0 + sZ; VT* p3 = p2 + sY;
+              // dL/dvolume through the eight trilinear weights, accumulated in the per-lane corner
+              // cache: consecutive slots of a ray share their cell or move to a face neighbour, so
+              // only the corners LEFT BEHIND are reduced into L2 (about 3.5 instead of 8 per slot;
+              // REDG costs about one LSU cycle per active lane, which is what bounded this kernel)
+              const int ix = c.ix(), iy = c.iy(), iz = c.iz();
+              const int ddx = ix - ccx, ddy = iy - ccy, ddz = iz - ccz;
+              if ((ddx | ddy | ddz) != 0) {
+                VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ);
+                if (max(max(abs(ddx), abs(ddy)), abs(ddz)) > 1) {
+                  MRT_FLUSH_ALL(pb);
+                } else {
+                  if (ddx > 0) { MRT_FLUSH4(pb, 0, 2, 4, 6); acc[0] = acc[1]; acc[2] = acc[3]; acc[4] = acc[5]; acc[6] = acc[7]; acc[1] = acc[3] = acc[5] = acc[7] = 0.0f; pb += 1; }
+                  if (ddx < 0) { MRT_FLUSH4(pb, 1, 3, 5, 7); acc[1] = acc[0]; acc[3] = acc[2]; acc[5] = acc[4]; acc[7] = acc[6]; acc[0] = acc[2] = acc[4] = acc[6] = 0.0f; pb -= 1; }
+                  if (ddy > 0) { MRT_FLUSH4(pb, 0, 1, 4, 5); acc[0] = acc[2]; acc[1] = acc[3]; acc[4] = acc[6]; acc[5] = acc[7]; acc[2] = acc[3] = acc[6] = acc[7] = 0.0f; pb += sY; }
+                  if (ddy < 0) { MRT_FLUSH4(pb, 2, 3, 6, 7); acc[2] = acc[0]; acc[3] = acc[1]; acc[6] = acc[4]; acc[7] = acc[5]; acc[0] = acc[1] = acc[4] = acc[5] = 0.0f; pb -= sY; }
+                  if (ddz > 0) { MRT_FLUSH4(pb, 0, 1, 2, 3); acc[0] = acc[4]; acc[1] = acc[5]; acc[2] = acc[6]; acc[3] = acc[7]; acc[4] = acc[5] = acc[6] = acc[7] = 0.0f; }
+                  if (ddz < 0) { MRT_FLUSH4(pb, 4, 5, 6, 7); acc[4] = acc[0]; acc[5] = acc[1]; acc[6] = acc[2]; acc[7] = acc[3]; acc[0] = acc[1] = acc[2] = acc[3] = 0.0f; }
+                }
+                ccx = ix; ccy = iy; ccz = iz;
+              }
               const float gx0 = 1.0f - c.fx, gy0 = 1.0f - c.fy, gz0 = 1.0f - c.fz;
               const float w00 = dv * gy0 * gz0, w10 = dv * c.fy * gz0, w01 = dv * gy0 * c.fz, w11 = dv * c.fy * c.fz;
-              vox_atomic_add(p0, w00 * gx0, P); vox_atomic_add(p0 + 1, w00 * c.fx, P);
-              vox_atomic_add(p1, w10 * gx0, P); vox_atomic_add(p1 + 1, w10 * c.fx, P);
-              vox_atomic_add(p2, w01 * gx0, P); vox_atomic_add(p2 + 1, w01 * c.fx, P);
-              vox_atomic_add(p3, w11 * gx0, P); vox_atomic_add(p3 + 1, w11 * c.fx, P);
+              acc[0] = fmaf(w00, gx0, acc[0]); acc[1] = fmaf(w00, c.fx, acc[1]);
+              acc[2] = fmaf(w10, gx0, acc[2]); acc[3] = fmaf(w10, c.fx, acc[3]);
+              acc[4] = fmaf(w01, gx0, acc[4]); acc[5] = fmaf(w01, c.fx, acc[5]);
+              acc[6] = fmaf(w11, gx0, acc[6]); acc[7] = fmaf(w11, c.fx, acc[7]);
             }
           }
           T *= (1.0f - alpha);
@@ -304,9 +319,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
         ++k; ++n_shaded;
         if (GENERIC) tacc += dt;
       }
-      if (use_hist) {
-        hist_add(hw, gpriv, lane, addtf, j0, fr, g4);
-      } else if (addtf) {
+      if (addtf) {
         const float f0 = 1.0f - fr;
         atomicAdd(gpriv + 2 * j0, make_float4(f0 * g4.x, f0 * g4.y, f0 * g4.z, f0 * g4.w));
         if (fr != 0.0f) atomicAdd(gpriv + 2 * j0 + 1, make_float4(fr * g4.x, fr * g4.y, fr * g4.z, fr * g4.w));
@@ -316,23 +329,15 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
       atomicAdd(&gpriv[2 * lj].w, (1.0f - lfr) * lacc);
       if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
     }
+    if (dvol != nullptr && ccx >= 0) {
+      VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ);
+      MRT_FLUSH_ALL(pb);
+    }
   }
 
   if (IO.stats != nullptr) {
     const unsigned s = __reduce_add_sync(full, n_shaded);
     if (lane == 0) { atomicAdd(IO.stats, (unsigned long long)s); atomicAdd(IO.stats + 1, (unsigned long long)n_tasks); }
-  }
-  if (use_hist) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < ntf * 2; i += blockDim.x) {
-      float4 s = s_hist[i];
-#pragma unroll
-      for (int w = 1; w < MRT_BWD_WARPS; ++w) {
-        const float4 v = s_hist[(size_t)w * ntf * 2 + i];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      if (s.x != 0.0f || s.y != 0.0f || s.z != 0.0f || s.w != 0.0f) atomicAdd(gpriv + i, s);
-    }
   }
 }
 
@@ -412,11 +417,7 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 
-  // shared-memory histogram: LUTs of 16..256 entries (smaller ones collide in every slot, larger ones do not fit)
-  static const char* env_hist = getenv("MRT_BWD_HIST");
-  const bool hist = A.dtf != nullptr && P.tfMode && ntf >= 16 && ntf <= 256 && !(env_hist && env_hist[0] == '0');
-  const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4) +
-                      (hist ? (size_t)MRT_BWD_WARPS * ntf * 2 * sizeof(float4) : 0);
+  const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4);
   auto kern = mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -435,7 +436,7 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   IO.dtf_priv = A.dtf ? priv : nullptr;
   IO.dray = A.dray; IO.stats = (unsigned long long*)A.stats;
   IO.tasks = tasks; IO.ntasks = counters; IO.next = counters + 1;
-  IO.S = seg ? A.seg_slots : 0; IO.nviews = nviews; IO.hist = hist ? 1 : 0;
+  IO.S = seg ? A.seg_slots : 0; IO.nviews = nviews;
   kern<<<(unsigned)grid, 32 * MRT_BWD_WARPS, smem, st>>>(P, B, IO, (const VT*)vol, (VT*)A.dvol);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
