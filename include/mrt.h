@@ -264,8 +264,10 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
  * Whole image only, skipping required.  `spans`: device int32[nviews][mrt_tiles_y(H)][2].
  * store_outside != 0: the march DOES store the background of the outside tiles itself — the
  * single-GPU fast path: the spans then only replace the per-ray box test of mrt_render_forward_batch
- * by one load and two compares per warp (same image, bit for bit); in this mode `spans` is pure
- * scratch: the call computes it itself (mrt_view_spans) before the march. */
+ * by one load and two compares per warp (same image, bit for bit).  store_outside == 1: `spans` is
+ * pure scratch, the call computes it itself (mrt_view_spans) before the march; == 2: `spans` already
+ * holds mrt_view_spans of the same arguments.
+ * The camera basis (U, V, W) may be any non-degenerate basis; a degenerate one disables the cull. */
 int mrt_view_spans(const MrtParams* params, const MrtCamera* cams, int32_t nviews, int32_t C,
                    const uint8_t* skip_levels, int32_t* spans, void* stream);
 int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
@@ -410,8 +412,8 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
 /* ------------------------------------------------ host-buffer pipeline
  * mrt_render_host for a host that renders step after step (each step: a [C][Z][Y][X] volume, a TF
  * and `nviews` cameras in, `nviews` frames out — the reference's load_dir + frame loop,
- * inr/viewer/brats_viewer.py:188-248,369-450, without a window): a double-buffered object that
- * owns its device buffers and three streams (upload / prepare+march / download), so that the
+ * inr/viewer/brats_viewer.py:188-248,369-450, without a window): a multi-buffered object that
+ * owns its device buffers and four streams (upload / prepare / march / download), so that the
  * download of step i, the compute of step i+1 and the upload of step i+2 overlap.  Host buffers
  * should be page-locked for the copies to be asynchronous.  submit() returns after queueing;
  * wait(ticket) blocks until that step's frames are in out_rgba_host.  Fixed geometry per object
@@ -419,10 +421,28 @@ int mrt_render_host(const MrtParams* params, const float* planar_host, int32_t C
 typedef struct MrtHostPipeline MrtHostPipeline;
 int mrt_host_pipeline_create(MrtHostPipeline** out, int32_t C, int32_t X, int32_t Y, int32_t Z,
                              int32_t W, int32_t H, int32_t max_views, int32_t max_tfN, int32_t depth);
+/* Make a planar [C][Z][Y][X] fp32 host volume RESIDENT on the device (queued; returns at once; the
+ * host buffer must stay valid until the next wait()).  This is the reference's own split: it uploads
+ * the modality buffers once in load_dir (inr/viewer/brats_viewer.py:219-230) and per frame only
+ * refills `gParams` (:405-426).  Steps submitted with planar_host == NULL render the resident volume. */
+int mrt_host_pipeline_set_volume(MrtHostPipeline* p, const float* planar_host);
+/* out_flags */
+#define MRT_OUT_FRESH 1   /* out_rgba_host holds unknown data: write the whole background, not just the damage */
+/* Queue one step.  planar_host: this step's own volume (uploaded now), or NULL for the resident one.
+ * Frames come back sparse when skipping is on (skipEmpty, tMode 0, gamma 1): per view only the
+ * bounding rectangle of the tiles that can differ from the background crosses PCIe; the rest of the
+ * host frame is kept at the background by the pipeline, which remembers what it last wrote into
+ * each output buffer and clears only the damage.  Contract: an out_rgba_host buffer that was handed
+ * to submit() is written by nobody else until mrt_host_pipeline_forget() or the pipeline's
+ * destruction (or pass MRT_OUT_FRESH), and is not submitted again before its ticket was waited for.
+ * The frames in host memory equal mrt_render_forward_batch + a dense download, bit for bit. */
 int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                              const float* planar_host, const float* tf_host, int32_t tfN,
-                             float* out_rgba_host, int64_t* ticket);
+                             float* out_rgba_host, int32_t out_flags, int64_t* ticket);
 int mrt_host_pipeline_wait(MrtHostPipeline* p, int64_t ticket);
+/* Bytes moved by the last submitted step: [0] host->device, [1] device->host, [2] host-side background fill. */
+void mrt_host_pipeline_last_bytes(const MrtHostPipeline* p, uint64_t out3[3]);
+void mrt_host_pipeline_forget(MrtHostPipeline* p, const float* out_rgba_host);
 const char* mrt_host_pipeline_error(const MrtHostPipeline* p);
 void mrt_host_pipeline_destroy(MrtHostPipeline* p);
 

@@ -123,7 +123,10 @@ PROTOTYPES = {
     "mrt_render_forward_strips": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mrt_gather_probe": (C.c_int, [_vp, _sz, _sz, _u32, _vp, _vp]),
     "mrt_host_pipeline_create": (C.c_int, [C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
-    "mrt_host_pipeline_submit": (C.c_int, [_vp, _PP, _vp, _i32, _vp, _vp, _i32, _vp, C.POINTER(C.c_int64)]),
+    "mrt_host_pipeline_set_volume": (C.c_int, [_vp, _vp]),
+    "mrt_host_pipeline_submit": (C.c_int, [_vp, _PP, _vp, _i32, _vp, _vp, _i32, _vp, _i32, C.POINTER(C.c_int64)]),
+    "mrt_host_pipeline_last_bytes": (None, [_vp, C.POINTER(C.c_uint64 * 3)]),
+    "mrt_host_pipeline_forget": (None, [_vp, _vp]),
     "mrt_host_pipeline_wait": (C.c_int, [_vp, C.c_int64]),
     "mrt_host_pipeline_error": (C.c_char_p, [_vp]),
     "mrt_host_pipeline_destroy": (None, [_vp]),

@@ -815,12 +815,19 @@ def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, 
 
 
 class HostPipeline:
-    """Host buffers in, host frames out, double-buffered (``mrt_host_pipeline_*``): per step a
-    ``[C,Z,Y,X]`` float32 host volume, an optional ``[N,4]`` TF and a list of cameras go in, and
-    ``[V,H,W,4]`` frames land in a host array.  Upload, prepare+march and download of successive
-    steps overlap (three streams); pass page-locked arrays (e.g. ``torch.Tensor.pin_memory()``
+    """Host buffers in, host frames out, pipelined (``mrt_host_pipeline_*``): per step a list of
+    cameras, params and an optional ``[N,4]`` TF go in — plus a ``[C,Z,Y,X]`` float32 host volume, or
+    ``None`` to render the RESIDENT volume uploaded once with :meth:`set_volume`, the way the
+    reference uploads its buffers at load time and only refills ``gParams`` per frame — and
+    ``[V,H,W,4]`` frames land in a host array.  Upload, prepare, march and download of successive
+    steps overlap (four streams); pass page-locked arrays (e.g. ``torch.Tensor.pin_memory()``
     ``.numpy()``) so the copies are asynchronous.  ``submit`` queues a step and returns a ticket;
-    ``wait`` blocks until that step's frames are on the host."""
+    ``wait`` blocks until that step's frames are on the host.
+
+    Frames are downloaded sparse (only each view's bounding rectangle of non-background tiles); the
+    pipeline keeps the rest of an output array at the background colour by tracking what it last
+    wrote there.  An array handed to ``submit`` therefore belongs to the pipeline until
+    :meth:`forget` / :meth:`close`: do not write to it in between."""
 
     def __init__(self, C_: int, dims, image_size, max_views: int, max_tf: int = 256, depth: int = 2):
         X, Y, Z = (int(v) for v in dims)
@@ -831,13 +838,32 @@ class HostPipeline:
         if rc != 0:
             raise _lib.MrtError(f"host_pipeline_create failed ({rc})")
         self._keep = {}
+        self._outs = {}          # address -> array: the outputs the pipeline tracks (kept alive so addresses are not recycled)
+        self._resident = None
 
-    def submit(self, volume: np.ndarray, cams: Sequence, params: RenderParams, tf: Optional[np.ndarray],
-               out: np.ndarray) -> int:
+    def _err(self, what, rc):
+        return _lib.MrtError(f"{what} failed ({rc}): {lib().mrt_host_pipeline_error(self._h).decode('utf-8', 'replace')}")
+
+    def _check_volume(self, volume):
         X, Y, Z = self.dims
-        W, H = self.image_size
         if volume.dtype != np.float32 or not volume.flags.c_contiguous or volume.shape != (self.C, Z, Y, X):
             raise ValueError(f"volume must be C-contiguous float32 {(self.C, Z, Y, X)}")
+
+    def set_volume(self, volume: np.ndarray):
+        """Upload ``volume`` once; later ``submit(None, ...)`` calls render it."""
+        self._check_volume(volume)
+        rc = lib().mrt_host_pipeline_set_volume(self._h, volume.ctypes.data)
+        if rc != 0:
+            raise self._err("host_pipeline_set_volume", rc)
+        self._resident = volume
+
+    def submit(self, volume: Optional[np.ndarray], cams: Sequence, params: RenderParams, tf: Optional[np.ndarray],
+               out: np.ndarray, fresh: bool = False) -> int:
+        W, H = self.image_size
+        if volume is not None:
+            self._check_volume(volume)
+        elif self._resident is None:
+            raise ValueError("no volume: pass one or call set_volume() first")
         V = len(cams)
         if out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (V, H, W, 4):
             raise ValueError(f"out must be C-contiguous float32 {(V, H, W, 4)}")
@@ -847,20 +873,33 @@ class HostPipeline:
         s = P.to_struct()
         arr = _camera_array(cams)
         ticket = C.c_int64(-1)
-        rc = lib().mrt_host_pipeline_submit(self._h, C.byref(s), arr.ctypes.data, V, volume.ctypes.data,
+        addr = out.ctypes.data
+        flags = 1 if (fresh or addr not in self._outs) else 0
+        rc = lib().mrt_host_pipeline_submit(self._h, C.byref(s), arr.ctypes.data, V,
+                                            None if volume is None else volume.ctypes.data,
                                             None if tf is None else tf.ctypes.data, 0 if tf is None else tf.shape[0],
-                                            out.ctypes.data, C.byref(ticket))
+                                            addr, flags, C.byref(ticket))
         if rc != 0:
-            raise _lib.MrtError(f"host_pipeline_submit failed ({rc}): "
-                                f"{lib().mrt_host_pipeline_error(self._h).decode('utf-8', 'replace')}")
+            raise self._err("host_pipeline_submit", rc)
+        self._outs[addr] = out
         self._keep[ticket.value] = (volume, tf, out)      # the host buffers must outlive the queued copies
         return int(ticket.value)
+
+    def last_bytes(self):
+        """(host->device, device->host, host background fill) bytes of the last submitted step."""
+        b = (C.c_uint64 * 3)()
+        lib().mrt_host_pipeline_last_bytes(self._h, C.byref(b))
+        return int(b[0]), int(b[1]), int(b[2])
+
+    def forget(self, out: np.ndarray):
+        """Stop tracking ``out`` (the caller wants to write to it, or to free it)."""
+        lib().mrt_host_pipeline_forget(self._h, out.ctypes.data)
+        self._outs.pop(out.ctypes.data, None)
 
     def wait(self, ticket: int):
         rc = lib().mrt_host_pipeline_wait(self._h, int(ticket))
         if rc != 0:
-            raise _lib.MrtError(f"host_pipeline_wait failed ({rc}): "
-                                f"{lib().mrt_host_pipeline_error(self._h).decode('utf-8', 'replace')}")
+            raise self._err("host_pipeline_wait", rc)
         for t in [t for t in self._keep if t <= ticket]:
             del self._keep[t]
 
@@ -868,6 +907,7 @@ class HostPipeline:
         if self._h:
             lib().mrt_host_pipeline_destroy(self._h)
             self._h = C.c_void_p()
+            self._outs.clear()
 
     def __del__(self):
         try:

@@ -368,7 +368,7 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
   for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     pack_cams(cams + v0, nv, chunk);
-    if (store_outside)      // single-GPU fast path: the spans are this call's own scratch, computed here
+    if (store_outside == 1) // single-GPU fast path: the spans are this call's own scratch, computed here
       e = mrt_launch_view_spans(K, chunk, nv, skip_levels, const_cast<int32_t*>(spans) + (size_t)v0 * 2 * mrt_tiles_y_(K.H),
                                 (cudaStream_t)stream);
     if (e != cudaSuccess) break;

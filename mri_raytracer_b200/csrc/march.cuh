@@ -217,6 +217,15 @@ __device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __r
                                               int band) {
   const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
   if (A.hi[0] < A.lo[0]) return make_int2(1, 0);                           // no active brick
+  // camera coordinates of a world offset w: (xc, yc, zc) = M^-1 w with M = [U V W] — rows (VxW, WxU,
+  // UxV)/det, which is M^T for the orthonormal bases the cameras produce but stays correct for any
+  // basis the C ABI lets through (the exact ray set-up never assumes orthonormality either)
+  const float r0x = V[1] * Wv[2] - V[2] * Wv[1], r0y = V[2] * Wv[0] - V[0] * Wv[2], r0z = V[0] * Wv[1] - V[1] * Wv[0];
+  const float r1x = Wv[1] * U[2] - Wv[2] * U[1], r1y = Wv[2] * U[0] - Wv[0] * U[2], r1z = Wv[0] * U[1] - Wv[1] * U[0];
+  const float r2x = U[1] * V[2] - U[2] * V[1], r2y = U[2] * V[0] - U[0] * V[2], r2z = U[0] * V[1] - U[1] * V[0];
+  const float det = U[0] * r0x + U[1] * r0y + U[2] * r0z;
+  if (!(fabsf(det) > 1e-12f)) return make_int2(0, P.W - 1);                // degenerate basis: no culling
+  const float idet = 1.0f / det;
   const float m = MRT_SPAN_MARGIN - MRT_BOX_MARGIN;
   const float aspect = (float)P.W / fmaxf(1.0f, (float)P.H);
   float cx[8], cy[8];
@@ -227,9 +236,9 @@ __device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __r
     const float iy = (c & 2) ? A.hi[1] + m : A.lo[1] - m;
     const float iz = (c & 4) ? A.hi[2] + m : A.lo[2] - m;
     const float wx = P.bmin[0] + ix * P.vs[0] - eye[0], wy = P.bmin[1] + iy * P.vs[1] - eye[1], wz = P.bmin[2] + iz * P.vs[2] - eye[2];
-    const float xc = wx * U[0] + wy * U[1] + wz * U[2];
-    const float yc = wx * V[0] + wy * V[1] + wz * V[2];
-    const float zc = wx * Wv[0] + wy * Wv[1] + wz * Wv[2];
+    const float xc = (wx * r0x + wy * r0y + wz * r0z) * idet;
+    const float yc = (wx * r1x + wy * r1y + wz * r1z) * idet;
+    const float zc = (wx * r2x + wy * r2y + wz * r2z) * idet;
     float uvx, uvy;
     if (P.ortho) {
       uvx = xc / (aspect * P.halfH); uvy = -yc / P.halfH;

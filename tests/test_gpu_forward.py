@@ -271,6 +271,43 @@ def test_host_pipeline_equals_device_renders(cuda, C, use_tf):
     pipe.close()
 
 
+def test_host_pipeline_resident_volume_sparse_download_and_damage_tracking(cuda):
+    """Resident volume (set_volume once, the reference's load-time upload) + sparse frame download:
+    only each view's bounding rectangle of non-background tiles crosses PCIe, the pipeline keeps the
+    rest of the host frame at the background.  Output arrays are REUSED across steps whose cameras
+    move (so the rectangle moves, shrinks, vanishes and the background colour changes): the host
+    frames must equal the device-side renders bit for bit every time."""
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    dims, W, H, V = (40, 36, 28), 75, 53, 2
+    vol, _, P = small_scene(C=4, dims=dims, W=W, H=H, seed=3)
+    tf = ramp_tf(64)
+    Vd = api.Volume(vol.cuda())
+    pipe = api.HostPipeline(4, dims, (W, H), max_views=V, max_tf=64, depth=3)
+    vh = vol.pin_memory()
+    pipe.set_volume(vh.numpy())
+    outs = [torch.full((V, H, W, 4), 7.0).pin_memory() for _ in range(2)]        # garbage: must be overwritten
+    total_d2h = 0
+    for step in range(7):
+        cam = Vd.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.7 * step, initial_phi=1.3))
+        cam.set_fov_degrees(70.0)
+        cam.radius *= (1.0, 1.6, 0.8, 2.5, 1.0, 1.0, 1.2)[step]                   # the footprint grows and shrinks
+        if step == 4:
+            cam.target = cam.target + np.float32(50.0)                            # looks away from the volume
+        cams = orbit_views(cam, V)
+        Ps = replace(P, bgColor=(0.1, 0.2, 0.3) if step >= 5 else (0.0, 0.0, 0.0),
+                     volWeight=(1.0, 0.5 + 0.1 * step, 2.0, 0.75))
+        out = outs[step % 2]
+        pipe.wait(pipe.submit(None, cams, Ps, tf.numpy(), out.numpy()))
+        up, down, fill = pipe.last_bytes()
+        total_d2h += down
+        assert up < 4096 + 64 * 16                                                # cameras, params, TF: no volume
+        ref = api.render_views(Vd, cams, tf.cuda(), Ps)
+        assert torch.equal(out, ref.cpu()), f"step {step} differs"
+    assert total_d2h < 7 * V * H * W * 16                                         # less than dense downloads
+    pipe.forget(outs[0].numpy())
+    pipe.close()
+
+
 def test_bad_arguments_raise(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     V = api.Volume(vol.cuda())

@@ -86,10 +86,69 @@ def cfg3():
         return loss
 
     ms = timeit(step, reps=2)
+    # the same step captured once in a CUDA graph and replayed (the step is ~25 short launches: eager
+    # Python + ctypes launch overhead is a third of its wall time)
+    ms_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        v.grad = None; t.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_g = ((api.render(v, None, t, P) - target) ** 2).mean()
+            loss_g.backward()
+        gv_eager = None
+        graph.replay(); torch.cuda.synchronize()
+        gv_graph = v.grad.clone(); gt_graph = t.grad.clone()
+        ms_graph = timeit(graph.replay, reps=4)
+        v.grad = None; t.grad = None
+        step(); torch.cuda.synchronize()
+        graph_rel = float((gv_graph - v.grad).abs().max() / v.grad.abs().max()), float((gt_graph - t.grad).abs().max() / t.grad.abs().max())
+    except Exception as e:                      # report, do not hide
+        graph_rel = f"graph capture failed: {type(e).__name__}: {e}"
     Vv = api.Volume(vol.cuda())
     _, _, counts = api.render_aux(Vv, None, tf.cuda(), P)
     c = counts.sum(dim=(0, 1)).tolist()
     ms_fwd = timeit(lambda: api.render(Vv, None, t.detach(), P), reps=4)
+    # ---- the two kernels of the step on their own (CUDA events), and the backward's roofline record
+    td = t.detach()
+    packed, mm = api.fold_volume_occupancy(vol.cuda(), P)
+    Pe = api.folded_params(P)
+    bits = api.classify_bricks(Pe, mm, 1, td)
+    flat = api.classify_bricks(Pe, mm, 1, td, flat=True)
+    img, ck = api.render_forward_ckpt(Pe, None, packed, 1, td, bits)
+    g = (2.0 / img.numel()) * (img - target)
+    ms_fwd_ckpt = timeit(lambda: api.render_forward_ckpt(Pe, None, packed, 1, td, bits), reps=4)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    api.render_backward(Pe, packed, 1, td, None, None, img, g, flat_levels=flat, minmax=mm, ckpt=ck, stats=stats)
+    shaded, tasks = (int(x) for x in stats.tolist())
+    ms_bwd = timeit(lambda: api.render_backward(Pe, packed, 1, td, None, None, img, g, flat_levels=flat, minmax=mm, ckpt=ck), reps=4)
+    ms_bwd_whole = timeit(lambda: api.render_backward(Pe, packed, 1, td, None, None, img, g, flat_levels=flat, minmax=mm), reps=4)
+    import json as _json
+    peaks = ROOT / "MEASURED_PEAKS.json"
+    peak = float(_json.loads(peaks.read_text())["hbm_gbs"]) if peaks.exists() else 6650.0
+    bytes_per_sample = 64                       # 32 B re-read of the 8 corners + 8 x 4 B of atomic read-modify-write
+    achieved = shaded * bytes_per_sample / (ms_bwd * 1e-3) / 1e9
+    prof = ROOT / "profiles" / "r02_bwd_cfg3.json"
+    issue = None
+    if prof.exists():
+        try:
+            issue = float(_json.loads(prof.read_text())[0]["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0])
+        except Exception:
+            issue = None
+    roof = {"kernel": "mrt_bwd_kernel<1,false,true,false> (segment-parallel)", "bound": "issue slots + L2 reductions (see profiles/r02_bwd_cfg3.json)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.exists() else "fallback 6.65 TB/s",
+            "bytes_per_sample": bytes_per_sample, "shaded_samples_per_launch": shaded, "warp_tasks_per_launch": tasks,
+            "segments": ck.nseg, "slots_per_segment": ck.seg_slots, "avg_launch_ms": ms_bwd,
+            "issue_active_pct_ncu": issue,
+            "note": "bytes = samples the backward really shades x (32 B gathered + 32 B reduced); ms = the whole mrt_render_backward "
+                    "call (dvol memset, task list, march, dL/dtf reduce). The volume and its gradient are L2-resident, so HBM is the "
+                    "reference line SURVEY 8(d) asks for, not what binds"}
     # gradient parity on a small scene (the oracle's autograd cannot hold 256^3 x 512^2)
     from scenes import small_scene
     from oracle import oracle_torch as O
@@ -102,9 +161,10 @@ def cfg3():
     api.render(ga, None, gb, sP).square().mean().backward()
     rel_v = float((ga.grad.cpu() - a.grad).abs().max() / a.grad.abs().max())
     rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
-    return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_fwd_only=ms_fwd, steps_per_s=1e3 / ms, samples_taken=c[1],
-                gsamples_per_s_fwd_bwd=c[1] / ms / 1e6, grad_rel_volume=rel_v, grad_rel_tf=rel_t,
-                note="fwd+bwd through the autograd API incl. pack, occupancy build, classify, march, adjoint, unpack")
+    return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_fwd_bwd_cuda_graph=ms_graph, graph_vs_eager_grad_rel=graph_rel, ms_fwd_only=ms_fwd, ms_forward_ckpt_kernel=ms_fwd_ckpt, ms_backward_call=ms_bwd,
+                ms_backward_whole_ray=ms_bwd_whole, steps_per_s=1e3 / ms, samples_taken=c[1],
+                gsamples_per_s_fwd_bwd=c[1] / ms / 1e6, grad_rel_volume=rel_v, grad_rel_tf=rel_t, roofline=roof,
+                note="fwd+bwd through the autograd API incl. layout + occupancy build, classify, checkpointing march, adjoint, unfold")
 
 
 def cfg4():
