@@ -276,6 +276,20 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
                                     int32_t store_outside, void* stream);
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews,
                            float* out_rgba, void* stream);
+/* Image-space partition across GPUs with the framebuffer gather done by the march's own stores
+ * (north_star: "partitioned by image-space tiles with the volume replicated, framebuffer gathered
+ * over NCCL/NVLink"): like mrt_render_forward_batch_sparse, but
+ *   view_out_dev : DEVICE array of nviews pointers, the [H][W] float4 frame of each view — local or
+ *                  peer-mapped memory of whichever GPU owns that view (frames striped over the ranks
+ *                  spread the ingress instead of funnelling it into one root);
+ *   row_mod, row_rem : render only tile rows ty with ty % row_mod == row_rem (row_mod <= 1: all) —
+ *                  rank r of R passes (R, r); rows are interleaved because the object sits mid-image.
+ * `spans` from mrt_view_spans of the same cameras (every rank computes the same integers).  The
+ * union over row_rem = 0..row_mod-1 equals mrt_render_forward_batch, bit for bit. */
+int mrt_render_forward_batch_scatter(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                     const uint8_t* skip_levels, float* const* view_out_dev, const int32_t* spans,
+                                     int32_t store_outside, int32_t row_mod, int32_t row_rem, void* stream);
 
 /* ------------------------------------------------ training forward (checkpoints)
  * The forward of differentiable rendering.  docs/DifferentiableRendering.md:213 ("checkpointing")

@@ -105,6 +105,7 @@ PROTOTYPES = {
     "mrt_view_spans": (C.c_int, [_PP, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_fill_outside_spans": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
+    "mrt_render_forward_batch_scatter": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mrt_checkpoint_plan": (C.c_int, [_PP, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "mrt_checkpoint_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mrt_half_tile_count": (_i32, [_i32, _i32]),

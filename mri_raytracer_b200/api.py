@@ -221,6 +221,24 @@ def render_forward_batch_sparse(P: RenderParams, cams: Sequence, packed: torch.T
           "render_forward_batch_sparse")
 
 
+def render_forward_batch_scatter(P: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
+                                 tf: Optional[torch.Tensor], skip_levels: torch.Tensor, view_ptrs: torch.Tensor,
+                                 spans: torch.Tensor, store_outside: bool = False, row_mod: int = 0, row_rem: int = 0):
+    """``mrt_render_forward_batch_scatter``: view ``v`` of the batch is stored to the frame at device
+    address ``view_ptrs[v]`` (int64 CUDA tensor; local or peer-mapped), only tile rows
+    ``ty % row_mod == row_rem`` are rendered — the image-space tile partition with the framebuffer
+    gather fused into the march."""
+    if view_ptrs.dtype != torch.int64 or not view_ptrs.is_cuda or view_ptrs.numel() < len(cams):
+        raise ValueError("view_ptrs must be an int64 CUDA tensor with one address per view")
+    s = P.to_struct()
+    arr = _camera_array(cams)
+    check(lib().mrt_render_forward_batch_scatter(C.byref(s), arr.ctypes.data, len(cams), packed.data_ptr(), Cn,
+                                                 _ptr(tf), 0 if tf is None else tf.shape[0], skip_levels.data_ptr(),
+                                                 view_ptrs.data_ptr(), spans.data_ptr(), int(bool(store_outside)),
+                                                 int(row_mod), int(row_rem), _stream()),
+          "render_forward_batch_scatter")
+
+
 def fill_outside_spans(P: RenderParams, spans: torch.Tensor, out: torch.Tensor):
     """``mrt_fill_outside_spans``: background into every tile outside its row's span."""
     s = P.to_struct()

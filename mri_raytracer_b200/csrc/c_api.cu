@@ -378,6 +378,32 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
   }
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_sparse");
 }
+int mrt_render_forward_batch_scatter(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                     const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                     const uint8_t* skip_levels, float* const* view_out_dev, const int32_t* spans,
+                                     int32_t store_outside, int32_t row_mod, int32_t row_rem, void* stream) {
+  MRT_REQUIRE(packed && view_out_dev && spans && skip_levels, "render_forward_batch_scatter: null pointer");
+  MRT_REQUIRE(cams != nullptr && nviews >= 1, "render_forward_batch_scatter: needs >= 1 camera");
+  MRT_REQUIRE(row_mod >= 0 && (row_mod <= 1 || (row_rem >= 0 && row_rem < row_mod)), "render_forward_batch_scatter: bad row partition %d/%d",
+              row_rem, row_mod);
+  KParams K;
+  const int W = params ? (int)params->imageSize[0] : 0, H = params ? (int)params->imageSize[1] : 0;
+  if (int r = derive(params, C, tfN, true, 0, mrt_tile_count(W > 0 ? W : 1, H > 0 ? H : 1), &K)) return r;
+  MRT_REQUIRE(K.skip, "render_forward_batch_scatter: needs skipEmpty=1 with indexed stepping");
+  MRT_REQUIRE(K.gamma == 1.0f, "render_forward_batch_scatter: gamma != 1 takes the generic kernel, which does not cull");
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_batch_scatter: tfMode=1 needs tf");
+  K.showSeg = K.showPred = 0;
+  cudaError_t e = cudaSuccess;
+  float chunk[MRT_MAX_VIEWS * 12];
+  for (int v0 = 0; v0 < nviews && e == cudaSuccess; v0 += MRT_MAX_VIEWS) {
+    const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
+    pack_cams(cams + v0, nv, chunk);
+    e = mrt_launch_forward_sparse(K, chunk, nv, mrt_packed_channels(C), packed, tf, skip_levels, nullptr,
+                                  spans + (size_t)v0 * 2 * mrt_tiles_y_(K.H), store_outside ? 1 : 0, (cudaStream_t)stream,
+                                  view_out_dev + v0, row_mod, row_rem);
+  }
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_scatter");
+}
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews, float* out_rgba, void* stream) {
   MRT_REQUIRE(params && spans && out_rgba && nviews >= 1, "fill_outside_spans: bad arguments");
   const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];

@@ -44,15 +44,23 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
   float4* s_lab = reinterpret_cast<float4*>(s_tf + (P.tfMode ? P.tfN : 0));  // [0..7] seg, [8..15] pred
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
+  int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
+  bool tile_ok = tile < P.tile_end;
+  if (S.row_mod > 1) {          // interleaved tile rows: local tile index -> (local row, column) -> global tile id
+    const int txn = mrt_tiles_x_(P.W), li = tile - P.tile_begin;
+    const int lrow = li / txn, ty = S.row_rem + S.row_mod * lrow;
+    tile_ok = tile_ok && ty < mrt_tiles_y_(P.H);
+    tile = ty * txn + (li - lrow * txn);
+  }
   const int view = blockIdx.y;                                             // batch of views: one camera each
   int px = 0, py = 0;
-  if (tile < P.tile_end) mrt_pixel_of_tile_lane_fast(P, tile, mrt_logical_lane(warp & 1, lane), &px, &py);
+  if (tile_ok) mrt_pixel_of_tile_lane_fast(P, tile, mrt_logical_lane(warp & 1, lane), &px, &py);
   // :89 — pixels outside the image keep their lane alive (the skip loop uses warp votes) with an
   // empty ray, and never store
-  const bool inside = (tile < P.tile_end) && (px < P.W) && (py < P.H);
+  const bool inside = tile_ok && (px < P.W) && (py < P.H);
   const size_t pix = ((size_t)view * P.H + py) * P.W + px;
   float4* dst = out_rgba + pix;
+  if (S.view_base != nullptr) dst = S.view_base[view] + ((size_t)py * P.W + px);
   if (S.n && inside) { const int strip = py / S.rows; dst = S.base[strip] + ((size_t)(py - strip * S.rows) * P.W + px); }
 
   // Cull against the active-brick box BEFORE any expensive work: a ray that cannot enter it is
@@ -67,7 +75,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         // the view's precomputed spans (projected hull of the active box, mrt_view_spans) answer the
         // question for the whole tile: one load and two compares instead of a per-ray slab test
         bool in_span = false;
-        if (tile < P.tile_end) {
+        if (tile_ok) {
           const int2 sp = __ldg(S.spans + (size_t)view * mrt_tiles_y_(P.H) + (py >> MRT_TILE_SHIFT));
           in_span = mrt_tile_in_span(sp, px & ~MRT_TILE_MASK);              // warp-uniform (one tile per warp pair)
         }
@@ -101,7 +109,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     }
   }
   __syncthreads();
-  if (tile >= P.tile_end) return;
+  if (!tile_ok) return;
   if (SKIP && !GENERIC && !CKPT) { if (!__any_sync(0xffffffffu, maybe)) return; }   // culled warp (already stored)
 
   Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
@@ -430,11 +438,23 @@ cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t*
 
 cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                       const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* spans,
-                                      int store_outside, cudaStream_t st) {
+                                      int store_outside, cudaStream_t st, float* const* view_base, int row_mod,
+                                      int row_rem) {
   if (nviews > MRT_MAX_VIEWS) return cudaErrorInvalidValue;     // the caller chunks (span offsets go with it)
   StripTargets S = {};
   S.spans = reinterpret_cast<const int2*>(spans);
   S.store_outside = store_outside;
+  S.view_base = reinterpret_cast<float4* const*>(view_base);
+  if (row_mod > 1) {
+    if (row_rem < 0 || row_rem >= row_mod) return cudaErrorInvalidValue;
+    S.row_mod = row_mod; S.row_rem = row_rem;
+    // the launch enumerates the rank's LOCAL tiles: its rows x all columns
+    KParams Q = P;
+    const int ty = mrt_tiles_y_(P.H), rows = ty > row_rem ? (ty - row_rem + row_mod - 1) / row_mod : 0;
+    Q.tile_begin = 0; Q.tile_end = rows * mrt_tiles_x_(P.W);
+    return mrt_launch_forward_to(Q, S, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
+                                 nullptr, st);
+  }
   return mrt_launch_forward_to(P, S, cams, nviews, packed_ch, vol, tf, levels, nullptr, nullptr, out_rgba, nullptr,
                                nullptr, st);
 }

@@ -16,7 +16,8 @@ cudaError_t mrt_launch_forward_strips(const KParams& P, int packed_ch, const voi
 
 cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                       const float* tf, const uint8_t* levels, float* out_rgba, const int32_t* spans,
-                                      int store_outside, cudaStream_t st);
+                                      int store_outside, cudaStream_t st, float* const* view_base = nullptr,
+                                      int row_mod = 0, int row_rem = 0);
 cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* spans,
                                   cudaStream_t st);
 cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st);

@@ -62,7 +62,14 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // march unless store_outside is set: the owner of the image fills them with the background itself
 // (mrt_fill_outside_spans), from the same spans.  With store_outside the spans only serve as the
 // (much cheaper) replacement of the per-ray box test: one LDG + two compares per warp.
-struct StripTargets { float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; int store_outside; };
+// view_base (optional, image-space scatter): a DEVICE array with one image pointer per view of the
+// launch — each view's [H][W] frame may live on a different GPU (peer-mapped) — replacing the
+// contiguous out_rgba.  row_mod > 1 (image-space tile partition): the launch renders only the tile
+// rows ty with ty % row_mod == row_rem, interleaved over the ranks because the object sits mid-image.
+struct StripTargets {
+  float4* base[MRT_MAX_STRIPS]; int n, rows; const int2* spans; int store_outside;
+  float4* const* view_base; int row_mod, row_rem;
+};
 
 // Outputs of the checkpointing (training) forward, consumed by the segment-parallel backward:
 // ck[(c-1)][view][H][W] = (C, T) of the ray before slot c*S (1 <= c < nseg), k_end[view][H][W] = the

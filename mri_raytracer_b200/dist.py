@@ -2,24 +2,26 @@
 
 The reference is single-GPU; these two modes are what BASELINE.json's north_star adds:
 
-* image space (``render_views``): the volume, TF and occupancy grid are replicated; a batch of
-  views is split over ranks either by whole views (``mode="views"``) or by contiguous
-  screen-space tile rows of every view (``mode="tiles"``, the integer map of tiles.py); the
-  framebuffer is gathered with ONE ``all_gather_into_tensor`` per batch (NCCL over NVLink).
-  Rays are independent, so there is no other exchange.
-* sort-last (``render_sort_last``): the volume is split into axis-aligned sub-boxes (+1 voxel
-  halo so trilinear sampling at the cut faces is exact); each rank marches every ray through
-  its own sub-box only, producing premultiplied colour + transmittance; image strips are
-  exchanged with ``all_to_all_single`` and composited front-to-back in visibility order
-  (``mrt_composite_over``), then the finished strips are all-gathered.
+* image space: the volume, TF and occupancy grid are replicated; a batch of views is split over
+  ranks by interleaved screen-space TILE ROWS of every view (or by whole views), and the framebuffer
+  gather is fused into the march: :class:`PeerFramebuffer` owns symmetric (peer-mapped) frames and
+  every rank's ONE batched launch stores its pixels straight into the owner GPU of each view over
+  NVLink.  Owners are striped over the ranks (or one root).  ``render_views`` is the plain NCCL
+  ``all_gather`` version of the same partitions.  Rays are independent: no other exchange.
+* sort-last (``render_sort_last`` / :class:`PeerSortLast`): the volume is split into axis-aligned
+  sub-boxes (+1 voxel halo so trilinear sampling at the cut faces is exact); each rank marches every
+  ray through its own sub-box only, producing premultiplied colour + transmittance; image strips are
+  exchanged and composited front-to-back in visibility order (``mrt_composite_over``).
 
-Both take an optional ``render_fn`` so the host logic can be exercised on CPU with the gloo
-backend (tests/test_dist_gloo.py injects the oracle there); the default is the CUDA path.
+Everything here drives CUDA tensors; the host-side logic (partitions, orders, collectives) is
+exercised on CPU with the gloo backend by tests that substitute duck-typed stand-ins for the
+renderer objects (tests/test_dist_gloo.py) — there is no oracle hook and no CPU path in this module.
 """
 from __future__ import annotations
 
+import warnings
 from dataclasses import replace
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -35,18 +37,12 @@ def _world(group=None) -> Tuple[int, int]:
     return 0, 1
 
 
-def _render_batch(volume, tf, P: RenderParams, cams: Sequence, tile_range: Tuple[int, int], out: torch.Tensor,
-                  render_fn: Optional[Callable]):
-    """``len(cams)`` views into the contiguous ``out [V,H,W,4]``: ONE batched launch on the CUDA
-    path (api.Volume.forward_batch), a per-view loop when a ``render_fn`` is injected (CPU tests)."""
+def _render_batch(volume, tf, P: RenderParams, cams: Sequence, tile_range: Tuple[int, int], out: torch.Tensor):
+    """``len(cams)`` views into the contiguous ``out [V,H,W,4]``: ONE batched launch
+    (api.Volume.forward_batch)."""
     if not len(cams):
         return
-    if render_fn is None:
-        volume.forward_batch(replace(P, tfMode=1 if tf is not None else 0), list(cams), tf, out=out,
-                             tile_range=tile_range)
-    else:
-        for v, cam in enumerate(cams):
-            render_fn(P.with_camera(cam), tile_range, out[v])
+    volume.forward_batch(replace(P, tfMode=1 if tf is not None else 0), list(cams), tf, out=out, tile_range=tile_range)
 
 
 # ----------------------------------------------------------------------------- image space
@@ -62,9 +58,10 @@ def padded_rows(H: int, nranks: int) -> int:
 
 
 def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views", group=None,
-                 render_fn: Optional[Callable] = None, device=None, gather: bool = True) -> torch.Tensor:
+                 device=None, gather: bool = True) -> torch.Tensor:
     """Render ``len(cams)`` views of one volume across all ranks -> ``[V,H,W,4]`` on every rank
-    (``gather=False``: only this rank's part is valid; used to time compute alone)."""
+    through ONE NCCL ``all_gather_into_tensor`` (``gather=False``: only this rank's part is valid;
+    used to time compute alone).  The peer-memory version is :class:`PeerFramebuffer`."""
     rank, R = _world(group)
     W, H = P.imageSize
     V = len(cams)
@@ -75,7 +72,7 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
             raise ValueError(f"mode='views' needs len(cams) ({V}) divisible by world size ({R})")
         out = torch.empty((V, H, W, 4), dtype=torch.float32, device=device)
         v0, v1 = view_partition(V, rank, R)
-        _render_batch(volume, tf, P, cams[v0:v1], (0, nt), out[v0:v1], render_fn)
+        _render_batch(volume, tf, P, cams[v0:v1], (0, nt), out[v0:v1])
         if R > 1 and gather:
             dist.all_gather_into_tensor(out.view(-1), out[v0:v1].reshape(-1), group=group)
         return out
@@ -89,7 +86,7 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
         y0, y1 = tr0 * tiles.TILE, min(tr1 * tiles.TILE, H)
         if tr1 > tr0:
             full = torch.empty((V, H, W, 4), dtype=torch.float32, device=device)
-            _render_batch(volume, tf, P, cams, (tr0 * tx, tr1 * tx), full, render_fn)
+            _render_batch(volume, tf, P, cams, (tr0 * tx, tr1 * tx), full)
             buf[rank, :, : y1 - y0] = full[:, y0:y1]
         if R > 1 and gather:
             dist.all_gather_into_tensor(buf.view(-1), buf[rank].reshape(-1), group=group)
@@ -101,111 +98,178 @@ def render_views(volume, cams: Sequence, tf, P: RenderParams, mode: str = "views
 
 # ----------------------------------------------------------------------------- fused gather
 class PeerFramebuffer:
-    """Framebuffer gather fused into the render kernel: every rank owns a symmetric (peer-mapped)
-    ``[R*Vloc,H,W,4]`` buffer; rank r's march kernel stores its pixels straight into the ROOT
-    rank's buffer through the NVLink peer mapping (16-byte coalesced stores, fire-and-forget),
-    so the transfer overlaps the march of the following rays and there is no separate collective
-    on the data path - only one barrier per batch.
+    """Framebuffer of ``n_views`` frames distributed over the ranks, written by the render kernels
+    themselves: every rank holds symmetric (peer-mapped) memory for the frames it OWNS, and each
+    rank's ONE batched march stores the pixels it renders straight into the owner GPU of their view
+    through the NVLink peer mapping (16-byte coalesced stores, fire-and-forget), so the transfer
+    overlaps the march of the following rays and no collective sits on the data path — one
+    stream-ordered barrier per batch.
 
-    ``sparse=True`` (default): tiles outside a view's *spans* — per tile row the x-extent of the
-    projected active-brick box, a deterministic function of (camera, params, occupancy) that every
-    rank computes for itself (``mrt_view_spans``) — are not sent; the root fills them with the
-    background on a side stream while everybody marches (``mrt_fill_outside_spans``; disjoint pixels, so no ordering
-    is needed).  More than half of a frame is background, and the root's NVLink ingress (7 ranks x
-    frames) is what bounds the dense gather at 8 GPUs.  The root needs the cameras of ALL views
-    (``cams_all`` of :func:`render_views_to`).
+    owners="striped" (default): view ``v`` lives on rank ``v // ceil(n_views/R)`` — every GPU
+    receives 1/R of the traffic (a single root's NVLink ingress is what bounded the round-1 gather
+    at 8 GPUs).  owners="root": all frames on ``root``.
 
-    Falls back to NCCL ``all_gather`` when symmetric memory is unavailable (``self.p2p`` False)."""
+    partition="tiles" (default): rank r renders tile rows ``ty % R == r`` of EVERY view
+    (north_star's image-space tile partition: a fixed batch scales strongly, and the load is even
+    because every rank gets a slice of every view).  partition="views": rank r renders whole views
+    ``[r*V/R, (r+1)*V/R)``.
 
-    def __init__(self, views_per_rank: int, H: int, W: int, device, group=None, root: int = 0, sparse: bool = True):
+    Tiles outside a view's *spans* — per tile row the x-extent of the projected active-brick box, a
+    deterministic function of (camera, params, occupancy) that every rank computes for itself
+    (``mrt_view_spans``) — are not sent; the owner fills them with the background on a side stream
+    while everybody marches (``mrt_fill_outside_spans``; disjoint pixels, no ordering needed).
+
+    Double-buffered: batch b is written into buffer ``b % 2``.  ``finish()`` returns this rank's
+    owned frames ``[n_owned,H,W,4]``; they stay valid until the ``finish()`` of the NEXT batch is
+    called on this rank's stream (peers cannot start batch b+2, which reuses the buffer, before
+    every rank has passed the barrier of batch b+1).
+
+    Symmetric memory is required: construction raises when it is unavailable unless
+    ``allow_nccl_fallback=True`` (then a warning is issued, every rank renders its part into a full
+    local ``[V,H,W,4]`` buffer and ``finish()`` completes it with ONE NCCL ``all_reduce``-free
+    ``all_gather``; ``self.p2p`` is False and every rank owns — sees — all frames)."""
+
+    def __init__(self, n_views: int, H: int, W: int, device, group=None, owners: str = "striped", root: int = 0,
+                 partition: str = "tiles", allow_nccl_fallback: bool = False):
         self.rank, self.R = _world(group)
         self.group = group if group is not None else (dist.group.WORLD if self.R > 1 else None)
-        self.Vloc, self.H, self.W, self.root = int(views_per_rank), H, W, root
-        self.shape = (self.R * self.Vloc, H, W, 4)
+        if owners not in ("striped", "root") or partition not in ("tiles", "views"):
+            raise ValueError("owners must be 'striped' or 'root', partition 'tiles' or 'views'")
+        self.V, self.H, self.W, self.root, self.owners, self.partition = int(n_views), int(H), int(W), int(root), owners, partition
+        R = self.R
+        if partition == "views" and self.V % R != 0:
+            raise ValueError(f"partition='views' needs n_views ({self.V}) divisible by world size ({R})")
+        self.per_owner = (self.V + R - 1) // R if owners == "striped" else self.V
+        self.device = torch.device(device)
         self.p2p = False
-        self.hdl = None
-        self.sparse = False
+        self.why = None
+        self.batch = 0
         self._fill_done = None
-        if self.R > 1 and torch.device(device).type == "cuda":
+        shape = (2, self.per_owner, H, W, 4)
+        if R > 1 and self.device.type == "cuda":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                self.local = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
+                self.local = symm_mem.empty(shape, dtype=torch.float32, device=self.device)
                 self.hdl = symm_mem.rendezvous(self.local, self.group)
-                self.remote = self.hdl.get_buffer(root, self.shape, torch.float32)
+                peers = [self.hdl.get_buffer(j, shape, torch.float32) for j in range(R)]
+                frame = H * W * 4 * 4
+                ptrs = torch.empty((2, self.V), dtype=torch.int64)
+                for b in range(2):
+                    for v in range(self.V):
+                        o, slot = self.owner_of(v)
+                        ptrs[b, v] = peers[o][b].data_ptr() + slot * frame
+                self.view_ptrs = ptrs.to(self.device)
                 self.p2p = True
-                self.sparse = bool(sparse)
-                if self.sparse:
-                    ty = tiles.tiles_y(H)
-                    self.spans = torch.empty((self.Vloc, ty, 2), dtype=torch.int32, device=device)
-                    self.spans_all = torch.empty((self.R * self.Vloc, ty, 2), dtype=torch.int32, device=device)
-                    self.side = torch.cuda.Stream(device=device)
-            except Exception as e:                      # pragma: no cover - depends on the platform
+            except Exception as e:                      # depends on the platform (driver, topology, torch build)
                 self.why = f"{type(e).__name__}: {e}"
+        elif R > 1:
+            self.why = f"symmetric memory needs CUDA tensors (device={self.device})"
+        if R == 1:
+            self.local = torch.empty(shape, dtype=torch.float32, device=self.device)
+            if self.device.type == "cuda":
+                frame = H * W * 4 * 4
+                self.view_ptrs = torch.tensor([[self.local[b].data_ptr() + v * frame for v in range(self.V)] for b in range(2)],
+                                              dtype=torch.int64, device=self.device)
+                self.p2p = True
         if not self.p2p:
-            self.local = torch.empty(self.shape, dtype=torch.float32, device=device)
-            self.remote = self.local
-
-    def targets(self) -> torch.Tensor:
-        """This rank's contiguous ``[Vloc,H,W,4]`` slice of the (root's, when p2p) framebuffer."""
-        buf = self.remote if self.p2p else self.local
-        return buf[self.rank * self.Vloc:(self.rank + 1) * self.Vloc]
-
-    def finish(self):
-        """Make the batch visible on the root: a barrier (p2p; the root also joins its background
-        fill) or the NCCL gather (fallback)."""
-        if self.R == 1:
-            return
+            if not allow_nccl_fallback:
+                raise RuntimeError(f"PeerFramebuffer: symmetric (peer-mapped) memory is unavailable — {self.why}; "
+                                   "pass allow_nccl_fallback=True to gather with NCCL instead")
+            warnings.warn(f"PeerFramebuffer: falling back to an NCCL all_gather ({self.why})", RuntimeWarning, stacklevel=2)
+            self.full = torch.zeros((self.V, H, W, 4), dtype=torch.float32, device=self.device)
+        ty = tiles.tiles_y(H)
         if self.p2p:
-            self.hdl.barrier()          # stream-ordered: after this rank's march kernels
-            if self._fill_done is not None:
-                torch.cuda.current_stream().wait_event(self._fill_done)
-                self._fill_done = None
-        else:
-            lo = self.rank * self.Vloc
-            dist.all_gather_into_tensor(self.local.view(-1), self.local[lo:lo + self.Vloc].reshape(-1).clone(),
-                                        group=self.group)
+            self.spans = torch.empty((self.V, ty, 2), dtype=torch.int32, device=self.device)
+            self.side = torch.cuda.Stream(device=self.device)
 
-    def frames(self) -> torch.Tensor:
-        """``[R*Vloc,H,W,4]``; complete on the root rank after :meth:`finish`."""
-        return self.local
+    # ---- integer maps (replicated on every rank)
+    def owner_of(self, v: int) -> Tuple[int, int]:
+        """(owner rank, slot in the owner's buffer) of view ``v``."""
+        if self.owners == "root":
+            return self.root, v
+        return v // self.per_owner, v % self.per_owner
 
+    def owned_views(self, rank: Optional[int] = None) -> range:
+        r = self.rank if rank is None else rank
+        if not self.p2p:
+            return range(self.V)
+        if self.owners == "root":
+            return range(self.V) if r == self.root else range(0)
+        return range(min(r * self.per_owner, self.V), min((r + 1) * self.per_owner, self.V))
 
-def render_views_to(fb: PeerFramebuffer, volume, cams_local: Sequence, tf, P: RenderParams,
-                    render_fn: Optional[Callable] = None, cams_all: Optional[Sequence] = None):
-    """Render this rank's views into the (peer) framebuffer; call ``fb.finish()`` afterwards.
-    ``cams_all`` (the cameras of every rank's views, in framebuffer order) enables the sparse
-    gather; without it every pixel is sent."""
-    W, H = P.imageSize
-    nt = tiles.tile_count(W, H)
-    if len(cams_local) != fb.Vloc:
-        raise ValueError(f"framebuffer holds {fb.Vloc} views per rank, got {len(cams_local)} cameras")
-    if fb.sparse and render_fn is None and cams_all is not None:
+    # ---- one batch
+    def render(self, volume, cams: Sequence, tf, P: RenderParams):
+        """Queue this rank's share of the batch (``cams`` = the cameras of ALL ``n_views`` views, in
+        frame order, identical on every rank).  Call :meth:`finish` afterwards."""
         from . import api
-        if len(cams_all) != fb.R * fb.Vloc:
-            raise ValueError(f"cams_all must hold {fb.R * fb.Vloc} cameras")
+        if len(cams) != self.V:
+            raise ValueError(f"the framebuffer holds {self.V} views, got {len(cams)} cameras")
+        cams = list(cams)
+        W, H = P.imageSize
+        if (W, H) != (self.W, self.H):
+            raise ValueError("imageSize does not match the framebuffer")
         Pm = replace(P, tfMode=1 if tf is not None else 0)
-        # every rank takes the same branch: it only depends on params and volume kind, which are replicated
-        plan = volume.sparse_plan(Pm, list(cams_local), tf)
-        if plan is not None:
-            packed, Cn, Pe, bits = plan
-            api.view_spans(Pe, list(cams_local), Cn, bits, out=fb.spans)
-            api.render_forward_batch_sparse(Pe, list(cams_local), packed, Cn, tf, bits, fb.targets().data_ptr(), fb.spans)
-            if fb.rank == fb.root:
-                # background of ALL views outside their rectangles, on a side stream, while everybody
-                # marches (queued after the root's own march so that its launch is not delayed)
-                ev = torch.cuda.Event(); ev.record()
-                with torch.cuda.stream(fb.side):
-                    fb.side.wait_event(ev)
-                    api.view_spans(Pe, list(cams_all), Cn, bits, out=fb.spans_all)
-                    api.fill_outside_spans(Pe, fb.spans_all, fb.local)
-                    fb._fill_done = torch.cuda.Event(); fb._fill_done.record()
+        R, r = self.R, self.rank
+        if not self.p2p:
+            self.full.zero_()
+            if self.partition == "views":
+                v0, v1 = view_partition(self.V, r, R)
+                _render_batch(volume, tf, Pm, cams[v0:v1], (0, tiles.tile_count(W, H)), self.full[v0:v1])
+            else:
+                tr0, tr1 = tiles.rank_tile_range(tiles.tiles_y(H), r, R)          # contiguous tile rows
+                tx = tiles.tiles_x(W)
+                _render_batch(volume, tf, Pm, cams, (tr0 * tx, tr1 * tx), self.full)
             return
-    _render_batch(volume, tf, P, cams_local, (0, nt), fb.targets(), render_fn)
+        plan = volume.sparse_plan(Pm, cams, tf)
+        if plan is None:
+            raise RuntimeError("PeerFramebuffer.render needs the span path: an occupancy grid, skipEmpty=1, indexed stepping, "
+                               "gamma 1 and no label overlays")
+        packed, Cn, Pe, bits = plan
+        buf = self.batch & 1
+        api.view_spans(Pe, cams, Cn, bits, out=self.spans)            # all views: senders and owners need them
+        if self.partition == "tiles":
+            api.render_forward_batch_scatter(Pe, cams, packed, Cn, tf, bits, self.view_ptrs[buf], self.spans,
+                                             store_outside=False, row_mod=R, row_rem=r)
+        else:
+            v0, v1 = view_partition(self.V, r, R)
+            if v1 > v0:
+                api.render_forward_batch_scatter(Pe, cams[v0:v1], packed, Cn, tf, bits, self.view_ptrs[buf, v0:v1].contiguous(),
+                                                 self.spans[v0:v1], store_outside=False)
+        own = self.owned_views()
+        if len(own):
+            # background of the owned views outside their spans, on a side stream, while everybody
+            # marches (queued after this rank's own march so that its launch is not delayed)
+            ev = torch.cuda.Event(); ev.record()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                api.fill_outside_spans(Pe, self.spans[own.start:own.stop], self.local[buf, :len(own)])
+                self._fill_done = torch.cuda.Event(); self._fill_done.record()
+
+    def finish(self) -> torch.Tensor:
+        """Complete the batch: one barrier (the owner also joins its background fill), or the NCCL
+        gather of the fallback.  -> this rank's owned frames ``[n_owned,H,W,4]`` (see class doc for
+        how long they stay valid)."""
+        if not self.p2p:
+            if self.R > 1:
+                if self.partition == "views":
+                    v0, v1 = view_partition(self.V, self.rank, self.R)
+                    dist.all_gather_into_tensor(self.full.view(-1), self.full[v0:v1].reshape(-1).clone(), group=self.group)
+                else:
+                    dist.all_reduce(self.full, op=dist.ReduceOp.SUM, group=self.group)   # disjoint rows, zeros elsewhere
+            return self.full
+        buf = self.batch & 1
+        if self.R > 1:
+            self.hdl.barrier()          # stream-ordered: after this rank's march kernel; all peers' stores have landed
+        if self._fill_done is not None:
+            torch.cuda.current_stream().wait_event(self._fill_done)
+            self._fill_done = None
+        self.batch += 1
+        return self.local[buf, :len(self.owned_views())]
 
 
 # ----------------------------------------------------------------------------- differentiable, image space
 def render_differentiable(volume: torch.Tensor, cam, tf: Optional[torch.Tensor], P: RenderParams, group=None,
-                          render_fn: Optional[Callable] = None, **kw) -> torch.Tensor:
+                          **kw) -> torch.Tensor:
     """Differentiable rendering, data-parallel over screen tiles: the
     volume and TF are replicated, rank r renders — and differentiates — tile range
     ``tiles.rank_tile_range(ntiles, r, R)``, and the frame is assembled with ONE differentiable
@@ -213,17 +277,13 @@ def render_differentiable(volume: torch.Tensor, cam, tf: Optional[torch.Tensor],
     whole ``[H,W,4]`` image and may compute any loss on it; after ``loss.backward()`` each rank holds
     the gradient contribution of ITS tiles — finish with :func:`allreduce_gradients` (the volume-
     sized ``all_reduce`` of dL/dvolume and the tiny one of dL/dtf), exactly like data-parallel
-    training.  ``render_fn(volume, tf, P, tile_range) -> [H,W,4]`` replaces the CUDA renderer
-    (CPU/gloo tests inject the oracle)."""
+    training."""
+    from . import api
     rank, R = _world(group)
     Pc = P.with_camera(cam) if cam is not None else P
     W, H = Pc.imageSize
     tr = tiles.rank_tile_range(tiles.tile_count(W, H), rank, R)
-    if render_fn is not None:
-        part = render_fn(volume, tf, Pc, tr)
-    else:
-        from . import api
-        part = api.render(volume, None, tf, Pc, tile_range=tr, **kw)
+    part = api.render(volume, None, tf, Pc, tile_range=tr, **kw)
     if R == 1:
         return part
     import torch.distributed.nn.functional as dfn
@@ -317,10 +377,9 @@ def slice_shard(planar: torch.Tensor, lo, hi) -> torch.Tensor:
 
 
 def composite_over(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:
-    """Ordered front-to-back `over` of ``[K,npix,4]`` partials -> ``[npix,4]``: the CUDA kernel
-    (``mrt_composite_over``) on CUDA tensors, the torch restatement on CPU tensors (gloo tests)."""
+    """Ordered front-to-back `over` of ``[K,npix,4]`` CUDA partials -> ``[npix,4]`` (``mrt_composite_over``)."""
     if not partials.is_cuda:
-        return composite_over_torch(partials, order, bg, alpha_mode)
+        raise RuntimeError("composite_over needs CUDA tensors: the render path has no CPU fallback")
     import ctypes as C
     from ._lib import check, lib
     K, npix = partials.shape[0], partials.shape[1]
@@ -333,24 +392,20 @@ def composite_over(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode:
     return out
 
 
-def render_sort_last(shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, int, int], group=None,
-                     partial_fn: Optional[Callable] = None, device=None) -> torch.Tensor:
-    """One frame of a brick-sharded volume (BASELINE config 5): this rank marches every ray through
-    its own sub-box only (``shard_volume`` = Volume(..., shard=shard_box(dims, grid, rank))) ->
-    partial (premultiplied rgb, T); image strips are exchanged with ONE ``all_to_all_single``;
-    each rank composites its strip front-to-back in visibility order and the finished strips are
-    all-gathered.  Early termination acts per shard (use a small ``ertThreshold``: the result
-    equals the unsharded render to within it).  ``partial_fn(P) -> [H,W,4]`` overrides the CUDA
-    march (CPU/gloo tests)."""
+def render_sort_last(shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, int, int], group=None) -> torch.Tensor:
+    """One frame of a brick-sharded volume (BASELINE config 5) through NCCL: this rank marches every
+    ray through its own sub-box only (``shard_volume`` = Volume(..., shard=shard_box(dims, grid,
+    rank))) -> partial (premultiplied rgb, T); image strips are exchanged with ONE
+    ``all_to_all_single``; each rank composites its strip front-to-back in visibility order and the
+    finished strips are all-gathered.  Early termination acts per shard (use a small
+    ``ertThreshold``: the result equals the unsharded render to within it).  The peer-memory version
+    is :class:`PeerSortLast`."""
     rank, R = _world(group)
     if grid[0] * grid[1] * grid[2] != R:
         raise ValueError(f"grid {grid} does not match world size {R}")
     W, H = P.imageSize
     Pc = P.with_camera(cam) if cam is not None else P
-    if partial_fn is not None:
-        partial = partial_fn(Pc)
-    else:
-        partial = shard_volume.forward(replace(Pc, tfMode=1 if tf is not None else 0), tf)
+    partial = shard_volume.forward(replace(Pc, tfMode=1 if tf is not None else 0), tf)
     device = partial.device
     order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
     if R == 1:
@@ -377,12 +432,12 @@ class PeerSortLast:
        into EVERY rank's final image (``mrt_composite_over_multi``) — the all-gather;
     4. one barrier (also protects the receive buffers from the next frame's stores).
 
-    No NCCL collective and no staging copy is on the data path.  Falls back to
-    :func:`render_sort_last` (NCCL all_to_all + all_gather) when symmetric memory is unavailable
-    (``self.p2p`` False).  ``emulate=R`` builds the single-process equivalent (all "ranks" on this
+    No NCCL collective and no staging copy is on the data path.  Symmetric memory is required:
+    construction raises when it is unavailable unless ``allow_nccl_fallback=True`` (then, with a
+    warning, ``render`` goes through :func:`render_sort_last`; ``self.p2p`` is False).  ``emulate=R`` builds the single-process equivalent (all "ranks" on this
     GPU, plain device buffers) used by the tests."""
 
-    def __init__(self, H: int, W: int, device, group=None, emulate: int = 0):
+    def __init__(self, H: int, W: int, device, group=None, emulate: int = 0, allow_nccl_fallback: bool = False):
         self.rank, self.R = (0, int(emulate)) if emulate else _world(group)
         self.emulate = bool(emulate)
         self.group = group if group is not None else (dist.group.WORLD if (self.R > 1 and not emulate) else None)
@@ -406,11 +461,14 @@ class PeerSortLast:
                 self.recv_peer = [self.hdl_recv.get_buffer(j, rshape, torch.float32) for j in range(R)]
                 self.final_peer = [self.hdl_final.get_buffer(j, fshape, torch.float32) for j in range(R)]
                 self.p2p = True
-            except Exception as e:                      # pragma: no cover - depends on the platform
+            except Exception as e:                      # depends on the platform (driver, topology, torch build)
                 self.why = f"{type(e).__name__}: {e}"
-        if not self.p2p and not self.emulate:
-            self.recv = torch.zeros(rshape, dtype=torch.float32, device=device)
-            self.final = torch.zeros(fshape, dtype=torch.float32, device=device)
+        if not self.p2p and not self.emulate and R > 1:
+            if not allow_nccl_fallback:
+                raise RuntimeError(f"PeerSortLast: symmetric (peer-mapped) memory is unavailable — {getattr(self, 'why', 'no CUDA device')}; "
+                                   "pass allow_nccl_fallback=True to exchange with NCCL (render_sort_last) instead")
+            warnings.warn(f"PeerSortLast: falling back to NCCL all_to_all + all_gather ({getattr(self, 'why', 'no CUDA device')})",
+                          RuntimeWarning, stacklevel=2)
 
     # the two halves, rank-parametrised so that the emulation can run them for every "rank"
     def _march(self, rank, shard_volume, tf, Pc):
@@ -476,15 +534,3 @@ def render_sort_last_emulated(planar: torch.Tensor, cam, tf, P: RenderParams, gr
         parts.append(V.forward(replace(Pc, tfMode=1 if tf is not None else 0), tf).reshape(H * W, 4))
     order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
     return composite_over(torch.stack(parts), order, Pc.bgColor, Pc.alphaMode).reshape(H, W, 4)
-
-
-def composite_over_torch(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:
-    """Reference composite in torch (CPU tests): partials [K,npix,4] = (premult rgb, T)."""
-    C = torch.zeros_like(partials[0, :, :3])
-    T = torch.ones_like(partials[0, :, 3])
-    for k in order:
-        C = C + T[:, None] * partials[k, :, :3]
-        T = T * partials[k, :, 3]
-    bgv = torch.as_tensor(bg, dtype=C.dtype, device=C.device)
-    a = (1.0 - T) if alpha_mode else torch.ones_like(T)
-    return torch.cat([bgv[None, :] + C, a[:, None]], dim=1)

@@ -73,3 +73,11 @@ def rank_of_tile(tile: int, ntiles: int, nranks: int) -> int:
 
 def all_rank_ranges(ntiles: int, nranks: int) -> List[Tuple[int, int]]:
     return [rank_tile_range(ntiles, r, nranks) for r in range(nranks)]
+
+
+def interleaved_rows(n_tile_rows: int, rank: int, nranks: int):
+    """Tile rows of ``rank`` in the interleaved image-space partition (``ty % nranks == rank``): the
+    map `mrt_render_forward_batch_scatter(row_mod=nranks, row_rem=rank)` renders.  Interleaved
+    because the object sits in the middle of the image: contiguous bands would leave the outer ranks
+    with background only."""
+    return range(rank, n_tile_rows, nranks)

@@ -1,6 +1,6 @@
-"""Multi-GPU host logic on CPU: world_size-2 gloo process group (127.0.0.1), the oracle standing
-in for the CUDA renderer through dist.render_views' `render_fn` hook.  Checks that the
-image-space partitions ('views' and 'tiles') + the single all_gather reproduce the
+"""Multi-GPU host logic on CPU: world_size-2 gloo process group (127.0.0.1), with duck-typed
+stand-ins for the CUDA renderer objects (tests/dist_fakes.py: renders come from the oracle).  Checks
+that the image-space partitions ('views' and 'tiles') + the single all_gather reproduce the
 single-process image exactly, for image sizes that do not divide evenly."""
 import os
 import socket
@@ -27,26 +27,6 @@ def _free_port():
     return p
 
 
-def _oracle_fn(vol, tf):
-    from oracle import oracle_torch as O
-    from mri_raytracer_b200 import tiles
-
-    def fn(P, tile_range, out):
-        W, H = P.imageSize
-        xs, ys = [], []
-        for t in range(*tile_range):
-            for lane in range(64):
-                x, y = tiles.pixel_of_tile_lane(t, lane, W)
-                if x < W and y < H:
-                    xs.append(x); ys.append(y)
-        if not xs:
-            return
-        px, py = torch.tensor(xs), torch.tensor(ys)
-        rgba = O.render(vol, replace(P, tfMode=1), tf=tf, pixels=(px, py))
-        out[py, px] = rgba
-    return fn
-
-
 def _worker(rank, world, port, mode, W, H, V, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -59,7 +39,8 @@ def _worker(rank, world, port, mode, W, H, V, ret):
         cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.3, initial_theta=0.4)
         cam.set_fov_degrees(70.0)
         cams = orbit_views(cam, V)
-        img = mdist.render_views(None, cams, tf, P, mode=mode, render_fn=_oracle_fn(vol, tf), device="cpu")
+        from dist_fakes import OracleVolume
+        img = mdist.render_views(OracleVolume(vol), cams, tf, replace(P, tfMode=1), mode=mode, device="cpu")
         if rank == 0:
             ret.put(img.numpy())
     finally:
@@ -101,7 +82,9 @@ def _sl_worker(rank, world, port, W, H, ret):
                          eye=(3.0, 2.0, 1.0), bgColor=(0.1, 0.2, 0.3), alphaMode=1)
         g = torch.Generator().manual_seed(100 + rank)
         partial = torch.rand(H, W, 4, generator=g)
-        img = mdist.render_sort_last(None, None, None, P, (2, 1, 1), partial_fn=lambda Pc: partial)
+        import dist_fakes
+        mdist.composite_over = dist_fakes.composite_over_torch            # the product composite is CUDA-only
+        img = mdist.render_sort_last(dist_fakes.OracleVolume(None, partial=partial), None, None, P, (2, 1, 1))
         if rank == 0:
             ret.put(img.numpy())
     finally:
@@ -128,7 +111,8 @@ def test_sort_last_exchange_world2(W, H):
                          for r in range(2)])
     order = mdist.visibility_order(np.array(P.eye, dtype=np.float64), P, (2, 1, 1))
     assert order == [1, 0]                                     # eye on the +x side: the +x half is in front
-    want = mdist.composite_over_torch(parts, order, P.bgColor, 1).reshape(H, W, 4).numpy()
+    from dist_fakes import composite_over_torch
+    want = composite_over_torch(parts, order, P.bgColor, 1).reshape(H, W, 4).numpy()
     assert np.array_equal(got, want)
 
 
@@ -151,7 +135,8 @@ def test_sort_last_helpers():
     # ordered 'over' compositing is associative: compositing halves equals compositing all
     g = torch.Generator().manual_seed(0)
     parts = torch.rand(4, 50, 4, generator=g)
-    full = mdist.composite_over_torch(parts, [2, 0, 3, 1], (0.1, 0.2, 0.3))
+    from dist_fakes import composite_over_torch
+    full = composite_over_torch(parts, [2, 0, 3, 1], (0.1, 0.2, 0.3))
     C = torch.zeros(50, 3); T = torch.ones(50)
     for k in [2, 0, 3, 1]:
         C = C + T[:, None] * parts[k, :, :3]; T = T * parts[k, :, 3]
@@ -167,7 +152,8 @@ def test_composite_kernel_matches_torch(cuda):
     K, n = 8, 4099
     parts = torch.rand(K, n, 4, generator=g)
     order = torch.tensor([3, 1, 7, 0, 2, 6, 5, 4], dtype=torch.int32)
-    want = mdist.composite_over_torch(parts, order.tolist(), (0.05, 0.1, 0.2), alpha_mode=1)
+    from dist_fakes import composite_over_torch
+    want = composite_over_torch(parts, order.tolist(), (0.05, 0.1, 0.2), alpha_mode=1)
     p, o = parts.cuda().contiguous(), order.cuda()
     bg = torch.tensor([0.05, 0.1, 0.2]).numpy()
     out = torch.empty(n, 4, device="cuda")
@@ -177,24 +163,6 @@ def test_composite_kernel_matches_torch(cuda):
 
 
 # ----------------------------------------------------------------------------- differentiable, data-parallel tiles
-def _oracle_part(volume, tf, P, tile_range):
-    """render_fn for dist.render_differentiable: the differentiable oracle on the pixels of a tile range."""
-    from oracle import oracle_torch as O
-    from mri_raytracer_b200 import tiles
-    W, H = P.imageSize
-    xs, ys = [], []
-    for t in range(*tile_range):
-        for lane in range(64):
-            x, y = tiles.pixel_of_tile_lane(t, lane, W)
-            if x < W and y < H:
-                xs.append(x); ys.append(y)
-    out = torch.zeros((H, W, 4), dtype=torch.float32)
-    if xs:
-        px, py = torch.tensor(xs), torch.tensor(ys)
-        out = out.index_put((py, px), O.render(volume, replace(P, tfMode=1), tf=tf, pixels=(px, py)))
-    return out
-
-
 def _grad_worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -205,7 +173,10 @@ def _grad_worker(rank, world, port, ret):
         vol, _, P = small_scene(C=2, dims=(14, 12, 10), W=19, H=13, seed=5)
         tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
         v = vol.clone().requires_grad_(True); t = tf.clone().requires_grad_(True)
-        img = mdist.render_differentiable(v, None, t, P, render_fn=_oracle_part)
+        import dist_fakes
+        from mri_raytracer_b200 import api
+        api.render = dist_fakes.oracle_render_part                         # stands in for the CUDA renderer
+        img = mdist.render_differentiable(v, None, t, P)
         target = torch.linspace(0, 1, img.numel()).reshape(img.shape)
         ((img - target) ** 2).mean().backward()
         mdist.allreduce_gradients([v, t])
@@ -241,31 +212,41 @@ def test_differentiable_tiles_world2_gradients_match_single_process():
 
 
 # ----------------------------------------------------------------------------- PeerFramebuffer fallback (no symmetric memory)
-def _fb_worker(rank, world, port, ret):
+def _fb_worker(rank, world, port, partition, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        import warnings
         from mri_raytracer_b200 import dist as mdist, orbit_views, OrbitalCamera
         from mri_raytracer_b200.synth import ramp_tf
         from scenes import small_scene
-        W, H, Vloc = 19, 13, 2
+        from dist_fakes import OracleVolume
+        W, H, V = 19, 13, 4
         vol, _, P = small_scene(C=1, dims=(16, 14, 12), W=W, H=H, seed=11)
         tf = ramp_tf(16, sigma_scale=20.0, cutoff=0.1)
         cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.2, initial_theta=0.1)
         cam.set_fov_degrees(70.0)
-        cams = orbit_views(cam, Vloc * world)
-        fb = mdist.PeerFramebuffer(Vloc, H, W, "cpu")
-        assert not fb.p2p and not fb.sparse                  # CPU / gloo: the NCCL-style gather path
-        mdist.render_views_to(fb, None, cams[rank * Vloc:(rank + 1) * Vloc], tf, P, render_fn=_oracle_fn(vol, tf),
-                              cams_all=cams)
-        fb.finish()
+        cams = orbit_views(cam, V)
+        try:
+            mdist.PeerFramebuffer(V, H, W, "cpu", partition=partition)
+            loud = False
+        except RuntimeError as e:                            # no symmetric memory on CPU: must be loud by default
+            loud = "symmetric" in str(e)
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            fb = mdist.PeerFramebuffer(V, H, W, "cpu", partition=partition, allow_nccl_fallback=True)
+        assert loud and not fb.p2p and any("falling back" in str(w.message) for w in rec)
+        assert list(fb.owned_views()) == list(range(V))
+        fb.render(OracleVolume(vol), cams, tf, P)
+        frames = fb.finish()
         if rank == 0:
-            ret.put(fb.frames().numpy().copy())
+            ret.put(frames.numpy().copy())
     finally:
         dist.destroy_process_group()
 
 
-def test_peer_framebuffer_falls_back_to_all_gather_world2():
+@pytest.mark.parametrize("partition", ["views", "tiles"])
+def test_peer_framebuffer_nccl_fallback_is_loud_and_exact_world2(partition):
     from oracle import oracle_torch as O
     from mri_raytracer_b200 import orbit_views, OrbitalCamera
     from mri_raytracer_b200.synth import ramp_tf
@@ -273,7 +254,7 @@ def test_peer_framebuffer_falls_back_to_all_gather_world2():
     ctx = mp.get_context("spawn")
     ret = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_fb_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_fb_worker, args=(r, 2, port, partition, ret)) for r in range(2)]
     for p in procs:
         p.start()
     got = ret.get()
@@ -290,3 +271,23 @@ def test_peer_framebuffer_falls_back_to_all_gather_world2():
     for v, c in enumerate(cams):
         ref = O.render(vol, replace(P.with_camera(c), tfMode=1), tf=tf).numpy()
         assert np.array_equal(got[v], ref), f"view {v}"
+
+
+def test_framebuffer_ownership_maps():
+    """Integer maps of the distributed framebuffer: striped owners partition the views, every view has
+    exactly one (owner, slot); interleaved tile rows partition the tile rows."""
+    from mri_raytracer_b200 import tiles
+    for V in (1, 3, 8, 13, 64):
+        for R in (1, 2, 4, 8):
+            per = (V + R - 1) // R
+            seen = set()
+            for v in range(V):
+                o, slot = v // per, v % per
+                assert 0 <= o < R and 0 <= slot < per
+                seen.add((o, slot))
+            assert len(seen) == V
+    for H in (1, 8, 13, 64, 1024, 2050):
+        ty = tiles.tiles_y(H)
+        for R in (1, 2, 3, 4, 8):
+            rows = sorted(t for r in range(R) for t in tiles.interleaved_rows(ty, r, R))
+            assert rows == list(range(ty))

@@ -308,6 +308,61 @@ def test_host_pipeline_resident_volume_sparse_download_and_damage_tracking(cuda)
     pipe.close()
 
 
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_interleaved_tile_rows_scattered_to_per_view_frames_equal_the_batch(cuda, R):
+    """mrt_render_forward_batch_scatter: the image-space tile partition with the gather fused into the
+    march.  R 'ranks' (emulated one after the other on this GPU) each render tile rows ty % R == r of
+    every view and store them through a per-view pointer table into frames that live in two separate
+    allocations (standing for two owner GPUs); the owners fill the background outside the spans.
+    The union equals render_views bit for bit."""
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views, tiles
+    dims, W, H, V = (48, 40, 36), 83, 61, 5
+    vol, _, P = small_scene(C=4, dims=dims, W=W, H=H, seed=5)
+    P = replace(P, tfMode=1, bgColor=(0.2, 0.1, 0.3))
+    tf = ramp_tf(64).cuda()
+    Vd = api.Volume(vol.cuda())
+    cam = Vd.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.3, initial_phi=1.2))
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, V)
+    ref = api.render_views(Vd, cams, tf, P)
+    packed, Cn, Pe, bits = Vd.sparse_plan(P, cams, tf)
+    owner_a = torch.full((3, H, W, 4), -1.0, device="cuda")          # views 0..2
+    owner_b = torch.full((2, H, W, 4), -1.0, device="cuda")          # views 3..4
+    frame = H * W * 16
+    ptrs = torch.tensor([owner_a.data_ptr() + i * frame for i in range(3)] + [owner_b.data_ptr() + i * frame for i in range(2)],
+                        dtype=torch.int64, device="cuda")
+    spans = api.view_spans(Pe, cams, Cn, bits)
+    for r in range(R):
+        api.render_forward_batch_scatter(Pe, cams, packed, Cn, tf, bits, ptrs, spans, store_outside=False, row_mod=R, row_rem=r)
+    api.fill_outside_spans(Pe, spans[:3].contiguous(), owner_a)
+    api.fill_outside_spans(Pe, spans[3:].contiguous(), owner_b)
+    assert torch.equal(torch.cat([owner_a, owner_b]), ref)
+    assert sorted(t for r in range(R) for t in tiles.interleaved_rows(tiles.tiles_y(H), r, R)) == list(range(tiles.tiles_y(H)))
+
+
+def test_peer_framebuffer_single_rank_double_buffer(cuda):
+    """dist.PeerFramebuffer degenerates to a local double-buffered framebuffer on one rank: the same
+    scatter + owner-fill code path as on N GPUs; frames of batch b stay intact while batch b+1 is
+    rendered into the other buffer."""
+    from mri_raytracer_b200 import dist as mdist, OrbitalCamera, orbit_views
+    dims, W, H, V = (40, 36, 28), 64, 48, 3
+    vol, _, P = small_scene(C=1, dims=dims, W=W, H=H, seed=9)
+    tf = ramp_tf(64).cuda()
+    Vd = api.Volume(vol.cuda())
+    fb = mdist.PeerFramebuffer(V, H, W, "cuda")
+    refs, got = [], []
+    for b in range(3):
+        cam = Vd.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.5 * b, initial_phi=1.2))
+        cam.set_fov_degrees(70.0)
+        cams = orbit_views(cam, V)
+        fb.render(Vd, cams, tf, P)
+        got.append(fb.finish())
+        refs.append(api.render_views(Vd, cams, tf, P))
+        if b >= 1:
+            assert torch.equal(got[b - 1], refs[b - 1])               # previous batch untouched by this one
+    assert torch.equal(got[2], refs[2])
+
+
 def test_bad_arguments_raise(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     V = api.Volume(vol.cuda())

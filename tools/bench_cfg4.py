@@ -4,11 +4,12 @@ partition across 1/2/4/8 B200 with the framebuffer gathered on rank 0.
     python tools/bench_cfg4.py                                   # one GPU
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_cfg4.py
 
-STRONG scaling: the 64 views are fixed; rank r renders views [r*64/R, (r+1)*64/R) in ONE batched
-launch and stores them straight into rank 0's peer-mapped framebuffer (dist.PeerFramebuffer, sparse
-gather: tiles outside the projected active-brick box are not sent, the root fills them).  Prints one
-JSON line: ms per 64-view batch (CUDA events, max over ranks), views/s, nominal samples/s, and a
-check of a few gathered views against local renders on rank 0.
+STRONG scaling: the 64 views are fixed; rank r renders tile rows ty % R == r of EVERY view (or whole
+views with --partition views) in ONE batched launch and stores them straight into the peer-mapped
+frame of each view's owner GPU (dist.PeerFramebuffer; owners striped over the ranks, or all on rank 0
+with --owners root; tiles outside the projected active-brick box are not sent, the owner fills them).
+Prints one JSON line: ms per 64-view batch (CUDA events, max over ranks), views/s, nominal samples/s,
+and a bit-exact check of owned views against local renders on every rank.
 """
 import argparse
 import json
@@ -36,7 +37,8 @@ def main():
     ap.add_argument("--img", type=int, default=2048)
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--dense-gather", action="store_true")
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "views"])
+    ap.add_argument("--owners", default="striped", choices=["striped", "root"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -66,15 +68,16 @@ def main():
         dist.all_reduce(tot)
     taken = int(tot)
 
-    fb = mdist.PeerFramebuffer(Vloc, args.img, args.img, dev, sparse=not args.dense_gather) if world > 1 else None
+    fb = mdist.PeerFramebuffer(args.views, args.img, args.img, dev, owners=args.owners, partition=args.partition) if world > 1 else None
     frames = torch.empty((Vloc, args.img, args.img, 4), device=dev) if world == 1 else None
+    got_holder = [None]
 
     def batch():
         if world == 1:
             api.render_views(V, mine, tf, P, out=frames)
         else:
-            mdist.render_views_to(fb, V, mine, tf, P, cams_all=cams_all)
-            fb.finish()
+            fb.render(V, cams_all, tf, P)
+            got_holder[0] = fb.finish()
 
     def barrier():
         if world > 1:
@@ -95,19 +98,25 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_batch = float(t)
-    ok = None
-    if rank == 0:
-        got = frames if world == 1 else fb.frames()
-        ok = True
+    # every owner checks its first and last owned view against a local render (bit-exact)
+    okl = True
+    if world == 1:
         for v in (0, args.views // 2 + 1, args.views - 1):
-            ok &= bool(torch.equal(got[v], api.render(V, cams_all[v], tf, P)))
+            okl &= bool(torch.equal(frames[v], api.render(V, cams_all[v], tf, P)))
+    else:
+        own = fb.owned_views()
+        for v in sorted({own.start, own.stop - 1}) if len(own) else []:
+            okl &= bool(torch.equal(got_holder[0][v - own.start], api.render(V, cams_all[v], tf, P)))
+    okt = torch.tensor([1 if okl else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
         print(json.dumps(dict(cfg="cfg4", dims=dims, image=args.img, views=args.views, n_gpus=world, scaling="strong",
                               gather=("none (single GPU)" if world == 1 else
-                                      ("peer stores, sparse" if (fb.p2p and fb.sparse) else
-                                       ("peer stores, dense" if fb.p2p else "NCCL all_gather"))),
+                                      f"peer (NVLink) stores from inside the march, partition={fb.partition}, owners={fb.owners}"),
                               ms_per_batch=ms_batch, views_per_s=args.views * 1e3 / ms_batch,
                               ms_per_view=ms_batch / args.views, nominal_samples_per_batch=taken,
-                              gsamples_per_s=taken / ms_batch / 1e6, gathered_views_equal_local_renders=ok,
+                              gsamples_per_s=taken / ms_batch / 1e6, gathered_views_equal_local_renders=bool(okt.item()),
                               reps=args.reps)), flush=True)
     if world > 1:
         dist.destroy_process_group()

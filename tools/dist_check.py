@@ -1,5 +1,7 @@
-"""Multi-GPU correctness check (torchrun, 2+ GPUs): image-space peer framebuffer, sort-last through
-NCCL and through peer memory, all against single-GPU renders.  Prints one line per check."""
+"""Multi-GPU correctness check (torchrun, 2+ GPUs): the distributed framebuffer (tile and view
+partitions, striped and root owners, several batches back to back without host syncs), the NCCL
+gather paths, sort-last through NCCL and through peer memory, and data-parallel differentiable
+rendering — all against single-GPU renders.  Prints one line per check and ALL OK / SOME FAILED."""
 import os, sys
 from dataclasses import replace
 from pathlib import Path
@@ -23,23 +25,32 @@ def report(name, ok, extra=""):
     if rank == 0:
         print(f"{name}: {'OK' if t.item() else 'FAIL'} {extra}", flush=True)
 
-# 1. image space, views per rank, fused peer gather
-V = 2
-P, cams_all = bench._scene(V * world)
+# 1. image space: distributed framebuffer, every partition x owner layout, 3 batches back to back
+V = 2 * world
+P, _ = bench._scene(V)
 P = replace(P, imageSize=(256, 256))
 vol = make_brats_like(4, bench.DIMS, seed=0, device=dev); tf = ramp_tf(256).to(dev)
 volume = api.Volume(vol)
-fb = mdist.PeerFramebuffer(V, 256, 256, dev)
-mdist.render_views_to(fb, volume, cams_all[rank * V:(rank + 1) * V], tf, P, cams_all=cams_all); fb.finish()
-torch.cuda.synchronize(); dist.barrier()
-ok = True
-if rank == 0:
-    ref = api.render_views(volume, cams_all, tf, P)
-    ok = bool(torch.equal(ref, fb.frames()))
-report("image-space peer framebuffer == local renders", ok, f"(p2p={fb.p2p})")
+for partition in ("tiles", "views"):
+    for owners in ("striped", "root"):
+        fb = mdist.PeerFramebuffer(V, 256, 256, dev, owners=owners, partition=partition)
+        kept, refs = [], []
+        for b in range(3):                         # no host sync between batches: the double buffer must hold
+            _, cams = bench._scene(V, theta0_deg=25.0 + 40.0 * b)
+            fb.render(volume, cams, tf, P)
+            kept.append(fb.finish())
+            refs.append(cams)
+        ok = True
+        own = fb.owned_views()
+        for b in (1, 2):                            # batch 0's buffer was legitimately reused by batch 2
+            ref = api.render_views(volume, refs[b], tf, P)
+            ok = ok and bool(torch.equal(kept[b], ref[own.start:own.stop]))
+        report(f"framebuffer partition={partition} owners={owners} (p2p={fb.p2p})", ok)
+        del fb
 for mode in ("views", "tiles"):
-    got = mdist.render_views(volume, cams_all, tf, P, mode=mode)
-    ref = api.render_views(volume, cams_all, tf, P)
+    _, cams = bench._scene(V)
+    got = mdist.render_views(volume, cams, tf, P, mode=mode)
+    ref = api.render_views(volume, cams, tf, P)
     report(f"image-space NCCL all_gather mode={mode}", bool(torch.equal(got, ref)))
 
 # 2. sort-last: NCCL exchange and peer exchange vs the unsharded render
@@ -76,3 +87,4 @@ report("differentiable tiles + all_reduce gradients == single GPU", rv <= 1e-5 a
 if rank == 0:
     print("ALL OK" if ok_all else "SOME FAILED", flush=True)
 dist.destroy_process_group()
+sys.exit(0 if ok_all else 1)
