@@ -16,12 +16,15 @@
 //     its buffers once at load time and only refills `gParams` per frame
 //     (inr/viewer/brats_viewer.py:219-230 vs :405-426); a step's inputs are then cameras, params,
 //     modality weights and the TF;
-//   * frames come down SPARSE: per view only the bounding rectangle of its spans — the screen
-//     footprint of the active-brick box, outside which every pixel is the background — is copied
-//     (one strided copy per view).  The host frame outside the rectangle is kept at the background
-//     by damage tracking: the pipeline remembers the rectangle it last wrote into each output
-//     buffer and clears only what the new rectangle no longer covers (everything, the first time
-//     it sees a buffer).  The frames in host memory are bit-identical to the dense download.
+//   * frames come down SPARSE: only the tiles inside each view's spans — the screen footprint of
+//     the active-brick box, outside which every pixel is the background — cross PCIe.  When the
+//     output buffer is page-locked (hence device-mapped under UVA) the march kernel stores those
+//     tiles STRAIGHT into host memory, exactly as the multi-GPU path stores into a peer GPU: the
+//     transfer overlaps the march and there is no copy at all; otherwise each view's bounding
+//     rectangle is copied (one strided copy per view).  The rest of the host frame is kept at the
+//     background by damage tracking: the pipeline remembers, per tile row, the range it last wrote
+//     into each output buffer and clears only what the new range no longer covers (everything, the
+//     first time it sees a buffer).  The frames in host memory are bit-identical to a dense download.
 // It is the only part of the library that owns device memory (documented exception to "the
 // caller owns every buffer": the caller here has no device pointers at all).
 #include "march.cuh"
@@ -31,11 +34,12 @@
 #include <unordered_map>
 #include <vector>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
-struct HpRect { int x0, y0, x1, y1; };                    // inclusive; empty when x1 < x0
 struct HpOutState {
-  std::vector<HpRect> rects;                               // per view slot: what the pipeline last wrote
+  std::vector<int32_t> ranges;      // [view][tile row][2]: pixel columns (inclusive) that may hold non-background; x0 > x1: none
+  int nviews;
   float bg[4];
   int W, H;
   int64_t last_ticket;
@@ -155,26 +159,38 @@ fail:
   return rc;
 }
 
-// background into the pixels of `from` that `keep` does not cover (row-major float4 image of width W)
-static size_t hp_fill_difference(float* img, int W, const HpRect& from, const HpRect& keep, const float bg[4]) {
+// background into columns [ox0, ox1] minus [nx0, nx1] of image rows [y0, y1] (row-major float4, width W)
+static size_t hp_fill_damage(float* img, int W, int y0, int y1, int ox0, int ox1, int nx0, int nx1, const float bg[4]) {
+  if (ox1 < ox0) return 0;
+  int seg[2][2] = {{ox0, ox1}, {1, 0}};
+  if (nx1 >= nx0) {
+    seg[0][1] = (nx0 - 1 < ox1) ? nx0 - 1 : ox1;
+    seg[1][0] = (nx1 + 1 > ox0) ? nx1 + 1 : ox0; seg[1][1] = ox1;
+  }
   size_t n = 0;
-  if (from.x1 < from.x0 || from.y1 < from.y0) return 0;
-  const bool keep_empty = keep.x1 < keep.x0 || keep.y1 < keep.y0;
-  for (int y = from.y0; y <= from.y1; ++y) {
+  for (int y = y0; y <= y1; ++y) {
     float* row = img + (size_t)y * W * 4;
-    int segs[2][2] = {{from.x0, from.x1}, {1, 0}};
-    if (!keep_empty && y >= keep.y0 && y <= keep.y1) {
-      segs[0][0] = from.x0; segs[0][1] = (keep.x0 - 1 < from.x1) ? keep.x0 - 1 : from.x1;
-      segs[1][0] = (keep.x1 + 1 > from.x0) ? keep.x1 + 1 : from.x0; segs[1][1] = from.x1;
-    }
-    for (int s = 0; s < 2; ++s)
-      for (int x = segs[s][0]; x <= segs[s][1]; ++x) {
+    for (int k = 0; k < 2; ++k)
+      for (int x = seg[k][0]; x <= seg[k][1]; ++x) {
         float* px = row + (size_t)x * 4;
         px[0] = bg[0]; px[1] = bg[1]; px[2] = bg[2]; px[3] = bg[3];
         ++n;
       }
   }
   return n * 4 * sizeof(float);
+}
+
+// can the device address this host buffer directly (page-locked => mapped under UVA)?
+static float* hp_device_view(const float* host, size_t bytes) {
+  static const char* env = getenv("MRT_HP_ZEROCOPY");
+  if (env && env[0] == '0') return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+  cudaPointerAttributes b;                                 // the whole range must belong to the allocation
+  if (cudaPointerGetAttributes(&b, reinterpret_cast<const char*>(host) + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (b.type != cudaMemoryTypeHost) return nullptr;
+  return reinterpret_cast<float*>(a.devicePointer);
 }
 
 int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const MrtCamera* cams, int32_t nviews,
@@ -197,8 +213,8 @@ int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const 
     if (s.ticket >= 0) HP_CUDA(cudaEventSynchronize(s.e_done));
     // an output buffer still being written by an earlier step must not be touched yet
     HpOutState& os = (*p->outs)[out_rgba_host];
-    const bool known = !os.rects.empty() && !(out_flags & MRT_OUT_FRESH) && os.W == p->W && os.H == p->H;
-    if (!os.rects.empty() && os.last_ticket >= 0) {
+    const bool known = !os.ranges.empty() && !(out_flags & MRT_OUT_FRESH) && os.W == p->W && os.H == p->H;
+    if (!os.ranges.empty() && os.last_ticket >= 0) {
       MrtHostPipeline::Slot& prev = p->slot[os.last_ticket % p->depth];
       if (prev.ticket == os.last_ticket) HP_CUDA(cudaEventSynchronize(prev.e_done));
     }
@@ -243,63 +259,83 @@ int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const 
     }
     if (rc != MRT_OK) { snprintf(p->err, sizeof(p->err), "submit: %s", mrt_last_error()); return rc; }
     HP_CUDA(cudaEventRecord(s.e_prep, p->s_prep));
-    // ---- march
+    // ---- march + download
     HP_CUDA(cudaStreamWaitEvent(p->s_cmp, s.e_prep, 0));
-    if (sparse)        // spans precomputed above: one load + two compares per warp instead of a per-ray box test
-      rc = mrt_render_forward_batch_sparse(&P, cams, nviews, s.d_packed, Ce, s.d_tf, tfN, s.d_levels, s.d_frames,
-                                           s.d_spans, 2, p->s_cmp);
-    else
+    uint64_t d2h = 0, filled = 0;
+    const float bgp[4] = {P.bgColor[0], P.bgColor[1], P.bgColor[2], P.alphaMode ? 0.0f : 1.0f};
+    const int ty = p->tiles_y;
+    float* out_dev = sparse ? hp_device_view(out_rgba_host, p->frame_bytes * nviews) : nullptr;
+    if (sparse) {
+      // spans precomputed above: one load + two compares per warp instead of a per-ray box test.
+      // Zero-copy: the in-span tiles go straight to the (device-mapped) host frames and nothing else is
+      // stored; staged: complete frames into the slot, bounding rectangles copied below.
+      if (out_dev) rc = mrt_render_forward_batch_sparse(&P, cams, nviews, s.d_packed, Ce, s.d_tf, tfN, s.d_levels, out_dev, s.d_spans, 0, p->s_cmp);
+      else rc = mrt_render_forward_batch_sparse(&P, cams, nviews, s.d_packed, Ce, s.d_tf, tfN, s.d_levels, s.d_frames, s.d_spans, 2, p->s_cmp);
+    } else {
       rc = mrt_render_forward_batch(&P, cams, nviews, s.d_packed, Ce, s.d_tf, tfN, skip ? s.d_levels : nullptr,
                                     nullptr, nullptr, s.d_frames, nullptr, nullptr, 0,
                                     mrt_tile_count(p->W, p->H), p->s_cmp);
+    }
     if (rc != MRT_OK) { snprintf(p->err, sizeof(p->err), "submit: %s", mrt_last_error()); return rc; }
     HP_CUDA(cudaEventRecord(s.e_cmp, p->s_cmp));
-    // ---- download
     HP_CUDA(cudaStreamWaitEvent(p->s_d2h, s.e_cmp, 0));
-    uint64_t d2h = 0, filled = 0;
-    const float bgp[4] = {P.bgColor[0], P.bgColor[1], P.bgColor[2], P.alphaMode ? 0.0f : 1.0f};
+    std::vector<int32_t> now((size_t)nviews * ty * 2);
     if (sparse) {
       // the spans of THIS step are on the host as soon as the (short) prepare stage is done; the
       // march runs meanwhile
       HP_CUDA(cudaEventSynchronize(s.e_prep));
       d2h += span_bytes;
       const bool same_bg = known && memcmp(os.bg, bgp, sizeof(bgp)) == 0;
-      if ((int)os.rects.size() < nviews) os.rects.resize(nviews, HpRect{0, 0, -1, -1});
-      const HpRect whole = {0, 0, p->W - 1, p->H - 1};
       for (int v = 0; v < nviews; ++v) {
-        HpRect r = {p->W, p->H, -1, -1};
-        const int32_t* sp = s.h_spans + (size_t)v * p->tiles_y * 2;
-        for (int b = 0; b < p->tiles_y; ++b) {
+        const int32_t* sp = s.h_spans + (size_t)v * ty * 2;
+        int32_t* nr = now.data() + (size_t)v * ty * 2;
+        int rx0 = p->W, rx1 = -1, ry0 = p->H, ry1 = -1;
+        for (int b = 0; b < ty; ++b) {
           const int x0 = sp[2 * b], x1 = sp[2 * b + 1];
+          nr[2 * b] = 1; nr[2 * b + 1] = 0;
           if (x0 > x1) continue;
-          const int y0 = b << MRT_TILE_SHIFT, y1 = ((b << MRT_TILE_SHIFT) + MRT_TILE_EDGE - 1 < p->H - 1) ? (b << MRT_TILE_SHIFT) + MRT_TILE_EDGE - 1 : p->H - 1;
           // whole tiles are stored by the march: round the span outward to tile columns
           const int tx0 = x0 & ~MRT_TILE_MASK, tx1 = ((x1 | MRT_TILE_MASK) < p->W - 1) ? (x1 | MRT_TILE_MASK) : p->W - 1;
-          if (tx0 < r.x0) r.x0 = tx0;
-          if (tx1 > r.x1) r.x1 = tx1;
-          if (y0 < r.y0) r.y0 = y0;
-          if (y1 > r.y1) r.y1 = y1;
+          nr[2 * b] = tx0; nr[2 * b + 1] = tx1;
+          const int y0 = b << MRT_TILE_SHIFT, y1 = (y0 + MRT_TILE_EDGE - 1 < p->H - 1) ? y0 + MRT_TILE_EDGE - 1 : p->H - 1;
+          if (tx0 < rx0) rx0 = tx0;
+          if (tx1 > rx1) rx1 = tx1;
+          if (y0 < ry0) ry0 = y0;
+          if (y1 > ry1) ry1 = y1;
+          if (out_dev) d2h += (uint64_t)(tx1 - tx0 + 1) * (y1 - y0 + 1) * 4 * sizeof(float);
+        }
+        if (!out_dev && rx1 >= rx0) {
+          // staged: the bounding rectangle of the view's spans in one strided copy; every band inside it
+          // then holds device data (background included), so the tracked range is the rectangle's
+          for (int b = ry0 >> MRT_TILE_SHIFT; b <= (ry1 >> MRT_TILE_SHIFT); ++b) { nr[2 * b] = rx0; nr[2 * b + 1] = rx1; }
         }
         float* himg = out_rgba_host + (size_t)v * p->W * p->H * 4;
-        // host frame outside r must hold the background: clear what the previous rectangle covered
-        // and r does not (everything outside r when the buffer's contents are unknown)
-        filled += hp_fill_difference(himg, p->W, (same_bg && v < (int)os.rects.size()) ? os.rects[v] : whole, r, bgp);
-        if (r.x1 >= r.x0) {
-          const size_t off = ((size_t)r.y0 * p->W + r.x0) * 4;
-          const size_t wbytes = (size_t)(r.x1 - r.x0 + 1) * 4 * sizeof(float);
+        // the host frame outside the new ranges must hold the background: clear what the previous
+        // ranges covered and the new ones do not (everything else when the contents are unknown)
+        const bool have_old = same_bg && v < os.nviews;
+        for (int b = 0; b < ty; ++b) {
+          const int y0 = b << MRT_TILE_SHIFT, y1 = (y0 + MRT_TILE_EDGE - 1 < p->H - 1) ? y0 + MRT_TILE_EDGE - 1 : p->H - 1;
+          const int ox0 = have_old ? os.ranges[((size_t)v * ty + b) * 2] : 0;
+          const int ox1 = have_old ? os.ranges[((size_t)v * ty + b) * 2 + 1] : p->W - 1;
+          filled += hp_fill_damage(himg, p->W, y0, y1, ox0, ox1, nr[2 * b], nr[2 * b + 1], bgp);
+        }
+        if (!out_dev && rx1 >= rx0) {
+          const size_t off = ((size_t)ry0 * p->W + rx0) * 4;
+          const size_t wbytes = (size_t)(rx1 - rx0 + 1) * 4 * sizeof(float);
           HP_CUDA(cudaMemcpy2DAsync(himg + off, (size_t)p->W * 4 * sizeof(float),
                                     s.d_frames + (size_t)v * p->W * p->H * 4 + off, (size_t)p->W * 4 * sizeof(float),
-                                    wbytes, (size_t)(r.y1 - r.y0 + 1), cudaMemcpyDeviceToHost, p->s_d2h));
-          d2h += wbytes * (size_t)(r.y1 - r.y0 + 1);
+                                    wbytes, (size_t)(ry1 - ry0 + 1), cudaMemcpyDeviceToHost, p->s_d2h));
+          d2h += wbytes * (size_t)(ry1 - ry0 + 1);
         }
-        os.rects[v] = r;
       }
-      for (size_t v = nviews; v < os.rects.size(); ++v) os.rects[v] = whole;     // untouched view slots: contents unknown to us
     } else {
       HP_CUDA(cudaMemcpyAsync(out_rgba_host, s.d_frames, p->frame_bytes * nviews, cudaMemcpyDeviceToHost, p->s_d2h));
       d2h += p->frame_bytes * nviews;
-      os.rects.assign(nviews, HpRect{0, 0, p->W - 1, p->H - 1});
+      for (int v = 0; v < nviews; ++v)
+        for (int b = 0; b < ty; ++b) { now[((size_t)v * ty + b) * 2] = 0; now[((size_t)v * ty + b) * 2 + 1] = p->W - 1; }
     }
+    os.ranges.swap(now);
+    os.nviews = nviews;               // view slots beyond nviews: contents unknown to us from now on
     memcpy(os.bg, bgp, sizeof(bgp));
     os.W = p->W; os.H = p->H; os.last_ticket = t;
     HP_CUDA(cudaEventRecord(s.e_done, p->s_d2h));

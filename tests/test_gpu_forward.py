@@ -271,12 +271,15 @@ def test_host_pipeline_equals_device_renders(cuda, C, use_tf):
     pipe.close()
 
 
-def test_host_pipeline_resident_volume_sparse_download_and_damage_tracking(cuda):
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_pipeline_resident_volume_sparse_download_and_damage_tracking(cuda, pinned):
     """Resident volume (set_volume once, the reference's load-time upload) + sparse frame download:
     only each view's bounding rectangle of non-background tiles crosses PCIe, the pipeline keeps the
     rest of the host frame at the background.  Output arrays are REUSED across steps whose cameras
-    move (so the rectangle moves, shrinks, vanishes and the background colour changes): the host
-    frames must equal the device-side renders bit for bit every time."""
+    move (so the footprint moves, shrinks, vanishes and the background colour changes): the host
+    frames must equal the device-side renders bit for bit every time.  Page-locked outputs are written
+    by the march kernel itself (zero-copy stores of the in-span tiles); pageable ones take the staged
+    path (one strided copy of each view's bounding rectangle)."""
     from mri_raytracer_b200 import OrbitalCamera, orbit_views
     dims, W, H, V = (40, 36, 28), 75, 53, 2
     vol, _, P = small_scene(C=4, dims=dims, W=W, H=H, seed=3)
@@ -285,7 +288,9 @@ def test_host_pipeline_resident_volume_sparse_download_and_damage_tracking(cuda)
     pipe = api.HostPipeline(4, dims, (W, H), max_views=V, max_tf=64, depth=3)
     vh = vol.pin_memory()
     pipe.set_volume(vh.numpy())
-    outs = [torch.full((V, H, W, 4), 7.0).pin_memory() for _ in range(2)]        # garbage: must be overwritten
+    outs = [torch.full((V, H, W, 4), 7.0) for _ in range(2)]                     # garbage: must be overwritten
+    if pinned:
+        outs = [o.pin_memory() for o in outs]
     total_d2h = 0
     for step in range(7):
         cam = Vd.frame_camera(OrbitalCamera(initial_radius=3.0, initial_theta=0.7 * step, initial_phi=1.3))
