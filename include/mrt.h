@@ -370,7 +370,10 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
  * predict_volume of the reference's implicit-neural-representation segmenter (inr/inr/model.py:119-141,
  * called at inr/viewer/brats_viewer.py:250-310): per voxel, normalised coordinates -> Fourier
  * features (:11-18) -> [coords | features | M intensities] (:21-23) -> dense/ReLU chain (:43-50) ->
- * argmax.  One fused kernel; fp32 accumulation.
+ * argmax.  One fused kernel.  impl 0 (default): tcgen05 tensor cores — 128-voxel tiles, fp32
+ * accumulators in TMEM, every product a 3-term TF32 split so the logits match fp32 to ~1e-6 — when
+ * the network fits (widths <= 64, weights within shared memory), else the fp32 FFMA kernel;
+ * impl 1: fp32 FFMA on the CUDA cores; impl 2: tensor cores or MRT_ERR_UNSUPPORTED.
  *   mods_planar : device fp32 [M][Z][Y][X] (the renderer's planar layout), z-scored by the caller
  *                 like brats_viewer.py:279-287
  *   weights     : device fp32, per layer W[in][out] row-major followed by b[out]
@@ -380,7 +383,7 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
  *   out_logits  : optional device fp32 [Z][Y][X][classes] */
 int mrt_inr_predict(const float* mods_planar, int32_t M, int32_t X, int32_t Y, int32_t Z,
                     const float* weights, const int32_t* layer_dims, int32_t n_layers, int32_t fourier_freqs,
-                    int32_t* out_labels, float* out_logits, void* stream);
+                    int32_t* out_labels, float* out_logits, int32_t impl, void* stream);
 
 /* ------------------------------------------------ sort-last compositing
  * Ordered front-to-back `over` of K partial images (premultiplied colour + transmittance):

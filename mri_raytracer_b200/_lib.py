@@ -118,7 +118,7 @@ PROTOTYPES = {
     "mrt_decode_bc4": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_u8_to_f32": (C.c_int, [_vp, _sz, _vp, _vp]),
     "mrt_normalize_f32": (C.c_int, [_vp, _sz, _f, _f, _vp, _vp]),
-    "mrt_inr_predict": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "mrt_inr_predict": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "mrt_composite_over": (C.c_int, [_vp, _i32, _vp, _sz, _vp, _i32, _vp, _vp]),
     "mrt_composite_over_multi": (C.c_int, [_vp, _i32, _vp, _sz, _vp, _i32, _vp, _i32, _vp]),
     "mrt_render_forward_strips": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

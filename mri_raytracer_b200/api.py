@@ -159,8 +159,11 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
     return out
 
 
-def _camera_array(cams: Sequence) -> np.ndarray:
-    """``MrtCamera[len(cams)]`` as a float32 ``[V,16]`` array (rows eye|pad, U|pad, V|pad, W|pad)."""
+def _camera_array(cams) -> np.ndarray:
+    """``MrtCamera[len(cams)]`` as a float32 ``[V,16]`` array (rows eye|pad, U|pad, V|pad, W|pad); an
+    array built by an earlier call passes through (callers that launch several kernels per batch)."""
+    if isinstance(cams, np.ndarray):
+        return cams
     a = np.zeros((len(cams), 4, 4), dtype=np.float32)
     a[:, :, :3] = np.asarray([(c.eye, c.U, c.V, c.W) for c in cams], dtype=np.float32)
     return a.reshape(len(cams), 16)
@@ -807,12 +810,15 @@ def render_host(volume: np.ndarray, params: RenderParams, tf: Optional[np.ndarra
     return out
 
 
-def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, return_logits: bool = False):
+def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, return_logits: bool = False,
+                impl: str = "auto"):
     """INR segmentation of a whole volume on the GPU (``mrt_inr_predict``): the reference's
     ``predict_volume`` (inr/inr/model.py:119-141) as one fused kernel.
 
     mods   : ``[M,Z,Y,X]`` CUDA float32, z-scored per modality (:func:`volume.zscore_modalities`)
     params : the reference's parameter list ``[{"W": [in,out], "b": [out]}, ...]`` (numpy or torch)
+    impl   : "auto" (tcgen05 tensor cores when the network fits, else FFMA), "ffma" (fp32 on the CUDA
+             cores: the parity reference), "tensor" (tensor cores or an error)
     -> int32 labels ``[Z,Y,X]`` — directly usable as ``preds`` of :class:`Volume` / :func:`render` —
     and, with ``return_logits``, float32 ``[Z,Y,X,classes]``."""
     _need_cuda(mods, "mods", torch.float32)
@@ -828,7 +834,8 @@ def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, 
     logits = torch.empty((Z, Y, X, dims[-1]), dtype=torch.float32, device=mods.device) if return_logits else None
     ld = (C.c_int32 * len(dims))(*dims)
     check(lib().mrt_inr_predict(mods.data_ptr(), M, X, Y, Z, wts.data_ptr(), C.cast(ld, C.c_void_p), len(params),
-                                int(fourier_freqs), labels.data_ptr(), _ptr(logits), _stream()), "inr_predict")
+                                int(fourier_freqs), labels.data_ptr(), _ptr(logits),
+                                {"auto": 0, "ffma": 1, "tensor": 2}[impl], _stream()), "inr_predict")
     return (labels, logits) if return_logits else labels
 
 

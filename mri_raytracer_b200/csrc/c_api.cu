@@ -557,7 +557,7 @@ int mrt_normalize_f32(const float* in, size_t n, float vmin, float rng, float* o
 // ---------------------------------------------------------------- INR inference (producer of gPreds)
 int mrt_inr_predict(const float* mods_planar, int32_t M, int32_t X, int32_t Y, int32_t Z, const float* weights,
                     const int32_t* layer_dims, int32_t n_layers, int32_t fourier_freqs, int32_t* out_labels,
-                    float* out_logits, void* stream) {
+                    float* out_logits, int32_t impl, void* stream) {
   MRT_REQUIRE(mods_planar && weights && layer_dims && out_labels, "inr_predict: null pointer");
   MRT_REQUIRE(M >= 1 && M <= 8 && X >= 2 && Y >= 2 && Z >= 2, "inr_predict: bad volume shape");
   MRT_REQUIRE(n_layers >= 1 && n_layers <= 8, "inr_predict: n_layers=%d outside 1..8", n_layers);
@@ -569,8 +569,10 @@ int mrt_inr_predict(const float* mods_planar, int32_t M, int32_t X, int32_t Y, i
     MRT_REQUIRE(layer_dims[l] >= 1 && layer_dims[l] <= 64, "inr_predict: hidden width %d outside 1..64", layer_dims[l]);
   MRT_REQUIRE(layer_dims[n_layers] >= 1 && layer_dims[n_layers] <= 8, "inr_predict: %d classes outside 1..8",
               layer_dims[n_layers]);
+  MRT_REQUIRE(impl >= 0 && impl <= 2, "inr_predict: impl %d unknown (0 auto, 1 fp32 FFMA, 2 tensor cores)", impl);
   cudaError_t e = mrt_launch_inr(mods_planar, M, X, Y, Z, weights, layer_dims, n_layers, fourier_freqs, out_labels,
-                                 out_logits, (cudaStream_t)stream);
+                                 out_logits, impl, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) return fail(MRT_ERR_UNSUPPORTED, "inr_predict: the network does not fit the tensor-core kernel");
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "inr_predict");
 }
 

@@ -8,9 +8,17 @@
 // (read as warp-wide broadcasts) and the activations in registers; input voxels are read in the
 // renderer's own planar [M][Z][Y][X] layout and labels are written as int32 [Z][Y][X], the layout
 // Volume(preds=...) takes — so the transpose of brats_viewer.py:297 disappears.
-// fp32 FFMA on the CUDA cores: the reference network is 31 -> 64 x 4 -> 4 (29 kFLOP per voxel,
-// 0.26 TFLOP per BraTS case).  A tcgen05 version (128-voxel tiles, TMEM accumulators) is the
-// planned follow-up; argmax parity wants fp32 accumulation either way.
+// Two implementations of the same network:
+//   * mrt_inr_tc_kernel (default): the dense chain on the 5th-generation tensor cores — tcgen05.mma
+//     kind::tf32 with 128-voxel M tiles, fp32 accumulators in TMEM, the activations fed back as the A
+//     operand FROM TMEM (bias + ReLU applied by the epilogue warps between tcgen05.ld and
+//     tcgen05.st), the weights resident in shared memory as K-major UMMA operands.  Every product
+//     is evaluated as a 3-term TF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate), so the logits
+//     agree with fp32 FFMA to ~1e-6 and argmax parity holds — a single-pass bf16/tf32 product
+//     would not keep labels stable where the top-2 logits are close;
+//   * mrt_inr_kernel2: fp32 FFMA on the CUDA cores, one thread per voxel (the parity reference for
+//     the tensor-core kernel and the fallback for networks whose weights do not fit shared memory).
+// The reference network is 31 -> 64 x 4 -> 4 (29 kFLOP per voxel, 0.26 TFLOP per BraTS case).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "kernels.h"
@@ -32,104 +40,6 @@ struct InrNet {
 template <int HID>
 __host__ __device__ inline int inr_smem_floats(int n_layers) {
   return (n_layers - 1) * (HID * HID + HID) + HID * MRT_INR_MAX_CLASSES + MRT_INR_MAX_CLASSES;
-}
-
-template <int HID>
-__global__ void __launch_bounds__(128)
-mrt_inr_kernel(const __grid_constant__ InrNet N, const float* __restrict__ mods, int X, int Y, int Z,
-               const float* __restrict__ wts, int32_t* __restrict__ labels, float* __restrict__ logits) {
-  extern __shared__ __align__(16) float s_w[];
-  const int total = inr_smem_floats<HID>(N.n_layers);
-  for (int i = threadIdx.x; i < total; i += blockDim.x) s_w[i] = 0.0f;
-  __syncthreads();
-  for (int l = 0; l < N.n_layers; ++l) {
-    const int in = N.dims[l], out = N.dims[l + 1];
-    const bool last = (l == N.n_layers - 1);
-    const int ld = last ? MRT_INR_MAX_CLASSES : HID;
-    float* W = s_w + l * (HID * HID + HID);
-    float* b = W + HID * ld;
-    const float* src = wts + N.src_off[l];
-    for (int i = threadIdx.x; i < in * out; i += blockDim.x) W[(i / out) * ld + (i % out)] = __ldg(src + i);
-    for (int i = threadIdx.x; i < out; i += blockDim.x) b[i] = __ldg(src + in * out + i);
-  }
-  __syncthreads();
-
-  const size_t nvox = (size_t)X * Y * Z;
-  const int ncls = N.dims[N.n_layers];
-  for (size_t vox = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vox < nvox; vox += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(vox % X), y = (int)((vox / X) % Y), z = (int)(vox / ((size_t)X * Y));
-    float h[HID], g[HID];
-#pragma unroll
-    for (int i = 0; i < HID; ++i) h[i] = 0.0f;
-    // model.py:128 normalises in float64 ((grid / (n-1)) * 2 - 1) and then casts to float32
-    float c[3];
-    c[0] = (float)(((double)x / (double)(X - 1)) * 2.0 - 1.0);
-    c[1] = (float)(((double)y / (double)(Y - 1)) * 2.0 - 1.0);
-    c[2] = (float)(((double)z / (double)(Z - 1)) * 2.0 - 1.0);
-    // build_input (:21-23): [coords | per coordinate: sin(f pi x) f=1..k, then cos | intensities]; the
-    // writes below use compile-time indices only (the runtime bounds are predicates), so h[] stays in registers
-    const float pi = 3.14159265358979323846f;
-#pragma unroll
-    for (int i = 0; i < HID; ++i) {
-      float v = 0.0f;
-      const int j = i - 3;                                   // index into the Fourier block
-      if (i < 3) {
-        v = (i == 0) ? c[0] : ((i == 1) ? c[1] : c[2]);
-      } else if (j < 6 * N.k) {
-        const int d = j / (2 * N.k), r = j - d * 2 * N.k;    // coordinate, position inside its [sin.. | cos..] group
-        const int f = (r < N.k ? r : r - N.k) + 1;
-        const float cd = (d == 0) ? c[0] : ((d == 1) ? c[1] : c[2]);
-        const float ang = __fmul_rn(__fmul_rn(cd, (float)f), pi);            // :14 (coords * freqs) * pi, in fp32
-        v = (r < N.k) ? sinf(ang) : cosf(ang);
-      } else if (j - 6 * N.k < N.M) {
-        v = __ldg(mods + (size_t)(j - 6 * N.k) * nvox + vox);
-      }
-      h[i] = v;
-    }
-    // apply_mlp (:43-50)
-    for (int l = 0; l < N.n_layers - 1; ++l) {
-      const float* W = s_w + l * (HID * HID + HID);
-      const float* b = W + HID * HID;
-#pragma unroll
-      for (int j = 0; j < HID; ++j) g[j] = b[j];
-#pragma unroll
-      for (int i = 0; i < HID; ++i) {
-        const float hi = h[i];
-        const float4* row = reinterpret_cast<const float4*>(W + i * HID);
-#pragma unroll
-        for (int j4 = 0; j4 < HID / 4; ++j4) {
-          const float4 w = row[j4];                           // warp-wide broadcast
-          g[4 * j4 + 0] = fmaf(hi, w.x, g[4 * j4 + 0]); g[4 * j4 + 1] = fmaf(hi, w.y, g[4 * j4 + 1]);
-          g[4 * j4 + 2] = fmaf(hi, w.z, g[4 * j4 + 2]); g[4 * j4 + 3] = fmaf(hi, w.w, g[4 * j4 + 3]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < HID; ++j) h[j] = fmaxf(g[j], 0.0f);
-    }
-    {
-      const float* W = s_w + (N.n_layers - 1) * (HID * HID + HID);
-      const float* b = W + HID * MRT_INR_MAX_CLASSES;
-      float o[MRT_INR_MAX_CLASSES];
-#pragma unroll
-      for (int j = 0; j < MRT_INR_MAX_CLASSES; ++j) o[j] = b[j];
-#pragma unroll
-      for (int i = 0; i < HID; ++i) {
-        const float hi = h[i];
-        const float4* row = reinterpret_cast<const float4*>(W + i * MRT_INR_MAX_CLASSES);
-        const float4 w0 = row[0], w1 = row[1];
-        o[0] = fmaf(hi, w0.x, o[0]); o[1] = fmaf(hi, w0.y, o[1]); o[2] = fmaf(hi, w0.z, o[2]); o[3] = fmaf(hi, w0.w, o[3]);
-        o[4] = fmaf(hi, w1.x, o[4]); o[5] = fmaf(hi, w1.y, o[5]); o[6] = fmaf(hi, w1.z, o[6]); o[7] = fmaf(hi, w1.w, o[7]);
-      }
-      int best = 0; float bv = o[0];
-#pragma unroll
-      for (int j = 1; j < MRT_INR_MAX_CLASSES; ++j) if (j < ncls && o[j] > bv) { bv = o[j]; best = j; }   // first maximum, like argmax
-      labels[vox] = best;
-      if (logits != nullptr) {
-#pragma unroll
-        for (int j = 0; j < MRT_INR_MAX_CLASSES; ++j) if (j < ncls) logits[vox * ncls + j] = o[j];
-      }
-    }
-  }
 }
 
 // Second version: the activations live in shared memory, one column per thread ([HID][block]:
@@ -231,35 +141,315 @@ mrt_inr_kernel2(const __grid_constant__ InrNet N, const float* __restrict__ mods
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version (tcgen05 / TMEM).  One CTA per SM, persistent over 128-voxel tiles:
+//   warps 0-3, 4-7 : two epilogue warpgroups, each owning one tile "slot" (TMEM lane = voxel row)
+//   warp 8         : one elected thread issues every tcgen05.mma
+// Per slot the TMEM holds D [64 columns] | A_hi [64] | A_lo [64].  A layer is
+//   D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (tf32 operands, fp32 accumulate in TMEM)
+// with A read from TMEM and W (K-major, no swizzle: 8x16-byte core matrices, K chunks LBO apart,
+// 8-row groups SBO = 128 B apart) from shared memory.  While the tensor core works on one slot the
+// other slot's warpgroup runs its epilogue: tcgen05.ld D -> + bias, ReLU -> split into tf32 hi/lo ->
+// tcgen05.st A.  The two hand-offs per slot are mbarriers: a_ready (128 epilogue threads arrive) and
+// d_ready (tcgen05.commit).
+#define INR_TC_THREADS 288
+#define INR_TC_SLOT_COLS 192
+#define INR_TC_HID 64
+#define INR_TC_NLAST 16
+
+__device__ __forceinline__ uint32_t inr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void inr_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(inr_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void inr_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(inr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void inr_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "INR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra INR_DONE_%=;\n"
+      "bra INR_WAIT_%=;\n"
+      "INR_DONE_%=:\n"
+      "}\n" :: "r"(inr_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t inr_tf32(float x) {      // round to nearest tf32 (low 13 mantissa bits zero)
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t inr_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, M = 128
+__device__ __forceinline__ uint32_t inr_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void inr_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void inr_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(inr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void inr_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void inr_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// byte offsets of the shared-memory image
+struct InrTcLayout { int bias_off, w_off[MRT_INR_MAX_LAYERS], kp[MRT_INR_MAX_LAYERS], np[MRT_INR_MAX_LAYERS], total; };
+static inline InrTcLayout inr_tc_layout(const InrNet& N) {
+  InrTcLayout L = {};
+  int off = 64;                                               // [0,4) TMEM base, [16,48) four mbarriers
+  L.bias_off = off; off += N.n_layers * INR_TC_HID * (int)sizeof(float);
+  off = (off + 127) & ~127;
+  for (int l = 0; l < N.n_layers; ++l) {
+    L.kp[l] = (l == 0) ? ((N.dims[0] + 7) & ~7) : INR_TC_HID;
+    L.np[l] = (l == N.n_layers - 1) ? INR_TC_NLAST : INR_TC_HID;
+    L.w_off[l] = off;
+    off += 2 * L.kp[l] * L.np[l] * (int)sizeof(float);        // hi image, then lo image
+  }
+  L.total = off;
+  return L;
+}
+
+__global__ void __launch_bounds__(INR_TC_THREADS, 1)
+mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrTcLayout L, const float* __restrict__ mods,
+                  int X, int Y, int Z, const float* __restrict__ wts, int32_t* __restrict__ labels, float* __restrict__ logits) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_raw);
+  uint64_t* a_ready = reinterpret_cast<uint64_t*>(s_raw + 16);     // [2]
+  uint64_t* d_ready = reinterpret_cast<uint64_t*>(s_raw + 32);     // [2]
+  float* s_bias = reinterpret_cast<float*>(s_raw + L.bias_off);    // [layer][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nl = N.n_layers;
+
+  // ---- one-time set-up: weights -> UMMA images (tf32 hi / lo), biases, barriers, TMEM
+  for (int i = threadIdx.x; i < (L.total - L.bias_off) / 4; i += blockDim.x) reinterpret_cast<float*>(s_raw + L.bias_off)[i] = 0.0f;
+  __syncthreads();
+  for (int l = 0; l < nl; ++l) {
+    const int in = N.dims[l], out = N.dims[l + 1], np = L.np[l], kp = L.kp[l];
+    const float* src = wts + N.src_off[l];
+    uint32_t* hi = reinterpret_cast<uint32_t*>(s_raw + L.w_off[l]);
+    uint32_t* lo = hi + kp * np;
+    for (int i = threadIdx.x; i < in * out; i += blockDim.x) {
+      const int k = i / out, n = i - k * out;                  // W[k][n]  ->  B[n][k] (K-major)
+      const float w = __ldg(src + i);
+      const uint32_t h = inr_tf32(w);
+      const int e = (k >> 2) * (np * 4) + n * 4 + (k & 3);     // 16-byte chunk (k/4) of row n
+      hi[e] = h;
+      lo[e] = inr_tf32(w - __uint_as_float(h));
+    }
+    for (int i = threadIdx.x; i < out; i += blockDim.x) s_bias[l * INR_TC_HID + i] = __ldg(src + in * out + i);
+  }
+  if (threadIdx.x == 0) {
+    inr_mbar_init(&a_ready[0], 128); inr_mbar_init(&a_ready[1], 128);
+    inr_mbar_init(&d_ready[0], 1);   inr_mbar_init(&d_ready[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(inr_smem_u32(s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the weight images are read by the tensor core (async proxy)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+
+  const size_t nvox = (size_t)X * Y * Z;
+  const int ntiles = (int)((nvox + 127) / 128);
+  const int mine = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles blockIdx.x + i*gridDim.x
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const int cnt0 = (mine + 1) >> 1;
+      for (int q = 0; q < cnt0; ++q) {
+        for (int l = 0; l < nl; ++l) {
+          for (int j = 0; j < 2; ++j) {
+            if (2 * q + j >= mine) continue;
+            inr_mbar_wait(&a_ready[j], (uint32_t)((q * nl + l) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kp = L.kp[l], np = L.np[l];
+            const uint32_t idesc = inr_idesc(np);
+            const uint32_t d = tmem + (uint32_t)(j * INR_TC_SLOT_COLS), a_hi = d + 64, a_lo = d + 128;
+            const uint32_t w_hi = inr_smem_u32(s_raw + L.w_off[l]), w_lo = w_hi + (uint32_t)(kp * np * 4);
+            const uint32_t lbo = (uint32_t)np * 16u, sbo = 128u;
+            for (int s8 = 0; s8 < kp / 8; ++s8) {              // one instruction = 8 tf32 of K = two 16-byte chunks
+              const uint64_t bh = inr_smem_desc(w_hi + (uint32_t)(2 * s8) * lbo, lbo, sbo);
+              const uint64_t bl = inr_smem_desc(w_lo + (uint32_t)(2 * s8) * lbo, lbo, sbo);
+              inr_mma_ts(d, a_lo + 8 * s8, bh, idesc, s8 > 0 ? 1u : 0u);
+              inr_mma_ts(d, a_hi + 8 * s8, bl, idesc, 1u);
+              inr_mma_ts(d, a_hi + 8 * s8, bh, idesc, 1u);
+            }
+            inr_commit(&d_ready[j]);                            // arrives when every MMA above has completed
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warpgroups
+    const int j = warp >> 2;                                     // slot
+    const int row = (warp & 3) * 32 + lane;                      // TMEM lane == voxel row of the tile
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * INR_TC_SLOT_COLS);
+    const uint32_t t_d = lane_base, t_hi = lane_base + 64, t_lo = lane_base + 128;
+    const int ncls = N.dims[nl];
+    const int cnt = (mine + 1 - j) >> 1;
+    for (int q = 0; q < cnt; ++q) {
+      const int tile = (int)blockIdx.x + (2 * q + j) * (int)gridDim.x;
+      const size_t vox = (size_t)tile * 128 + row;
+      const bool valid = vox < nvox;
+      // ---- layer-0 operand: [coords | Fourier features | intensities] (model.py:11-23), zero padded to kp[0]
+      {
+        const size_t vv = valid ? vox : 0;
+        const int x = (int)(vv % X), y = (int)((vv / X) % Y), z = (int)(vv / ((size_t)X * Y));
+        float c[3];
+        c[0] = (float)(((double)x / (double)(X - 1)) * 2.0 - 1.0);      // model.py:128 (float64, then cast)
+        c[1] = (float)(((double)y / (double)(Y - 1)) * 2.0 - 1.0);
+        c[2] = (float)(((double)z / (double)(Z - 1)) * 2.0 - 1.0);
+        const int kp0 = L.kp[0];
+        for (int c0 = 0; c0 < kp0; c0 += 16) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = c0 + u, jf = i - 3;
+            float v = 0.0f;
+            if (i < 3) {
+              v = (i == 0) ? c[0] : ((i == 1) ? c[1] : c[2]);
+            } else if (jf < 6 * N.k) {
+              const int dd = jf / (2 * N.k), r = jf - dd * 2 * N.k;
+              const int f = (r < N.k ? r : r - N.k) + 1;
+              const float cd = (dd == 0) ? c[0] : ((dd == 1) ? c[1] : c[2]);
+              // sin / cos of (coords * freqs) * pi (:14): evaluated as sinpi / cospi of the fp32 product
+              // (no large-argument reduction; differs from rounding the angle first by < 1e-6)
+              const float xf = __fmul_rn(cd, (float)f);
+              v = (r < N.k) ? sinpif(xf) : cospif(xf);
+            } else if (jf - 6 * N.k < N.M) {
+              v = valid ? __ldg(mods + (size_t)(jf - 6 * N.k) * nvox + vox) : 0.0f;
+            }
+            hi[u] = inr_tf32(v);
+            lo[u] = inr_tf32(v - __uint_as_float(hi[u]));
+          }
+          inr_tmem_st16(t_hi + c0, hi);
+          inr_tmem_st16(t_lo + c0, lo);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      inr_mbar_arrive(&a_ready[j]);
+      for (int l = 0; l < nl; ++l) {
+        inr_mbar_wait(&d_ready[j], (uint32_t)((q * nl + l) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float* b = s_bias + l * INR_TC_HID;
+        if (l < nl - 1) {                                        // bias + ReLU (model.py:47), next layer's A operand
+          for (int c0 = 0; c0 < INR_TC_HID; c0 += 16) {
+            uint32_t dreg[16], hi[16], lo[16];
+            inr_tmem_ld16(t_d + c0, dreg);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float v = fmaxf(__uint_as_float(dreg[u]) + b[c0 + u], 0.0f);
+              hi[u] = inr_tf32(v);
+              lo[u] = inr_tf32(v - __uint_as_float(hi[u]));
+            }
+            inr_tmem_st16(t_hi + c0, hi);
+            inr_tmem_st16(t_lo + c0, lo);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          inr_mbar_arrive(&a_ready[j]);
+        } else {                                                 // logits (:49), argmax (:135-137)
+          uint32_t dreg[16];
+          inr_tmem_ld16(t_d, dreg);
+          float o[MRT_INR_MAX_CLASSES];
+#pragma unroll
+          for (int u = 0; u < MRT_INR_MAX_CLASSES; ++u) o[u] = __uint_as_float(dreg[u]) + b[u];
+          int best = 0; float bv = o[0];
+#pragma unroll
+          for (int u = 1; u < MRT_INR_MAX_CLASSES; ++u) if (u < ncls && o[u] > bv) { bv = o[u]; best = u; }   // first maximum, like argmax
+          if (valid) {
+            labels[vox] = best;
+            if (logits != nullptr) {
+#pragma unroll
+              for (int u = 0; u < MRT_INR_MAX_CLASSES; ++u) if (u < ncls) logits[vox * ncls + u] = o[u];
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D is free for the next tile's first MMA
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
+static int inr_num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
+// -> cudaErrorNotSupported when the network does not fit the tensor-core kernel (the caller falls back)
+static cudaError_t launch_inr_tc(const InrNet& N, const float* mods, int X, int Y, int Z, const float* wts,
+                                 int32_t* labels, float* logits, cudaStream_t st) {
+  if (N.n_layers < 2) return cudaErrorNotSupported;
+  if (N.dims[0] > INR_TC_HID || N.dims[N.n_layers] > MRT_INR_MAX_CLASSES) return cudaErrorNotSupported;
+  for (int l = 1; l < N.n_layers; ++l) if (N.dims[l] > INR_TC_HID) return cudaErrorNotSupported;
+  const InrTcLayout L = inr_tc_layout(N);
+  if (L.total > 227 * 1024) return cudaErrorNotSupported;
+  cudaError_t e = cudaFuncSetAttribute(mrt_inr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (e != cudaSuccess) return e;
+  const size_t nvox = (size_t)X * Y * Z;
+  const long long ntiles = (long long)((nvox + 127) / 128);
+  long long grid = inr_num_sms();
+  if (grid > ntiles) grid = ntiles;
+  // one CTA per SM: a CTA allocates all 512 TMEM columns, so a second resident CTA would wait for them
+  // (the 113 KB+ of shared memory normally rules it out; ask for the rest to be sure)
+  int smem = L.total;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  e = cudaFuncSetAttribute(mrt_inr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  mrt_inr_tc_kernel<<<(int)grid, INR_TC_THREADS, smem, st>>>(N, L, mods, X, Y, Z, wts, labels, logits);
+  return cudaGetLastError();
+}
+
 template <int HID>
 static cudaError_t launch_inr(const InrNet& N, const float* mods, int X, int Y, int Z, const float* wts,
                               int32_t* labels, float* logits, cudaStream_t st) {
   const size_t nvox = (size_t)X * Y * Z;
-#ifndef MRT_INR_V1
   const size_t wfl = ((size_t)inr_smem_floats<HID>(N.n_layers) + 3) & ~(size_t)3;
   const size_t smem = (wfl + (size_t)HID * MRT_INR_BLOCK) * sizeof(float);
-  if (smem <= 227 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mrt_inr_kernel2<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    size_t grid = (nvox + MRT_INR_BLOCK - 1) / MRT_INR_BLOCK;
-    if (grid > 148 * 2) grid = 148 * 2;          // the weights are staged once per CTA
-    mrt_inr_kernel2<HID><<<(int)grid, MRT_INR_BLOCK, smem, st>>>(N, mods, X, Y, Z, wts, labels, logits);
-    return cudaGetLastError();
-  }
-#endif
-  // first version (activations in registers, fully unrolled): also the fall-back for very deep networks
-  const size_t smem1 = (size_t)inr_smem_floats<HID>(N.n_layers) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(mrt_inr_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;       // deeper than shared memory holds
+  cudaError_t e = cudaFuncSetAttribute(mrt_inr_kernel2<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  size_t grid = (nvox + 127) / 128;
-  if (grid > 148 * 8) grid = 148 * 8;            // persistent-ish: the weights are staged once per CTA
-  mrt_inr_kernel<HID><<<(int)grid, 128, smem1, st>>>(N, mods, X, Y, Z, wts, labels, logits);
+  size_t grid = (nvox + MRT_INR_BLOCK - 1) / MRT_INR_BLOCK;
+  if (grid > 148 * 2) grid = 148 * 2;          // the weights are staged once per CTA
+  mrt_inr_kernel2<HID><<<(int)grid, MRT_INR_BLOCK, smem, st>>>(N, mods, X, Y, Z, wts, labels, logits);
   return cudaGetLastError();
 }
 
 // layer_dims: n_layers + 1 widths; weights: per layer W[in][out] row-major followed by b[out]
+// impl: 0 = tensor cores when the network fits (else FFMA), 1 = fp32 FFMA, 2 = tensor cores or fail
 cudaError_t mrt_launch_inr(const float* mods, int M, int X, int Y, int Z, const float* weights, const int32_t* layer_dims,
-                           int n_layers, int fourier_freqs, int32_t* labels, float* logits, cudaStream_t st) {
+                           int n_layers, int fourier_freqs, int32_t* labels, float* logits, int impl, cudaStream_t st) {
   InrNet N = {};
   N.n_layers = n_layers; N.k = fourier_freqs; N.M = M;
   int off = 0, hid = 0;
@@ -270,6 +460,10 @@ cudaError_t mrt_launch_inr(const float* mods, int M, int X, int Y, int Z, const 
     if (l < n_layers - 1 && N.dims[l + 1] > hid) hid = N.dims[l + 1];
   }
   if (N.dims[0] > hid) hid = N.dims[0];
+  if (impl != 1) {
+    cudaError_t e = launch_inr_tc(N, mods, X, Y, Z, weights, labels, logits, st);
+    if (e != cudaErrorNotSupported || impl == 2) return e;
+  }
   if (hid <= 32) return launch_inr<32>(N, mods, X, Y, Z, weights, labels, logits, st);
   if (hid <= 64) return launch_inr<64>(N, mods, X, Y, Z, weights, labels, logits, st);
   return cudaErrorInvalidValue;

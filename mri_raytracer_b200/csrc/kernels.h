@@ -71,7 +71,7 @@ cudaError_t mrt_launch_u8_to_f32(const uint8_t* in, size_t n, float* out, cudaSt
 cudaError_t mrt_launch_normalize(const float* in, size_t n, float vmin, float rng, float* out, cudaStream_t st);
 
 cudaError_t mrt_launch_inr(const float* mods, int M, int X, int Y, int Z, const float* weights, const int32_t* layer_dims,
-                           int n_layers, int fourier_freqs, int32_t* labels, float* logits, cudaStream_t st);
+                           int n_layers, int fourier_freqs, int32_t* labels, float* logits, int impl, cudaStream_t st);
 
 struct MrtSlabParams;
 cudaError_t mrt_launch_slab(const MrtSlabParams& P, float tan_half, const uint8_t* vol, float* out,

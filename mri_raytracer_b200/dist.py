@@ -226,14 +226,15 @@ class PeerFramebuffer:
                                "gamma 1 and no label overlays")
         packed, Cn, Pe, bits = plan
         buf = self.batch & 1
-        api.view_spans(Pe, cams, Cn, bits, out=self.spans)            # all views: senders and owners need them
+        arr = api._camera_array(cams)                                 # one host-side packing for both launches
+        api.view_spans(Pe, arr, Cn, bits, out=self.spans)             # all views: senders and owners need them
         if self.partition == "tiles":
-            api.render_forward_batch_scatter(Pe, cams, packed, Cn, tf, bits, self.view_ptrs[buf], self.spans,
+            api.render_forward_batch_scatter(Pe, arr, packed, Cn, tf, bits, self.view_ptrs[buf], self.spans,
                                              store_outside=False, row_mod=R, row_rem=r)
         else:
             v0, v1 = view_partition(self.V, r, R)
             if v1 > v0:
-                api.render_forward_batch_scatter(Pe, cams[v0:v1], packed, Cn, tf, bits, self.view_ptrs[buf, v0:v1].contiguous(),
+                api.render_forward_batch_scatter(Pe, arr[v0:v1], packed, Cn, tf, bits, self.view_ptrs[buf, v0:v1].contiguous(),
                                                  self.spans[v0:v1], store_outside=False)
         own = self.owned_views()
         if len(own):

@@ -81,6 +81,11 @@ class RenderParams:
     shard: object = None        # ((lox,loy,loz), (hix,hiy,hiz)) voxel range of a sort-last sub-box, or None
     volDtype: int = 0           # 0 fp32 voxels, 1 fp16 single-channel (set by api.Volume)
 
+    def __setattr__(self, k, v):
+        object.__setattr__(self, k, v)
+        if k != "_struct":
+            self.__dict__.pop("_struct", None)       # the packed C struct is cached per instance
+
     def validate(self):
         W, H = self.imageSize
         if W <= 0 or H <= 0:
@@ -104,6 +109,9 @@ class RenderParams:
     def to_struct(self) -> MrtParams:
         """The C struct, packed in one go (filling 432 bytes field by field through ctypes costs
         ~45 us — as much as launching a kernel; ``struct.pack`` + ``from_buffer_copy`` takes ~8)."""
+        cached = self.__dict__.get("_struct")
+        if cached is not None:
+            return cached
         self.validate()
         f3 = lambda v: (float(v[0]), float(v[1]), float(v[2]))
         lut = np.asarray(self.lutColorAlpha, dtype=np.float32).reshape(32).tolist()
@@ -130,7 +138,9 @@ class RenderParams:
             0 if self.tMode == T_INDEXED else 1, int(bool(self.alphaMode)), int(bool(self.skipEmpty)),
             int(bool(self.tfMode)),
             1 if self.shard is not None else 0, *slo, *shi, int(self.volDtype))
-        return MrtParams.from_buffer_copy(raw)
+        st = MrtParams.from_buffer_copy(raw)
+        self.__dict__["_struct"] = st                # callers only read it (C.byref)
+        return st
 
 
 

@@ -14,9 +14,10 @@ from oracle import oracle_inr as I
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("impl", ["ffma", "auto"])
 @pytest.mark.parametrize("dims,M,k,hidden", [((23, 19, 17), 4, 4, [64, 64, 64, 64]), ((9, 8, 7), 2, 2, [32, 16]),
                                               ((12, 11, 10), 4, 0, [])])
-def test_inr_predict_matches_oracle(cuda, dims, M, k, hidden):
+def test_inr_predict_matches_oracle(cuda, dims, M, k, hidden, impl):
     X, Y, Z = dims
     rng = np.random.default_rng(7)
     params = I.init_mlp(rng, I.input_dim(M, k), hidden, 4)
@@ -25,7 +26,7 @@ def test_inr_predict_matches_oracle(cuda, dims, M, k, hidden):
     raw = torch.from_numpy(rng.gamma(2.0, 50.0, size=(M, Z, Y, X)).astype(np.float32))
     raw[:, :, :2] = 0.0                                  # background zeros, like skull-stripped MRI
     mods = mvol.zscore_modalities(raw)
-    labels, logits = api.inr_predict(mods.cuda(), params, k, return_logits=True)
+    labels, logits = api.inr_predict(mods.cuda(), params, k, return_logits=True, impl=impl)
     # oracle works in the reference's [M,H,W,D] = [M,X,Y,Z] order
     pred, want = I.predict_volume(params, mods.numpy().transpose(0, 3, 2, 1), k, chunk=1000, return_logits=True)
     got = logits.cpu().numpy().transpose(2, 1, 0, 3)     # [Z,Y,X,c] -> [X,Y,Z,c]
@@ -64,3 +65,27 @@ def test_inr_labels_feed_the_prediction_overlay(cuda):
     img = api.render(V, None, None, P).cpu()
     ref = O.render(vol, P, preds=preds.cpu().long())
     assert (img - ref).abs().max() <= 1e-4
+
+
+def test_tensor_core_inr_equals_the_fp32_kernel(cuda):
+    """The tcgen05 kernel (3-term TF32 split, fp32 accumulation in TMEM) against the fp32 FFMA kernel
+    on a volume of many 128-voxel tiles with a ragged tail: logits within 2e-5, labels identical
+    wherever the top-2 logits are more than 1e-3 apart; a network too deep for its shared-memory
+    weight image is refused by impl="tensor" and served by impl="auto"."""
+    X, Y, Z, M, k = 131, 37, 29, 4, 4
+    rng = np.random.default_rng(11)
+    params = I.init_mlp(rng, I.input_dim(M, k), [64, 64, 64, 64], 4)
+    for p in params:
+        p["b"] = rng.normal(scale=0.2, size=p["b"].shape).astype(np.float32)
+    raw = torch.from_numpy(rng.gamma(2.0, 50.0, size=(M, Z, Y, X)).astype(np.float32))
+    mods = mvol.zscore_modalities(raw).cuda()
+    lab_f, log_f = api.inr_predict(mods, params, k, return_logits=True, impl="ffma")
+    lab_t, log_t = api.inr_predict(mods, params, k, return_logits=True, impl="tensor")
+    assert float((log_t - log_f).abs().max()) <= 2e-5
+    top2 = torch.sort(log_f, dim=-1).values[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 1e-3
+    assert bool((lab_t == lab_f)[clear].all()) and float((lab_t == lab_f).float().mean()) > 0.9999
+    deep = I.init_mlp(rng, I.input_dim(M, k), [64] * 7, 4)
+    with pytest.raises(api._lib.MrtError):
+        api.inr_predict(mods, deep, k, impl="tensor")
+    assert api.inr_predict(mods, deep, k, impl="auto").shape == (Z, Y, X)
