@@ -47,8 +47,7 @@ __host__ __device__ inline int inr_smem_floats(int n_layers) {
 // input index can stay ROLLED (a rolled loop cannot index a register array): ~330 instructions of
 // loop body instead of ~5000 fully unrolled ones (instruction-cache friendly), ~100 registers instead
 // of 180, 16 warps per SM instead of 8 sharing one copy of the weights.
-#define MRT_INR_BLOCK 512
-template <int HID>
+template <int HID, int MRT_INR_BLOCK>
 __global__ void __launch_bounds__(MRT_INR_BLOCK)
 mrt_inr_kernel2(const __grid_constant__ InrNet N, const float* __restrict__ mods, int X, int Y, int Z,
                 const float* __restrict__ wts, int32_t* __restrict__ labels, float* __restrict__ logits) {
@@ -143,17 +142,25 @@ mrt_inr_kernel2(const __grid_constant__ InrNet N, const float* __restrict__ mods
 
 // ------------------------------------------------------------------------------------------------
 // Tensor-core version (tcgen05 / TMEM).  One CTA per SM, persistent over 128-voxel tiles:
-//   warps 0-3, 4-7 : two epilogue warpgroups, each owning one tile "slot" (TMEM lane = voxel row)
-//   warp 8         : one elected thread issues every tcgen05.mma
-// Per slot the TMEM holds D [64 columns] | A_hi [64] | A_lo [64].  A layer is
-//   D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (tf32 operands, fp32 accumulate in TMEM)
+//   warps 0-7, 8-15 : the epilogue warps of tile "slot" 0 and 1 (TMEM lane = voxel row); within a slot
+//                     warps 0-3 own activation columns 0-31, warps 4-7 columns 32-63
+//   warps 16, 17    : one elected thread per slot issues that slot's tcgen05.mma
+// Per slot the TMEM holds D [64 columns] | A_hi [64] | A_lo [64] | ones [8].  A layer is
+//   D = ones*B_bias + A_lo*W_hi + A_hi*W_lo + A_hi*W_hi      (tf32 operands, fp32 accumulate in TMEM)
 // with A read from TMEM and W (K-major, no swizzle: 8x16-byte core matrices, K chunks LBO apart,
-// 8-row groups SBO = 128 B apart) from shared memory.  While the tensor core works on one slot the
-// other slot's warpgroup runs its epilogue: tcgen05.ld D -> + bias, ReLU -> split into tf32 hi/lo ->
-// tcgen05.st A.  The two hand-offs per slot are mbarriers: a_ready (128 epilogue threads arrive) and
-// d_ready (tcgen05.commit).
-#define INR_TC_THREADS 288
-#define INR_TC_SLOT_COLS 192
+// 8-row groups SBO = 128 B apart) from shared memory; the bias rides on a constant A block (two
+// columns of ones against b_hi, b_lo), so the epilogue has nothing to add.  While the tensor core
+// works on one slot the other slot's warpgroup runs its epilogue: tcgen05.ld D -> ReLU -> split into
+// tf32 hi/lo -> tcgen05.st A (3 instructions per activation: FMNMX, LOP, FADD — cvt.rna.tf32 costs
+// five SASS instructions, so hi is the TRUNCATED value: the tensor core ignores the low 13 mantissa
+// bits anyway and lo = v - hi is exact).  The two hand-offs per slot are
+// mbarriers: a_ready (256 epilogue threads arrive) and d_ready (tcgen05.commit).
+// The layer-0 operand comes from per-axis tables built once per CTA in shared memory: for every x,
+// y and z index its normalised coordinate and the 2k Fourier features (model.py:11-18 depend on one
+// coordinate each), so a voxel costs three table rows and M loads instead of 6k sin/cos evaluations.
+#define INR_TC_EPI_WARPS 16        // 2 slots x 2 column halves x 4 warps (TMEM lanes 32*(warp%4)..+31)
+#define INR_TC_THREADS (32 * (INR_TC_EPI_WARPS + 2))
+#define INR_TC_SLOT_COLS 256
 #define INR_TC_HID 64
 #define INR_TC_NLAST 16
 
@@ -200,31 +207,52 @@ __device__ __forceinline__ void inr_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 __device__ __forceinline__ void inr_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(inr_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void inr_tmem_ld16(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void inr_tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void inr_tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void inr_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void inr_tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
                :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void inr_tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 
 // byte offsets of the shared-memory image
-struct InrTcLayout { int bias_off, w_off[MRT_INR_MAX_LAYERS], kp[MRT_INR_MAX_LAYERS], np[MRT_INR_MAX_LAYERS], total; };
-static inline InrTcLayout inr_tc_layout(const InrNet& N) {
+struct InrTcLayout {
+  int col_off;                                  // int32[64]: where column i of the layer-0 operand comes from
+  int tab_off, tab_row;                         // float[X+Y+Z][tab_row]: coordinate + 2k Fourier features per axis index
+  int b_off[MRT_INR_MAX_LAYERS];                // bias images: [np][8] K-major, k=0 -> b_hi, k=1 -> b_lo
+  int w_off[MRT_INR_MAX_LAYERS], kp[MRT_INR_MAX_LAYERS], np[MRT_INR_MAX_LAYERS];
+  int total;
+};
+static inline InrTcLayout inr_tc_layout(const InrNet& N, int X, int Y, int Z) {
   InrTcLayout L = {};
   int off = 64;                                               // [0,4) TMEM base, [16,48) four mbarriers
-  L.bias_off = off; off += N.n_layers * INR_TC_HID * (int)sizeof(float);
+  L.col_off = off; off += 64 * (int)sizeof(int32_t);
+  L.tab_row = 1 + 2 * N.k;
+  L.tab_off = off; off += (X + Y + Z) * L.tab_row * (int)sizeof(float);
   off = (off + 127) & ~127;
   for (int l = 0; l < N.n_layers; ++l) {
     L.kp[l] = (l == 0) ? ((N.dims[0] + 7) & ~7) : INR_TC_HID;
     L.np[l] = (l == N.n_layers - 1) ? INR_TC_NLAST : INR_TC_HID;
-    L.w_off[l] = off;
-    off += 2 * L.kp[l] * L.np[l] * (int)sizeof(float);        // hi image, then lo image
+    L.b_off[l] = off; off += L.np[l] * 8 * (int)sizeof(float);
+    L.w_off[l] = off; off += 2 * L.kp[l] * L.np[l] * (int)sizeof(float);      // hi image, then lo image
   }
   L.total = off;
   return L;
@@ -237,12 +265,13 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_raw);
   uint64_t* a_ready = reinterpret_cast<uint64_t*>(s_raw + 16);     // [2]
   uint64_t* d_ready = reinterpret_cast<uint64_t*>(s_raw + 32);     // [2]
-  float* s_bias = reinterpret_cast<float*>(s_raw + L.bias_off);    // [layer][64]
+  int32_t* s_col = reinterpret_cast<int32_t*>(s_raw + L.col_off);
+  float* s_tab = reinterpret_cast<float*>(s_raw + L.tab_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nl = N.n_layers;
 
-  // ---- one-time set-up: weights -> UMMA images (tf32 hi / lo), biases, barriers, TMEM
-  for (int i = threadIdx.x; i < (L.total - L.bias_off) / 4; i += blockDim.x) reinterpret_cast<float*>(s_raw + L.bias_off)[i] = 0.0f;
+  // ---- one-time set-up: weight / bias images (tf32 hi / lo), axis tables, barriers, TMEM
+  for (int i = threadIdx.x; i < (L.total - L.col_off) / 4; i += blockDim.x) reinterpret_cast<float*>(s_raw + L.col_off)[i] = 0.0f;
   __syncthreads();
   for (int l = 0; l < nl; ++l) {
     const int in = N.dims[l], out = N.dims[l + 1], np = L.np[l], kp = L.kp[l];
@@ -257,10 +286,37 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
       hi[e] = h;
       lo[e] = inr_tf32(w - __uint_as_float(h));
     }
-    for (int i = threadIdx.x; i < out; i += blockDim.x) s_bias[l * INR_TC_HID + i] = __ldg(src + in * out + i);
+    uint32_t* bi = reinterpret_cast<uint32_t*>(s_raw + L.b_off[l]);            // [chunk 0: k 0..3][np rows], [chunk 1]
+    for (int i = threadIdx.x; i < out; i += blockDim.x) {
+      const float bv = __ldg(src + in * out + i);
+      const uint32_t h = inr_tf32(bv);
+      bi[i * 4 + 0] = h;
+      bi[i * 4 + 1] = inr_tf32(bv - __uint_as_float(h));
+    }
+  }
+  // layer-0 column sources: 0 = zero padding; 1 + (axis << 8 | entry) = table; 0x10000 + m = modality m
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    int code = 0;
+    const int jf = i - 3;
+    if (i < 3) code = 1 + (i << 8);
+    else if (jf < 6 * N.k) { const int dd = jf / (2 * N.k), r = jf - dd * 2 * N.k; code = 1 + ((dd << 8) | (1 + r)); }
+    else if (jf - 6 * N.k < N.M) code = 0x10000 + (jf - 6 * N.k);
+    s_col[i] = code;
+  }
+  for (int i = threadIdx.x; i < X + Y + Z; i += blockDim.x) {
+    const int n = (i < X) ? X : ((i < X + Y) ? Y : Z), idx = (i < X) ? i : ((i < X + Y) ? i - X : i - X - Y);
+    const float c = (float)(((double)idx / (double)(n - 1)) * 2.0 - 1.0);       // model.py:128 (float64, then cast)
+    float* row = s_tab + (size_t)i * L.tab_row;
+    row[0] = c;
+    const float pi = 3.14159265358979323846f;
+    for (int f = 1; f <= N.k; ++f) {
+      const float ang = __fmul_rn(__fmul_rn(c, (float)f), pi);                  // :14 (coords * freqs) * pi, in fp32
+      row[f] = sinf(ang);                                                        // :15-17 sines, then cosines
+      row[N.k + f] = cosf(ang);
+    }
   }
   if (threadIdx.x == 0) {
-    inr_mbar_init(&a_ready[0], 128); inr_mbar_init(&a_ready[1], 128);
+    inr_mbar_init(&a_ready[0], 256); inr_mbar_init(&a_ready[1], 256);
     inr_mbar_init(&d_ready[0], 1);   inr_mbar_init(&d_ready[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -278,75 +334,82 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
   const int ntiles = (int)((nvox + 127) / 128);
   const int mine = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles blockIdx.x + i*gridDim.x
 
-  if (warp == 8) {
-    // ---------------------------------------------------------------- MMA issuer
+  if (warp >= INR_TC_EPI_WARPS) {
+    // ---------------------------------------------------------------- MMA issuers (one elected thread per slot)
     if (lane == 0) {
-      const int cnt0 = (mine + 1) >> 1;
-      for (int q = 0; q < cnt0; ++q) {
+      const int j = warp - INR_TC_EPI_WARPS;
+      const int cnt = (mine + 1 - j) >> 1;
+      const uint32_t d = tmem + (uint32_t)(j * INR_TC_SLOT_COLS), a_hi = d + 64, a_lo = d + 128, a_one = d + 192;
+      const uint32_t desc_hi = 8u | (1u << 14);                 // SBO = 128 B, descriptor version 1 (bits 32..47 of the descriptor)
+      uint32_t ph = 0;
+      for (int q = 0; q < cnt; ++q) {
         for (int l = 0; l < nl; ++l) {
-          for (int j = 0; j < 2; ++j) {
-            if (2 * q + j >= mine) continue;
-            inr_mbar_wait(&a_ready[j], (uint32_t)((q * nl + l) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kp = L.kp[l], np = L.np[l];
-            const uint32_t idesc = inr_idesc(np);
-            const uint32_t d = tmem + (uint32_t)(j * INR_TC_SLOT_COLS), a_hi = d + 64, a_lo = d + 128;
-            const uint32_t w_hi = inr_smem_u32(s_raw + L.w_off[l]), w_lo = w_hi + (uint32_t)(kp * np * 4);
-            const uint32_t lbo = (uint32_t)np * 16u, sbo = 128u;
-            for (int s8 = 0; s8 < kp / 8; ++s8) {              // one instruction = 8 tf32 of K = two 16-byte chunks
-              const uint64_t bh = inr_smem_desc(w_hi + (uint32_t)(2 * s8) * lbo, lbo, sbo);
-              const uint64_t bl = inr_smem_desc(w_lo + (uint32_t)(2 * s8) * lbo, lbo, sbo);
-              inr_mma_ts(d, a_lo + 8 * s8, bh, idesc, s8 > 0 ? 1u : 0u);
+          // everything that depends on the layer, before the wait: the issue loop below must be short —
+          // ONE thread feeds the tensor core, and every instruction it spends per MMA is tensor-core idle time
+          const int ksteps = L.kp[l] >> 3, np = L.np[l];
+          const uint32_t idesc = inr_idesc(np);
+          const uint32_t lbo16 = (uint32_t)np;                  // LBO = np * 16 bytes, in 16-byte units
+          const uint32_t w_hi = ((inr_smem_u32(s_raw + L.w_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
+          const uint32_t w_lo = w_hi + (uint32_t)((L.kp[l] * np * 4) >> 4);
+          const uint32_t b_b = ((inr_smem_u32(s_raw + L.b_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
+          const uint32_t step = 2u * lbo16;                     // one MMA consumes two 16-byte K chunks
+          inr_mbar_wait(&a_ready[j], ph);
+          ph ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          inr_mma_ts(d, a_one, ((uint64_t)desc_hi << 32) | b_b, idesc, 0u);                  // D = bias
+#pragma unroll
+          for (int s8 = 0; s8 < INR_TC_HID / 8; ++s8) {
+            if (s8 < ksteps) {
+              const uint64_t bh = ((uint64_t)desc_hi << 32) | (w_hi + (uint32_t)s8 * step);
+              const uint64_t bl = ((uint64_t)desc_hi << 32) | (w_lo + (uint32_t)s8 * step);
+              inr_mma_ts(d, a_lo + 8 * s8, bh, idesc, 1u);
               inr_mma_ts(d, a_hi + 8 * s8, bl, idesc, 1u);
               inr_mma_ts(d, a_hi + 8 * s8, bh, idesc, 1u);
             }
-            inr_commit(&d_ready[j]);                            // arrives when every MMA above has completed
           }
+          inr_commit(&d_ready[j]);                              // arrives when every MMA above has completed
         }
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue warpgroups
-    const int j = warp >> 2;                                     // slot
+    const int j = warp >> 3;                                     // slot
+    const int half = (warp >> 2) & 1;                            // which 32 activation columns this warp owns
     const int row = (warp & 3) * 32 + lane;                      // TMEM lane == voxel row of the tile
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * INR_TC_SLOT_COLS);
     const uint32_t t_d = lane_base, t_hi = lane_base + 64, t_lo = lane_base + 128;
     const int ncls = N.dims[nl];
     const int cnt = (mine + 1 - j) >> 1;
+    if (half == 0) {                                             // the constant A block of the bias MMA: ones in columns 0, 1
+      uint32_t one[8] = {0x3f800000u, 0x3f800000u, 0u, 0u, 0u, 0u, 0u, 0u};
+      inr_tmem_st8(lane_base + 192, one);
+    }
     for (int q = 0; q < cnt; ++q) {
       const int tile = (int)blockIdx.x + (2 * q + j) * (int)gridDim.x;
       const size_t vox = (size_t)tile * 128 + row;
       const bool valid = vox < nvox;
-      // ---- layer-0 operand: [coords | Fourier features | intensities] (model.py:11-23), zero padded to kp[0]
+      // ---- layer-0 operand: [coords | Fourier features | intensities] (model.py:11-23), zero padded to kp[0];
+      // the two halves of the slot take alternate 16-column chunks
       {
-        const size_t vv = valid ? vox : 0;
-        const int x = (int)(vv % X), y = (int)((vv / X) % Y), z = (int)(vv / ((size_t)X * Y));
-        float c[3];
-        c[0] = (float)(((double)x / (double)(X - 1)) * 2.0 - 1.0);      // model.py:128 (float64, then cast)
-        c[1] = (float)(((double)y / (double)(Y - 1)) * 2.0 - 1.0);
-        c[2] = (float)(((double)z / (double)(Z - 1)) * 2.0 - 1.0);
+        const unsigned vv = valid ? (unsigned)vox : 0u;         // (nvox < 2^32: checked by the launcher)
+        const unsigned yz = vv / (unsigned)X, x = vv - yz * (unsigned)X, z = yz / (unsigned)Y, y = yz - z * (unsigned)Y;
+        const float* rx = s_tab + (size_t)x * L.tab_row;
+        const float* ry = s_tab + (size_t)(X + y) * L.tab_row;
+        const float* rz = s_tab + (size_t)(X + Y + z) * L.tab_row;
         const int kp0 = L.kp[0];
-        for (int c0 = 0; c0 < kp0; c0 += 16) {
+        for (int c0 = 16 * half; c0 < kp0; c0 += 32) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int i = c0 + u, jf = i - 3;
+            const int code = s_col[c0 + u];                      // warp-uniform
             float v = 0.0f;
-            if (i < 3) {
-              v = (i == 0) ? c[0] : ((i == 1) ? c[1] : c[2]);
-            } else if (jf < 6 * N.k) {
-              const int dd = jf / (2 * N.k), r = jf - dd * 2 * N.k;
-              const int f = (r < N.k ? r : r - N.k) + 1;
-              const float cd = (dd == 0) ? c[0] : ((dd == 1) ? c[1] : c[2]);
-              // sin / cos of (coords * freqs) * pi (:14): evaluated as sinpi / cospi of the fp32 product
-              // (no large-argument reduction; differs from rounding the angle first by < 1e-6)
-              const float xf = __fmul_rn(cd, (float)f);
-              v = (r < N.k) ? sinpif(xf) : cospif(xf);
-            } else if (jf - 6 * N.k < N.M) {
-              v = valid ? __ldg(mods + (size_t)(jf - 6 * N.k) * nvox + vox) : 0.0f;
+            if (code >= 0x10000) v = valid ? __ldg(mods + (size_t)(code - 0x10000) * nvox + vox) : 0.0f;
+            else if (code > 0) {
+              const int ax = (code - 1) >> 8, e = (code - 1) & 255;
+              v = (ax == 0 ? rx : (ax == 1 ? ry : rz))[e];
             }
-            hi[u] = inr_tf32(v);
-            lo[u] = inr_tf32(v - __uint_as_float(hi[u]));
+            hi[u] = __float_as_uint(v) & 0xFFFFE000u;
+            lo[u] = __float_as_uint(v - __uint_as_float(hi[u]));
           }
           inr_tmem_st16(t_hi + c0, hi);
           inr_tmem_st16(t_lo + c0, lo);
@@ -356,31 +419,35 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       inr_mbar_arrive(&a_ready[j]);
       for (int l = 0; l < nl; ++l) {
-        inr_mbar_wait(&d_ready[j], (uint32_t)((q * nl + l) & 1));
+        inr_mbar_wait(&d_ready[j], (uint32_t)((q * nl + l) & 1));     // one d_ready phase per (tile, layer)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float* b = s_bias + l * INR_TC_HID;
-        if (l < nl - 1) {                                        // bias + ReLU (model.py:47), next layer's A operand
-          for (int c0 = 0; c0 < INR_TC_HID; c0 += 16) {
-            uint32_t dreg[16], hi[16], lo[16];
-            inr_tmem_ld16(t_d + c0, dreg);
+        if (l < nl - 1) {                                        // ReLU (model.py:47; the bias came with the MMA), next layer's A operand
+          uint32_t dreg[32];
+          const int cb = 32 * half;
+          inr_tmem_ld32_nowait(t_d + cb, dreg);
+          inr_tmem_ld_wait();
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              const float v = fmaxf(__uint_as_float(dreg[u]) + b[c0 + u], 0.0f);
-              hi[u] = inr_tf32(v);
-              lo[u] = inr_tf32(v - __uint_as_float(hi[u]));
+              const float v = fmaxf(__uint_as_float(dreg[c0 + u]), 0.0f);
+              hi[u] = __float_as_uint(v) & 0xFFFFE000u;          // tf32 by truncation: what the tensor core would read anyway
+              lo[u] = __float_as_uint(v - __uint_as_float(hi[u]));
             }
-            inr_tmem_st16(t_hi + c0, hi);
-            inr_tmem_st16(t_lo + c0, lo);
+            inr_tmem_st16(t_hi + cb + c0, hi);
+            inr_tmem_st16(t_lo + cb + c0, lo);
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           inr_mbar_arrive(&a_ready[j]);
-        } else {                                                 // logits (:49), argmax (:135-137)
+        } else if (half == 0) {                                  // logits (:49), argmax (:135-137)
           uint32_t dreg[16];
-          inr_tmem_ld16(t_d, dreg);
+          inr_tmem_ld16_nowait(t_d, dreg);
+          inr_tmem_ld_wait();
           float o[MRT_INR_MAX_CLASSES];
 #pragma unroll
-          for (int u = 0; u < MRT_INR_MAX_CLASSES; ++u) o[u] = __uint_as_float(dreg[u]) + b[u];
+          for (int u = 0; u < MRT_INR_MAX_CLASSES; ++u) o[u] = __uint_as_float(dreg[u]);
           int best = 0; float bv = o[0];
 #pragma unroll
           for (int u = 1; u < MRT_INR_MAX_CLASSES; ++u) if (u < ncls && o[u] > bv) { bv = o[u]; best = u; }   // first maximum, like argmax
@@ -407,43 +474,53 @@ static int inr_num_sms() {
   return n;
 }
 
-// -> cudaErrorNotSupported when the network does not fit the tensor-core kernel (the caller falls back)
+// -> cudaErrorNotSupported when the network or the volume does not fit the tensor-core kernel (the caller falls back)
 static cudaError_t launch_inr_tc(const InrNet& N, const float* mods, int X, int Y, int Z, const float* wts,
                                  int32_t* labels, float* logits, cudaStream_t st) {
   if (N.n_layers < 2) return cudaErrorNotSupported;
-  if (N.dims[0] > INR_TC_HID || N.dims[N.n_layers] > MRT_INR_MAX_CLASSES) return cudaErrorNotSupported;
+  if (N.dims[0] > INR_TC_HID || N.dims[N.n_layers] > MRT_INR_MAX_CLASSES || 1 + 2 * N.k > 255) return cudaErrorNotSupported;
   for (int l = 1; l < N.n_layers; ++l) if (N.dims[l] > INR_TC_HID) return cudaErrorNotSupported;
-  const InrTcLayout L = inr_tc_layout(N);
-  if (L.total > 227 * 1024) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(mrt_inr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-  if (e != cudaSuccess) return e;
   const size_t nvox = (size_t)X * Y * Z;
+  if (nvox >= (1ull << 32) - 128) return cudaErrorNotSupported;
+  if ((long long)(X + Y + Z) * (1 + 2 * N.k) * 4 > 200 * 1024) return cudaErrorNotSupported;
+  const InrTcLayout L = inr_tc_layout(N, X, Y, Z);
+  if (L.total > 227 * 1024) return cudaErrorNotSupported;     // weights + axis tables must fit shared memory
   const long long ntiles = (long long)((nvox + 127) / 128);
   long long grid = inr_num_sms();
   if (grid > ntiles) grid = ntiles;
   // one CTA per SM: a CTA allocates all 512 TMEM columns, so a second resident CTA would wait for them
-  // (the 113 KB+ of shared memory normally rules it out; ask for the rest to be sure)
+  // (ask for more than half of the shared memory to be sure)
   int smem = L.total;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  e = cudaFuncSetAttribute(mrt_inr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(mrt_inr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   mrt_inr_tc_kernel<<<(int)grid, INR_TC_THREADS, smem, st>>>(N, L, mods, X, Y, Z, wts, labels, logits);
   return cudaGetLastError();
 }
 
+template <int HID, int BLOCK>
+static cudaError_t launch_inr_b(const InrNet& N, const float* mods, int X, int Y, int Z, const float* wts,
+                                int32_t* labels, float* logits, cudaStream_t st) {
+  const size_t nvox = (size_t)X * Y * Z;
+  const size_t wfl = ((size_t)inr_smem_floats<HID>(N.n_layers) + 3) & ~(size_t)3;
+  const size_t smem = (wfl + (size_t)HID * BLOCK) * sizeof(float);
+  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  cudaError_t e = cudaFuncSetAttribute(mrt_inr_kernel2<HID, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  size_t grid = (nvox + BLOCK - 1) / BLOCK;
+  const size_t cap = 148 * (size_t)(1024 / BLOCK);          // the weights are staged once per CTA
+  if (grid > cap) grid = cap;
+  mrt_inr_kernel2<HID, BLOCK><<<(int)grid, BLOCK, smem, st>>>(N, mods, X, Y, Z, wts, labels, logits);
+  return cudaGetLastError();
+}
+// the widest block whose activation columns still fit next to the weights (deep networks take a narrower one)
 template <int HID>
 static cudaError_t launch_inr(const InrNet& N, const float* mods, int X, int Y, int Z, const float* wts,
                               int32_t* labels, float* logits, cudaStream_t st) {
-  const size_t nvox = (size_t)X * Y * Z;
-  const size_t wfl = ((size_t)inr_smem_floats<HID>(N.n_layers) + 3) & ~(size_t)3;
-  const size_t smem = (wfl + (size_t)HID * MRT_INR_BLOCK) * sizeof(float);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;       // deeper than shared memory holds
-  cudaError_t e = cudaFuncSetAttribute(mrt_inr_kernel2<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  size_t grid = (nvox + MRT_INR_BLOCK - 1) / MRT_INR_BLOCK;
-  if (grid > 148 * 2) grid = 148 * 2;          // the weights are staged once per CTA
-  mrt_inr_kernel2<HID><<<(int)grid, MRT_INR_BLOCK, smem, st>>>(N, mods, X, Y, Z, wts, labels, logits);
-  return cudaGetLastError();
+  cudaError_t e = launch_inr_b<HID, 512>(N, mods, X, Y, Z, wts, labels, logits, st);
+  if (e == cudaErrorNotSupported) e = launch_inr_b<HID, 256>(N, mods, X, Y, Z, wts, labels, logits, st);
+  if (e == cudaErrorNotSupported) e = launch_inr_b<HID, 128>(N, mods, X, Y, Z, wts, labels, logits, st);
+  return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
 }
 
 // layer_dims: n_layers + 1 widths; weights: per layer W[in][out] row-major followed by b[out]

@@ -70,8 +70,8 @@ def test_inr_labels_feed_the_prediction_overlay(cuda):
 def test_tensor_core_inr_equals_the_fp32_kernel(cuda):
     """The tcgen05 kernel (3-term TF32 split, fp32 accumulation in TMEM) against the fp32 FFMA kernel
     on a volume of many 128-voxel tiles with a ragged tail: logits within 2e-5, labels identical
-    wherever the top-2 logits are more than 1e-3 apart; a network too deep for its shared-memory
-    weight image is refused by impl="tensor" and served by impl="auto"."""
+    wherever the top-2 logits are more than 1e-3 apart; the deepest network the API takes still fits;
+    a single dense layer is refused by impl="tensor" and served by impl="auto"."""
     X, Y, Z, M, k = 131, 37, 29, 4, 4
     rng = np.random.default_rng(11)
     params = I.init_mlp(rng, I.input_dim(M, k), [64, 64, 64, 64], 4)
@@ -85,7 +85,11 @@ def test_tensor_core_inr_equals_the_fp32_kernel(cuda):
     top2 = torch.sort(log_f, dim=-1).values[..., -2:]
     clear = (top2[..., 1] - top2[..., 0]) > 1e-3
     assert bool((lab_t == lab_f)[clear].all()) and float((lab_t == lab_f).float().mean()) > 0.9999
-    deep = I.init_mlp(rng, I.input_dim(M, k), [64] * 7, 4)
+    deep = I.init_mlp(rng, I.input_dim(M, k), [64] * 6, 4)            # 7 layers: 190 KB of tf32 hi/lo weight images + tables still fit
+    ld, gd = api.inr_predict(mods, deep, k, return_logits=True, impl="tensor")
+    _, gdf = api.inr_predict(mods, deep, k, return_logits=True, impl="ffma")
+    assert float((gd - gdf).abs().max()) <= 2e-5
+    linear = I.init_mlp(rng, I.input_dim(M, k), [], 4)                # a single dense layer has no hidden activations to feed back
     with pytest.raises(api._lib.MrtError):
-        api.inr_predict(mods, deep, k, impl="tensor")
-    assert api.inr_predict(mods, deep, k, impl="auto").shape == (Z, Y, X)
+        api.inr_predict(mods, linear, k, impl="tensor")
+    assert api.inr_predict(mods, linear, k, impl="auto").shape == (Z, Y, X)
