@@ -21,6 +21,7 @@
 // The reference network is 31 -> 64 x 4 -> 4 (29 kFLOP per voxel, 0.26 TFLOP per BraTS case).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 #define MRT_INR_MAX_LAYERS 8
@@ -32,6 +33,7 @@ struct InrNet {
   int src_off[MRT_INR_MAX_LAYERS];            // offset of layer l's W (then b) in the caller's packed weights
   int k;                                      // Fourier frequencies
   int M;                                      // modalities
+  int dbg;                                    // dev only (MRT_INR_DBG): 1 = issue no MMA, 2 = skip the epilogue arithmetic, 4 = skip the layer-0 operand
 };
 
 // shared-memory image of the weights: hidden layers padded to [HID][HID] (+[HID] bias), the last
@@ -154,7 +156,8 @@ mrt_inr_kernel2(const __grid_constant__ InrNet N, const float* __restrict__ mods
 // tf32 hi/lo -> tcgen05.st A (3 instructions per activation: FMNMX, LOP, FADD — cvt.rna.tf32 costs
 // five SASS instructions, so hi is the TRUNCATED value: the tensor core ignores the low 13 mantissa
 // bits anyway and lo = v - hi is exact).  The two hand-offs per slot are
-// mbarriers: a_ready (256 epilogue threads arrive) and d_ready (tcgen05.commit).
+// mbarriers: a_ready (one arrival per epilogue warp, after its lanes' tcgen05.st have completed) and
+// d_ready (tcgen05.commit; one lane per warp waits and releases its warp).
 // The layer-0 operand comes from per-axis tables built once per CTA in shared memory: for every x,
 // y and z index its normalised coordinate and the 2k Fourier features (model.py:11-18 depend on one
 // coordinate each), so a voxel costs three table rows and M loads instead of 6k sin/cos evaluations.
@@ -181,6 +184,16 @@ __device__ __forceinline__ void inr_mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra INR_WAIT_%=;\n"
       "INR_DONE_%=:\n"
       "}\n" :: "r"(inr_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool inr_elect_one() {             // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t inr_tf32(float x) {      // round to nearest tf32 (low 13 mantissa bits zero)
   uint32_t u;
@@ -267,7 +280,7 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
   uint64_t* d_ready = reinterpret_cast<uint64_t*>(s_raw + 32);     // [2]
   int32_t* s_col = reinterpret_cast<int32_t*>(s_raw + L.col_off);
   float* s_tab = reinterpret_cast<float*>(s_raw + L.tab_off);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (warp-uniform for the compiler)
   const int nl = N.n_layers;
 
   // ---- one-time set-up: weight / bias images (tf32 hi / lo), axis tables, barriers, TMEM
@@ -316,7 +329,7 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
     }
   }
   if (threadIdx.x == 0) {
-    inr_mbar_init(&a_ready[0], 256); inr_mbar_init(&a_ready[1], 256);
+    inr_mbar_init(&a_ready[0], INR_TC_EPI_WARPS / 2); inr_mbar_init(&a_ready[1], INR_TC_EPI_WARPS / 2);   // one arrival per warp
     inr_mbar_init(&d_ready[0], 1);   inr_mbar_init(&d_ready[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -335,31 +348,33 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
   const int mine = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles blockIdx.x + i*gridDim.x
 
   if (warp >= INR_TC_EPI_WARPS) {
-    // ---------------------------------------------------------------- MMA issuers (one elected thread per slot)
-    if (lane == 0) {
-      const int j = warp - INR_TC_EPI_WARPS;
-      const int cnt = (mine + 1 - j) >> 1;
-      const uint32_t d = tmem + (uint32_t)(j * INR_TC_SLOT_COLS), a_hi = d + 64, a_lo = d + 128, a_one = d + 192;
-      const uint32_t desc_hi = 8u | (1u << 14);                 // SBO = 128 B, descriptor version 1 (bits 32..47 of the descriptor)
-      uint32_t ph = 0;
-      for (int q = 0; q < cnt; ++q) {
-        for (int l = 0; l < nl; ++l) {
-          // everything that depends on the layer, before the wait: the issue loop below must be short —
-          // ONE thread feeds the tensor core, and every instruction it spends per MMA is tensor-core idle time
-          const int ksteps = L.kp[l] >> 3, np = L.np[l];
-          const uint32_t idesc = inr_idesc(np);
-          const uint32_t lbo16 = (uint32_t)np;                  // LBO = np * 16 bytes, in 16-byte units
-          const uint32_t w_hi = ((inr_smem_u32(s_raw + L.w_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
-          const uint32_t w_lo = w_hi + (uint32_t)((L.kp[l] * np * 4) >> 4);
-          const uint32_t b_b = ((inr_smem_u32(s_raw + L.b_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
-          const uint32_t step = 2u * lbo16;                     // one MMA consumes two 16-byte K chunks
-          inr_mbar_wait(&a_ready[j], ph);
-          ph ^= 1u;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          inr_mma_ts(d, a_one, ((uint64_t)desc_hi << 32) | b_b, idesc, 0u);                  // D = bias
+    // ---------------------------------------------------------------- MMA issuers (one warp per slot)
+    // The WHOLE warp runs this loop with warp-uniform values and one elected lane issues: with a
+    // divergent `if (lane == 0)` around it the compiler cannot keep the descriptors in uniform
+    // registers and wraps every UTCHMMA in R2UR.BROADCAST + ELECT loops — 15 instructions and ~100
+    // cycles of one thread per MMA, which made the issue loop (not the tensor core) the bottleneck.
+    const int j = warp - INR_TC_EPI_WARPS;
+    const int cnt = (mine + 1 - j) >> 1;
+    const uint32_t d = tmem + (uint32_t)(j * INR_TC_SLOT_COLS), a_hi = d + 64, a_lo = d + 128, a_one = d + 192;
+    const uint32_t desc_hi = 8u | (1u << 14);                   // SBO = 128 B, descriptor version 1 (bits 32..47 of the descriptor)
+    uint32_t ph = 0;
+    for (int q = 0; q < cnt; ++q) {
+      for (int l = 0; l < nl; ++l) {
+        const int ksteps = L.kp[l] >> 3, np = L.np[l];
+        const uint32_t idesc = inr_idesc(np);
+        const uint32_t lbo16 = (uint32_t)np;                    // LBO = np * 16 bytes, in 16-byte units
+        const uint32_t w_hi = ((inr_smem_u32(s_raw + L.w_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
+        const uint32_t w_lo = w_hi + (uint32_t)((L.kp[l] * np * 4) >> 4);
+        const uint32_t b_b = ((inr_smem_u32(s_raw + L.b_off[l]) & 0x3FFFFu) >> 4) | (lbo16 << 16);
+        const uint32_t step = 2u * lbo16;                       // one MMA consumes two 16-byte K chunks
+        inr_mbar_wait(&a_ready[j], ph);
+        ph ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (inr_elect_one()) {
+          if (!(N.dbg & 1)) inr_mma_ts(d, a_one, ((uint64_t)desc_hi << 32) | b_b, idesc, 0u);                  // D = bias
 #pragma unroll
           for (int s8 = 0; s8 < INR_TC_HID / 8; ++s8) {
-            if (s8 < ksteps) {
+            if (s8 < ksteps && !(N.dbg & 1)) {
               const uint64_t bh = ((uint64_t)desc_hi << 32) | (w_hi + (uint32_t)s8 * step);
               const uint64_t bl = ((uint64_t)desc_hi << 32) | (w_lo + (uint32_t)s8 * step);
               inr_mma_ts(d, a_lo + 8 * s8, bh, idesc, 1u);
@@ -369,6 +384,7 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
           }
           inr_commit(&d_ready[j]);                              // arrives when every MMA above has completed
         }
+        __syncwarp();
       }
     }
   } else {
@@ -397,7 +413,7 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
         const float* ry = s_tab + (size_t)(X + y) * L.tab_row;
         const float* rz = s_tab + (size_t)(X + Y + z) * L.tab_row;
         const int kp0 = L.kp[0];
-        for (int c0 = 16 * half; c0 < kp0; c0 += 32) {
+        for (int c0 = 16 * half; c0 < kp0 && !(N.dbg & 4); c0 += 32) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
@@ -417,17 +433,21 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      inr_mbar_arrive(&a_ready[j]);
+      __syncwarp();
+      if (lane == 0) inr_mbar_arrive(&a_ready[j]);
       for (int l = 0; l < nl; ++l) {
-        inr_mbar_wait(&d_ready[j], (uint32_t)((q * nl + l) & 1));     // one d_ready phase per (tile, layer)
+        if (lane == 0) inr_mbar_wait(&d_ready[j], (uint32_t)((q * nl + l) & 1));     // one d_ready phase per (tile, layer)
+        __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (l < nl - 1) {                                        // ReLU (model.py:47; the bias came with the MMA), next layer's A operand
           uint32_t dreg[32];
           const int cb = 32 * half;
+          if (!(N.dbg & 2)) {
           inr_tmem_ld32_nowait(t_d + cb, dreg);
           inr_tmem_ld_wait();
+          }
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < 32 && !(N.dbg & 2); c0 += 16) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
@@ -440,7 +460,8 @@ mrt_inr_tc_kernel(const __grid_constant__ InrNet N, const __grid_constant__ InrT
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          inr_mbar_arrive(&a_ready[j]);
+          __syncwarp();
+          if (lane == 0) inr_mbar_arrive(&a_ready[j]);
         } else if (half == 0) {                                  // logits (:49), argmax (:135-137)
           uint32_t dreg[16];
           inr_tmem_ld16_nowait(t_d, dreg);
@@ -537,6 +558,7 @@ cudaError_t mrt_launch_inr(const float* mods, int M, int X, int Y, int Z, const 
     if (l < n_layers - 1 && N.dims[l + 1] > hid) hid = N.dims[l + 1];
   }
   if (N.dims[0] > hid) hid = N.dims[0];
+  { static const char* dbg = getenv("MRT_INR_DBG"); N.dbg = dbg ? atoi(dbg) : 0; }
   if (impl != 1) {
     cudaError_t e = launch_inr_tc(N, mods, X, Y, Z, weights, labels, logits, st);
     if (e != cudaErrorNotSupported || impl == 2) return e;
