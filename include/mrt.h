@@ -97,7 +97,7 @@ typedef struct MrtParams {
    * Output is the partial (r,g,b premultiplied WITHOUT background, a = T_local) for
    * mrt_composite_over.  Early termination acts on the shard-local transmittance. */
   uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3];
-  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16 single-channel (mrt_pack_volume_f16), forward only */
+  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16, 2: u8 single-channel (mrt_pack_volume_f16 / _u8), forward only */
 } MrtParams;
 
 /* One camera of a batch of views: the four camera rows of `struct Params`
@@ -174,6 +174,16 @@ void mrt_packed_layout_f16(int32_t X, int32_t Y, int32_t Z, int64_t* pitchY, int
 int mrt_pack_volume_f16(const void* planar_f16, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream);
 int mrt_unpack_volume_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, void* planar_f16, void* stream);
 int mrt_build_occupancy_f16(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream);
+
+/* u8 storage, 1 byte per voxel (the reference's single-volume app uploads bytes — one per u32 lane,
+ * scripts/volumeRendering/app.py:145-158 — and reads value = byte/255, volume_render.slang:33-38):
+ * planar [Z][Y][X] uint8 -> packed uint8 with 128 voxels per 128-byte line.  Render it with C = 1 and
+ * params->volDtype = 2 through mrt_render_forward(_batch): the same marcher (occupancy skipping,
+ * TF, ERT) gathering 8 B per sample; the image equals the fp32 path on byte/255 to fp32 rounding.
+ * mrt_build_occupancy_u8 returns min/max already divided by 255.  Forward only. */
+size_t mrt_packed_volume_bytes_u8(int32_t X, int32_t Y, int32_t Z);
+int mrt_pack_volume_u8(const uint8_t* planar_u8, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream);
+int mrt_build_occupancy_u8(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream);
 
 /* ------------------------------------------------ modality fold
  * The modality blend v = sum_c w_c s_c / wSum (brats_rt.slang:123-130) is linear and commutes

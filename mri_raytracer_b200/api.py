@@ -80,6 +80,23 @@ def pack_volume_f16(planar: torch.Tensor) -> torch.Tensor:
     return packed
 
 
+def pack_volume_u8(planar: torch.Tensor) -> torch.Tensor:
+    """[1,Z,Y,X] (or [Z,Y,X]) uint8 -> packed uint8 buffer (``mrt_pack_volume_u8``)."""
+    _need_cuda(planar, "volume", torch.uint8)
+    Z, Y, X = planar.shape[-3:]
+    nbytes = lib().mrt_packed_volume_bytes_u8(X, Y, Z)
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=planar.device)
+    check(lib().mrt_pack_volume_u8(planar.data_ptr(), X, Y, Z, packed.data_ptr(), _stream()), "pack_volume_u8")
+    return packed
+
+
+def build_occupancy_u8(packed: torch.Tensor, dims) -> torch.Tensor:
+    X, Y, Z = dims
+    mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=packed.device)
+    check(lib().mrt_build_occupancy_u8(packed.data_ptr(), X, Y, Z, mm.data_ptr(), _stream()), "build_occupancy_u8")
+    return mm
+
+
 def unpack_volume_f16(packed: torch.Tensor, dims) -> torch.Tensor:
     X, Y, Z = dims
     planar = torch.empty((1, Z, Y, X), dtype=torch.float16, device=packed.device)
@@ -436,12 +453,13 @@ class Volume:
         """``shard=((lox,loy,loz),(hix,hiy,hiz))`` + ``global_dims``: ``planar`` holds only voxels
         [lo, hi] (inclusive) of a larger volume — a sort-last sub-box (dist.render_sort_last)."""
         self.half = isinstance(planar, torch.Tensor) and planar.dtype == torch.float16
-        _need_cuda(planar, "volume", torch.float16 if self.half else torch.float32)
+        self.u8 = isinstance(planar, torch.Tensor) and planar.dtype == torch.uint8
+        _need_cuda(planar, "volume", torch.float16 if self.half else (torch.uint8 if self.u8 else torch.float32))
         if planar.dim() != 4 or not (1 <= planar.shape[0] <= 4):
             raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(planar.shape)}")
         self.C = int(planar.shape[0])
-        if self.half and (self.C != 1 or labels is not None or preds is not None):
-            raise ValueError("fp16 volumes are single-channel and take no label overlays")
+        if (self.half or self.u8) and (self.C != 1 or labels is not None or preds is not None):
+            raise ValueError("fp16 / u8 volumes are single-channel and take no label overlays")
         Z, Y, X = (int(v) for v in planar.shape[1:])
         self.dims = (X, Y, Z)
         self.shard = None
@@ -463,6 +481,9 @@ class Volume:
         elif self.half:
             self.packed = pack_volume_f16(planar)
             self.minmax = build_occupancy_f16(self.packed, self.dims) if occupancy else None
+        elif self.u8:
+            self.packed = pack_volume_u8(planar)
+            self.minmax = build_occupancy_u8(self.packed, self.dims) if occupancy else None
         else:
             self.packed = pack_volume(planar)
             self.minmax = build_occupancy(self.packed, self.C, self.dims) if occupancy else None
@@ -478,8 +499,8 @@ class Volume:
         """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
         if self.shard is not None:
             P = replace(P, shard=self.shard)
-        if self.half:
-            P = replace(P, volDtype=1)
+        if self.half or self.u8:
+            P = replace(P, volDtype=1 if self.half else 2)
         if not self.fold:
             return self.packed, self.C, P
         key = _fold_key(P, self.C)

@@ -108,6 +108,33 @@ int mrt_build_occupancy_f16(const void* packed, int32_t X, int32_t Y, int32_t Z,
   cudaError_t e = mrt_launch_build_occupancy_f16(packed, X, Y, Z, minmax, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_occupancy_f16");
 }
+// u8 storage (scripts/volumeRendering/app.py:145-158 uploads the volume as bytes; volume_render.slang:33-38
+// reads value = byte/255): 1 byte per voxel, 128 voxels per 128-byte line
+size_t mrt_packed_volume_bytes_u8(int32_t X, int32_t Y, int32_t Z) {
+  if (X < 1 || Y < 1 || Z < 1) return 0;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 1, X, Y, Z, &pY, &pZ);
+  return ((size_t)pZ * Z + 15) & ~(size_t)15;
+}
+static int check_dims_u8(const char* who, int X, int Y, int Z) {
+  MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
+  int64_t pY, pZ;
+  mrt_layout_e(1, 1, X, Y, Z, &pY, &pZ);
+  MRT_REQUIRE((uint64_t)pZ * Z < (1ull << 32), "%s: more than 2^32 voxels per shard (SURVEY Q14)", who);
+  return MRT_OK;
+}
+int mrt_pack_volume_u8(const uint8_t* planar_u8, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream) {
+  MRT_REQUIRE(planar_u8 && packed, "pack_volume_u8: null pointer");
+  if (int r = check_dims_u8("pack_volume_u8", X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_pack_u8(planar_u8, X, Y, Z, packed, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume_u8");
+}
+int mrt_build_occupancy_u8(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream) {
+  MRT_REQUIRE(packed && minmax, "build_occupancy_u8: null pointer");
+  if (int r = check_dims_u8("build_occupancy_u8", X, Y, Z)) return r;
+  cudaError_t e = mrt_launch_build_occupancy_u8(packed, X, Y, Z, minmax, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "build_occupancy_u8");
+}
 int mrt_unpack_volume_f32(const void* packed, int32_t C, int32_t X, int32_t Y, int32_t Z, float* planar, void* stream) {
   MRT_REQUIRE(planar && packed, "unpack_volume: null pointer");
   if (int r = check_dims("unpack_volume", C, X, Y, Z)) return r;
@@ -143,15 +170,15 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on sharded volumes");
     MRT_REQUIRE(M->tMode == 0, "sharded volumes need indexed stepping (tMode 0)");
   }
-  MRT_REQUIRE(M->volDtype <= 1, "volDtype %u unknown (0 fp32, 1 fp16)", M->volDtype);
-  K->half = M->volDtype == 1;
+  MRT_REQUIRE(M->volDtype <= 2, "volDtype %u unknown (0 fp32, 1 fp16, 2 u8)", M->volDtype);
+  K->half = (int)M->volDtype;
   if (K->half) {
-    MRT_REQUIRE(C == 1, "fp16 volumes are single-channel (C=%d)", C);
-    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on fp16 volumes");
+    MRT_REQUIRE(C == 1, "fp16 / u8 volumes are single-channel (C=%d)", C);
+    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on fp16 / u8 volumes");
   }
   {
     int64_t pY, pZ;
-    mrt_layout_e(mrt_packed_channels(C), K->half ? 2 : 4, ldim[0], ldim[1], ldim[2], &pY, &pZ);
+    mrt_layout_e(mrt_packed_channels(C), K->half == 1 ? 2 : (K->half == 2 ? 1 : 4), ldim[0], ldim[1], ldim[2], &pY, &pZ);
     MRT_REQUIRE((uint64_t)pZ * ldim[2] < (1ull << 32), "more than 2^32 voxels per shard (SURVEY Q14)");
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
     K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;
@@ -180,6 +207,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   K->lo = M->wl - M->ww * 0.5f;                            // :132
   K->inv_ww = 1.0f / M->ww;
   for (int c = 0; c < 4; ++c) K->wq[c] = K->wgt[c] * K->inv_wsum * K->inv_ww;
+  if (K->half == 2) K->wq[0] = K->wq[0] / 255.0f;         // u8 voxels are sampled as integers: value = byte/255 (volume_render.slang:38)
   K->wbias = -K->lo * K->inv_ww;
   K->neg_dt_log2e = -(float)((double)M->stepSize * 1.4426950408889634);
   K->ia = M->intensityAlpha;
@@ -496,7 +524,7 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
   MRT_REQUIRE(cams == nullptr || (nviews >= 1 && nviews <= MRT_MAX_VIEWS), "render_backward: nviews outside 1..%d", MRT_MAX_VIEWS);
   KParams K;
   if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
-  if (K.half) return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 volumes are forward-only");
+  if (K.half) return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 / u8 volumes are forward-only");
   if (K.shard) return fail(MRT_ERR_UNSUPPORTED, "render_backward: sharded volumes are forward-only");
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
   const bool seg = k_end != nullptr || warp_kmax != nullptr || ckpt != nullptr;

@@ -25,7 +25,7 @@
 
 // CKPT (training forward): additionally stores (C, T) of every ray before each slot c*CK.S, the
 // ray's end slot and every warp's longest end slot, for the segment-parallel backward (backward.cu).
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF, bool CKPT = false>
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF, bool CKPT = false>
 __global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 128 * MRT_FWD_MINB) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
@@ -306,7 +306,7 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
                                          const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                                          int32_t* out_counts, cudaStream_t st);
 static const CkptOut g_no_ckpt = {};
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC, bool HALF = false, bool CKPT = false>
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF = 0, bool CKPT = false>
 static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, const StripTargets& S, int nviews, const void* vol, const float* tf, const uint8_t* levels,
                               const int32_t* labels, const int32_t* preds, float* out_rgba, float* out_T,
                               int32_t* out_counts, cudaStream_t st, const CkptOut& CK = g_no_ckpt) {
@@ -325,10 +325,10 @@ template <int NCH>
 static cudaError_t dispatch_fwd_ckpt(const KParams& P, const CamBatch& B, int nviews, bool lab, bool skip, const void* vol,
                                      const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                      float* o, const CkptOut& CK, cudaStream_t st) {
-  if (lab) return skip ? launch_fwd<NCH, true, true, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
-                       : launch_fwd<NCH, true, false, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
-  return skip ? launch_fwd<NCH, false, true, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
-              : launch_fwd<NCH, false, false, false, false, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
+  if (lab) return skip ? launch_fwd<NCH, true, true, false, 0, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
+                       : launch_fwd<NCH, true, false, false, 0, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
+  return skip ? launch_fwd<NCH, false, true, false, 0, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK)
+              : launch_fwd<NCH, false, false, false, 0, true>(P, B, g_no_targets, nviews, vol, tf, levels, labels, preds, o, nullptr, nullptr, st, CK);
 }
 cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                     const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
@@ -505,12 +505,16 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && levels != nullptr && P.tMode == 0;
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
-  if (P.half) {            // fp16 voxels: single channel, no label overlays (c_api.cu checks)
+  if (P.half) {            // fp16 / u8 voxels: single channel, no label overlays (c_api.cu checks)
     if (packed_ch != 1 || lab) return cudaErrorInvalidValue;
-    if (skip) return gen ? launch_fwd<1, false, true, true, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
-                         : launch_fwd<1, false, true, false, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
-    return gen ? launch_fwd<1, false, false, true, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st)
-               : launch_fwd<1, false, false, false, true>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+#define MRT_NARROW(H) \
+    if (skip) return gen ? launch_fwd<1, false, true, true, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st) \
+                         : launch_fwd<1, false, true, false, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st); \
+    return gen ? launch_fwd<1, false, false, true, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st) \
+               : launch_fwd<1, false, false, false, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
+    if (P.half == 1) { MRT_NARROW(1) }
+    MRT_NARROW(2)
+#undef MRT_NARROW
   }
   switch (packed_ch) {
     case 1: return dispatch_fwd<1>(P, B, S, nviews, lab, skip, gen, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);

@@ -43,6 +43,8 @@ size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg);
 cudaError_t mrt_launch_pack_f16(const void* planar_f16, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar_f16, cudaStream_t st);
 cudaError_t mrt_launch_build_occupancy_f16(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
+cudaError_t mrt_launch_pack_u8(const void* planar_u8, int X, int Y, int Z, void* packed, cudaStream_t st);
+cudaError_t mrt_launch_build_occupancy_u8(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
 

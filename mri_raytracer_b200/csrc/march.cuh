@@ -40,7 +40,7 @@ struct KParams {
   int tile_begin, tile_end;
   // sort-last shard (all zero when off): owned cell range [slo, shi) in GLOBAL voxel indices;
   // the packed buffer / brick grid / pitches are those of the sub-volume starting at slo.
-  int half;               // voxels are fp16 (single channel): the sampler widens them to fp32 on load
+  int half;               // voxel storage: 0 fp32, 1 fp16, 2 u8 (narrow types: single channel, widened to fp32 on load)
   int shard;
   int slo[3], shi[3];
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
@@ -291,9 +291,12 @@ template <int NCH> struct Vox;
 template <> struct Vox<1> { typedef float T; };
 template <> struct Vox<2> { typedef float2 T; };
 template <> struct Vox<4> { typedef float4 T; };
-// element type the sampler loads: Vox<NCH> in fp32, __half for the single-channel fp16 layout
-template <int NCH, bool HALF> struct VoxT { typedef typename Vox<NCH>::T T; };
-template <> struct VoxT<1, true> { typedef __half T; };
+// element type the sampler loads (HALF = the storage type: 0 fp32 Vox<NCH>, 1 __half, 2 uint8_t; the
+// narrow types are single-channel).  u8 voxels are widened to their INTEGER value: the /255 of
+// volume_render.slang:38 is linear, so it is folded into KParams::wq on the host.
+template <int NCH, int HALF> struct VoxT { typedef typename Vox<NCH>::T T; };
+template <> struct VoxT<1, 1> { typedef __half T; };
+template <> struct VoxT<1, 2> { typedef uint8_t T; };
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
@@ -306,8 +309,10 @@ __device__ __forceinline__ float mrt_f32(float v) { return v; }
 __device__ __forceinline__ float2 mrt_f32(float2 v) { return v; }
 __device__ __forceinline__ float4 mrt_f32(float4 v) { return v; }
 __device__ __forceinline__ float mrt_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float mrt_f32(uint8_t v) { return (float)v; }
 __device__ __forceinline__ float mrt_scalar(float v) { return v; }
 __device__ __forceinline__ float mrt_scalar(__half v) { return __half2float(v); }
+__device__ __forceinline__ float mrt_scalar(uint8_t v) { return (float)v; }
 __device__ __forceinline__ float mrt_scalar(float2 v) { return v.x; }   // never used (NCH == 1 only)
 __device__ __forceinline__ float mrt_scalar(float4 v) { return v.x; }
 __device__ __forceinline__ float foldv(float2 s, const KParams& P) { return fmaf(s.y, P.wq[1], s.x * P.wq[0]); }
@@ -354,9 +359,9 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
 // The 8 corners of a cell, fetched (mrt_fetch) separately from their interpolation (mrt_interp) so
 // that a kernel can issue the loads of the NEXT slot before the dependent arithmetic of this one.
-template <int NCH, bool HALF> struct Corners { typename VoxT<NCH, HALF>::T v[8]; };
+template <int NCH, int HALF> struct Corners { typename VoxT<NCH, HALF>::T v[8]; };
 
-template <int NCH, bool HALF = false>
+template <int NCH, int HALF = 0>
 __device__ __forceinline__ Corners<NCH, HALF> mrt_fetch(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                                                        const Cell& c) {
   typedef typename VoxT<NCH, HALF>::T VT;
@@ -376,7 +381,7 @@ __device__ __forceinline__ Corners<NCH, HALF> mrt_fetch(const KParams& P, const 
   return k;
 }
 
-template <int NCH, bool HALF = false>
+template <int NCH, int HALF = 0>
 __device__ __forceinline__ float mrt_interp(const KParams& P, const Corners<NCH, HALF>& k, const Cell& c) {
   if (NCH == 1) {
     // one modality: the (linear) window scale is applied once, after the interpolation
@@ -396,7 +401,7 @@ __device__ __forceinline__ float mrt_interp(const KParams& P, const Corners<NCH,
 
 // d(raw)/d(index-space position) of the same interpolant (docs/DifferentiableRendering.md section 6,
 // :116-127: ds/dx = sum_n v_n dw_n/dx), per axis the lerp of the four corner differences.
-template <int NCH, bool HALF = false>
+template <int NCH, int HALF = 0>
 __device__ __forceinline__ void mrt_interp_grad(const KParams& P, const Corners<NCH, HALF>& k, const Cell& c,
                                                 float* gx, float* gy, float* gz) {
   float v[8];
@@ -410,7 +415,7 @@ __device__ __forceinline__ void mrt_interp_grad(const KParams& P, const Corners<
 
 // sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
-template <int NCH, bool HALF = false>
+template <int NCH, int HALF = 0>
 __device__ __forceinline__ float mrt_sample_raw(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                                                 const Cell& c) {
   return mrt_interp<NCH, HALF>(P, mrt_fetch<NCH, HALF>(P, vol, c), c);

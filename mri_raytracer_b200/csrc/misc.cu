@@ -44,17 +44,18 @@ mrt_unpack_kernel(const typename Vox<PC>::T* __restrict__ packed, int C, int X, 
   }
 }
 
-// fp16 single-channel volume: planar [Z][Y][X] half <-> packed half with the skewed pitches of
-// mrt_layout_e(1, 2, ...) (64 voxels per 128-byte line)
+// narrow single-channel volumes (fp16, u8): planar [Z][Y][X] <-> packed with the skewed pitches of
+// mrt_layout_e(1, sizeof(T), ...) (64 / 128 voxels per 128-byte line)
+template <typename T>
 __global__ void __launch_bounds__(256)
-mrt_pack_f16_kernel(const __half* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
-                    __half* __restrict__ packed, bool inverse) {
+mrt_pack_narrow_kernel(const T* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                       T* __restrict__ packed, bool inverse) {
   const int rows = Y * Z;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int y = row % Y, z = row / Y;
     const size_t a = (size_t)row * X, b = (size_t)y * pitchY + (size_t)z * pitchZ;
     for (int x = threadIdx.x; x < X; x += blockDim.x) {
-      if (inverse) const_cast<__half*>(planar)[a + x] = packed[b + x];
+      if (inverse) const_cast<T*>(planar)[a + x] = packed[b + x];
       else packed[b + x] = planar[a + x];
     }
   }
@@ -81,15 +82,22 @@ cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, voi
 cudaError_t mrt_launch_pack_f16(const void* planar, int X, int Y, int Z, void* packed, cudaStream_t st) {
   int64_t pY, pZ;
   mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
-  mrt_pack_f16_kernel<<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
-                                                                         (__half*)packed, false);
+  mrt_pack_narrow_kernel<__half><<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
+                                                                                    (__half*)packed, false);
+  return cudaGetLastError();
+}
+cudaError_t mrt_launch_pack_u8(const void* planar, int X, int Y, int Z, void* packed, cudaStream_t st) {
+  int64_t pY, pZ;
+  mrt_layout_e(1, 1, X, Y, Z, &pY, &pZ);
+  mrt_pack_narrow_kernel<uint8_t><<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const uint8_t*)planar, X, Y, Z, pY, pZ,
+                                                                                     (uint8_t*)packed, false);
   return cudaGetLastError();
 }
 cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar, cudaStream_t st) {
   int64_t pY, pZ;
   mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
-  mrt_pack_f16_kernel<<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
-                                                                         (__half*)const_cast<void*>(packed), true);
+  mrt_pack_narrow_kernel<__half><<<grid_for((size_t)Y * Z * 256, 256), 256, 0, st>>>((const __half*)planar, X, Y, Z, pY, pZ,
+                                                                                    (__half*)const_cast<void*>(packed), true);
   return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@
 // brick b covers voxel indices [8b, 8b+8] per axis (clipped): the union of the 2x2x2
 // footprints of all samples with base index in [8b, 8b+7], and of the nearest-label
 // footprint round(p) of the same samples.
-template <int NCH, bool HALF = false>
+template <int NCH, int HALF = 0>
 __global__ void __launch_bounds__(128)
 mrt_build_minmax_kernel(const typename VoxT<NCH, HALF>::T* __restrict__ vol, int X, int Y, int Z,
                         size_t pitchY, size_t pitchZ, int nbx, int nby, float2* __restrict__ minmax) {
@@ -29,7 +29,8 @@ mrt_build_minmax_kernel(const typename VoxT<NCH, HALF>::T* __restrict__ vol, int
   for (int i = threadIdx.x; i < nvox; i += blockDim.x) {
     const int lx = i % ex, ly = (i / ex) % ey, lz = i / (ex * ey);
     const size_t idx = (size_t)(x0 + lx) + pitchY * (size_t)(y0 + ly) + pitchZ * (size_t)(z0 + lz);
-    const auto v = mrt_f32(__ldg(vol + idx));
+    auto v = mrt_f32(__ldg(vol + idx));
+    if (HALF == 2) *reinterpret_cast<float*>(&v) = __fdiv_rn(*reinterpret_cast<float*>(&v), 255.0f);   // u8: the value is v/255 (volume_render.slang:38)
     const float* f = reinterpret_cast<const float*>(&v);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { mn[c] = fminf(mn[c], f[c]); mx[c] = fmaxf(mx[c], f[c]); }
@@ -76,8 +77,16 @@ cudaError_t mrt_launch_build_occupancy_f16(const void* packed, int X, int Y, int
   const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
   int64_t pY, pZ;
   mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);
-  mrt_build_minmax_kernel<1, true><<<nbx * nby * nbz, 128, 0, st>>>((const __half*)packed, X, Y, Z, pY, pZ, nbx, nby,
-                                                                   (float2*)minmax);
+  mrt_build_minmax_kernel<1, 1><<<nbx * nby * nbz, 128, 0, st>>>((const __half*)packed, X, Y, Z, pY, pZ, nbx, nby,
+                                                                (float2*)minmax);
+  return cudaGetLastError();
+}
+cudaError_t mrt_launch_build_occupancy_u8(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st) {
+  const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 1, X, Y, Z, &pY, &pZ);
+  mrt_build_minmax_kernel<1, 2><<<nbx * nby * nbz, 128, 0, st>>>((const uint8_t*)packed, X, Y, Z, pY, pZ, nbx, nby,
+                                                                (float2*)minmax);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,25 @@ def cfg1():
                 gsamples_per_s=c[1] / ms / 1e6, parity_max_abs=mx, parity_pixels_over_1e4=nbad, parity_pixels=npx)
 
 
+def cfg1_u8():
+    """cfg1's shape with the volume stored as bytes (8 B gathered per sample instead of 32)."""
+    dims = (240, 240, 155)
+    vol = make_brats_like(1, dims, seed=0)
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 512, 512, ortho=True), tfMode=1)
+    u8 = (vol * 255.0).round().clamp(0, 255).to(torch.uint8)
+    V8 = api.Volume(u8.cuda())
+    V32 = api.Volume((u8.float() / 255.0).cuda())
+    tfd = tf.cuda()
+    _, _, counts = api.render_aux(V8, None, tfd, P)
+    c = counts.sum(dim=(0, 1)).tolist()
+    ms8 = timeit(lambda: api.render(V8, None, tfd, P), reps=10)
+    ms32 = timeit(lambda: api.render(V32, None, tfd, P), reps=10)
+    diff = float((api.render(V8, None, tfd, P) - api.render(V32, None, tfd, P)).abs().max())
+    return dict(cfg="cfg1_u8", ms_per_frame_u8=ms8, ms_per_frame_fp32_same_values=ms32, samples_taken=c[1], samples_evaluated=c[2],
+                gsamples_per_s_u8=c[1] / ms8 / 1e6, max_abs_u8_vs_fp32=diff)
+
+
 def cfg3():
     dims = (256, 256, 256)
     vol = make_brats_like(1, dims, seed=4)
@@ -243,6 +262,6 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4"]
     for w in which:
         t0 = time.time()
-        r = dict(cfg1=cfg1, cfg3=cfg3, cfg4=cfg4, inr=inr)[w]()
+        r = dict(cfg1=cfg1, cfg1_u8=cfg1_u8, cfg3=cfg3, cfg4=cfg4, inr=inr)[w]()
         r["wall_s"] = time.time() - t0
         print(json.dumps(r), flush=True)
