@@ -53,8 +53,8 @@ def test_cfg2_four_modalities_perspective_1024(cuda):
     P = replace(framed_params(dims, 1024, 1024), tfMode=1)
     V = api.Volume(vol.cuda())
     img, T, counts = api.render_aux(V, None, tf.cuda(), P)
-    st = check_subset(img, counts, vol, P, tf, stride=8)
-    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    st = check_subset(img, counts, vol, P, tf, stride=4)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 16, st
     _properties(V, P, tf.cuda(), img)
     # per-sample blending from the interleaved layout (fold=False) agrees with the folded volume
     Vn = api.Volume(vol.cuda(), fold=False)
@@ -67,6 +67,13 @@ def test_cfg2_four_modalities_perspective_1024(cuda):
     assert torch.equal(batch[0], img)
     for v in (3, 7):
         assert torch.equal(batch[v], api.render(V, cams[v], tf.cuda(), P))
+    # the oracle on two more of the bench's eight views (65 536 rays each)
+    for v in (3, 6):
+        Pv = P.with_camera(cams[v])
+        imv, _, cv = api.render_aux(V, cams[v], tf.cuda(), P)
+        assert torch.equal(imv, batch[v])
+        st = check_subset(imv, cv, vol, Pv, tf, stride=4)
+        assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 16, (v, st)
 
 
 def test_cfg3_gradients_256_cubed_on_a_ray_subset(cuda):
@@ -75,7 +82,8 @@ def test_cfg3_gradients_256_cubed_on_a_ray_subset(cuda):
     through directional derivatives: <dL/dvolume, delta> against a float64 central difference of the
     oracle's loss along smooth fields delta (the oracle's dense autograd over 256^3 takes minutes;
     full dL/dvolume-vs-autograd parity is in test_gpu_backward.py on small volumes).  The finite
-    difference of a piecewise-linear function carries its own O(eps) error: tolerance 2e-3."""
+    difference of a piecewise-linear function carries its own O(eps) error — the step is 1e-4 in
+    float64, which keeps it below north_star's 1e-3."""
     import torch.nn.functional as F
     dims = (256, 256, 256)
     vol = make_brats_like(1, dims, seed=4)
@@ -100,7 +108,7 @@ def test_cfg3_gradients_256_cubed_on_a_ray_subset(cuda):
     img = api.render(gv, None, tf.cuda(), P2)
     (img[py.cuda(), px.cuda()] * wgt.cuda()).sum().backward()
     grad = gv.grad.cpu().double()
-    eps = 1e-3
+    eps = 1e-4
     for seed in (1, 2):
         gd = torch.Generator().manual_seed(seed)
         d = F.interpolate(torch.rand(1, 1, 6, 6, 6, generator=gd) - 0.5, size=(256, 256, 256), mode="trilinear",
@@ -109,7 +117,7 @@ def test_cfg3_gradients_256_cubed_on_a_ray_subset(cuda):
         lm = (O.render((vol - eps * d).double(), P2, tf=tf.double(), pixels=(px, py), dtype=torch.float64) * wgt.double()).sum()
         fd = float((lp - lm) / (2 * eps))
         an = float((grad * d.double()).sum())
-        assert abs(an - fd) <= 2e-3 * abs(fd), (seed, an, fd)
+        assert abs(an - fd) <= 1e-3 * abs(fd), (seed, an, fd)
 
 
 def test_cfg4_orbit_view_2048_over_512_cubed(cuda):
@@ -119,7 +127,27 @@ def test_cfg4_orbit_view_2048_over_512_cubed(cuda):
     P = replace(framed_params(dims, 2048, 2048, theta_deg=0.0), tfMode=1)
     V = api.Volume(vol)
     img, T, counts = api.render_aux(V, None, tf.cuda(), P)
-    st = check_subset(img, counts, vol.cpu(), P, tf, stride=32)
-    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    st = check_subset(img, counts, vol.cpu(), P, tf, stride=16)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 16, st
     assert int(counts[..., 0].max()) > 1024, "config 4 must exceed the reference's [MaxIters(1024)] hint"
     _properties(V, P, tf.cuda(), img)
+
+
+def test_cfg5_shaped_fp16_sort_last_2x2x2_over_512_cubed(cuda):
+    """BASELINE config 5 in shape (fp16 storage, 2x2x2 brick shards, sort-last compositing) at 512^3 and
+    2048^2 on ONE GPU (the eight shards rendered one after the other; the 8-GPU exchange itself is
+    checked by tools/dist_check.py / test_gpu_multi.py): the composited frame equals the unsharded
+    fp16 render to the early-termination threshold, and the unsharded render matches the oracle on
+    the fp16-rounded volume (per-ray counts bit-exact, max-abs 1e-4) on a strided subset."""
+    from mri_raytracer_b200 import dist as mdist
+    dims = (512, 512, 512)
+    vol16 = make_brats_like(1, dims, seed=6, device="cuda").half()
+    tf = ramp_tf(256)
+    P = replace(framed_params(dims, 2048, 2048, theta_deg=35.0, phi_deg=70.0), tfMode=1, ertThreshold=1e-6)
+    V = api.Volume(vol16)
+    img, T, counts = api.render_aux(V, None, tf.cuda(), P)
+    st = check_subset(img, counts, vol16.float().cpu(), P, tf, stride=32)
+    assert st["max_abs"] <= 1e-4 and st["n_flip"] <= 8, st
+    sl = mdist.render_sort_last_emulated(vol16, None, tf.cuda(), P, (2, 2, 2))
+    assert float((sl - img).abs().max()) <= 2e-5
+    assert torch.equal(api.render(V, None, tf.cuda(), replace(P, skipEmpty=0)), img)
