@@ -359,6 +359,24 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
                         void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray, uint64_t* stats,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* ------------------------------------------------ differentiable adaptive sampling
+ * docs/DifferentiableRendering.md section 7 (:131-148; maths only, no reference code): per ray a
+ * coarse pass of n_coarse uniform samples gives importance weights w_k = sigma_k + eps_w, their
+ * piecewise-linear CDF is inverted at the fixed quantiles (j+1/2)/n_fine, and the n_fine samples
+ * placed there are composited front to back with alpha_j = 1 - exp(-sigma_j * Delta_j), Delta_j the
+ * length of sample j's quantile interval.  The backward includes the dependence of the sample
+ * times and interval lengths on the weights (the implicit differentiation of :142-146).
+ * fp32 unsharded volumes, no overlays, no skipping (the sampler is the acceleration).
+ *   n_coarse <= 64;  dL_dvol / dL_dtf ACCUMULATED into (caller zeroes), layouts as mrt_render_backward;
+ *   scratch: mrt_adaptive_scratch_bytes(tfN) bytes when dL_dtf != NULL. */
+size_t mrt_adaptive_scratch_bytes(int32_t tfN);
+int mrt_render_adaptive_forward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                int32_t n_coarse, int32_t n_fine, float eps_w, float* out_rgba,
+                                int32_t tile_begin, int32_t tile_end, void* stream);
+int mrt_render_adaptive_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                 int32_t n_coarse, int32_t n_fine, float eps_w, const float* out_rgba, const float* dL_dout,
+                                 void* dL_dvol, float* dL_dtf, void* scratch, int32_t tile_begin, int32_t tile_end, void* stream);
+
 /* ------------------------------------------------ slab renderer (u8 volume)
  * volume_cs, scripts/volumeRendering/volume_render.slang:104-148.
  * vol_u8: uint8 [Z][Y][X], one byte per voxel (the reference stores one voxel per u32

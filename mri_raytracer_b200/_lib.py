@@ -117,6 +117,9 @@ PROTOTYPES = {
     "mrt_backward_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mrt_adaptive_scratch_bytes": (_sz, [_i32]),
+    "mrt_render_adaptive_forward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _f, _vp, _i32, _i32, _vp]),
+    "mrt_render_adaptive_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _f, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_slab_u8": (C.c_int, [_SP, _vp, _vp, _i32, _i32, _vp]),
     "mrt_decode_bc4": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_u8_to_f32": (C.c_int, [_vp, _sz, _vp, _vp]),

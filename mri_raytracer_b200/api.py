@@ -734,6 +734,63 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
     return _RenderFn.apply(volume, tf, P, labels, preds, fold, tile_range)
 
 
+class _AdaptiveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planar, tf, P: RenderParams, K, J, eps_w):
+        Cn = planar.shape[0]
+        packed = pack_volume(planar.detach())
+        W, H = P.imageSize
+        out = torch.empty((H, W, 4), dtype=torch.float32, device=planar.device)
+        s = P.to_struct()
+        check(lib().mrt_render_adaptive_forward(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                                int(K), int(J), float(eps_w), out.data_ptr(), 0, _tiles.tile_count(W, H), _stream()),
+              "render_adaptive_forward")
+        ctx.P, ctx.Cn, ctx.K, ctx.J, ctx.eps_w, ctx.has_tf = P, Cn, int(K), int(J), float(eps_w), tf is not None
+        ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=planar.device), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        packed, tf, out = ctx.saved_tensors
+        tf = tf if ctx.has_tf else None
+        want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
+        P = ctx.P
+        W, H = P.imageSize
+        dvol = torch.zeros_like(packed) if want_vol else None
+        ntf = tf.shape[0] if tf is not None else 2
+        dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_tf else None
+        scratch = torch.empty((lib().mrt_adaptive_scratch_bytes(ntf) // 4,), dtype=torch.float32, device=packed.device) if want_tf else None
+        s = P.to_struct()
+        check(lib().mrt_render_adaptive_backward(C.byref(s), packed.data_ptr(), ctx.Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                                 ctx.K, ctx.J, ctx.eps_w, out.data_ptr(), g.contiguous().data_ptr(), _ptr(dvol),
+                                                 _ptr(dtf), _ptr(scratch), 0, _tiles.tile_count(W, H), _stream()),
+              "render_adaptive_backward")
+        gvol = unpack_volume(dvol, ctx.Cn, P.dims) if want_vol else None
+        return gvol, dtf, None, None, None, None
+
+
+def render_adaptive(volume: torch.Tensor, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams,
+                    n_coarse: int = 16, n_fine: int = 64, eps_w: float = 1e-3) -> torch.Tensor:
+    """Differentiable adaptive sampling (docs/DifferentiableRendering.md section 7, :131-148): a coarse
+    pass of ``n_coarse`` uniform samples per ray -> piecewise-linear CDF of the extinction (+ ``eps_w``)
+    -> ``n_fine`` samples at the fixed quantiles ``(j+1/2)/n_fine`` of the inverse CDF, composited
+    front to back with the length of each quantile interval.  ``volume``: ``[C,Z,Y,X]`` CUDA fp32
+    tensor; differentiable w.r.t. it and ``tf`` (the gradient includes the motion of the samples with
+    the weights).  -> float32 ``[H,W,4]``."""
+    P = params if camera is None else params.with_camera(camera)
+    _need_cuda(volume, "volume", torch.float32)
+    if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
+        raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(volume.shape)}")
+    Z, Y, X = (int(v) for v in volume.shape[1:])
+    if tuple(P.dims) != (X, Y, Z):
+        raise ValueError(f"params.dims {P.dims} != volume dims {(X, Y, Z)}")
+    if tf is not None:
+        _need_cuda(tf, "tf", torch.float32)
+    P = replace(P, tfMode=1 if tf is not None else 0)
+    P.validate()
+    return _AdaptiveFn.apply(volume, tf, P, n_coarse, n_fine, eps_w)
+
+
 def render_views(volume: Union[torch.Tensor, Volume], cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,
                  out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None,
                  fold: bool = True) -> torch.Tensor:

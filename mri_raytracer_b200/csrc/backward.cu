@@ -376,6 +376,11 @@ __global__ void mrt_dtf_reduce_kernel(const float4* __restrict__ priv, int ncopi
   dtf[j] = d;
 }
 
+cudaError_t mrt_launch_dtf_reduce(const void* priv, int ncopies, int ntf, float* dtf, cudaStream_t st) {
+  mrt_dtf_reduce_kernel<<<(ntf + 127) / 128, 128, 0, st>>>((const float4*)priv, ncopies, ntf, (float4*)dtf);
+  return cudaGetLastError();
+}
+
 // scratch layout: [0,256) counters (ntasks, next) | privatised dL/dtf | task list
 static inline size_t bwd_priv_bytes(int ntf) { return (size_t)MRT_DTF_COPIES * ntf * 2 * sizeof(float4); }
 size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg) {

@@ -548,6 +548,44 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
 }
 
+// ---------------------------------------------------------------- adaptive (inverse-CDF) sampling
+size_t mrt_adaptive_scratch_bytes(int32_t tfN) { return mrt_adaptive_scratch(tfN < 2 ? 2 : tfN); }
+
+static int adaptive_common(const char* who, const MrtParams* params, int32_t C, int32_t tfN, int32_t K, int32_t J, float eps_w,
+                           int32_t tile_begin, int32_t tile_end, KParams* Kp) {
+  if (int r = derive(params, C, tfN, false, tile_begin, tile_end, Kp)) return r;
+  MRT_REQUIRE(K >= 1 && K <= 64, "%s: n_coarse=%d outside 1..64", who, K);
+  MRT_REQUIRE(J >= 1 && J <= 65536, "%s: n_fine=%d outside 1..65536", who, J);
+  MRT_REQUIRE(eps_w > 0.0f, "%s: eps_w must be > 0 (the importance needs a floor for the CDF to be invertible)", who);
+  if (Kp->half || Kp->shard || Kp->showSeg || Kp->showPred || Kp->gamma != 1.0f)
+    return fail(MRT_ERR_UNSUPPORTED, "%s: fp32 unsharded volumes without overlays, gamma 1", who);
+  return MRT_OK;
+}
+int mrt_render_adaptive_forward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                int32_t n_coarse, int32_t n_fine, float eps_w, float* out_rgba,
+                                int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba, "render_adaptive_forward: null pointer");
+  KParams K;
+  if (int r = adaptive_common("render_adaptive_forward", params, C, tfN, n_coarse, n_fine, eps_w, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_adaptive_forward: tfMode=1 needs tf");
+  cudaError_t e = mrt_launch_adaptive(K, n_coarse, n_fine, eps_w, mrt_packed_channels(C), packed, tf, out_rgba, nullptr, nullptr,
+                                      nullptr, nullptr, false, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_adaptive_forward");
+}
+int mrt_render_adaptive_backward(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                 int32_t n_coarse, int32_t n_fine, float eps_w, const float* out_rgba, const float* dL_dout,
+                                 void* dL_dvol, float* dL_dtf, void* scratch, int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && dL_dout, "render_adaptive_backward: null pointer");
+  MRT_REQUIRE(dL_dvol || dL_dtf, "render_adaptive_backward: nothing to differentiate");
+  MRT_REQUIRE(!dL_dtf || scratch, "render_adaptive_backward: dL_dtf needs the scratch buffer");
+  KParams K;
+  if (int r = adaptive_common("render_adaptive_backward", params, C, tfN, n_coarse, n_fine, eps_w, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_adaptive_backward: tfMode=1 needs tf");
+  cudaError_t e = mrt_launch_adaptive(K, n_coarse, n_fine, eps_w, mrt_packed_channels(C), packed, tf, const_cast<float*>(out_rgba),
+                                      dL_dout, dL_dvol, dL_dtf, scratch, true, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_adaptive_backward");
+}
+
 // ---------------------------------------------------------------- slab
 int mrt_render_slab_u8(const MrtSlabParams* P, const uint8_t* vol_u8, float* out_rgba,
                        int32_t tile_begin, int32_t tile_end, void* stream) {

@@ -39,6 +39,14 @@ struct MrtBwdArgs {
 cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                 const MrtBwdArgs& A, cudaStream_t st);
 size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg);
+// dtf[j] += sum over `ncopies` privatised [ntf][2] float4 accumulators (lo -> entry j, hi -> entry j+1)
+cudaError_t mrt_launch_dtf_reduce(const void* priv, int ncopies, int ntf, float* dtf, cudaStream_t st);
+
+// adaptive (inverse-CDF) sampling, forward (bwd = false: writes out_rgba) and backward
+cudaError_t mrt_launch_adaptive(const KParams& P, int K, int J, float eps_w, int packed_ch, const void* vol, const float* tf,
+                                float* out_rgba, const float* dL_dout, void* dvol, float* dtf, void* scratch, bool bwd,
+                                cudaStream_t st);
+size_t mrt_adaptive_scratch(int ntf);
 
 cudaError_t mrt_launch_pack_f16(const void* planar_f16, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar_f16, cudaStream_t st);
