@@ -197,7 +197,8 @@ mrt_adaptive_kernel(const __grid_constant__ KParams P, const __grid_constant__ A
     if (gs == 0.0f) continue;
     Cell c; Corners<NCH, false> cor; float raw, fr; int j0;
     field(ray.t0 + ((float)l + 0.5f) * h, &c, &cor, &raw, &j0, &fr);
-    if (!(P.tfMode || __saturatef(raw) > 0.0f)) continue;
+    // no (val > 0) gate here: :135 gates the COMPOSITING of a sample; the importance weight is
+    // sigma = ia * clamp(raw), whose derivative at raw == 0 (air) follows torch.clamp's closed interval
     if (gpriv) {
       atomicAdd(&gpriv[2 * j0].w, (1.0f - fr) * gs);
       if (fr != 0.0f) atomicAdd(&gpriv[2 * j0 + 1].w, fr * gs);

@@ -56,6 +56,7 @@ def render_adaptive(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None, 
     Ccol = bg[None, :].expand(nray, 3).clone()
     T = torch.ones(nray, dtype=dtype)
     taken = torch.zeros(nray, dtype=torch.int64)
+    margin = torch.full((nray,), float("inf"), dtype=torch.float64)     # closest approach of T to the ERT threshold
     hidx = torch.nonzero(hit).reshape(-1)
     if hidx.numel() > 0:
         ho, hd, ht0, ht1 = o[hidx], d[hidx], t0[hidx], t1[hidx]
@@ -101,8 +102,10 @@ def render_adaptive(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None, 
         qb = [ht0] + [quantile(j / J) for j in range(1, J)] + [ht1]
         hC, hT = Ccol[hidx], T[hidx]
         htaken = taken[hidx]
+        hmargin = torch.full((hidx.numel(),), float("inf"), dtype=torch.float64)
         for j in range(J):
             active = hT > thr                                         # :117
+            hmargin = torch.minimum(hmargin, ((hT.detach().to(torch.float64) / float(thr)) - 1.0).abs())
             if not bool(active.any()):
                 break
             tm = quantile((j + 0.5) / J)
@@ -119,6 +122,7 @@ def render_adaptive(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None, 
         Ccol = Ccol.index_copy(0, hidx, hC)
         T = T.index_copy(0, hidx, hT)
         taken = taken.index_copy(0, hidx, htaken)
+        margin = margin.index_copy(0, hidx, hmargin)
     a_out = torch.ones(nray, dtype=dtype) if alpha_mode == 0 else (one - T)
     rgba = torch.cat([Ccol, a_out[:, None]], dim=1)
     if pixels is None:
@@ -126,4 +130,4 @@ def render_adaptive(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None, 
     if not return_aux:
         return rgba
     shp = (Hd, Wd) if pixels is None else (nray,)
-    return rgba, dict(T=T.reshape(shp), n_taken=taken.reshape(shp), hit=hit.reshape(shp))
+    return rgba, dict(T=T.reshape(shp), n_taken=taken.reshape(shp), hit=hit.reshape(shp), ert_margin=margin.reshape(shp))
