@@ -97,7 +97,7 @@ typedef struct MrtParams {
    * Output is the partial (r,g,b premultiplied WITHOUT background, a = T_local) for
    * mrt_composite_over.  Early termination acts on the shard-local transmittance. */
   uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3];
-  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16, 2: u8 single-channel (mrt_pack_volume_f16 / _u8), forward only */
+  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16, 2: u8, 3: fp32 quads — single-channel (mrt_pack_volume_f16 / _u8 / _quad), forward only */
 } MrtParams;
 
 /* One camera of a batch of views: the four camera rows of `struct Params`
@@ -185,6 +185,16 @@ size_t mrt_packed_volume_bytes_u8(int32_t X, int32_t Y, int32_t Z);
 int mrt_pack_volume_u8(const uint8_t* planar_u8, int32_t X, int32_t Y, int32_t Z, void* packed, void* stream);
 int mrt_build_occupancy_u8(const void* packed, int32_t X, int32_t Y, int32_t Z, float* minmax, void* stream);
 
+/* "quad" sampler layout of a single-channel fp32 volume: element (x,y,z) = the four voxels (x,y)
+ * (x+1,y) (x,y+1) (x+1,y+1) of slice z (neighbours clamped at the far faces), 16 B per voxel.  A
+ * trilinear footprint (brats_rt.slang:60-76) is then two 16-byte loads instead of eight 4-byte ones:
+ * the march issues a quarter of the load instructions for 4x the bytes.  Built from the packed C = 1
+ * layout (mrt_pack_volume_f32 with C = 1, or the folded volume); the occupancy grid is the one of that
+ * source.  Render it with C = 1 and params->volDtype = 3; the image is bit-identical to volDtype 0.
+ * Forward only. */
+size_t mrt_packed_volume_bytes_quad(int32_t X, int32_t Y, int32_t Z);
+int mrt_pack_volume_quad(const float* packed1, int32_t X, int32_t Y, int32_t Z, void* quad, void* stream);
+
 /* ------------------------------------------------ modality fold
  * The modality blend v = sum_c w_c s_c / wSum (brats_rt.slang:123-130) is linear and commutes
  * with trilinear interpolation.  mrt_fold_volume_f32 evaluates it ONCE per voxel for the
@@ -217,6 +227,9 @@ int mrt_build_label_occupancy(const int32_t* labels, int32_t X, int32_t Y, int32
  *               this brick is provably empty under (params, tf, labels): every sample slot
  *               whose trilinear base index lies in it is a no-op, so the march may leap to
  *               the cell's exit.
+ *   0x80 | l, l in 2..4 (flat == 0 only) : active, and so is every brick of the aligned cell of
+ *               2^(l-1) bricks per axis around it: the march shades through the whole cell on one
+ *               look-up.  Consumers that only ask "empty?" test (level & 0x80) == 0 && level != 0.
  *   flat != 0 (levels for the BACKWARD): a cell additionally has to be flat — every voxel in it
  *               holds one and the same value — so that all slots inside share one TF bin and
  *               one dL/dsigma, which mrt_render_backward adds in closed form.

@@ -90,6 +90,17 @@ def pack_volume_u8(planar: torch.Tensor) -> torch.Tensor:
     return packed
 
 
+def pack_volume_quad(packed1: torch.Tensor, dims, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """packed single-channel fp32 volume -> the "quad" sampler layout (``mrt_pack_volume_quad``:
+    16 B per voxel holding its 2x2 (x,y) neighbourhood; render with ``volDtype=3``)."""
+    X, Y, Z = (int(v) for v in dims)
+    nbytes = lib().mrt_packed_volume_bytes_quad(X, Y, Z)
+    if out is None or out.numel() * out.element_size() != nbytes:
+        out = torch.empty((nbytes // 4,), dtype=torch.float32, device=packed1.device)
+    check(lib().mrt_pack_volume_quad(packed1.data_ptr(), X, Y, Z, out.data_ptr(), _stream()), "pack_volume_quad")
+    return out
+
+
 def build_occupancy_u8(packed: torch.Tensor, dims) -> torch.Tensor:
     X, Y, Z = dims
     mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=packed.device)
@@ -449,9 +460,12 @@ class Volume:
 
     def __init__(self, planar: torch.Tensor, labels: Optional[torch.Tensor] = None,
                  preds: Optional[torch.Tensor] = None, zooms=(1.0, 1.0, 1.0), occupancy: bool = True,
-                 fold: bool = True, shard=None, global_dims=None):
+                 fold: bool = True, shard=None, global_dims=None, quad: Optional[bool] = None):
         """``shard=((lox,loy,loz),(hix,hiy,hiz))`` + ``global_dims``: ``planar`` holds only voxels
-        [lo, hi] (inclusive) of a larger volume — a sort-last sub-box (dist.render_sort_last)."""
+        [lo, hi] (inclusive) of a larger volume — a sort-last sub-box (dist.render_sort_last).
+        ``quad``: sample from the 16 B/voxel quad layout (``pack_volume_quad``; two 16-byte loads per
+        sample instead of eight scalar ones, bit-identical images).  Default: on whenever the sampler
+        is single-channel fp32 without label overlays; the layout is rebuilt with the fold."""
         self.half = isinstance(planar, torch.Tensor) and planar.dtype == torch.float16
         self.u8 = isinstance(planar, torch.Tensor) and planar.dtype == torch.uint8
         _need_cuda(planar, "volume", torch.float16 if self.half else (torch.uint8 if self.u8 else torch.float32))
@@ -490,6 +504,12 @@ class Volume:
         self.labels = self.preds = self.seg_any = self.pred_any = None
         self.set_labels(labels)
         self.set_preds(preds)
+        single = (self.fold or self.C == 1) and not (self.half or self.u8)
+        if quad and not single:
+            raise ValueError("the quad layout needs a single-channel fp32 sampler (C == 1 or fold=True)")
+        self.quad = single if quad is None else bool(quad)
+        self._quad_buf = None
+        self._quad_src = None
         from .synth import world_box
         self.voxel_size, self.vol_min = world_box(self.global_dims, zooms)
         self._bits = None
@@ -501,16 +521,24 @@ class Volume:
             P = replace(P, shard=self.shard)
         if self.half or self.u8:
             P = replace(P, volDtype=1 if self.half else 2)
-        if not self.fold:
-            return self.packed, self.C, P
-        key = _fold_key(P, self.C)
-        if key != self._key:
-            if self.occupancy:
-                self.packed, self.minmax = fold_volume_occupancy(self.planar, P)
-            else:
-                self.packed, self.minmax = fold_volume(self.planar, P), None
-            self._key = key
-        return self.packed, 1, folded_params(P)
+        if self.fold:
+            key = _fold_key(P, self.C)
+            if key != self._key:
+                if self.occupancy:
+                    self.packed, self.minmax = fold_volume_occupancy(self.planar, P)
+                else:
+                    self.packed, self.minmax = fold_volume(self.planar, P), None
+                self._key = key
+                self._quad_src = None
+            P = folded_params(P)
+        Cn = 1 if self.fold else self.C
+        overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
+        if self.quad and not overlays:
+            if self._quad_src is not self.packed:
+                self._quad_buf = pack_volume_quad(self.packed, self.dims, out=self._quad_buf)
+                self._quad_src = self.packed
+            return self._quad_buf, 1, replace(P, volDtype=3)
+        return self.packed, Cn, P
 
     def invalidate(self):
         """Drop the folded-volume cache (the next frame re-folds and rebuilds the occupancy grid)."""

@@ -116,6 +116,22 @@ size_t mrt_packed_volume_bytes_u8(int32_t X, int32_t Y, int32_t Z) {
   mrt_layout_e(1, 1, X, Y, Z, &pY, &pZ);
   return ((size_t)pZ * Z + 15) & ~(size_t)15;
 }
+// quad layout of a single-channel fp32 volume (march.cuh VoxT<1,3>)
+size_t mrt_packed_volume_bytes_quad(int32_t X, int32_t Y, int32_t Z) {
+  if (X < 2 || Y < 2 || Z < 2) return 0;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 16, X, Y, Z, &pY, &pZ);
+  return (size_t)pZ * (size_t)Z * 16;
+}
+int mrt_pack_volume_quad(const float* packed1, int32_t X, int32_t Y, int32_t Z, void* quad, void* stream) {
+  MRT_REQUIRE(packed1 && quad, "pack_volume_quad: null pointer");
+  if (int r = check_dims("pack_volume_quad", 1, X, Y, Z)) return r;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 16, X, Y, Z, &pY, &pZ);
+  MRT_REQUIRE((uint64_t)pZ * (uint64_t)Z < (1ull << 32), "pack_volume_quad: more than 2^32 elements");
+  cudaError_t e = mrt_launch_pack_quad(packed1, X, Y, Z, quad, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume_quad");
+}
 static int check_dims_u8(const char* who, int X, int Y, int Z) {
   MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
   int64_t pY, pZ;
@@ -170,15 +186,15 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on sharded volumes");
     MRT_REQUIRE(M->tMode == 0, "sharded volumes need indexed stepping (tMode 0)");
   }
-  MRT_REQUIRE(M->volDtype <= 2, "volDtype %u unknown (0 fp32, 1 fp16, 2 u8)", M->volDtype);
+  MRT_REQUIRE(M->volDtype <= 3, "volDtype %u unknown (0 fp32, 1 fp16, 2 u8, 3 fp32 quad)", M->volDtype);
   K->half = (int)M->volDtype;
   if (K->half) {
-    MRT_REQUIRE(C == 1, "fp16 / u8 volumes are single-channel (C=%d)", C);
-    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on fp16 / u8 volumes");
+    MRT_REQUIRE(C == 1, "fp16 / u8 / quad volumes are single-channel (C=%d)", C);
+    MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on fp16 / u8 / quad volumes");
   }
   {
     int64_t pY, pZ;
-    mrt_layout_e(mrt_packed_channels(C), K->half == 1 ? 2 : (K->half == 2 ? 1 : 4), ldim[0], ldim[1], ldim[2], &pY, &pZ);
+    mrt_layout_e(mrt_packed_channels(C), K->half == 1 ? 2 : (K->half == 2 ? 1 : (K->half == 3 ? 16 : 4)), ldim[0], ldim[1], ldim[2], &pY, &pZ);
     MRT_REQUIRE((uint64_t)pZ * ldim[2] < (1ull << 32), "more than 2^32 voxels per shard (SURVEY Q14)");
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
     K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;
@@ -196,6 +212,8 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   }
   MRT_REQUIRE(M->stepSize > 0.0f, "stepSize must be > 0");
   K->dt = M->stepSize; K->nearT = M->nearT; K->farT = M->farT;
+  K->inv_dt = 1.0f / K->dt;
+  for (int i = 0; i < 3; ++i) K->inv_vs[i] = 1.0f / K->vs[i];
   MRT_REQUIRE(M->ww > 0.0f, "ww must be > 0 (SURVEY Q10)");
   float wsum = 0.0f;
   for (int c = 0; c < 4; ++c) {

@@ -23,6 +23,8 @@
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
 #endif
 
+template <bool B> struct BoolTag { static constexpr bool value = B; };
+
 // CKPT (training forward): additionally stores (C, T) of every ray before each slot c*CK.S, the
 // ray's end slot and every warp's longest end slot, for the segment-parallel backward (backward.cu).
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF, bool CKPT = false>
@@ -134,31 +136,43 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     const IdxRay q = mrt_index_ray(P, ray);
     const float hix = (float)P.dims[0] - 1.001f, hiy = (float)P.dims[1] - 1.001f, hiz = (float)P.dims[2] - 1.001f;
     const float dt = P.dt, thr = P.thr;
-    const float nm1 = (float)(P.tfN - 1);
-    uint32_t s_tf_addr = (uint32_t)__cvta_generic_to_shared(s_tf);
-    asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
+    float nm1 = (float)(P.tfN - 1);
+    asm volatile("" : "+f"(nm1));              // opaque: one register, not an I2F per sample
+    uint32_t s_tf_adj = (uint32_t)__cvta_generic_to_shared(s_tf) - MRT_TF_ADJ;
+    asm volatile("" : "+r"(s_tf_adj));         // opaque: keep the address in a register, do not re-derive it per sample
+    // sample slot k sits at index-space position so + k*sd  (t_k = t0 + k*dt folded into the ray: one
+    // fma per axis; the look-ups of phase 1 use the same expression, so skipping stays exact)
+    float sox = fmaf(ray.t0, q.dx, q.ox), soy = fmaf(ray.t0, q.dy, q.oy), soz = fmaf(ray.t0, q.dz, q.oz);
+    float sdx = q.dx * dt, sdy = q.dy * dt, sdz = q.dz * dt;
 
-    // one sample slot at ray parameter t  (:119-162)
-    auto shade = [&](float t) {
-      const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-      const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
+    // one sample slot at index-space position pp (:119-162).  `on` = false turns the slot into an
+    // exact no-op WITHOUT a branch (alpha := 0), so a warp's run of slots is straight-line code;
+    // INT = the caller has proven the position inside [0, dims-1.001] (no clamps needed).
+    auto shade_p = [&](float ppx, float ppy, float ppz, bool on, auto tfm, auto inter) {
+      constexpr bool TFM = decltype(tfm)::value, INT = decltype(inter)::value;
+      const Cell c = mrt_cell_t<!INT>(ppx, ppy, ppz, hix, hiy, hiz);
       const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH, HALF>(P, vol, c));
-      if (P.tfMode) {
-        const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val);
-        const float alpha = mrt_alpha(P, rgba.w);
-        const float aT = alpha * T;
+      // alpha = 1 - e, e = exp(-sigma dt) (:137); C += alpha T rgb, T *= 1 - alpha (:138-139) as
+      // T' = T e, alpha T = T - T'  (same quantities, two instructions less)
+      if (TFM) {
+        const float4 rgba = mrt_tf_lookup_adj(s_tf_adj, nm1, val);
+        const float e = mrt_ex2(rgba.w * P.neg_dt_log2e);
+        const float Tn = T * (on ? e : 1.0f);
+        const float aT = T - Tn;
         Cr = fmaf(aT, rgba.x, Cr); Cg = fmaf(aT, rgba.y, Cg); Cb = fmaf(aT, rgba.z, Cb);
-        T *= (1.0f - alpha);
-      } else if (val > 0.0f) {                                             // :135
-        const float alpha = mrt_alpha(P, val * P.ia);                      // :136-137
-        const float c1 = alpha * T * val;                                  // :138
+        T = Tn;
+      } else {
+        // :135 — val == 0 gives e == 1 exactly: the (val > 0) gate is implicit
+        const float e = mrt_ex2(val * P.ia * P.neg_dt_log2e);              // :136-137
+        const float Tn = T * (on ? e : 1.0f);
+        const float c1 = (T - Tn) * val;                                   // :138
         Cr += c1; Cg += c1; Cb += c1;
-        T *= (1.0f - alpha);                                               // :139
+        T = Tn;                                                            // :139
       }
       if (LABELS) {
         if (P.showSeg) {                                                   // :143-151
           const int l = mrt_sample_label(P, labels, ppx, ppy, ppz);
-          if (l > 0 && l < 8) {
+          if (on && l > 0 && l < 8) {
             const float4 col = s_lab[l];
             const float aT = col.w * T;
             Cr = fmaf(aT, col.x, Cr); Cg = fmaf(aT, col.y, Cg); Cb = fmaf(aT, col.z, Cb);
@@ -167,7 +181,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         }
         if (P.showPred) {                                                  // :154-162
           const int l = mrt_sample_label(P, preds, ppx, ppy, ppz);
-          if (l > 0 && l < 8) {
+          if (on && l > 0 && l < 8) {
             const float4 col = s_lab[8 + l];
             const float aT = col.w * T;
             Cr = fmaf(aT, col.x, Cr); Cg = fmaf(aT, col.y, Cg); Cb = fmaf(aT, col.z, Cb);
@@ -176,17 +190,20 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         }
       }
     };
+    const BoolTag<true> yes; const BoolTag<false> no;
 
     if (GENERIC && P.tMode == 1) {
       // reference-faithful running sum t += stepSize (:113,:164); no skipping possible
-      float t = ray.t0;
-      while (ray.n > 0 && t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) {
-        shade(t);
-        t += dt; ++k; ++n_eval;
-      }
+      auto loop = [&](auto tfm) {
+        float t = ray.t0;
+        while (ray.n > 0 && t < ray.t1 && T > thr && (P.maxSteps == 0 || k < P.maxSteps)) {
+          shade_p(fmaf(t, q.dx, q.ox), fmaf(t, q.dy, q.oy), fmaf(t, q.dz, q.oz), true, tfm, no);
+          t += dt; ++k; ++n_eval;
+        }
+      };
+      if (P.tfMode) loop(yes); else loop(no);
     } else if (SKIP) {
-      const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
-      const float inv_dt = 1.0f / dt;
+      const float inv_dt = P.inv_dt;
       int n = ray.n;
       if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, inv_dt, ray.n, &ks, &n); k = ks; }
       const int n_full = n;
@@ -201,6 +218,51 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
           n = k;
         }
       }
+      // Clamp-free march: every slot of [k, n] lies within 2 steps (+ margins) of the active box, so
+      // when the box widened by 2.5 steps stays inside [0, dims-1.001] the sampler's clamps are
+      // identities for the whole warp.  A lane without slots never shades for real, but it rides
+      // along masked: park it on a harmless position (the box centre).
+      bool interior = false;
+      if (!GENERIC && !LABELS) {
+        bool lane_int = true;
+        if (n > k) {
+          const float mx = 2.5f * fabsf(sdx), my = 2.5f * fabsf(sdy), mz = 2.5f * fabsf(sdz);
+          lane_int = (abox.lo[0] - mx >= 0.0f) && (abox.hi[0] + mx <= hix) && (abox.lo[1] - my >= 0.0f) &&
+                     (abox.hi[1] + my <= hiy) && (abox.lo[2] - mz >= 0.0f) && (abox.hi[2] + mz <= hiz);
+        } else if (abox.hi[0] >= abox.lo[0]) {
+          sox = 0.5f * (abox.lo[0] + abox.hi[0]); soy = 0.5f * (abox.lo[1] + abox.hi[1]); soz = 0.5f * (abox.lo[2] + abox.hi[2]);
+          sdx = sdy = sdz = 0.0f;
+        } else {
+          lane_int = false;                                                // no active brick at all: nothing to shade anyway
+        }
+        interior = !P.shard && __all_sync(0xffffffffu, lane_int);
+      }
+      const SlotRay sr = mrt_slot_ray(sox, soy, soz, sdx, sdy, sdz);
+      // a warp's run of m slots: straight-line, masked by the lane's own liveness
+      // (a masked lane still FETCHES at its frozen slot: always inside the buffer for a whole volume —
+      // the sampler clamps to it — but not for a shard's sub-volume, which therefore branches instead)
+      auto run = [&](int m, bool live, auto tfm, auto inter) {
+        bool on = live;
+        float kf = (float)k;
+        if (P.shard) {
+          for (int i = 0; i < m; ++i) {
+            if (on) {
+              shade_p(fmaf(kf, sdx, sox), fmaf(kf, sdy, soy), fmaf(kf, sdz, soz), true, tfm, no);
+              kf += 1.0f; if (GENERIC) ++n_eval;
+              if (CKPT) { if ((int)kf == next_ck) ck_flush(next_ck); }
+              on = T > thr;
+            }
+          }
+        } else {
+          for (int i = 0; i < m; ++i) {
+            shade_p(fmaf(kf, sdx, sox), fmaf(kf, sdy, soy), fmaf(kf, sdz, soz), on, tfm, inter);
+            if (on) { kf += 1.0f; if (GENERIC) ++n_eval; }
+            if (CKPT) { if (on && (int)kf == next_ck) ck_flush(next_ck); }
+            on = on && (T > thr);
+          }
+        }
+        k = (int)kf;
+      };
       // Per-lane knowledge of the ray, in slot indices (k <= kact <= kf <= kl):
       //   [k, kact)   current run, inside active bricks: to be shaded
       //   [kact, kf)  known empty (leapt cells / another shard's slots)
@@ -225,21 +287,26 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         const unsigned wst = __reduce_or_sync(0xffffffffu, (live ? 1u : 0u) | (want ? 2u : 0u));
         if (wst & 2u) {
           if (live && kl < n) {
-            const float t = fmaf((float)kl, dt, ray.t0);
-            const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
-            const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix);             // == floor of the clamped coord
-            const int iy = (int)fminf(fmaxf(ppy, 0.0f), hiy);
-            const int iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+            const float klf = (float)kl;
+            const float ppx = fmaf(klf, sdx, sox), ppy = fmaf(klf, sdy, soy), ppz = fmaf(klf, sdz, soz);
+            int ix, iy, iz;                                                // == floor of the clamped coord
+            if (interior) { ix = (int)ppx; iy = (int)ppy; iz = (int)ppz; }
+            else {
+              ix = (int)fminf(fmaxf(ppx, 0.0f), hix); iy = (int)fminf(fmaxf(ppy, 0.0f), hiy); iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+            }
             int lvl = 1, kend = kl + 1;                                   // another rank's slot: a 1-slot gap
             if (!P.shard || mrt_shard_owns(P, ix, iy, iz)) {
               const int jx = ix - P.slo[0], jy = iy - P.slo[1], jz = iz - P.slo[2];   // brick grid is shard-local
               lvl = __ldg(levels + (((jz >> MRT_BRICK_SHIFT) * P.nby + (jy >> MRT_BRICK_SHIFT)) * P.nbx +
                                     (jx >> MRT_BRICK_SHIFT)));
-              const int sh = lvl ? lvl + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
-              kend = min(n, kl + mrt_cell_slots(q, ivx, ivy, ivz, jx >> sh, jy >> sh, jz >> sh, sh, t, inv_dt,
-                                                P.slo[0], P.slo[1], P.slo[2]));
+              // 0 = active brick, 1..4 = empty cell, 0x80 | 2..4 = all-active cell; edge 2^((lvl & 7) + 2)
+              const int sh = lvl ? (lvl & 7) + (MRT_BRICK_SHIFT - 1) : MRT_BRICK_SHIFT;
+              lvl = (lvl & 0x80) ? 0 : lvl;
+              kend = min(n, kl + mrt_cell_slots_k(sr, jx, jy, jz, sh, klf, P.slo[0], P.slo[1], P.slo[2]));
               // an ACTIVE brick may straddle the shard's far faces: stop at the owned box's exit
-              if (P.shard && !lvl) kend = min(kend, kl + mrt_shard_slots(P, q, ivx, ivy, ivz, t, inv_dt));
+              if (P.shard && !lvl)
+                kend = min(kend, kl + mrt_shard_slots(P, q, mrt_rcp(q.dx), mrt_rcp(q.dy), mrt_rcp(q.dz),
+                                                      fmaf(klf, dt, ray.t0), inv_dt));
               if (GENERIC) ++n_seg;
             }
             if (!lvl) {
@@ -255,15 +322,8 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
         // slots back to back (no lane can run dry before that, so nothing has to be re-checked
         // but the lane's own early termination)
         const int m = __reduce_min_sync(0xffffffffu, live ? kact - k : 0x7fffffff);
-        bool on = live;
-        for (int i = 0; i < m; ++i) {
-          if (on) {
-            shade(fmaf((float)k, dt, ray.t0));
-            ++k; if (GENERIC) ++n_eval;
-            if (CKPT) { if (k == next_ck) ck_flush(k); }
-            on = T > thr;
-          }
-        }
+        if (P.tfMode) { if (interior) run(m, live, yes, yes); else run(m, live, yes, no); }
+        else          { if (interior) run(m, live, no, yes);  else run(m, live, no, no); }
       }
       if (T > thr) {                       // ran to the end: the oracle's n_taken counts the clipped no-op slots too
         k = n_full;
@@ -271,19 +331,22 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       }
     } else {
       int n = ray.n;
-      if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, 1.0f / dt, ray.n, &ks, &n); k = ks; }
-      while (k < n && T > thr) {                                           // :117
-        const float t = fmaf((float)k, dt, ray.t0);
-        if (P.shard) {
-          const int ix = (int)fminf(fmaxf(fmaf(t, q.dx, q.ox), 0.0f), hix);
-          const int iy = (int)fminf(fmaxf(fmaf(t, q.dy, q.oy), 0.0f), hiy);
-          const int iz = (int)fminf(fmaxf(fmaf(t, q.dz, q.oz), 0.0f), hiz);
-          if (!mrt_shard_owns(P, ix, iy, iz)) { ++k; continue; }
+      if (P.shard) { int ks; mrt_shard_range(P, q, ray.t0, P.inv_dt, ray.n, &ks, &n); k = ks; }
+      auto loop = [&](auto tfm) {
+        while (k < n && T > thr) {                                         // :117
+          const float kf = (float)k;
+          const float ppx = fmaf(kf, sdx, sox), ppy = fmaf(kf, sdy, soy), ppz = fmaf(kf, sdz, soz);
+          if (P.shard) {
+            const int ix = (int)fminf(fmaxf(ppx, 0.0f), hix), iy = (int)fminf(fmaxf(ppy, 0.0f), hiy),
+                      iz = (int)fminf(fmaxf(ppz, 0.0f), hiz);
+            if (!mrt_shard_owns(P, ix, iy, iz)) { ++k; continue; }
+          }
+          shade_p(ppx, ppy, ppz, true, tfm, no);
+          ++k; if (GENERIC) ++n_eval;
+          if (CKPT) { if (k == next_ck) ck_flush(k); }
         }
-        shade(t);
-        ++k; if (GENERIC) ++n_eval;
-        if (CKPT) { if (k == next_ck) ck_flush(k); }
-      }
+      };
+      if (P.tfMode) loop(yes); else loop(no);
       if (CKPT) { if (T > thr) ck_flush(n - 1); }
     }
   }
@@ -505,7 +568,7 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && levels != nullptr && P.tMode == 0;
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
-  if (P.half) {            // fp16 / u8 voxels: single channel, no label overlays (c_api.cu checks)
+  if (P.half) {            // fp16 / u8 / quad voxels: single channel, no label overlays (c_api.cu checks)
     if (packed_ch != 1 || lab) return cudaErrorInvalidValue;
 #define MRT_NARROW(H) \
     if (skip) return gen ? launch_fwd<1, false, true, true, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st) \
@@ -513,6 +576,7 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
     return gen ? launch_fwd<1, false, false, true, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st) \
                : launch_fwd<1, false, false, false, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
     if (P.half == 1) { MRT_NARROW(1) }
+    if (P.half == 3) { MRT_NARROW(3) }
     MRT_NARROW(2)
 #undef MRT_NARROW
   }

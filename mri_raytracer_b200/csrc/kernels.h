@@ -53,6 +53,7 @@ cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void*
 cudaError_t mrt_launch_build_occupancy_f16(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_pack_u8(const void* planar_u8, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_build_occupancy_u8(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
+cudaError_t mrt_launch_pack_quad(const float* packed1, int X, int Y, int Z, void* quad, cudaStream_t st);
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
 
@@ -97,7 +98,7 @@ static inline int mrt_packed_channels(int C) { return C <= 1 ? 1 : (C == 2 ? 2 :
 // 128-byte line, pitchY = S/4 and pitchZ = S/2 (mod S) put the cells of a small 3-D
 // neighbourhood into distinct L1 data banks, so a warp's gather is not serialised by bank
 // conflicts between rows/slices (row pitches that are multiples of 128 B alias every row).
-// `elem_bytes` = 4 (fp32 voxels) or 2 (fp16, single channel).
+// `elem_bytes` = 4 (fp32 voxels), 2 (fp16), 1 (u8) or 16 (quad of fp32), the last three single channel.
 static inline void mrt_layout_e(int packed_ch, int elem_bytes, int X, int Y, int Z, int64_t* pitchY, int64_t* pitchZ) {
   const int64_t S = 128 / (packed_ch * elem_bytes);
   int64_t py = X;

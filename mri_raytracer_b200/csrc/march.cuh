@@ -23,6 +23,7 @@ struct KParams {
   int dims[3];            // X, Y, Z
   unsigned pitchY, pitchZ; // packed-layout pitches in voxels (kernels.h mrt_layout)
   float dt, nearT, farT;
+  float inv_dt, inv_vs[3];  // 1/dt, 1/vs (rounded once on the host; only the non-bit-exact index-space math uses them)
   float bg[3];
   float wgt[4];           // volWeight if enabled else 0
   float inv_wsum;         // 1/wSum if wSum > 0 else 1
@@ -297,6 +298,11 @@ template <> struct Vox<4> { typedef float4 T; };
 template <int NCH, int HALF> struct VoxT { typedef typename Vox<NCH>::T T; };
 template <> struct VoxT<1, 1> { typedef __half T; };
 template <> struct VoxT<1, 2> { typedef uint8_t T; };
+// HALF = 3, the "quad" layout of a single-channel fp32 volume: element (x,y,z) holds the four voxels
+// (x,y) (x+1,y) (x,y+1) (x+1,y+1) of slice z, so a trilinear footprint is TWO 16-byte loads (slices z
+// and z+1) instead of eight 4-byte ones: a quarter of the load instructions and about half the L1
+// data-stage wavefronts of the march, for 4x the bytes (mrt_pack_volume_quad).  Forward only.
+template <> struct VoxT<1, 3> { typedef float4 T; };
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
@@ -324,8 +330,8 @@ __device__ __forceinline__ float foldv(float4 s, const KParams& P) {
 struct IdxRay { float ox, oy, oz, dx, dy, dz; };
 __device__ __forceinline__ IdxRay mrt_index_ray(const KParams& P, const Ray& r) {
   IdxRay q;
-  q.ox = (r.ox - P.bmin[0]) / P.vs[0]; q.oy = (r.oy - P.bmin[1]) / P.vs[1]; q.oz = (r.oz - P.bmin[2]) / P.vs[2];
-  q.dx = r.dx / P.vs[0]; q.dy = r.dy / P.vs[1]; q.dz = r.dz / P.vs[2];
+  q.ox = (r.ox - P.bmin[0]) * P.inv_vs[0]; q.oy = (r.oy - P.bmin[1]) * P.inv_vs[1]; q.oz = (r.oz - P.bmin[2]) * P.inv_vs[2];
+  q.dx = r.dx * P.inv_vs[0]; q.dy = r.dy * P.inv_vs[1]; q.dz = r.dz * P.inv_vs[2];
   return q;
 }
 
@@ -340,12 +346,13 @@ struct Cell {
   __device__ __forceinline__ int iz() const { return (int)(mz - MRT_MAGIC_BITS); }
 };
 
-__device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, float pz,
-                                         float hix, float hiy, float hiz) {
+// CLAMP = false: the caller has proven 0 <= p <= hi on every axis (the clamps are identities there)
+template <bool CLAMP>
+__device__ __forceinline__ Cell mrt_cell_t(float px, float py, float pz, float hix, float hiy, float hiz) {
   Cell c;
-  const float qx = fminf(fmaxf(px, 0.0f), hix);
-  const float qy = fminf(fmaxf(py, 0.0f), hiy);
-  const float qz = fminf(fmaxf(pz, 0.0f), hiz);
+  const float qx = CLAMP ? fminf(fmaxf(px, 0.0f), hix) : px;
+  const float qy = CLAMP ? fminf(fmaxf(py, 0.0f), hiy) : py;
+  const float qz = CLAMP ? fminf(fmaxf(pz, 0.0f), hiz) : pz;
   // floor of a value in [0, 2^22) without the conversion (XU) pipe: q + 2^23 rounded toward
   // -inf is exactly 2^23 + floor(q); its low mantissa bits are the integer.  Same result as
   // floorf / (int), three FADD/IADD instead of F2I + FRND per axis.
@@ -354,31 +361,54 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
   c.fx = qx - (mx - 8388608.0f); c.fy = qy - (my - 8388608.0f); c.fz = qz - (mz - 8388608.0f);
   return c;
 }
+__device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, float pz,
+                                         float hix, float hiy, float hiz) {
+  return mrt_cell_t<true>(px, py, pz, hix, hiy, hiz);
+}
 
 // sampleLinear (brats_rt.slang:60-76; lerp order x, y, z) of the folded scalar field, i.e.
 // raw = ((blend of the <=4 modalities, :123-130) - (wl - ww/2)) / ww  (:132) before saturate.
 // The 8 corners of a cell, fetched (mrt_fetch) separately from their interpolation (mrt_interp) so
 // that a kernel can issue the loads of the NEXT slot before the dependent arithmetic of this one.
-template <int NCH, int HALF> struct Corners { typename VoxT<NCH, HALF>::T v[8]; };
+template <int NCH, int HALF> struct CornerT { typedef typename VoxT<NCH, HALF>::T T; };
+template <> struct CornerT<1, 3> { typedef float T; };
+template <int NCH, int HALF> struct Corners { typename CornerT<NCH, HALF>::T v[8]; };
 
+template <int NCH, int HALF> struct FetchImpl {
+  static __device__ __forceinline__ Corners<NCH, HALF> run(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
+                                                           const Cell& c) {
+    typedef typename VoxT<NCH, HALF>::T VT;
+    // element index straight from the magic-number bits: the three -0x4b000000 corrections and the
+    // shard offset are one precomputed constant (uint32 wrap-around is exact)
+    const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
+    const char* q0 = reinterpret_cast<const char*>(vol) + (size_t)b * sizeof(VT);
+    const VT* p0 = reinterpret_cast<const VT*>(q0);
+    const VT* p1 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchY * sizeof(VT));
+    const VT* p2 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchZ * sizeof(VT));
+    const VT* p3 = reinterpret_cast<const VT*>(q0 + ((size_t)P.pitchY + (size_t)P.pitchZ) * sizeof(VT));
+    Corners<NCH, HALF> k;
+    k.v[0] = __ldg(p0); k.v[1] = __ldg(p0 + 1);
+    k.v[2] = __ldg(p1); k.v[3] = __ldg(p1 + 1);
+    k.v[4] = __ldg(p2); k.v[5] = __ldg(p2 + 1);
+    k.v[6] = __ldg(p3); k.v[7] = __ldg(p3 + 1);
+    return k;
+  }
+};
+template <> struct FetchImpl<1, 3> {
+  static __device__ __forceinline__ Corners<1, 3> run(const KParams& P, const float4* __restrict__ vol, const Cell& c) {
+    const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
+    const float4* p0 = vol + b;
+    const float4 lo = __ldg(p0), hi = __ldg(p0 + P.pitchZ);
+    Corners<1, 3> k;
+    k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
+    k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+    return k;
+  }
+};
 template <int NCH, int HALF = 0>
 __device__ __forceinline__ Corners<NCH, HALF> mrt_fetch(const KParams& P, const typename VoxT<NCH, HALF>::T* __restrict__ vol,
                                                        const Cell& c) {
-  typedef typename VoxT<NCH, HALF>::T VT;
-  // element index straight from the magic-number bits: the three -0x4b000000 corrections and the
-  // shard offset are one precomputed constant (uint32 wrap-around is exact)
-  const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
-  const char* q0 = reinterpret_cast<const char*>(vol) + (size_t)b * sizeof(VT);
-  const VT* p0 = reinterpret_cast<const VT*>(q0);
-  const VT* p1 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchY * sizeof(VT));
-  const VT* p2 = reinterpret_cast<const VT*>(q0 + (size_t)P.pitchZ * sizeof(VT));
-  const VT* p3 = reinterpret_cast<const VT*>(q0 + ((size_t)P.pitchY + (size_t)P.pitchZ) * sizeof(VT));
-  Corners<NCH, HALF> k;
-  k.v[0] = __ldg(p0); k.v[1] = __ldg(p0 + 1);
-  k.v[2] = __ldg(p1); k.v[3] = __ldg(p1 + 1);
-  k.v[4] = __ldg(p2); k.v[5] = __ldg(p2 + 1);
-  k.v[6] = __ldg(p3); k.v[7] = __ldg(p3 + 1);
-  return k;
+  return FetchImpl<NCH, HALF>::run(P, vol, c);
 }
 
 template <int NCH, int HALF = 0>
@@ -483,6 +513,22 @@ __device__ __forceinline__ float4 mrt_tf_lookup(uint32_t s_tf, float nm1, float 
   return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
 }
 
+// The march's copy of the look-up: `s_tf_adj` = shared-window address of the LUT minus
+// (0x4b000000 << 5) mod 2^32, so that the entry address is ONE shift-add of the magic-number bits of
+// floor(u), and both 16-byte halves of the entry come from one address register.
+#define MRT_TF_ADJ 0x60000000u
+__device__ __forceinline__ float4 mrt_tf_lookup_adj(uint32_t s_tf_adj, float nm1, float val) {
+  static_assert(sizeof(TfEntry) == 32, "entry address = index << 5");
+  const float u = val * nm1;
+  const float mu = __fadd_rd(u, 8388608.0f);
+  const float fr = u - (mu - 8388608.0f);
+  const uint32_t ea = s_tf_adj + (__float_as_uint(mu) << 5);
+  float4 a, d;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%8];\n\tld.shared.v4.f32 {%4,%5,%6,%7}, [%8+16];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "r"(ea));
+  return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
+}
+
 // CTA index -> position in the launch's tile range, "middle-out": CTA 0 takes the middle of the
 // range and successive CTAs alternate outward.  The tile ids of a frame are row-major, so the
 // rows through the image centre — where the camera frames the volume and rays are longest —
@@ -533,6 +579,31 @@ __device__ __forceinline__ int mrt_cell_slots(const IdxRay& q, float ivx, float 
   const float tz = (q.dz != 0.0f) ? (plz - q.oz) * ivz : 3.0e38f;
   const float te = fminf(fminf(tx, ty), tz);
   const float ns = floorf((te - t) * inv_dt) + 1.0f;     // slots j with t + j*dt <= te
+  return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
+}
+
+// The same question in SLOT units for a ray whose slot k sits at so + k*sd (index space): per axis
+// isd = 1/sd and ec = -so*isd (isd = 0, ec = 3e38 for an axis the ray does not move along), so the
+// slot coordinate of a plane pl is one fma.  (jx,jy,jz) = integer position inside the (sub-)volume
+// whose origin sits at global voxel (ox,oy,oz); the cell is the aligned 2^sh cube around it.
+struct SlotRay { float isdx, isdy, isdz, ecx, ecy, ecz; };
+__device__ __forceinline__ SlotRay mrt_slot_ray(float sox, float soy, float soz, float sdx, float sdy, float sdz) {
+  SlotRay r;
+  r.isdx = (sdx != 0.0f) ? mrt_rcp(sdx) : 0.0f; r.ecx = (sdx != 0.0f) ? -sox * r.isdx : 3.0e38f;
+  r.isdy = (sdy != 0.0f) ? mrt_rcp(sdy) : 0.0f; r.ecy = (sdy != 0.0f) ? -soy * r.isdy : 3.0e38f;
+  r.isdz = (sdz != 0.0f) ? mrt_rcp(sdz) : 0.0f; r.ecz = (sdz != 0.0f) ? -soz * r.isdz : 3.0e38f;
+  return r;
+}
+__device__ __forceinline__ int mrt_cell_slots_k(const SlotRay& r, int jx, int jy, int jz, int sh, float kf,
+                                                int ox, int oy, int oz) {
+  const int mask = (int)(0xffffffffu << sh);
+  const float Sf = __int_as_float((127 + sh) << 23);           // 2^sh
+  const float far_adj = Sf - MRT_PLANE_EPS;
+  const float plx = (float)((jx & mask) + ox) + ((r.isdx > 0.0f) ? far_adj : MRT_PLANE_EPS);
+  const float ply = (float)((jy & mask) + oy) + ((r.isdy > 0.0f) ? far_adj : MRT_PLANE_EPS);
+  const float plz = (float)((jz & mask) + oz) + ((r.isdz > 0.0f) ? far_adj : MRT_PLANE_EPS);
+  const float ke = fminf(fminf(fmaf(plx, r.isdx, r.ecx), fmaf(ply, r.isdy, r.ecy)), fmaf(plz, r.isdz, r.ecz));
+  const float ns = floorf(ke - kf) + 1.0f;                     // slots j with k + j <= ke
   return (ns >= 1.0f) ? (int)fminf(ns, 1.0e9f) : 1;
 }
 

@@ -93,6 +93,32 @@ cudaError_t mrt_launch_pack_u8(const void* planar, int X, int Y, int Z, void* pa
                                                                                      (uint8_t*)packed, false);
   return cudaGetLastError();
 }
+// quad layout (march.cuh VoxT<1,3>): element (x,y,z) = voxels (x,y) (x+1,y) (x,y+1) (x+1,y+1) of the
+// single-channel packed fp32 volume, neighbours clamped at the far faces (never read as a base cell)
+__global__ void __launch_bounds__(256)
+mrt_pack_quad_kernel(const float* __restrict__ src, int X, int Y, int Z, size_t sY, size_t sZ, size_t qY, size_t qZ,
+                     float4* __restrict__ quad) {
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const int y1 = min(y + 1, Y - 1);
+    const float* r0 = src + (size_t)y * sY + (size_t)z * sZ;
+    const float* r1 = src + (size_t)y1 * sY + (size_t)z * sZ;
+    float4* o = quad + (size_t)y * qY + (size_t)z * qZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      const int x1 = min(x + 1, X - 1);
+      o[x] = make_float4(__ldg(r0 + x), __ldg(r0 + x1), __ldg(r1 + x), __ldg(r1 + x1));
+    }
+  }
+}
+cudaError_t mrt_launch_pack_quad(const float* packed1, int X, int Y, int Z, void* quad, cudaStream_t st) {
+  int64_t sY, sZ, qY, qZ;
+  mrt_layout(1, X, Y, Z, &sY, &sZ);
+  mrt_layout_e(1, 16, X, Y, Z, &qY, &qZ);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  mrt_pack_quad_kernel<<<grid_for((size_t)Y * Z * 256, 256), blk, 0, st>>>(packed1, X, Y, Z, sY, sZ, qY, qZ, (float4*)quad);
+  return cudaGetLastError();
+}
 cudaError_t mrt_launch_unpack_f16(const void* packed, int X, int Y, int Z, void* planar, cudaStream_t st) {
   int64_t pY, pZ;
   mrt_layout_e(1, 2, X, Y, Z, &pY, &pZ);

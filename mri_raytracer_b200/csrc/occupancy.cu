@@ -164,7 +164,8 @@ __device__ __forceinline__ bool mrt_brick_active(const KParams& P, const float2*
 // One CTA per 8x8x8-brick super-cell (64^3 voxels): classify each brick, then reduce the
 // flags over the aligned 2^3, 4^3 and 8^3 brick cells and store, per brick, the largest
 // aligned empty cell that contains it (skip level 1..4; 0 = active).  Bricks outside the
-// grid count as empty (no sample slot ever lands there).
+// grid count as empty (no sample slot ever lands there).  Non-FLAT levels additionally carry
+// 0x80 | 2..4 for an active brick inside an aligned all-active 2^3 / 4^3 / 8^3 brick cell.
 // FLAT variant (for the backward): a brick only counts as skippable if it is empty AND flat
 // (min == max: every voxel holds the same value), and a coarse cell only if all its bricks are
 // flat-empty with the SAME value — then every slot inside has identical TF bin, colour and
@@ -179,6 +180,7 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
   __shared__ uint8_t s_or2[64];
   __shared__ uint8_t s_or4[8];
   __shared__ uint8_t s_or8;
+  __shared__ uint8_t s_all[512], s_and2[64], s_and4[8], s_and8;   // all-active cells (bricks outside the grid: don't care)
   __shared__ int s_box[6];
   __shared__ float s_lo[512], s_hi[512], s_lo2[64], s_hi2[64], s_lo4[8], s_hi4[8];
   const int t = threadIdx.x;
@@ -202,6 +204,7 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
     s_lo[t] = lo; s_hi[t] = hi;
   }
   s_act[t] = act;
+  if (!FLAT) s_all[t] = act || !inside;
   __syncthreads();
   // bounding box of the active bricks (brick units), all six as maxima: (-lo, hi).  The march
   // culls rays / whole CTAs against it before the exact ray set-up and clips every ray's slot
@@ -212,39 +215,48 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
   }
   if (t < 64) {            // 2x2x2 groups: group (gx,gy,gz) in 4x4x4
     const int gx = t & 3, gy = (t >> 2) & 3, gz = t >> 4;
-    int o = 0;
+    int o = 0, a = 1;
     float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = ((gz * 2 + (i >> 2)) << 6) + ((gy * 2 + ((i >> 1) & 1)) << 3) + gx * 2 + (i & 1);
       o |= s_act[j];
+      if (!FLAT) a &= s_all[j];
       if (FLAT) { lo = fminf(lo, s_lo[j]); hi = fmaxf(hi, s_hi[j]); }
     }
     if (FLAT) { s_lo2[t] = lo; s_hi2[t] = hi; if (lo < hi) o = 1; }
     s_or2[t] = (uint8_t)o;
+    if (!FLAT) s_and2[t] = (uint8_t)a;
   }
   __syncthreads();
   if (t < 8) {             // 4x4x4 groups: (hx,hy,hz) in 2x2x2, each = 2x2x2 of the or2 groups
     const int hx = t & 1, hy = (t >> 1) & 1, hz = t >> 2;
-    int o = 0;
+    int o = 0, a = 1;
     float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = ((hz * 2 + (i >> 2)) << 4) + ((hy * 2 + ((i >> 1) & 1)) << 2) + hx * 2 + (i & 1);
       o |= s_or2[j];
+      if (!FLAT) a &= s_and2[j];
       if (FLAT) { lo = fminf(lo, s_lo2[j]); hi = fmaxf(hi, s_hi2[j]); }
     }
     if (FLAT) { s_lo4[t] = lo; s_hi4[t] = hi; if (lo < hi) o = 1; }
     s_or4[t] = (uint8_t)o;
+    if (!FLAT) s_and4[t] = (uint8_t)a;
   }
   __syncthreads();
   if (t == 0) {
-    int o = 0;
+    int o = 0, a = 1;
     float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o |= s_or4[i]; if (FLAT) { lo = fminf(lo, s_lo4[i]); hi = fmaxf(hi, s_hi4[i]); } }
+    for (int i = 0; i < 8; ++i) {
+      o |= s_or4[i];
+      if (!FLAT) a &= s_and4[i];
+      if (FLAT) { lo = fminf(lo, s_lo4[i]); hi = fmaxf(hi, s_hi4[i]); }
+    }
     if (FLAT && lo < hi) o = 1;
     s_or8 = (uint8_t)o;
+    if (!FLAT) s_and8 = (uint8_t)a;
   }
   __syncthreads();
   if (t < 6 && s_box[t] != INT_MIN) atomicMax(box + t, s_box[t]);     // s_box complete: 3 barriers ago
@@ -258,6 +270,16 @@ mrt_classify_kernel(const __grid_constant__ KParams P, const float2* __restrict_
           lvl = 3;
           if (!s_or8) lvl = 4;
         }
+      }
+    }
+    // the march's levels also mark the largest aligned ALL-ACTIVE cell around an active brick
+    // (0x80 | 2..4 = 16^3, 32^3, 64^3 voxels; cell edge 2^((lvl & 7) + 2) like the empty levels), so a
+    // ray inside a solid region asks once per cell instead of once per brick
+    if (!FLAT && act && s_and2[((lz >> 1) << 4) + ((ly >> 1) << 2) + (lx >> 1)]) {
+      lvl = 0x80 | 2;
+      if (s_and4[((lz >> 2) << 2) + ((ly >> 2) << 1) + (lx >> 2)]) {
+        lvl = 0x80 | 3;
+        if (s_and8) lvl = 0x80 | 4;
       }
     }
     levels[b] = (uint8_t)lvl;

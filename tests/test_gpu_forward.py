@@ -397,6 +397,33 @@ def test_u8_volume_through_the_main_marcher(cuda, ortho, use_tf):
         api.render_backward(replace(P, volDtype=2), V8.packed, 1, tfd, None, None, img, torch.ones_like(img))
 
 
+@pytest.mark.parametrize("C,ortho,use_tf", [(1, False, True), (4, False, True), (2, True, False), (1, True, True)])
+def test_quad_layout_is_bit_identical_to_the_scalar_layout(cuda, C, ortho, use_tf):
+    """The 16 B/voxel quad sampler layout (mrt_pack_volume_quad, volDtype 3: two 16-byte loads per
+    sample) holds the same eight corners as the scalar layout: images, transmittance and per-ray
+    counts must be bit-identical, with skipping on and off, single frames and batches."""
+    vol, _, P = small_scene(C=C, dims=(52, 44, 37), W=72, H=56, seed=21, ortho=ortho)
+    P = replace(P, tfMode=int(use_tf), intensityAlpha=8.0, bgColor=(0.05, 0.0, 0.1))
+    tfd = ramp_tf(64, sigma_scale=20.0, cutoff=0.1).cuda() if use_tf else None
+    Vq, Vs = api.Volume(vol.cuda(), quad=True), api.Volume(vol.cuda(), quad=False)
+    assert Vq.quad and not Vs.quad
+    _, _, Pq = Vq.prepared(P)
+    assert Pq.volDtype == 3
+    for skip in (1, 0):
+        a = api.render_aux(Vq, None, tfd, replace(P, skipEmpty=skip))
+        b = api.render_aux(Vs, None, tfd, replace(P, skipEmpty=skip))
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert torch.equal(api.render(Vq, None, tfd, P), api.render(Vs, None, tfd, P))
+    img, _, counts = api.render_aux(Vq, None, tfd, P)
+    stats, _, _ = check_forward(img, counts, vol, P, tf_cpu=None if tfd is None else tfd.cpu())
+    assert stats["max_abs"] <= 1e-4
+    # the far faces (x = X-1 / y = Y-1 are only ever read as the +1 neighbour) and a changed fold
+    if C > 1:
+        P2 = replace(P, volWeight=(0.2, 1.0, 0.5, 2.0))
+        assert torch.equal(api.render(Vq, None, tfd, P2), api.render(Vs, None, tfd, P2))
+
+
 def test_bad_arguments_raise(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     V = api.Volume(vol.cuda())
