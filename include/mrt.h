@@ -261,6 +261,19 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C,
                        float* out_rgba, float* out_T, int32_t* out_counts,
                        int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* The staged-brick variant of the single-view march (forward_tma.cu): one CTA per `tile`x`tile`
+ * pixel block (8 or 16) streams the boxes of `box_edge`^3 voxels (8 or 16, +1 halo) its ray bundle
+ * crosses through a double-buffered shared-memory stage with 3-D TMA box loads and samples them from
+ * shared memory; same image as mrt_render_forward (same sampler arithmetic, brats_rt.slang:60-76).
+ * Scalar fp32 single-channel `packed` (C = 1 layout, e.g. the folded volume), params->skipEmpty set and
+ * `skip_levels` from mrt_classify_bricks(flat = 0), indexed stepping, no shards / overlays / gamma.
+ * `stats` (optional, device, 4 x uint64, zeroed by the caller): slots shaded from the stage, slots
+ * finished by direct gathers, boxes staged, lists that overflowed.  MEASURED SLOWER than the direct
+ * gathers of mrt_render_forward at every configuration: kept selectable, not the default. */
+int mrt_render_forward_tma(const MrtParams* params, const void* packed, const float* tf, int32_t tfN,
+                           const uint8_t* skip_levels, float* out_rgba, int32_t box_edge, int32_t tile,
+                           uint64_t* stats, void* stream);
+
 /* A batch of views of ONE volume under ONE parameter block: what the reference's frame loop
  * does with `nviews` successive dispatches whose params differ only in (eye, U, V, W)
  * (brats_viewer.py:400-442).  Here it is one launch per <= mrt_max_views_per_launch() views

@@ -187,6 +187,24 @@ def render_forward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[
     return out
 
 
+def render_forward_tma(P: RenderParams, packed: torch.Tensor, tf: Optional[torch.Tensor], skip_levels: torch.Tensor,
+                       box_edge: int = 8, tile: int = 8, out: Optional[torch.Tensor] = None,
+                       stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The staged-brick variant of the march (``mrt_render_forward_tma``, forward_tma.cu): boxes of
+    ``box_edge``^3 voxels streamed through shared memory with 3-D TMA loads, one CTA per
+    ``tile``x``tile`` pixels.  Same image as :func:`render_forward` on a scalar single-channel fp32
+    ``packed`` volume; measured slower — a selectable variant, not the default.
+    ``stats``: optional zeroed int64[4] CUDA tensor (staged slots, direct slots, boxes, overflows)."""
+    W, H = P.imageSize
+    if out is None:
+        out = torch.empty((H, W, 4), dtype=torch.float32, device=packed.device)
+    s = P.to_struct()
+    check(lib().mrt_render_forward_tma(C.byref(s), packed.data_ptr(), _ptr(tf), 0 if tf is None else tf.shape[0],
+                                       skip_levels.data_ptr(), out.data_ptr(), int(box_edge), int(tile), _ptr(stats),
+                                       _stream()), "render_forward_tma")
+    return out
+
+
 def _camera_array(cams) -> np.ndarray:
     """``MrtCamera[len(cams)]`` as a float32 ``[V,16]`` array (rows eye|pad, U|pad, V|pad, W|pad); an
     array built by an earlier call passes through (callers that launch several kernels per batch)."""

@@ -19,7 +19,7 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libmrt.so"
 OBJ = PKG / "build"
 
-SOURCES = ["c_api.cu", "forward.cu", "backward.cu", "occupancy.cu", "misc.cu", "slab.cu", "host_pipeline.cu", "inr.cu", "adaptive.cu"]
+SOURCES = ["c_api.cu", "forward.cu", "forward_tma.cu", "backward.cu", "occupancy.cu", "misc.cu", "slab.cu", "host_pipeline.cu", "inr.cu", "adaptive.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # No -use_fast_math: the parity contract needs IEEE div/sqrt and full-precision expf.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",

@@ -340,6 +340,19 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, c
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
 }
 
+int mrt_render_forward_tma(const MrtParams* params, const void* packed, const float* tf, int32_t tfN,
+                           const uint8_t* skip_levels, float* out_rgba, int32_t box_edge, int32_t tile,
+                           uint64_t* stats, void* stream) {
+  MRT_REQUIRE(params && packed && out_rgba && skip_levels, "render_forward_tma: null pointer");
+  MRT_REQUIRE(!params->tfMode || tf, "render_forward_tma: tfMode=1 needs a LUT");
+  KParams K;
+  if (int r = derive(params, 1, tfN, true, 0, mrt_tile_count(params->imageSize[0], params->imageSize[1]), &K)) return r;
+  MRT_REQUIRE(!K.half && !K.shard && K.tMode == 0 && K.gamma == 1.0f && !K.showSeg && !K.showPred && K.skip,
+              "render_forward_tma: scalar fp32 single-channel volumes, indexed stepping, skipping on, no shards / overlays / gamma");
+  MRT_REQUIRE((box_edge == 8 || box_edge == 16) && (tile == 8 || tile == 16), "render_forward_tma: box_edge and tile must be 8 or 16");
+  cudaError_t e = mrt_launch_forward_tma(K, box_edge, tile, packed, tf, skip_levels, out_rgba, stats, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_tma");
+}
 int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                              const void* packed, int32_t C, const float* tf, int32_t tfN,
                              const uint8_t* skip_levels, const int32_t* labels, const int32_t* preds,

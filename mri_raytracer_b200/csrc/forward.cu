@@ -17,7 +17,7 @@
 #define MRT_RUN_MIN 1           // slots of known-active run a lane likes to keep ahead of itself
 #endif
 #ifndef MRT_FWD_MINB
-#define MRT_FWD_MINB 8          // resident CTAs per SM the register allocation aims for (single-channel variants)
+#define MRT_FWD_MINB 10         // resident CTAs per SM the register allocation aims for (single-channel variants; measured 8: 0.634, 9: 0.643, 10: 0.618 ms per cfg2 batch)
 #endif
 #ifndef MRT_FWD_TPB
 #define MRT_FWD_TPB 2           // 8x8 tiles per CTA  (CTA = 64*TPB threads)
@@ -28,7 +28,7 @@ template <bool B> struct BoolTag { static constexpr bool value = B; };
 // CKPT (training forward): additionally stores (C, T) of every ray before each slot c*CK.S, the
 // ray's end slot and every warp's longest end slot, for the segment-parallel backward (backward.cu).
 template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF, bool CKPT = false>
-__global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 128 * MRT_FWD_MINB) / (64 * MRT_FWD_TPB))
+__global__ void __launch_bounds__(64 * MRT_FWD_TPB, (NCH == 4 ? 768 : 128 * ((LABELS || GENERIC || CKPT) ? 8 : MRT_FWD_MINB)) / (64 * MRT_FWD_TPB))
 mrt_fwd_kernel(const __grid_constant__ KParams P,
                const __grid_constant__ CamBatch B,
                const __grid_constant__ StripTargets S,
@@ -42,8 +42,9 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
                float* __restrict__ out_T,
                int4* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  TfEntry* s_tf = reinterpret_cast<TfEntry*>(s_raw);                        // [tfN]
-  float4* s_lab = reinterpret_cast<float4*>(s_tf + (P.tfMode ? P.tfN : 0));  // [0..7] seg, [8..15] pred
+  unsigned char* s_tf = s_raw;                                              // [tfN] entries of mrt_tf_stride bytes
+  const uint32_t tf_stride = mrt_tf_stride(P.tfN);
+  float4* s_lab = reinterpret_cast<float4*>(s_raw + (P.tfMode ? (size_t)P.tfN * tf_stride : 0));   // [0..7] seg, [8..15] pred
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = P.tile_begin + mrt_middle_out(blockIdx.x, gridDim.x) * MRT_FWD_TPB + (warp >> 1);
@@ -101,7 +102,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     if (GENERIC || CKPT || S.spans != nullptr) abox = mrt_active_box(P, levels);   // (still needed to clip the slot ranges)
   }
 
-  if (P.tfMode) mrt_tf_stage(s_tf, tf, P.tfN);
+  if (P.tfMode) mrt_tf_stage_strided(s_tf, tf_stride, tf, P.tfN);
   if (LABELS) {
     if (threadIdx.x < 16) {
       const int l = threadIdx.x & 7;
@@ -138,8 +139,10 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
     const float dt = P.dt, thr = P.thr;
     float nm1 = (float)(P.tfN - 1);
     asm volatile("" : "+f"(nm1));              // opaque: one register, not an I2F per sample
-    uint32_t s_tf_adj = (uint32_t)__cvta_generic_to_shared(s_tf) - MRT_TF_ADJ;
+    uint32_t s_tf_adj = (uint32_t)__cvta_generic_to_shared(s_tf) - 0x4b000000u * tf_stride;
     asm volatile("" : "+r"(s_tf_adj));         // opaque: keep the address in a register, do not re-derive it per sample
+    uint32_t s_tf_stride = tf_stride;
+    asm volatile("" : "+r"(s_tf_stride));
     // sample slot k sits at index-space position so + k*sd  (t_k = t0 + k*dt folded into the ray: one
     // fma per axis; the look-ups of phase 1 use the same expression, so skipping stays exact)
     float sox = fmaf(ray.t0, q.dx, q.ox), soy = fmaf(ray.t0, q.dy, q.oy), soz = fmaf(ray.t0, q.dz, q.oz);
@@ -155,7 +158,7 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       // alpha = 1 - e, e = exp(-sigma dt) (:137); C += alpha T rgb, T *= 1 - alpha (:138-139) as
       // T' = T e, alpha T = T - T'  (same quantities, two instructions less)
       if (TFM) {
-        const float4 rgba = mrt_tf_lookup_adj(s_tf_adj, nm1, val);
+        const float4 rgba = mrt_tf_lookup_strided(s_tf_adj, s_tf_stride, nm1, val);
         const float e = mrt_ex2(rgba.w * P.neg_dt_log2e);
         const float Tn = T * (on ? e : 1.0f);
         const float aT = T - Tn;
@@ -376,7 +379,7 @@ static cudaError_t launch_fwd(const KParams& P, const CamBatch& B, const StripTa
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = (ntiles + MRT_FWD_TPB - 1) / MRT_FWD_TPB;
-  const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * sizeof(TfEntry) + 16 * sizeof(float4);
+  const size_t smem = (size_t)(P.tfMode ? P.tfN : 0) * (P.tfN <= 512 ? 48 : 32) + 16 * sizeof(float4);
   mrt_fwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF, CKPT><<<dim3(grid, nviews), 64 * MRT_FWD_TPB, smem, st>>>(
       P, B, S, CK, (const typename VoxT<NCH, HALF>::T*)vol, (const float4*)tf, levels, labels, preds,
       (float4*)out_rgba, out_T, (int4*)out_counts);

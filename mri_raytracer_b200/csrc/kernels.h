@@ -22,6 +22,10 @@ cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nview
                                   cudaStream_t st);
 cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st);
 
+// staged-brick (TMA + shared memory) variant of the single-view march, forward_tma.cu
+cudaError_t mrt_launch_forward_tma(const KParams& P, int box_edge, int tile, const void* vol, const float* tf,
+                                   const uint8_t* levels, float* out_rgba, void* stats, cudaStream_t st);
+
 cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                     const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                     float* out_rgba, float* ck, int seg_slots, int nseg, int32_t* k_end, int32_t* warp_kmax,

@@ -529,6 +529,34 @@ __device__ __forceinline__ float4 mrt_tf_lookup_adj(uint32_t s_tf_adj, float nm1
   return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
 }
 
+// The march's LUT in shared memory with a 48-byte entry stride (base at +0, delta at +16, 16 B pad):
+// entry j starts in 16-byte bank group 3j mod 8, so eight consecutive entries fall into eight
+// different groups (32-byte entries only ever use every other group: ncu, shared wavefronts per
+// look-up) — the bank spread of a structure-of-arrays layout while the delta stays at an immediate
+// offset of the base.  Falls back to 32 bytes for LUTs whose padded copy would cost occupancy.
+// `adj` = base address - 0x4b000000 * stride (mod 2^32), so the entry address is ONE multiply-add of
+// the magic-number bits of floor(u).
+__device__ __forceinline__ uint32_t mrt_tf_stride(int N) { return N <= 512 ? 48u : 32u; }
+__device__ __forceinline__ void mrt_tf_stage_strided(unsigned char* __restrict__ s, uint32_t stride,
+                                                     const float4* __restrict__ tf, int N) {
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 a = __ldg(tf + i), b = __ldg(tf + min(i + 1, N - 1));
+    float4* e = reinterpret_cast<float4*>(s + (size_t)i * stride);
+    e[0] = a;
+    e[1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
+  }
+}
+__device__ __forceinline__ float4 mrt_tf_lookup_strided(uint32_t adj, uint32_t stride, float nm1, float val) {
+  const float u = val * nm1;
+  const float mu = __fadd_rd(u, 8388608.0f);
+  const float fr = u - (mu - 8388608.0f);
+  const uint32_t ea = __float_as_uint(mu) * stride + adj;
+  float4 a, d;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%8];\n\tld.shared.v4.f32 {%4,%5,%6,%7}, [%8+16];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "r"(ea));
+  return make_float4(fmaf(fr, d.x, a.x), fmaf(fr, d.y, a.y), fmaf(fr, d.z, a.z), fmaf(fr, d.w, a.w));
+}
+
 // CTA index -> position in the launch's tile range, "middle-out": CTA 0 takes the middle of the
 // range and successive CTAs alternate outward.  The tile ids of a frame are row-major, so the
 // rows through the image centre — where the camera frames the volume and rays are longest —

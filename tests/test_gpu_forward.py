@@ -424,6 +424,28 @@ def test_quad_layout_is_bit_identical_to_the_scalar_layout(cuda, C, ortho, use_t
         assert torch.equal(api.render(Vq, None, tfd, P2), api.render(Vs, None, tfd, P2))
 
 
+@pytest.mark.parametrize("box_edge,tile", [(8, 8), (16, 8), (8, 16), (16, 16)])
+@pytest.mark.parametrize("ortho,use_tf", [(False, True), (True, True), (False, False)])
+def test_staged_brick_tma_variant_renders_the_same_image(cuda, box_edge, tile, ortho, use_tf):
+    """mrt_render_forward_tma (boxes staged through shared memory by 3-D TMA loads) against the direct
+    gathers of mrt_render_forward: the same sampler arithmetic on the same voxels, so the images agree
+    to fp32 contraction noise; nearly every slot must really come from the staged boxes."""
+    vol, _, P = small_scene(C=1, dims=(60, 52, 44), W=88, H=72, seed=31, ortho=ortho)
+    P = replace(P, tfMode=int(use_tf), intensityAlpha=8.0, bgColor=(0.05, 0.0, 0.1), alphaMode=1)
+    tfd = ramp_tf(64, sigma_scale=20.0, cutoff=0.1).cuda() if use_tf else None
+    V = api.Volume(vol.cuda(), quad=False)
+    packed, Cn, Pe = V.prepared(P)
+    bits = V.skip_levels(P, tfd)
+    ref = api.render_forward(Pe, packed, Cn, tfd, bits)
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    img = api.render_forward_tma(Pe, packed, tfd, bits, box_edge=box_edge, tile=tile, stats=stats)
+    d = (img - ref).abs().amax(-1)
+    assert float(d.max()) <= 2e-6, float(d.max())
+    staged, direct, boxes, overflow = (int(x) for x in stats.tolist())
+    assert staged > 0 and boxes > 0 and overflow == 0
+    assert direct <= 0.02 * staged, (staged, direct)
+
+
 def test_bad_arguments_raise(cuda):
     vol, _, P = small_scene(C=1, dims=(16, 16, 16), W=16, H=16)
     V = api.Volume(vol.cuda())
