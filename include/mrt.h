@@ -209,6 +209,11 @@ int mrt_unfold_grad_f32(const MrtParams* params, const float* dfolded, int32_t C
  * volume: `minmax` is float2[mrt_brick_count] of the FOLDED field.  Same outputs, bit for bit. */
 int mrt_fold_volume_occupancy_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
                                   float* minmax, void* stream);
+/* The same pass writing the march's quad layout (mrt_pack_volume_quad) directly: `quad`
+ * (mrt_packed_volume_bytes_quad bytes) and `minmax` are filled; the scalar folded volume only when
+ * `folded` is non-NULL.  One launch instead of fold+occupancy followed by the quad pack. */
+int mrt_fold_volume_occupancy_quad_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
+                                       void* quad, float* minmax, void* stream);
 
 /* ------------------------------------------------ occupancy brick grid
  * (new relative to the reference; must never change the image.)

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "mrt_build_occupancy_u8": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_fold_volume_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
     "mrt_fold_volume_occupancy_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp, _vp]),
+    "mrt_fold_volume_occupancy_quad_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mrt_unfold_grad_f32": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
     "mrt_brick_count": (_i32, [_i32, _i32, _i32]),
     "mrt_skip_levels_bytes": (_sz, [_i32, _i32, _i32]),

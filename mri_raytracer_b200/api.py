@@ -448,6 +448,24 @@ def fold_volume_occupancy(planar: torch.Tensor, P: RenderParams) -> Tuple[torch.
     return folded, mm
 
 
+def fold_volume_occupancy_quad(planar: torch.Tensor, P: RenderParams, quad: Optional[torch.Tensor] = None,
+                               minmax: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fold + occupancy + the march's quad layout in ONE pass (``mrt_fold_volume_occupancy_quad_f32``):
+    -> (quad buffer for ``volDtype=3``, minmax float32 [nbricks,1,2]); no scalar folded volume is written.
+    ``quad`` / ``minmax``: buffers of an earlier call to reuse."""
+    _need_cuda(planar, "volume", torch.float32)
+    Cn, Z, Y, X = planar.shape
+    nbytes = lib().mrt_packed_volume_bytes_quad(X, Y, Z)
+    if quad is None or quad.numel() * quad.element_size() != nbytes:
+        quad = torch.empty((nbytes // 4,), dtype=torch.float32, device=planar.device)
+    if minmax is None:
+        minmax = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=planar.device)
+    s = (P if (tuple(P.dims) == (X, Y, Z) and P.shard is None) else replace(P, dims=(X, Y, Z), shard=None)).to_struct()
+    check(lib().mrt_fold_volume_occupancy_quad_f32(C.byref(s), planar.data_ptr(), Cn, None, quad.data_ptr(), minmax.data_ptr(),
+                                                   _stream()), "fold_volume_occupancy_quad")
+    return quad, minmax
+
+
 def unfold_grad(dfolded: torch.Tensor, P: RenderParams, Cn: int) -> torch.Tensor:
     X, Y, Z = P.dims
     out = torch.empty((Cn, Z, Y, X), dtype=torch.float32, device=dfolded.device)
@@ -527,7 +545,7 @@ class Volume:
             raise ValueError("the quad layout needs a single-channel fp32 sampler (C == 1 or fold=True)")
         self.quad = single if quad is None else bool(quad)
         self._quad_buf = None
-        self._quad_src = None
+        self._quad_ok = False
         from .synth import world_box
         self.voxel_size, self.vol_min = world_box(self.global_dims, zooms)
         self._bits = None
@@ -539,24 +557,30 @@ class Volume:
             P = replace(P, shard=self.shard)
         if self.half or self.u8:
             P = replace(P, volDtype=1 if self.half else 2)
+        overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
+        want_quad = self.quad and not overlays
         if self.fold:
             key = _fold_key(P, self.C)
-            if key != self._key:
+            if key != self._key:                       # weights changed: every cached layout is stale
+                self.packed, self._quad_ok, self._key = None, False, key
+            Pf = folded_params(P)                      # how the folded field is rendered; P still holds the blend weights
+            if want_quad and self.occupancy:           # one pass: fold + occupancy + quad layout, no scalar copy
+                if not self._quad_ok:
+                    self._quad_buf, self.minmax = fold_volume_occupancy_quad(self.planar, P, self._quad_buf, self.minmax)
+                    self._quad_ok = True
+                return self._quad_buf, 1, replace(Pf, volDtype=3)
+            if self.packed is None:
                 if self.occupancy:
                     self.packed, self.minmax = fold_volume_occupancy(self.planar, P)
                 else:
                     self.packed, self.minmax = fold_volume(self.planar, P), None
-                self._key = key
-                self._quad_src = None
-            P = folded_params(P)
-        Cn = 1 if self.fold else self.C
-        overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
-        if self.quad and not overlays:
-            if self._quad_src is not self.packed:
+            P = Pf
+        if want_quad:
+            if not self._quad_ok:
                 self._quad_buf = pack_volume_quad(self.packed, self.dims, out=self._quad_buf)
-                self._quad_src = self.packed
+                self._quad_ok = True
             return self._quad_buf, 1, replace(P, volDtype=3)
-        return self.packed, Cn, P
+        return self.packed, (1 if self.fold else self.C), P
 
     def invalidate(self):
         """Drop the folded-volume cache (the next frame re-folds and rebuilds the occupancy grid)."""

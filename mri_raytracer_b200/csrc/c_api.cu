@@ -271,6 +271,19 @@ int mrt_fold_volume_f32(const MrtParams* params, const float* planar, int32_t C,
   cudaError_t e = mrt_launch_fold(planar, C, X, Y, Z, wgt, inv_wsum, folded, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fold_volume");
 }
+int mrt_fold_volume_occupancy_quad_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
+                                       void* quad, float* minmax, void* stream) {
+  MRT_REQUIRE(params && planar && quad && minmax, "fold_volume_occupancy_quad: null pointer");
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("fold_volume_occupancy_quad", C, X, Y, Z)) return r;
+  int64_t qY, qZ;
+  mrt_layout_e(1, 16, X, Y, Z, &qY, &qZ);
+  MRT_REQUIRE((uint64_t)qZ * (uint64_t)Z < (1ull << 32), "fold_volume_occupancy_quad: more than 2^32 elements");
+  float wgt[4], inv_wsum;
+  blend_weights(params, C, wgt, &inv_wsum);
+  cudaError_t e = mrt_launch_fold_occ_quad(planar, C, X, Y, Z, wgt, inv_wsum, folded, quad, minmax, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fold_volume_occupancy_quad");
+}
 int mrt_fold_volume_occupancy_f32(const MrtParams* params, const float* planar, int32_t C, float* folded,
                                   float* minmax, void* stream) {
   MRT_REQUIRE(params && planar && folded && minmax, "fold_volume_occupancy: null pointer");

@@ -97,10 +97,13 @@ const char* mrt_host_pipeline_error(const MrtHostPipeline* p) { return p ? p->er
 #define HP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(p->err, sizeof(p->err), "%s: %s", #call, cudaGetErrorString(e_)); rc = MRT_ERR_CUDA; goto fail; } } while (0)
 
-// the march samples from the 16 B/voxel quad layout (mrt_pack_volume_quad) unless MRT_HP_QUAD=0
+// MRT_HP_QUAD=1: the march samples from the 16 B/voxel quad layout (mrt_pack_volume_quad).  Off by
+// default HERE: this pipeline's march stores straight into host memory and is bound by those PCIe
+// writes, so the faster sampler buys nothing and building the 4x larger layout costs a little
+// (measured 0.945 vs 0.918 ms per 8-view step); the device-resident paths (api.Volume) default to it.
 static bool hp_use_quad() {
   static const char* env = getenv("MRT_HP_QUAD");
-  return !(env && env[0] == '0');
+  return env && env[0] == '1';
 }
 
 int mrt_host_pipeline_create(MrtHostPipeline** out, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t W, int32_t H,
@@ -126,7 +129,16 @@ int mrt_host_pipeline_create(MrtHostPipeline** out, int32_t C, int32_t X, int32_
   p->tiles_y = mrt_tiles_y_(H);
   for (int i = 0; i < depth; ++i) p->slot[i].ticket = -1;
   HP_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
-  HP_CUDA(cudaStreamCreateWithFlags(&p->s_prep, cudaStreamNonBlocking));
+  {
+    // the prepare stage of step i+1 (fold, occupancy, classify, spans: short kernels) must not queue
+    // behind the 65k-CTA march of step i: highest priority, so its CTAs take the SM slots the march
+    // frees as it drains (MRT_HP_PRIO=0 switches this off)
+    int lo_p = 0, hi_p = 0;
+    static const char* env = getenv("MRT_HP_PRIO");
+    const bool prio = !(env && env[0] == '0');
+    HP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    HP_CUDA(cudaStreamCreateWithPriority(&p->s_prep, cudaStreamNonBlocking, prio ? hi_p : lo_p));
+  }
   HP_CUDA(cudaStreamCreateWithFlags(&p->s_cmp, cudaStreamNonBlocking));
   HP_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
   HP_CUDA(cudaEventCreateWithFlags(&p->e_resident, cudaEventDisableTiming));
@@ -247,8 +259,12 @@ int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const 
     const bool skip = P.skipEmpty && P.tMode == 0;
     const bool sparse = skip && P.gamma == 1.0f;            // the span path (cull + sparse download)
     int Ce = p->C;
-    if (p->C > 1) {                    // modality fold (+ occupancy of the folded field in the same pass)
-      if (skip) rc = mrt_fold_volume_occupancy_f32(&P, d_planar, p->C, (float*)s.d_packed, s.d_minmax, p->s_prep);
+    bool quad_done = false;
+    if (p->C > 1) {                    // modality fold (+ occupancy of the folded field, + the quad layout, in the same pass)
+      if (skip && s.d_quad) {
+        rc = mrt_fold_volume_occupancy_quad_f32(&P, d_planar, p->C, nullptr, s.d_quad, s.d_minmax, p->s_prep);
+        quad_done = true;
+      } else if (skip) rc = mrt_fold_volume_occupancy_f32(&P, d_planar, p->C, (float*)s.d_packed, s.d_minmax, p->s_prep);
       else rc = mrt_fold_volume_f32(&P, d_planar, p->C, (float*)s.d_packed, p->s_prep);
       P.volEnabled[0] = 1; P.volEnabled[1] = P.volEnabled[2] = P.volEnabled[3] = 0;
       P.volWeight[0] = 1.0f;
@@ -261,7 +277,7 @@ int mrt_host_pipeline_submit(MrtHostPipeline* p, const MrtParams* params, const 
       rc = mrt_classify_bricks(&P, s.d_minmax, Ce, s.d_tf, tfN, nullptr, nullptr, s.d_levels, 0, p->s_prep);
     const void* d_sampler = s.d_packed;
     if (rc == MRT_OK && s.d_quad) {      // two 16-byte loads per sample instead of eight scalar ones; same image
-      rc = mrt_pack_volume_quad((const float*)s.d_packed, p->X, p->Y, p->Z, s.d_quad, p->s_prep);
+      if (!quad_done) rc = mrt_pack_volume_quad((const float*)s.d_packed, p->X, p->Y, p->Z, s.d_quad, p->s_prep);
       d_sampler = s.d_quad;
     }
     const size_t span_bytes = (size_t)nviews * p->tiles_y * 2 * sizeof(int32_t);

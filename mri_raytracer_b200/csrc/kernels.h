@@ -65,6 +65,8 @@ cudaError_t mrt_launch_fold(const float* planar, int C, int X, int Y, int Z, con
                             float* folded, cudaStream_t st);
 cudaError_t mrt_launch_fold_occ(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
                                 float* folded, float* minmax, cudaStream_t st);
+cudaError_t mrt_launch_fold_occ_quad(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                                     float* folded, void* quad, float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_unfold_grad(const float* dfolded, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
                                    float* dplanar, cudaStream_t st);
 

@@ -218,6 +218,90 @@ _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
     minmax[((size_t)bz * nby + by) * nbx + bx] = make_float2(a, b);
   }
 }
+// Fold + occupancy + QUAD layout in one pass: as above, but the blended value goes straight into
+// the march's 16 B/voxel quad layout (element (x,y,z) = v(x,y), v(x+1,y), v(x,y+1), v(x+1,y+1) of slice
+// z; march.cuh VoxT<1,3>) — the scalar folded volume is only written when `folded` is non-null.  The
+// x+1 neighbour comes from the next lane (the last lane of a warp re-blends it: L1 hits on the loads
+// its neighbour warp issues anyway), the y+1 row is the next iteration of the scanline loop.
+template <int C>
+__global__ void __launch_bounds__(256)
+mrt_fold_occ_quad_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
+                         size_t qY, size_t qZ, float w0, float w1, float w2, float w3, float inv_wsum, int nbx, int nby,
+                         float* __restrict__ folded, float4* __restrict__ quad, float2* __restrict__ minmax) {
+  __shared__ float s_mn[256], s_mx[256];
+  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const int chunk = blockIdx.x % chunks, by = (blockIdx.x / chunks) % nby, bz = blockIdx.x / (chunks * nby);
+  const int x0 = chunk * MRT_FOLD_COLS;
+  const int x = x0 + threadIdx.x;
+  const bool rd = (threadIdx.x <= MRT_FOLD_COLS) && (x < X);
+  const bool wr = rd && (threadIdx.x < MRT_FOLD_COLS);
+  const int lane = threadIdx.x & 31;
+  const int xn = min(x + 1, X - 1);                      // clamped neighbour column
+  const size_t nvox = (size_t)X * Y * Z;
+  const int y0 = by << 3, z0 = bz << 3;
+  const int ny = min(9, Y - y0), nz = min(9, Z - z0);
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  auto blend = [&](size_t src) {
+    float v = __ldg(planar + src) * w0;
+    if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
+    if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
+    if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
+    return v * inv_wsum;
+  };
+  for (int lz = 0; lz < nz; ++lz) {
+    const int z = z0 + lz;
+    float pv = 0.0f, pn = 0.0f;                          // previous scanline: v(x, y-1), v(x+1, y-1)
+_Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
+    for (int ly = 0; ly < ny; ++ly) {
+      const int y = y0 + ly;
+      const size_t row = ((size_t)z * Y + y) * X;
+      float v = 0.0f;
+      if (rd) {
+        v = blend(row + x);
+        if (wr && folded && ly < 8 && lz < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+      }
+      float vn = __shfl_down_sync(0xffffffffu, v, 1);
+      if (lane == 31 && wr) vn = blend(row + xn);       // (a storing thread always has its neighbour column in range or clamped)
+      if (x + 1 >= X) vn = v;
+      if (wr && lz < 8) {
+        if (ly > 0) quad[(size_t)x + (size_t)(y - 1) * qY + (size_t)z * qZ] = make_float4(pv, pn, v, vn);
+        if (ly == ny - 1 && ny < 9) quad[(size_t)x + (size_t)y * qY + (size_t)z * qZ] = make_float4(v, vn, v, vn);   // y == Y-1
+      }
+      pv = v; pn = vn;
+    }
+  }
+  s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
+  __syncthreads();
+  const int bxl = threadIdx.x;
+  const int bx = chunk * (MRT_FOLD_COLS >> 3) + bxl;
+  if (bxl < (MRT_FOLD_COLS >> 3) && bx < nbx) {
+    float a = FLT_MAX, b = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i <= 8; ++i) { a = fminf(a, s_mn[(bxl << 3) + i]); b = fmaxf(b, s_mx[(bxl << 3) + i]); }
+    minmax[((size_t)bz * nby + by) * nbx + bx] = make_float2(a, b);
+  }
+}
+cudaError_t mrt_launch_fold_occ_quad(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
+                                     float* folded, void* quad, float* minmax, cudaStream_t st) {
+  int64_t pY, pZ, qY, qZ;
+  mrt_layout(1, X, Y, Z, &pY, &pZ);
+  mrt_layout_e(1, 16, X, Y, Z, &qY, &qZ);
+  const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
+  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const long long grid = (long long)chunks * nby * nbz;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+#define MRT_FQ(CC) mrt_fold_occ_quad_kernel<CC><<<(int)grid, 256, 0, st>>>(planar, X, Y, Z, pY, pZ, qY, qZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, nbx, nby, folded, (float4*)quad, (float2*)minmax)
+  switch (C) {
+    case 1: MRT_FQ(1); break;
+    case 2: MRT_FQ(2); break;
+    case 3: MRT_FQ(3); break;
+    case 4: MRT_FQ(4); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef MRT_FQ
+  return cudaGetLastError();
+}
 cudaError_t mrt_launch_fold_occ(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
                                 float* folded, float* minmax, cudaStream_t st) {
   int64_t pY, pZ;
