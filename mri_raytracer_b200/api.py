@@ -30,7 +30,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # (torch.cuda.current_stream() builds a Stream object through three Python layers: ~3 us a call,
+    # several calls per frame)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _need_cuda(t: torch.Tensor, name: str, dtype=None):
@@ -554,21 +556,23 @@ class Volume:
     def prepared(self, P: RenderParams):
         """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
         if self.shard is not None:
-            P = replace(P, shard=self.shard)
+            shard = self.shard
+            P = P.derived(("shard", shard), lambda p: replace(p, shard=shard))
         if self.half or self.u8:
-            P = replace(P, volDtype=1 if self.half else 2)
+            vd = 1 if self.half else 2
+            P = P.derived(("voldtype", vd), lambda p: replace(p, volDtype=vd))
         overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
         want_quad = self.quad and not overlays
         if self.fold:
             key = _fold_key(P, self.C)
             if key != self._key:                       # weights changed: every cached layout is stale
                 self.packed, self._quad_ok, self._key = None, False, key
-            Pf = folded_params(P)                      # how the folded field is rendered; P still holds the blend weights
+            Pf = P.derived("folded", folded_params)    # how the folded field is rendered; P still holds the blend weights
             if want_quad and self.occupancy:           # one pass: fold + occupancy + quad layout, no scalar copy
                 if not self._quad_ok:
                     self._quad_buf, self.minmax = fold_volume_occupancy_quad(self.planar, P, self._quad_buf, self.minmax)
                     self._quad_ok = True
-                return self._quad_buf, 1, replace(Pf, volDtype=3)
+                return self._quad_buf, 1, Pf.derived("quad", lambda p: replace(p, volDtype=3))
             if self.packed is None:
                 if self.occupancy:
                     self.packed, self.minmax = fold_volume_occupancy(self.planar, P)
@@ -579,7 +583,7 @@ class Volume:
             if not self._quad_ok:
                 self._quad_buf = pack_volume_quad(self.packed, self.dims, out=self._quad_buf)
                 self._quad_ok = True
-            return self._quad_buf, 1, replace(P, volDtype=3)
+            return self._quad_buf, 1, P.derived("quad", lambda p: replace(p, volDtype=3))
         return self.packed, (1 if self.fold else self.C), P
 
     def invalidate(self):
@@ -646,7 +650,7 @@ class Volume:
                       out_counts: Optional[torch.Tensor] = None,
                       tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """classify ONCE (the skip levels do not depend on the camera) + one batched march."""
-        P = P.with_camera(cams[0])                     # projection (fov / ortho window) of the batch
+        P = P.with_projection_of(cams[0])              # projection (fov / ortho window) of the batch
         packed, Cn, Pe = self.prepared(P)
         bits = self._classify(P, Pe, Cn, tf)
         return self.march_batch(Pe, cams, packed, Cn, tf, bits, out=out, out_T=out_T, out_counts=out_counts,
@@ -679,7 +683,7 @@ class Volume:
     def sparse_plan(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor]):
         """Prepare a sparse batched march: -> (packed, Cn, Pe, skip_levels) or None if this
         configuration cannot use it (no occupancy grid / skipping off / gamma != 1 / overlays)."""
-        P = P.with_camera(cams[0])
+        P = P.with_projection_of(cams[0])
         if (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred) or P.gamma != 1.0:
             return None
         packed, Cn, Pe = self.prepared(P)
@@ -882,7 +886,8 @@ def render_views(volume: Union[torch.Tensor, Volume], cams: Sequence, tf: Option
         _need_cuda(tf, "tf", torch.float32)
         if tf.dim() != 2 or tf.shape[1] != 4 or not (2 <= tf.shape[0] <= _lib.MRT_MAX_TF):
             raise ValueError(f"tf must be [N,4] with 2 <= N <= {_lib.MRT_MAX_TF}, got {tuple(tf.shape)}")
-    P = replace(params, tfMode=1 if tf is not None else 0)
+    tfm = 1 if tf is not None else 0
+    P = params if params.tfMode == tfm else params.derived(("tfmode", tfm), lambda p: replace(p, tfMode=tfm))
     if isinstance(volume, torch.Tensor):
         # differentiable w.r.t. the volume tensor and the TF: one checkpointing march + one
         # segment-parallel backward launch for the whole batch (a multi-view training step)

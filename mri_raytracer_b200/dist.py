@@ -208,7 +208,8 @@ class PeerFramebuffer:
         W, H = P.imageSize
         if (W, H) != (self.W, self.H):
             raise ValueError("imageSize does not match the framebuffer")
-        Pm = replace(P, tfMode=1 if tf is not None else 0)
+        tfm = 1 if tf is not None else 0
+        Pm = P if P.tfMode == tfm else P.derived(("tfmode", tfm), lambda p: replace(p, tfMode=tfm))
         R, r = self.R, self.rank
         if not self.p2p:
             self.full.zero_()

@@ -82,9 +82,25 @@ class RenderParams:
     volDtype: int = 0           # 0 fp32 voxels, 1 fp16 single-channel (set by api.Volume)
 
     def __setattr__(self, k, v):
-        object.__setattr__(self, k, v)
-        if k != "_struct":
-            self.__dict__.pop("_struct", None)       # the packed C struct is cached per instance
+        d = self.__dict__
+        d[k] = v
+        if "_struct" in d or "_derived" in d:        # the packed C struct and derived copies are cached per instance
+            d.pop("_struct", None)
+            d.pop("_derived", None)
+
+    def derived(self, key, make):
+        """Memoised derived copy (``make(self)``), dropped when any field of this instance changes:
+        a frame loop that re-submits the same parameter block does not pay ``dataclasses.replace``
+        (34 fields, ~6 us each time) several times per frame."""
+        cache = self.__dict__.get("_derived")
+        if cache is None:
+            cache = {}
+            self.__dict__["_derived"] = cache
+        out = cache.get(key)
+        if out is None:
+            out = make(self)
+            cache[key] = out
+        return out
 
     def validate(self):
         W, H = self.imageSize
@@ -100,6 +116,14 @@ class RenderParams:
             raise ValueError(f"tMode {self.tMode!r} unknown")
         if np.asarray(self.lutColorAlpha).shape != (8, 4):
             raise ValueError("lutColorAlpha must be [8,4]")
+
+    def with_projection_of(self, cam) -> "RenderParams":
+        """For batched launches (the cameras travel separately): ``self`` if its projection already is
+        the camera's, else :meth:`with_camera`."""
+        proj = (float(cam.fovY), int(cam.ortho), float(cam.ortho_half_height))
+        if (float(self.fovY), int(self.ortho), float(self.orthoHalfHeight)) == proj:
+            return self
+        return self.derived(("projection", proj), lambda p: replace(p, fovY=proj[0], ortho=proj[1], orthoHalfHeight=proj[2]))
 
     def with_camera(self, cam) -> "RenderParams":
         """Copy with eye/U/V/W/fov/ortho taken from a :class:`camera.Camera`."""
