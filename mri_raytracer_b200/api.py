@@ -417,7 +417,7 @@ def ray_gradients(volume: "Volume", camera: Optional[Camera], tf: Optional[torch
     P = params if camera is None else params.with_camera(camera)
     P = replace(P, tfMode=1 if tf is not None else 0)
     _need_cuda(dL_dout, "dL_dout", torch.float32)
-    packed, Cn, Pe = volume.prepared(P)
+    packed, Cn, Pe = volume.prepared(P, quad=False)             # the backward reads the scalar layout
     out = render_forward(Pe, packed, Cn, tf, volume._classify(P, Pe, Cn, tf), volume.labels, volume.preds)
     _, _, dray = render_backward(Pe, packed, Cn, tf, volume.labels, volume.preds, out, dL_dout.contiguous(),
                                  want_dvol=False, want_dtf=False, want_dray=True)
@@ -553,8 +553,9 @@ class Volume:
         self._bits = None
         self._spans = None
 
-    def prepared(self, P: RenderParams):
-        """-> (sampler buffer, channel count, params) to hand to ``render_forward``."""
+    def prepared(self, P: RenderParams, quad: Optional[bool] = None):
+        """-> (sampler buffer, channel count, params) to hand to ``render_forward``.  ``quad=False``
+        forces the scalar layout (the backward kernels read that one)."""
         if self.shard is not None:
             shard = self.shard
             P = P.derived(("shard", shard), lambda p: replace(p, shard=shard))
@@ -562,7 +563,7 @@ class Volume:
             vd = 1 if self.half else 2
             P = P.derived(("voldtype", vd), lambda p: replace(p, volDtype=vd))
         overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
-        want_quad = self.quad and not overlays
+        want_quad = (self.quad if quad is None else (quad and self.quad)) and not overlays
         if self.fold:
             key = _fold_key(P, self.C)
             if key != self._key:                       # weights changed: every cached layout is stale

@@ -191,20 +191,33 @@ mrt_fold_occ_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_
   const int ny = min(9, Y - y0), nz = min(9, Z - z0);
   float mn = FLT_MAX, mx = -FLT_MAX;
   if (rd) {
-    for (int lz = 0; lz < nz; ++lz) {
-      const int z = z0 + lz;
+    auto blend = [&](size_t src) {
+      float v = __ldg(planar + src) * w0;
+      if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
+      if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
+      if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
+      return v * inv_wsum;
+    };
+    // SL slices per trip: all their loads are issued before the first dependent store, so a thread
+    // keeps 9 * SL * C loads in flight (one channel with SL = 1 ran at a third of the HBM rate)
+    constexpr int SL = C == 1 ? 3 : (C == 2 ? 2 : 1);
+    for (int lz = 0; lz < nz; lz += SL) {
+      float v[SL][9];
+#pragma unroll
+      for (int s = 0; s < SL; ++s)
 _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
-      for (int ly = 0; ly < ny; ++ly) {
-        const int y = y0 + ly;
-        const size_t src = ((size_t)z * Y + y) * X + x;
-        float v = __ldg(planar + src) * w0;
-        if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
-        if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
-        if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
-        v *= inv_wsum;
-        if (wr && ly < 8 && lz < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v;
-        mn = fminf(mn, v); mx = fmaxf(mx, v);
-      }
+        for (int ly = 0; ly < 9; ++ly)
+          v[s][ly] = (lz + s < nz && ly < ny) ? blend(((size_t)(z0 + lz + s) * Y + (y0 + ly)) * X + x) : 0.0f;
+#pragma unroll
+      for (int s = 0; s < SL; ++s)
+_Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
+        for (int ly = 0; ly < 9; ++ly) {
+          if (lz + s < nz && ly < ny) {
+            const int y = y0 + ly, z = z0 + lz + s;
+            if (wr && ly < 8 && lz + s < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v[s][ly];
+            mn = fminf(mn, v[s][ly]); mx = fmaxf(mx, v[s][ly]);
+          }
+        }
     }
   }
   s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
@@ -338,6 +351,37 @@ mrt_unfold_grad_kernel(const float* __restrict__ dfolded, int C, int X, int Y, i
     }
   }
 }
+// the same with 16-byte accesses and four independent rows-chunks in flight per thread (X % 4 == 0):
+// the scalar kernel keeps one 4-byte load in flight per thread and runs at a third of the HBM rate
+__global__ void __launch_bounds__(256)
+mrt_unfold_grad_v4_kernel(const float* __restrict__ dfolded, int C, int X4, int Y, int Z, size_t pitchY, size_t pitchZ,
+                          float w0, float w1, float w2, float w3, float inv_wsum, float* __restrict__ dplanar) {
+  const size_t nvox4 = (size_t)X4 * Y * Z;
+  const size_t total = nvox4, stride = (size_t)gridDim.x * blockDim.x;
+  const float w[4] = {w0 * inv_wsum, w1 * inv_wsum, w2 * inv_wsum, w3 * inv_wsum};
+  float4* out = reinterpret_cast<float4*>(dplanar);
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < total) {
+        const size_t row = i / X4; const int x4 = (int)(i - row * X4);
+        const int y = (int)(row % Y), z = (int)(row / Y);
+        g[u] = __ldg(reinterpret_cast<const float4*>(dfolded + (size_t)y * pitchY + (size_t)z * pitchZ) + x4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < total) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < C) out[(size_t)c * nvox4 + i] = make_float4(g[u].x * w[c], g[u].y * w[c], g[u].z * w[c], g[u].w * w[c]);
+      }
+    }
+  }
+}
 cudaError_t mrt_launch_fold(const float* planar, int C, int X, int Y, int Z, const float* wgt, float inv_wsum,
                             float* folded, cudaStream_t st) {
   int64_t pY, pZ;
@@ -353,6 +397,15 @@ cudaError_t mrt_launch_unfold_grad(const float* dfolded, int C, int X, int Y, in
   mrt_layout(1, X, Y, Z, &pY, &pZ);
   const int g = grid_for((size_t)Y * Z * 256, 256);
   const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  if ((X & 3) == 0 && (pY & 3) == 0 && (pZ & 3) == 0 && (((uintptr_t)dfolded | (uintptr_t)dplanar) & 15) == 0 &&
+      (((size_t)X * Y * Z) & 3) == 0) {
+    const size_t n4 = (size_t)X / 4 * Y * Z;
+    size_t g4 = (n4 + 4 * 256 - 1) / (4 * 256);
+    if (g4 > 148 * 32) g4 = 148 * 32;
+    mrt_unfold_grad_v4_kernel<<<(int)(g4 ? g4 : 1), 256, 0, st>>>(dfolded, C, X / 4, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3],
+                                                                 inv_wsum, dplanar);
+    return cudaGetLastError();
+  }
   mrt_unfold_grad_kernel<<<g, blk, 0, st>>>(dfolded, C, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, dplanar);
   return cudaGetLastError();
 }
