@@ -97,7 +97,7 @@ typedef struct MrtParams {
    * Output is the partial (r,g,b premultiplied WITHOUT background, a = T_local) for
    * mrt_composite_over.  Early termination acts on the shard-local transmittance. */
   uint32_t shardEnabled; uint32_t shardLo[3]; uint32_t shardHi[3];
-  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16, 2: u8, 3: fp32 quads — single-channel (mrt_pack_volume_f16 / _u8 / _quad), forward only */
+  uint32_t volDtype;        /* 0: `packed` holds fp32 voxels; 1: fp16, 2: u8, 3: fp32 quads, 4: fp16 quads — single-channel (mrt_pack_volume_f16 / _u8 / _quad / _quad_f16), forward only */
 } MrtParams;
 
 /* One camera of a batch of views: the four camera rows of `struct Params`
@@ -194,6 +194,10 @@ int mrt_build_occupancy_u8(const void* packed, int32_t X, int32_t Y, int32_t Z, 
  * Forward only. */
 size_t mrt_packed_volume_bytes_quad(int32_t X, int32_t Y, int32_t Z);
 int mrt_pack_volume_quad(const float* packed1, int32_t X, int32_t Y, int32_t Z, void* quad, void* stream);
+/* The same over fp16 voxels (8 B per element), from the packed fp16 layout of mrt_pack_volume_f16;
+ * params->volDtype = 4.  Bit-identical to volDtype 1. */
+size_t mrt_packed_volume_bytes_quad_f16(int32_t X, int32_t Y, int32_t Z);
+int mrt_pack_volume_quad_f16(const void* packed_f16, int32_t X, int32_t Y, int32_t Z, void* quad, void* stream);
 
 /* ------------------------------------------------ modality fold
  * The modality blend v = sum_c w_c s_c / wSum (brats_rt.slang:123-130) is linear and commutes

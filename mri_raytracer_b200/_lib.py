@@ -92,6 +92,8 @@ PROTOTYPES = {
     "mrt_unpack_volume_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_build_occupancy_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_render_forward_tma": (C.c_int, [C.POINTER(MrtParams), _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "mrt_packed_volume_bytes_quad_f16": (_sz, [_i32, _i32, _i32]),
+    "mrt_pack_volume_quad_f16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_packed_volume_bytes_quad": (_sz, [_i32, _i32, _i32]),
     "mrt_pack_volume_quad": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mrt_packed_volume_bytes_u8": (_sz, [_i32, _i32, _i32]),

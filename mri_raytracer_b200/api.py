@@ -103,6 +103,16 @@ def pack_volume_quad(packed1: torch.Tensor, dims, out: Optional[torch.Tensor] = 
     return out
 
 
+def pack_volume_quad_f16(packed_f16: torch.Tensor, dims, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """packed fp16 volume -> the quad layout over fp16 voxels (``mrt_pack_volume_quad_f16``; ``volDtype=4``)."""
+    X, Y, Z = (int(v) for v in dims)
+    nbytes = lib().mrt_packed_volume_bytes_quad_f16(X, Y, Z)
+    if out is None or out.numel() * out.element_size() != nbytes:
+        out = torch.empty((nbytes // 2,), dtype=torch.float16, device=packed_f16.device)
+    check(lib().mrt_pack_volume_quad_f16(packed_f16.data_ptr(), X, Y, Z, out.data_ptr(), _stream()), "pack_volume_quad_f16")
+    return out
+
+
 def build_occupancy_u8(packed: torch.Tensor, dims) -> torch.Tensor:
     X, Y, Z = dims
     mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=packed.device)
@@ -542,9 +552,9 @@ class Volume:
         self.labels = self.preds = self.seg_any = self.pred_any = None
         self.set_labels(labels)
         self.set_preds(preds)
-        single = (self.fold or self.C == 1) and not (self.half or self.u8)
+        single = (self.fold or self.C == 1) and not self.u8
         if quad and not single:
-            raise ValueError("the quad layout needs a single-channel fp32 sampler (C == 1 or fold=True)")
+            raise ValueError("the quad layout needs a single-channel fp32 / fp16 sampler (C == 1 or fold=True)")
         self.quad = single if quad is None else bool(quad)
         self._quad_buf = None
         self._quad_ok = False
@@ -559,7 +569,7 @@ class Volume:
         if self.shard is not None:
             shard = self.shard
             P = P.derived(("shard", shard), lambda p: replace(p, shard=shard))
-        if self.half or self.u8:
+        if self.u8 or (self.half and not self.quad):
             vd = 1 if self.half else 2
             P = P.derived(("voldtype", vd), lambda p: replace(p, volDtype=vd))
         overlays = (self.labels is not None and P.showSeg) or (self.preds is not None and P.showPred)
@@ -582,9 +592,12 @@ class Volume:
             P = Pf
         if want_quad:
             if not self._quad_ok:
-                self._quad_buf = pack_volume_quad(self.packed, self.dims, out=self._quad_buf)
+                self._quad_buf = (pack_volume_quad_f16 if self.half else pack_volume_quad)(self.packed, self.dims, out=self._quad_buf)
                 self._quad_ok = True
-            return self._quad_buf, 1, P.derived("quad", lambda p: replace(p, volDtype=3))
+            vq = 4 if self.half else 3
+            return self._quad_buf, 1, P.derived(("quad", vq), lambda p: replace(p, volDtype=vq))
+        if self.half and P.volDtype != 1:
+            P = P.derived(("voldtype", 1), lambda p: replace(p, volDtype=1))
         return self.packed, (1 if self.fold else self.C), P
 
     def invalidate(self):

@@ -132,6 +132,21 @@ int mrt_pack_volume_quad(const float* packed1, int32_t X, int32_t Y, int32_t Z, 
   cudaError_t e = mrt_launch_pack_quad(packed1, X, Y, Z, quad, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume_quad");
 }
+size_t mrt_packed_volume_bytes_quad_f16(int32_t X, int32_t Y, int32_t Z) {
+  if (X < 2 || Y < 2 || Z < 2) return 0;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 8, X, Y, Z, &pY, &pZ);
+  return (size_t)pZ * (size_t)Z * 8;
+}
+int mrt_pack_volume_quad_f16(const void* packed_f16, int32_t X, int32_t Y, int32_t Z, void* quad, void* stream) {
+  MRT_REQUIRE(packed_f16 && quad, "pack_volume_quad_f16: null pointer");
+  if (int r = check_dims_f16("pack_volume_quad_f16", X, Y, Z)) return r;
+  int64_t pY, pZ;
+  mrt_layout_e(1, 8, X, Y, Z, &pY, &pZ);
+  MRT_REQUIRE((uint64_t)pZ * (uint64_t)Z < (1ull << 32), "pack_volume_quad_f16: more than 2^32 elements");
+  cudaError_t e = mrt_launch_pack_quad_f16(packed_f16, X, Y, Z, quad, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "pack_volume_quad_f16");
+}
 static int check_dims_u8(const char* who, int X, int Y, int Z) {
   MRT_REQUIRE(X >= 2 && Y >= 2 && Z >= 2, "%s: dims (%d,%d,%d) must be >= 2 per axis", who, X, Y, Z);
   int64_t pY, pZ;
@@ -186,7 +201,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
     MRT_REQUIRE(!M->showSeg && !M->showPred, "label overlays are not supported on sharded volumes");
     MRT_REQUIRE(M->tMode == 0, "sharded volumes need indexed stepping (tMode 0)");
   }
-  MRT_REQUIRE(M->volDtype <= 3, "volDtype %u unknown (0 fp32, 1 fp16, 2 u8, 3 fp32 quad)", M->volDtype);
+  MRT_REQUIRE(M->volDtype <= 4, "volDtype %u unknown (0 fp32, 1 fp16, 2 u8, 3 fp32 quad, 4 fp16 quad)", M->volDtype);
   K->half = (int)M->volDtype;
   if (K->half) {
     MRT_REQUIRE(C == 1, "fp16 / u8 / quad volumes are single-channel (C=%d)", C);
@@ -194,7 +209,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   }
   {
     int64_t pY, pZ;
-    mrt_layout_e(mrt_packed_channels(C), K->half == 1 ? 2 : (K->half == 2 ? 1 : (K->half == 3 ? 16 : 4)), ldim[0], ldim[1], ldim[2], &pY, &pZ);
+    mrt_layout_e(mrt_packed_channels(C), K->half == 1 ? 2 : (K->half == 2 ? 1 : (K->half == 3 ? 16 : (K->half == 4 ? 8 : 4))), ldim[0], ldim[1], ldim[2], &pY, &pZ);
     MRT_REQUIRE((uint64_t)pZ * ldim[2] < (1ull << 32), "more than 2^32 voxels per shard (SURVEY Q14)");
     K->pitchY = (unsigned)pY; K->pitchZ = (unsigned)pZ;
     K->base_off = K->shard ? (unsigned)(K->slo[0] + K->slo[1] * pY + K->slo[2] * pZ) : 0u;

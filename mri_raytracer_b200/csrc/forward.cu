@@ -580,6 +580,7 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
                : launch_fwd<1, false, false, false, H>(P, B, S, nviews, vol, tf, levels, labels, preds, out_rgba, out_T, out_counts, st);
     if (P.half == 1) { MRT_NARROW(1) }
     if (P.half == 3) { MRT_NARROW(3) }
+    if (P.half == 4) { MRT_NARROW(4) }
     MRT_NARROW(2)
 #undef MRT_NARROW
   }

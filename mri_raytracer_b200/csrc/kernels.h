@@ -58,6 +58,7 @@ cudaError_t mrt_launch_build_occupancy_f16(const void* packed, int X, int Y, int
 cudaError_t mrt_launch_pack_u8(const void* planar_u8, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_build_occupancy_u8(const void* packed, int X, int Y, int Z, float* minmax, cudaStream_t st);
 cudaError_t mrt_launch_pack_quad(const float* packed1, int X, int Y, int Z, void* quad, cudaStream_t st);
+cudaError_t mrt_launch_pack_quad_f16(const void* packed_f16, int X, int Y, int Z, void* quad, cudaStream_t st);
 cudaError_t mrt_launch_pack(const float* planar, int C, int X, int Y, int Z, void* packed, cudaStream_t st);
 cudaError_t mrt_launch_unpack(const void* packed, int C, int X, int Y, int Z, float* planar, cudaStream_t st);
 

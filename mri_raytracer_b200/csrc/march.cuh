@@ -303,6 +303,8 @@ template <> struct VoxT<1, 2> { typedef uint8_t T; };
 // and z+1) instead of eight 4-byte ones: a quarter of the load instructions and about half the L1
 // data-stage wavefronts of the march, for 4x the bytes (mrt_pack_volume_quad).  Forward only.
 template <> struct VoxT<1, 3> { typedef float4 T; };
+// HALF = 4: the same quad layout over fp16 voxels (4 x __half = 8 B per element; mrt_pack_volume_quad_f16).
+template <> struct VoxT<1, 4> { typedef uint2 T; };
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
@@ -372,6 +374,7 @@ __device__ __forceinline__ Cell mrt_cell(const KParams& P, float px, float py, f
 // that a kernel can issue the loads of the NEXT slot before the dependent arithmetic of this one.
 template <int NCH, int HALF> struct CornerT { typedef typename VoxT<NCH, HALF>::T T; };
 template <> struct CornerT<1, 3> { typedef float T; };
+template <> struct CornerT<1, 4> { typedef float T; };
 template <int NCH, int HALF> struct Corners { typename CornerT<NCH, HALF>::T v[8]; };
 
 template <int NCH, int HALF> struct FetchImpl {
@@ -402,6 +405,19 @@ template <> struct FetchImpl<1, 3> {
     Corners<1, 3> k;
     k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
     k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+    return k;
+  }
+};
+template <> struct FetchImpl<1, 4> {
+  static __device__ __forceinline__ Corners<1, 4> run(const KParams& P, const uint2* __restrict__ vol, const Cell& c) {
+    const uint32_t b = c.mx + c.my * P.pitchY + c.mz * P.pitchZ - P.idx_bias;
+    const uint2* p0 = vol + b;
+    const uint2 lo = __ldg(p0), hi = __ldg(p0 + P.pitchZ);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), bb = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+    const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), d = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    Corners<1, 4> k;
+    k.v[0] = a.x; k.v[1] = a.y; k.v[2] = bb.x; k.v[3] = bb.y;
+    k.v[4] = cc.x; k.v[5] = cc.y; k.v[6] = d.x; k.v[7] = d.y;
     return k;
   }
 };

@@ -111,6 +111,32 @@ mrt_pack_quad_kernel(const float* __restrict__ src, int X, int Y, int Z, size_t 
     }
   }
 }
+// the same over fp16 voxels: source = the packed fp16 scalar layout, element = 4 x __half (8 B)
+__global__ void __launch_bounds__(256)
+mrt_pack_quad_f16_kernel(const __half* __restrict__ src, int X, int Y, int Z, size_t sY, size_t sZ, size_t qY, size_t qZ,
+                         uint2* __restrict__ quad) {
+  const int rows = Y * Z;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % Y, z = row / Y;
+    const int y1 = min(y + 1, Y - 1);
+    const unsigned short* r0 = reinterpret_cast<const unsigned short*>(src) + (size_t)y * sY + (size_t)z * sZ;
+    const unsigned short* r1 = reinterpret_cast<const unsigned short*>(src) + (size_t)y1 * sY + (size_t)z * sZ;
+    uint2* o = quad + (size_t)y * qY + (size_t)z * qZ;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      const int x1 = min(x + 1, X - 1);
+      o[x] = make_uint2((uint32_t)__ldg(r0 + x) | ((uint32_t)__ldg(r0 + x1) << 16), (uint32_t)__ldg(r1 + x) | ((uint32_t)__ldg(r1 + x1) << 16));
+    }
+  }
+}
+cudaError_t mrt_launch_pack_quad_f16(const void* packed_f16, int X, int Y, int Z, void* quad, cudaStream_t st) {
+  int64_t sY, sZ, qY, qZ;
+  mrt_layout_e(1, 2, X, Y, Z, &sY, &sZ);
+  mrt_layout_e(1, 8, X, Y, Z, &qY, &qZ);
+  const int blk = X >= 192 ? 256 : (X >= 96 ? 128 : 64);
+  mrt_pack_quad_f16_kernel<<<grid_for((size_t)Y * Z * 256, 256), blk, 0, st>>>((const __half*)packed_f16, X, Y, Z, sY, sZ, qY, qZ,
+                                                                               (uint2*)quad);
+  return cudaGetLastError();
+}
 cudaError_t mrt_launch_pack_quad(const float* packed1, int X, int Y, int Z, void* quad, cudaStream_t st) {
   int64_t sY, sZ, qY, qZ;
   mrt_layout(1, X, Y, Z, &sY, &sZ);

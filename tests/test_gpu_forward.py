@@ -424,6 +424,25 @@ def test_quad_layout_is_bit_identical_to_the_scalar_layout(cuda, C, ortho, use_t
         assert torch.equal(api.render(Vq, None, tfd, P2), api.render(Vs, None, tfd, P2))
 
 
+def test_fp16_quad_layout_is_bit_identical_incl_shards(cuda):
+    """volDtype 4 (quads of fp16 voxels, 8 B per element) against volDtype 1 on the same fp16 volume:
+    whole volume and a sort-last sub-box (BASELINE config 5's storage), skipping on and off."""
+    vol, _, P = small_scene(C=1, dims=(52, 44, 37), W=72, H=56, seed=22)
+    P = replace(P, tfMode=1, bgColor=(0.05, 0.0, 0.1), ertThreshold=1e-4)
+    tfd = ramp_tf(64, sigma_scale=20.0, cutoff=0.1).cuda()
+    vh = vol.cuda().half()
+    Vq, Vs = api.Volume(vh, quad=True), api.Volume(vh, quad=False)
+    assert Vq.prepared(P)[2].volDtype == 4 and Vs.prepared(P)[2].volDtype == 1
+    for skip in (1, 0):
+        assert torch.equal(api.render(Vq, None, tfd, replace(P, skipEmpty=skip)), api.render(Vs, None, tfd, replace(P, skipEmpty=skip)))
+    lo, hi = (8, 0, 16), (40, 43, 36)
+    sub = vh[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1].contiguous()
+    Sq = api.Volume(sub, shard=(lo, hi), global_dims=(52, 44, 37), quad=True)
+    Ss = api.Volume(sub, shard=(lo, hi), global_dims=(52, 44, 37), quad=False)
+    a, b = Sq.forward(P, tfd), Ss.forward(P, tfd)
+    assert torch.equal(a, b) and float(a[..., 3].min()) < 1.0
+
+
 @pytest.mark.parametrize("box_edge,tile", [(8, 8), (16, 8), (8, 16), (16, 16)])
 @pytest.mark.parametrize("ortho,use_tf", [(False, True), (True, True), (False, False)])
 def test_staged_brick_tma_variant_renders_the_same_image(cuda, box_edge, tile, ortho, use_tf):

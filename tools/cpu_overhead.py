@@ -36,4 +36,4 @@ import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 for _ in range(200): fbstep()
 pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)
