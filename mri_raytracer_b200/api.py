@@ -641,19 +641,25 @@ class Volume:
         packed, Cn, Pe = self.prepared(P)
         return self._classify(P, Pe, Cn, tf)
 
-    def _classify(self, P: RenderParams, Pe: RenderParams, Cn: int, tf: Optional[torch.Tensor]):
+    def _classify(self, P: RenderParams, Pe: RenderParams, Cn: int, tf: Optional[torch.Tensor],
+                  own_labels: bool = True, own_preds: bool = True):
+        """``own_labels`` / ``own_preds`` = False: the frame overlays a label volume OTHER than the
+        Volume's own, so its per-brick label occupancy does not apply — classification then keeps
+        every brick active for that overlay (exact, just slower) instead of skipping by stale flags."""
         if self.minmax is None or not P.skipEmpty or P.tMode != "indexed":
             return None
         if self._bits is None:
             self._bits = skip_levels_buffer(Pe, self.device)
-        return classify_bricks(Pe, self.minmax, Cn, tf, self.seg_any, self.pred_any, out=self._bits)
+        return classify_bricks(Pe, self.minmax, Cn, tf, self.seg_any if own_labels else None,
+                               self.pred_any if own_preds else None, out=self._bits)
 
     def forward(self, P: RenderParams, tf: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
                 out_T: Optional[torch.Tensor] = None, out_counts: Optional[torch.Tensor] = None,
                 tile_range: Optional[Tuple[int, int]] = None, labels=None, preds=None) -> torch.Tensor:
         """classify + march for one frame (two launches); ``P.tfMode`` must already be set."""
         packed, Cn, Pe = self.prepared(P)
-        bits = self._classify(P, Pe, Cn, tf)
+        bits = self._classify(P, Pe, Cn, tf, own_labels=labels is None or labels is self.labels,
+                              own_preds=preds is None or preds is self.preds)
         return render_forward(Pe, packed, Cn, tf, bits, labels if labels is not None else self.labels,
                               preds if preds is not None else self.preds, out=out, out_T=out_T,
                               out_counts=out_counts, tile_range=tile_range)

@@ -1,8 +1,9 @@
 """CPU (numpy) restatement of the reference's INR inference path.  TEST INFRASTRUCTURE ONLY.
 
-Groundwork for SURVEY.md section 8(f) rank 3 (INR ``predict_volume`` on the GPU, the producer of the
-``gPreds`` label volume the renderer overlays, inr/viewer/brats_viewer.py:250-310).  No product kernel
-exists for it yet; nothing under ``mri_raytracer_b200/`` imports this file.
+The checker of SURVEY.md section 8(f) rank 3: INR ``predict_volume`` on the GPU (``mrt_inr_predict``,
+csrc/inr.cu — the producer of the ``gPreds`` label volume the renderer overlays,
+inr/viewer/brats_viewer.py:250-310).  Only tests/, ``__graft_entry__.smoke()`` and the benchmark's CPU
+baseline import this file; nothing under ``mri_raytracer_b200/`` does.
 
 PARITY STATUS: **parity unpinned** — the reference implements this in JAX (inr/inr/model.py), which
 is not installed in this image, so the restatement cannot be checked against the executed reference;
