@@ -983,30 +983,47 @@ def render_host(volume: np.ndarray, params: RenderParams, tf: Optional[np.ndarra
     return out
 
 
-def inr_predict(mods: torch.Tensor, params: Sequence[dict], fourier_freqs: int, return_logits: bool = False,
-                impl: str = "auto"):
-    """INR segmentation of a whole volume on the GPU (``mrt_inr_predict``): the reference's
-    ``predict_volume`` (inr/inr/model.py:119-141) as one fused kernel.
+class InrWeights:
+    """The reference's parameter list uploaded once (``inr_upload_params``): flat device tensor + layer widths."""
+    __slots__ = ("wts", "dims", "n_layers")
 
-    mods   : ``[M,Z,Y,X]`` CUDA float32, z-scored per modality (:func:`volume.zscore_modalities`)
-    params : the reference's parameter list ``[{"W": [in,out], "b": [out]}, ...]`` (numpy or torch)
-    impl   : "auto" (tcgen05 tensor cores when the network fits, else FFMA), "ffma" (fp32 on the CUDA
-             cores: the parity reference), "tensor" (tensor cores or an error)
-    -> int32 labels ``[Z,Y,X]`` — directly usable as ``preds`` of :class:`Volume` / :func:`render` —
-    and, with ``return_logits``, float32 ``[Z,Y,X,classes]``."""
-    _need_cuda(mods, "mods", torch.float32)
-    M, Z, Y, X = (int(v) for v in mods.shape)
+    def __init__(self, wts: torch.Tensor, dims: Sequence[int], n_layers: int):
+        self.wts, self.dims, self.n_layers = wts, list(dims), int(n_layers)
+
+
+def inr_upload_params(params: Sequence[dict], device) -> InrWeights:
+    """``[{"W": [in,out], "b": [out]}, ...]`` (numpy or torch) -> :class:`InrWeights` on ``device``; pass it to
+    :func:`inr_predict` instead of the list when predicting many volumes with one network (saves the
+    host-side flatten + upload per call)."""
     dims = [int(np.asarray(params[0]["W"]).shape[0])] + [int(np.asarray(p["W"]).shape[1]) for p in params]
     flat = []
     for p in params:
         W = torch.as_tensor(np.asarray(p["W"], dtype=np.float32)) if not isinstance(p["W"], torch.Tensor) else p["W"].float().cpu()
         b = torch.as_tensor(np.asarray(p["b"], dtype=np.float32)) if not isinstance(p["b"], torch.Tensor) else p["b"].float().cpu()
         flat += [W.reshape(-1), b.reshape(-1)]
-    wts = torch.cat(flat).contiguous().to(mods.device)
+    return InrWeights(torch.cat(flat).contiguous().to(device), dims, len(params))
+
+
+def inr_predict(mods: torch.Tensor, params, fourier_freqs: int, return_logits: bool = False,
+                impl: str = "auto"):
+    """INR segmentation of a whole volume on the GPU (``mrt_inr_predict``): the reference's
+    ``predict_volume`` (inr/inr/model.py:119-141) as one fused kernel.
+
+    mods   : ``[M,Z,Y,X]`` CUDA float32, z-scored per modality (:func:`volume.zscore_modalities`)
+    params : the reference's parameter list ``[{"W": [in,out], "b": [out]}, ...]`` (numpy or torch), or
+             the :class:`InrWeights` of :func:`inr_upload_params`
+    impl   : "auto" (tcgen05 tensor cores when the network fits, else FFMA), "ffma" (fp32 on the CUDA
+             cores: the parity reference), "tensor" (tensor cores or an error)
+    -> int32 labels ``[Z,Y,X]`` — directly usable as ``preds`` of :class:`Volume` / :func:`render` —
+    and, with ``return_logits``, float32 ``[Z,Y,X,classes]``."""
+    _need_cuda(mods, "mods", torch.float32)
+    M, Z, Y, X = (int(v) for v in mods.shape)
+    w = params if isinstance(params, InrWeights) else inr_upload_params(params, mods.device)
+    dims = w.dims
     labels = torch.empty((Z, Y, X), dtype=torch.int32, device=mods.device)
     logits = torch.empty((Z, Y, X, dims[-1]), dtype=torch.float32, device=mods.device) if return_logits else None
     ld = (C.c_int32 * len(dims))(*dims)
-    check(lib().mrt_inr_predict(mods.data_ptr(), M, X, Y, Z, wts.data_ptr(), C.cast(ld, C.c_void_p), len(params),
+    check(lib().mrt_inr_predict(mods.data_ptr(), M, X, Y, Z, w.wts.data_ptr(), C.cast(ld, C.c_void_p), w.n_layers,
                                 int(fourier_freqs), labels.data_ptr(), _ptr(logits),
                                 {"auto": 0, "ffma": 1, "tensor": 2}[impl], _stream()), "inr_predict")
     return (labels, logits) if return_logits else labels
