@@ -614,6 +614,7 @@ def run_ours(args):
         cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": dt,
                "torch_oracle": {"value": nt_ / dtt, "sample": sample_t, "seconds": dtt}}
 
+    line = None
     if rank == 0:
         cfg = _config(V, world)
         line = {
@@ -635,9 +636,70 @@ def run_ours(args):
             # (+ the owners' background fill at N > 1)
             "gpu_launches": ((V if args.per_view else 1) + 3 + (1 if world > 1 else 0)) * world * args.steps,
         }
+    # ---- the other BASELINE configs (outside every timed region above), attached to the same line
+    if not args.no_configs:
+        del frames, flush
+        torch.cuda.empty_cache()
+        other = _other_configs(rank, world, dev, line)
+        if line is not None:
+            line["other_configs"] = other
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _other_configs(rank, world, dev, line):
+    """BASELINE.json's other configs, each measured by its own tool function (tools/bench_configs.py,
+    tools/bench_cfg4.py, tools/bench_cfg5.py) and attached to the bench line so that they are on the
+    driver's record: cfg1 (+ u8 storage), cfg3 (forward + backward, with the backward's roofline), INR
+    inference (tensor roofline) and cfg4 at N = 1; cfg4 strong-scaled and cfg5 (brick-sharded fp16,
+    sort-last over NVLink) at N > 1.  Not part of `value`: each record names its own unit.  A
+    watchdog prints the headline line alone if this leg hangs (a peer that died inside a collective)."""
+    import argparse as _ap
+    import threading
+    import torch
+    sys.path.insert(0, str(ROOT / "tools")); sys.path.insert(0, str(ROOT / "tests"))
+
+    def bail():
+        if line is not None:
+            line["other_configs"] = {"error": "watchdog: the secondary configs did not finish in time"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    dog = threading.Timer(240.0, bail)
+    dog.daemon = True
+    dog.start()
+    out = {}
+
+    def attempt(name, fn):
+        t0 = time.perf_counter()
+        try:
+            rec = fn()
+            rec["wall_s"] = time.perf_counter() - t0
+            out[name] = rec
+        except Exception as e:                  # reported in the line, never hidden
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+
+    if world == 1:
+        import bench_configs as BC
+        BC.WITH_ORACLE = False
+        for name in ("cfg1", "cfg1_u8", "cfg3", "cfg4", "inr"):
+            attempt(name, getattr(BC, name))
+    else:
+        import bench_cfg4
+        import bench_cfg5
+        # cfg4 as BASELINE states it: 64 views at 2048^2 over 512^3, strong-scaled over the ranks
+        attempt("cfg4", lambda: bench_cfg4.run(_ap.Namespace(dim=512, img=2048, views=64, reps=5, partition="tiles", owners="striped"),
+                                               rank, world, dev))
+        # cfg5: 1024^3 fp16 voxels per GPU, the shard grid of the world size: 2048^3 (BASELINE's size) on 8 GPUs,
+        # 1024 x 2048 x 2048 on 4, 1024 x 1024 x 2048 on 2 (2048^3 itself needs >= 4 shards: < 2^32 voxels per shard)
+        from mri_raytracer_b200 import dist as mdist
+        dims5 = tuple(1024 * g for g in mdist.shard_grid(world))
+        attempt("cfg5", lambda: bench_cfg5.run(_ap.Namespace(dims=dims5, dim=0, img=4096, views=4, reps=3, emulate=0, nccl=False, check=False),
+                                               rank, world, dev))
+    dog.cancel()
+    return out
 
 
 def main():
@@ -654,6 +716,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--no-probe", action="store_true", help="skip the gather-ceiling probe")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configs attached as `other_configs`")
     ap.add_argument("--no-fold", action="store_true", help="blend modalities per sample (float4 gathers) instead of folding")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -31,22 +31,10 @@ from mri_raytracer_b200.synth import make_brats_like, ramp_tf  # noqa: E402
 from scenes import framed_params  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--dim", type=int, default=512)
-    ap.add_argument("--img", type=int, default=2048)
-    ap.add_argument("--views", type=int, default=64)
-    ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--partition", default="tiles", choices=["tiles", "views"])
-    ap.add_argument("--owners", default="striped", choices=["striped", "root"])
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def run(args, rank, world, dev):
+    """The measurement itself; the process group (world > 1) is the caller's.  Returns the record on every rank."""
     if args.views % world:
-        raise SystemExit("--views must be divisible by the number of GPUs")
+        raise ValueError("--views must be divisible by the number of GPUs")
     dims = (args.dim,) * 3
     vol = make_brats_like(1, dims, seed=5, device=dev)
     tf = ramp_tf(256).to(dev)
@@ -110,14 +98,31 @@ def main():
     okt = torch.tensor([1 if okl else 0], device=dev)
     if world > 1:
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    return dict(cfg="cfg4", dims=dims, image=args.img, views=args.views, n_gpus=world, scaling="strong",
+                gather=("none (single GPU)" if world == 1 else
+                        f"peer (NVLink) stores from inside the march, partition={fb.partition}, owners={fb.owners}"),
+                ms_per_batch=ms_batch, views_per_s=args.views * 1e3 / ms_batch,
+                ms_per_view=ms_batch / args.views, nominal_samples_per_batch=taken,
+                gsamples_per_s=taken / ms_batch / 1e6, gathered_views_equal_local_renders=bool(okt.item()),
+                reps=args.reps)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--img", type=int, default=2048)
+    ap.add_argument("--views", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "views"])
+    ap.add_argument("--owners", default="striped", choices=["striped", "root"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rec = run(args, rank, world, dev)
     if rank == 0:
-        print(json.dumps(dict(cfg="cfg4", dims=dims, image=args.img, views=args.views, n_gpus=world, scaling="strong",
-                              gather=("none (single GPU)" if world == 1 else
-                                      f"peer (NVLink) stores from inside the march, partition={fb.partition}, owners={fb.owners}"),
-                              ms_per_batch=ms_batch, views_per_s=args.views * 1e3 / ms_batch,
-                              ms_per_view=ms_batch / args.views, nominal_samples_per_batch=taken,
-                              gsamples_per_s=taken / ms_batch / 1e6, gathered_views_equal_local_renders=bool(okt.item()),
-                              reps=args.reps)), flush=True)
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

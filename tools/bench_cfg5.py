@@ -32,25 +32,11 @@ from mri_raytracer_b200 import dist as mdist  # noqa: E402
 from mri_raytracer_b200.synth import make_brats_like_box, ramp_tf, world_box  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--dim", type=int, default=2048)
-    ap.add_argument("--img", type=int, default=4096)
-    ap.add_argument("--views", type=int, default=4)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--emulate", type=int, default=0, help="run all R shards on one GPU")
-    ap.add_argument("--nccl", action="store_true", help="use the NCCL all_to_all/all_gather exchange")
-    ap.add_argument("--check", action="store_true", help="compare with the unsharded render (small sizes only)")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def run(args, rank, world, dev):
+    """The measurement itself; the process group (world > 1) is the caller's.  Returns the record on every rank."""
     R = args.emulate or world
     grid = mdist.shard_grid(R)
-    dims = (args.dim, args.dim, args.dim)
+    dims = tuple(args.dims) if getattr(args, "dims", None) else (args.dim, args.dim, args.dim)
     vs, vmin = world_box(dims)
     P = RenderParams(imageSize=(args.img, args.img), dims=dims, voxelSize=tuple(float(v) for v in vs),
                      volMin=tuple(float(v) for v in vmin), stepSize=float(np.float32(0.5) * vs[0]), skipEmpty=1,
@@ -119,6 +105,26 @@ def main():
         ref = api.render(full, cams[0], tf, P)
         got = frame(cams[0])
         rec["max_abs_vs_unsharded"] = float((got - ref).abs().max())
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dim", type=int, default=2048)
+    ap.add_argument("--img", type=int, default=4096)
+    ap.add_argument("--views", type=int, default=4)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--emulate", type=int, default=0, help="run all R shards on one GPU")
+    ap.add_argument("--nccl", action="store_true", help="use the NCCL all_to_all/all_gather exchange")
+    ap.add_argument("--check", action="store_true", help="compare with the unsharded render (small sizes only)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rec = run(args, rank, world, dev)
     if rank == 0:
         print(json.dumps(rec), flush=True)
     if world > 1:

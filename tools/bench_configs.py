@@ -26,6 +26,24 @@ from mri_raytracer_b200.synth import make_brats_like, ramp_tf  # noqa: E402
 from scenes import framed_params  # noqa: E402
 
 
+# bench.py attaches these records to its JSON line with WITH_ORACLE = False: the CPU oracle is then not
+# imported at all (parity lives in tests/; here it is a spot check for the stand-alone tool)
+WITH_ORACLE = True
+
+
+def glorot_mlp(rng, in_dim, hidden, out_dim):
+    """Glorot-uniform weights + small random biases in the reference's parameter layout
+    (a list of {"W": [in,out], "b": [out]}, inr/inr/model.py:26-40)."""
+    import numpy as np
+    dims = [in_dim] + list(hidden) + [out_dim]
+    params = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        lim = math.sqrt(6.0 / (a + b))
+        params.append({"W": rng.uniform(-lim, lim, size=(a, b)).astype(np.float32),
+                       "b": rng.normal(scale=0.1, size=(b,)).astype(np.float32)})
+    return params
+
+
 def timeit(fn, n=5, warm=2, reps=4):
     for _ in range(warm):
         fn()
@@ -64,9 +82,12 @@ def cfg1():
     img, T, counts = api.render_aux(V, None, tfd, P)
     c = counts.sum(dim=(0, 1)).tolist()
     ms = timeit(lambda: api.render(V, None, tfd, P), reps=10)
-    mx, nbad, npx = parity_subset(vol, P, tf, img, 4)
-    return dict(cfg="cfg1", ms_per_frame=ms, fps=1e3 / ms, samples_taken=c[1], samples_evaluated=c[2],
-                gsamples_per_s=c[1] / ms / 1e6, parity_max_abs=mx, parity_pixels_over_1e4=nbad, parity_pixels=npx)
+    rec = dict(cfg="cfg1", ms_per_frame=ms, fps=1e3 / ms, samples_taken=c[1], samples_evaluated=c[2],
+               gsamples_per_s=c[1] / ms / 1e6)
+    if WITH_ORACLE:
+        mx, nbad, npx = parity_subset(vol, P, tf, img, 4)
+        rec.update(parity_max_abs=mx, parity_pixels_over_1e4=nbad, parity_pixels=npx)
+    return rec
 
 
 def cfg1_u8():
@@ -169,17 +190,19 @@ def cfg3():
                     "call (dvol memset, task list, march, dL/dtf reduce). The volume and its gradient are L2-resident, so HBM is the "
                     "reference line SURVEY 8(d) asks for, not what binds"}
     # gradient parity on a small scene (the oracle's autograd cannot hold 256^3 x 512^2)
-    from scenes import small_scene
-    from oracle import oracle_torch as O
-    sv, _, sP = small_scene(C=1, dims=(32, 32, 32), W=48, H=48, seed=4)
-    sP = replace(sP, tfMode=1)
-    stf = ramp_tf(64, sigma_scale=20.0, cutoff=0.05)
-    a = sv.clone().requires_grad_(True); b = stf.clone().requires_grad_(True)
-    O.render(a, sP, tf=b).square().mean().backward()
-    ga = sv.cuda().requires_grad_(True); gb = stf.cuda().requires_grad_(True)
-    api.render(ga, None, gb, sP).square().mean().backward()
-    rel_v = float((ga.grad.cpu() - a.grad).abs().max() / a.grad.abs().max())
-    rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
+    rel_v = rel_t = None
+    if WITH_ORACLE:
+        from scenes import small_scene
+        from oracle import oracle_torch as O
+        sv, _, sP = small_scene(C=1, dims=(32, 32, 32), W=48, H=48, seed=4)
+        sP = replace(sP, tfMode=1)
+        stf = ramp_tf(64, sigma_scale=20.0, cutoff=0.05)
+        a = sv.clone().requires_grad_(True); b = stf.clone().requires_grad_(True)
+        O.render(a, sP, tf=b).square().mean().backward()
+        ga = sv.cuda().requires_grad_(True); gb = stf.cuda().requires_grad_(True)
+        api.render(ga, None, gb, sP).square().mean().backward()
+        rel_v = float((ga.grad.cpu() - a.grad).abs().max() / a.grad.abs().max())
+        rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
     return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_fwd_bwd_cuda_graph=ms_graph, graph_vs_eager_grad_rel=graph_rel, ms_fwd_only=ms_fwd, ms_forward_ckpt_kernel=ms_fwd_ckpt, ms_backward_call=ms_bwd,
                 ms_backward_whole_ray=ms_bwd_whole, steps_per_s=1e3 / ms, samples_taken=c[1],
                 gsamples_per_s_fwd_bwd=c[1] / ms / 1e6, grad_rel_volume=rel_v, grad_rel_tf=rel_t, roofline=roof,
@@ -218,13 +241,10 @@ def inr():
     import json as _json
     import numpy as np
     from mri_raytracer_b200 import volume as mvol
-    from oracle import oracle_inr as I
     dims = (240, 240, 155)
     X, Y, Z = dims
     rng = np.random.default_rng(0)
-    params = I.init_mlp(rng, I.input_dim(4, 4), [64, 64, 64, 64], 4)
-    for p in params:
-        p["b"] = rng.normal(scale=0.1, size=p["b"].shape).astype(np.float32)
+    params = glorot_mlp(rng, 3 + 3 * 2 * 4 + 4, [64, 64, 64, 64], 4)       # in_dim = coords + 6k Fourier + M (inr/inr/train.py)
     mods = mvol.zscore_modalities(make_brats_like(4, dims, seed=0, device="cuda"))
     wdev = api.inr_upload_params(params, mods.device)          # the network is uploaded once, like the volume
     ms = timeit(lambda: api.inr_predict(mods, wdev, 4, impl="tensor"), reps=4)
@@ -247,16 +267,19 @@ def inr():
                        "columns): MMA-only the kernel takes 0.96 ms, the empty hand-off skeleton 0.47 ms (DESIGN.md)",
             "note": "achieved counts the tensor-core work really issued (every product as 3 tf32 MMAs, K padded 31->32, classes "
                     "padded 4->16, one bias step per layer); useful_tflops counts the network's own 29 kFLOP per voxel"}
-    sub = mods[:, ::4, ::4, ::4].cpu().numpy().transpose(0, 3, 2, 1).copy()
-    t0 = time.perf_counter()
-    I.predict_volume(params, sub, 4)
-    cpu_s = time.perf_counter() - t0
-    return dict(cfg="inr_predict", dims=dims, ms=ms, ms_fp32_ffma_kernel=ms_ffma, gvoxels_per_s=nvox / ms / 1e6,
-                max_logit_diff_vs_ffma=float((gt - gf).abs().max()),
-                labels_equal_where_top2_gap_over_1e3=bool((lt == lf)[clear].all()), label_agreement=float((lt == lf).float().mean()),
-                roofline=roof, cpu_numpy_oracle_voxels_per_s=sub[0].size / cpu_s,
-                cpu_sample="every 4th voxel per axis (1/64 of the case)",
-                speedup_vs_numpy=(nvox / (ms * 1e-3)) / (sub[0].size / cpu_s))
+    rec = dict(cfg="inr_predict", dims=dims, ms=ms, ms_fp32_ffma_kernel=ms_ffma, gvoxels_per_s=nvox / ms / 1e6,
+               max_logit_diff_vs_ffma=float((gt - gf).abs().max()),
+               labels_equal_where_top2_gap_over_1e3=bool((lt == lf)[clear].all()), label_agreement=float((lt == lf).float().mean()),
+               roofline=roof)
+    if WITH_ORACLE:
+        from oracle import oracle_inr as I
+        sub = mods[:, ::4, ::4, ::4].cpu().numpy().transpose(0, 3, 2, 1).copy()
+        t0 = time.perf_counter()
+        I.predict_volume(params, sub, 4)
+        cpu_s = time.perf_counter() - t0
+        rec.update(cpu_numpy_oracle_voxels_per_s=sub[0].size / cpu_s, cpu_sample="every 4th voxel per axis (1/64 of the case)",
+                   speedup_vs_numpy=(nvox / (ms * 1e-3)) / (sub[0].size / cpu_s))
+    return rec
 
 
 if __name__ == "__main__":
