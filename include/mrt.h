@@ -371,7 +371,14 @@ int mrt_render_forward_ckpt(const MrtParams* params, const MrtCamera* cams, int3
  *   ckpt, seg_slots, nseg, k_end, warp_kmax : the outputs of mrt_render_forward_ckpt for the SAME
  *                arguments -> segment-parallel backward; all NULL / 0 -> one task per half tile that
  *                walks whole rays (any tMode / gamma)
- *   dL_dvol    : packed layout, same shape as `packed`, ACCUMULATED into (caller zeroes)
+ *   dL_dvol    : packed layout, same shape as `packed`, ACCUMULATED into (caller zeroes).  fp16 storage
+ *                (volDtype 1): the gradient is fp32 with the fp16 layout's element pitches
+ *                (mrt_packed_layout_f16; pitchZ*Z floats)
+ *   sharded volumes (params->shardEnabled; sort-last sub-boxes): whole-ray path only (ckpt... NULL,
+ *                dL_dray NULL).  `out_rgba` / `dL_dout` are the shard's PARTIAL (premultiplied rgb
+ *                without background, T_local) and its gradient: .w of dL_dout is dL/dT_local.
+ *                A slot is differentiated iff its base cell is owned, as in the forward, so the
+ *                shards' gradients add up to the unsharded gradient.  u8 / quad layouts: forward only.
  *   dL_dtf     : float [tfN][4] (tfMode 1) or float[2][4] (tfMode 0: entry [1][3] is
  *                dL/d intensityAlpha), ACCUMULATED into (caller zeroes)
  *   scratch    : device scratch of mrt_backward_scratch_bytes(W,H,nviews,tfN,nseg) bytes (task list,

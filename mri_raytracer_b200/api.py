@@ -391,7 +391,8 @@ def render_backward(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional
     W, H = P.imageSize
     V = 1 if cams is None else len(cams)
     t0, t1 = tile_range if tile_range is not None else (0, _tiles.tile_count(W, H))
-    dvol = torch.zeros_like(packed) if want_dvol else None
+    # (fp16 storage: the gradient is fp32 with the fp16 layout's element pitches)
+    dvol = torch.zeros(packed.shape, dtype=torch.float32, device=packed.device) if want_dvol else None
     ntf = tf.shape[0] if (tf is not None and P.tfMode) else 2
     dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_dtf else None
     nseg = ckpt.nseg if ckpt is not None else 1
@@ -778,6 +779,77 @@ class _RenderFn(torch.autograd.Function):
         if want_vol:
             gvol = unfold_grad(dvol, ctx.P, ctx.Cn) if ctx.fold else unpack_volume(dvol, ctx.Cn, ctx.P.dims)
         return gvol, (dtf if want_tf else None), None, None, None, None, None, None
+
+
+def packed_layout_f16(dims) -> Tuple[int, int]:
+    """(pitchY, pitchZ) in voxels of the packed fp16 layout (``mrt_packed_layout_f16``)."""
+    X, Y, Z = dims
+    py, pz = C.c_int64(), C.c_int64()
+    lib().mrt_packed_layout_f16(X, Y, Z, C.byref(py), C.byref(pz))
+    return int(py.value), int(pz.value)
+
+
+class _ShardRenderFn(torch.autograd.Function):
+    """Differentiable PARTIAL render of one sort-last sub-box (premultiplied rgb without background,
+    T_local), fp32 or fp16 voxel storage: the building block of a differentiable cfg5."""
+
+    @staticmethod
+    def forward(ctx, sub, tf, P: RenderParams, shard, half):
+        st = sub.detach()
+        if half and st.dtype != torch.float16:
+            st = st.half()                       # storage rounding; the gradient passes straight through it
+        vol = Volume(st.contiguous(), shard=shard, global_dims=P.dims, quad=False)
+        out = vol.forward(P, tf)
+        packed, Ce, Pe = vol.prepared(P, quad=False)
+        ctx.Pe, ctx.dims, ctx.half, ctx.in_dtype = Pe, vol.dims, bool(vol.half), sub.dtype
+        ctx.has_tf = tf is not None
+        ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=sub.device), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        packed, tf, out = ctx.saved_tensors
+        tf = tf if ctx.has_tf else None
+        want_vol, want_tf = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf
+        dvol, dtf = render_backward(ctx.Pe, packed, 1, tf, None, None, out, g.contiguous(),
+                                    want_dvol=want_vol, want_dtf=want_tf)
+        gvol = None
+        if want_vol:
+            X, Y, Z = ctx.dims
+            if ctx.half:
+                pY, pZ = packed_layout_f16(ctx.dims)
+                gvol = dvol.as_strided((1, Z, Y, X), (0, pZ, pY, 1)).contiguous()
+            else:
+                gvol = unpack_volume(dvol, 1, ctx.dims)
+            gvol = gvol.to(ctx.in_dtype)
+        return gvol, (dtf if want_tf else None), None, None, None
+
+
+def render_shard(sub: torch.Tensor, shard, global_dims, camera: Optional[Camera], tf: Optional[torch.Tensor],
+                 params: RenderParams, storage: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Partial frame of ONE sort-last sub-box, differentiable w.r.t. ``sub`` and ``tf``.
+
+    sub     : ``[1,z,y,x]`` CUDA fp32 or fp16 tensor holding voxels ``[lo, hi]`` (inclusive) of the
+              global volume, ``shard = (lo, hi)`` in (x,y,z) order (``dist.shard_box``).
+    storage : ``torch.float16`` samples an fp16 copy of an fp32 ``sub`` (cfg5's storage; the gradient
+              comes back in fp32, straight through the rounding).  An fp16 ``sub`` gets an fp16 gradient.
+    Returns float32 ``[H,W,4]`` = (premultiplied rgb WITHOUT background, T_local): composite the
+    shards' partials front to back (``dist.composite_over_differentiable``) for the image.  The
+    gradients of all shards, added in global coordinates, equal the unsharded gradient; early
+    termination acts per shard (use a small ``ertThreshold``)."""
+    if sub.dim() != 4 or sub.shape[0] != 1:
+        raise ValueError(f"sub must be [1,z,y,x], got {tuple(sub.shape)}")
+    _need_cuda(sub, "sub", sub.dtype if sub.dtype in (torch.float16, torch.float32) else torch.float32)
+    P = params if camera is None else params.with_camera(camera)
+    if tuple(P.dims) != tuple(int(v) for v in global_dims):
+        raise ValueError(f"params.dims {P.dims} != global_dims {tuple(global_dims)}")
+    if tf is not None:
+        _need_cuda(tf, "tf", torch.float32)
+    P = replace(P, tfMode=1 if tf is not None else 0)
+    P.validate()
+    lo, hi = tuple(int(v) for v in shard[0]), tuple(int(v) for v in shard[1])
+    half = sub.dtype == torch.float16 or storage == torch.float16
+    return _ShardRenderFn.apply(sub, tf, P, (lo, hi), half)
 
 
 def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Optional[torch.Tensor],

@@ -73,11 +73,15 @@ struct BwdIO {
   int S, nviews;
 };
 
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+// HALF = 1: fp16 voxel storage (single channel); the gradient buffer stays fp32 with the SAME element
+// pitches.  Sort-last shards (P.shard; whole-ray tasks only, SKIP off): the slot range is clipped to
+// the sub-box, a slot is differentiated iff its base cell is owned (forward.cu's rule), the state
+// starts at (0,0,0,1) and the upstream gradient of the partial's fourth channel is dL/dT_local.
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF = 0>
 __global__ void __launch_bounds__(32 * MRT_BWD_WARPS, MRT_BWD_MINB)
 mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B,
                const __grid_constant__ BwdIO IO,
-               const typename Vox<NCH>::T* __restrict__ vol, typename Vox<NCH>::T* __restrict__ dvol) {
+               const typename VoxT<NCH, HALF>::T* __restrict__ vol, typename Vox<NCH>::T* __restrict__ dvol) {
   typedef typename Vox<NCH>::T VT;
   extern __shared__ __align__(16) unsigned char s_raw[];   // [ntf] LUT | [16] labels
   const int ntf = P.tfMode ? P.tfN : 2;
@@ -116,6 +120,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
   asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
   const uint32_t sY = P.pitchY, sZ = P.pitchZ;
   const bool acc_mode = GENERIC && P.tMode == 1;           // reference-faithful running sum t += dt (unsegmented only)
+  const float bgx = P.shard ? 0.0f : P.bg[0], bgy = P.shard ? 0.0f : P.bg[1], bgz = P.shard ? 0.0f : P.bg[2];
   unsigned n_shaded = 0, n_tasks = 0;
 
   // the queue is read one task ahead: the atomic of the NEXT fetch is in flight while this task runs
@@ -136,9 +141,9 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
     const float4 G = inside ? __ldg(IO.dL_dout + pix) : zero4;
     const float4 Cout = inside ? __ldg(IO.out_rgba + pix) : zero4;
     const int ke = (seg && inside) ? __ldg(IO.k_end + pix) : 0;
-    float4 c0 = make_float4(P.bg[0], P.bg[1], P.bg[2], 1.0f);            // state before the segment's first slot
+    float4 c0 = make_float4(bgx, bgy, bgz, 1.0f);                        // state before the segment's first slot
     if (seg && sg > 0 && inside) c0 = __ldg(IO.ck + ((size_t)(sg - 1) * IO.nviews + view) * npix + pixl);
-    bool live = inside && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || (P.alphaMode && G.w != 0.0f));
+    bool live = inside && (G.x != 0.0f || G.y != 0.0f || G.z != 0.0f || ((P.alphaMode || P.shard) && G.w != 0.0f));
     int k0 = 0, k1 = INT_MAX;
     if (seg) {
       k0 = sg * IO.S;
@@ -148,17 +153,23 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
     if (!__any_sync(full, live)) continue;
     const Ray ray = mrt_setup_ray(P, B.cam[view], px, py);
     k1 = min(k1, ray.n);
+    const IdxRay q = mrt_index_ray(P, ray);
+    if (P.shard) {                       // candidate slots inside this shard's sub-box (ownership is decided per slot)
+      int ks, ke2;
+      mrt_shard_range(P, q, ray.t0, 1.0f / dt, k1, &ks, &ke2);
+      k0 = max(k0, ks); k1 = min(k1, ke2);
+    }
     live = live && k1 > k0;
     if (!__any_sync(full, live)) continue;
     if (!live) k1 = k0;
     ++n_tasks;
 
-    const float S_tot = G.x * (Cout.x - P.bg[0]) + G.y * (Cout.y - P.bg[1]) + G.z * (Cout.z - P.bg[2]);
-    // alphaMode 1: a = 1 - T_N  =>  dL/dT_N = -G.w ;  dsigma_i += -dt*T_N*dL/dT_N
-    const float tn_term = P.alphaMode ? -(1.0f - Cout.w) * G.w : 0.0f;   // = T_N * dL/dT_N
+    const float S_tot = G.x * (Cout.x - bgx) + G.y * (Cout.y - bgy) + G.z * (Cout.z - bgz);
+    // alphaMode 1: a = 1 - T_N  =>  dL/dT_N = -G.w ;  dsigma_i += -dt*T_N*dL/dT_N.  A shard's partial
+    // carries T_local itself in .w: dL/dT_N = G.w
+    const float tn_term = P.shard ? Cout.w * G.w : (P.alphaMode ? -(1.0f - Cout.w) * G.w : 0.0f);   // = T_N * dL/dT_N
     float T = c0.w;
-    float prefix = G.x * (c0.x - P.bg[0]) + G.y * (c0.y - P.bg[1]) + G.z * (c0.z - P.bg[2]);
-    const IdxRay q = mrt_index_ray(P, ray);
+    float prefix = G.x * (c0.x - bgx) + G.y * (c0.y - bgy) + G.z * (c0.z - bgz);
     const float ivx = 1.0f / q.dx, ivy = 1.0f / q.dy, ivz = 1.0f / q.dz;
     const float inv_dt = 1.0f / dt;
     int k = k0, kact = k0;
@@ -229,10 +240,12 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
         const float t = acc_mode ? tacc : fmaf((float)k, dt, ray.t0);
         const float ppx = fmaf(t, q.dx, q.ox), ppy = fmaf(t, q.dy, q.oy), ppz = fmaf(t, q.dz, q.oz);
         const Cell c = mrt_cell(P, ppx, ppy, ppz, hix, hiy, hiz);
-        const Corners<NCH, false> cor = mrt_fetch<NCH, false>(P, vol, c);
-        const float raw = mrt_interp<NCH, false>(P, cor, c);
+        const bool mine = !P.shard || mrt_shard_owns(P, c.ix(), c.iy(), c.iz());   // another shard's slot: a no-op here
+        Corners<NCH, HALF> cor;
+        float raw = 0.0f;
+        if (mine) { cor = mrt_fetch<NCH, HALF>(P, vol, c); raw = mrt_interp<NCH, HALF>(P, cor, c); }
         const float val = mrt_window<GENERIC>(P, raw);
-        if (P.tfMode || val > 0.0f) {
+        if (mine && (P.tfMode || val > 0.0f)) {
           const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
           const float alpha = mrt_alpha(P, rgba.w);
           const float aT = alpha * T;
@@ -256,7 +269,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
               // dL/do += dL/dx_i and dL/dd += t_i dL/dx_i, with dL/dx_i = dL/ds * ds/dx (section 6); an
               // axis on which the position was clamped (:62) carries no gradient
               float sx, sy, sz;
-              mrt_interp_grad<NCH, false>(P, cor, c, &sx, &sy, &sz);
+              mrt_interp_grad<NCH, HALF>(P, cor, c, &sx, &sy, &sz);
               const float wx = (ppx >= 0.0f && ppx <= hix) ? dv * sx / P.vs[0] : 0.0f;
               const float wy = (ppy >= 0.0f && ppy <= hiy) ? dv * sy / P.vs[1] : 0.0f;
               const float wz = (ppz >= 0.0f && ppz <= hiz) ? dv * sz / P.vs[2] : 0.0f;
@@ -275,7 +288,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
               const int ix = c.ix(), iy = c.iy(), iz = c.iz();
               const int ddx = ix - ccx, ddy = iy - ccy, ddz = iz - ccz;
               if ((ddx | ddy | ddz) != 0) {
-                VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ);
+                VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ - P.base_off);
                 if (max(max(abs(ddx), abs(ddy)), abs(ddz)) > 1) {
                   MRT_FLUSH_ALL(pb);
                 } else {
@@ -330,7 +343,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
       if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
     }
     if (dvol != nullptr && ccx >= 0) {
-      VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ);
+      VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ - P.base_off);
       MRT_FLUSH_ALL(pb);
     }
   }
@@ -413,10 +426,11 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int NCH, bool LABELS, bool SKIP, bool GENERIC>
+template <int NCH, bool LABELS, bool SKIP, bool GENERIC, int HALF = 0>
 static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, const void* vol, const MrtBwdArgs& A,
                               cudaStream_t st) {
   typedef typename Vox<NCH>::T VT;
+  typedef typename VoxT<NCH, HALF>::T ST;
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0) return cudaSuccess;
   const int ntf = P.tfMode ? P.tfN : 2;
@@ -436,7 +450,7 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   if (e != cudaSuccess) return e;
 
   const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4);
-  auto kern = mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC>;
+  auto kern = mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -455,7 +469,7 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   IO.dray = A.dray; IO.stats = (unsigned long long*)A.stats;
   IO.tasks = tasks; IO.ntasks = counters; IO.next = counters + 1;
   IO.S = seg ? A.seg_slots : 0; IO.nviews = nviews;
-  kern<<<(unsigned)grid, 32 * MRT_BWD_WARPS, smem, st>>>(P, B, IO, (const VT*)vol, (VT*)A.dvol);
+  kern<<<(unsigned)grid, 32 * MRT_BWD_WARPS, smem, st>>>(P, B, IO, (const ST*)vol, (VT*)A.dvol);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (A.dtf) {
@@ -488,7 +502,12 @@ cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews,
   }
   const bool lab = (P.showSeg || P.showPred);
   const bool gen = (P.tMode != 0) || (P.gamma != 1.0f);
-  const bool skip = P.skip && A.flat_levels != nullptr && A.minmax != nullptr && P.tMode == 0 && packed_ch == 1;
+  const bool skip = P.skip && A.flat_levels != nullptr && A.minmax != nullptr && P.tMode == 0 && packed_ch == 1 && !P.shard;
+  if (P.half) {                        // fp16 storage: single channel, no overlays, indexed stepping (c_api.cu checks)
+    if (P.half != 1 || packed_ch != 1 || lab || gen) return cudaErrorInvalidValue;
+    return skip ? launch_bwd<1, false, true, false, 1>(P, B, nviews, vol, A, st)
+                : launch_bwd<1, false, false, false, 1>(P, B, nviews, vol, A, st);
+  }
   switch (packed_ch) {
     case 1: return skip ? dispatch_bwd<1, true>(P, B, nviews, lab, gen, vol, A, st)
                         : dispatch_bwd<1, false>(P, B, nviews, lab, gen, vol, A, st);

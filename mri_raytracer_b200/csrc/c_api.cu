@@ -583,10 +583,13 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
   MRT_REQUIRE(cams == nullptr || (nviews >= 1 && nviews <= MRT_MAX_VIEWS), "render_backward: nviews outside 1..%d", MRT_MAX_VIEWS);
   KParams K;
   if (int r = derive(params, C, tfN, flat_levels != nullptr && minmax != nullptr, tile_begin, tile_end, &K)) return r;
-  if (K.half) return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 / u8 volumes are forward-only");
-  if (K.shard) return fail(MRT_ERR_UNSUPPORTED, "render_backward: sharded volumes are forward-only");
+  if (K.half > 1) return fail(MRT_ERR_UNSUPPORTED, "render_backward: u8 / quad volumes are forward-only (fp32 and fp16 storage differentiate)");
+  if (K.half && (K.tMode != 0 || K.gamma != 1.0f || K.showSeg || K.showPred))
+    return fail(MRT_ERR_UNSUPPORTED, "render_backward: fp16 volumes need indexed stepping, gamma 1, no overlays");
   MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward: tfMode=1 needs tf");
   const bool seg = k_end != nullptr || warp_kmax != nullptr || ckpt != nullptr;
+  if (K.shard && (seg || dL_dray))
+    return fail(MRT_ERR_UNSUPPORTED, "render_backward: sharded volumes take the whole-ray path (no checkpoints, no ray gradients)");
   if (seg) {
     MRT_REQUIRE(k_end && warp_kmax && seg_slots >= 1 && nseg >= 1 && (nseg == 1 || ckpt),
                 "render_backward: the segmented path needs ckpt, k_end and warp_kmax of mrt_render_forward_ckpt");

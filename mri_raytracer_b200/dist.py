@@ -394,6 +394,67 @@ def composite_over(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode:
     return out
 
 
+def composite_over_differentiable(partials: torch.Tensor, order: Sequence[int], bg, alpha_mode: int = 0) -> torch.Tensor:
+    """The ordered `over` of :func:`composite_over` written in differentiable tensor operations:
+    ``[K,npix,4]`` partials (premultiplied rgb, T) -> ``[npix,4]``; C = bg + sum_k (prod_{j<k} T_j) C_k.
+    Used by the differentiable sort-last path (the forward-only paths use the fused kernel)."""
+    p = partials[list(order)]
+    T = p[..., 3]
+    Tcum = torch.cumprod(T, dim=0)
+    Tprev = torch.cat([torch.ones_like(T[:1]), Tcum[:-1]], dim=0)
+    rgb = (Tprev.unsqueeze(-1) * p[..., :3]).sum(dim=0) + torch.as_tensor(bg, dtype=p.dtype, device=p.device)[:3]
+    a = (1.0 - Tcum[-1]) if alpha_mode else torch.ones_like(Tcum[-1])
+    return torch.cat([rgb, a.unsqueeze(-1)], dim=-1)
+
+
+class _AllToAllStrips(torch.autograd.Function):
+    """``all_to_all_single`` of equal image strips; its adjoint is the same exchange of the gradients."""
+
+    @staticmethod
+    def forward(ctx, send, group):
+        ctx.group = group
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv.view(-1), send.contiguous().view(-1), group=group)
+        return recv
+
+    @staticmethod
+    def backward(ctx, g):
+        back = torch.empty_like(g)
+        dist.all_to_all_single(back.view(-1), g.contiguous().view(-1), group=ctx.group)
+        return back, None
+
+
+def render_sort_last_differentiable(sub: torch.Tensor, cam, tf, P: RenderParams, grid: Tuple[int, int, int],
+                                    group=None, storage: Optional[torch.dtype] = None):
+    """Differentiable cfg5: this rank renders the partial of ITS sub-box (``sub`` = voxels
+    ``shard_box(P.dims, grid, rank)`` inclusive, fp32 or fp16, ``requires_grad`` as wanted) with
+    :func:`api.render_shard`, image strips are exchanged by ONE differentiable ``all_to_all_single``
+    and this rank composites ITS strip front to back.  Returns ``(strip [rows,W,4], row0)``: rows
+    ``row0 .. row0+rows`` of the frame (rows beyond ``H`` are padding).  Build the loss from the
+    strip (each pixel belongs to exactly one rank, so the ranks' losses add up to the frame's);
+    ``loss.backward()`` then leaves dL/d(sub) on the rank that stores those voxels — halo voxels are
+    stored by two shards, each holding its own cells' share — and dL/dtf as this rank's share:
+    finish with :func:`allreduce_gradients` on tf."""
+    from . import api
+    rank, R = _world(group)
+    if grid[0] * grid[1] * grid[2] != R:
+        raise ValueError(f"grid {grid} does not match world size {R}")
+    W, H = P.imageSize
+    Pc = P.with_camera(cam) if cam is not None else P
+    lo, hi, _ = shard_box(Pc.dims, grid, rank)
+    partial = api.render_shard(sub, (lo, hi), Pc.dims, None, tf, Pc, storage=storage)
+    order = visibility_order(np.asarray(Pc.eye, dtype=np.float64), Pc, grid)
+    rows = padded_rows(H, R)
+    if R == 1:
+        return composite_over_differentiable(partial.reshape(1, H * W, 4), order, Pc.bgColor, Pc.alphaMode).reshape(H, W, 4), 0
+    pad = torch.zeros((R * rows - H, W, 4), dtype=torch.float32, device=partial.device)
+    pad[..., 3] = 1.0                                    # padding rows: empty partial (T = 1)
+    send = torch.cat([partial, pad], dim=0).reshape(R, rows, W, 4)
+    recv = _AllToAllStrips.apply(send, group)            # recv[j] = rank j's partial of MY strip
+    mine = composite_over_differentiable(recv.reshape(R, rows * W, 4), order, Pc.bgColor, Pc.alphaMode)
+    return mine.reshape(rows, W, 4), rank * rows
+
+
 def render_sort_last(shard_volume, cam, tf, P: RenderParams, grid: Tuple[int, int, int], group=None) -> torch.Tensor:
     """One frame of a brick-sharded volume (BASELINE config 5) through NCCL: this rank marches every
     ray through its own sub-box only (``shard_volume`` = Volume(..., shard=shard_box(dims, grid,

@@ -211,6 +211,70 @@ def test_differentiable_tiles_world2_gradients_match_single_process():
     assert np.abs(gt - t.grad.numpy()).max() <= 1e-5 * max(1.0, float(t.grad.abs().max()))
 
 
+def _sl_grad_worker(rank, world, port, W, H, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mri_raytracer_b200 import api, dist as mdist, RenderParams
+        P = RenderParams(imageSize=(W, H), dims=(32, 32, 32), voxelSize=(0.05, 0.05, 0.05), volMin=(-0.8, -0.8, -0.8),
+                         eye=(3.0, 2.0, 1.0), bgColor=(0.1, 0.2, 0.3), alphaMode=1)
+        w = torch.randn(H, W, 4, generator=torch.Generator().manual_seed(200 + rank)).requires_grad_(True)
+        # stands in for the CUDA shard renderer: a differentiable partial that depends on this rank's parameters only
+        api.render_shard = lambda sub, shard, gdims, cam, tf, Pp, storage=None: torch.sigmoid(sub)
+        strip, row0 = mdist.render_sort_last_differentiable(w, None, None, P, (2, 1, 1))
+        rows = strip.shape[0]
+        valid = max(0, min(rows, H - row0))
+        wmap = torch.linspace(0.5, 1.5, H * W * 4).reshape(H, W, 4)
+        loss = (strip[:valid] * wmap[row0:row0 + valid]).sum()
+        loss.backward()
+        ret.put((rank, float(loss), w.grad.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("W,H", [(16, 16), (21, 27)])
+def test_differentiable_sort_last_world2(W, H):
+    """Differentiable all_to_all of strips + tensor-op composite: the ranks' strip losses add up to the
+    whole-frame loss and every rank ends up with d(total loss)/d(its own partial's parameters)."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sl_grad_worker, args=(r, 2, port, W, H, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, l, g = ret.get()
+        got[r] = (l, g)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    from mri_raytracer_b200 import dist as mdist, RenderParams
+    from dist_fakes import composite_over_torch
+    P = RenderParams(imageSize=(W, H), dims=(32, 32, 32), voxelSize=(0.05, 0.05, 0.05), volMin=(-0.8, -0.8, -0.8),
+                     eye=(3.0, 2.0, 1.0), bgColor=(0.1, 0.2, 0.3), alphaMode=1)
+    ws = [torch.randn(H, W, 4, generator=torch.Generator().manual_seed(200 + r)).requires_grad_(True) for r in range(2)]
+    order = mdist.visibility_order(np.array(P.eye, dtype=np.float64), P, (2, 1, 1))
+    img = composite_over_torch(torch.stack([torch.sigmoid(w).reshape(-1, 4) for w in ws]), order, P.bgColor, 1).reshape(H, W, 4)
+    wmap = torch.linspace(0.5, 1.5, H * W * 4).reshape(H, W, 4)
+    loss = (img * wmap).sum()
+    loss.backward()
+    assert abs(got[0][0] + got[1][0] - float(loss)) <= 1e-4 * abs(float(loss))
+    for r in range(2):
+        assert np.abs(got[r][1] - ws[r].grad.numpy()).max() <= 1e-5
+
+
+def test_composite_over_differentiable_matches_the_loop():
+    from mri_raytracer_b200 import dist as mdist
+    from dist_fakes import composite_over_torch
+    parts = torch.rand(5, 37, 4, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    order = [3, 0, 4, 1, 2]
+    for am in (0, 1):
+        a = mdist.composite_over_differentiable(parts, order, (0.1, 0.2, 0.3), am)
+        b = composite_over_torch(parts, order, (0.1, 0.2, 0.3), am)
+        assert torch.allclose(a, b, atol=1e-12)
+
+
 # ----------------------------------------------------------------------------- PeerFramebuffer fallback (no symmetric memory)
 def _fb_worker(rank, world, port, partition, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

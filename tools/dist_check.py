@@ -1,7 +1,7 @@
 """Multi-GPU correctness check (torchrun, 2+ GPUs): the distributed framebuffer (tile and view
 partitions, striped and root owners, several batches back to back without host syncs), the NCCL
-gather paths, sort-last through NCCL and through peer memory, and data-parallel differentiable
-rendering — all against single-GPU renders.  Prints one line per check and ALL OK / SOME FAILED."""
+gather paths, sort-last through NCCL and through peer memory, data-parallel differentiable
+rendering and differentiable sort-last (sharded fp32 / fp16 backward) — all against single-GPU renders.  Prints one line per check and ALL OK / SOME FAILED."""
 import os, sys
 from dataclasses import replace
 from pathlib import Path
@@ -84,6 +84,28 @@ img = mdist.render_differentiable(v2, None, t2, Pg)
 mdist.allreduce_gradients([v2, t2])
 rv = float((v2.grad - v1.grad).abs().max() / v1.grad.abs().max()); rt = float((t2.grad - t1.grad).abs().max() / t1.grad.abs().max())
 report("differentiable tiles + all_reduce gradients == single GPU", rv <= 1e-5 and rt <= 1e-5, f"rel dvol {rv:.1e} dtf {rt:.1e}")
+# 4. differentiable sort-last (cfg5 trains): every rank differentiates its own sub-box; the strips' losses add
+#    up to the frame's, dL/d(sub) stays on the rank that stores the voxels, dL/dtf is all-reduced
+grid = mdist.shard_grid(world)
+for storage in (None, torch.float16):
+    vfull = volc if storage is None else volc.half().float()
+    lo, hi, _ = mdist.shard_box(dims, grid, rank)
+    sub = mdist.slice_shard(vfull, lo, hi).clone().requires_grad_(True)
+    t3 = tfs.clone().requires_grad_(True)
+    wg = torch.rand((136, 200, 4), generator=torch.Generator().manual_seed(4)).to(dev)
+    strip, row0 = mdist.render_sort_last_differentiable(sub, None, t3, Ps, grid, storage=storage)
+    valid = max(0, min(strip.shape[0], 136 - row0))
+    (strip[:valid] * wg[row0:row0 + valid]).sum().backward()
+    mdist.allreduce_gradients([t3])
+    vr = vfull.clone().requires_grad_(True); tr = tfs.clone().requires_grad_(True)
+    (api.render(vr, None, tr, Ps) * wg).sum().backward()
+    # assemble the global gradient from the shards' (halo voxels are shared: SUM)
+    gfull = torch.zeros_like(vfull)
+    gfull[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = sub.grad.float()
+    dist.all_reduce(gfull)
+    rv = float((gfull - vr.grad).abs().max() / vr.grad.abs().max()); rt = float((t3.grad - tr.grad).abs().max() / tr.grad.abs().max())
+    report(f"differentiable sort-last (storage={'f16' if storage else 'f32'}) gradients == single GPU", rv <= 1e-3 and rt <= 1e-3,
+           f"rel dvol {rv:.1e} dtf {rt:.1e}")
 if rank == 0:
     print("ALL OK" if ok_all else "SOME FAILED", flush=True)
 dist.destroy_process_group()
