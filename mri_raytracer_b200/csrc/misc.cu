@@ -198,42 +198,60 @@ mrt_fold_kernel(const float* __restrict__ planar, int C, int X, int Y, int Z, si
 #endif
 #define MRT_STR2(x) #x
 #define MRT_STR(x) MRT_STR2(x)
+#ifndef MRT_FOLD_SL1
+#define MRT_FOLD_SL1 2             // slices per trip of the single-channel fold (9 * SL loads in flight per thread)
+#endif
+#ifndef MRT_FOLD_G4
+#define MRT_FOLD_G4 9              // scanlines per trip of the 3-4 channel quad fold (G * C loads in flight per thread)
+#endif
 #define MRT_FOLD_COLS 248          // 31 bricks of 8 columns (+1 halo column) per 256-thread CTA
 template <int C>
 __global__ void __launch_bounds__(256)
 mrt_fold_occ_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
-                    float w0, float w1, float w2, float w3, float inv_wsum, int nbx, int nby,
+                    float w0, float w1, float w2, float w3, float inv_wsum, int nbx, int nby, int cols,
                     float* __restrict__ folded, float2* __restrict__ minmax) {
   __shared__ float s_mn[256], s_mx[256];
-  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  // `cols` (a multiple of 8, <= MRT_FOLD_COLS) columns per CTA, chosen by the launcher so that the
+  // chunks of a scanline are equal (256 -> 2 x 128, not 248 + 8); blockDim >= cols + 1
+  const int chunks = (X + cols - 1) / cols;
   const int chunk = blockIdx.x % chunks, by = (blockIdx.x / chunks) % nby, bz = blockIdx.x / (chunks * nby);
-  const int x0 = chunk * MRT_FOLD_COLS;
+  const int x0 = chunk * cols;
   const int x = x0 + threadIdx.x;
-  // columns [x0, x0+248] are read (the last one only as the halo of brick 30); [x0, x0+247] are stored
-  const bool rd = (threadIdx.x <= MRT_FOLD_COLS) && (x < X);
-  const bool wr = rd && (threadIdx.x < MRT_FOLD_COLS);
+  // columns [x0, x0+cols] are read (the last one only as the halo of the last brick); [x0, x0+cols) are stored
+  const bool rd = ((int)threadIdx.x <= cols) && (x < X);
+  const bool wr = rd && ((int)threadIdx.x < cols);
   const size_t nvox = (size_t)X * Y * Z;
   const int y0 = by << 3, z0 = bz << 3;
   const int ny = min(9, Y - y0), nz = min(9, Z - z0);
   float mn = FLT_MAX, mx = -FLT_MAX;
   if (rd) {
-    auto blend = [&](size_t src) {
-      float v = __ldg(planar + src) * w0;
-      if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
-      if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
-      if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
-      return v * inv_wsum;
-    };
     // SL slices per trip: all their loads are issued before the first dependent store, so a thread
-    // keeps 9 * SL * C loads in flight (one channel with SL = 1 ran at a third of the HBM rate)
-    constexpr int SL = C == 1 ? 3 : (C == 2 ? 2 : 1);
+    // keeps 9 * SL * C loads in flight.  The loads are UNCONDITIONAL (row / slice indices clamped into
+    // the volume, the value is simply not used): with `cond ? load : 0` the compiler emitted one
+    // scanline's loads at a time, each followed by its consumer — a chain of 81 dependent DRAM round
+    // trips per thread (ncu: long_scoreboard 15 stalls per issue at 39 % of the DRAM peak)
+    constexpr int SL = C == 1 ? MRT_FOLD_SL1 : (C == 2 ? 2 : 1);
     for (int lz = 0; lz < nz; lz += SL) {
+      float raw[SL][9][C];
+#pragma unroll
+      for (int s = 0; s < SL; ++s)
+_Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
+        for (int ly = 0; ly < 9; ++ly) {
+          const size_t src = ((size_t)min(z0 + lz + s, Z - 1) * Y + min(y0 + ly, Y - 1)) * X + x;
+#pragma unroll
+          for (int c = 0; c < C; ++c) raw[s][ly][c] = __ldg(planar + (size_t)c * nvox + src);
+        }
       float v[SL][9];
 #pragma unroll
       for (int s = 0; s < SL; ++s)
 _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
-        for (int ly = 0; ly < 9; ++ly)
-          v[s][ly] = (lz + s < nz && ly < ny) ? blend(((size_t)(z0 + lz + s) * Y + (y0 + ly)) * X + x) : 0.0f;
+        for (int ly = 0; ly < 9; ++ly) {
+          float t = raw[s][ly][0] * w0;
+          if (C > 1) t = fmaf(raw[s][ly][1], w1, t);
+          if (C > 2) t = fmaf(raw[s][ly][2], w2, t);
+          if (C > 3) t = fmaf(raw[s][ly][3], w3, t);
+          v[s][ly] = t * inv_wsum;
+        }
 #pragma unroll
       for (int s = 0; s < SL; ++s)
 _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
@@ -249,8 +267,8 @@ _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
   s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
   __syncthreads();
   const int bxl = threadIdx.x;                       // local brick
-  const int bx = chunk * (MRT_FOLD_COLS >> 3) + bxl;
-  if (bxl < (MRT_FOLD_COLS >> 3) && bx < nbx) {
+  const int bx = chunk * (cols >> 3) + bxl;
+  if (bxl < (cols >> 3) && bx < nbx) {
     float a = FLT_MAX, b = -FLT_MAX;
 #pragma unroll
     for (int i = 0; i <= 8; ++i) { a = fminf(a, s_mn[(bxl << 3) + i]); b = fmaxf(b, s_mx[(bxl << 3) + i]); }
@@ -260,8 +278,8 @@ _Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
 // Fold + occupancy + QUAD layout in one pass: as above, but the blended value goes straight into
 // the march's 16 B/voxel quad layout (element (x,y,z) = v(x,y), v(x+1,y), v(x,y+1), v(x+1,y+1) of slice
 // z; march.cuh VoxT<1,3>) — the scalar folded volume is only written when `folded` is non-null.  The
-// x+1 neighbour comes from the next lane (the last lane of a warp re-blends it: L1 hits on the loads
-// its neighbour warp issues anyway), the y+1 row is the next iteration of the scanline loop.
+// x+1 neighbour comes from the next lane (a warp reads 32 columns and owns 31), the y+1 row is the
+// next iteration of the scanline loop.
 template <int C>
 __global__ void __launch_bounds__(256)
 mrt_fold_occ_quad_kernel(const float* __restrict__ planar, int X, int Y, int Z, size_t pitchY, size_t pitchZ,
@@ -271,46 +289,61 @@ mrt_fold_occ_quad_kernel(const float* __restrict__ planar, int X, int Y, int Z, 
   const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
   const int chunk = blockIdx.x % chunks, by = (blockIdx.x / chunks) % nby, bz = blockIdx.x / (chunks * nby);
   const int x0 = chunk * MRT_FOLD_COLS;
-  const int x = x0 + threadIdx.x;
-  const bool rd = (threadIdx.x <= MRT_FOLD_COLS) && (x < X);
-  const bool wr = rd && (threadIdx.x < MRT_FOLD_COLS);
-  const int lane = threadIdx.x & 31;
-  const int xn = min(x + 1, X - 1);                      // clamped neighbour column
+  // a warp owns 31 columns and reads 32: lane 31 holds the x+1 neighbour of lane 30 (= the next warp's
+  // first column; an L1 hit), so every neighbour comes from a shuffle.  8 warps x 31 = 248 columns.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = 31 * warp + lane;                      // 0..248 within the chunk
+  const int x = x0 + col;
+  const bool rd = x < X;
+  const bool wr = rd && lane < 31;
+  const int xc = min(x, X - 1);                          // loads are unconditional: clamped into the volume
   const size_t nvox = (size_t)X * Y * Z;
   const int y0 = by << 3, z0 = bz << 3;
   const int ny = min(9, Y - y0), nz = min(9, Z - z0);
   float mn = FLT_MAX, mx = -FLT_MAX;
-  auto blend = [&](size_t src) {
-    float v = __ldg(planar + src) * w0;
-    if (C > 1) v = fmaf(__ldg(planar + nvox + src), w1, v);
-    if (C > 2) v = fmaf(__ldg(planar + 2 * nvox + src), w2, v);
-    if (C > 3) v = fmaf(__ldg(planar + 3 * nvox + src), w3, v);
-    return v * inv_wsum;
-  };
+  // G scanlines per trip: their G*C loads are issued back to back before the first consumer (see
+  // mrt_fold_occ_kernel: conditional loads serialised into one DRAM round trip per scanline)
+  constexpr int G = C <= 2 ? 9 : MRT_FOLD_G4;
   for (int lz = 0; lz < nz; ++lz) {
     const int z = z0 + lz;
     float pv = 0.0f, pn = 0.0f;                          // previous scanline: v(x, y-1), v(x+1, y-1)
-_Pragma(MRT_STR(unroll MRT_FOLD_UNROLL))
-    for (int ly = 0; ly < ny; ++ly) {
-      const int y = y0 + ly;
-      const size_t row = ((size_t)z * Y + y) * X;
-      float v = 0.0f;
-      if (rd) {
-        v = blend(row + x);
-        if (wr && folded && ly < 8 && lz < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v;
-        mn = fminf(mn, v); mx = fmaxf(mx, v);
+#pragma unroll
+    for (int g0 = 0; g0 < 9; g0 += G) {
+      float raw[G][C];
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+        if (g0 + r < 9) {
+          const size_t src = ((size_t)z * Y + min(y0 + g0 + r, Y - 1)) * X + xc;
+#pragma unroll
+          for (int c = 0; c < C; ++c) raw[r][c] = __ldg(planar + (size_t)c * nvox + src);
+        }
       }
-      float vn = __shfl_down_sync(0xffffffffu, v, 1);
-      if (lane == 31 && wr) vn = blend(row + xn);       // (a storing thread always has its neighbour column in range or clamped)
-      if (x + 1 >= X) vn = v;
-      if (wr && lz < 8) {
-        if (ly > 0) quad[(size_t)x + (size_t)(y - 1) * qY + (size_t)z * qZ] = make_float4(pv, pn, v, vn);
-        if (ly == ny - 1 && ny < 9) quad[(size_t)x + (size_t)y * qY + (size_t)z * qZ] = make_float4(v, vn, v, vn);   // y == Y-1
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+        const int ly = g0 + r;
+        if (ly < 9 && ly < ny) {                         // (uniform over the CTA)
+          const int y = y0 + ly;
+          float v = raw[r][0] * w0;
+          if (C > 1) v = fmaf(raw[r][1], w1, v);
+          if (C > 2) v = fmaf(raw[r][2], w2, v);
+          if (C > 3) v = fmaf(raw[r][3], w3, v);
+          v *= inv_wsum;
+          if (rd) {
+            if (wr && folded && ly < 8 && lz < 8) folded[(size_t)x + (size_t)y * pitchY + (size_t)z * pitchZ] = v;
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+          }
+          float vn = __shfl_down_sync(0xffffffffu, v, 1);
+          if (x + 1 >= X) vn = v;
+          if (wr && lz < 8) {
+            if (ly > 0) quad[(size_t)x + (size_t)(y - 1) * qY + (size_t)z * qZ] = make_float4(pv, pn, v, vn);
+            if (ly == ny - 1 && ny < 9) quad[(size_t)x + (size_t)y * qY + (size_t)z * qZ] = make_float4(v, vn, v, vn);   // y == Y-1
+          }
+          pv = v; pn = vn;
+        }
       }
-      pv = v; pn = vn;
     }
   }
-  s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
+  if (lane < 31 || warp == 7) { s_mn[col] = mn; s_mx[col] = mx; }       // column 248 (the last halo) comes from warp 7's lane 31
   __syncthreads();
   const int bxl = threadIdx.x;
   const int bx = chunk * (MRT_FOLD_COLS >> 3) + bxl;
@@ -346,10 +379,13 @@ cudaError_t mrt_launch_fold_occ(const float* planar, int C, int X, int Y, int Z,
   int64_t pY, pZ;
   mrt_layout(1, X, Y, Z, &pY, &pZ);
   const int nbx = (X + 7) >> 3, nby = (Y + 7) >> 3, nbz = (Z + 7) >> 3;
-  const int chunks = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const int chunks0 = (X + MRT_FOLD_COLS - 1) / MRT_FOLD_COLS;
+  const int cols = (((X + chunks0 - 1) / chunks0) + 7) & ~7;              // equal chunks, whole bricks, <= MRT_FOLD_COLS
+  const int chunks = (X + cols - 1) / cols;
+  const int nthreads = (cols + 1 + 31) & ~31;                             // one thread per column + the halo column
   const long long grid = (long long)chunks * nby * nbz;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-#define MRT_FO(CC) mrt_fold_occ_kernel<CC><<<(int)grid, 256, 0, st>>>(planar, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, nbx, nby, folded, (float2*)minmax)
+#define MRT_FO(CC) mrt_fold_occ_kernel<CC><<<(int)grid, nthreads, 0, st>>>(planar, X, Y, Z, pY, pZ, wgt[0], wgt[1], wgt[2], wgt[3], inv_wsum, nbx, nby, cols, folded, (float2*)minmax)
   switch (C) {
     case 1: MRT_FO(1); break;
     case 2: MRT_FO(2); break;
