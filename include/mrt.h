@@ -401,6 +401,24 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
                         void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray, uint64_t* stats,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* ------------------------------------------------ soft (learnable) occupancy
+ * docs/DifferentiableRendering.md section 11 (:202-206; maths only, no reference code): "hard empty-space
+ * skipping -> continuous occupancy o(x) in [0,1] learned and used multiplicatively".  `soft_occ` holds one
+ * float per 8^3 brick of the occupancy grid ([nbz][nby][nbx], mrt_brick_count entries); a sample whose
+ * trilinear base cell lies in brick b uses sigma' = soft_occ[b] * sigma in the compositing of
+ * brats_rt.slang:135-139.  soft_occ == 1 everywhere reproduces mrt_render_forward bit for bit; hard
+ * skipping (skip_levels) stays exact next to it, because a brick the classification proves empty has
+ * sigma == 0 whatever its occupancy.  The backward returns dL/dsoft_occ[b] = sum of dL/dsigma'_i * sigma_i
+ * over the samples of brick b (ACCUMULATED into; caller zeroes) next to dL/dvolume and dL/dtf (both now
+ * through sigma = o * sigma).  fp32 unsharded volumes, no overlays; whole-ray backward. */
+int mrt_render_forward_soft_occ(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                const uint8_t* skip_levels, const float* soft_occ, float* out_rgba,
+                                int32_t tile_begin, int32_t tile_end, void* stream);
+int mrt_render_backward_soft_occ(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                 const float* soft_occ, const float* out_rgba, const float* dL_dout,
+                                 void* dL_dvol, float* dL_dtf, float* dL_dsoft_occ, void* scratch,
+                                 int32_t tile_begin, int32_t tile_end, void* stream);
+
 /* ------------------------------------------------ differentiable adaptive sampling
  * docs/DifferentiableRendering.md section 7 (:131-148; maths only, no reference code): per ray a
  * coarse pass of n_coarse uniform samples gives importance weights w_k = sigma_k + eps_w, their

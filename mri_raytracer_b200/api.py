@@ -935,6 +935,69 @@ class _AdaptiveFn(torch.autograd.Function):
         return gvol, dtf, None, None, None, None
 
 
+class _SoftOccFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planar, tf, occ, P: RenderParams):
+        Cn = planar.shape[0]
+        packed = pack_volume(planar.detach())
+        occ_c = occ.detach().contiguous()
+        W, H = P.imageSize
+        bits = None
+        if P.skipEmpty and P.tMode == "indexed":
+            bits = classify_bricks(P, build_occupancy(packed, Cn, P.dims), Cn, tf)
+        out = torch.empty((H, W, 4), dtype=torch.float32, device=planar.device)
+        s = P.to_struct()
+        check(lib().mrt_render_forward_soft_occ(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                                _ptr(bits), occ_c.data_ptr(), out.data_ptr(), 0, _tiles.tile_count(W, H),
+                                                _stream()), "render_forward_soft_occ")
+        ctx.P, ctx.Cn, ctx.has_tf = P, Cn, tf is not None
+        ctx.save_for_backward(packed, tf if tf is not None else torch.empty(0, device=planar.device), occ_c, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        packed, tf, occ, out = ctx.saved_tensors
+        tf = tf if ctx.has_tf else None
+        P, Cn = ctx.P, ctx.Cn
+        W, H = P.imageSize
+        want_vol, want_tf, want_occ = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tf, ctx.needs_input_grad[2]
+        dvol = torch.zeros_like(packed) if want_vol else None
+        ntf = tf.shape[0] if tf is not None else 2
+        dtf = torch.zeros((ntf, 4), dtype=torch.float32, device=packed.device) if want_tf else None
+        docc = torch.zeros_like(occ) if want_occ else None
+        scratch = torch.empty((lib().mrt_backward_scratch_bytes(W, H, 1, ntf, 1) // 4,), dtype=torch.float32, device=packed.device)
+        s = P.to_struct()
+        check(lib().mrt_render_backward_soft_occ(C.byref(s), packed.data_ptr(), Cn, _ptr(tf), 0 if tf is None else tf.shape[0],
+                                                 occ.data_ptr(), out.data_ptr(), g.contiguous().data_ptr(), _ptr(dvol), _ptr(dtf),
+                                                 _ptr(docc), scratch.data_ptr(), 0, _tiles.tile_count(W, H), _stream()),
+              "render_backward_soft_occ")
+        gvol = unpack_volume(dvol, Cn, P.dims) if want_vol else None
+        return gvol, dtf, docc, None
+
+
+def render_soft_occupancy(volume: torch.Tensor, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams,
+                          occupancy: torch.Tensor) -> torch.Tensor:
+    """Differentiable rendering with a learnable, continuous occupancy (docs/DifferentiableRendering.md
+    section 11, :202-206: the smooth replacement of hard empty-space skipping): ``occupancy`` is a
+    float32 ``[nbz, nby, nbx]`` tensor over the 8^3-voxel brick grid, values in [0,1]; a sample in brick
+    b composites with ``sigma' = occupancy[b] * sigma``.  Differentiable w.r.t. ``volume`` ``[C,Z,Y,X]``,
+    ``tf`` and ``occupancy``; ``occupancy == 1`` reproduces :func:`render`.  -> ``[H,W,4]``."""
+    _need_cuda(volume, "volume", torch.float32)
+    _need_cuda(occupancy, "occupancy", torch.float32)
+    P = params if camera is None else params.with_camera(camera)
+    Z, Y, X = (int(v) for v in volume.shape[1:])
+    if tuple(P.dims) != (X, Y, Z):
+        raise ValueError(f"params.dims {P.dims} != volume dims {(X, Y, Z)}")
+    nb = ((Z + 7) // 8, (Y + 7) // 8, (X + 7) // 8)
+    if tuple(occupancy.shape) != nb:
+        raise ValueError(f"occupancy must be [nbz,nby,nbx] = {nb}, got {tuple(occupancy.shape)}")
+    if tf is not None:
+        _need_cuda(tf, "tf", torch.float32)
+    P = replace(P, tfMode=1 if tf is not None else 0, showSeg=0, showPred=0)
+    P.validate()
+    return _SoftOccFn.apply(volume, tf, occupancy, P)
+
+
 def render_adaptive(volume: torch.Tensor, camera: Optional[Camera], tf: Optional[torch.Tensor], params: RenderParams,
                     n_coarse: int = 16, n_fine: int = 64, eps_w: float = 1e-3) -> torch.Tensor:
     """Differentiable adaptive sampling (docs/DifferentiableRendering.md section 7, :131-148): a coarse

@@ -247,12 +247,22 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
         const float val = mrt_window<GENERIC>(P, raw);
         if (mine && (P.tfMode || val > 0.0f)) {
           const float4 rgba = mrt_tf_lookup(s_tf_addr, nm1, val, &j0, &fr);
-          const float alpha = mrt_alpha(P, rgba.w);
+          float so = 1.0f; int obid = 0;           // soft occupancy (section 11): sigma' = o(brick) * sigma
+          if (GENERIC) {
+            if (P.occ != nullptr) { obid = mrt_brick_id(P, c.ix(), c.iy(), c.iz()); so = __ldg(P.occ + obid); }
+          }
+          const float alpha = mrt_alpha(P, rgba.w * so);
           const float aT = alpha * T;
           const float gc = G.x * rgba.x + G.y * rgba.y + G.z * rgba.z;
           prefix = fmaf(aT, gc, prefix);
           const float suffix = S_tot - prefix;
-          const float dsig = dt * ((1.0f - alpha) * T * gc - suffix - tn_term);
+          float dsig = dt * ((1.0f - alpha) * T * gc - suffix - tn_term);        // dL/dsigma'
+          if (GENERIC) {
+            if (P.occ != nullptr) {
+              if (P.docc != nullptr && dsig * rgba.w != 0.0f) atomicAdd(P.docc + obid, dsig * rgba.w);   // dL/do = dL/dsigma' * sigma
+              dsig *= so;                                                            // dL/dsigma
+            }
+          }
           const float dr = aT * G.x, dg = aT * G.y, db = aT * G.z;
           addtf = want_tf;
           g4 = make_float4(dr, dg, db, dsig);
@@ -501,8 +511,8 @@ cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews,
     for (int v = 0; v < nviews; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)v * 12 + i];
   }
   const bool lab = (P.showSeg || P.showPred);
-  const bool gen = (P.tMode != 0) || (P.gamma != 1.0f);
-  const bool skip = P.skip && A.flat_levels != nullptr && A.minmax != nullptr && P.tMode == 0 && packed_ch == 1 && !P.shard;
+  const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (P.occ != nullptr);
+  const bool skip = P.skip && A.flat_levels != nullptr && A.minmax != nullptr && P.tMode == 0 && packed_ch == 1 && !P.shard && P.occ == nullptr;
   if (P.half) {                        // fp16 storage: single channel, no overlays, indexed stepping (c_api.cu checks)
     if (P.half != 1 || packed_ch != 1 || lab || gen) return cudaErrorInvalidValue;
     return skip ? launch_bwd<1, false, true, false, 1>(P, B, nviews, vol, A, st)

@@ -256,6 +256,7 @@ static int derive(const MrtParams* M, int C, int tfN, bool have_bits, int tile_b
   if (K->tfMode) MRT_REQUIRE(tfN >= 2 && tfN <= MRT_MAX_TF, "tfN=%d outside 2..%d", tfN, MRT_MAX_TF);
   K->skip = (M->skipEmpty && have_bits && K->tMode == 0) ? 1 : 0;
   K->nbx = (ldim[0] + 7) >> 3; K->nby = (ldim[1] + 7) >> 3; K->nbz = (ldim[2] + 7) >> 3;
+  K->occ = nullptr; K->docc = nullptr;
   const int nt = mrt_tiles_x_(K->W) * mrt_tiles_y_(K->H);
   MRT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt,
               "tile range [%d,%d) outside [0,%d]", tile_begin, tile_end, nt);
@@ -366,6 +367,45 @@ int mrt_render_forward(const MrtParams* params, const void* packed, int32_t C, c
   cudaError_t e = mrt_launch_forward(K, nullptr, 1, mrt_packed_channels(C), packed, tf, skip_levels, labels, preds,
                                      out_rgba, out_T, out_counts, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward");
+}
+
+// ---------------------------------------------------------------- soft (learnable) occupancy
+static int soft_occ_common(const char* who, const KParams& K) {
+  if (K.half || K.shard || K.showSeg || K.showPred)
+    return fail(MRT_ERR_UNSUPPORTED, "%s: fp32 unsharded volumes without overlays", who);
+  return MRT_OK;
+}
+int mrt_render_forward_soft_occ(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                const uint8_t* skip_levels, const float* soft_occ, float* out_rgba,
+                                int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && soft_occ, "render_forward_soft_occ: null pointer");
+  KParams K;
+  if (int r = derive(params, C, tfN, skip_levels != nullptr, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_forward_soft_occ: tfMode=1 needs tf");
+  K.showSeg = K.showPred = 0;
+  if (int r = soft_occ_common("render_forward_soft_occ", K)) return r;
+  K.occ = soft_occ;
+  cudaError_t e = mrt_launch_forward(K, nullptr, 1, mrt_packed_channels(C), packed, tf, skip_levels, nullptr, nullptr,
+                                     out_rgba, nullptr, nullptr, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_soft_occ");
+}
+int mrt_render_backward_soft_occ(const MrtParams* params, const void* packed, int32_t C, const float* tf, int32_t tfN,
+                                 const float* soft_occ, const float* out_rgba, const float* dL_dout,
+                                 void* dL_dvol, float* dL_dtf, float* dL_dsoft_occ, void* scratch,
+                                 int32_t tile_begin, int32_t tile_end, void* stream) {
+  MRT_REQUIRE(packed && out_rgba && dL_dout && scratch && soft_occ, "render_backward_soft_occ: null pointer");
+  MRT_REQUIRE(dL_dvol || dL_dtf || dL_dsoft_occ, "render_backward_soft_occ: nothing to differentiate");
+  KParams K;
+  if (int r = derive(params, C, tfN, false, tile_begin, tile_end, &K)) return r;
+  MRT_REQUIRE(!K.tfMode || tf != nullptr, "render_backward_soft_occ: tfMode=1 needs tf");
+  K.showSeg = K.showPred = 0;
+  if (int r = soft_occ_common("render_backward_soft_occ", K)) return r;
+  K.occ = soft_occ; K.docc = dL_dsoft_occ;
+  MrtBwdArgs A = {};
+  A.tf = tf; A.out_rgba = out_rgba; A.dL_dout = dL_dout;
+  A.dvol = dL_dvol; A.dtf = dL_dtf; A.scratch = scratch;
+  cudaError_t e = mrt_launch_backward(K, nullptr, 1, mrt_packed_channels(C), packed, A, (cudaStream_t)stream);
+  return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward_soft_occ");
 }
 
 int mrt_render_forward_tma(const MrtParams* params, const void* packed, const float* tf, int32_t tfN,

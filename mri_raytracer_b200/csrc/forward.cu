@@ -155,18 +155,20 @@ mrt_fwd_kernel(const __grid_constant__ KParams P,
       constexpr bool TFM = decltype(tfm)::value, INT = decltype(inter)::value;
       const Cell c = mrt_cell_t<!INT>(ppx, ppy, ppz, hix, hiy, hiz);
       const float val = mrt_window<GENERIC>(P, mrt_sample_raw<NCH, HALF>(P, vol, c));
+      float so = P.neg_dt_log2e;               // soft occupancy (section 11): sigma' = o(brick) * sigma
+      if (GENERIC) { if (P.occ != nullptr) so *= __ldg(P.occ + mrt_brick_id(P, c.ix(), c.iy(), c.iz())); }
       // alpha = 1 - e, e = exp(-sigma dt) (:137); C += alpha T rgb, T *= 1 - alpha (:138-139) as
       // T' = T e, alpha T = T - T'  (same quantities, two instructions less)
       if (TFM) {
         const float4 rgba = mrt_tf_lookup_strided(s_tf_adj, s_tf_stride, nm1, val);
-        const float e = mrt_ex2(rgba.w * P.neg_dt_log2e);
+        const float e = mrt_ex2(rgba.w * so);
         const float Tn = T * (on ? e : 1.0f);
         const float aT = T - Tn;
         Cr = fmaf(aT, rgba.x, Cr); Cg = fmaf(aT, rgba.y, Cg); Cb = fmaf(aT, rgba.z, Cb);
         T = Tn;
       } else {
         // :135 — val == 0 gives e == 1 exactly: the (val > 0) gate is implicit
-        const float e = mrt_ex2(val * P.ia * P.neg_dt_log2e);              // :136-137
+        const float e = mrt_ex2(val * P.ia * so);                          // :136-137
         const float Tn = T * (on ? e : 1.0f);
         const float c1 = (T - Tn) * val;                                   // :138
         Cr += c1; Cg += c1; Cb += c1;
@@ -570,7 +572,7 @@ static cudaError_t mrt_launch_forward_to(const KParams& P, const StripTargets& S
   }
   const bool lab = (P.showSeg || P.showPred);
   const bool skip = P.skip && levels != nullptr && P.tMode == 0;
-  const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr);
+  const bool gen = (P.tMode != 0) || (P.gamma != 1.0f) || (out_counts != nullptr) || (P.occ != nullptr);
   if (P.half) {            // fp16 / u8 / quad voxels: single channel, no label overlays (c_api.cu checks)
     if (packed_ch != 1 || lab) return cudaErrorInvalidValue;
 #define MRT_NARROW(H) \

@@ -47,7 +47,14 @@ struct KParams {
   unsigned base_off;      // slo.x + slo.y*pitchY + slo.z*pitchZ, subtracted from global sample indices
   unsigned tdiv_mul;      // floor(2^32/tiles_x)+1 when tile/tiles_x == umulhi(tile, tdiv_mul) for every tile id, else 0
   unsigned idx_bias;      // base_off + 0x4b000000*(1 + pitchY + pitchZ) mod 2^32 (see mrt_sample_raw)
+  // soft occupancy (docs/DifferentiableRendering.md section 11: "hard empty-space skipping -> continuous
+  // occupancy o(x) in [0,1] learned and used multiplicatively"): one value per 8^3 brick, sigma' = o * sigma.
+  // GENERIC variants only; nullptr = off.  docc: where the backward accumulates dL/do.
+  const float* occ; float* docc;
 };
+__device__ __forceinline__ int mrt_brick_id(const KParams& P, int ix, int iy, int iz) {
+  return ((iz >> MRT_BRICK_SHIFT) * P.nby + (iy >> MRT_BRICK_SHIFT)) * P.nbx + (ix >> MRT_BRICK_SHIFT);
+}
 
 // Cameras of a batch of views rendered by ONE launch (blockIdx.y = view): everything else in
 // KParams is shared.  12 floats per view: eye, U, V, W.

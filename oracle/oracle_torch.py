@@ -231,7 +231,7 @@ def sample_counts(P, t0, t1, dtype=torch.float32):
 def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
            labels: Optional[torch.Tensor] = None, preds: Optional[torch.Tensor] = None,
            pixels=None, dtype=torch.float32, force_steps: Optional[torch.Tensor] = None,
-           chunk: int = 1 << 16, return_aux: bool = False, ray_delta=None):
+           chunk: int = 1 << 16, return_aux: bool = False, ray_delta=None, soft_occ: Optional[torch.Tensor] = None):
     """``brats_main`` (brats_rt.slang:85-168) restated on CPU.
 
     volume : [C,Z,Y,X] (C<=4) values; differentiable leaf allowed.
@@ -246,6 +246,10 @@ def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
              the clip and the sample times t_i are fixed — their autograd gradients are the
              dL/do, dL/dd of docs/DifferentiableRendering.md section 9 (:172-188, "x_i = o + t_i d
              with fixed t_i").
+    soft_occ : optional [nbz,nby,nbx] continuous occupancy over 8^3-voxel bricks
+             (docs/DifferentiableRendering.md section 11, :202-206: "continuous occupancy o(x) in [0,1]
+             learned and used multiplicatively"): a sample whose trilinear base cell lies in brick b
+             composites with sigma' = soft_occ[b] * sigma.  Maths-only in the reference: parity unpinned.
     Returns rgba [H,W,4] (or [N,4] with ``pixels``) and optionally aux dict with
     T, n_samples (clip count), n_taken (after ERT), ert_margin.
     """
@@ -343,8 +347,16 @@ def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
                 if gamma != 1.0:                              # :133 (pow(x,1)==x exactly)
                     val = torch.pow(val, torch.tensor(gamma, dtype=dtype))
                 newC, newT = hC, hT
+                so = None
+                if soft_occ is not None:                      # brick of the sample's base cell (sampleLinear's floor, :62-63)
+                    hi3 = torch.tensor([float(np.float32(n) - np.float32(1.001)) for n in (X, Y, Z)], dtype=dtype) \
+                        if dtype == torch.float32 else torch.tensor([X - 1.001, Y - 1.001, Z - 1.001], dtype=dtype)
+                    bi = torch.floor(torch.minimum(torch.maximum(pIdx.detach(), torch.zeros((), dtype=dtype)), hi3[None, :])).to(torch.int64) >> 3
+                    so = soft_occ.to(dtype)[bi[:, 2], bi[:, 1], bi[:, 0]]
                 if tfd is None:                               # :135-140
                     a = val * ia
+                    if so is not None:
+                        a = a * so
                     alpha = one - torch.exp(-a * dt)
                     gate = val > 0
                     alpha = torch.where(gate, alpha, torch.zeros_like(alpha))
@@ -352,7 +364,8 @@ def render(volume: torch.Tensor, P, tf: Optional[torch.Tensor] = None,
                     newT = newT * (one - alpha)
                 else:
                     rgba = tf_lookup(tfd, val)
-                    alpha = one - torch.exp(-rgba[:, 3] * dt)
+                    sig = rgba[:, 3] if so is None else rgba[:, 3] * so
+                    alpha = one - torch.exp(-sig * dt)
                     newC = newC + (alpha * newT)[:, None] * rgba[:, :3]
                     newT = newT * (one - alpha)
                 if show_seg:                                  # :143-151
