@@ -359,6 +359,24 @@ int mrt_render_forward_ckpt(const MrtParams* params, const MrtCamera* cams, int3
                             int32_t* k_end, int32_t* warp_kmax,
                             int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* ------------------------------------------------ one call per frame-loop step
+ * The reference's frame loop re-reads its UI state every frame (inr/viewer/brats_viewer.py:400-442: weights,
+ * window, cameras) and dispatches.  mrt_render_views_refold is that step for a device-resident planar
+ * volume in ONE call: mrt_fold_volume_occupancy_quad_f32 (blend + occupancy + quad layout) ->
+ * mrt_classify_bricks -> spans + mrt_render_forward_batch_sparse (dense frames [nviews][H][W][4]), all queued
+ * on `stream` back to back.  Frames are bit-identical to the separate calls.  Caller-owned scratch:
+ *   quad        mrt_packed_volume_bytes_quad(X,Y,Z) bytes     minmax  mrt_brick_count * 2 floats
+ *   skip_levels mrt_skip_levels_bytes(X,Y,Z) bytes            spans   nviews * mrt_tiles_y(H) * 2 int32
+ * ev_march_begin / ev_march_end: optional cudaEvent_t recorded around the spans + march launches (a host
+ * that wants the march's own device time); NULL to skip.  stage: 0 = the whole step; 1 = only the fold pass
+ * (needs no cameras: a host can queue it first and prepare its camera array while the GPU folds), 2 = the
+ * rest of a step whose stage 1 was queued on the same stream.  Needs skipEmpty = 1, tMode = 0, gamma = 1, no
+ * overlays, volDtype = 0 (MRT_ERR_UNSUPPORTED otherwise: use the separate calls). */
+int mrt_render_views_refold(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                            const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
+                            int32_t* spans, const float* tf, int32_t tfN, float* out_rgba,
+                            void* ev_march_begin, void* ev_march_end, int32_t stage, void* stream);
+
 /* ------------------------------------------------ backward
  * Adjoint of the forward w.r.t. the volume and the transfer function
  * (docs/DifferentiableRendering.md:88-127).  Recomputes the forward per ray (segment).

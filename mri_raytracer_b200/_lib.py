@@ -123,6 +123,7 @@ PROTOTYPES = {
     "mrt_backward_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mrt_render_views_refold": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_render_forward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_backward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_adaptive_scratch_bytes": (_sz, [_i32]),

@@ -669,13 +669,64 @@ class Volume:
     def forward_batch(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor],
                       out: Optional[torch.Tensor] = None, out_T: Optional[torch.Tensor] = None,
                       out_counts: Optional[torch.Tensor] = None,
-                      tile_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-        """classify ONCE (the skip levels do not depend on the camera) + one batched march."""
+                      tile_range: Optional[Tuple[int, int]] = None, march_events=None) -> torch.Tensor:
+        """classify ONCE (the skip levels do not depend on the camera) + one batched march.  When the
+        folded volume is stale (weights changed / :meth:`invalidate`) and the frame is a plain one, the
+        whole step — fold + occupancy + layout, classify, spans, march — is ONE library call
+        (``mrt_render_views_refold``).  ``march_events``: optional pair of recorded-once
+        ``torch.cuda.Event(enable_timing=True)`` that bracket the march on the device."""
         P = P.with_projection_of(cams[0])              # projection (fov / ortho window) of the batch
+        if (self.fold and self.quad and self.occupancy and self.shard is None and tile_range is None and out_T is None
+                and out_counts is None and P.skipEmpty and P.tMode == "indexed" and P.gamma == 1.0
+                and _fold_key(P, self.C) != self._key
+                and not (self.labels is not None and P.showSeg) and not (self.preds is not None and P.showPred)):
+            return self._refold_and_march(P, cams, tf, out, march_events)
         packed, Cn, Pe = self.prepared(P)
         bits = self._classify(P, Pe, Cn, tf)
         return self.march_batch(Pe, cams, packed, Cn, tf, bits, out=out, out_T=out_T, out_counts=out_counts,
                                 tile_range=tile_range)
+
+    def _refold_and_march(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor],
+                          out: Optional[torch.Tensor], march_events=None) -> torch.Tensor:
+        """``mrt_render_views_refold``: the stale-volume step in one call; leaves every cache of the Volume
+        (quad layout, min/max, skip levels) as the separate calls would."""
+        W, H = P.imageSize
+        V = len(cams)
+        X, Y, Z = self.dims
+        dev = self.device
+        nbytes = lib().mrt_packed_volume_bytes_quad(X, Y, Z)
+        if self._quad_buf is None or self._quad_buf.numel() * self._quad_buf.element_size() != nbytes:
+            self._quad_buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+        if self.minmax is None:
+            self.minmax = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=dev)
+        s = P.to_struct()
+        stream = _stream()
+        # stage 1 (the fold pass needs no cameras) is queued first: the camera array and the output
+        # checks below are prepared while the GPU folds
+        check(lib().mrt_render_views_refold(C.byref(s), None, 0, self.planar.data_ptr(), self.C, self._quad_buf.data_ptr(),
+                                            self.minmax.data_ptr(), None, None, None, 0, None, None, None, 1, stream),
+              "render_views_refold")
+        self.packed, self._quad_ok, self._key = None, True, _fold_key(P, self.C)
+        if self._bits is None:
+            self._bits = skip_levels_buffer(P, dev)
+        ty = _tiles.tiles_y(H)
+        if self._spans is None or self._spans.shape[0] < V or self._spans.shape[1] != ty:
+            self._spans = torch.empty((V, ty, 2), dtype=torch.int32, device=dev)
+        if out is None:
+            out = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (V, H, W, 4) or not out.is_contiguous():
+            raise ValueError(f"out must be contiguous [V,H,W,4]={(V, H, W, 4)}, got {tuple(out.shape)}")
+        if V > lib().mrt_max_views_per_launch() and march_events is not None:
+            raise ValueError("march_events bracket a single launch: at most mrt_max_views_per_launch views")
+        arr = _camera_array(cams)
+        e0 = e1 = None
+        if march_events is not None:
+            e0, e1 = (C.c_void_p(int(e.cuda_event)) for e in march_events)
+        check(lib().mrt_render_views_refold(C.byref(s), arr.ctypes.data, V, self.planar.data_ptr(), self.C,
+                                            self._quad_buf.data_ptr(), self.minmax.data_ptr(), self._bits.data_ptr(),
+                                            self._spans.data_ptr(), _ptr(tf), 0 if tf is None else tf.shape[0], out.data_ptr(),
+                                            e0, e1, 2, stream), "render_views_refold")
+        return out
 
     def march_batch(self, Pe: RenderParams, cams: Sequence, packed: torch.Tensor, Cn: int,
                     tf: Optional[torch.Tensor], bits: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
@@ -1022,7 +1073,7 @@ def render_adaptive(volume: torch.Tensor, camera: Optional[Camera], tf: Optional
 
 def render_views(volume: Union[torch.Tensor, Volume], cams: Sequence, tf: Optional[torch.Tensor], params: RenderParams,
                  out: Optional[torch.Tensor] = None, tile_range: Optional[Tuple[int, int]] = None,
-                 fold: bool = True) -> torch.Tensor:
+                 fold: bool = True, march_events=None) -> torch.Tensor:
     """Render a batch of views of a prepared :class:`Volume` -> float32 ``[V,H,W,4]``: the
     reference's frame loop over successive camera poses (inr/viewer/brats_viewer.py:400-442) as
     one classify + one march launch per 64 views.  View ``v`` is bit-identical to
@@ -1064,6 +1115,8 @@ def render_views(volume: Union[torch.Tensor, Volume], cams: Sequence, tf: Option
     if tuple(P.dims) != tuple(volume.global_dims):
         raise ValueError(f"params.dims {P.dims} != volume dims {volume.global_dims}")
     P.validate()
+    if march_events is not None:
+        return volume.forward_batch(P, cams, tf, out=out, tile_range=tile_range, march_events=march_events)
     return volume.forward_batch(P, cams, tf, out=out, tile_range=tile_range)
 
 

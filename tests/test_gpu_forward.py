@@ -476,3 +476,48 @@ def test_bad_arguments_raise(cuda):
         api.render(V, None, None, replace(P, dims=(8, 8, 8)))
     with pytest.raises(api._lib.MrtError):
         api.render_forward(replace(P, fovY=4.0), V.packed, V.C)
+
+
+def test_one_call_refold_step_equals_the_separate_calls(cuda):
+    """mrt_render_views_refold (fold + occupancy + layout, classify, spans, march in ONE library call, taken
+    by render_views whenever the folded volume is stale) gives the frames of the separate calls bit for
+    bit, leaves the Volume's caches valid, and re-records the caller's timing events around the march."""
+    import numpy as np
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    vol, _, P = small_scene(C=4, dims=(44, 37, 30), W=72, H=56, seed=17, theta_deg=20.0, phi_deg=70.0)
+    P = replace(P, tfMode=1, volWeight=(1.0, 0.5, 2.0, 0.25))
+    tf = ramp_tf(64, sigma_scale=12.0, cutoff=0.1).cuda()
+    cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.2, initial_theta=0.3)
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 5)
+    V = api.Volume(vol.cuda())
+    ref = torch.stack([api.render(V, c, tf, P) for c in cams])          # separate calls (fold cached by the first)
+    V.invalidate()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); e1.record()
+    one = api.render_views(V, cams, tf, P, march_events=(e0, e1))       # stale -> the one-call step
+    assert torch.equal(one, ref)
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) > 0.0
+    again = api.render_views(V, cams, tf, P)                            # caches valid -> classify + march only
+    assert torch.equal(again, ref)
+    P2 = replace(P, volWeight=(0.3, 1.0, 1.0, 2.0))                     # weights changed -> stale again
+    ref2 = torch.stack([api.render(api.Volume(vol.cuda()), c, tf, P2) for c in cams])
+    assert torch.equal(api.render_views(V, cams, tf, P2), ref2)
+    # the C form a non-Python host uses: stage 0 = the whole step in one call
+    import ctypes as C
+    from mri_raytracer_b200._lib import check, lib
+    from mri_raytracer_b200 import tiles as _t
+    X, Y, Z = 44, 37, 30
+    quad = torch.empty((lib().mrt_packed_volume_bytes_quad(X, Y, Z) // 4,), device="cuda")
+    mm = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), device="cuda")
+    lv = torch.empty((lib().mrt_skip_levels_bytes(X, Y, Z),), dtype=torch.uint8, device="cuda")
+    sp = torch.empty((5, _t.tiles_y(56), 2), dtype=torch.int32, device="cuda")
+    out = torch.empty((5, 56, 72, 4), device="cuda")
+    arr = api._camera_array(cams)
+    s = P.with_projection_of(cams[0]).to_struct()
+    planar = vol.cuda()
+    check(lib().mrt_render_views_refold(C.byref(s), arr.ctypes.data, 5, planar.data_ptr(), 4, quad.data_ptr(), mm.data_ptr(),
+                                        lv.data_ptr(), sp.data_ptr(), tf.data_ptr(), 64, out.data_ptr(), None, None, 0,
+                                        torch.cuda.current_stream().cuda_stream), "render_views_refold")
+    assert torch.equal(out, ref)

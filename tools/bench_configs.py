@@ -119,9 +119,11 @@ def cfg3():
     v = vol.cuda().requires_grad_(True)
     t = tf.cuda().requires_grad_(True)
 
+    mse = torch.nn.functional.mse_loss                      # mean((img - target)^2), BASELINE cfg3's loss, as one fused op
+
     def step():
         v.grad = None; t.grad = None
-        loss = ((api.render(v, None, t, P) - target) ** 2).mean()
+        loss = mse(api.render(v, None, t, P), target)
         loss.backward()
         return loss
 
@@ -139,7 +141,7 @@ def cfg3():
         v.grad = None; t.grad = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss_g = ((api.render(v, None, t, P) - target) ** 2).mean()
+            loss_g = mse(api.render(v, None, t, P), target)
             loss_g.backward()
         gv_eager = None
         graph.replay(); torch.cuda.synchronize()
