@@ -321,6 +321,13 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
                                     int32_t store_outside, void* stream);
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews,
                            float* out_rgba, void* stream);
+/* Delta form for a framebuffer that is reused batch after batch: `prev_spans` = the spans of the batch
+ * that last wrote `out_rgba` (after which the image held the background everywhere outside them, same
+ * background colour): only tiles inside the previous spans and outside the new ones are written — a few
+ * MB instead of the > half frame per view when the camera moves in small steps.  prev_spans == NULL:
+ * mrt_fill_outside_spans. */
+int mrt_fill_outside_spans_delta(const MrtParams* params, const int32_t* spans, const int32_t* prev_spans,
+                                 int32_t nviews, float* out_rgba, void* stream);
 /* Image-space partition across GPUs with the framebuffer gather done by the march's own stores
  * (north_star: "partitioned by image-space tiles with the volume replicated, framebuffer gathered
  * over NCCL/NVLink"): like mrt_render_forward_batch_sparse, but
@@ -376,6 +383,14 @@ int mrt_render_views_refold(const MrtParams* params, const MrtCamera* cams, int3
                             const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
                             int32_t* spans, const float* tf, int32_t tfN, float* out_rgba,
                             void* ev_march_begin, void* ev_march_end, int32_t stage, void* stream);
+
+/* The same step for the distributed framebuffer (mrt_render_forward_batch_scatter's arguments): spans of all
+ * views into `spans`, this rank's tile rows (ty % row_mod == row_rem) of every view stored to view_out_dev[v];
+ * tiles outside the spans are not stored (the frame's owner fills them, mrt_fill_outside_spans). */
+int mrt_render_views_refold_scatter(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                    const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
+                                    int32_t* spans, const float* tf, int32_t tfN, float* const* view_out_dev,
+                                    int32_t row_mod, int32_t row_rem, int32_t stage, void* stream);
 
 /* ------------------------------------------------ backward
  * Adjoint of the forward w.r.t. the volume and the transfer function

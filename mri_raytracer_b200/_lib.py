@@ -114,6 +114,7 @@ PROTOTYPES = {
     "mrt_view_spans": (C.c_int, [_PP, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mrt_render_forward_batch_sparse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_fill_outside_spans": (C.c_int, [_PP, _vp, _i32, _vp, _vp]),
+    "mrt_fill_outside_spans_delta": (C.c_int, [_PP, _vp, _vp, _i32, _vp, _vp]),
     "mrt_render_forward_batch_scatter": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mrt_checkpoint_plan": (C.c_int, [_PP, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "mrt_checkpoint_bytes": (_sz, [_i32, _i32, _i32, _i32]),
@@ -124,6 +125,7 @@ PROTOTYPES = {
     "mrt_render_backward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_views_refold": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "mrt_render_views_refold_scatter": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "mrt_render_forward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_backward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_adaptive_scratch_bytes": (_sz, [_i32]),

@@ -300,11 +300,12 @@ def render_forward_batch_scatter(P: RenderParams, cams: Sequence, packed: torch.
           "render_forward_batch_scatter")
 
 
-def fill_outside_spans(P: RenderParams, spans: torch.Tensor, out: torch.Tensor):
-    """``mrt_fill_outside_spans``: background into every tile outside its row's span."""
+def fill_outside_spans(P: RenderParams, spans: torch.Tensor, out: torch.Tensor, prev_spans: Optional[torch.Tensor] = None):
+    """``mrt_fill_outside_spans(_delta)``: background into every tile outside its row's span; with
+    ``prev_spans`` (the spans of the batch that last wrote ``out``) only into the tiles those covered."""
     s = P.to_struct()
-    check(lib().mrt_fill_outside_spans(C.byref(s), spans.data_ptr(), int(spans.shape[0]), out.data_ptr(), _stream()),
-          "fill_outside_spans")
+    check(lib().mrt_fill_outside_spans_delta(C.byref(s), spans.data_ptr(), _ptr(prev_spans), int(spans.shape[0]), out.data_ptr(),
+                                             _stream()), "fill_outside_spans")
 
 
 def render_forward_strips(P: RenderParams, packed: torch.Tensor, Cn: int, tf: Optional[torch.Tensor],
@@ -676,22 +677,23 @@ class Volume:
         (``mrt_render_views_refold``).  ``march_events``: optional pair of recorded-once
         ``torch.cuda.Event(enable_timing=True)`` that bracket the march on the device."""
         P = P.with_projection_of(cams[0])              # projection (fov / ortho window) of the batch
-        if (self.fold and self.quad and self.occupancy and self.shard is None and tile_range is None and out_T is None
-                and out_counts is None and P.skipEmpty and P.tMode == "indexed" and P.gamma == 1.0
-                and _fold_key(P, self.C) != self._key
-                and not (self.labels is not None and P.showSeg) and not (self.preds is not None and P.showPred)):
+        if tile_range is None and out_T is None and out_counts is None and self.stale_and_fusable(P):
             return self._refold_and_march(P, cams, tf, out, march_events)
         packed, Cn, Pe = self.prepared(P)
         bits = self._classify(P, Pe, Cn, tf)
         return self.march_batch(Pe, cams, packed, Cn, tf, bits, out=out, out_T=out_T, out_counts=out_counts,
                                 tile_range=tile_range)
 
-    def _refold_and_march(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor],
-                          out: Optional[torch.Tensor], march_events=None) -> torch.Tensor:
-        """``mrt_render_views_refold``: the stale-volume step in one call; leaves every cache of the Volume
-        (quad layout, min/max, skip levels) as the separate calls would."""
-        W, H = P.imageSize
-        V = len(cams)
+    def stale_and_fusable(self, P: RenderParams) -> bool:
+        """True when the folded volume is stale for ``P`` (weights changed / :meth:`invalidate`) and the
+        frame is a plain one: the step can then be queued by ``mrt_render_views_refold(_scatter)``."""
+        return (self.fold and self.quad and self.occupancy and self.shard is None and bool(P.skipEmpty)
+                and P.tMode == "indexed" and P.gamma == 1.0 and _fold_key(P, self.C) != self._key
+                and not (self.labels is not None and P.showSeg) and not (self.preds is not None and P.showPred))
+
+    def _refold_stage1(self, P: RenderParams):
+        """Queue the fold pass (it needs no cameras) -> (params struct, stream); the caller prepares its
+        camera array while the GPU folds, then queues stage 2."""
         X, Y, Z = self.dims
         dev = self.device
         nbytes = lib().mrt_packed_volume_bytes_quad(X, Y, Z)
@@ -701,14 +703,35 @@ class Volume:
             self.minmax = torch.empty((lib().mrt_brick_count(X, Y, Z), 1, 2), dtype=torch.float32, device=dev)
         s = P.to_struct()
         stream = _stream()
-        # stage 1 (the fold pass needs no cameras) is queued first: the camera array and the output
-        # checks below are prepared while the GPU folds
         check(lib().mrt_render_views_refold(C.byref(s), None, 0, self.planar.data_ptr(), self.C, self._quad_buf.data_ptr(),
                                             self.minmax.data_ptr(), None, None, None, 0, None, None, None, 1, stream),
               "render_views_refold")
         self.packed, self._quad_ok, self._key = None, True, _fold_key(P, self.C)
         if self._bits is None:
             self._bits = skip_levels_buffer(P, dev)
+        return s, stream
+
+    def refold_and_scatter(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor], view_ptrs: torch.Tensor,
+                           spans: torch.Tensor, row_mod: int, row_rem: int):
+        """``mrt_render_views_refold_scatter``: the stale-volume step of the distributed framebuffer
+        (``dist.PeerFramebuffer``) in one staged library call.  ``P`` must satisfy :meth:`stale_and_fusable`."""
+        s, stream = self._refold_stage1(P)
+        arr = _camera_array(cams)
+        check(lib().mrt_render_views_refold_scatter(C.byref(s), arr.ctypes.data, len(cams), self.planar.data_ptr(), self.C,
+                                                    self._quad_buf.data_ptr(), self.minmax.data_ptr(), self._bits.data_ptr(),
+                                                    spans.data_ptr(), _ptr(tf), 0 if tf is None else tf.shape[0],
+                                                    view_ptrs.data_ptr(), int(row_mod), int(row_rem), 2, stream),
+              "render_views_refold_scatter")
+
+    def _refold_and_march(self, P: RenderParams, cams: Sequence, tf: Optional[torch.Tensor],
+                          out: Optional[torch.Tensor], march_events=None) -> torch.Tensor:
+        """``mrt_render_views_refold``: the stale-volume step in one (staged) call; leaves every cache of the
+        Volume (quad layout, min/max, skip levels) as the separate calls would."""
+        W, H = P.imageSize
+        V = len(cams)
+        dev = self.device
+        # stage 1 is queued first: the camera array and the output checks below are prepared while the GPU folds
+        s, stream = self._refold_stage1(P)
         ty = _tiles.tiles_y(H)
         if self._spans is None or self._spans.shape[0] < V or self._spans.shape[1] != ty:
             self._spans = torch.empty((V, ty, 2), dtype=torch.int32, device=dev)

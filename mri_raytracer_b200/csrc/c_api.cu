@@ -509,13 +509,14 @@ int mrt_render_forward_batch_sparse(const MrtParams* params, const MrtCamera* ca
 // have changed: blend + occupancy + quad layout, classify, spans, ONE batched march.  The four
 // launches are queued back to back from C, so the host costs one call per step instead of three
 // (measured: 0.72 -> 0.66 ms per cfg2 step would be the gain of removing the host path entirely).
-int mrt_render_views_refold(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
-                            const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
-                            int32_t* spans, const float* tf, int32_t tfN, float* out_rgba,
-                            void* ev_march_begin, void* ev_march_end, int32_t stage, void* stream) {
+static int refold_impl(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                       const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
+                       int32_t* spans, const float* tf, int32_t tfN, float* out_rgba,
+                       float* const* view_out_dev, int32_t row_mod, int32_t row_rem,
+                       void* ev_march_begin, void* ev_march_end, int32_t stage, void* stream) {
   MRT_REQUIRE(stage >= 0 && stage <= 2, "render_views_refold: stage %d unknown (0 all, 1 fold only, 2 after the fold)", stage);
   MRT_REQUIRE(params && planar && quad && minmax, "render_views_refold: null pointer");
-  MRT_REQUIRE(stage == 1 || (cams && skip_levels && spans && out_rgba), "render_views_refold: null pointer");
+  MRT_REQUIRE(stage == 1 || (cams && skip_levels && spans && (out_rgba || view_out_dev)), "render_views_refold: null pointer");
   MRT_REQUIRE(stage == 1 || nviews >= 1, "render_views_refold: needs >= 1 camera");
   if (!params->skipEmpty || params->tMode != 0 || params->gamma != 1.0f || params->volDtype != 0 || params->shardEnabled)
     return fail(MRT_ERR_UNSUPPORTED, "render_views_refold: needs skipEmpty=1, indexed stepping, gamma 1, an unsharded fp32 planar volume "
@@ -534,13 +535,37 @@ int mrt_render_views_refold(const MrtParams* params, const MrtCamera* cams, int3
     cudaError_t e = cudaEventRecord((cudaEvent_t)ev_march_begin, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_views_refold");
   }
-  // store_outside = 1: the call computes the spans into `spans` itself, then marches into dense frames
-  if (int r = mrt_render_forward_batch_sparse(&P, cams, nviews, quad, 1, tf, tfN, skip_levels, out_rgba, spans, 1, stream)) return r;
+  if (view_out_dev) {
+    // distributed framebuffer: spans of every view (owners fill outside them), then this rank's tile rows of every
+    // view stored straight into the owners' frames; tiles outside the spans are not stored
+    MrtParams Ps = P; Ps.volDtype = 0;
+    if (int r = mrt_view_spans(&Ps, cams, nviews, 1, skip_levels, spans, stream)) return r;
+    if (int r = mrt_render_forward_batch_scatter(&P, cams, nviews, quad, 1, tf, tfN, skip_levels, view_out_dev, spans, 0,
+                                                 row_mod, row_rem, stream)) return r;
+  } else {
+    // store_outside = 1: the call computes the spans into `spans` itself, then marches into dense frames
+    if (int r = mrt_render_forward_batch_sparse(&P, cams, nviews, quad, 1, tf, tfN, skip_levels, out_rgba, spans, 1, stream)) return r;
+  }
   if (ev_march_end) {
     cudaError_t e = cudaEventRecord((cudaEvent_t)ev_march_end, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_views_refold");
   }
   return MRT_OK;
+}
+int mrt_render_views_refold(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                            const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
+                            int32_t* spans, const float* tf, int32_t tfN, float* out_rgba,
+                            void* ev_march_begin, void* ev_march_end, int32_t stage, void* stream) {
+  return refold_impl(params, cams, nviews, planar, C, quad, minmax, skip_levels, spans, tf, tfN, out_rgba, nullptr, 0, 0,
+                     ev_march_begin, ev_march_end, stage, stream);
+}
+int mrt_render_views_refold_scatter(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                                    const float* planar, int32_t C, void* quad, float* minmax, uint8_t* skip_levels,
+                                    int32_t* spans, const float* tf, int32_t tfN, float* const* view_out_dev,
+                                    int32_t row_mod, int32_t row_rem, int32_t stage, void* stream) {
+  MRT_REQUIRE(stage == 1 || view_out_dev, "render_views_refold_scatter: null pointer");
+  return refold_impl(params, cams, nviews, planar, C, quad, minmax, skip_levels, spans, tf, tfN, nullptr, view_out_dev,
+                     row_mod, row_rem, nullptr, nullptr, stage, stream);
 }
 int mrt_render_forward_batch_scatter(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                                      const void* packed, int32_t C, const float* tf, int32_t tfN,
@@ -569,6 +594,10 @@ int mrt_render_forward_batch_scatter(const MrtParams* params, const MrtCamera* c
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_forward_batch_scatter");
 }
 int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_t nviews, float* out_rgba, void* stream) {
+  return mrt_fill_outside_spans_delta(params, spans, nullptr, nviews, out_rgba, stream);
+}
+int mrt_fill_outside_spans_delta(const MrtParams* params, const int32_t* spans, const int32_t* prev_spans, int32_t nviews,
+                                 float* out_rgba, void* stream) {
   MRT_REQUIRE(params && spans && out_rgba && nviews >= 1, "fill_outside_spans: bad arguments");
   const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
   MRT_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "fill_outside_spans: imageSize invalid");
@@ -581,7 +610,7 @@ int mrt_fill_outside_spans(const MrtParams* params, const int32_t* spans, int32_
     const uint64_t d = (uint64_t)mrt_tiles_x_(W);
     K.tdiv_mul = (d > 1 && (uint64_t)K.tile_end * d < (1ull << 32)) ? (unsigned)((1ull << 32) / d + 1) : 0u;
   }
-  cudaError_t e = mrt_launch_fill_outside(K, nviews, spans, out_rgba, (cudaStream_t)stream);
+  cudaError_t e = mrt_launch_fill_outside(K, nviews, spans, prev_spans, out_rgba, (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "fill_outside_spans");
 }
 

@@ -460,8 +460,8 @@ mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__
   spans[(size_t)v * ty + band] = mrt_view_span(P, B.cam[v], A, band);
 }
 __global__ void __launch_bounds__(256)
-mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int2* __restrict__ spans, int nviews,
-                        float4* __restrict__ out) {
+mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int2* __restrict__ spans,
+                        const int2* __restrict__ prev, int nviews, float4* __restrict__ out) {
   // one WARP per tile (two 512-byte warp stores), grid-stride over (view, tile)
   const float4 bgp = P.shard ? make_float4(0.0f, 0.0f, 0.0f, 1.0f)
                              : make_float4(P.bg[0], P.bg[1], P.bg[2], P.alphaMode ? 0.0f : 1.0f);
@@ -474,6 +474,9 @@ mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int2* __restric
     int px, py;
     mrt_pixel_of_tile_lane_fast(P, tile, lane, &px, &py);                 // lanes 0..31 = the tile's upper half
     if (mrt_tile_in_span(__ldg(spans + (size_t)view * ty + (py >> MRT_TILE_SHIFT)), px & ~MRT_TILE_MASK)) continue;
+    // delta fill: the image already holds the background outside `prev` (the spans of the batch that
+    // last wrote this buffer), so only tiles that were inside those and are outside the new ones change
+    if (prev != nullptr && !mrt_tile_in_span(__ldg(prev + (size_t)view * ty + (py >> MRT_TILE_SHIFT)), px & ~MRT_TILE_MASK)) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int y = py + 4 * h;
@@ -495,12 +498,14 @@ cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nview
   }
   return cudaSuccess;
 }
-cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st) {
+cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, const int32_t* prev_spans, float* out_rgba,
+                                    cudaStream_t st) {
   const int ntiles = P.tile_end - P.tile_begin;
   if (ntiles <= 0 || nviews <= 0) return cudaSuccess;
   size_t grid = ((size_t)ntiles * nviews + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
-  mrt_fill_outside_kernel<<<(int)grid, 256, 0, st>>>(P, reinterpret_cast<const int2*>(spans), nviews, (float4*)out_rgba);
+  mrt_fill_outside_kernel<<<(int)grid, 256, 0, st>>>(P, reinterpret_cast<const int2*>(spans),
+                                                     reinterpret_cast<const int2*>(prev_spans), nviews, (float4*)out_rgba);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,8 @@ cudaError_t mrt_launch_forward_sparse(const KParams& P, const float* cams, int n
                                       int row_mod = 0, int row_rem = 0);
 cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nviews, const uint8_t* levels, int32_t* spans,
                                   cudaStream_t st);
-cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, float* out_rgba, cudaStream_t st);
+cudaError_t mrt_launch_fill_outside(const KParams& P, int nviews, const int32_t* spans, const int32_t* prev_spans, float* out_rgba,
+                                    cudaStream_t st);
 
 // staged-brick (TMA + shared memory) variant of the single-view march, forward_tma.cu
 cudaError_t mrt_launch_forward_tma(const KParams& P, int box_edge, int tile, const void* vol, const float* tf,

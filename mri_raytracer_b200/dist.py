@@ -181,6 +181,9 @@ class PeerFramebuffer:
         if self.p2p:
             self.spans = torch.empty((self.V, ty, 2), dtype=torch.int32, device=self.device)
             self.side = torch.cuda.Stream(device=self.device)
+            n_own = max(1, len(self.owned_views()))
+            self._prev_spans = [torch.empty((n_own, ty, 2), dtype=torch.int32, device=self.device) for _ in range(2)]
+            self._prev_key = [None, None]            # (background, alphaMode) the buffer was last filled with
 
     # ---- integer maps (replicated on every rank)
     def owner_of(self, v: int) -> Tuple[int, int]:
@@ -221,6 +224,14 @@ class PeerFramebuffer:
                 tx = tiles.tiles_x(W)
                 _render_batch(volume, tf, Pm, cams, (tr0 * tx, tr1 * tx), self.full)
             return
+        Pq = Pm.with_projection_of(cams[0])
+        if self.partition == "tiles" and hasattr(volume, "stale_and_fusable") and volume.stale_and_fusable(Pq):
+            # stale folded volume (weights changed): fold + occupancy + layout, classify, spans of every view and this
+            # rank's tile rows of every view in ONE staged library call (mrt_render_views_refold_scatter)
+            buf = self.batch & 1
+            volume.refold_and_scatter(Pq, cams, tf, self.view_ptrs[buf], self.spans, R, r)
+            self._fill_owned(api, Pq, buf)
+            return
         plan = volume.sparse_plan(Pm, cams, tf)
         if plan is None:
             raise RuntimeError("PeerFramebuffer.render needs the span path: an occupancy grid, skipEmpty=1, indexed stepping, "
@@ -237,14 +248,25 @@ class PeerFramebuffer:
             if v1 > v0:
                 api.render_forward_batch_scatter(Pe, arr[v0:v1], packed, Cn, tf, bits, self.view_ptrs[buf, v0:v1].contiguous(),
                                                  self.spans[v0:v1], store_outside=False)
+        self._fill_owned(api, Pe, buf)
+
+    def _fill_owned(self, api, Pe, buf):
         own = self.owned_views()
         if len(own):
             # background of the owned views outside their spans, on a side stream, while everybody
             # marches (queued after this rank's own march so that its launch is not delayed)
+            # Delta fill: this buffer already holds the background outside the spans of the batch that last
+            # wrote it (two batches ago), so only the tiles those spans covered and the new ones do not are
+            # written — unless the background changed or the buffer is new.
+            key = (tuple(float(v) for v in Pe.bgColor), int(Pe.alphaMode))
+            prev = self._prev_spans[buf] if self._prev_key[buf] == key else None
             ev = torch.cuda.Event(); ev.record()
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ev)
-                api.fill_outside_spans(Pe, self.spans[own.start:own.stop], self.local[buf, :len(own)])
+                now = self.spans[own.start:own.stop]
+                api.fill_outside_spans(Pe, now, self.local[buf, :len(own)], prev_spans=prev)
+                self._prev_spans[buf].copy_(now)
+                self._prev_key[buf] = key
                 self._fill_done = torch.cuda.Event(); self._fill_done.record()
 
     def finish(self) -> torch.Tensor:

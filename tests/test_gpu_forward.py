@@ -219,6 +219,16 @@ def test_sparse_batch_plus_fill_equals_dense_batch(cuda, W, H, alpha, ortho):
     api.fill_outside_spans(Pe, spans, out)
     assert torch.equal(out, dense)
     assert V.sparse_plan(replace(Pm, gamma=1.5), cams, tf) is None
+    # the same buffer reused by the next batch (the camera moved): the DELTA fill only writes the tiles the
+    # previous spans covered and the new ones do not, and the frame is still the dense one bit for bit
+    cam.theta += 0.35; cam.phi -= 0.1
+    cams2 = orbit_views(cam, 5, ortho=ortho)
+    dense2 = api.render_views(V, cams2, tf, P)
+    spans2 = api.view_spans(Pe, cams2, Cn, bits)
+    assert not torch.equal(spans2, spans)
+    api.render_forward_batch_sparse(Pe, cams2, packed, Cn, tf, bits, out.data_ptr(), spans2)
+    api.fill_outside_spans(Pe, spans2, out, prev_spans=spans)
+    assert torch.equal(out, dense2)
 
 
 def test_refold_when_weights_change(cuda):
