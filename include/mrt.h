@@ -434,6 +434,30 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
                         void* dL_dvol, float* dL_dtf, void* scratch, float* dL_dray, uint64_t* stats,
                         int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* ------------------------------------------------ one call per training step
+ * BASELINE cfg3 / docs/DifferentiableRendering.md:88-127 + :213 as ONE call: the optimisation loop the doc
+ * describes (render, L = mean((C - C_target)^2), dL/dvolume, dL/dTF) with the volume a learnable planar
+ * tensor that changes every step.  Queued from C: mrt_fold_volume_occupancy_f32 -> mrt_classify_bricks
+ * (skip levels; flat levels on a side stream) -> mrt_render_forward_ckpt -> the segment-parallel adjoint,
+ * which forms G = (2/n)(out - target) per pixel itself (no dL/dout tensor is ever materialised) ->
+ * mrt_unfold_grad_f32; the gradient buffers are cleared and the loss is reduced on a library-owned side
+ * stream that forks from and joins `stream`, beside the march and the adjoint.  Results equal
+ * mrt_render_forward_ckpt + mse + mrt_render_backward (image bit for bit, gradients to rounding).
+ *   planar     : device float [C][Z][Y][X], the learnable volume (read only)
+ *   tf         : device float [tfN][4] (tfMode 1) or NULL (tfMode 0)
+ *   target_rgba: device float [nviews][H][W][4]
+ *   workspace  : device, mrt_train_step_workspace_bytes(params, nviews, tfN) bytes, caller-owned, ZERO IT ONCE
+ *                before the first call; it may be reused by every later step of the same geometry
+ *   out_rgba   : device float [nviews][H][W][4], this step's image (result)
+ *   loss       : optional device float[1] = mean((out - target)^2) over all nviews*H*W*4 values
+ *   dL_dplanar : optional device float [C][Z][Y][X], overwritten      dL_dtf : optional float [tfN][4], overwritten
+ * `cams` NULL: one view with the camera in params.  Needs skipEmpty = 1, tMode = 0, gamma = 1, no overlays,
+ * volDtype = 0, unsharded (MRT_ERR_UNSUPPORTED otherwise: use the separate calls). */
+size_t mrt_train_step_workspace_bytes(const MrtParams* params, int32_t nviews, int32_t tfN);
+int mrt_train_step_mse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                       const float* planar, int32_t C, const float* tf, int32_t tfN, const float* target_rgba,
+                       void* workspace, float* out_rgba, float* loss, float* dL_dplanar, float* dL_dtf, void* stream);
+
 /* ------------------------------------------------ soft (learnable) occupancy
  * docs/DifferentiableRendering.md section 11 (:202-206; maths only, no reference code): "hard empty-space
  * skipping -> continuous occupancy o(x) in [0,1] learned and used multiplicatively".  `soft_occ` holds one

@@ -10,12 +10,12 @@ from .params import RenderParams, SlabParams, default_label_lut
 from . import tiles
 
 __all__ = ["Camera", "OrbitalCamera", "OrbitalCameraYUp", "orbit_views", "RenderParams", "SlabParams",
-           "default_label_lut", "tiles", "render", "render_views", "render_aux", "render_slab", "render_host", "HostPipeline", "Volume"]
+           "default_label_lut", "tiles", "render", "render_views", "render_aux", "render_slab", "render_host", "HostPipeline", "Volume", "TrainStep"]
 
 
 def __getattr__(name):
     # torch-dependent API is imported lazily so the pure-host pieces work without torch/CUDA
-    if name in ("render", "inr_predict", "ray_gradients", "render_views", "render_aux", "render_slab", "render_host", "Volume", "pack_volume", "unpack_volume",
+    if name in ("render", "inr_predict", "ray_gradients", "render_views", "render_aux", "render_slab", "render_host", "Volume", "TrainStep", "HostPipeline", "pack_volume", "unpack_volume",
                 "render_forward", "render_backward", "build_occupancy", "classify_bricks", "tile_index_map",
                 "build_label_occupancy"):
         from . import api

@@ -974,6 +974,75 @@ def render(volume: Union[torch.Tensor, Volume], camera: Optional[Camera], tf: Op
     return _RenderFn.apply(volume, tf, P, labels, preds, fold, tile_range)
 
 
+class TrainStep:
+    """One optimisation step of differentiable rendering with an MSE image loss in ONE library call
+    (``mrt_train_step_mse``; BASELINE cfg3, docs/DifferentiableRendering.md:88-127 + :213): fold +
+    occupancy of the CURRENT volume, classification, checkpointing march, loss, segment-parallel
+    adjoint (which forms ``dL/dC = 2 (C - target) / n`` per pixel itself) and the fold's adjoint,
+    queued back to back from C with the buffer clears and the loss reduction on a side stream.
+
+    The results equal ``mse_loss(render(volume, ...), target).backward()`` — image bit for bit, loss
+    and gradients to rounding — without the autograd graph, the dL/dC tensor and ~20 Python-level
+    launches.  Buffers are owned by the object and reused: the tensors a call returns are valid
+    until the next call.
+
+        step = TrainStep(params, n_views=1, tf_entries=256)
+        loss, image, dvol, dtf = step(volume, tf, target)          # all device tensors
+    """
+
+    def __init__(self, params: RenderParams, n_views: int = 1, tf_entries: int = 0, device=None):
+        self.P = replace(params, tfMode=1 if tf_entries else 0)
+        self.P.validate()
+        self.V, self.ntf = int(n_views), int(tf_entries)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        s = self.P.to_struct()
+        nbytes = lib().mrt_train_step_workspace_bytes(C.byref(s), self.V, self.ntf)
+        if nbytes == 0:
+            raise ValueError("TrainStep: " + lib().mrt_last_error().decode("utf-8", "replace"))
+        self.workspace = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)   # zeroed ONCE (header contract)
+        W, H = self.P.imageSize
+        self.image = torch.empty((self.V, H, W, 4), dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.dvol = None
+        self.dtf = torch.empty((self.ntf, 4), dtype=torch.float32, device=self.device) if self.ntf else None
+
+    def __call__(self, volume: torch.Tensor, tf: Optional[torch.Tensor], target: torch.Tensor,
+                 cams: Optional[Sequence] = None, want_dvol: bool = True, want_dtf: bool = True):
+        """-> (loss 0-dim, image ``[V,H,W,4]`` (``[H,W,4]`` when ``cams`` is None), dL/dvolume
+        ``[C,Z,Y,X]`` or None, dL/dtf ``[N,4]`` or None)."""
+        P = self.P
+        _need_cuda(volume, "volume", torch.float32)
+        _need_cuda(target, "target", torch.float32)
+        if volume.dim() != 4 or not (1 <= volume.shape[0] <= 4):
+            raise ValueError(f"volume must be [C,Z,Y,X] with C in 1..4, got {tuple(volume.shape)}")
+        Z, Y, X = (int(v) for v in volume.shape[1:])
+        if tuple(P.dims) != (X, Y, Z):
+            raise ValueError(f"params.dims {P.dims} != volume dims {(X, Y, Z)}")
+        nv = 1 if cams is None else len(cams)
+        if nv != self.V:
+            raise ValueError(f"TrainStep was built for {self.V} views, got {nv}")
+        if target.numel() != self.image.numel():
+            raise ValueError(f"target must hold {tuple(self.image.shape)} values, got {tuple(target.shape)}")
+        if (tf is None) != (self.ntf == 0) or (tf is not None and tuple(tf.shape) != (self.ntf, 4)):
+            raise ValueError(f"TrainStep was built for tf_entries={self.ntf}")
+        if tf is not None:
+            _need_cuda(tf, "tf", torch.float32)
+        want_dtf = bool(want_dtf) and tf is not None
+        if not (want_dvol or want_dtf):
+            raise ValueError("nothing to differentiate")
+        if want_dvol and (self.dvol is None or self.dvol.shape != volume.shape):
+            self.dvol = torch.empty_like(volume)
+        s = P.to_struct()
+        arr = None if cams is None else _camera_array(cams)
+        check(lib().mrt_train_step_mse(C.byref(s), None if arr is None else arr.ctypes.data, nv, volume.data_ptr(),
+                                       int(volume.shape[0]), _ptr(tf), self.ntf, target.data_ptr(),
+                                       self.workspace.data_ptr(), self.image.data_ptr(), self.loss.data_ptr(),
+                                       self.dvol.data_ptr() if want_dvol else None,
+                                       self.dtf.data_ptr() if want_dtf else None, _stream()), "train_step_mse")
+        img = self.image if cams is not None else self.image[0]
+        return self.loss, img, (self.dvol if want_dvol else None), (self.dtf if want_dtf else None)
+
+
 class _AdaptiveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planar, tf, P: RenderParams, K, J, eps_w):

@@ -52,8 +52,8 @@ __device__ __forceinline__ void vox_atomic_add(float4* p, float w, const KParams
   atomicAdd(p, make_float4(w * P.wq[0], w * P.wq[1], w * P.wq[2], w * P.wq[3]));
 }
 
-// Corner cache flushes (acc[i], i = x + 2y + 4z, belongs to voxel pb + x + y*sY + z*sZ).
-#define MRT_CORNER(pb, i) ((pb) + ((i) & 1) + (((i) >> 1) & 1) * sY + ((i) >> 2) * sZ)
+// Corner cache flushes (acc[i], i = x + 2y + 4z, belongs to voxel pb + x + y*gY + z*gZ of the gradient buffer).
+#define MRT_CORNER(pb, i) ((pb) + ((i) & 1) + (((i) >> 1) & 1) * IO.gY + ((i) >> 2) * IO.gZ)
 #define MRT_FLUSH1(pb, i) do { if (acc[i] != 0.0f) vox_atomic_add(MRT_CORNER(pb, i), acc[i], P); } while (0)
 #define MRT_FLUSH4(pb, a, b, c_, d) do { MRT_FLUSH1(pb, a); MRT_FLUSH1(pb, b); MRT_FLUSH1(pb, c_); MRT_FLUSH1(pb, d); } while (0)
 #define MRT_FLUSH_ALL(pb) do { MRT_FLUSH4(pb, 0, 1, 2, 3); MRT_FLUSH4(pb, 4, 5, 6, 7); \
@@ -64,6 +64,7 @@ struct BwdIO {
   const float4* tf; const uint8_t* flat_levels; const float2* minmax;
   const int32_t* labels; const int32_t* preds;
   const float4* out_rgba; const float4* dL_dout;
+  const float4* target; float gscale;   // dL_dout == nullptr: G = gscale * (out_rgba - target) (fused MSE loss)
   const float4* ck;            // checkpoints [(c-1)][view][H][W] = (C, T) before slot c*S; nullptr = unsegmented
   const int32_t* k_end;        // [view][H][W] end slot of every ray (forward's n_taken)
   float4* dtf_priv;            // [MRT_DTF_COPIES][ntf][2]: (lo, hi) = contributions to entry j0 and j0+1
@@ -71,6 +72,7 @@ struct BwdIO {
   unsigned long long* stats;   // [0] lane-slots shaded, [1] warp tasks that did work
   const uint2* tasks; const unsigned* ntasks; unsigned* next;
   int S, nviews;
+  uint32_t g_base_off, gY, gZ;  // element pitches of the GRADIENT buffer (= the volume's unless the caller asks for another layout)
 };
 
 // HALF = 1: fp16 voxel storage (single channel); the gradient buffer stays fp32 with the SAME element
@@ -118,7 +120,6 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
   const float nm1 = (float)(ntf - 1);
   uint32_t s_tf_addr = (uint32_t)__cvta_generic_to_shared(s_tf);
   asm volatile("" : "+r"(s_tf_addr));        // opaque: keep the address in a register, do not re-derive it per sample
-  const uint32_t sY = P.pitchY, sZ = P.pitchZ;
   const bool acc_mode = GENERIC && P.tMode == 1;           // reference-faithful running sum t += dt (unsegmented only)
   const float bgx = P.shard ? 0.0f : P.bg[0], bgy = P.shard ? 0.0f : P.bg[1], bgz = P.shard ? 0.0f : P.bg[2];
   unsigned n_shaded = 0, n_tasks = 0;
@@ -138,8 +139,15 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
     const size_t pixl = inside ? (size_t)py * P.W + px : 0, pix = (size_t)view * npix + pixl;
     // everything the task needs from memory, requested together (one round trip, not four)
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 G = inside ? __ldg(IO.dL_dout + pix) : zero4;
     const float4 Cout = inside ? __ldg(IO.out_rgba + pix) : zero4;
+    float4 G = zero4;
+    if (IO.dL_dout) {
+      if (inside) G = __ldg(IO.dL_dout + pix);
+    } else if (inside) {                        // d mean((out - target)^2) / d out
+      const float4 tg = __ldg(IO.target + pix);
+      G = make_float4(IO.gscale * (Cout.x - tg.x), IO.gscale * (Cout.y - tg.y), IO.gscale * (Cout.z - tg.z),
+                      IO.gscale * (Cout.w - tg.w));
+    }
     const int ke = (seg && inside) ? __ldg(IO.k_end + pix) : 0;
     float4 c0 = make_float4(bgx, bgy, bgz, 1.0f);                        // state before the segment's first slot
     if (seg && sg > 0 && inside) c0 = __ldg(IO.ck + ((size_t)(sg - 1) * IO.nviews + view) * npix + pixl);
@@ -298,14 +306,14 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
               const int ix = c.ix(), iy = c.iy(), iz = c.iz();
               const int ddx = ix - ccx, ddy = iy - ccy, ddz = iz - ccz;
               if ((ddx | ddy | ddz) != 0) {
-                VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ - P.base_off);
+                VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * IO.gY + (uint32_t)ccz * IO.gZ - IO.g_base_off);
                 if (max(max(abs(ddx), abs(ddy)), abs(ddz)) > 1) {
                   MRT_FLUSH_ALL(pb);
                 } else {
                   if (ddx > 0) { MRT_FLUSH4(pb, 0, 2, 4, 6); acc[0] = acc[1]; acc[2] = acc[3]; acc[4] = acc[5]; acc[6] = acc[7]; acc[1] = acc[3] = acc[5] = acc[7] = 0.0f; pb += 1; }
                   if (ddx < 0) { MRT_FLUSH4(pb, 1, 3, 5, 7); acc[1] = acc[0]; acc[3] = acc[2]; acc[5] = acc[4]; acc[7] = acc[6]; acc[0] = acc[2] = acc[4] = acc[6] = 0.0f; pb -= 1; }
-                  if (ddy > 0) { MRT_FLUSH4(pb, 0, 1, 4, 5); acc[0] = acc[2]; acc[1] = acc[3]; acc[4] = acc[6]; acc[5] = acc[7]; acc[2] = acc[3] = acc[6] = acc[7] = 0.0f; pb += sY; }
-                  if (ddy < 0) { MRT_FLUSH4(pb, 2, 3, 6, 7); acc[2] = acc[0]; acc[3] = acc[1]; acc[6] = acc[4]; acc[7] = acc[5]; acc[0] = acc[1] = acc[4] = acc[5] = 0.0f; pb -= sY; }
+                  if (ddy > 0) { MRT_FLUSH4(pb, 0, 1, 4, 5); acc[0] = acc[2]; acc[1] = acc[3]; acc[4] = acc[6]; acc[5] = acc[7]; acc[2] = acc[3] = acc[6] = acc[7] = 0.0f; pb += IO.gY; }
+                  if (ddy < 0) { MRT_FLUSH4(pb, 2, 3, 6, 7); acc[2] = acc[0]; acc[3] = acc[1]; acc[6] = acc[4]; acc[7] = acc[5]; acc[0] = acc[1] = acc[4] = acc[5] = 0.0f; pb -= IO.gY; }
                   if (ddz > 0) { MRT_FLUSH4(pb, 0, 1, 2, 3); acc[0] = acc[4]; acc[1] = acc[5]; acc[2] = acc[6]; acc[3] = acc[7]; acc[4] = acc[5] = acc[6] = acc[7] = 0.0f; }
                   if (ddz < 0) { MRT_FLUSH4(pb, 4, 5, 6, 7); acc[4] = acc[0]; acc[5] = acc[1]; acc[6] = acc[2]; acc[7] = acc[3]; acc[0] = acc[1] = acc[2] = acc[3] = 0.0f; }
                 }
@@ -353,7 +361,7 @@ mrt_bwd_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBat
       if (lfr != 0.0f) atomicAdd(&gpriv[2 * lj + 1].w, lfr * lacc);
     }
     if (dvol != nullptr && ccx >= 0) {
-      VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * sY + (uint32_t)ccz * sZ - P.base_off);
+      VT* pb = dvol + ((uint32_t)ccx + (uint32_t)ccy * IO.gY + (uint32_t)ccz * IO.gZ - IO.g_base_off);
       MRT_FLUSH_ALL(pb);
     }
   }
@@ -424,6 +432,8 @@ size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg) {
   return 256 + bwd_priv_bytes(ntf) + nht * (size_t)nviews * (size_t)(nseg < 1 ? 1 : nseg) * sizeof(uint2);
 }
 
+size_t mrt_bwd_zeroed_scratch_bytes(int ntf) { return 256 + bwd_priv_bytes(ntf); }
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -448,9 +458,10 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   const bool seg = A.ck != nullptr && A.k_end != nullptr && A.warp_kmax != nullptr && A.seg_slots > 0;
   unsigned char* scr = reinterpret_cast<unsigned char*>(A.scratch);
   unsigned* counters = reinterpret_cast<unsigned*>(scr);
-  float4* priv = reinterpret_cast<float4*>(scr + 256);
+  float4* priv = A.shared_priv ? reinterpret_cast<float4*>(A.shared_priv) : reinterpret_cast<float4*>(scr + 256);
   uint2* tasks = reinterpret_cast<uint2*>(scr + 256 + bwd_priv_bytes(ntf));
-  cudaError_t e = cudaMemsetAsync(scr, 0, 256 + (A.dtf ? bwd_priv_bytes(ntf) : 0), st);
+  cudaError_t e = cudaSuccess;
+  if (!A.scratch_zeroed) e = cudaMemsetAsync(scr, 0, 256 + (A.dtf ? bwd_priv_bytes(ntf) : 0), st);
   if (e != cudaSuccess) return e;
   const long long nthreads = (long long)nviews * nht;
   mrt_bwd_tasks_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(P.W, P.H, P.tile_begin, P.tile_end, nviews,
@@ -461,12 +472,21 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
 
   const size_t smem = (size_t)ntf * sizeof(TfEntry) + 16 * sizeof(float4);
   auto kern = mrt_bwd_kernel<NCH, LABELS, SKIP, GENERIC, HALF>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // (attribute + occupancy query memoised per instantiation, device and LUT size: both are host round trips)
+  static int c_dev = -1, c_occ = 0; static size_t c_smem = 0;
+  int dev = 0, occ = 0;
+  e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * MRT_BWD_WARPS, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) occ = 1;
+  if (dev == c_dev && smem == c_smem) {
+    occ = c_occ;
+  } else {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * MRT_BWD_WARPS, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    c_dev = dev; c_smem = smem; c_occ = occ;
+  }
   const long long max_tasks = (long long)nviews * 2 * ntiles * (seg ? A.nseg : 1);
   long long grid = (max_tasks + MRT_BWD_WARPS - 1) / MRT_BWD_WARPS;
   if (grid > (long long)num_sms() * occ) grid = (long long)num_sms() * occ;
@@ -474,15 +494,18 @@ static cudaError_t launch_bwd(const KParams& P, const CamBatch& B, int nviews, c
   IO.tf = (const float4*)A.tf; IO.flat_levels = A.flat_levels; IO.minmax = (const float2*)A.minmax;
   IO.labels = A.labels; IO.preds = A.preds;
   IO.out_rgba = (const float4*)A.out_rgba; IO.dL_dout = (const float4*)A.dL_dout;
+  IO.target = (const float4*)A.target; IO.gscale = A.gscale;
   IO.ck = seg ? (const float4*)A.ck : nullptr; IO.k_end = seg ? A.k_end : nullptr;
   IO.dtf_priv = A.dtf ? priv : nullptr;
   IO.dray = A.dray; IO.stats = (unsigned long long*)A.stats;
   IO.tasks = tasks; IO.ntasks = counters; IO.next = counters + 1;
   IO.S = seg ? A.seg_slots : 0; IO.nviews = nviews;
+  IO.gY = A.grad_pitchY ? A.grad_pitchY : P.pitchY; IO.gZ = A.grad_pitchZ ? A.grad_pitchZ : P.pitchZ;
+  IO.g_base_off = A.grad_pitchY ? 0u : P.base_off;
   kern<<<(unsigned)grid, 32 * MRT_BWD_WARPS, smem, st>>>(P, B, IO, (const ST*)vol, (VT*)A.dvol);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (A.dtf) {
+  if (A.dtf && !A.no_dtf_reduce) {
     mrt_dtf_reduce_kernel<<<ntf, 64, 0, st>>>(priv, MRT_DTF_COPIES, ntf, (float4*)A.dtf);
     e = cudaGetLastError();
   }

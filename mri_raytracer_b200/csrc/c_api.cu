@@ -5,6 +5,7 @@
 // through a thread-local string.  No allocation, no synchronisation (except *_host).
 #include "march.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 #include "../../include/mrt.h"
 #include <math.h>
 #include <stdarg.h>
@@ -714,6 +715,202 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
   cudaError_t e = mrt_launch_backward(K, cams ? chunk : nullptr, cams ? nviews : 1, mrt_packed_channels(C), packed, A,
                                       (cudaStream_t)stream);
   return e == cudaSuccess ? MRT_OK : cuda_fail(e, "render_backward");
+}
+
+// ---------------------------------------------------------------- one call per training step
+#define MRT_TRAIN_MAX_PARTS 8
+// The workspace is carved into 256-byte aligned pieces, in this order.
+struct TrainCarve {
+  size_t folded, minmax, skip, flat, ckpt, k_end, kmax, dfolded, priv, scratch, scratch_stride, mse, total;
+  int seg_slots, nseg;
+};
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int train_carve(const MrtParams* params, int32_t nviews, int32_t tfN, TrainCarve* T) {
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  if (int r = check_dims("train_step_mse", 1, X, Y, Z)) return r;
+  const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
+  MRT_REQUIRE(W >= 1 && H >= 1 && nviews >= 1 && nviews <= MRT_MAX_VIEWS, "train_step_mse: image %dx%d, %d views (1..%d)", W, H,
+              nviews, MRT_MAX_VIEWS);
+  int S = 0, nseg = 0;
+  if (int r = mrt_checkpoint_plan(params, 0, &S, &nseg)) return r;
+  T->seg_slots = S; T->nseg = nseg;
+  const size_t vol_bytes = mrt_packed_volume_bytes(1, X, Y, Z);
+  const size_t nb = (size_t)mrt_brick_count(X, Y, Z);
+  const int ntf = (params->tfMode && tfN >= 2) ? tfN : 2;
+  size_t o = 0;
+  T->folded = o;  o += align256(vol_bytes);
+  T->minmax = o;  o += align256(nb * 2 * sizeof(float));
+  T->skip = o;    o += align256(mrt_skip_levels_bytes(X, Y, Z));
+  T->flat = o;    o += align256(mrt_skip_levels_bytes(X, Y, Z));
+  T->ckpt = o;    o += align256(mrt_checkpoint_bytes(W, H, nviews, nseg));
+  T->k_end = o;   o += align256((size_t)nviews * W * H * sizeof(int32_t));
+  T->kmax = o;    o += align256((size_t)nviews * mrt_half_tile_count(W, H) * sizeof(int32_t));
+  T->dfolded = o; o += align256(vol_bytes);
+  // the privatised dL/dtf copies are shared by all parts; every part has its own task list + counters
+  T->priv = o;    o += align256(mrt_bwd_zeroed_scratch_bytes(ntf));
+  T->scratch_stride = align256(mrt_bwd_scratch_bytes(W, H, nviews, ntf, nseg));
+  T->scratch = o; o += T->scratch_stride * MRT_TRAIN_MAX_PARTS;
+  T->mse = o;     o += align256(MRT_MSE_WORK_BYTES);
+  T->total = o;
+  return MRT_OK;
+}
+size_t mrt_train_step_workspace_bytes(const MrtParams* params, int32_t nviews, int32_t tfN) {
+  TrainCarve T;
+  if (!params || train_carve(params, nviews, tfN, &T) != MRT_OK) return 0;
+  return T.total;
+}
+
+// A second stream per device carries what does not depend on the march — the flat-brick classification, the
+// gradient-buffer clears — beside it, and the adjoint (so that the loss reduction can run beside THAT on the
+// caller's stream).  It forks from and joins the caller's stream through events: the caller sees one
+// stream-ordered call (and may capture it in a graph).  With the loss gradient formed per pixel inside the
+// adjoint, the backward of an image part depends on no other part's forward, so the image can also be split
+// into tile-range parts, part i differentiated while part i+1 marches (MRT_TRAIN_PARTS; measured, see below).
+struct TrainSide { cudaStream_t s2; cudaEvent_t ev[MRT_TRAIN_MAX_PARTS + 2]; bool ok; };
+static TrainSide* train_side() {
+  static TrainSide side[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  TrainSide* S = &side[dev];
+  if (!S->ok) {
+    if (cudaStreamCreateWithFlags(&S->s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < MRT_TRAIN_MAX_PARTS + 2; ++i)
+      if (cudaEventCreateWithFlags(&S->ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    S->ok = true;
+  }
+  return S;
+}
+#define MRT_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, "train_step_mse"); } while (0)
+// Stage trace for tools/ (not part of the ABI in mrt.h): when armed, the NEXT mrt_train_step_mse records a timing
+// event on the caller's stream after every stage; mrt_debug_train_trace(ms[6]) synchronises and returns the
+// device time of fold | classify | march (all parts) | wait for the last adjoint + dL/dtf reduce | fold adjoint |
+// loss + final join, as seen by the caller's stream.
+static cudaEvent_t g_trace_ev[7];
+static int g_trace_state = 0;            // 0 off, 1 armed, 2 recorded
+#define MRT_TRACE(i) do { if (g_trace_state == 1) cudaEventRecord(g_trace_ev[i], s); } while (0)
+int mrt_debug_train_trace(float* ms6) {
+  if (ms6 == nullptr) {                  // arm
+    if (!g_trace_ev[0]) for (int i = 0; i < 7; ++i) if (cudaEventCreate(&g_trace_ev[i]) != cudaSuccess) return MRT_ERR_CUDA;
+    g_trace_state = 1;
+    return MRT_OK;
+  }
+  if (g_trace_state != 2) return MRT_ERR_BAD_ARG;
+  if (cudaEventSynchronize(g_trace_ev[6]) != cudaSuccess) return MRT_ERR_CUDA;
+  for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms6[i], g_trace_ev[i], g_trace_ev[i + 1]);
+  g_trace_state = 0;
+  return MRT_OK;
+}
+static int train_env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+// Measured at cfg3 (gpurun_out/call_t4.txt, profiles/r02_train_step_parts.txt): 1 part 0.494 ms per step, 2 parts
+// 0.627, 4 parts 0.644, 8 parts 0.953 — the persistent adjoint CTAs fill the register file (5 x 128 threads x 102
+// registers per SM), so the next part's march finds no room beside them and the parts serialise with one tail each.
+// The split stays as a knob (MRT_TRAIN_PARTS) for the measurement; the default is ONE part.
+#ifndef MRT_TRAIN_PARTS
+#define MRT_TRAIN_PARTS 1
+#endif
+
+int mrt_train_step_mse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
+                       const float* planar, int32_t C, const float* tf, int32_t tfN, const float* target_rgba,
+                       void* workspace, float* out_rgba, float* loss, float* dL_dplanar, float* dL_dtf, void* stream) {
+  MRT_REQUIRE(params && planar && target_rgba && workspace && out_rgba, "train_step_mse: null pointer");
+  MRT_REQUIRE(dL_dplanar || dL_dtf, "train_step_mse: nothing to differentiate");
+  if (!params->skipEmpty || params->tMode != 0 || params->gamma != 1.0f || params->volDtype != 0 || params->shardEnabled ||
+      params->showSeg || params->showPred)
+    return fail(MRT_ERR_UNSUPPORTED, "train_step_mse: needs skipEmpty=1, indexed stepping, gamma 1, no overlays, an unsharded fp32 "
+                                     "planar volume (use mrt_render_forward_ckpt + mrt_render_backward otherwise)");
+  MRT_REQUIRE(!dL_dtf || (params->tfMode && tf), "train_step_mse: dL_dtf needs tfMode=1 and a LUT");
+  const int V = cams ? nviews : 1;
+  TrainCarve T;
+  if (int r = train_carve(params, V, tfN, &T)) return r;
+  TrainSide* S = train_side();
+  if (!S) return fail(MRT_ERR_CUDA, "train_step_mse: cannot create the side stream");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* folded = reinterpret_cast<float*>(ws + T.folded);
+  float* minmax = reinterpret_cast<float*>(ws + T.minmax);
+  uint8_t* skip = ws + T.skip; uint8_t* flat = ws + T.flat;
+  float* ckpt = reinterpret_cast<float*>(ws + T.ckpt);
+  int32_t* k_end = reinterpret_cast<int32_t*>(ws + T.k_end);
+  int32_t* kmax = reinterpret_cast<int32_t*>(ws + T.kmax);
+  float* dfolded = reinterpret_cast<float*>(ws + T.dfolded);
+  const int X = (int)params->dims[0], Y = (int)params->dims[1], Z = (int)params->dims[2];
+  const int W = (int)params->imageSize[0], H = (int)params->imageSize[1];
+  const int ntf = (params->tfMode && tfN >= 2) ? tfN : 2;
+  const int ntiles = mrt_tile_count(W, H);
+  // measurement knobs (tools/time_train_step.py): no side stream at all; number of image parts; unfold always
+  static const bool no_side = getenv("MRT_TRAIN_NO_SIDE") != nullptr;
+  static const int parts_cfg = train_env_int("MRT_TRAIN_PARTS", MRT_TRAIN_PARTS, 1, MRT_TRAIN_MAX_PARTS);
+  static const bool no_direct = getenv("MRT_TRAIN_NO_DIRECT") != nullptr;
+  cudaStream_t s = (cudaStream_t)stream, s2 = no_side ? s : S->s2;
+  int parts = parts_cfg;
+  if (parts > ntiles) parts = ntiles;
+
+  MrtParams P = *params;                       // the folded field is rendered as ONE modality of weight 1
+  P.volEnabled[0] = 1; P.volEnabled[1] = P.volEnabled[2] = P.volEnabled[3] = 0;
+  P.volWeight[0] = P.volWeight[1] = P.volWeight[2] = P.volWeight[3] = 1.0f;
+  // A single modality whose fold is the identity: the adjoint reduces straight into the caller's planar
+  // gradient ([Z][Y][X] pitches; reductions go to L2, which has no use for the sampler layout's bank skew) and the
+  // fold's adjoint (a 2 x 67 MB layout copy at 256^3) disappears.
+  float wgt[4], inv_wsum;
+  blend_weights(params, C, wgt, &inv_wsum);
+  const bool direct = dL_dplanar && C == 1 && wgt[0] * inv_wsum == 1.0f && !no_direct;
+
+  // caller's stream: fold + occupancy -> classify -> checkpointing march, part by part
+  MRT_TRACE(0);
+  if (int r = mrt_fold_volume_occupancy_f32(params, planar, C, folded, minmax, s)) return r;
+  MRT_CU(cudaEventRecord(S->ev[0], s));
+  MRT_TRACE(1);
+  if (int r = mrt_classify_bricks(&P, minmax, 1, tf, tfN, nullptr, nullptr, skip, 0, s)) return r;
+  MRT_TRACE(2);
+  // side stream: flat-brick levels, cleared gradient buffers
+  MRT_CU(cudaStreamWaitEvent(s2, S->ev[0], 0));
+  if (int r = mrt_classify_bricks(&P, minmax, 1, tf, tfN, nullptr, nullptr, flat, 1, s2)) return r;
+  MRT_CU(cudaMemsetAsync(ws + T.priv, 0, T.scratch - T.priv, s2));                       // shared privatised dL/dtf copies
+  MRT_CU(cudaMemset2DAsync(ws + T.scratch, T.scratch_stride, 0, 256, (size_t)parts, s2));   // every part's task counters
+  if (dL_dplanar)
+    MRT_CU(cudaMemsetAsync(direct ? dL_dplanar : dfolded, 0,
+                           direct ? (size_t)X * Y * Z * sizeof(float) : mrt_packed_volume_bytes(1, X, Y, Z), s2));
+  if (dL_dtf) MRT_CU(cudaMemsetAsync(dL_dtf, 0, (size_t)ntf * 4 * sizeof(float), s2));
+
+  float chunk[MRT_MAX_VIEWS * 12];
+  if (cams) pack_cams(cams, V, chunk);
+  MrtBwdArgs A = {};
+  A.tf = tf; A.flat_levels = flat; A.minmax = minmax;
+  A.out_rgba = out_rgba; A.dL_dout = nullptr; A.target = target_rgba;
+  A.gscale = 2.0f / (float)((size_t)V * W * H * 4);
+  A.ck = T.nseg > 1 ? ckpt : out_rgba; A.seg_slots = T.seg_slots; A.nseg = T.nseg; A.k_end = k_end; A.warp_kmax = kmax;
+  A.dvol = dL_dplanar ? (direct ? (void*)dL_dplanar : (void*)dfolded) : nullptr;
+  if (direct) { A.grad_pitchY = (uint32_t)X; A.grad_pitchZ = (uint32_t)X * (uint32_t)Y; }
+  A.dtf = dL_dtf; A.scratch_zeroed = 1; A.no_dtf_reduce = 1; A.shared_priv = ws + T.priv + 256;
+  for (int i = 0; i < parts; ++i) {
+    const int t0 = (int)((long long)ntiles * i / parts), t1 = (int)((long long)ntiles * (i + 1) / parts);
+    KParams K;
+    if (int r = derive(&P, 1, tfN, true, t0, t1, &K)) return r;
+    MRT_REQUIRE(!K.tfMode || tf != nullptr, "train_step_mse: tfMode=1 needs tf");
+    MRT_CU(mrt_launch_forward_ckpt(K, cams ? chunk : nullptr, V, 1, folded, tf, skip, nullptr, nullptr, out_rgba,
+                                   T.nseg > 1 ? ckpt : nullptr, T.seg_slots, T.nseg, k_end, kmax, s, /*clear_aux=*/false));
+    MRT_CU(cudaEventRecord(S->ev[1 + i], s));
+    MRT_CU(cudaStreamWaitEvent(s2, S->ev[1 + i], 0));
+    A.scratch = ws + T.scratch + T.scratch_stride * (size_t)i;
+    MRT_CU(mrt_launch_backward(K, cams ? chunk : nullptr, V, 1, folded, A, s2));
+  }
+  MRT_TRACE(3);
+  MRT_CU(cudaEventRecord(S->ev[MRT_TRAIN_MAX_PARTS + 1], s2));
+  // caller's stream again: the loss beside the last adjoint, then the dL/dtf reduction and the fold's adjoint
+  if (loss) MRT_CU(mrt_launch_mse(out_rgba, target_rgba, (size_t)V * W * H * 4, ws + T.mse, loss, s));
+  MRT_CU(cudaStreamWaitEvent(s, S->ev[MRT_TRAIN_MAX_PARTS + 1], 0));
+  if (dL_dtf) MRT_CU(mrt_launch_dtf_reduce(ws + T.priv + 256, 64, ntf, dL_dtf, s));
+  MRT_TRACE(4);
+  if (dL_dplanar && !direct)
+    if (int r = mrt_unfold_grad_f32(params, dfolded, C, dL_dplanar, s)) return r;
+  MRT_TRACE(5);
+  MRT_TRACE(6);
+  if (g_trace_state == 1) g_trace_state = 2;
+  return MRT_OK;
 }
 
 // ---------------------------------------------------------------- adaptive (inverse-CDF) sampling

@@ -401,7 +401,7 @@ static cudaError_t dispatch_fwd_ckpt(const KParams& P, const CamBatch& B, int nv
 cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                     const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                     float* out_rgba, float* ck, int seg_slots, int nseg, int32_t* k_end, int32_t* warp_kmax,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, bool clear_aux) {
   if (P.half || P.shard || P.tMode != 0 || P.gamma != 1.0f || seg_slots < 1 || nseg < 1 || !k_end || !warp_kmax ||
       (nseg > 1 && !ck))
     return cudaErrorInvalidValue;
@@ -414,8 +414,14 @@ cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nvi
     for (int v = 0; v < nviews; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)v * 12 + i];
   }
   const size_t npix = (size_t)P.W * P.H, nht = 2 * (size_t)mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H);
-  cudaError_t e = cudaMemsetAsync(k_end, 0, npix * nviews * sizeof(int32_t), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(warp_kmax, 0, nht * nviews * sizeof(int32_t), st);
+  // every tile of [tile_begin, tile_end) writes its k_end / warp_kmax entries (the checkpointing variant culls nothing);
+  // the entries of the OTHER tiles are defined as zero: clear unless the range is the whole image or the caller
+  // covers the image with several launches (clear_aux = false)
+  cudaError_t e = cudaSuccess;
+  if (clear_aux && !(P.tile_begin == 0 && P.tile_end == mrt_tiles_x_(P.W) * mrt_tiles_y_(P.H))) {
+    e = cudaMemsetAsync(k_end, 0, npix * nviews * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(warp_kmax, 0, nht * nviews * sizeof(int32_t), st);
+  }
   if (e != cudaSuccess) return e;
   CkptOut CK;
   CK.ck = reinterpret_cast<float4*>(ck); CK.S = seg_slots; CK.nseg = nseg; CK.k_end = k_end; CK.warp_kmax = warp_kmax;

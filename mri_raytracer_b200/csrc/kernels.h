@@ -30,7 +30,7 @@ cudaError_t mrt_launch_forward_tma(const KParams& P, int box_edge, int tile, con
 cudaError_t mrt_launch_forward_ckpt(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                     const float* tf, const uint8_t* levels, const int32_t* labels, const int32_t* preds,
                                     float* out_rgba, float* ck, int seg_slots, int nseg, int32_t* k_end, int32_t* warp_kmax,
-                                    cudaStream_t st);
+                                    cudaStream_t st, bool clear_aux = true);
 
 // Everything mrt_launch_backward takes besides geometry and the volume.  ck / k_end / warp_kmax
 // (all three, from mrt_launch_forward_ckpt) switch on the segment-parallel path.
@@ -40,7 +40,20 @@ struct MrtBwdArgs {
   const float* out_rgba; const float* dL_dout;
   const float* ck; int seg_slots, nseg; const int32_t* k_end; const int32_t* warp_kmax;
   void* dvol; float* dtf; void* scratch; float* dray; void* stats;
+  // fused MSE loss (mrt_train_step_mse): dL_dout == nullptr and the kernel forms G = gscale * (out_rgba - target)
+  // per pixel itself; scratch_zeroed: the caller already cleared the counters and the privatised dL/dtf block
+  const float* target; float gscale; int scratch_zeroed;
+  // gradient buffer with its own element pitches (0 = the volume's packed pitches): the one-call training step lets
+  // the adjoint reduce a single-modality gradient straight into the caller's planar [Z][Y][X] tensor
+  uint32_t grad_pitchY, grad_pitchZ;
+  int no_dtf_reduce;           // leave the privatised dL/dtf copies where they are (the caller reduces several launches at once)
+  void* shared_priv;           // privatised dL/dtf block shared by several launches (mrt_bwd_zeroed_scratch_bytes - 256 bytes, zeroed)
 };
+// loss[0] = mean((a - b)^2) over n floats (n % 4 == 0), deterministic (fixed-order two-stage sum).
+// `work` = MRT_MSE_WORK_BYTES bytes, zero before the FIRST use (the kernel leaves it ready for the next).
+#define MRT_MSE_WORK_BYTES 4096
+cudaError_t mrt_launch_mse(const float* a, const float* b, size_t n, void* work, float* loss, cudaStream_t st);
+size_t mrt_bwd_zeroed_scratch_bytes(int ntf);
 cudaError_t mrt_launch_backward(const KParams& P, const float* cams, int nviews, int packed_ch, const void* vol,
                                 const MrtBwdArgs& A, cudaStream_t st);
 size_t mrt_bwd_scratch_bytes(int W, int H, int nviews, int ntf, int nseg);

@@ -621,3 +621,61 @@ cudaError_t mrt_launch_normalize(const float* in, size_t n, float vmin, float rn
   mrt_normalize_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, vmin, rng, out);
   return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------ mean squared error (training-step loss)
+// loss = mean((a - b)^2), BASELINE cfg3's loss, as ONE launch: every CTA writes its partial sum, the
+// CTA that arrives last (atomic ticket) adds the partials in index order — the same bits every run —
+// and hands the ticket counter back at zero, so `work` needs clearing only before its first use.
+#define MRT_MSE_CTAS 256
+__global__ void __launch_bounds__(256) mrt_mse_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t n4,
+                                                      float inv_n, float* __restrict__ partial, unsigned* __restrict__ ticket,
+                                                      float* __restrict__ loss) {
+  __shared__ float s_w[8];
+  __shared__ bool s_last;
+  float s = 0.0f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(a + i), y = __ldg(b + i);
+    const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z, dw = x.w - y.w;
+    s += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float t = 0.0f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(partial + i);   // gridDim.x <= 256: one term per thread
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_w[w];
+    *loss = r * inv_n;
+    *ticket = 0u;
+  }
+}
+cudaError_t mrt_launch_mse(const float* a, const float* b, size_t n, void* work, float* loss, cudaStream_t st) {
+  if (n == 0 || (n & 3)) return cudaErrorInvalidValue;
+  const size_t n4 = n / 4;
+  size_t g = (n4 + 255) / 256;
+  if (g > MRT_MSE_CTAS) g = MRT_MSE_CTAS;
+  static_assert(MRT_MSE_CTAS * sizeof(float) + 64 <= MRT_MSE_WORK_BYTES, "mse work area too small");
+  float* partial = reinterpret_cast<float*>(work);
+  unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(work) + MRT_MSE_CTAS * sizeof(float));
+  mrt_mse_kernel<<<(unsigned)g, 256, 0, st>>>((const float4*)a, (const float4*)b, n4, 1.0f / (float)n, partial, ticket, loss);
+  return cudaGetLastError();
+}

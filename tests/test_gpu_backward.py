@@ -196,3 +196,61 @@ def test_differentiable_batch_of_views(cuda):
         tot = tot + (ref * G[i]).sum()
     tot.backward()
     assert _rel(v.grad.cpu(), vo.grad) <= RTOL and _rel(t.grad.cpu(), to.grad) <= RTOL
+
+
+@pytest.mark.parametrize("C,alpha", [(1, 0), (3, 1)])
+def test_train_step_one_call_equals_autograd_and_oracle(cuda, C, alpha):
+    """api.TrainStep (mrt_train_step_mse: fold + occupancy, classify, checkpointing march, loss,
+    adjoint with dL/dC formed in the kernel, fold adjoint — ONE library call) against the autograd
+    path of the same library (image bit for bit, gradients to the order of the atomics) and against
+    the oracle's autograd (1e-3); a second call on the same object reuses the workspace."""
+    vol, _, P = small_scene(C=C, dims=(32, 30, 28), W=48, H=40, seed=4 + C)
+    P = replace(P, tfMode=1, alphaMode=alpha, volWeight=(1.0, 0.5, 2.0, 0.75))
+    tf = ramp_tf(64, sigma_scale=20.0, cutoff=0.1)
+    target = O.render(vol, P, tf=tf * torch.tensor([0.8, 1.0, 1.1, 1.3]))
+    v0 = vol.clone().requires_grad_(True); t0 = tf.clone().requires_grad_(True)
+    loss_o = ((O.render(v0, P, tf=t0) - target) ** 2).mean()
+    loss_o.backward()
+    v = vol.cuda().requires_grad_(True); t = tf.cuda().requires_grad_(True)
+    img_a = api.render(v, None, t, P)
+    loss_a = torch.nn.functional.mse_loss(img_a, target.cuda())
+    loss_a.backward()
+    step = api.TrainStep(P, n_views=1, tf_entries=64)
+    for it in range(2):                                    # the second pass runs on a used workspace
+        loss, img, dvol, dtf = step(vol.cuda(), tf.cuda(), target.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(img, img_a.detach())
+        assert abs(float(loss) - float(loss_a)) <= 1e-6 * abs(float(loss_a)) + 1e-12
+        assert abs(float(loss) - float(loss_o)) <= 1e-6 + 1e-4 * abs(float(loss_o))
+        assert _rel(dvol, v.grad) <= 2e-5 and _rel(dtf, t.grad) <= 2e-5
+        assert _rel(dvol.cpu(), v0.grad) <= RTOL and _rel(dtf.cpu(), t0.grad) <= RTOL
+    # one gradient only
+    _, _, dv_only, none_tf = step(vol.cuda(), tf.cuda(), target.cuda(), want_dtf=False)
+    assert none_tf is None and _rel(dv_only, v.grad) <= 2e-5
+    _, _, none_v, dt_only = step(vol.cuda(), tf.cuda(), target.cuda(), want_dvol=False)
+    assert none_v is None and _rel(dt_only, t.grad) <= 2e-5
+
+
+def test_train_step_batch_of_views_and_unsupported_modes(cuda):
+    from mri_raytracer_b200 import OrbitalCamera, orbit_views
+    import numpy as np
+    vol, _, P = small_scene(C=1, dims=(30, 28, 24), W=40, H=32, seed=17)
+    P = replace(P, tfMode=1)
+    tf = ramp_tf(32, sigma_scale=15.0, cutoff=0.1)
+    cam = OrbitalCamera(initial_radius=float(np.linalg.norm(np.asarray(P.eye))), initial_phi=1.3, initial_theta=0.4)
+    cam.set_fov_degrees(70.0)
+    cams = orbit_views(cam, 3)
+    target = torch.rand((3, 32, 40, 4), generator=torch.Generator().manual_seed(2)).cuda()
+    v = vol.cuda().requires_grad_(True); t = tf.cuda().requires_grad_(True)
+    imgs = api.render_views(v, cams, t, P)
+    loss_a = torch.nn.functional.mse_loss(imgs, target)
+    loss_a.backward()
+    step = api.TrainStep(P, n_views=3, tf_entries=32)
+    loss, img, dvol, dtf = step(vol.cuda(), tf.cuda(), target, cams=cams)
+    assert torch.equal(img, imgs.detach())
+    assert abs(float(loss) - float(loss_a)) <= 1e-6 * abs(float(loss_a))
+    assert _rel(dvol, v.grad) <= 2e-5 and _rel(dtf, t.grad) <= 2e-5
+    with pytest.raises(ValueError):
+        step(vol.cuda(), tf.cuda(), target[:1])            # built for 3 views
+    with pytest.raises(RuntimeError):                      # MRT_ERR_UNSUPPORTED: the one-call step needs skipping on
+        api.TrainStep(replace(P, skipEmpty=0), n_views=1, tf_entries=32)(vol.cuda(), tf.cuda(), target[0].contiguous())

@@ -152,6 +152,30 @@ def cfg3():
         graph_rel = float((gv_graph - v.grad).abs().max() / v.grad.abs().max()), float((gt_graph - t.grad).abs().max() / t.grad.abs().max())
     except Exception as e:                      # report, do not hide
         graph_rel = f"graph capture failed: {type(e).__name__}: {e}"
+    # ---- the same step as ONE library call (mrt_train_step_mse): no autograd graph, no dL/dC tensor, buffer
+    # clears + flat classification + loss on a side stream
+    one = {}
+    try:
+        ts = api.TrainStep(P, n_views=1, tf_entries=tf.shape[0])
+        vd, tdd = v.detach(), t.detach()
+        v.grad = None; t.grad = None
+        loss_e = step(); torch.cuda.synchronize()
+        loss_1, img_1, dv_1, dt_1 = ts(vd, tdd, target); torch.cuda.synchronize()
+        one["grad_rel_vs_autograd"] = [float((dv_1 - v.grad).abs().max() / v.grad.abs().max()),
+                                       float((dt_1 - t.grad).abs().max() / t.grad.abs().max())]
+        one["loss_rel_vs_autograd"] = abs(float(loss_1) - float(loss_e)) / abs(float(loss_e))
+        one["ms"] = timeit(lambda: ts(vd, tdd, target), reps=2)
+        one["ms_pipelined_8"] = timeit(lambda: ts(vd, tdd, target), reps=8)
+        try:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                ts(vd, tdd, target)
+            g1.replay(); torch.cuda.synchronize()
+            one["ms_cuda_graph"] = timeit(g1.replay, reps=4)
+        except Exception as e:
+            one["ms_cuda_graph"] = f"graph capture failed: {type(e).__name__}: {e}"
+    except Exception as e:                      # report, do not hide
+        one["error"] = f"{type(e).__name__}: {e}"
     Vv = api.Volume(vol.cuda())
     _, _, counts = api.render_aux(Vv, None, tf.cuda(), P)
     c = counts.sum(dim=(0, 1)).tolist()
@@ -205,7 +229,7 @@ def cfg3():
         api.render(ga, None, gb, sP).square().mean().backward()
         rel_v = float((ga.grad.cpu() - a.grad).abs().max() / a.grad.abs().max())
         rel_t = float((gb.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
-    return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_fwd_bwd_cuda_graph=ms_graph, graph_vs_eager_grad_rel=graph_rel, ms_fwd_only=ms_fwd, ms_forward_ckpt_kernel=ms_fwd_ckpt, ms_backward_call=ms_bwd,
+    return dict(cfg="cfg3", ms_fwd_bwd=ms, ms_train_step_one_call=one.get("ms"), one_call=one, ms_fwd_bwd_cuda_graph=ms_graph, graph_vs_eager_grad_rel=graph_rel, ms_fwd_only=ms_fwd, ms_forward_ckpt_kernel=ms_fwd_ckpt, ms_backward_call=ms_bwd,
                 ms_backward_whole_ray=ms_bwd_whole, steps_per_s=1e3 / ms, samples_taken=c[1],
                 gsamples_per_s_fwd_bwd=c[1] / ms / 1e6, grad_rel_volume=rel_v, grad_rel_tf=rel_t, roofline=roof,
                 note="fwd+bwd through the autograd API incl. layout + occupancy build, classify, checkpointing march, adjoint, unfold")
