@@ -453,17 +453,52 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, const Strip
 // outputs are [nviews][H][W](...) contiguous.  Views are rendered by ONE launch per chunk of
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
-// Sparse framebuffer gather.  mrt_view_spans_kernel: one thread per (view, tile row) evaluates
-// mrt_view_span.  mrt_fill_outside_kernel (receiving side): background into every tile outside its
-// row's span — exactly the tiles the senders skip.  Same tile geometry as the march.
+// Sparse framebuffer gather.  The span of a (view, tile row) is the x-extent of everything that can be
+// non-background there: the UNION, over the ACTIVE BRICKS, of the row band's cut through each brick's projected
+// box (mrt_project_box / mrt_band_extent: margins and outward rounding as before, now per brick).  Round 2
+// projected only the bounding box of all active bricks: for the bench's head that hull holds 5 500 tiles per
+// 1024^2 view, the union of the brick footprints 3 000-3 400 — everything in between was marched, stored and sent
+// over PCIe / NVLink although it is pure background.  Every sample slot a ray can evaluate lies in an active
+// brick, i.e. the pixel lies inside that brick's projection: pixels outside the union are exactly the background.
+// Integer min / max reductions: deterministic in (P, cam, levels), so the sender of a sparse gather and the owner
+// of the image still compute the same spans independently.  mrt_spans_init_kernel empties the spans first.
+// mrt_fill_outside_kernel (receiving side): background into every tile outside its row's span — exactly the
+// tiles the senders skip.  Same tile geometry as the march.
+__global__ void __launch_bounds__(128)
+mrt_spans_init_kernel(int n, int2* __restrict__ spans) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) spans[i] = make_int2(0x7fffffff, -1);
+}
 __global__ void __launch_bounds__(128)
 mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B, int nviews,
                       const uint8_t* __restrict__ levels, int2* __restrict__ spans) {
-  const int band = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  const int nb = P.nbx * P.nby * P.nbz;
+  if (b >= nb || v >= nviews) return;
+  const int lvl = __ldg(levels + b);
+  if (lvl != 0 && !(lvl & 0x80)) return;                                   // an empty brick: no slot in it is ever evaluated
   const int ty = mrt_tiles_y_(P.H);
-  if (band >= ty || v >= nviews) return;
-  const ActiveBox A = mrt_active_box(P, levels);
-  spans[(size_t)v * ty + band] = mrt_view_span(P, B.cam[v], A, band);
+  const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
+  ActiveBox A;                                                             // as mrt_active_box, for this one brick
+  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
+  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
+  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + 1) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
+  int2* sp = spans + (size_t)v * ty;
+  float cx[8], cy[8];
+  if (mrt_project_box(P, B.cam[v], A, cx, cy) != 0) {                      // behind the eye / degenerate basis: no culling
+    for (int band = 0; band < ty; ++band) { atomicMin(&sp[band].x, 0); atomicMax(&sp[band].y, P.W - 1); }
+    return;
+  }
+  float ymin = cy[0], ymax = cy[0];
+#pragma unroll
+  for (int c = 1; c < 8; ++c) { ymin = fminf(ymin, cy[c]); ymax = fmaxf(ymax, cy[c]); }
+  if (!(ymax >= -2.0f) || !(ymin <= (float)P.H + 1.0f)) return;            // off screen
+  const int b0 = max(0, ((int)floorf(fmaxf(ymin, -8.0f)) >> MRT_TILE_SHIFT) - 1);
+  const int b1 = min(ty - 1, ((int)ceilf(fminf(ymax, (float)P.H + 8.0f)) >> MRT_TILE_SHIFT) + 1);
+  for (int band = b0; band <= b1; ++band) {
+    const int2 e = mrt_band_extent(P, cx, cy, band);
+    if (e.x <= e.y) { atomicMin(&sp[band].x, e.x); atomicMax(&sp[band].y, e.y); }
+  }
 }
 __global__ void __launch_bounds__(256)
 mrt_fill_outside_kernel(const __grid_constant__ KParams P, const int2* __restrict__ spans,
@@ -497,8 +532,10 @@ cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nview
     const int nv = (nviews - v0 < MRT_MAX_VIEWS) ? nviews - v0 : MRT_MAX_VIEWS;
     CamBatch B;
     for (int v = 0; v < nv; ++v) for (int i = 0; i < 12; ++i) B.cam[v][i] = cams[(size_t)(v0 + v) * 12 + i];
-    mrt_view_spans_kernel<<<dim3((ty + 127) / 128, nv), 128, 0, st>>>(P, B, nv, levels,
-                                                                     reinterpret_cast<int2*>(spans) + (size_t)v0 * ty);
+    int2* sp = reinterpret_cast<int2*>(spans) + (size_t)v0 * ty;
+    const int nb = P.nbx * P.nby * P.nbz;
+    mrt_spans_init_kernel<<<(nv * ty + 127) / 128, 128, 0, st>>>(nv * ty, sp);
+    mrt_view_spans_kernel<<<dim3((nb + 127) / 128, nv), 128, 0, st>>>(P, B, nv, levels, sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

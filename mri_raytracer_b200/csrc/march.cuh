@@ -65,8 +65,8 @@ struct CamBatch { float cam[MRT_MAX_VIEWS][12]; };
 // to base[strip] (a peer-mapped buffer of the strip's owner rank) instead of the local image.
 #define MRT_MAX_STRIPS 16
 // spans (optional, sparse framebuffer gather): per view of the launch and per tile row an int2
-// (x0, x1), the inclusive pixel span outside which every ray of that row band certainly misses the
-// active-brick box (mrt_view_span); tiles_y entries per view.  Tiles outside are NOT stored by the
+// (x0, x1), the inclusive pixel span outside which every ray of that row band certainly misses every
+// active brick (mrt_view_spans_kernel); tiles_y entries per view.  Tiles outside are NOT stored by the
 // march unless store_outside is set: the owner of the image fills them with the background itself
 // (mrt_fill_outside_spans), from the same spans.  With store_outside the spans only serve as the
 // (much cheaper) replacement of the per-ray box test: one LDG + two compares per warp.
@@ -220,18 +220,20 @@ __device__ __forceinline__ bool mrt_ray_may_hit(const KParams& P, const float* _
   return tout >= fmaxf(tin, 0.0f);
 }
 
-// Screen footprint of the active-brick box for one camera, as one x-span per 8-pixel row band
-// (tile row): the 8 corners of the box widened by MRT_SPAN_MARGIN voxels (> MRT_BOX_MARGIN, so a ray
-// the slab test lets through always lies inside) are projected, and the convex hull's x-extent
-// inside the band is the extent of the 12 projected edges clipped to the band (the hull's boundary
-// is made of edges; the others lie inside), rounded outward by one pixel.  Deterministic in
-// (P, cam, box): the sender of a sparse gather and the owner of the image evaluate it
-// independently and get the same integers.  Empty span: x0 > x1.
+// Screen footprint of a box of bricks for one camera, as one x-span per 8-pixel row band (tile row):
+// the 8 corners of the box widened by MRT_SPAN_MARGIN voxels (> MRT_BOX_MARGIN, so a ray the slab
+// test lets through always lies inside) are projected, and the convex hull's x-extent inside the
+// band is the extent of the 12 projected edges clipped to the band (the hull's boundary is made of
+// edges; the others lie inside), rounded outward by one pixel.  A view's spans are the union of
+// these over its active bricks (forward.cu: mrt_view_spans_kernel).  Deterministic in (P, cam, box).
+// Empty span: x0 > x1.
 #define MRT_SPAN_MARGIN 0.75f
-__device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __restrict__ cam, const ActiveBox& A,
-                                              int band) {
+// Projects the 8 corners of box A (widened to MRT_SPAN_MARGIN) to pixel coordinates.  Returns 0 = done,
+// 1 = no culling possible (degenerate basis, or the box reaches behind the eye), 2 = empty box.
+__device__ __forceinline__ int mrt_project_box(const KParams& P, const float* __restrict__ cam, const ActiveBox& A,
+                                               float cx[8], float cy[8]) {
   const float* eye = cam; const float* U = cam + 3; const float* V = cam + 6; const float* Wv = cam + 9;
-  if (A.hi[0] < A.lo[0]) return make_int2(1, 0);                           // no active brick
+  if (A.hi[0] < A.lo[0]) return 2;                                         // no active brick
   // camera coordinates of a world offset w: (xc, yc, zc) = M^-1 w with M = [U V W] — rows (VxW, WxU,
   // UxV)/det, which is M^T for the orthonormal bases the cameras produce but stays correct for any
   // basis the C ABI lets through (the exact ray set-up never assumes orthonormality either)
@@ -239,11 +241,10 @@ __device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __r
   const float r1x = Wv[1] * U[2] - Wv[2] * U[1], r1y = Wv[2] * U[0] - Wv[0] * U[2], r1z = Wv[0] * U[1] - Wv[1] * U[0];
   const float r2x = U[1] * V[2] - U[2] * V[1], r2y = U[2] * V[0] - U[0] * V[2], r2z = U[0] * V[1] - U[1] * V[0];
   const float det = U[0] * r0x + U[1] * r0y + U[2] * r0z;
-  if (!(fabsf(det) > 1e-12f)) return make_int2(0, P.W - 1);                // degenerate basis: no culling
+  if (!(fabsf(det) > 1e-12f)) return 1;                                    // degenerate basis: no culling
   const float idet = 1.0f / det;
   const float m = MRT_SPAN_MARGIN - MRT_BOX_MARGIN;
   const float aspect = (float)P.W / fmaxf(1.0f, (float)P.H);
-  float cx[8], cy[8];
   bool behind = false;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -263,7 +264,10 @@ __device__ __forceinline__ int2 mrt_view_span(const KParams& P, const float* __r
     }
     cx[c] = (uvx + 1.0f) * 0.5f * (float)P.W - 0.5f; cy[c] = (uvy + 1.0f) * 0.5f * (float)P.H - 0.5f;
   }
-  if (behind) return make_int2(0, P.W - 1);                                // the box reaches behind the eye: everything
+  return behind ? 1 : 0;                                                   // the box reaches behind the eye: everything
+}
+// x-extent of the projected box's convex hull inside row band `band` (rounded outward by one pixel); empty: x0 > x1
+__device__ __forceinline__ int2 mrt_band_extent(const KParams& P, const float cx[8], const float cy[8], int band) {
   const float ylo = (float)(band << MRT_TILE_SHIFT) - 1.0f, yhi = (float)((band << MRT_TILE_SHIFT) + MRT_TILE_EDGE);
   float xmin = 3.0e38f, xmax = -3.0e38f;
 #pragma unroll
