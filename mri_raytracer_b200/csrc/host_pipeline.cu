@@ -97,13 +97,14 @@ const char* mrt_host_pipeline_error(const MrtHostPipeline* p) { return p ? p->er
 #define HP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(p->err, sizeof(p->err), "%s: %s", #call, cudaGetErrorString(e_)); rc = MRT_ERR_CUDA; goto fail; } } while (0)
 
-// MRT_HP_QUAD=1: the march samples from the 16 B/voxel quad layout (mrt_pack_volume_quad).  Off by
-// default HERE: this pipeline's march stores straight into host memory and is bound by those PCIe
-// writes, so the faster sampler buys nothing and building the 4x larger layout costs a little
-// (measured 0.945 vs 0.918 ms per 8-view step); the device-resident paths (api.Volume) default to it.
+// The march samples from the 16 B/voxel quad layout (mrt_pack_volume_quad) unless MRT_HP_QUAD=0.  While the
+// frames' PCIe writes bounded this pipeline (spans = hull of the active box, 45 MB per step) the faster sampler
+// bought nothing and building the 4x larger layout cost a little (0.945 vs 0.918 ms per 8-view step), so it was
+// off; with the brick-union spans (26 MB per step) the step is bound by the march itself and the quad layout wins,
+// 0.640 vs 0.664 ms (gpurun_out/bench_t8_*.json).
 static bool hp_use_quad() {
   static const char* env = getenv("MRT_HP_QUAD");
-  return env && env[0] == '1';
+  return !(env && env[0] == '0');
 }
 
 int mrt_host_pipeline_create(MrtHostPipeline** out, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t W, int32_t H,
