@@ -479,10 +479,18 @@ mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__
   if (lvl != 0 && !(lvl & 0x80)) return;                                   // an empty brick: no slot in it is ever evaluated
   const int ty = mrt_tiles_y_(P.H);
   const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
-  ActiveBox A;                                                             // as mrt_active_box, for this one brick
-  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
-  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
-  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + 1) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
+  // a brick inside an aligned ALL-ACTIVE cell of e^3 bricks (level 0x80 | l, e = 2^(l-1)): the union of the cell's
+  // brick boxes IS the cell's box, so the cell's first brick projects that one box and the others have nothing to
+  // add (a solid 512^3 interior would otherwise send 10^7 reductions at a few thousand addresses)
+  int e = 1;
+  if (lvl & 0x80) {
+    e = 1 << ((lvl & 7) - 1);
+    if (((bx | by | bz) & (e - 1)) != 0) return;
+  }
+  ActiveBox A;                                                             // as mrt_active_box, for this brick / cell
+  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + e) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
+  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + e) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
+  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + e) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
   int2* sp = spans + (size_t)v * ty;
   float cx[8], cy[8];
   if (mrt_project_box(P, B.cam[v], A, cx, cy) != 0) {                      // behind the eye / degenerate basis: no culling
@@ -496,8 +504,13 @@ mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__
   const int b0 = max(0, ((int)floorf(fmaxf(ymin, -8.0f)) >> MRT_TILE_SHIFT) - 1);
   const int b1 = min(ty - 1, ((int)ceilf(fminf(ymax, (float)P.H + 8.0f)) >> MRT_TILE_SHIFT) + 1);
   for (int band = b0; band <= b1; ++band) {
-    const int2 e = mrt_band_extent(P, cx, cy, band);
-    if (e.x <= e.y) { atomicMin(&sp[band].x, e.x); atomicMax(&sp[band].y, e.y); }
+    const int2 x = mrt_band_extent(P, cx, cy, band);
+    if (x.x > x.y) continue;
+    // (a plain look first: a stale value is only ever LOOSER than the current one, so a reduction that could
+    // matter is never skipped, and interior bricks stop hammering the same few words)
+    const int2 cur = __ldcg(sp + band);
+    if (x.x < cur.x) atomicMin(&sp[band].x, x.x);
+    if (x.y > cur.y) atomicMax(&sp[band].y, x.y);
   }
 }
 __global__ void __launch_bounds__(256)
