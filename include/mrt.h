@@ -300,9 +300,9 @@ int mrt_render_forward_batch(const MrtParams* params, const MrtCamera* cams, int
 /* Sparse variant for a framebuffer that lives on ANOTHER GPU (image-space gather through peer
  * memory).  mrt_view_spans computes, per view and per tile row (8 pixel rows), the inclusive pixel
  * span (x0,x1) outside which every ray certainly misses every ACTIVE BRICK: the union over the
- * bricks mrt_classify_bricks left active of the row band's cut through each brick's projected box,
+ * bricks mrt_classify_bricks left active of the bounding rectangles of their projected boxes,
  * rounded outward (empty: x0 > x1) — much tighter than the hull of the bricks' bounding box (the bench's
- * head: 3 000-3 400 tiles per 1024^2 view instead of 5 500).  It is
+ * head: 3 200 tiles per 1024^2 view instead of 5 500).  It is
  * deterministic in its inputs, so the sender and the owner of the image compute identical spans
  * independently.  mrt_render_forward_batch_sparse does NOT store the tiles outside its views'
  * spans; the owner of the image calls mrt_fill_outside_spans on its local copy (any time: the two

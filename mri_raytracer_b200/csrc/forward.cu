@@ -454,14 +454,14 @@ static cudaError_t dispatch_fwd(const KParams& P, const CamBatch& B, const Strip
 // MRT_MAX_VIEWS (blockIdx.y = view): the short CTAs of one view fill the SMs that the long
 // central rays of the previous one leave idle, so the per-launch tail is paid once per batch.
 // Sparse framebuffer gather.  The span of a (view, tile row) is the x-extent of everything that can be
-// non-background there: the UNION, over the ACTIVE BRICKS, of the row band's cut through each brick's projected
-// box (mrt_project_box / mrt_band_extent: margins and outward rounding as before, now per brick).  Round 2
-// projected only the bounding box of all active bricks: for the bench's head that hull holds 5 500 tiles per
-// 1024^2 view, the union of the brick footprints 3 000-3 400 — everything in between was marched, stored and sent
-// over PCIe / NVLink although it is pure background.  Every sample slot a ray can evaluate lies in an active
-// brick, i.e. the pixel lies inside that brick's projection: pixels outside the union are exactly the background.
-// Integer min / max reductions: deterministic in (P, cam, levels), so the sender of a sparse gather and the owner
-// of the image still compute the same spans independently.  mrt_spans_init_kernel empties the spans first.
+// non-background there: the UNION, over the ACTIVE BRICKS, of the bounding rectangles of their projected boxes
+// (mrt_project_box: margins and outward rounding as before, now per brick).  Round 2 first projected only the
+// bounding box of all active bricks: for the bench's head that hull holds 5 500 tiles per 1024^2 view, the union
+// of the brick footprints 3 200 — everything in between was marched, stored and sent over PCIe / NVLink although
+// it is pure background.  Every sample slot a ray can evaluate lies in an active brick, i.e. the pixel lies inside
+// that brick's projection: pixels outside the union are exactly the background.  Integer min / max reductions:
+// deterministic in (P, cam, levels), so the sender of a sparse gather and the owner of the image still compute the
+// same spans independently.  mrt_spans_init_kernel empties the spans first.
 // mrt_fill_outside_kernel (receiving side): background into every tile outside its row's span — exactly the
 // tiles the senders skip.  Same tile geometry as the march.
 __global__ void __launch_bounds__(128)
@@ -479,33 +479,34 @@ mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__
   if (lvl != 0 && !(lvl & 0x80)) return;                                   // an empty brick: no slot in it is ever evaluated
   const int ty = mrt_tiles_y_(P.H);
   const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
-  // a brick inside an aligned ALL-ACTIVE cell of e^3 bricks (level 0x80 | l, e = 2^(l-1)): the union of the cell's
-  // brick boxes IS the cell's box, so the cell's first brick projects that one box and the others have nothing to
-  // add (a solid 512^3 interior would otherwise send 10^7 reductions at a few thousand addresses)
-  int e = 1;
-  if (lvl & 0x80) {
-    e = 1 << ((lvl & 7) - 1);
-    if (((bx | by | bz) & (e - 1)) != 0) return;
-  }
-  ActiveBox A;                                                             // as mrt_active_box, for this brick / cell
-  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + e) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
-  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + e) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
-  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + e) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
+  ActiveBox A;                                                             // as mrt_active_box, for this one brick
+  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
+  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
+  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + 1) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
   int2* sp = spans + (size_t)v * ty;
   float cx[8], cy[8];
   if (mrt_project_box(P, B.cam[v], A, cx, cy) != 0) {                      // behind the eye / degenerate basis: no culling
     for (int band = 0; band < ty; ++band) { atomicMin(&sp[band].x, 0); atomicMax(&sp[band].y, P.W - 1); }
     return;
   }
-  float ymin = cy[0], ymax = cy[0];
+  float ymin = cy[0], ymax = cy[0], xmin = cx[0], xmax = cx[0];
 #pragma unroll
-  for (int c = 1; c < 8; ++c) { ymin = fminf(ymin, cy[c]); ymax = fmaxf(ymax, cy[c]); }
+  for (int c = 1; c < 8; ++c) {
+    ymin = fminf(ymin, cy[c]); ymax = fmaxf(ymax, cy[c]); xmin = fminf(xmin, cx[c]); xmax = fmaxf(xmax, cx[c]);
+  }
   if (!(ymax >= -2.0f) || !(ymin <= (float)P.H + 1.0f)) return;            // off screen
-  const int b0 = max(0, ((int)floorf(fmaxf(ymin, -8.0f)) >> MRT_TILE_SHIFT) - 1);
-  const int b1 = min(ty - 1, ((int)ceilf(fminf(ymax, (float)P.H + 8.0f)) >> MRT_TILE_SHIFT) + 1);
+  // The brick contributes its bounding RECTANGLE to every band it touches: at the usual zoom (a brick = 3-5 tiles)
+  // that is at most a tile looser than the band's cut through the footprint's hull, for a tenth of the arithmetic and,
+  // above all, bounded work per thread: cutting hulls band by band — and merging all-active cells into one box, whose
+  // thread then walked 30+ bands alone — took 31-34 us per 8-view batch under ncu (5 % of the step).
+  const float lim = 1.0e8f;
+  const int rx0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), rx1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1);
+  if (rx0 > rx1) return;
+  // bands whose pixel rows, widened by one pixel like the x-extent, meet [ymin, ymax]
+  const int b0 = max(0, (int)floorf((fmaxf(ymin, -16.0f) - (float)MRT_TILE_EDGE) * (1.0f / MRT_TILE_EDGE)));
+  const int b1 = min(ty - 1, (int)floorf((fminf(ymax, (float)P.H + 16.0f) + 1.0f) * (1.0f / MRT_TILE_EDGE)));
   for (int band = b0; band <= b1; ++band) {
-    const int2 x = mrt_band_extent(P, cx, cy, band);
-    if (x.x > x.y) continue;
+    const int2 x = make_int2(rx0, rx1);
     // (a plain look first: a stale value is only ever LOOSER than the current one, so a reduction that could
     // matter is never skipped, and interior bricks stop hammering the same few words)
     const int2 cur = __ldcg(sp + band);

@@ -220,13 +220,10 @@ __device__ __forceinline__ bool mrt_ray_may_hit(const KParams& P, const float* _
   return tout >= fmaxf(tin, 0.0f);
 }
 
-// Screen footprint of a box of bricks for one camera, as one x-span per 8-pixel row band (tile row):
-// the 8 corners of the box widened by MRT_SPAN_MARGIN voxels (> MRT_BOX_MARGIN, so a ray the slab
-// test lets through always lies inside) are projected, and the convex hull's x-extent inside the
-// band is the extent of the 12 projected edges clipped to the band (the hull's boundary is made of
-// edges; the others lie inside), rounded outward by one pixel.  A view's spans are the union of
-// these over its active bricks (forward.cu: mrt_view_spans_kernel).  Deterministic in (P, cam, box).
-// Empty span: x0 > x1.
+// Screen footprint of a box of voxels for one camera: its 8 corners, widened by MRT_SPAN_MARGIN voxels
+// (> MRT_BOX_MARGIN, so a ray the slab test lets through always lies inside), in pixel coordinates.  A view's
+// spans — one x-extent per 8-pixel row band (tile row), empty: x0 > x1 — are the union over its active bricks of
+// these footprints' bounding rectangles, rounded outward by one pixel (forward.cu: mrt_view_spans_kernel).
 #define MRT_SPAN_MARGIN 0.75f
 // Projects the 8 corners of box A (widened to MRT_SPAN_MARGIN) to pixel coordinates.  Returns 0 = done,
 // 1 = no culling possible (degenerate basis, or the box reaches behind the eye), 2 = empty box.
@@ -265,33 +262,6 @@ __device__ __forceinline__ int mrt_project_box(const KParams& P, const float* __
     cx[c] = (uvx + 1.0f) * 0.5f * (float)P.W - 0.5f; cy[c] = (uvy + 1.0f) * 0.5f * (float)P.H - 0.5f;
   }
   return behind ? 1 : 0;                                                   // the box reaches behind the eye: everything
-}
-// x-extent of the projected box's convex hull inside row band `band` (rounded outward by one pixel); empty: x0 > x1
-__device__ __forceinline__ int2 mrt_band_extent(const KParams& P, const float cx[8], const float cy[8], int band) {
-  const float ylo = (float)(band << MRT_TILE_SHIFT) - 1.0f, yhi = (float)((band << MRT_TILE_SHIFT) + MRT_TILE_EDGE);
-  float xmin = 3.0e38f, xmax = -3.0e38f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (c & (1 << a)) continue;                                          // each edge once: c -> c | (1 << a)
-      const int d = c | (1 << a);
-      const float y0 = cy[c], y1 = cy[d], x0 = cx[c], x1 = cx[d];
-      if ((y0 < ylo && y1 < ylo) || (y0 > yhi && y1 > yhi)) continue;
-      const float dy = y1 - y0;
-      float t0 = 0.0f, t1 = 1.0f;
-      if (fabsf(dy) > 1e-12f) {
-        const float ta = (ylo - y0) / dy, tb = (yhi - y0) / dy;
-        t0 = fmaxf(0.0f, fminf(ta, tb)); t1 = fminf(1.0f, fmaxf(ta, tb));
-      }
-      const float xa = x0 + t0 * (x1 - x0), xb = x0 + t1 * (x1 - x0);
-      xmin = fminf(xmin, fminf(xa, xb)); xmax = fmaxf(xmax, fmaxf(xa, xb));
-    }
-  }
-  if (!(xmin <= xmax)) return make_int2(1, 0);
-  const float lim = 1.0e8f;
-  const int x0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), x1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1);
-  return make_int2(x0, x1);
 }
 // does the 8x8 tile with left pixel column tx0 intersect its row band's span?
 __device__ __forceinline__ bool mrt_tile_in_span(int2 sp, int tx0) {
