@@ -666,15 +666,15 @@ def run_ours(args):
             "partition": ("single GPU" if world == 1 else
                           f"image space, {fb.partition} (interleaved tile rows of every view per rank), volume replicated; frames "
                           f"owned {fb.owners} over the ranks and written by peer (NVLink) stores from inside the march kernel; tiles "
-                          "outside the projected active-brick box are not sent but filled by the owner"),
+                          "outside the projected footprints of the active bricks are not sent but filled by the owner"),
             "ms_per_step_median": med_ms, "value_at_median_step": taken / (med_ms * 1e-3), "step_ms": step_ms,
             "frames_per_sec": VT * args.steps / tot_s,
             "samples_per_step": {"nominal_taken": taken, "clip": clip, "evaluated": evaluated},
             "gathered_frames_verified": verified, "strong": strong, "graph_replay": graph_rec,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            # our kernels inside the timed region, whole job: per rank fold+occupancy, classify, spans, march
-            # (+ the owners' background fill at N > 1)
-            "gpu_launches": ((V if args.per_view else 1) + 3 + (1 if world > 1 else 0)) * world * args.steps,
+            # our kernels inside the timed region, whole job: per rank fold+occupancy, classify, spans (init + the
+            # per-brick union), march (+ the owners' background fill at N > 1)
+            "gpu_launches": ((V + 2 if args.per_view else 5) + (1 if world > 1 else 0)) * world * args.steps,
         }
     # ---- the other BASELINE configs (outside every timed region above), attached to the same line
     if not args.no_configs:
