@@ -479,6 +479,17 @@ mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__
   if (lvl != 0 && !(lvl & 0x80)) return;                                   // an empty brick: no slot in it is ever evaluated
   const int ty = mrt_tiles_y_(P.H);
   const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
+  // A brick whose six face neighbours are all active adds nothing to the union: a ray through it enters and leaves
+  // through a face (or an edge / corner, which the neighbours' boxes, widened by the margin, contain as well), i.e.
+  // through an active neighbour whose own footprint covers the pixel.  Only the surface bricks project — a third
+  // of the bench head's active bricks, a seventh of a solid 512^3 interior's.
+  if (bx > 0 && bx < P.nbx - 1 && by > 0 && by < P.nby - 1 && bz > 0 && bz < P.nbz - 1) {
+    const int sxy = P.nbx * P.nby;
+    const int l0 = __ldg(levels + b - 1), l1 = __ldg(levels + b + 1), l2 = __ldg(levels + b - P.nbx),
+              l3 = __ldg(levels + b + P.nbx), l4 = __ldg(levels + b - sxy), l5 = __ldg(levels + b + sxy);
+    const auto act = [](int l) { return l == 0 || (l & 0x80) != 0; };
+    if (act(l0) && act(l1) && act(l2) && act(l3) && act(l4) && act(l5)) return;
+  }
   ActiveBox A;                                                             // as mrt_active_box, for this one brick
   A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
   A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
