@@ -469,60 +469,91 @@ mrt_spans_init_kernel(int n, int2* __restrict__ spans) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) spans[i] = make_int2(0x7fffffff, -1);
 }
+// One thread per (brick, view).  The CTA's 128 consecutive bricks (four x-rows of the bench grid) touch nearly the
+// same bands, so their rectangles are first merged in shared memory (SMEM: one int2 per band) and every touched
+// band then costs the CTA one look and at most two reductions in global memory — the per-thread version sent a
+// hundred reductions at each of a view's 8 cache lines.  SMEM = false (more bands than fit): straight to global.
+template <bool SMEM>
 __global__ void __launch_bounds__(128)
 mrt_view_spans_kernel(const __grid_constant__ KParams P, const __grid_constant__ CamBatch B, int nviews,
                       const uint8_t* __restrict__ levels, int2* __restrict__ spans) {
+  extern __shared__ int2 s_sp[];                                           // [ty] when SMEM
   const int b = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   const int nb = P.nbx * P.nby * P.nbz;
-  if (b >= nb || v >= nviews) return;
-  const int lvl = __ldg(levels + b);
-  if (lvl != 0 && !(lvl & 0x80)) return;                                   // an empty brick: no slot in it is ever evaluated
   const int ty = mrt_tiles_y_(P.H);
-  const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
-  // A brick whose six face neighbours are all active adds nothing to the union: a ray through it enters and leaves
-  // through a face (or an edge / corner, which the neighbours' boxes, widened by the margin, contain as well), i.e.
-  // through an active neighbour whose own footprint covers the pixel.  Only the surface bricks project — a third
-  // of the bench head's active bricks, a seventh of a solid 512^3 interior's.
-  if (bx > 0 && bx < P.nbx - 1 && by > 0 && by < P.nby - 1 && bz > 0 && bz < P.nbz - 1) {
-    const int sxy = P.nbx * P.nby;
-    const int l0 = __ldg(levels + b - 1), l1 = __ldg(levels + b + 1), l2 = __ldg(levels + b - P.nbx),
-              l3 = __ldg(levels + b + P.nbx), l4 = __ldg(levels + b - sxy), l5 = __ldg(levels + b + sxy);
-    const auto act = [](int l) { return l == 0 || (l & 0x80) != 0; };
-    if (act(l0) && act(l1) && act(l2) && act(l3) && act(l4) && act(l5)) return;
-  }
-  ActiveBox A;                                                             // as mrt_active_box, for this one brick
-  A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
-  A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
-  A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + 1) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
+  if (v >= nviews) return;                                                 // (whole CTA)
   int2* sp = spans + (size_t)v * ty;
-  float cx[8], cy[8];
-  if (mrt_project_box(P, B.cam[v], A, cx, cy) != 0) {                      // behind the eye / degenerate basis: no culling
-    for (int band = 0; band < ty; ++band) { atomicMin(&sp[band].x, 0); atomicMax(&sp[band].y, P.W - 1); }
-    return;
+  if (SMEM) {
+    for (int i = threadIdx.x; i < ty; i += blockDim.x) s_sp[i] = make_int2(0x7fffffff, -1);
+    __syncthreads();
   }
-  float ymin = cy[0], ymax = cy[0], xmin = cx[0], xmax = cx[0];
+  int2* dst = SMEM ? s_sp : sp;
+  bool work = b < nb;
+  if (work) {
+    const int lvl = __ldg(levels + b);
+    work = lvl == 0 || (lvl & 0x80);                                       // an empty brick: no slot in it is ever evaluated
+  }
+  if (work) {
+    const int bx = b % P.nbx, by = (b / P.nbx) % P.nby, bz = b / (P.nbx * P.nby);
+    // A brick whose six face neighbours are all active adds nothing to the union: a ray through it enters and leaves
+    // through a face (or an edge / corner, which the neighbours' boxes, widened by the margin, contain as well), i.e.
+    // through an active neighbour whose own footprint covers the pixel.  Only the surface bricks project — a third
+    // of the bench head's active bricks, a seventh of a solid 512^3 interior's.
+    if (bx > 0 && bx < P.nbx - 1 && by > 0 && by < P.nby - 1 && bz > 0 && bz < P.nbz - 1) {
+      const int sxy = P.nbx * P.nby;
+      const int l0 = __ldg(levels + b - 1), l1 = __ldg(levels + b + 1), l2 = __ldg(levels + b - P.nbx),
+                l3 = __ldg(levels + b + P.nbx), l4 = __ldg(levels + b - sxy), l5 = __ldg(levels + b + sxy);
+      const auto act = [](int l) { return l == 0 || (l & 0x80) != 0; };
+      if (act(l0) && act(l1) && act(l2) && act(l3) && act(l4) && act(l5)) work = false;
+    }
+    if (work) {
+      ActiveBox A;                                                         // as mrt_active_box, for this one brick
+      A.lo[0] = (float)((bx << MRT_BRICK_SHIFT) + P.slo[0]) - MRT_BOX_MARGIN; A.hi[0] = (float)(((bx + 1) << MRT_BRICK_SHIFT) + P.slo[0]) + MRT_BOX_MARGIN;
+      A.lo[1] = (float)((by << MRT_BRICK_SHIFT) + P.slo[1]) - MRT_BOX_MARGIN; A.hi[1] = (float)(((by + 1) << MRT_BRICK_SHIFT) + P.slo[1]) + MRT_BOX_MARGIN;
+      A.lo[2] = (float)((bz << MRT_BRICK_SHIFT) + P.slo[2]) - MRT_BOX_MARGIN; A.hi[2] = (float)(((bz + 1) << MRT_BRICK_SHIFT) + P.slo[2]) + MRT_BOX_MARGIN;
+      float cx[8], cy[8];
+      int rx0 = 0, rx1 = P.W - 1, b0 = 0, b1 = ty - 1;                     // behind the eye / degenerate basis: no culling
+      if (mrt_project_box(P, B.cam[v], A, cx, cy) == 0) {
+        float ymin = cy[0], ymax = cy[0], xmin = cx[0], xmax = cx[0];
 #pragma unroll
-  for (int c = 1; c < 8; ++c) {
-    ymin = fminf(ymin, cy[c]); ymax = fmaxf(ymax, cy[c]); xmin = fminf(xmin, cx[c]); xmax = fmaxf(xmax, cx[c]);
+        for (int c = 1; c < 8; ++c) {
+          ymin = fminf(ymin, cy[c]); ymax = fmaxf(ymax, cy[c]); xmin = fminf(xmin, cx[c]); xmax = fmaxf(xmax, cx[c]);
+        }
+        // The brick contributes its bounding RECTANGLE to every band it touches: at the usual zoom (a brick = 3-5
+        // tiles) that is at most a tile looser than the band's cut through the footprint's hull, for a tenth of the
+        // arithmetic and, above all, bounded work per thread: cutting hulls band by band — and merging all-active
+        // cells into one box, whose thread then walked 30+ bands alone — took 31-34 us per 8-view batch under ncu.
+        const float lim = 1.0e8f;
+        rx0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1); rx1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1);
+        // bands whose pixel rows, widened by one pixel like the x-extent, meet [ymin, ymax]
+        b0 = max(0, (int)floorf((fmaxf(ymin, -16.0f) - (float)MRT_TILE_EDGE) * (1.0f / MRT_TILE_EDGE)));
+        b1 = min(ty - 1, (int)floorf((fminf(ymax, (float)P.H + 16.0f) + 1.0f) * (1.0f / MRT_TILE_EDGE)));
+        if (!(ymax >= -2.0f) || !(ymin <= (float)P.H + 1.0f)) b1 = b0 - 1;  // off screen
+      }
+      if (rx0 <= rx1) {
+        for (int band = b0; band <= b1; ++band) {
+          if (SMEM) {
+            atomicMin(&dst[band].x, rx0); atomicMax(&dst[band].y, rx1);
+          } else {
+            // (a plain look first: a stale value is only ever LOOSER than the current one, so a reduction that
+            // could matter is never skipped, and interior bricks stop hammering the same few words)
+            const int2 cur = __ldcg(sp + band);
+            if (rx0 < cur.x) atomicMin(&sp[band].x, rx0);
+            if (rx1 > cur.y) atomicMax(&sp[band].y, rx1);
+          }
+        }
+      }
+    }
   }
-  if (!(ymax >= -2.0f) || !(ymin <= (float)P.H + 1.0f)) return;            // off screen
-  // The brick contributes its bounding RECTANGLE to every band it touches: at the usual zoom (a brick = 3-5 tiles)
-  // that is at most a tile looser than the band's cut through the footprint's hull, for a tenth of the arithmetic and,
-  // above all, bounded work per thread: cutting hulls band by band — and merging all-active cells into one box, whose
-  // thread then walked 30+ bands alone — took 31-34 us per 8-view batch under ncu (5 % of the step).
-  const float lim = 1.0e8f;
-  const int rx0 = max(0, (int)floorf(fmaxf(xmin, -lim)) - 1), rx1 = min(P.W - 1, (int)ceilf(fminf(xmax, lim)) + 1);
-  if (rx0 > rx1) return;
-  // bands whose pixel rows, widened by one pixel like the x-extent, meet [ymin, ymax]
-  const int b0 = max(0, (int)floorf((fmaxf(ymin, -16.0f) - (float)MRT_TILE_EDGE) * (1.0f / MRT_TILE_EDGE)));
-  const int b1 = min(ty - 1, (int)floorf((fminf(ymax, (float)P.H + 16.0f) + 1.0f) * (1.0f / MRT_TILE_EDGE)));
-  for (int band = b0; band <= b1; ++band) {
-    const int2 x = make_int2(rx0, rx1);
-    // (a plain look first: a stale value is only ever LOOSER than the current one, so a reduction that could
-    // matter is never skipped, and interior bricks stop hammering the same few words)
-    const int2 cur = __ldcg(sp + band);
-    if (x.x < cur.x) atomicMin(&sp[band].x, x.x);
-    if (x.y > cur.y) atomicMax(&sp[band].y, x.y);
+  if (SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ty; i += blockDim.x) {
+      const int2 m = s_sp[i];
+      if (m.x > m.y) continue;
+      const int2 cur = __ldcg(sp + i);
+      if (m.x < cur.x) atomicMin(&sp[i].x, m.x);
+      if (m.y > cur.y) atomicMax(&sp[i].y, m.y);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
@@ -560,7 +591,9 @@ cudaError_t mrt_launch_view_spans(const KParams& P, const float* cams, int nview
     int2* sp = reinterpret_cast<int2*>(spans) + (size_t)v0 * ty;
     const int nb = P.nbx * P.nby * P.nbz;
     mrt_spans_init_kernel<<<(nv * ty + 127) / 128, 128, 0, st>>>(nv * ty, sp);
-    mrt_view_spans_kernel<<<dim3((nb + 127) / 128, nv), 128, 0, st>>>(P, B, nv, levels, sp);
+    const size_t smem = (size_t)ty * sizeof(int2);
+    if (smem <= 32 * 1024) mrt_view_spans_kernel<true><<<dim3((nb + 127) / 128, nv), 128, smem, st>>>(P, B, nv, levels, sp);
+    else mrt_view_spans_kernel<false><<<dim3((nb + 127) / 128, nv), 128, 0, st>>>(P, B, nv, levels, sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
