@@ -459,6 +459,14 @@ size_t mrt_train_step_workspace_bytes(const MrtParams* params, int32_t nviews, i
 int mrt_train_step_mse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                        const float* planar, int32_t C, const float* tf, int32_t tfN, const float* target_rgba,
                        void* workspace, float* out_rgba, float* loss, float* dL_dplanar, float* dL_dtf, void* stream);
+/* Diagnostics (tools/time_train_step.py; not thread-safe): mrt_debug_train_trace(NULL) arms a stage trace — the NEXT
+ * mrt_train_step_mse records a timing event on the caller's stream after every stage; mrt_debug_train_trace(ms)
+ * then synchronises and fills ms[6] with the device time of fold | classify | march | loss + wait for the adjoint
+ * (side stream) + dL/dtf reduce | fold adjoint | final join, as the caller's stream saw them.  Measurement knobs read
+ * once from the environment: MRT_TRAIN_NO_SIDE (everything on the caller's stream), MRT_TRAIN_NO_DIRECT (always
+ * through the fold adjoint), MRT_TRAIN_PARTS=n (split the image into n tile-range parts, part i differentiated
+ * while part i+1 marches: the measured loser). */
+int mrt_debug_train_trace(float* ms6);
 
 /* ------------------------------------------------ soft (learnable) occupancy
  * docs/DifferentiableRendering.md section 11 (:202-206; maths only, no reference code): "hard empty-space

@@ -127,6 +127,7 @@ PROTOTYPES = {
     "mrt_render_views_refold": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "mrt_render_views_refold_scatter": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "mrt_train_step_workspace_bytes": (_sz, [_PP, _i32, _i32]),
+    "mrt_debug_train_trace": (C.c_int, [_vp]),
     "mrt_train_step_mse": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mrt_render_forward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mrt_render_backward_soft_occ": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

@@ -781,7 +781,7 @@ static TrainSide* train_side() {
   return S;
 }
 #define MRT_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, "train_step_mse"); } while (0)
-// Stage trace for tools/ (not part of the ABI in mrt.h): when armed, the NEXT mrt_train_step_mse records a timing
+// Stage trace for tools/ (mrt.h, diagnostics): when armed, the NEXT mrt_train_step_mse records a timing
 // event on the caller's stream after every stage; mrt_debug_train_trace(ms[6]) synchronises and returns the
 // device time of fold | classify | march (all parts) | wait for the last adjoint + dL/dtf reduce | fold adjoint |
 // loss + final join, as seen by the caller's stream.

@@ -58,6 +58,14 @@ def test_host_side_helpers_need_no_gpu(built_lib):
         assert built_lib.mrt_packed_volume_bytes(Cn, 240, 240, 155) == pz.value * 155 * 4 * Cn
     assert built_lib.mrt_brick_count(240, 240, 155) == 30 * 30 * 20
     assert built_lib.mrt_packed_volume_bytes(5, 8, 8, 8) == 0
+    # workspace of the one-call training step: host arithmetic only, grows with the views, 0 for an invalid request
+    from mri_raytracer_b200 import RenderParams
+    P = RenderParams(imageSize=(64, 48), dims=(40, 36, 28), tfMode=1)
+    s = P.to_struct()
+    w1 = built_lib.mrt_train_step_workspace_bytes(C.byref(s), 1, 64)
+    w3 = built_lib.mrt_train_step_workspace_bytes(C.byref(s), 3, 64)
+    assert w1 > 2 * built_lib.mrt_packed_volume_bytes(1, 40, 36, 28) and w3 > w1 and w1 % 256 == 0
+    assert built_lib.mrt_train_step_workspace_bytes(C.byref(s), 0, 64) == 0
 
 
 def test_packed_params_equal_field_by_field_ctypes():

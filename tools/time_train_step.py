@@ -35,8 +35,6 @@ def main():
         ts(vol, tf, target)
     torch.cuda.synchronize()
     trace = lib().mrt_debug_train_trace
-    trace.restype = C.c_int
-    trace.argtypes = [C.c_void_p]
     rows = []
     for _ in range(5):
         trace(None)
