@@ -17,7 +17,7 @@
 //     (inr/viewer/brats_viewer.py:219-230 vs :405-426); a step's inputs are then cameras, params,
 //     modality weights and the TF;
 //   * frames come down SPARSE: only the tiles inside each view's spans — the screen footprint of
-//     the active-brick box, outside which every pixel is the background — cross PCIe.  When the
+//     the active bricks (mrt_view_spans), outside which every pixel is the background — cross PCIe.  When the
 //     output buffer is page-locked (hence device-mapped under UVA) the march kernel stores those
 //     tiles STRAIGHT into host memory, exactly as the multi-GPU path stores into a peer GPU: the
 //     transfer overlaps the march and there is no copy at all; otherwise each view's bounding

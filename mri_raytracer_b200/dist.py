@@ -114,7 +114,7 @@ class PeerFramebuffer:
     because every rank gets a slice of every view).  partition="views": rank r renders whole views
     ``[r*V/R, (r+1)*V/R)``.
 
-    Tiles outside a view's *spans* — per tile row the x-extent of the projected active-brick box, a
+    Tiles outside a view's *spans* — per tile row the x-extent of the union of the active bricks' projected footprints, a
     deterministic function of (camera, params, occupancy) that every rank computes for itself
     (``mrt_view_spans``) — are not sent; the owner fills them with the background on a side stream
     while everybody marches (``mrt_fill_outside_spans``; disjoint pixels, no ordering needed).
