@@ -526,6 +526,11 @@ def run_ours(args):
                         "launch time; `frac` is that over the HBM copy peak and is a reference line only. `value` counts the "
                         "oracle-defined (nominal) slots, which include slots skipped as provably empty: the evaluated rate is "
                         "evaluated_samples_per_sec. instr_per_slot = warp instructions per 32 evaluated lane-slots"}
+        if traffic:
+            # what really crosses the HBM interface (ncu dram__bytes of the same launch / this run's launch time): `frac`
+            # above can exceed 1 because the requested bytes are served from L1 (86 % hit) and L2, not from DRAM
+            roof["dram_gbs"] = float(traffic) / (avg_ms * 1e-3) / 1e9
+            roof["dram_frac"] = roof["dram_gbs"] / peak
 
     # ---- same-run gather ceilings: random 32-byte-sector gathers over an
     # L2-resident (32 MiB) and an HBM-resident (4 GiB) buffer, mrt_gather_probe
