@@ -456,8 +456,8 @@ int mrt_render_backward(const MrtParams* params, const MrtCamera* cams, int32_t 
  * `cams` NULL: one view with the camera in params.  Needs skipEmpty = 1, tMode = 0, gamma = 1, no overlays,
  * volDtype = 0, unsharded (MRT_ERR_UNSUPPORTED otherwise: use the separate calls).
  * The side stream and its events are one set per device: calls on the same device must be issued from one host
- * thread and are ordered among themselves like calls on one stream (each call joins the side stream before it
- * returns control of `stream`), whichever caller streams they use. */
+ * thread (their side work then runs in call order; each call joins the side stream before it returns control of
+ * `stream`).  Two workspaces may be in flight on two caller streams; one workspace belongs to one stream. */
 size_t mrt_train_step_workspace_bytes(const MrtParams* params, int32_t nviews, int32_t tfN);
 int mrt_train_step_mse(const MrtParams* params, const MrtCamera* cams, int32_t nviews,
                        const float* planar, int32_t C, const float* tf, int32_t tfN, const float* target_rgba,
