@@ -460,9 +460,9 @@ def run_ours(args):
                   "static_volume": {"what": "the same batch with the fold / occupancy / sampler layout cached (volume static, camera moving)",
                                     "ms_per_step_1gpu_same_run": m1s, "ms_per_step": mns, "speedup": m1s / mns,
                                     "efficiency": m1s / mns / world},
-                  "limiter": "the modality fold + occupancy + quad layout (one pass over the 143 MB planar volume, ~0.09 ms) and "
+                  "limiter": "the modality fold + occupancy + quad layout (one pass over the 143 MB planar volume, ~0.06 ms) and "
                              "classify + spans are replicated on every rank, plus one symmetric-memory barrier and ~6 launches; only "
-                             "the march (0.62 of 0.77 ms at N=1) divides by N.  Sharding the fold would need an all-gather of the "
+                             "the march (~0.56 of ~0.66 ms at N=1) divides by N.  Sharding the fold would need an all-gather of the "
                              "folded volume that costs as much as folding it locally"}
         del fbs
 
